@@ -1,0 +1,121 @@
+"""CPU: the oracle (numpy restatement) against fixtures frozen from the live reference
+(`oracle/make_golden.py`).  This is the pin that lets the GPU parity tests trust the oracle."""
+import numpy as np
+import pytest
+import torch
+
+import cova_b200.synth as synth
+from conftest import load_golden, rel_err
+from oracle import cova_oracle as O
+
+
+def np_sd(**cfg):
+    return {k: v.numpy() for k, v in synth.make_state_dict(123, **cfg).items()}
+
+
+def np_inp(*a, **k):
+    return [t.numpy() for t in synth.gen(*a, **k)]
+
+
+def test_state_dict_spec_matches_reference_keys():
+    for bk in ("resnet18", "resnet50"):
+        g = load_golden("state_dict_keys_" + bk)
+        spec = synth.state_dict_spec(backbone=bk)
+        assert [k for k, _ in spec] == list(g["keys"])
+        assert [str(tuple(s)) for _, s in spec] == list(g["shapes"])
+
+
+def test_full_forward_small_r18():
+    g = load_golden("g_small_r18_img128")
+    r = O.cova_forward(np_sd(), *np_inp(2, 12, 8, seed=0, img=128), return_intermediates=True)
+    assert rel_err(r["fm"], g["fm"]) < 2e-6
+    assert rel_err(r["visual"], g["visual"]) < 2e-6
+    assert rel_err(r["own"], g["own"]) < 2e-6
+    assert rel_err(r["ctx"], g["ctx"]) < 5e-6
+    assert rel_err(r["logits"], g["logits"]) < 5e-6
+
+
+def test_roi_pool_bit_exact_on_reference_fm():
+    """Given the reference's own feature map, RoIPool must reproduce its visual features exactly."""
+    g = load_golden("g_small_r18_img128")
+    _, bboxes, _, _ = np_inp(2, 12, 8, seed=0, img=128)
+    v = O.roi_pool(g["fm"], bboxes, (3, 3), 0.25).reshape(len(bboxes), -1)
+    assert np.array_equal(v, g["visual"])
+
+
+@pytest.mark.parametrize("P", [(1, 1), (3, 3), (7, 7), (2, 5)])
+def test_roi_pool_adversarial_boxes_bit_exact(P):
+    g = load_golden("g_roi")
+    out = O.roi_pool(g["fm"], g["boxes"], P, 0.25)
+    assert np.array_equal(out, g["pool_%dx%d" % P])
+
+
+@pytest.mark.parametrize("P", [(1, 1), (3, 3), (7, 7), (2, 5)])
+def test_roi_align_adversarial_boxes(P):
+    g = load_golden("g_roi")
+    out = O.roi_align(g["fm"], g["boxes"], P, 0.25, 2, False)
+    assert np.abs(out - g["align_%dx%d" % P]).max() < 2e-6
+
+
+def test_ragged_pages_and_c1_tail_from_reference_fm():
+    """Everything after the feature map, on ragged pages (11/1/30 boxes, K=24) and on BASELINE
+    config 1 (1280^2, N=32, K=8) - driven from the reference's `own` so no 1280^2 conv runs on CPU."""
+    for name, cfgen in (("g_ragged_r18_img256", dict(B=3, N=0, K=24, seed=3, img=256, counts=[11, 1, 30])),
+                        ("g_c1_r18_img1280", dict(B=1, N=32, K=8, seed=0, img=64))):
+        g = load_golden(name)
+        sd = np_sd()
+        ci = synth.gen(**cfgen)[3].numpy()
+        ctx, attn = O.gat(g["own"], ci, sd["gat.W_i.weight"], sd["gat.W_j.weight"],
+                          sd["gat.attention_layer.weight"], sd["gat.attention_layer.bias"], return_attn_wts=True)
+        assert rel_err(ctx, g["ctx"]) < 5e-6 and np.abs(attn - g["attn"]).max() < 2e-6
+        logits = O.decoder(np.concatenate([g["own"], ctx], 1), sd)
+        assert rel_err(logits, g["logits"]) < 5e-6
+
+
+def test_bbox_encoder():
+    g = load_golden("g_ragged_r18_img256")
+    bboxes = synth.gen(3, 0, 24, seed=3, img=256, counts=[11, 1, 30])[1].numpy()
+    assert rel_err(O.bbox_encoder(bboxes, np_sd()), g["bbox"]) < 2e-6
+
+
+def test_roi_align_variant_forward():
+    g = load_golden("g_align_r18_img256")
+    r = O.cova_forward(np_sd(), *np_inp(2, 20, 8, seed=4, img=256), roi_mode="align", return_intermediates=True)
+    assert rel_err(r["visual"], g["visual"]) < 5e-6
+    assert rel_err(r["logits"], g["logits"]) < 5e-6
+
+
+def test_resnet50_variant():
+    g = load_golden("g_r50_img128")
+    r = O.cova_forward(np_sd(backbone="resnet50"), *np_inp(1, 16, 8, seed=5, img=128), return_intermediates=True)
+    assert rel_err(r["fm"], g["fm"]) < 5e-6
+    assert rel_err(r["logits"], g["logits"]) < 1e-5
+
+
+def test_constructor_variants():
+    g = load_golden("g_noctx_nobbox_roi2x5")
+    sd = np_sd(roi_output_size=(2, 5), use_context=False, hidden_dim=0, bbox_hidden_dim=0)
+    images, bboxes, add, _ = np_inp(2, 9, 0, seed=6, img=128)
+    out = O.cova_forward(sd, images, bboxes, add, np.empty((18, 0), np.int64), roi_output_size=(2, 5))
+    assert rel_err(out, g["logits"]) < 5e-6
+    g = load_golden("g_addfeat7")
+    images, bboxes, _, ci = np_inp(2, 9, 8, seed=7, img=128)
+    out = O.cova_forward(np_sd(n_additional_feat=7), images, bboxes, g["additional_feats"], ci)
+    assert rel_err(out, g["logits"]) < 5e-6
+
+
+def test_gat_layer_edge_cases_and_heads():
+    g = load_golden("g_gat")
+    out, attn = O.gat(g["h"], g["ci"], g["W_i"], g["W_j"], g["att_w"], g["att_b"], return_attn_wts=True)
+    assert np.abs(out - g["out"]).max() < 2e-6 and np.abs(attn - g["attn"]).max() < 1e-6
+    assert np.all(out[3] == 0) and np.allclose(attn[3], 1.0 / g["ci"].shape[1])   # all -1 row
+    heads = [(g[f"h{i}_W_i"], g[f"h{i}_W_j"], g[f"h{i}_att_w"], g[f"h{i}_att_b"]) for i in range(2)]
+    assert np.abs(O.gat_multihead(g["h"], g["ci"], heads) - g["out_2head"]).max() < 2e-6
+
+
+def test_train_mode_forward():
+    g = load_golden("g_train_r18_img128")
+    images, bboxes, add, ci, labels = synth.gen(2, 12, 8, seed=8, img=128, with_labels=True)
+    out = O.cova_forward(np_sd(), images.numpy(), bboxes.numpy(), add.numpy(), ci.numpy(), train=True)
+    assert rel_err(out, g["logits"]) < 2e-5
+    assert np.array_equal(labels.numpy(), g["labels"])
