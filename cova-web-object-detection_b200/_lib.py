@@ -1,0 +1,92 @@
+"""Build + ctypes binding of ``libcova_b200.so`` (C ABI declared in ``include/cova_b200.h``).
+
+The library is built IN-TREE with nvcc for sm_100a only (it travels to the GPU box with the repo snapshot).
+There is no fallback: if the library is missing or fails to load, every op raises.
+"""
+import ctypes
+import glob
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_CSRC = os.path.join(_HERE, "csrc")
+LIB_PATH = os.path.join(_HERE, "libcova_b200.so")
+HEADER = os.path.join(os.path.dirname(_HERE), "include", "cova_b200.h")
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+    "-Xcompiler", "-fPIC", "-shared", "--cudart", "static",
+]
+
+F32, BF16, BF16X2 = 0, 1, 2
+ENGINE_SIMT, ENGINE_TCGEN05 = 0, 1
+
+
+def sources():
+    return sorted(glob.glob(os.path.join(_CSRC, "*.cu")))
+
+
+def _stale():
+    if not os.path.exists(LIB_PATH):
+        return True
+    t = os.path.getmtime(LIB_PATH)
+    deps = sources() + glob.glob(os.path.join(_CSRC, "*.cuh")) + [HEADER]
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force=False, verbose=False):
+    """Compile every ``csrc/*.cu`` into ``libcova_b200.so`` (nvcc cross-compiles without a GPU)."""
+    if not force and not _stale():
+        return LIB_PATH
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + sources()
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + r.stdout + r.stderr)
+    if verbose:
+        print(r.stderr)
+    return LIB_PATH
+
+
+_c = ctypes
+_P, _I, _L, _F = _c.c_void_p, _c.c_int, _c.c_int64, _c.c_float
+
+# name -> (restype, argtypes); must list every symbol include/cova_b200.h declares
+SIGNATURES = {
+    "cova_abi_version": (_I, []),
+    "cova_last_error": (_c.c_char_p, []),
+    "cova_device_info": (_I, [_c.POINTER(_I), _c.POINTER(_I)]),
+    "cova_stem_fwd": (_I, [_P, _I, _I, _I, _P, _P, _P, _I, _P, _P, _I, _P]),
+    "cova_conv3x3_bn_act_fwd": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _I, _I, _P, _P, _I, _P]),
+    "cova_pack_conv_weight": (_I, [_P, _I, _I, _I, _I, _P, _P, _P, _P]),
+    "cova_roi_fwd": (_I, [_P, _I, _I, _I, _I, _P, _I, _I, _I, _F, _I, _I, _P, _L, _P, _P]),
+    "cova_bbox_enc_fwd": (_I, [_P, _I, _P, _P, _P, _P, _I, _P, _L, _P]),
+    "cova_affine_cols_fwd": (_I, [_P, _I, _I, _L, _P, _P, _P, _L, _P]),
+    "cova_linear_fwd": (_I, [_P, _L, _I, _I, _P, _I, _P, _P, _P, _P, _L, _I, _P, _L, _I, _P]),
+    "cova_gat_fwd": (_I, [_P, _L, _P, _P, _L, _F, _F, _P, _I, _I, _I, _P, _L, _P, _P]),
+}
+
+_lib = None
+
+
+def lib():
+    """The loaded library.  Raises (never falls back) if it is absent or its ABI version is wrong."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing - run `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(cova_b200 has no CPU or PyTorch fallback for its hot path)")
+        h = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(h, name)
+            fn.restype, fn.argtypes = res, args
+        if h.cova_abi_version() != 1:
+            raise RuntimeError("libcova_b200.so ABI version mismatch")
+        _lib = h
+    return _lib
+
+
+def check(rc, what):
+    if rc != 0:
+        raise RuntimeError(f"{what} failed (code {rc}): {lib().cova_last_error().decode()}")

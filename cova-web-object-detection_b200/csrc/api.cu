@@ -1,0 +1,65 @@
+// extern "C" entry points that dispatch between the engines (include/cova_b200.h).
+#include "common.cuh"
+
+namespace cova {
+int stem_simt(const float* images, int B, int H, int W, const float* w, const float* bn_scale, const float* bn_shift,
+              int out_dtype, void* out0, void* out1, cudaStream_t st);
+int conv3x3_simt(const float* x, int B, int H, int W, const float* w, const float* bn_scale, const float* bn_shift,
+                 const float* res, int relu, float* y, cudaStream_t st);
+int conv3x3_tc(const void* x_hi, const void* x_lo, int split, int B, int H, int W, const void* w_hi, const void* w_lo,
+               const float* bn_scale, const float* bn_shift, const void* res_hi, const void* res_lo, int relu,
+               int out_dtype, void* y0, void* y1, cudaStream_t st);
+int linear_simt(const float* x, int64_t ld_x, int M, int K, const float* w, int N, const float* bias,
+                const float* scale, const float* shift, const float* res, int64_t ld_res, int relu, float* y,
+                int64_t ld_y, cudaStream_t st);
+}  // namespace cova
+
+using namespace cova;
+
+static bool dtype_ok(int d) { return d == COVA_F32 || d == COVA_BF16 || d == COVA_BF16X2; }
+
+extern "C" int cova_stem_fwd(const float* images, int B, int H, int W, const float* w, const float* bn_scale,
+                             const float* bn_shift, int out_dtype, void* out0, void* out1, int engine, void* stream) {
+  COVA_REQUIRE(images && w && bn_scale && bn_shift && out0, "cova_stem_fwd: null pointer");
+  COVA_REQUIRE(B > 0 && H >= 7 && W >= 7, "cova_stem_fwd: bad dims B=%d H=%d W=%d", B, H, W);
+  COVA_REQUIRE(dtype_ok(out_dtype), "cova_stem_fwd: bad out_dtype %d", out_dtype);
+  COVA_REQUIRE(out_dtype != COVA_BF16X2 || out1, "cova_stem_fwd: BF16X2 output needs the lo plane");
+  COVA_REQUIRE(engine == COVA_ENGINE_SIMT || engine == COVA_ENGINE_TCGEN05, "cova_stem_fwd: bad engine");
+  // the tensor-core stem is not built yet: both engines run the fused CUDA-core kernel
+  return stem_simt(images, B, H, W, w, bn_scale, bn_shift, out_dtype, out0, out1, (cudaStream_t)stream);
+}
+
+extern "C" int cova_conv3x3_bn_act_fwd(const void* x0, const void* x1, int dtype, int B, int H, int W, int Cin, int Cout,
+                                       const void* w_a, const void* w_b, const float* bn_scale, const float* bn_shift,
+                                       const void* res0, const void* res1, int relu, int out_dtype, void* y0, void* y1,
+                                       int engine, void* stream) {
+  COVA_REQUIRE(x0 && w_a && bn_scale && bn_shift && y0, "cova_conv3x3_bn_act_fwd: null pointer");
+  COVA_REQUIRE(B > 0 && H > 0 && W > 0, "cova_conv3x3_bn_act_fwd: bad dims");
+  COVA_REQUIRE(Cin == 64 && Cout == 64, "cova_conv3x3_bn_act_fwd: only Cin=Cout=64 is built (got %d->%d)", Cin, Cout);
+  COVA_REQUIRE(dtype_ok(dtype) && dtype_ok(out_dtype), "cova_conv3x3_bn_act_fwd: bad dtype");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (engine == COVA_ENGINE_SIMT) {
+    COVA_REQUIRE(dtype == COVA_F32 && out_dtype == COVA_F32, "cova_conv3x3_bn_act_fwd: the SIMT engine is fp32 in/out");
+    return conv3x3_simt((const float*)x0, B, H, W, (const float*)w_a, bn_scale, bn_shift, (const float*)res0, relu,
+                        (float*)y0, st);
+  }
+  COVA_REQUIRE(engine == COVA_ENGINE_TCGEN05, "cova_conv3x3_bn_act_fwd: bad engine %d", engine);
+  COVA_REQUIRE(dtype == COVA_BF16 || dtype == COVA_BF16X2, "cova_conv3x3_bn_act_fwd: tcgen05 engine takes bf16 planes");
+  const int split = dtype == COVA_BF16X2;
+  COVA_REQUIRE(!split || (x1 && w_b), "cova_conv3x3_bn_act_fwd: BF16X2 needs lo planes for x and w");
+  COVA_REQUIRE(!split || !res0 || res1, "cova_conv3x3_bn_act_fwd: BF16X2 residual needs its lo plane");
+  COVA_REQUIRE(out_dtype != COVA_BF16X2 || y1, "cova_conv3x3_bn_act_fwd: BF16X2 output needs the lo plane");
+  return conv3x3_tc(x0, x1, split, B, H, W, w_a, w_b, bn_scale, bn_shift, res0, res1, relu, out_dtype, y0, y1, st);
+}
+
+extern "C" int cova_linear_fwd(const float* x, int64_t ld_x, int M, int K, const float* w, int N, const float* bias,
+                               const float* scale, const float* shift, const float* res, int64_t ld_res, int relu,
+                               float* y, int64_t ld_y, int engine, void* stream) {
+  COVA_REQUIRE(M >= 0 && K > 0 && N > 0, "cova_linear_fwd: bad dims");
+  if (M == 0) return COVA_OK;
+  COVA_REQUIRE(x && w && y && ld_x >= K && ld_y >= N, "cova_linear_fwd: bad arguments");
+  COVA_REQUIRE((scale == nullptr) == (shift == nullptr), "cova_linear_fwd: scale/shift must come together");
+  COVA_REQUIRE(engine == COVA_ENGINE_SIMT || engine == COVA_ENGINE_TCGEN05, "cova_linear_fwd: bad engine");
+  COVA_REQUIRE(!res || ld_res >= N, "cova_linear_fwd: ld_res too small");
+  return linear_simt(x, ld_x, M, K, w, N, bias, scale, shift, res, ld_res, relu, y, ld_y, (cudaStream_t)stream);
+}

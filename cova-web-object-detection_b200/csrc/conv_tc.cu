@@ -1,0 +1,331 @@
+// A2 BasicBlock half on the 5th-gen tensor cores: 3x3 s1 p1 conv (64->64) as an implicit GEMM with
+// tcgen05.mma (accumulators in TMEM), operands staged by TMA, + folded BN (+ residual) (+ ReLU) epilogue.
+// Replaces `convnet.4.{b}.conv{1,2}` + `bn{1,2}` (torchvision BasicBlock.forward via
+// `/root/reference/models.py:49-51`).
+//
+// GEMM view per output tile (8 wide x 16 high = 128 pixels = UMMA M):
+//     D[128 px, 64 cout] = sum over 9 taps (r,s):  A_rs[128 px, 64 cin] * W_rs[64 cin, 64 cout]
+// Activations are NHWC bf16 planes, so a pixel's 64 input channels are exactly one 128-byte swizzle row and
+// "im2col" is nothing but a shifted TMA box: for horizontal tap s one 4-D box {64 c, 8 w, 18 h} at
+// (w0+s-1, h0-1) lands in shared memory as 144 rows x 128 B; the three vertical taps r are the 1024-B-aligned
+// sub-views [r*8, r*8+128) of those rows (r*1024 bytes = one swizzle atom per 8 rows), so one load feeds three
+// taps.  Conv zero padding = TMA out-of-bounds zero fill.  L2->smem traffic is 3*144/128 = 3.4x the tile
+// (a per-tap load would be 9x); HBM traffic stays 1x because neighbouring tiles share halos through L2.
+//
+// fp32-parity mode (SPLIT): x = hi + lo (two bf16 planes), w = hi + lo; D = Ahi*Whi + Alo*Whi + Ahi*Wlo with
+// fp32 accumulation in TMEM: ~2^-17 relative per product, i.e. an fp32 convolution to ~1e-5, at 3 MMAs
+// per term.  Plain bf16 mode issues the first product only.
+//
+// Persistent CTAs (grid = #SMs, 1 CTA/SM, 192 threads):
+//   warp 0   TMA producer: all 9 filter taps once (resident, 72 KB per plane), then the activation ring
+//   warp 1   TMEM alloc + single-thread tcgen05.mma issue; tcgen05.commit releases ring slots / publishes tiles
+//   warps 2-5 epilogue: tcgen05.ld (lane = pixel, column = cout), BN scale/shift, residual, ReLU, NHWC stores
+// TMEM accumulator is double-buffered (2 x 64 columns): the epilogue of tile i overlaps the MMAs of tile i+1.
+//
+// Bound: tensor pipe in SPLIT mode (108 MMAs x 32 clk = 3456 clk/tile), HBM in bf16 mode.
+// Algorithmic work: 2*9*64*64 = 73,728 FLOP per output pixel (7.55 GFLOP per 320x320 page).
+#include "common.cuh"
+#include "ptx.cuh"
+#include "tma_host.cuh"
+
+namespace cova {
+
+constexpr int CT_C = 64;                       // Cin = Cout
+constexpr int CT_TW = 8, CT_TH = 16;           // output tile
+constexpr int CT_HALO_ROWS = (CT_TH + 2) * CT_TW;          // 144 smem rows per load
+constexpr int CT_PLANE_BYTES = CT_HALO_ROWS * 128;         // 18,432
+constexpr int CT_W_PLANE_BYTES = 9 * CT_C * 128;           // 73,728 (9 taps x 64 cout rows x 128 B)
+constexpr int CT_THREADS = 192;
+constexpr int CT_TMEM_COLS = 128;              // 2 accumulator buffers x 64 fp32 columns
+
+template <bool SPLIT>
+struct ConvTcCfg {
+  static constexpr int NPLANE = SPLIT ? 2 : 1;
+  static constexpr int NSTAGE = SPLIT ? 2 : 6;
+  static constexpr int STAGE_BYTES = CT_PLANE_BYTES * NPLANE;
+  static constexpr int W_BYTES = CT_W_PLANE_BYTES * NPLANE;
+  static constexpr int SMEM_BYTES = W_BYTES + NSTAGE * STAGE_BYTES + 1024 /*tail*/ + 1024 /*align slack*/;
+};
+
+struct ConvTcTail {   // lives after the operand buffers
+  float scale[CT_C], shift[CT_C];
+  uint64_t full[8], empty[8], tmem_full[2], tmem_empty[2], wbar;
+  uint32_t tmem_base;
+};
+
+struct ConvTcParams {
+  int B, H, W, tiles_w, tiles_h, n_tiles, relu;
+  const float* bn_scale;
+  const float* bn_shift;
+  const __nv_bfloat16* res_hi;
+  const __nv_bfloat16* res_lo;
+  void* y0;
+  void* y1;
+};
+
+template <bool SPLIT, int OUT_DTYPE>
+__global__ void __launch_bounds__(CT_THREADS, 1)
+conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ CUtensorMap tm_x_lo,
+                  const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo,
+                  const ConvTcParams p) {
+  using Cfg = ConvTcCfg<SPLIT>;
+  extern __shared__ unsigned char smem_raw[];
+  const uint32_t raw_addr = ptx::smem_u32(smem_raw);
+  unsigned char* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);   // 1024-B aligned (swizzle atoms)
+  unsigned char* sm_w = smem;
+  unsigned char* sm_a = smem + Cfg::W_BYTES;
+  ConvTcTail& tail = *reinterpret_cast<ConvTcTail*>(smem + Cfg::W_BYTES + Cfg::NSTAGE * Cfg::STAGE_BYTES);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x < CT_C) {
+    tail.scale[threadIdx.x] = p.bn_scale[threadIdx.x];
+    tail.shift[threadIdx.x] = p.bn_shift[threadIdx.x];
+  }
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < Cfg::NSTAGE; ++i) {
+      ptx::mbar_init(&tail.full[i], 1);
+      ptx::mbar_init(&tail.empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(&tail.tmem_full[i], 1);
+      ptx::mbar_init(&tail.tmem_empty[i], 128);
+    }
+    ptx::mbar_init(&tail.wbar, 1);
+    ptx::fence_barrier_init();
+    ptx::prefetch_tensormap(&tm_x_hi);
+    ptx::prefetch_tensormap(&tm_w_hi);
+    if (SPLIT) {
+      ptx::prefetch_tensormap(&tm_x_lo);
+      ptx::prefetch_tensormap(&tm_w_lo);
+    }
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(&tail.tmem_base, CT_TMEM_COLS);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = tail.tmem_base;
+
+  if (warp == 0) {
+    // ======================= TMA producer =======================
+    if (lane == 0) {
+      // resident filter: 9 taps x 64 rows per plane, three 192-row boxes each
+      ptx::mbar_arrive_expect_tx(&tail.wbar, Cfg::W_BYTES);
+      for (int i = 0; i < 3; ++i) {
+        ptx::tma_load_2d(sm_w + i * 192 * 128, &tm_w_hi, &tail.wbar, 0, i * 192);
+        if (SPLIT) ptx::tma_load_2d(sm_w + CT_W_PLANE_BYTES + i * 192 * 128, &tm_w_lo, &tail.wbar, 0, i * 192);
+      }
+      uint32_t stage = 0, phase = 0;
+      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+        const int b = tile / (p.tiles_h * p.tiles_w);
+        const int th = (tile / p.tiles_w) % p.tiles_h, tw = tile % p.tiles_w;
+        const int h0 = th * CT_TH, w0 = tw * CT_TW;
+        for (int s = 0; s < 3; ++s) {
+          ptx::mbar_wait(&tail.empty[stage], phase ^ 1);
+          ptx::mbar_arrive_expect_tx(&tail.full[stage], Cfg::STAGE_BYTES);
+          unsigned char* dst = sm_a + stage * Cfg::STAGE_BYTES;
+          ptx::tma_load_4d(dst, &tm_x_hi, &tail.full[stage], 0, w0 + s - 1, h0 - 1, b);
+          if (SPLIT) ptx::tma_load_4d(dst + CT_PLANE_BYTES, &tm_x_lo, &tail.full[stage], 0, w0 + s - 1, h0 - 1, b);
+          if (++stage == Cfg::NSTAGE) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ======================= MMA issuer (one thread) =======================
+    if (lane == 0) {
+      constexpr uint32_t idesc = ptx::umma_idesc_bf16(128, CT_C);
+      const uint32_t w_addr = ptx::smem_u32(sm_w), a_addr = ptx::smem_u32(sm_a);
+      ptx::mbar_wait(&tail.wbar, 0);
+      uint32_t stage = 0, phase = 0, it = 0;
+      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
+        const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
+        ptx::mbar_wait(&tail.tmem_empty[acc], acc_phase ^ 1);
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * CT_C;
+        uint32_t accumulate = 0;
+        for (int s = 0; s < 3; ++s) {
+          ptx::mbar_wait(&tail.full[stage], phase);
+          ptx::tc_fence_after();
+          const uint32_t a_hi = a_addr + stage * Cfg::STAGE_BYTES;
+#pragma unroll
+          for (int r = 0; r < 3; ++r) {
+            const uint32_t w_hi = w_addr + (r * 3 + s) * (CT_C * 128);
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {   // 4 x K=16 bf16 (32 B) inside the 128-B swizzle row
+              const uint64_t da_hi = ptx::umma_desc_sw128(a_hi + r * 1024 + kk * 32, 1024);
+              const uint64_t db_hi = ptx::umma_desc_sw128(w_hi + kk * 32, 1024);
+              ptx::umma_bf16(d_tmem, da_hi, db_hi, idesc, accumulate);
+              accumulate = 1;
+              if (SPLIT) {
+                const uint64_t da_lo = ptx::umma_desc_sw128(a_hi + CT_PLANE_BYTES + r * 1024 + kk * 32, 1024);
+                const uint64_t db_lo = ptx::umma_desc_sw128(w_hi + CT_W_PLANE_BYTES + kk * 32, 1024);
+                ptx::umma_bf16(d_tmem, da_lo, db_hi, idesc, 1);
+                ptx::umma_bf16(d_tmem, da_hi, db_lo, idesc, 1);
+              }
+            }
+          }
+          ptx::umma_commit(&tail.empty[stage]);          // ring slot free once these MMAs have read it
+          if (s == 2) ptx::umma_commit(&tail.tmem_full[acc]);   // accumulator complete
+          if (++stage == Cfg::NSTAGE) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else {
+    // ======================= epilogue warps (TMEM lane group = warp % 4) =======================
+    const int lg = warp & 3;
+    const int m = lg * 32 + lane;                 // accumulator row = pixel within the tile
+    const int py = m >> 3, px = m & 7;
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
+      const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
+      const int b = tile / (p.tiles_h * p.tiles_w);
+      const int th = (tile / p.tiles_w) % p.tiles_h, tw = tile % p.tiles_w;
+      const int oh = th * CT_TH + py, ow = tw * CT_TW + px;
+      const bool inb = oh < p.H && ow < p.W;
+      const size_t pix = ((size_t)b * p.H + oh) * p.W + ow;
+
+      // residual prefetch (independent of the accumulator)
+      uint4 rh[8], rl[8];
+      const bool has_res = p.res_hi != nullptr;
+      if (has_res && inb) {
+        const uint4* ph = reinterpret_cast<const uint4*>(p.res_hi + pix * CT_C);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) rh[j] = __ldg(ph + j);
+        if (SPLIT) {
+          const uint4* pl = reinterpret_cast<const uint4*>(p.res_lo + pix * CT_C);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) rl[j] = __ldg(pl + j);
+        }
+      }
+
+      ptx::mbar_wait(&tail.tmem_full[acc], acc_phase);
+      ptx::tc_fence_after();
+      uint32_t v[4][16];
+      const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + acc * CT_C;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) ptx::tmem_ld16(taddr + q * 16, v[q]);
+      ptx::tmem_ld_wait();
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(&tail.tmem_empty[acc]);     // accumulator buffer is free for tile it+2
+
+      if (!inb) continue;
+      float o[64];
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int c = q * 16 + j;
+          o[c] = fmaf(__uint_as_float(v[q][j]), tail.scale[c], tail.shift[c]);
+        }
+      if (has_res) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const uint32_t wh[4] = {rh[j].x, rh[j].y, rh[j].z, rh[j].w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            o[j * 8 + 2 * e] += bf16lo_to_f32(wh[e]);
+            o[j * 8 + 2 * e + 1] += bf16hi_to_f32(wh[e]);
+          }
+          if (SPLIT) {
+            const uint32_t wl[4] = {rl[j].x, rl[j].y, rl[j].z, rl[j].w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              o[j * 8 + 2 * e] += bf16lo_to_f32(wl[e]);
+              o[j * 8 + 2 * e + 1] += bf16hi_to_f32(wl[e]);
+            }
+          }
+        }
+      }
+      if (p.relu) {
+#pragma unroll
+        for (int c = 0; c < 64; ++c) o[c] = fmaxf(o[c], 0.f);
+      }
+      if (OUT_DTYPE == COVA_F32) {
+        float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.y0) + pix * CT_C);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) dst[j] = make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+      } else {
+        uint4* dh = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.y0) + pix * CT_C);
+        uint4* dl = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.y1) + pix * CT_C);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          uint32_t hw[4], lw[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            __nv_bfloat16 h0, l0, h1, l1;
+            split_bf16(o[j * 8 + 2 * e], h0, l0);
+            split_bf16(o[j * 8 + 2 * e + 1], h1, l1);
+            hw[e] = pack_bf16x2(h0, h1);
+            lw[e] = pack_bf16x2(l0, l1);
+          }
+          dh[j] = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+          if (OUT_DTYPE == COVA_BF16X2) dl[j] = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+        }
+      }
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, CT_TMEM_COLS);
+  }
+}
+
+template <bool SPLIT, int OUT_DTYPE>
+static int launch_conv_tc(const CUtensorMap& xh, const CUtensorMap& xl, const CUtensorMap& wh, const CUtensorMap& wl,
+                          const ConvTcParams& p, cudaStream_t st) {
+  using Cfg = ConvTcCfg<SPLIT>;
+  static_assert(sizeof(ConvTcTail) <= 1024, "tail too large");
+  auto kern = conv3x3_tc_kernel<SPLIT, OUT_DTYPE>;
+  COVA_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+  const int grid = p.n_tiles < sm_count() ? p.n_tiles : sm_count();
+  kern<<<grid, CT_THREADS, Cfg::SMEM_BYTES, st>>>(xh, xl, wh, wl, p);
+  COVA_LAUNCH_OK();
+  return COVA_OK;
+}
+
+int conv3x3_tc(const void* x_hi, const void* x_lo, int split, int B, int H, int W, const void* w_hi, const void* w_lo,
+               const float* bn_scale, const float* bn_shift, const void* res_hi, const void* res_lo, int relu,
+               int out_dtype, void* y0, void* y1, cudaStream_t st) {
+  CUtensorMap tx_hi, tx_lo, tw_hi, tw_lo;
+  const uint64_t xd[4] = {(uint64_t)CT_C, (uint64_t)W, (uint64_t)H, (uint64_t)B};
+  const uint64_t xs[3] = {(uint64_t)CT_C * 2, (uint64_t)W * CT_C * 2, (uint64_t)H * W * CT_C * 2};
+  const uint32_t xb[4] = {CT_C, CT_TW, CT_TH + 2, 1};
+  const uint64_t wd[2] = {(uint64_t)CT_C, (uint64_t)9 * CT_C};
+  const uint64_t ws[1] = {(uint64_t)CT_C * 2};
+  const uint32_t wb[2] = {CT_C, 192};
+  int rc;
+  if ((rc = make_tmap_bf16(&tx_hi, x_hi, 4, xd, xs, xb))) return rc;
+  if ((rc = make_tmap_bf16(&tw_hi, w_hi, 2, wd, ws, wb))) return rc;
+  tx_lo = tx_hi;
+  tw_lo = tw_hi;
+  if (split) {
+    if ((rc = make_tmap_bf16(&tx_lo, x_lo, 4, xd, xs, xb))) return rc;
+    if ((rc = make_tmap_bf16(&tw_lo, w_lo, 2, wd, ws, wb))) return rc;
+  }
+  ConvTcParams p;
+  p.B = B; p.H = H; p.W = W;
+  p.tiles_w = ceil_div(W, CT_TW);
+  p.tiles_h = ceil_div(H, CT_TH);
+  p.n_tiles = B * p.tiles_w * p.tiles_h;
+  p.relu = relu;
+  p.bn_scale = bn_scale; p.bn_shift = bn_shift;
+  p.res_hi = (const __nv_bfloat16*)res_hi;
+  p.res_lo = (const __nv_bfloat16*)res_lo;
+  p.y0 = y0; p.y1 = y1;
+#define DISPATCH(SP)                                                                               \
+  switch (out_dtype) {                                                                             \
+    case COVA_F32: return launch_conv_tc<SP, COVA_F32>(tx_hi, tx_lo, tw_hi, tw_lo, p, st);         \
+    case COVA_BF16: return launch_conv_tc<SP, COVA_BF16>(tx_hi, tx_lo, tw_hi, tw_lo, p, st);       \
+    default: return launch_conv_tc<SP, COVA_BF16X2>(tx_hi, tx_lo, tw_hi, tw_lo, p, st);            \
+  }
+  if (split) { DISPATCH(true) } else { DISPATCH(false) }
+#undef DISPATCH
+}
+
+}  // namespace cova

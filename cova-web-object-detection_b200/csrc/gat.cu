@@ -1,0 +1,171 @@
+// A6: fused graph-attention gather.  Replaces `GraphAttentionLayer.forward` lines 180-208 of
+// `/root/reference/models.py` after the once-per-node projections (whj = W_j h, s = a_i.W_i h, t = a_j.W_j h;
+// SURVEY.md row A6 - algebraically identical to the as-written layer, which re-projects every neighbour K
+// times and materialises [T,K,F], [T,K,H] x2 and [T,K,2H] intermediates).
+//
+// One CTA = GAT_E consecutive elements, one warp per element:
+//   1. lanes read the element's K neighbour ids; block-reduce the CTA's [min,max] id range
+//   2. if that range fits the staging buffer, ONE elected thread TMA-bulk-copies rows [min,max] of whj into
+//      shared memory (neighbour windows of consecutive elements overlap almost entirely: reuse E*K/(E+K));
+//      otherwise rows are gathered straight from L2
+//   3. logits e_k = LeakyReLU(s_i + t_c(k) + b), mask, softmax over K with warp shuffles
+//   4. out_i = sum_k alpha_k * whj[c(k)], float4 per lane across the hidden dim
+// HBM-bound; algorithmic bytes = T*K*Hd*4 read + T*Hd*4 written; real DRAM traffic is
+// ~T*Hd*4*(1+K/E) because of the staging (and whj sits in L2 straight out of the projection GEMM).
+#include <float.h>
+#include <limits.h>
+
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace cova {
+
+constexpr int GAT_E = 8;                 // elements (= warps) per CTA
+constexpr int GAT_THREADS = GAT_E * 32;
+constexpr int GAT_KMAX = 128;            // neighbours per element handled by one warp (4 per lane)
+constexpr int GAT_STAGE_BYTES = 96 * 1024;
+
+__global__ void __launch_bounds__(GAT_THREADS)
+gat_fwd_kernel(const float* __restrict__ whj, int64_t ld_whj, const float* __restrict__ s_vec,
+               const float* __restrict__ t_vec, int64_t ld_st, float att_b, float alpha, const int64_t* __restrict__ ctx, int T,
+               int K, int Hd, float* __restrict__ out, int64_t ld_out, float* __restrict__ attn, int stage_ok) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float* stage = reinterpret_cast<float*>(smem_raw);
+  __shared__ uint64_t bar;
+  __shared__ int s_min[GAT_E], s_max[GAT_E];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int i = blockIdx.x * GAT_E + warp;
+  const bool live = i < T;
+
+  // neighbour ids (4 per lane, k = lane + 32*j) and this warp's id range
+  int cid[GAT_KMAX / 32];
+  int lo = INT_MAX, hi = -1;
+#pragma unroll
+  for (int j = 0; j < GAT_KMAX / 32; ++j) {
+    const int k = lane + 32 * j;
+    int c = -1;
+    if (live && k < K) c = (int)ctx[(size_t)i * K + k];
+    cid[j] = c;
+    if (c >= 0) { lo = min(lo, c); hi = max(hi, c); }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+    hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+  }
+  if (lane == 0) { s_min[warp] = lo; s_max[warp] = hi; }
+  if (threadIdx.x == 0) {
+    ptx::mbar_init(&bar, 1);
+    ptx::fence_barrier_init();
+  }
+  __syncthreads();
+  int cmin = INT_MAX, cmax = -1;
+#pragma unroll
+  for (int w = 0; w < GAT_E; ++w) { cmin = min(cmin, s_min[w]); cmax = max(cmax, s_max[w]); }
+  const int nrows = cmax >= cmin ? cmax - cmin + 1 : 0;
+  const bool staged = stage_ok && nrows > 0 && (size_t)nrows * Hd * 4 <= (size_t)GAT_STAGE_BYTES;
+  if (staged && threadIdx.x == 0) {
+    const uint32_t row_bytes = (uint32_t)Hd * 4u;
+    ptx::mbar_arrive_expect_tx(&bar, row_bytes * (uint32_t)nrows);
+    if (ld_whj == Hd) {
+      ptx::tma_bulk_g2s(stage, whj + (size_t)cmin * ld_whj, row_bytes * (uint32_t)nrows, &bar);
+    } else {
+      for (int r = 0; r < nrows; ++r)
+        ptx::tma_bulk_g2s(stage + (size_t)r * Hd, whj + (size_t)(cmin + r) * ld_whj, row_bytes, &bar);
+    }
+  }
+
+  // attention logits + softmax over K (overlaps the bulk copy)
+  const float si = live ? s_vec[(size_t)i * ld_st] : 0.f;
+  float e[GAT_KMAX / 32];
+  float mx = -FLT_MAX;
+#pragma unroll
+  for (int j = 0; j < GAT_KMAX / 32; ++j) {
+    const int k = lane + 32 * j;
+    float v = -FLT_MAX;                    // k >= K: not part of the softmax
+    if (live && k < K) {
+      if (cid[j] >= 0) {
+        v = si + __ldg(t_vec + (size_t)cid[j] * ld_st) + att_b;
+        v = v > 0.f ? v : alpha * v;       // LeakyReLU (models.py:200)
+      } else {
+        v = -9e15f;                        // models.py:202-203
+      }
+    }
+    e[j] = v;
+    mx = fmaxf(mx, v);
+  }
+  mx = warp_max(mx);
+  float sum = 0.f;
+#pragma unroll
+  for (int j = 0; j < GAT_KMAX / 32; ++j) {
+    const int k = lane + 32 * j;
+    e[j] = (live && k < K) ? expf(e[j] - mx) : 0.f;
+    sum += e[j];
+  }
+  sum = warp_sum(sum);
+  const float inv = 1.f / sum;
+#pragma unroll
+  for (int j = 0; j < GAT_KMAX / 32; ++j) {
+    e[j] *= inv;
+    const int k = lane + 32 * j;
+    if (attn != nullptr && live && k < K) attn[(size_t)i * K + k] = e[j];
+  }
+
+  if (staged) ptx::mbar_wait(&bar, 0);
+  if (!live) return;
+
+  // weighted sum of neighbour rows; lane covers float4 columns lane, lane+32, ...
+  const int nvec = Hd >> 2;
+  for (int v0 = 0; v0 < nvec; v0 += 128) {     // up to 4 float4 per lane per pass
+    float4 acc[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) acc[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int j = 0; j < GAT_KMAX / 32; ++j) {
+      if (32 * j >= K) break;
+      const int kend = min(32, K - 32 * j);
+      for (int kk = 0; kk < kend; ++kk) {
+        const int c = __shfl_sync(0xffffffffu, cid[j], kk);
+        const float a = __shfl_sync(0xffffffffu, e[j], kk);
+        if (c < 0) continue;                  // zero row of models.py:180-184: contributes exactly 0
+        const float4* row = staged ? reinterpret_cast<const float4*>(stage + (size_t)(c - cmin) * Hd)
+                                   : reinterpret_cast<const float4*>(whj + (size_t)c * ld_whj);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int v = v0 + lane + 32 * q;
+          if (v < nvec) {
+            const float4 x = staged ? row[v] : __ldg(row + v);
+            acc[q].x = fmaf(a, x.x, acc[q].x); acc[q].y = fmaf(a, x.y, acc[q].y);
+            acc[q].z = fmaf(a, x.z, acc[q].z); acc[q].w = fmaf(a, x.w, acc[q].w);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int v = v0 + lane + 32 * q;
+      if (v < nvec) *reinterpret_cast<float4*>(out + (size_t)i * ld_out + 4 * v) = acc[q];
+    }
+  }
+}
+
+}  // namespace cova
+
+extern "C" int cova_gat_fwd(const float* whj, int64_t ld_whj, const float* s, const float* t, int64_t ld_st, float att_b,
+                            float alpha, const int64_t* ctx_idx, int T, int K, int Hd, float* out, int64_t ld_out,
+                            float* attn, void* stream) {
+  using namespace cova;
+  COVA_REQUIRE(T >= 0 && K >= 0 && Hd > 0, "cova_gat_fwd: bad dims");
+  if (T == 0) return COVA_OK;
+  COVA_REQUIRE(whj && s && t && out && (ctx_idx || K == 0), "cova_gat_fwd: null pointer");
+  COVA_REQUIRE(ld_st >= 1, "cova_gat_fwd: ld_st must be >= 1");
+  COVA_REQUIRE(K >= 1 && K <= GAT_KMAX, "cova_gat_fwd: K=%d outside [1,%d]", K, GAT_KMAX);
+  COVA_REQUIRE(Hd % 4 == 0 && ld_whj % 4 == 0 && ld_out % 4 == 0 && ld_whj >= Hd && ld_out >= Hd,
+               "cova_gat_fwd: Hd/ld must be multiples of 4 (float4 rows)");
+  COVA_REQUIRE(((uintptr_t)whj & 15) == 0 && ((uintptr_t)out & 15) == 0, "cova_gat_fwd: whj/out must be 16-byte aligned");
+  COVA_CUDA_OK(cudaFuncSetAttribute(gat_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GAT_STAGE_BYTES));
+  gat_fwd_kernel<<<ceil_div(T, GAT_E), GAT_THREADS, GAT_STAGE_BYTES, (cudaStream_t)stream>>>(
+      whj, ld_whj, s, t, ld_st, att_b, alpha, ctx_idx, T, K, Hd, out, ld_out, attn, 1);
+  COVA_LAUNCH_OK();
+  return COVA_OK;
+}

@@ -1,0 +1,303 @@
+// A4 / A4' / A5: RoIPool (bit-exact), RoIAlign and the positional encoder, writing straight into the
+// `own` feature row so the concat of `/root/reference/models.py:110` costs no pass of its own.
+//
+// Replaces `torchvision.ops.RoIPool(P, scale)` (`models.py:58`, applied `:125-127`), the D1 variant
+// `RoIAlign(P, scale, sampling_ratio, aligned=False)`, and `_get_bbox_features` + `bbox_feat_encoder`
+// (`models.py:129-148`, `:65-70`).  Feature map is NHWC fp32: a pixel's 64 channels are 256 contiguous
+// bytes, a crop row is one contiguous run, so every warp load is a full 512 B (two pixels x 16 lanes x 16 B).
+//
+// HBM-bound: algorithmic bytes per box = crop_h*crop_w*C*4 read + C*P*P*4 written.
+#include <float.h>
+#include <math.h>
+
+#include "common.cuh"
+
+namespace cova {
+
+constexpr int ROI_THREADS = 256;
+constexpr int ROI_WARPS = ROI_THREADS / 32;
+constexpr int ROI_CB = 64;   // channels per CTA (grid.y walks channel blocks)
+
+struct RoiGeom {
+  int b, sw, sh, rw, rh;
+  float bin_h, bin_w;
+};
+
+// box edge quantisation of torchvision's roi_pool kernel: C round() of the fp32 product
+__device__ __forceinline__ RoiGeom roi_geom(const float* __restrict__ roi, float scale, int PH, int PW) {
+  RoiGeom g;
+  g.b = (int)roi[0];
+  g.sw = (int)roundf(roi[1] * scale);
+  g.sh = (int)roundf(roi[2] * scale);
+  const int ew = (int)roundf(roi[3] * scale), eh = (int)roundf(roi[4] * scale);
+  g.rw = max(ew - g.sw + 1, 1);
+  g.rh = max(eh - g.sh + 1, 1);
+  g.bin_h = (float)g.rh / (float)PH;
+  g.bin_w = (float)g.rw / (float)PW;
+  return g;
+}
+__device__ __forceinline__ int bin_lo(int p, float bin, int start, int limit) {
+  return min(max((int)floorf((float)p * bin) + start, 0), limit);
+}
+__device__ __forceinline__ int bin_hi(int p, float bin, int start, int limit) {
+  return min(max((int)ceilf((float)(p + 1) * bin) + start, 0), limit);
+}
+
+// One CTA = one box x one 64-channel block.  Warps take crop rows round-robin; per row a warp walks the
+// PW column segments, two pixels per load (half-warp each, float4 per lane), and folds each segment's
+// max into its private smem accumulators for the (<=2) row bins the row belongs to.
+template <bool WITH_ARGMAX>
+__global__ void __launch_bounds__(ROI_THREADS)
+roi_pool_kernel(const float* __restrict__ fm, int Hf, int Wf, int C, const float* __restrict__ rois, int PH,
+                int PW, float scale, float* __restrict__ out, int64_t ld_out, int32_t* __restrict__ argmax) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int nbins = PH * PW;
+  float* acc = reinterpret_cast<float*>(smem_raw);                         // [warp][bin][64]
+  int* acc_i = reinterpret_cast<int*>(acc + ROI_WARPS * nbins * ROI_CB);   // same shape, only WITH_ARGMAX
+  const int t = blockIdx.x, cb = blockIdx.y * ROI_CB;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int half = lane >> 4, c4 = (lane & 15) * 4;
+  const RoiGeom g = roi_geom(rois + (size_t)t * 5, scale, PH, PW);
+
+  for (int i = threadIdx.x; i < ROI_WARPS * nbins * ROI_CB; i += ROI_THREADS) {
+    acc[i] = -FLT_MAX;
+    if (WITH_ARGMAX) acc_i[i] = -1;
+  }
+  __syncthreads();
+
+  const int h_lo = bin_lo(0, g.bin_h, g.sh, Hf), h_hi = bin_hi(PH - 1, g.bin_h, g.sh, Hf);
+  const float* base = fm + (size_t)g.b * Hf * Wf * C + cb;
+  float* wacc = acc + warp * nbins * ROI_CB;
+  int* wacc_i = acc_i + warp * nbins * ROI_CB;
+
+  for (int h = h_lo + warp; h < h_hi; h += ROI_WARPS) {
+    const float* row = base + (size_t)h * Wf * C;
+    for (int pw = 0; pw < PW; ++pw) {
+      const int ws = bin_lo(pw, g.bin_w, g.sw, Wf), we = bin_hi(pw, g.bin_w, g.sw, Wf);
+      if (we <= ws) continue;
+      float4 m = make_float4(-FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX);
+      int4 mi = make_int4(-1, -1, -1, -1);
+      int w = ws + half;
+#pragma unroll 4
+      for (; w < we; w += 2) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(row + (size_t)w * C + c4));
+        if (WITH_ARGMAX) {
+          const int idx = h * Wf + w;   // ascending per lane, so strict '>' keeps the first maximum
+          if (v.x > m.x) { m.x = v.x; mi.x = idx; }
+          if (v.y > m.y) { m.y = v.y; mi.y = idx; }
+          if (v.z > m.z) { m.z = v.z; mi.z = idx; }
+          if (v.w > m.w) { m.w = v.w; mi.w = idx; }
+        } else {
+          m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
+        }
+      }
+      // merge the two half-warps (odd/even pixels)
+      float4 o;
+      o.x = __shfl_xor_sync(0xffffffffu, m.x, 16); o.y = __shfl_xor_sync(0xffffffffu, m.y, 16);
+      o.z = __shfl_xor_sync(0xffffffffu, m.z, 16); o.w = __shfl_xor_sync(0xffffffffu, m.w, 16);
+      if (WITH_ARGMAX) {
+        int4 oi;
+        oi.x = __shfl_xor_sync(0xffffffffu, mi.x, 16); oi.y = __shfl_xor_sync(0xffffffffu, mi.y, 16);
+        oi.z = __shfl_xor_sync(0xffffffffu, mi.z, 16); oi.w = __shfl_xor_sync(0xffffffffu, mi.w, 16);
+#define MERGE(f)                                                                  \
+  if (oi.f >= 0 && (mi.f < 0 || o.f > m.f || (o.f == m.f && oi.f < mi.f))) {      \
+    m.f = o.f;                                                                    \
+    mi.f = oi.f;                                                                  \
+  }
+        MERGE(x) MERGE(y) MERGE(z) MERGE(w)
+#undef MERGE
+      } else {
+        m.x = fmaxf(m.x, o.x); m.y = fmaxf(m.y, o.y); m.z = fmaxf(m.z, o.z); m.w = fmaxf(m.w, o.w);
+      }
+      if (half == 0) {
+        for (int ph = 0; ph < PH; ++ph) {   // rows belong to at most two adjacent row bins
+          if (h < bin_lo(ph, g.bin_h, g.sh, Hf) || h >= bin_hi(ph, g.bin_h, g.sh, Hf)) continue;
+          float4* a = reinterpret_cast<float4*>(wacc + (ph * PW + pw) * ROI_CB + c4);
+          float4 cur = *a;
+          if (WITH_ARGMAX) {
+            int4* ai = reinterpret_cast<int4*>(wacc_i + (ph * PW + pw) * ROI_CB + c4);
+            int4 ci = *ai;
+#define FOLD(f)                                                                       \
+  if (mi.f >= 0 && (ci.f < 0 || m.f > cur.f || (m.f == cur.f && mi.f < ci.f))) {      \
+    cur.f = m.f;                                                                      \
+    ci.f = mi.f;                                                                      \
+  }
+            FOLD(x) FOLD(y) FOLD(z) FOLD(w)
+#undef FOLD
+            *ai = ci;
+          } else {
+            cur.x = fmaxf(cur.x, m.x); cur.y = fmaxf(cur.y, m.y); cur.z = fmaxf(cur.z, m.z); cur.w = fmaxf(cur.w, m.w);
+          }
+          *a = cur;
+        }
+      }
+    }
+  }
+  __syncthreads();
+
+  // cross-warp reduce; output index = c*PH*PW + bin  (the `.view(T, C*P*P)` order of models.py:125-127)
+  for (int o = threadIdx.x; o < ROI_CB * nbins; o += ROI_THREADS) {
+    const int c = o / nbins, bin = o % nbins;
+    const int ph = bin / PW, pw = bin % PW;
+    const bool empty = bin_hi(ph, g.bin_h, g.sh, Hf) <= bin_lo(ph, g.bin_h, g.sh, Hf) ||
+                       bin_hi(pw, g.bin_w, g.sw, Wf) <= bin_lo(pw, g.bin_w, g.sw, Wf);
+    float m = -FLT_MAX;
+    int mi = -1;
+    for (int w = 0; w < ROI_WARPS; ++w) {
+      const float v = acc[(w * nbins + bin) * ROI_CB + c];
+      if (WITH_ARGMAX) {
+        const int vi = acc_i[(w * nbins + bin) * ROI_CB + c];
+        if (vi >= 0 && (mi < 0 || v > m || (v == m && vi < mi))) { m = v; mi = vi; }
+      } else {
+        m = fmaxf(m, v);
+      }
+    }
+    if (empty) { m = 0.f; mi = -1; }
+    out[(size_t)t * ld_out + (size_t)(cb + c) * nbins + bin] = m;
+    if (WITH_ARGMAX) argmax[((size_t)t * C + cb + c) * nbins + bin] = mi;
+  }
+}
+
+// torchvision roi_align bilinear sample (clamp-to-edge, zero outside [-1, size])
+__device__ __forceinline__ float4 bilinear4(const float* __restrict__ base, int Hf, int Wf, int C, float y, float x) {
+  if (y < -1.0f || y > (float)Hf || x < -1.0f || x > (float)Wf) return make_float4(0.f, 0.f, 0.f, 0.f);
+  y = fmaxf(y, 0.f);
+  x = fmaxf(x, 0.f);
+  int yl = (int)y, xl = (int)x, yh, xh;
+  if (yl >= Hf - 1) { yh = yl = Hf - 1; y = (float)yl; } else { yh = yl + 1; }
+  if (xl >= Wf - 1) { xh = xl = Wf - 1; x = (float)xl; } else { xh = xl + 1; }
+  const float ly = y - (float)yl, lx = x - (float)xl, hy = 1.f - ly, hx = 1.f - lx;
+  const float w1 = hy * hx, w2 = hy * lx, w3 = ly * hx, w4 = ly * lx;
+  const float4 a = __ldg(reinterpret_cast<const float4*>(base + ((size_t)yl * Wf + xl) * C));
+  const float4 b = __ldg(reinterpret_cast<const float4*>(base + ((size_t)yl * Wf + xh) * C));
+  const float4 c = __ldg(reinterpret_cast<const float4*>(base + ((size_t)yh * Wf + xl) * C));
+  const float4 d = __ldg(reinterpret_cast<const float4*>(base + ((size_t)yh * Wf + xh) * C));
+  float4 r;   // same association order as torchvision: w1*v1 + w2*v2 + w3*v3 + w4*v4
+  r.x = w1 * a.x + w2 * b.x + w3 * c.x + w4 * d.x;
+  r.y = w1 * a.y + w2 * b.y + w3 * c.y + w4 * d.y;
+  r.z = w1 * a.z + w2 * b.z + w3 * c.z + w4 * d.z;
+  r.w = w1 * a.w + w2 * b.w + w3 * c.w + w4 * d.w;
+  return r;
+}
+
+// One CTA = one box; 16 lanes x float4 = one 64-channel block of one bin; items (bin, channel block) are
+// spread over the 16 half-warps of the CTA.
+__global__ void __launch_bounds__(ROI_THREADS)
+roi_align_kernel(const float* __restrict__ fm, int Hf, int Wf, int C, const float* __restrict__ rois, int PH,
+                 int PW, float scale, int sampling_ratio, float* __restrict__ out, int64_t ld_out) {
+  const int t = blockIdx.x;
+  const float* roi = rois + (size_t)t * 5;
+  const int b = (int)roi[0];
+  const float x1 = roi[1] * scale, y1 = roi[2] * scale, x2 = roi[3] * scale, y2 = roi[4] * scale;
+  const float rw = fmaxf(x2 - x1, 1.f), rh = fmaxf(y2 - y1, 1.f);
+  const float bh = rh / (float)PH, bw = rw / (float)PW;
+  const int gh = sampling_ratio > 0 ? sampling_ratio : (int)ceilf(rh / (float)PH);
+  const int gw = sampling_ratio > 0 ? sampling_ratio : (int)ceilf(rw / (float)PW);
+  const float cnt = (float)max(gh * gw, 1);
+  const int nbins = PH * PW, ncb = C / ROI_CB;
+  const int hw = threadIdx.x >> 4, c4 = (threadIdx.x & 15) * 4;
+  const float* base = fm + (size_t)b * Hf * Wf * C;
+  for (int item = hw; item < nbins * ncb; item += ROI_THREADS / 16) {
+    const int bin = item % nbins, cb = (item / nbins) * ROI_CB;
+    const int ph = bin / PW, pw = bin % PW;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int iy = 0; iy < gh; ++iy) {
+      const float y = y1 + (float)ph * bh + ((float)iy + 0.5f) * bh / (float)gh;
+      for (int ix = 0; ix < gw; ++ix) {
+        const float x = x1 + (float)pw * bw + ((float)ix + 0.5f) * bw / (float)gw;
+        const float4 v = bilinear4(base + cb + c4, Hf, Wf, C, y, x);
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+      }
+    }
+    float* o = out + (size_t)t * ld_out + (size_t)(cb + c4) * nbins + bin;
+    o[0] = acc.x / cnt;
+    o[nbins] = acc.y / cnt;
+    o[2 * nbins] = acc.z / cnt;
+    o[3 * nbins] = acc.w / cnt;
+  }
+}
+
+// [x1,y1,w,h,w/h] -> Linear(5,D) -> folded BN1d -> ReLU; one thread per (box, d)
+__global__ void bbox_enc_kernel(const float* __restrict__ rois, int T, const float* __restrict__ w,
+                                const float* __restrict__ bias, const float* __restrict__ scale,
+                                const float* __restrict__ shift, int D, float* __restrict__ out, int64_t ld_out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= T * D) return;
+  const int t = i / D, d = i % D;
+  const float* r = rois + (size_t)t * 5;
+  const float x = r[1], y = r[2], bw = r[3] - r[1], bh = r[4] - r[2];
+  const float f[5] = {x, y, bw, bh, bw / bh};   // models.py:134-142 (h == 0 -> inf/NaN, as the reference)
+  float acc = 0.f;                              // fp32 dot in index order, then + bias (nn.Linear)
+#pragma unroll
+  for (int k = 0; k < 5; ++k) acc = fmaf(f[k], w[d * 5 + k], acc);
+  acc += bias[d];
+  if (scale) acc = fmaf(acc, scale[d], shift[d]);
+  out[(size_t)t * ld_out + d] = fmaxf(acc, 0.f);
+}
+
+__global__ void affine_cols_kernel(const float* __restrict__ x, int T, int D, int64_t ld_x,
+                                   const float* __restrict__ scale, const float* __restrict__ shift,
+                                   float* __restrict__ out, int64_t ld_out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= T * D) return;
+  const int t = i / D, d = i % D;
+  float v = x[(size_t)t * ld_x + d];
+  if (scale) v = fmaf(v, scale[d], shift[d]);
+  out[(size_t)t * ld_out + d] = v;
+}
+
+}  // namespace cova
+
+extern "C" int cova_roi_fwd(const float* fm, int B, int Hf, int Wf, int C, const float* rois, int T, int PH, int PW,
+                            float spatial_scale, int mode, int sampling_ratio, float* out, int64_t ld_out,
+                            int32_t* argmax, void* stream) {
+  using namespace cova;
+  COVA_REQUIRE(fm && rois && out, "cova_roi_fwd: null pointer");
+  COVA_REQUIRE(B > 0 && Hf > 0 && Wf > 0 && PH > 0 && PW > 0 && T >= 0, "cova_roi_fwd: bad dims");
+  COVA_REQUIRE(C % ROI_CB == 0, "cova_roi_fwd: C=%d must be a multiple of %d", C, ROI_CB);
+  COVA_REQUIRE(ld_out >= (int64_t)C * PH * PW, "cova_roi_fwd: ld_out too small");
+  COVA_REQUIRE(mode == 0 || mode == 1, "cova_roi_fwd: mode must be 0 (pool) or 1 (align)");
+  if (T == 0) return COVA_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (mode == 1) {
+    COVA_REQUIRE(argmax == nullptr, "cova_roi_fwd: RoIAlign has no argmax");
+    roi_align_kernel<<<T, ROI_THREADS, 0, st>>>(fm, Hf, Wf, C, rois, PH, PW, spatial_scale, sampling_ratio, out, ld_out);
+  } else {
+    const size_t one = (size_t)ROI_WARPS * PH * PW * ROI_CB * 4;
+    const size_t smem = argmax ? 2 * one : one;
+    COVA_REQUIRE(smem <= (size_t)max_smem_optin(), "cova_roi_fwd: P=%dx%d needs %zu B of shared memory", PH, PW, smem);
+    dim3 grid(T, C / ROI_CB);
+    if (argmax) {
+      COVA_CUDA_OK(cudaFuncSetAttribute(roi_pool_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      roi_pool_kernel<true><<<grid, ROI_THREADS, smem, st>>>(fm, Hf, Wf, C, rois, PH, PW, spatial_scale, out, ld_out, argmax);
+    } else {
+      COVA_CUDA_OK(cudaFuncSetAttribute(roi_pool_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      roi_pool_kernel<false><<<grid, ROI_THREADS, smem, st>>>(fm, Hf, Wf, C, rois, PH, PW, spatial_scale, out, ld_out, argmax);
+    }
+  }
+  COVA_LAUNCH_OK();
+  return COVA_OK;
+}
+
+extern "C" int cova_bbox_enc_fwd(const float* rois, int T, const float* w, const float* b, const float* bn_scale,
+                                 const float* bn_shift, int D, float* out, int64_t ld_out, void* stream) {
+  COVA_REQUIRE(rois && w && b && out && D > 0 && T >= 0 && ld_out >= D, "cova_bbox_enc_fwd: bad arguments");
+  COVA_REQUIRE((bn_scale == nullptr) == (bn_shift == nullptr), "cova_bbox_enc_fwd: scale/shift must come together");
+  if (T == 0) return COVA_OK;
+  cova::bbox_enc_kernel<<<cova::ceil_div(T * D, 256), 256, 0, (cudaStream_t)stream>>>(rois, T, w, b, bn_scale, bn_shift,
+                                                                                   D, out, ld_out);
+  COVA_LAUNCH_OK();
+  return COVA_OK;
+}
+
+extern "C" int cova_affine_cols_fwd(const float* x, int T, int D, int64_t ld_x, const float* scale, const float* shift,
+                                    float* out, int64_t ld_out, void* stream) {
+  COVA_REQUIRE(T >= 0 && D >= 0, "cova_affine_cols_fwd: bad dims");
+  if (T == 0 || D == 0) return COVA_OK;
+  COVA_REQUIRE(x && out && ld_x >= D && ld_out >= D, "cova_affine_cols_fwd: bad arguments");
+  COVA_REQUIRE((scale == nullptr) == (shift == nullptr), "cova_affine_cols_fwd: scale/shift must come together");
+  cova::affine_cols_kernel<<<cova::ceil_div(T * D, 256), 256, 0, (cudaStream_t)stream>>>(x, T, D, ld_x, scale, shift, out,
+                                                                                     ld_out);
+  COVA_LAUNCH_OK();
+  return COVA_OK;
+}

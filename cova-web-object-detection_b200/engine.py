@@ -1,0 +1,179 @@
+"""Native (libcova_b200.so) inference forward of the CoVA hot path.
+
+Owns the derived weight caches the kernels need - folded eval-mode BatchNorm (scale/shift), repacked /
+split-bf16 convolution filters, the extended GAT projection matrix - and rebuilds them whenever a parameter
+or buffer of the model changed (``optimizer.step()``, ``load_state_dict`` bump ``Tensor._version``).
+The fp32 ``nn.Parameter``s in PyTorch layout stay the single source of truth.
+
+Stage order = ``CoVA.forward`` (`/root/reference/models.py:94-122`):
+  stem -> BasicBlock x2 (or Bottleneck x3) -> RoIPool/RoIAlign + positional encoder + additional feats written
+  straight into one [T, n_feat + hidden] row buffer (the two `torch.cat`s of `:110` / `:119` never run)
+  -> GAT projection GEMM -> fused gather/softmax/weighted-sum -> decoder GEMM + BN + ReLU -> logits GEMM.
+"""
+import torch
+
+from . import ops
+from .ops import BF16, BF16X2, ENGINE_SIMT, ENGINE_TCGEN05, F32
+
+
+def fold_bn(bn):
+    """Eval-mode BatchNorm as y = x*scale + shift (eps from the module)."""
+    scale = bn.weight.detach() / torch.sqrt(bn.running_var.detach() + bn.eps)
+    shift = bn.bias.detach() - bn.running_mean.detach() * scale
+    return scale.float().contiguous(), shift.float().contiguous()
+
+
+class NativeForward:
+    def __init__(self, model):
+        self.m = model
+        self._key = None
+        self.c = {}
+
+    # ------------------------------------------------------------------ caches
+    def _state_key(self):
+        m = self.m
+        return (m.engine, m.precision) + tuple((t.data_ptr(), t._version) for t in
+                                               list(m.parameters()) + list(m.buffers()))
+
+    def prepare(self):
+        key = self._state_key()
+        if key == self._key:
+            return
+        m, c = self.m, {}
+        tc = m.engine == "tcgen05" and m.backbone == "resnet18"
+        split = m.precision == "fp32"
+        c["tc"] = tc
+        c["act_dtype"] = (BF16X2 if split else BF16) if tc else F32
+        cn = m.convnet
+        c["stem_w"] = cn[0].weight.detach().float().contiguous()
+        c["stem_bn"] = fold_bn(cn[1])
+        blocks = []
+        for blk in cn[4]:
+            d = {}
+            if m.backbone == "resnet18":
+                for i in (1, 2):
+                    conv, bn = getattr(blk, f"conv{i}"), getattr(blk, f"bn{i}")
+                    s, hi, lo = ops.pack_conv_weight(conv.weight.detach().float(), simt=not tc, tc=tc, split=split)
+                    d[f"w{i}"] = (hi, lo) if tc else (s, None)
+                    d[f"bn{i}"] = fold_bn(bn)
+            else:  # Bottleneck: 1x1 convs are row-major GEMMs on NHWC, 3x3 on the CUDA-core engine
+                d["w1"] = blk.conv1.weight.detach().float().flatten(1).contiguous()
+                d["w2"] = ops.pack_conv_weight(blk.conv2.weight.detach().float(), simt=True, tc=False)[0]
+                d["w3"] = blk.conv3.weight.detach().float().flatten(1).contiguous()
+                for i in (1, 2, 3):
+                    d[f"bn{i}"] = fold_bn(getattr(blk, f"bn{i}"))
+                if blk.downsample is not None:
+                    d["wd"] = blk.downsample[0].weight.detach().float().flatten(1).contiguous()
+                    d["bnd"] = fold_bn(blk.downsample[1])
+            blocks.append(d)
+        c["blocks"] = blocks
+        if m.bbox_hidden_dim > 0:
+            enc = m.bbox_feat_encoder
+            c["bbox"] = (enc[0].weight.detach().float().contiguous(), enc[0].bias.detach().float().contiguous(),
+                         *fold_bn(enc[1]))
+        if m.n_additional_feat > 0:
+            c["add_bn"] = fold_bn(m.bn_additional_feat)
+        if m.use_context:
+            c["gat"] = [self._gat_cache(h) for h in m.gat_heads()]
+        dec = m.decoder
+        c["dec1"] = (dec[1].weight.detach().float().contiguous(), dec[1].bias.detach().float().contiguous(),
+                     *fold_bn(dec[2]))
+        c["dec2"] = (dec[5].weight.detach().float().contiguous(), dec[5].bias.detach().float().contiguous())
+        self.c, self._key = c, key
+
+    @staticmethod
+    def _gat_cache(layer):
+        """[W_j ; a_i^T W_i ; a_j^T W_j ; 0 ; 0]: one GEMM yields whj, s and t."""
+        Hd = layer.hidden_dim
+        Wi, Wj = layer.W_i.weight.detach().float(), layer.W_j.weight.detach().float()
+        a = layer.attention_layer.weight.detach().float()[0]
+        ext = torch.zeros((Hd + 4, Wj.shape[1]), dtype=torch.float32, device=Wj.device)
+        ext[:Hd] = Wj
+        ext[Hd] = a[:Hd] @ Wi
+        ext[Hd + 1] = a[Hd:] @ Wj
+        return dict(ext=ext.contiguous(), Hd=Hd, b=float(layer.attention_layer.bias.detach().float().item()),
+                    alpha=float(layer.leakyrelu.negative_slope))
+
+    # ------------------------------------------------------------------ stages
+    def _eng(self):
+        return ENGINE_TCGEN05 if self.c["tc"] else ENGINE_SIMT
+
+    def feature_map(self, images):
+        """A2: [B,3,H,W] fp32 NCHW -> fp32 NHWC feature map [B,H/4,W/4,C]."""
+        self.prepare()
+        c, m = self.c, self.m
+        eng = self._eng()
+        x = ops.stem_fwd(images, c["stem_w"], *c["stem_bn"], out_dtype=c["act_dtype"], engine=eng)
+        if m.backbone == "resnet18":
+            nb = len(c["blocks"])
+            for bi, d in enumerate(c["blocks"]):
+                y = ops.conv3x3_bn_act_fwd(x, d["w1"][0], d["w1"][1], *d["bn1"], relu=True, engine=eng)
+                last = bi == nb - 1
+                x = ops.conv3x3_bn_act_fwd(y, d["w2"][0], d["w2"][1], *d["bn2"], res=x, relu=True,
+                                           out_dtype=F32 if last else None, engine=eng)
+            return x.p0
+        # resnet50 Bottlenecks (CUDA-core fp32 engine)
+        B, H, W, _ = x.shape
+        cur = x.p0.view(B * H * W, 64)
+        for d in c["blocks"]:
+            o = ops.linear_fwd(cur, d["w1"], None, *d["bn1"], relu=True)
+            p = ops.Planes.__new__(ops.Planes)
+            p.dtype, p.shape, p.p0, p.p1 = F32, (B, H, W, 64), o.view(B, H, W, 64), None
+            o = ops.conv3x3_bn_act_fwd(p, d["w2"], None, *d["bn2"], relu=True, engine=ENGINE_SIMT).p0.view(B * H * W, 64)
+            idt = ops.linear_fwd(cur, d["wd"], None, *d["bnd"]) if "wd" in d else cur
+            cur = ops.linear_fwd(o, d["w3"], None, *d["bn3"], res=idt, relu=True)
+        return cur.view(B, H, W, 256)
+
+    def own_into(self, fm, bboxes, additional_feats, comb):
+        """A4 + A5 + A5b: fill comb[:, :n_feat] (visual | bbox | additional)."""
+        c, m = self.c, self.m
+        scale = fm.shape[1] / m.img_H
+        ops.roi_fwd(fm, bboxes, m.roi_output_size, scale, comb, mode=m.roi_mode, sampling_ratio=2)
+        col = m.n_visual_feat
+        if m.bbox_hidden_dim > 0:
+            ops.bbox_enc_fwd(bboxes, *c["bbox"], comb[:, col:])
+            col += m.bbox_hidden_dim
+        if m.n_additional_feat > 0:
+            ops.affine_cols_fwd(additional_feats.float(), *c["add_bn"], comb[:, col:])
+
+    def gat_into(self, own, context_indices, out, want_attn=False, heads=None):
+        """A6: own [T,n_feat] (strided view ok) -> out [T, hidden] ; returns attn of the (single) head or None."""
+        self.prepare()
+        attn, col = None, 0
+        for g in (self.c["gat"] if heads is None else heads):
+            ext = ops.linear_fwd(own, g["ext"])
+            Hd = g["Hd"]
+            attn = ops.gat_fwd(ext[:, :Hd], ext[:, Hd], ext[:, Hd + 1], g["b"], g["alpha"], context_indices,
+                               out[:, col:col + Hd], want_attn=want_attn)
+            col += Hd
+        return attn
+
+    def visual_features(self, images, bboxes):
+        """`CoVA._get_visual_features` (`models.py:124-127`)."""
+        fm = self.feature_map(images)
+        out = torch.empty((bboxes.shape[0], self.m.n_visual_feat), dtype=torch.float32, device=fm.device)
+        scale = fm.shape[1] / self.m.img_H
+        ops.roi_fwd(fm, bboxes, self.m.roi_output_size, scale, out, mode=self.m.roi_mode)
+        return out
+
+    def bbox_features(self, bboxes):
+        """`CoVA._get_bbox_features` (`models.py:129-148`)."""
+        self.prepare()
+        out = torch.empty((bboxes.shape[0], self.m.bbox_hidden_dim), dtype=torch.float32, device=bboxes.device)
+        if self.m.bbox_hidden_dim > 0:
+            ops.bbox_enc_fwd(bboxes, *self.c["bbox"], out)
+        return out
+
+    def forward(self, images, bboxes, additional_feats, context_indices, return_intermediates=False):
+        m = self.m
+        fm = self.feature_map(images)
+        T = bboxes.shape[0]
+        comb = torch.empty((T, m.n_total_feat), dtype=torch.float32, device=fm.device)
+        self.own_into(fm, bboxes, additional_feats, comb)
+        if m.use_context:
+            self.gat_into(comb[:, :m.n_feat], context_indices, comb[:, m.n_feat:])
+        h1 = ops.linear_fwd(comb, self.c["dec1"][0], self.c["dec1"][1], self.c["dec1"][2], self.c["dec1"][3], relu=True)
+        logits = ops.linear_fwd(h1, *self.c["dec2"])
+        if return_intermediates:
+            return dict(fm=fm, own=comb[:, :m.n_feat], ctx=comb[:, m.n_feat:], logits=logits)
+        return logits

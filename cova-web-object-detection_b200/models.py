@@ -1,0 +1,310 @@
+"""Drop-in replacement for the reference's ``models.py``: same ``CoVA`` / ``GraphAttentionLayer`` classes,
+constructor arguments, ``forward`` signature, attributes and ``state_dict`` keys
+(`/root/reference/models.py:9-212`), so the reference's ``main.py`` / ``train.py`` /
+``evaluate.py`` / ``extract_attn_wts_and_visualize.py`` run unchanged and its checkpoints load.
+
+Execution:
+  * inference (``torch.no_grad()``, ``model.eval()``, CUDA tensors) runs the hand-written sm_100a kernels of
+    ``libcova_b200.so`` through ``engine.NativeForward`` - engine ``"tcgen05"`` (tensor-core convolutions,
+    precision ``"fp32"`` = split-bf16 3-product fp32-parity mode, or ``"bf16"``) or ``"simt"`` (exact fp32
+    CUDA cores).
+  * anything that needs autograd (``train.py:45-60``) or batch statistics runs a PyTorch-operator composite
+    of the same arithmetic with the native RoIPool forward (own backward).  That composite is library code
+    (cuDNN/cuBLAS), kept so the unmodified training loop works; hand-written backward kernels are the next
+    round's work.
+  * non-CUDA inputs raise: this package has no CPU path.
+
+Extra keyword-only constructor arguments (all with reference-preserving defaults):
+``backbone`` ("resnet18" | "resnet50"), ``n_heads``, ``roi_mode`` ("pool" | "align"), ``engine``, ``precision``.
+"""
+import os
+import warnings
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import ops
+from .engine import NativeForward
+
+
+def count_parameters(model):
+    """`/root/reference/utils.py:37-41`."""
+    return sum(p.numel() for p in model.parameters() if p.requires_grad)
+
+
+# ----------------------------------------------------------------------------- backbone blocks
+# Same attribute names as torchvision's BasicBlock / Bottleneck so `convnet.4.{b}.*` checkpoint keys match.
+class BasicBlock(nn.Module):
+    def __init__(self, planes=64):
+        super().__init__()
+        self.conv1 = nn.Conv2d(planes, planes, 3, 1, 1, bias=False)
+        self.bn1 = nn.BatchNorm2d(planes)
+        self.relu = nn.ReLU(inplace=True)
+        self.conv2 = nn.Conv2d(planes, planes, 3, 1, 1, bias=False)
+        self.bn2 = nn.BatchNorm2d(planes)
+        self.downsample = None
+
+    def forward(self, x):
+        out = self.relu(self.bn1(self.conv1(x)))
+        out = self.bn2(self.conv2(out))
+        return self.relu(out + x)
+
+
+class Bottleneck(nn.Module):
+    def __init__(self, inplanes, planes=64, downsample=False):
+        super().__init__()
+        self.conv1 = nn.Conv2d(inplanes, planes, 1, bias=False)
+        self.bn1 = nn.BatchNorm2d(planes)
+        self.conv2 = nn.Conv2d(planes, planes, 3, 1, 1, bias=False)
+        self.bn2 = nn.BatchNorm2d(planes)
+        self.conv3 = nn.Conv2d(planes, planes * 4, 1, bias=False)
+        self.bn3 = nn.BatchNorm2d(planes * 4)
+        self.relu = nn.ReLU(inplace=True)
+        self.downsample = (nn.Sequential(nn.Conv2d(inplanes, planes * 4, 1, bias=False), nn.BatchNorm2d(planes * 4))
+                           if downsample else None)
+
+    def forward(self, x):
+        out = self.relu(self.bn1(self.conv1(x)))
+        out = self.relu(self.bn2(self.conv2(out)))
+        out = self.bn3(self.conv3(out))
+        idt = x if self.downsample is None else self.downsample(x)
+        return self.relu(out + idt)
+
+
+def _truncated_resnet(backbone):
+    """`list(resnet.children())[:-5]` (`models.py:49-51`): conv1, bn1, relu, maxpool, layer1."""
+    if backbone == "resnet18":
+        layer1, C = nn.Sequential(BasicBlock(), BasicBlock()), 64
+    elif backbone == "resnet50":
+        layer1, C = nn.Sequential(Bottleneck(64, 64, True), Bottleneck(256), Bottleneck(256)), 256
+    else:
+        raise ValueError("backbone must be 'resnet18' or 'resnet50'")
+    net = nn.Sequential(nn.Conv2d(3, 64, 7, 2, 3, bias=False), nn.BatchNorm2d(64), nn.ReLU(inplace=True),
+                        nn.MaxPool2d(3, 2, 1), layer1)
+    for mod in net.modules():   # torchvision ResNet init
+        if isinstance(mod, nn.Conv2d):
+            nn.init.kaiming_normal_(mod.weight, mode="fan_out", nonlinearity="relu")
+    return net, C
+
+
+_PRETRAINED_FILES = {"resnet18": "resnet18-f37072fd.pth", "resnet50": "resnet50-0676ba61.pth"}
+
+
+def _try_load_pretrained(convnet, backbone):
+    """The reference starts from ImageNet weights (`models.py:49`, `pretrained=True`).  Use them when the
+    torchvision checkpoint is already in the local torch-hub cache; never touch the network.  Otherwise
+    keep the random init and say so."""
+    path = os.path.join(torch.hub.get_dir(), "checkpoints", _PRETRAINED_FILES[backbone])
+    if not os.path.exists(path):
+        warnings.warn("cova_b200: pretrained %s weights not in %s - backbone is randomly initialised; "
+                      "load a checkpoint with load_state_dict()" % (backbone, os.path.dirname(path)))
+        return False
+    src = torch.load(path, map_location="cpu")
+    remap = {"conv1.": "0.", "bn1.": "1.", "layer1.": "4."}
+    sd = {new + k[len(old):]: v for k, v in src.items() for old, new in remap.items() if k.startswith(old)}
+    convnet.load_state_dict(sd, strict=True)
+    return True
+
+
+# ----------------------------------------------------------------------------- RoI autograd (training path)
+class _RoIPoolFn(torch.autograd.Function):
+    """Native RoIPool forward (NHWC fp32 feature map) with the scatter-add backward of torchvision's
+    roi_pool (every output's gradient goes to its arg-max pixel)."""
+
+    @staticmethod
+    def forward(ctx, fm_nhwc, rois, P, scale):
+        B, Hf, Wf, C = fm_nhwc.shape
+        out = torch.empty((rois.shape[0], C * P[0] * P[1]), dtype=torch.float32, device=fm_nhwc.device)
+        argmax = ops.roi_fwd(fm_nhwc.contiguous(), rois, P, scale, out, mode="pool", want_argmax=True)
+        ctx.save_for_backward(argmax, rois)
+        ctx.shape = (B, Hf, Wf, C)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        argmax, rois = ctx.saved_tensors
+        B, Hf, Wf, C = ctx.shape
+        T = rois.shape[0]
+        g = grad_out.reshape(T, C, -1)
+        am = argmax.reshape(T, C, -1).long()
+        valid = am >= 0
+        b = rois[:, 0].long().view(T, 1, 1)
+        c = torch.arange(C, device=g.device).view(1, C, 1)
+        flat = ((b * Hf * Wf + am.clamp_min(0)) * C + c)
+        grad_fm = torch.zeros(B * Hf * Wf * C, dtype=g.dtype, device=g.device)
+        grad_fm.index_add_(0, flat[valid], g[valid])
+        return grad_fm.view(B, Hf, Wf, C), None, None, None
+
+
+# ----------------------------------------------------------------------------- GAT
+class GraphAttentionLayer(nn.Module):
+    """Simple GAT layer, similar to https://arxiv.org/abs/1710.10903 (`/root/reference/models.py:151-212`)."""
+
+    def __init__(self, in_features, hidden_dim, alpha=0.2):
+        super().__init__()
+        self.in_features = in_features
+        self.hidden_dim = hidden_dim
+        self.W_i = nn.Linear(in_features, hidden_dim, bias=False)
+        self.W_j = nn.Linear(in_features, hidden_dim, bias=False)
+        self.attention_layer = nn.Linear(2 * hidden_dim, 1)
+        self.leakyrelu = nn.LeakyReLU(alpha)
+        self._native = None
+
+    def forward(self, h_i, context_indices, return_attn_wts=False):
+        """h_i [N,in_features]; context_indices int64 [N,n_context] (ids 0..N-1, -1 = padding)."""
+        if not h_i.is_cuda:
+            raise RuntimeError("cova_b200: GraphAttentionLayer needs CUDA tensors (no CPU path)")
+        if torch.is_grad_enabled() and (h_i.requires_grad or any(p.requires_grad for p in self.parameters())):
+            return self._forward_composite(h_i, context_indices, return_attn_wts)
+        key = tuple((p.data_ptr(), p._version) for p in self.parameters())
+        if self._native is None or self._native[0] != key:
+            self._native = (key, NativeForward._gat_cache(self))
+        g = self._native[1]
+        h = h_i.float()
+        if h.stride(-1) != 1:
+            h = h.contiguous()
+        out = torch.empty((h.shape[0], self.hidden_dim), dtype=torch.float32, device=h.device)
+        ext = ops.linear_fwd(h, g["ext"])
+        Hd = self.hidden_dim
+        attn = ops.gat_fwd(ext[:, :Hd], ext[:, Hd], ext[:, Hd + 1], g["b"], g["alpha"], context_indices, out,
+                           want_attn=return_attn_wts)
+        return (out, attn) if return_attn_wts else out
+
+    def _forward_composite(self, h_i, context_indices, return_attn_wts=False):
+        """Autograd path: project each node once, gather, masked softmax (same algebra as the native kernel)."""
+        N, K = context_indices.shape
+        Hd = self.hidden_dim
+        a = self.attention_layer.weight[0]
+        Wh_i, Wh_j = self.W_i(h_i), self.W_j(h_i)
+        s, t = Wh_i @ a[:Hd], Wh_j @ a[Hd:]
+        valid = context_indices >= 0
+        idx = context_indices.clamp_min(0)
+        e = self.leakyrelu(s[:, None] + t[idx] + self.attention_layer.bias)
+        e = torch.where(valid, e, torch.full_like(e, -9e15))
+        attn = torch.softmax(e, dim=1)
+        nb = Wh_j[idx.reshape(-1)].view(N, K, Hd) * valid.unsqueeze(-1)
+        out = (attn.unsqueeze(-1) * nb).sum(1)
+        return (out, attn) if return_attn_wts else out
+
+
+class MultiHeadGAT(nn.Module):
+    """`n_heads` independent reference layers of width hidden_dim // n_heads, concatenated."""
+
+    def __init__(self, in_features, hidden_dim, n_heads):
+        super().__init__()
+        assert hidden_dim % n_heads == 0
+        self.heads = nn.ModuleList(GraphAttentionLayer(in_features, hidden_dim // n_heads) for _ in range(n_heads))
+
+    def forward(self, h_i, context_indices, return_attn_wts=False):
+        outs = [h(h_i, context_indices, return_attn_wts) for h in self.heads]
+        if return_attn_wts:
+            return torch.cat([o[0] for o in outs], 1), torch.stack([o[1] for o in outs], 1)
+        return torch.cat(outs, 1)
+
+
+# ----------------------------------------------------------------------------- CoVA
+class CoVA(nn.Module):
+    def __init__(self, roi_output_size, img_H, n_classes, use_context=True, hidden_dim=384, bbox_hidden_dim=32,
+                 n_additional_feat=0, drop_prob=0.2, class_names=None, *, backbone="resnet18", n_heads=1,
+                 roi_mode="pool", engine=None, precision=None, pretrained=True):
+        """Same positional arguments as `/root/reference/models.py:10-21` (callers pass all nine positionally:
+        `main.py:122-132`).  The feature-map shape is computed analytically (no probe forward on
+        uninitialised memory as in `models.py:53-54`)."""
+        super().__init__()
+        self.n_classes = n_classes
+        self.use_context = use_context
+        self.hidden_dim = hidden_dim
+        self.bbox_hidden_dim = bbox_hidden_dim
+        self.n_additional_feat = n_additional_feat
+        self.class_names = np.arange(self.n_classes).astype(str) if class_names is None else class_names
+        self.img_H = img_H
+        self.roi_output_size = tuple(roi_output_size)
+        self.backbone = backbone
+        self.roi_mode = roi_mode
+        self.engine = engine or os.environ.get("COVA_B200_ENGINE", "tcgen05")
+        self.precision = precision or os.environ.get("COVA_B200_PRECISION", "fp32")
+        if self.engine not in ("tcgen05", "simt") or self.precision not in ("fp32", "bf16") or roi_mode not in ("pool", "align"):
+            raise ValueError("engine in {tcgen05, simt}, precision in {fp32, bf16}, roi_mode in {pool, align}")
+
+        ##### REPRESENTATION NETWORK (RN) #####
+        self.convnet, C = _truncated_resnet(backbone)
+        if pretrained:
+            _try_load_pretrained(self.convnet, backbone)
+        Hc = (img_H + 6 - 7) // 2 + 1
+        self.fm_H = (Hc + 2 - 3) // 2 + 1
+        self.spatial_scale = self.fm_H / img_H                       # models.py:56
+        self.n_visual_feat = C * self.roi_output_size[0] * self.roi_output_size[1]
+        self.n_feat = self.n_visual_feat + self.bbox_hidden_dim + self.n_additional_feat
+
+        if self.bbox_hidden_dim > 0:
+            self.bbox_feat_encoder = nn.Sequential(nn.Linear(5, self.bbox_hidden_dim),
+                                                   nn.BatchNorm1d(self.bbox_hidden_dim), nn.ReLU())
+        if self.n_additional_feat > 0:
+            self.bn_additional_feat = nn.BatchNorm1d(self.n_additional_feat)
+        else:
+            self.bn_additional_feat = lambda x: x
+
+        ##### GRAPH ATTENTION LAYER (GAT) #####
+        if self.use_context:
+            self.gat = (GraphAttentionLayer(self.n_feat, self.hidden_dim) if n_heads == 1
+                        else MultiHeadGAT(self.n_feat, self.hidden_dim, n_heads))
+
+        ##### FC LAYERS #####
+        self.n_total_feat = self.n_feat + self.hidden_dim
+        self.decoder = nn.Sequential(nn.Dropout(drop_prob), nn.Linear(self.n_total_feat, self.n_total_feat),
+                                     nn.BatchNorm1d(self.n_total_feat), nn.ReLU(), nn.Dropout(drop_prob),
+                                     nn.Linear(self.n_total_feat, self.n_classes))
+        self._native = NativeForward(self)
+        print("Model Parameters:", count_parameters(self))
+
+    def gat_heads(self):
+        return list(self.gat.heads) if isinstance(self.gat, MultiHeadGAT) else [self.gat]
+
+    # ------------------------------------------------------------------ dispatch
+    def _use_native(self, *tensors):
+        for t in tensors:
+            if not t.is_cuda:
+                raise RuntimeError("cova_b200: CoVA needs CUDA tensors - the hot path has no CPU implementation")
+        return not self.training and not torch.is_grad_enabled()
+
+    def forward(self, images, bboxes, additional_feats, context_indices):
+        """images [B,3,img_H,img_H] f32; bboxes [N,5] = [batch_idx,x1,y1,x2,y2]; additional_feats [N,n_add];
+        context_indices int64 [N,n_context] (-1 padded) -> logits [N,n_classes] (`models.py:94-122`)."""
+        if self._use_native(images, bboxes):
+            return self._native.forward(images.float(), bboxes.float(), additional_feats, context_indices)
+        return self._forward_composite(images, bboxes, additional_feats, context_indices)
+
+    def _forward_composite(self, images, bboxes, additional_feats, context_indices):
+        visual_feats = self._get_visual_features(images, bboxes)
+        bbox_feats = self._get_bbox_features(bboxes)
+        additional_feats = self.bn_additional_feat(additional_feats)
+        own_features = torch.cat((visual_feats, bbox_feats, additional_feats), dim=1)
+        if self.use_context:
+            context_representation = self.gat(own_features, context_indices)
+        else:
+            context_representation = own_features[:, :0]
+        return self.decoder(torch.cat((own_features, context_representation), dim=1))
+
+    def _get_visual_features(self, images, bboxes):
+        """`models.py:124-127` -> [N, C*P*P]."""
+        if self._use_native(images, bboxes):
+            return self._native.visual_features(images.float(), bboxes.float())
+        fm = self.convnet(images).permute(0, 2, 3, 1)                # NCHW -> NHWC view for the native RoI kernel
+        if self.roi_mode == "pool":
+            return _RoIPoolFn.apply(fm, bboxes.float(), self.roi_output_size, self.spatial_scale)
+        import torchvision   # RoIAlign backward is not written yet: library op on the autograd path only
+        return torchvision.ops.roi_align(fm.permute(0, 3, 1, 2), bboxes, self.roi_output_size, self.spatial_scale,
+                                         2, False).reshape(bboxes.shape[0], self.n_visual_feat)
+
+    def _get_bbox_features(self, bboxes):
+        """`models.py:129-148`: [x,y,w,h,asp_ratio] -> bbox_hidden_dim features (or [N,0])."""
+        if self.bbox_hidden_dim <= 0:
+            return bboxes[:, :0]
+        if self._use_native(bboxes):
+            return self._native.bbox_features(bboxes.float())
+        f = bboxes[:, 1:].clone()
+        f[:, 2:] -= f[:, :2]
+        f = torch.cat((f, (f[:, 2] / f[:, 3]).view(-1, 1)), dim=1)
+        return self.bbox_feat_encoder(f)

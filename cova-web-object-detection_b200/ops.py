@@ -1,0 +1,160 @@
+"""Python wrappers over the C ABI (``include/cova_b200.h``).  PyTorch is used for device memory and the
+current stream only; every op below is one call into ``libcova_b200.so``.  CUDA tensors only - there is no
+CPU path here (the CPU restatement lives in ``oracle/`` and is test infrastructure)."""
+import torch
+
+from . import _lib
+from ._lib import BF16, BF16X2, ENGINE_SIMT, ENGINE_TCGEN05, F32  # noqa: F401
+
+ENGINES = {"simt": ENGINE_SIMT, "tcgen05": ENGINE_TCGEN05}
+
+# kernels launched through this module since the last reset (bench.py's `gpu_launches` claim)
+launch_count = 0
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _cuda(t, dtype=None, name="tensor"):
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise RuntimeError(f"cova_b200: `{name}` must be a CUDA tensor (the hot path has no CPU implementation)")
+    if dtype is not None and t.dtype != dtype:
+        raise RuntimeError(f"cova_b200: `{name}` must be {dtype}, got {t.dtype}")
+    return t
+
+
+def _ptr(t):
+    return 0 if t is None else t.data_ptr()
+
+
+def _call(name, *args):
+    global launch_count
+    launch_count += 1
+    _lib.check(getattr(_lib.lib(), name)(*args), name)
+
+
+class Planes:
+    """An NHWC activation [B,H,W,C] in one of the ABI dtypes: fp32 (p0), bf16 (p0) or split-bf16 (p0=hi, p1=lo)."""
+
+    __slots__ = ("dtype", "p0", "p1", "shape")
+
+    def __init__(self, dtype, shape, device):
+        self.dtype, self.shape = dtype, tuple(shape)
+        td = torch.float32 if dtype == F32 else torch.bfloat16
+        self.p0 = torch.empty(self.shape, dtype=td, device=device)
+        self.p1 = torch.empty(self.shape, dtype=td, device=device) if dtype == BF16X2 else None
+
+    def float(self):
+        """fp32 NHWC view of the value (hi + lo for split-bf16)."""
+        if self.dtype == F32:
+            return self.p0
+        return self.p0.float() + self.p1.float() if self.p1 is not None else self.p0.float()
+
+
+def device_info():
+    sm, smem = _lib._I(), _lib._I()
+    _lib.check(_lib.lib().cova_device_info(sm, smem), "cova_device_info")
+    return sm.value, smem.value
+
+
+def stem_fwd(images, w, bn_scale, bn_shift, out_dtype=F32, engine=ENGINE_SIMT):
+    """conv7x7 s2 p3 + BN + ReLU + maxpool3x3 s2 p1; images [B,3,H,W] fp32 NCHW -> Planes [B,H/4,W/4,64]."""
+    _cuda(images, torch.float32, "images")
+    images = images.contiguous()
+    B, C, H, W = images.shape
+    if C != 3:
+        raise RuntimeError("cova_b200: images must be [B,3,H,W]")
+    Hc, Wc = (H + 6 - 7) // 2 + 1, (W + 6 - 7) // 2 + 1
+    Hp, Wp = (Hc + 2 - 3) // 2 + 1, (Wc + 2 - 3) // 2 + 1
+    out = Planes(out_dtype, (B, Hp, Wp, 64), images.device)
+    _call("cova_stem_fwd", images.data_ptr(), B, H, W, w.data_ptr(), bn_scale.data_ptr(), bn_shift.data_ptr(),
+          out_dtype, out.p0.data_ptr(), _ptr(out.p1), engine, _stream())
+    return out
+
+
+def pack_conv_weight(w_oihw, simt=True, tc=True, split=True):
+    """OIHW fp32 -> (simt fp32 [kh,kw,Cin,Cout] | None, tc_hi bf16 [kh*kw,Cout,Cin] | None, tc_lo | None)."""
+    _cuda(w_oihw, torch.float32, "w")
+    w = w_oihw.contiguous()
+    Co, Ci, kh, kw = w.shape
+    s = torch.empty((kh, kw, Ci, Co), dtype=torch.float32, device=w.device) if simt else None
+    hi = torch.empty((kh * kw, Co, Ci), dtype=torch.bfloat16, device=w.device) if tc else None
+    lo = torch.empty_like(hi) if (tc and split) else None
+    _call("cova_pack_conv_weight", w.data_ptr(), Co, Ci, kh, kw, _ptr(s), _ptr(hi), _ptr(lo), _stream())
+    return s, hi, lo
+
+
+def conv3x3_bn_act_fwd(x, w_a, w_b, bn_scale, bn_shift, res=None, relu=True, out_dtype=None, engine=ENGINE_SIMT):
+    """3x3 s1 p1 conv (64->64) + folded BN (+ residual) (+ ReLU) on NHWC Planes."""
+    B, H, W, C = x.shape
+    out_dtype = x.dtype if out_dtype is None else out_dtype
+    y = Planes(out_dtype, (B, H, W, C), x.p0.device)
+    if res is not None and res.dtype != x.dtype:
+        raise RuntimeError("cova_b200: residual must have the input's dtype")
+    _call("cova_conv3x3_bn_act_fwd", x.p0.data_ptr(), _ptr(x.p1), x.dtype, B, H, W, C, C, w_a.data_ptr(), _ptr(w_b),
+          bn_scale.data_ptr(), bn_shift.data_ptr(), _ptr(res.p0) if res is not None else 0,
+          _ptr(res.p1) if res is not None else 0, int(relu), out_dtype, y.p0.data_ptr(), _ptr(y.p1), engine, _stream())
+    return y
+
+
+def roi_fwd(fm, rois, P, spatial_scale, out, mode="pool", sampling_ratio=2, want_argmax=False):
+    """fm NHWC fp32 [B,Hf,Wf,C]; rois [T,5]; writes out[:, :C*PH*PW] (out may be a wider row-major buffer)."""
+    _cuda(fm, torch.float32, "fm")
+    _cuda(rois, torch.float32, "bboxes")
+    rois = rois.contiguous()
+    B, Hf, Wf, C = fm.shape
+    T = rois.shape[0]
+    PH, PW = P
+    assert out.stride(1) == 1 and out.dtype == torch.float32
+    argmax = torch.empty((T, C, PH, PW), dtype=torch.int32, device=fm.device) if want_argmax else None
+    _call("cova_roi_fwd", fm.data_ptr(), B, Hf, Wf, C, rois.data_ptr(), T, PH, PW, float(spatial_scale),
+          0 if mode == "pool" else 1, int(sampling_ratio), out.data_ptr(), out.stride(0), _ptr(argmax), _stream())
+    return argmax
+
+
+def bbox_enc_fwd(rois, w, b, bn_scale, bn_shift, out):
+    _cuda(rois, torch.float32, "bboxes")
+    rois = rois.contiguous()
+    assert out.stride(1) == 1
+    _call("cova_bbox_enc_fwd", rois.data_ptr(), rois.shape[0], w.data_ptr(), b.data_ptr(), _ptr(bn_scale),
+          _ptr(bn_shift), w.shape[0], out.data_ptr(), out.stride(0), _stream())
+
+
+def affine_cols_fwd(x, scale, shift, out):
+    _cuda(x, torch.float32, "additional_feats")
+    T, D = x.shape
+    if T == 0 or D == 0:
+        return
+    if x.stride(1) != 1:
+        x = x.contiguous()
+    _call("cova_affine_cols_fwd", x.data_ptr(), T, D, x.stride(0), _ptr(scale), _ptr(shift), out.data_ptr(),
+          out.stride(0), _stream())
+
+
+def linear_fwd(x, w, bias=None, scale=None, shift=None, res=None, relu=False, out=None, engine=ENGINE_SIMT):
+    """Y = act((X @ W^T + bias) * scale + shift + res); x [M,K] (row stride free), w [N,K] contiguous."""
+    _cuda(x, torch.float32, "x")
+    M, K = x.shape
+    N = w.shape[0]
+    assert x.stride(1) == 1 and w.is_contiguous() and w.shape[1] == K
+    if out is None:
+        out = torch.empty((M, N), dtype=torch.float32, device=x.device)
+    assert out.stride(1) == 1
+    _call("cova_linear_fwd", x.data_ptr(), x.stride(0), M, K, w.data_ptr(), N, _ptr(bias), _ptr(scale), _ptr(shift),
+          _ptr(res), res.stride(0) if res is not None else 0, int(relu), out.data_ptr(), out.stride(0), engine,
+          _stream())
+    return out
+
+
+def gat_fwd(whj, s, t, att_b, alpha, ctx_idx, out, want_attn=False):
+    """Fused neighbour gather + masked softmax + weighted sum.  whj [T,Hd] (row stride free), s/t [T] (stride free)."""
+    _cuda(ctx_idx, torch.int64, "context_indices")
+    ctx_idx = ctx_idx.contiguous()
+    T, K = ctx_idx.shape
+    Hd = whj.shape[1]
+    assert s.stride(0) == t.stride(0) and whj.stride(1) == 1 and out.stride(1) == 1
+    attn = torch.empty((T, K), dtype=torch.float32, device=whj.device) if want_attn else None
+    _call("cova_gat_fwd", whj.data_ptr(), whj.stride(0), s.data_ptr(), t.data_ptr(), s.stride(0), float(att_b),
+          float(alpha), ctx_idx.data_ptr(), T, K, Hd, out.data_ptr(), out.stride(0), _ptr(attn), _stream())
+    return attn

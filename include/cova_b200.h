@@ -1,0 +1,110 @@
+/*
+ * cova_b200.h - C ABI of libcova_b200.so: the B200 (sm_100a) kernels behind CoVA's per-webpage
+ * forward hot path.  The reference (`/root/reference`, pure Python) has no FFI of its own; each entry
+ * point below replaces the torch/torchvision call the reference makes at the cited `models.py` line
+ * (SURVEY.md section 8(a)/(b)).  The reference-side binding is a ctypes stub - see INTEGRATION.md.
+ *
+ * Conventions
+ *  - Every pointer is a DEVICE pointer unless named `h_*`.  The caller (PyTorch) owns all memory:
+ *    inputs, outputs and workspaces.  The library never allocates, frees or retains a pointer.
+ *  - `stream` is a `cudaStream_t` passed as `void*` (pass `torch.cuda.current_stream().cuda_stream`).
+ *    Launches are asynchronous; no entry point synchronises.
+ *  - Return value: 0 = success, otherwise a COVA_ERR_* code; `cova_last_error()` returns a
+ *    thread-local message.  Nothing throws or exits across this boundary.
+ *  - Activation tensors are NHWC.  `dtype`:
+ *      COVA_F32   one fp32 plane (`p0`; `p1` ignored)
+ *      COVA_BF16  one bf16 plane (`p0`)
+ *      COVA_BF16X2 split-bf16: `p0` = hi plane = bf16(x), `p1` = lo plane = bf16(x - hi).  hi+lo carries
+ *                 ~16 mantissa bits; products hi*Whi + lo*Whi + hi*Wlo on tcgen05 tensor cores with fp32
+ *                 accumulate reproduce an fp32 convolution to ~1e-5 (the "fp32-parity" tensor-core mode).
+ *  - Eval-mode BatchNorm is passed folded: y = x*scale[c] + shift[c]
+ *    (scale = weight/sqrt(running_var+eps), shift = bias - running_mean*scale).
+ */
+#ifndef COVA_B200_H
+#define COVA_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define COVA_ABI_VERSION 1
+
+enum { COVA_OK = 0, COVA_ERR_ARG = 1, COVA_ERR_CUDA = 2, COVA_ERR_UNSUPPORTED = 3 };
+enum { COVA_F32 = 0, COVA_BF16 = 1, COVA_BF16X2 = 2 };
+enum { COVA_ENGINE_SIMT = 0, COVA_ENGINE_TCGEN05 = 1 };
+
+int cova_abi_version(void);
+const char* cova_last_error(void);
+/* SM count / max dynamic smem of the current device (host query; used to size persistent grids). */
+int cova_device_info(int* sm_count, int* max_smem_optin);
+
+/* ---- A2: backbone stem.  Replaces `convnet[0:4]` = conv1 7x7 s2 p3 (no bias) -> bn1 -> relu ->
+ * maxpool 3x3 s2 p1 (`models.py:49-51`, applied `models.py:125`).  ONE fused kernel: the
+ * [B,64,H/2,W/2] conv output never reaches HBM.
+ *   images  [B,3,H,W] fp32 NCHW (the reference's input contract, `models.py:96`)
+ *   w       [64,3,7,7] fp32 OIHW (`convnet.0.weight`), bn_scale/bn_shift [64] folded `convnet.1`
+ *   out     NHWC [B,H/4,W/4,64] in `out_dtype` (planes out0/out1)                                   */
+int cova_stem_fwd(const float* images, int B, int H, int W, const float* w, const float* bn_scale,
+                  const float* bn_shift, int out_dtype, void* out0, void* out1, int engine, void* stream);
+
+/* ---- A2: 3x3 s1 p1 convolution + folded BN (+ residual) (+ ReLU): one BasicBlock half
+ * (torchvision BasicBlock.forward; `convnet.4.{b}.conv{1,2}` + `bn{1,2}`), Cin = Cout = 64.
+ *   x / res / y : NHWC [B,H,W,64]; `dtype` applies to x and res, `out_dtype` to y.
+ *   w: engine SIMT   -> fp32 [3][3][Cin][Cout]           (repacked from OIHW by cova_pack_conv_weight)
+ *      engine TCGEN05-> bf16 hi/lo [9][Cout][Cin] K-major (w_hi, w_lo; w_lo may be NULL for COVA_BF16)  */
+int cova_conv3x3_bn_act_fwd(const void* x0, const void* x1, int dtype, int B, int H, int W, int Cin, int Cout,
+                            const void* w_a, const void* w_b, const float* bn_scale, const float* bn_shift,
+                            const void* res0, const void* res1, int relu, int out_dtype, void* y0, void* y1,
+                            int engine, void* stream);
+
+/* Repack an OIHW fp32 conv weight [Cout,Cin,kh,kw] for the engines above.
+ *   simt_out  : fp32 [kh][kw][Cin][Cout]                       (may be NULL)
+ *   tc_hi/lo  : bf16 [kh*kw][Cout][Cin] hi/lo split            (may be NULL)                         */
+int cova_pack_conv_weight(const float* w_oihw, int Cout, int Cin, int kh, int kw, float* simt_out,
+                          void* tc_hi, void* tc_lo, void* stream);
+
+/* ---- A4: RoIPool.  Replaces `torchvision.ops.RoIPool(P, scale)` (`models.py:58`, `:125-127`).
+ * Bit-exact in fp32.  fm NHWC fp32 [B,Hf,Wf,C]; rois [T,5] fp32 = [batch_idx,x1,y1,x2,y2] image pixels.
+ * Writes out[t*ld_out + c*PH*PW + ph*PW + pw] (the `.view(T, C*P*P)` flatten order of `models.py:125-127`).
+ * argmax (optional, int32 [T,C,PH,PW], flat h*Wf+w index or -1) is what the backward needs.
+ * mode 0 = RoIPool; mode 1 = RoIAlign(P, scale, sampling_ratio, aligned=False) (A4').      */
+int cova_roi_fwd(const float* fm, int B, int Hf, int Wf, int C, const float* rois, int T, int PH, int PW,
+                 float spatial_scale, int mode, int sampling_ratio, float* out, int64_t ld_out, int32_t* argmax,
+                 void* stream);
+
+/* ---- A5: positional encoder.  Replaces `_get_bbox_features` + `bbox_feat_encoder`
+ * (`models.py:129-148`, `:65-70`): [x1,y1,w,h,w/h] -> Linear(5,D) -> folded BN1d -> ReLU.
+ * Writes out[t*ld_out + d], d < D (so it can land at column C*P*P of the `own` row: the concat of
+ * `models.py:110` costs no extra pass).                                                             */
+int cova_bbox_enc_fwd(const float* rois, int T, const float* w /*[D,5]*/, const float* b /*[D]*/,
+                      const float* bn_scale, const float* bn_shift, int D, float* out, int64_t ld_out, void* stream);
+
+/* ---- A5b: `bn_additional_feat` (folded BN1d, or identity when scale == NULL) + concat column copy
+ * (`models.py:72-75`, `:109-110`).                                                                  */
+int cova_affine_cols_fwd(const float* x, int T, int D, int64_t ld_x, const float* scale, const float* shift,
+                         float* out, int64_t ld_out, void* stream);
+
+/* ---- generic row-major linear layer  Y[M,N] = act((X[M,K] @ W[N,K]^T + bias) * scale + shift + res)
+ * (`nn.Linear` = `models.py:160-164` W_i/W_j, `:85`, `:89`; also the 1x1 convolutions of the ResNet-50
+ * Bottleneck on NHWC activations, where `res` is the identity branch); bias/scale/shift/res may be NULL. */
+int cova_linear_fwd(const float* x, int64_t ld_x, int M, int K, const float* w, int N, const float* bias,
+                    const float* scale, const float* shift, const float* res, int64_t ld_res, int relu, float* y,
+                    int64_t ld_y, int engine, void* stream);
+
+/* ---- A6: graph-attention gather.  Replaces `GraphAttentionLayer.forward` lines `models.py:180-208`
+ * after the once-per-node projections (algebraically identical restructuring):
+ *   whj [T,Hd] = W_j h (ld_whj), s_i = s[i*ld_st] = a_i . W_i h, t_i = t[i*ld_st] = a_j . W_j h, att_b = bias
+ *   e_ik = LeakyReLU_alpha(s_i + t_c(i,k) + att_b); masked (c<0) -> -9e15; softmax over K;
+ *   out_i = sum_k alpha_ik whj[c(i,k)]   (c<0 rows contribute exactly 0)
+ * ctx_idx: int64 [T,K] batch-global row ids or -1 (`datasets.py:117-128`, `:175`).
+ * attn (optional) [T,K] = the `return_attn_wts=True` output (`models.py:210-211`).                  */
+int cova_gat_fwd(const float* whj, int64_t ld_whj, const float* s, const float* t, int64_t ld_st, float att_b,
+                 float alpha, const int64_t* ctx_idx, int T, int K, int Hd, float* out, int64_t ld_out, float* attn,
+                 void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* COVA_B200_H */

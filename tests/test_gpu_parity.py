@@ -1,0 +1,424 @@
+"""GPU parity tests: every kernel, called through the C ABI (``cova_b200.ops`` -> ctypes -> libcova_b200.so),
+against the oracle (``oracle/cova_oracle.py``) on the same seeded inputs and against the fixtures frozen from
+the live reference (``tests/golden``).  Tolerances (max|a-b| / max|b| unless stated):
+  * RoIPool ....................................... bit-exact
+  * exact-fp32 engine (simt), every stage ......... 1e-5
+  * tcgen05 fp32-parity mode (split-bf16 x3) ...... 1e-4 on the feature map, 1e-4 on logits
+  * tcgen05 bf16 mode ............................. 2e-2 on the feature map, 1e-3 on logits (north-star bar)
+"""
+import warnings
+
+import numpy as np
+import pytest
+import torch
+
+import cova_b200.synth as synth
+from conftest import load_golden, rel_err
+from oracle import cova_oracle as O
+
+pytestmark = pytest.mark.gpu
+warnings.filterwarnings("ignore")
+DEV = "cuda:0"
+
+
+def ops():
+    from cova_b200 import ops as _ops
+    return _ops
+
+
+def t2n(t):
+    return t.detach().float().cpu().numpy()
+
+
+def torch_conv(x, w, stride, pad):
+    """Oracle conv for the larger cases: same arithmetic as cova_oracle.conv2d_nchw, CPU fp32, via ATen."""
+    return torch.nn.functional.conv2d(torch.from_numpy(np.ascontiguousarray(x)), torch.from_numpy(np.ascontiguousarray(w)),
+                                      None, stride, pad).numpy()
+
+
+def make_model(engine, precision="fp32", img=1280, **kw):
+    from cova_b200.models import CoVA
+    cfg = dict(roi=(3, 3), use_context=True, hidden=384, bbhd=32, n_add=0)
+    cfg.update({k: kw.pop(k) for k in list(kw) if k in cfg})
+    m = CoVA(cfg["roi"], img, 4, cfg["use_context"], cfg["hidden"], cfg["bbhd"], cfg["n_add"], 0.2, None,
+             pretrained=False, engine=engine, precision=precision, **kw)
+    sd = synth.make_state_dict(123, backbone=kw.get("backbone", "resnet18"), roi_output_size=cfg["roi"],
+                               hidden_dim=cfg["hidden"], bbox_hidden_dim=cfg["bbhd"], n_additional_feat=cfg["n_add"],
+                               use_context=cfg["use_context"], n_heads=kw.get("n_heads", 1))
+    m.load_state_dict(sd, strict=True)
+    return m.to(DEV).eval(), {k: v.numpy() for k, v in sd.items()}
+
+
+def to_dev(inp):
+    return [t.to(DEV) for t in inp]
+
+
+# ----------------------------------------------------------------------------- single kernels
+@pytest.mark.parametrize("out_dtype", ["f32", "bf16x2"])
+def test_stem_kernel(out_dtype):
+    o = ops()
+    g = torch.Generator().manual_seed(1)
+    B, H = 2, 104                       # 104 -> conv 52 -> pooled 26: partial 8x8 tiles on both edges
+    img = torch.rand(B, 3, H, H, generator=g)
+    w = torch.randn(64, 3, 7, 7, generator=g) * 0.1
+    scale, shift = 0.5 + torch.rand(64, generator=g), 0.1 * torch.randn(64, generator=g)
+    ref = O.conv2d_nchw(img.numpy(), w.numpy(), 2, 3) * scale.numpy().reshape(1, -1, 1, 1) + shift.numpy().reshape(1, -1, 1, 1)
+    ref = O.maxpool3x3s2p1(np.maximum(ref, 0)).transpose(0, 2, 3, 1)
+    out = o.stem_fwd(img.to(DEV), w.to(DEV), scale.to(DEV), shift.to(DEV),
+                     out_dtype=o.F32 if out_dtype == "f32" else o.BF16X2)
+    assert out.shape == (B, 26, 26, 64)
+    assert rel_err(t2n(out.float()), ref) < (1e-5 if out_dtype == "f32" else 3e-5)
+
+
+def _conv_case(seed, B, H, W, with_res):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(B, H, W, 64, generator=g)
+    w = torch.randn(64, 64, 3, 3, generator=g) * (2.0 / 576) ** 0.5
+    scale, shift = 0.5 + torch.rand(64, generator=g), 0.1 * torch.randn(64, generator=g)
+    res = torch.randn(B, H, W, 64, generator=g) if with_res else None
+    ref = torch_conv(x.permute(0, 3, 1, 2).numpy(), w.numpy(), 1, 1).transpose(0, 2, 3, 1)
+    ref = ref * scale.numpy() + shift.numpy()
+    if with_res:
+        ref = ref + res.numpy()
+    return x, w, scale, shift, res, np.maximum(ref, 0)
+
+
+@pytest.mark.parametrize("with_res", [False, True])
+def test_conv3x3_simt_kernel(with_res):
+    o = ops()
+    x, w, scale, shift, res, ref = _conv_case(2, 2, 21, 35, with_res)     # ragged: partial 8x16 tiles
+    ws, _, _ = o.pack_conv_weight(w.to(DEV), simt=True, tc=False)
+    xp = o.Planes(o.F32, x.shape, DEV); xp.p0.copy_(x)
+    rp = None
+    if with_res:
+        rp = o.Planes(o.F32, x.shape, DEV); rp.p0.copy_(res)
+    y = o.conv3x3_bn_act_fwd(xp, ws, None, scale.to(DEV), shift.to(DEV), res=rp, relu=True, engine=o.ENGINE_SIMT)
+    assert rel_err(t2n(y.p0), ref) < 1e-5
+
+
+def _split(t):
+    hi = t.bfloat16()
+    lo = (t - hi.float()).bfloat16()
+    return hi, lo
+
+
+@pytest.mark.parametrize("mode,out", [("split", "f32"), ("split", "bf16x2"), ("bf16", "bf16"), ("bf16", "f32")])
+@pytest.mark.parametrize("shape", [(1, 16, 8), (2, 37, 45), (1, 80, 64)])
+def test_conv3x3_tcgen05_kernel(mode, out, shape):
+    """tcgen05 implicit-GEMM conv vs the oracle conv; shapes cover 1 tile, ragged tiles, multi-tile."""
+    o = ops()
+    B, H, W = shape
+    x, w, scale, shift, res, ref = _conv_case(3, B, H, W, True)
+    split = mode == "split"
+    _, whi, wlo = o.pack_conv_weight(w.to(DEV), simt=False, tc=True, split=split)
+    dt = o.BF16X2 if split else o.BF16
+    xp, rp = o.Planes(dt, x.shape, DEV), o.Planes(dt, x.shape, DEV)
+    for p, t in ((xp, x), (rp, res)):
+        hi, lo = _split(t)
+        p.p0.copy_(hi)
+        if split:
+            p.p1.copy_(lo)
+    if not split:   # oracle sees what the kernel sees: bf16-rounded input, residual and weights
+        xq, rq, wq = x.bfloat16().float(), res.bfloat16().float(), w.bfloat16().float()
+        ref = torch_conv(xq.permute(0, 3, 1, 2).numpy(), wq.numpy(), 1, 1).transpose(0, 2, 3, 1)
+        ref = np.maximum(ref * scale.numpy() + shift.numpy() + rq.numpy(), 0)
+    od = {"f32": o.F32, "bf16": o.BF16, "bf16x2": o.BF16X2}[out]
+    y = o.conv3x3_bn_act_fwd(xp, whi, wlo, scale.to(DEV), shift.to(DEV), res=rp, relu=True, out_dtype=od,
+                             engine=o.ENGINE_TCGEN05)
+    torch.cuda.synchronize()
+    tol = {"f32": 3e-5, "bf16x2": 5e-5, "bf16": 6e-3}[out]   # bf16 out: one bf16 rounding of the result
+    assert rel_err(t2n(y.float()), ref) < tol
+
+
+@pytest.mark.parametrize("P", [(1, 1), (3, 3), (7, 7), (2, 5)])
+def test_roi_pool_adversarial_bit_exact(P):
+    """Fixture from `torchvision.ops.roi_pool` itself: negative coords, sub-pixel boxes, .5 ties, empty bins.
+    C=8 in the fixture -> tiled x8 to the kernel's 64-channel blocks."""
+    o = ops()
+    g = load_golden("g_roi")
+    fm = np.tile(g["fm"], (1, 8, 1, 1))
+    want = np.tile(g["pool_%dx%d" % P], (1, 8, 1, 1)).reshape(len(g["boxes"]), -1)
+    fm_d = torch.from_numpy(fm).permute(0, 2, 3, 1).contiguous().to(DEV)
+    out = torch.empty((len(g["boxes"]), 64 * P[0] * P[1]), device=DEV)
+    am = o.roi_fwd(fm_d, torch.from_numpy(g["boxes"]).to(DEV), P, 0.25, out, want_argmax=True)
+    assert np.array_equal(t2n(out), want)
+    out2 = torch.empty_like(out)
+    o.roi_fwd(fm_d, torch.from_numpy(g["boxes"]).to(DEV), P, 0.25, out2)
+    assert torch.equal(out, out2)                                       # argmax and plain variants agree
+    # argmax points at a pixel holding the max (or -1 for empty bins)
+    am = am.cpu().numpy().reshape(len(g["boxes"]), 64, -1)
+    v = want.reshape(len(g["boxes"]), 64, -1)
+    flat = fm.reshape(2, 64, -1)
+    bidx = g["boxes"][:, 0].astype(int)
+    for n in range(0, len(bidx), 7):
+        for c in (0, 13, 63):
+            for k in range(v.shape[2]):
+                if am[n, c, k] >= 0:
+                    assert flat[bidx[n], c, am[n, c, k]] == v[n, c, k]
+                else:
+                    assert v[n, c, k] == 0
+
+
+@pytest.mark.parametrize("P", [(3, 3), (7, 7), (2, 5)])
+def test_roi_align_adversarial(P):
+    o = ops()
+    g = load_golden("g_roi")
+    fm = np.tile(g["fm"], (1, 8, 1, 1))
+    want = np.tile(g["align_%dx%d" % P], (1, 8, 1, 1)).reshape(len(g["boxes"]), -1)
+    fm_d = torch.from_numpy(fm).permute(0, 2, 3, 1).contiguous().to(DEV)
+    out = torch.empty((len(g["boxes"]), 64 * P[0] * P[1]), device=DEV)
+    o.roi_fwd(fm_d, torch.from_numpy(g["boxes"]).to(DEV), P, 0.25, out, mode="align")
+    assert np.abs(t2n(out) - want).max() < 1e-5
+
+
+def test_roi_pool_wide_row_buffer_and_c256():
+    """Writes into a wider row (the fused concat) and walks 4 channel blocks (ResNet-50 C=256)."""
+    o = ops()
+    g = torch.Generator().manual_seed(4)
+    fm = torch.randn(2, 30, 40, 256, generator=g)
+    _, bboxes, _, _ = synth.gen(2, 25, 8, seed=4, img=160)
+    bboxes[:, 1:] *= 0.75
+    want = O.roi_pool(fm.permute(0, 3, 1, 2).numpy(), bboxes.numpy(), (3, 3), 0.25).reshape(50, -1)
+    buf = torch.full((50, 2304 + 40), -7.0, device=DEV)
+    o.roi_fwd(fm.to(DEV), bboxes.to(DEV), (3, 3), 0.25, buf)
+    assert np.array_equal(t2n(buf[:, :2304]), want) and bool((buf[:, 2304:] == -7).all())
+
+
+def test_bbox_encoder_and_affine_cols():
+    o = ops()
+    sd = {k: v for k, v in synth.make_state_dict(123).items()}
+    _, bboxes, _, _ = synth.gen(3, 0, 8, seed=3, img=256, counts=[11, 1, 30])
+    want = O.bbox_encoder(bboxes.numpy(), {k: v.numpy() for k, v in sd.items()})
+    rv, rm = sd["bbox_feat_encoder.1.running_var"], sd["bbox_feat_encoder.1.running_mean"]
+    scale = sd["bbox_feat_encoder.1.weight"] / torch.sqrt(rv + 1e-5)
+    shift = sd["bbox_feat_encoder.1.bias"] - rm * scale
+    out = torch.zeros((42, 40), device=DEV)
+    o.bbox_enc_fwd(bboxes.to(DEV), sd["bbox_feat_encoder.0.weight"].to(DEV), sd["bbox_feat_encoder.0.bias"].to(DEV),
+                   scale.to(DEV), shift.to(DEV), out[:, 4:36])
+    assert rel_err(t2n(out[:, 4:36]), want) < 1e-5 and bool((out[:, :4] == 0).all()) and bool((out[:, 36:] == 0).all())
+    x = torch.randn(42, 7)
+    o.affine_cols_fwd(x.to(DEV), scale[:7].to(DEV), shift[:7].to(DEV), out[:, 10:])
+    assert np.allclose(t2n(out[:, 10:17]), x.numpy() * scale[:7].numpy() + shift[:7].numpy(), rtol=1e-6, atol=1e-6)
+
+
+@pytest.mark.parametrize("M,K,N", [(1, 5, 32), (77, 608, 388), (1440, 992, 992), (130, 992, 4)])
+def test_linear_kernel(M, K, N):
+    o = ops()
+    g = torch.Generator().manual_seed(5)
+    x, w = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g) / K ** 0.5
+    b, sc, sh = torch.randn(N, generator=g), 0.5 + torch.rand(N, generator=g), torch.randn(N, generator=g)
+    res = torch.randn(M, N, generator=g)
+    want = np.maximum((O.linear(x.numpy(), w.numpy(), b.numpy()) * sc.numpy() + sh.numpy()) + res.numpy(), 0)
+    y = o.linear_fwd(x.to(DEV), w.to(DEV), b.to(DEV), sc.to(DEV), sh.to(DEV), res=res.to(DEV), relu=True)
+    assert rel_err(t2n(y), want) < 1e-5
+    y = o.linear_fwd(x.to(DEV), w.to(DEV))
+    assert rel_err(t2n(y), O.linear(x.numpy(), w.numpy())) < 1e-5
+
+
+def test_gat_layer_golden_edge_cases_and_heads():
+    """The layer fixture of the live reference: arbitrary (non-window) ids, an all -1 row, partial padding,
+    attention weights, and the 2-head composition."""
+    from cova_b200.models import GraphAttentionLayer
+    g = load_golden("g_gat")
+    layer = GraphAttentionLayer(96, 64).to(DEV).eval()
+    layer.load_state_dict({"W_i.weight": torch.from_numpy(g["W_i"]), "W_j.weight": torch.from_numpy(g["W_j"]),
+                           "attention_layer.weight": torch.from_numpy(g["att_w"]),
+                           "attention_layer.bias": torch.from_numpy(g["att_b"])})
+    h, ci = torch.from_numpy(g["h"]).to(DEV), torch.from_numpy(g["ci"]).to(DEV)
+    with torch.no_grad():
+        out, attn = layer(h, ci, return_attn_wts=True)
+        out_only = layer(h, ci)
+    assert np.abs(t2n(out) - g["out"]).max() < 5e-6 and np.abs(t2n(attn) - g["attn"]).max() < 2e-6
+    assert torch.equal(out, out_only)
+    assert bool((out[3] == 0).all()) and np.allclose(t2n(attn[3]), 0.1)          # all -1 row: uniform, exact 0 out
+    outs = []
+    for i in range(2):
+        hd = GraphAttentionLayer(96, 32).to(DEV).eval()
+        hd.load_state_dict({"W_i.weight": torch.from_numpy(g[f"h{i}_W_i"]), "W_j.weight": torch.from_numpy(g[f"h{i}_W_j"]),
+                            "attention_layer.weight": torch.from_numpy(g[f"h{i}_att_w"]),
+                            "attention_layer.bias": torch.from_numpy(g[f"h{i}_att_b"])})
+        with torch.no_grad():
+            outs.append(hd(h, ci))
+    assert np.abs(t2n(torch.cat(outs, 1)) - g["out_2head"]).max() < 5e-6
+
+
+@pytest.mark.parametrize("T,K,Hd", [(5, 1, 4), (300, 48, 192), (1000, 128, 384)])
+def test_gat_kernel_shapes_vs_oracle(T, K, Hd):
+    """K=1, the stress K=48 and the kernel's K limit; ids far apart force the un-staged (direct L2) gather."""
+    o = ops()
+    g = torch.Generator().manual_seed(6)
+    h = torch.randn(T, 64, generator=g)
+    Wi, Wj = torch.randn(Hd, 64, generator=g) / 8, torch.randn(Hd, 64, generator=g) / 8
+    aw, ab = torch.randn(1, 2 * Hd, generator=g) / Hd ** 0.5, torch.randn(1, generator=g)
+    ci = torch.randint(-1, T, (T, K), generator=g)
+    want, want_attn = O.gat(h.numpy(), ci.numpy(), Wi.numpy(), Wj.numpy(), aw.numpy(), ab.numpy(), return_attn_wts=True)
+    whj = (h @ Wj.T).contiguous()
+    s, t = (h @ Wi.T) @ aw[0, :Hd], whj @ aw[0, Hd:]
+    out = torch.empty(T, Hd, device=DEV)
+    attn = o.gat_fwd(whj.to(DEV), s.to(DEV), t.to(DEV), float(ab), 0.2, ci.to(DEV), out, want_attn=True)
+    assert np.abs(t2n(out) - want).max() < 2e-5 and np.abs(t2n(attn) - want_attn).max() < 5e-6
+
+
+# ----------------------------------------------------------------------------- whole forward vs the live reference
+ENGINES = [("simt", "fp32", 1e-5, 2e-5), ("tcgen05", "fp32", 1e-4, 1e-4), ("tcgen05", "bf16", 2e-2, 1e-3)]
+
+
+@pytest.mark.parametrize("engine,precision,tol_fm,tol_logits", ENGINES)
+def test_forward_small_golden(engine, precision, tol_fm, tol_logits):
+    g = load_golden("g_small_r18_img128")
+    m, _ = make_model(engine, precision, img=128)
+    inp = to_dev(synth.gen(2, 12, 8, seed=0, img=128))
+    with torch.no_grad():
+        r = m._native.forward(*inp, return_intermediates=True)
+        logits = m(*inp)
+    assert rel_err(t2n(r["fm"]).transpose(0, 3, 1, 2), g["fm"]) < tol_fm
+    assert rel_err(t2n(r["own"]), g["own"]) < tol_fm
+    assert rel_err(t2n(r["ctx"]), g["ctx"]) < max(tol_fm, 2e-5)
+    assert rel_err(t2n(logits), g["logits"]) < tol_logits
+
+
+@pytest.mark.parametrize("engine,precision,tol_fm,tol_logits", ENGINES)
+def test_forward_config1_golden(engine, precision, tol_fm, tol_logits):
+    """BASELINE.json config 1: one 1280x1280 page, N=32, K=8 - the reference's own CPU-runnable case."""
+    g = load_golden("g_c1_r18_img1280")
+    m, _ = make_model(engine, precision)
+    inp = to_dev(synth.gen(1, 32, 8, seed=0, img=1280))
+    with torch.no_grad():
+        r = m._native.forward(*inp, return_intermediates=True)
+    assert rel_err(t2n(r["fm"]).transpose(0, 3, 1, 2)[:, :, ::8, ::8], g["fm_sample"]) < tol_fm
+    assert rel_err(t2n(r["own"]), g["own"]) < tol_fm
+    assert rel_err(t2n(r["logits"]), g["logits"]) < tol_logits
+
+
+@pytest.mark.parametrize("engine,precision,tol_fm,tol_logits", ENGINES)
+def test_forward_ragged_pages_golden(engine, precision, tol_fm, tol_logits):
+    g = load_golden("g_ragged_r18_img256")
+    m, _ = make_model(engine, precision, img=256)
+    inp = to_dev(synth.gen(3, 0, 24, seed=3, img=256, counts=[11, 1, 30]))
+    with torch.no_grad():
+        logits = m(*inp)
+        vis, bb = m._get_visual_features(inp[0], inp[1]), m._get_bbox_features(inp[1])
+        own = torch.cat((vis, bb, m.bn_additional_feat(inp[2])), 1)
+        ctx, attn = m.gat(own, inp[3], return_attn_wts=True)      # extract_attn_wts_and_visualize.py:117-124
+    assert rel_err(t2n(logits), g["logits"]) < tol_logits
+    assert rel_err(t2n(vis), g["visual"]) < tol_fm and rel_err(t2n(bb), g["bbox"]) < 1e-5
+    assert rel_err(t2n(ctx), g["ctx"]) < max(tol_fm, 2e-5) and np.abs(t2n(attn) - g["attn"]).max() < max(tol_fm, 1e-5)
+
+
+def test_forward_roi_align_variant_golden():
+    g = load_golden("g_align_r18_img256")
+    m, _ = make_model("simt", img=256, roi_mode="align")
+    with torch.no_grad():
+        logits = m(*to_dev(synth.gen(2, 20, 8, seed=4, img=256)))
+    assert rel_err(t2n(logits), g["logits"]) < 2e-5
+
+
+def test_forward_resnet50_golden():
+    g = load_golden("g_r50_img128")
+    m, _ = make_model("simt", img=128, backbone="resnet50")
+    with torch.no_grad():
+        r = m._native.forward(*to_dev(synth.gen(1, 16, 8, seed=5, img=128)), return_intermediates=True)
+    assert rel_err(t2n(r["fm"]).transpose(0, 3, 1, 2), g["fm"]) < 2e-5
+    assert rel_err(t2n(r["logits"]), g["logits"]) < 5e-5
+
+
+def test_forward_constructor_variants_golden():
+    g = load_golden("g_noctx_nobbox_roi2x5")
+    m, _ = make_model("simt", img=128, roi=(2, 5), use_context=False, hidden=0, bbhd=0)
+    images, bboxes, add, _ = to_dev(synth.gen(2, 9, 0, seed=6, img=128))
+    with torch.no_grad():
+        out = m(images, bboxes, add, torch.empty((18, 0), dtype=torch.long, device=DEV))
+    assert rel_err(t2n(out), g["logits"]) < 2e-5
+    g = load_golden("g_addfeat7")
+    m, _ = make_model("simt", img=128, n_add=7)
+    images, bboxes, _, ci = to_dev(synth.gen(2, 9, 8, seed=7, img=128))
+    with torch.no_grad():
+        out = m(images, bboxes, torch.from_numpy(g["additional_feats"]).to(DEV), ci)
+    assert rel_err(t2n(out), g["logits"]) < 2e-5
+
+
+def test_two_head_forward_vs_oracle():
+    m, sd = make_model("simt", img=128, n_heads=2)
+    inp = synth.gen(2, 12, 8, seed=9, img=128)
+    with torch.no_grad():
+        r = m._native.forward(*to_dev(inp), return_intermediates=True)
+    own = t2n(r["own"])
+    heads = [(sd[f"gat.heads.{i}.W_i.weight"], sd[f"gat.heads.{i}.W_j.weight"],
+              sd[f"gat.heads.{i}.attention_layer.weight"], sd[f"gat.heads.{i}.attention_layer.bias"]) for i in range(2)]
+    want = O.gat_multihead(own, inp[3].numpy(), heads)
+    assert rel_err(t2n(r["ctx"]), want) < 2e-5
+    assert rel_err(t2n(r["logits"]), O.decoder(np.concatenate([own, want], 1), sd)) < 2e-5
+
+
+# ----------------------------------------------------------------------------- full BASELINE size: properties
+def test_full_size_properties_config2():
+    """BASELINE config 2 (B=16, 1280^2, N=90, K=24) is too big for the CPU oracle in a test, so check
+    size-independent properties: (1) the two engines agree, (2) a page's logits do not depend on the rest of the
+    batch (pages are independent units in eval mode), (3) RoIPool of the produced feature map is
+    bit-identical to the oracle's RoIPool on a sample of boxes, (4) determinism."""
+    B, N, K = 16, 90, 24
+    inp = synth.gen(B, N, K, seed=1)
+    dinp = to_dev(inp)
+    m_tc, _ = make_model("tcgen05", "fp32")
+    m_si, _ = make_model("simt")
+    with torch.no_grad():
+        r = m_tc._native.forward(*dinp, return_intermediates=True)
+        l_tc, l_tc2, l_si = r["logits"], m_tc(*dinp), m_si(*dinp)
+        p = 11
+        rows = slice(p * N, (p + 1) * N)
+        ci = dinp[3][rows].clone()
+        ci[ci >= 0] -= p * N
+        bb = dinp[1][rows].clone()
+        bb[:, 0] = 0
+        l_page = m_tc(dinp[0][p:p + 1], bb, dinp[2][rows], ci)
+    assert torch.equal(l_tc, l_tc2)
+    assert rel_err(t2n(l_tc), t2n(l_si)) < 1e-4
+    assert rel_err(t2n(l_page), t2n(l_tc[rows])) < 1e-5
+    sample = torch.arange(0, B * N, 37)
+    fm_nchw = t2n(r["fm"]).transpose(0, 3, 1, 2)
+    want = O.roi_pool(fm_nchw, inp[1][sample].numpy(), (3, 3), 0.25).reshape(len(sample), -1)
+    assert np.array_equal(t2n(r["own"][sample.to(DEV), :576]), want)
+
+
+# ----------------------------------------------------------------------------- training path (composite + native RoI)
+def test_train_step_matches_reference_grads():
+    """`train.py:45-60` semantics on the autograd path: train-mode BN (batch stats), dropout off, CE(sum)."""
+    from cova_b200.models import CoVA
+    g = load_golden("g_train_r18_img128")
+    m = CoVA((3, 3), 128, 4, True, 384, 32, 0, 0.0, None, pretrained=False)
+    m.load_state_dict(synth.make_state_dict(123), strict=True)
+    m = m.to(DEV).train()
+    images, bboxes, add, ci, labels = to_dev(synth.gen(2, 12, 8, seed=8, img=128, with_labels=True))
+    out = m(images, bboxes, add, ci)
+    loss = torch.nn.CrossEntropyLoss(reduction="sum")(out, labels)
+    loss.backward()
+    assert rel_err(t2n(out), g["logits"]) < 1e-4 and abs(float(loss) - float(g["loss"])) < 1e-3 * abs(float(g["loss"]))
+    grads = dict(m.named_parameters())
+    for k in [k for k in g if k.startswith("grad:")]:
+        assert rel_err(t2n(grads[k[5:]].grad), g[k]) < 2e-3, k
+    sd = m.state_dict()
+    for k in [k for k in g if k.startswith("buf:")]:
+        assert rel_err(t2n(sd[k[4:]]), g[k]) < 1e-4, k
+    opt = torch.optim.Adam(m.parameters(), lr=1e-3)
+    first = float(loss)
+    for _ in range(5):
+        opt.zero_grad()
+        l2 = torch.nn.CrossEntropyLoss(reduction="sum")(m(images, bboxes, add, ci), labels)
+        l2.backward()
+        opt.step()
+    assert float(l2) < first
+    m.eval()                                   # weights changed -> the native path must rebuild its caches
+    with torch.no_grad():
+        a = m(images, bboxes, add, ci)
+        m.engine = "simt"
+        b = m(images, bboxes, add, ci)
+    assert rel_err(t2n(a), t2n(b)) < 1e-4
+
+
+def test_inputs_rejected_loudly():
+    o = ops()
+    with pytest.raises(RuntimeError, match="CUDA tensor"):
+        o.roi_fwd(torch.zeros(1, 8, 8, 64), torch.zeros(1, 5), (3, 3), 0.25, torch.zeros(1, 576))
+    with pytest.raises(RuntimeError, match="multiple of 64"):
+        o.roi_fwd(torch.zeros(1, 8, 8, 48, device=DEV), torch.zeros(1, 5, device=DEV), (3, 3), 0.25,
+                  torch.zeros(1, 432, device=DEV))

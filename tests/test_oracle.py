@@ -119,3 +119,14 @@ def test_train_mode_forward():
     out = O.cova_forward(np_sd(), images.numpy(), bboxes.numpy(), add.numpy(), ci.numpy(), train=True)
     assert rel_err(out, g["logits"]) < 2e-5
     assert np.array_equal(labels.numpy(), g["labels"])
+
+
+def test_torch_port_matches_golden():
+    """The CPU-baseline port (`oracle/torch_port.py`, timed by bench.py) reproduces the live reference."""
+    from oracle import torch_port as TP
+    for name, args, kw in (("g_small_r18_img128", (2, 12, 8), dict(seed=0, img=128)),
+                           ("g_ragged_r18_img256", (3, 0, 24), dict(seed=3, img=256, counts=[11, 1, 30]))):
+        out = TP.forward(synth.make_state_dict(123), *synth.gen(*args, **kw))
+        assert rel_err(out.numpy(), load_golden(name)["logits"]) < 5e-6
+    out = TP.forward(synth.make_state_dict(123, backbone="resnet50"), *synth.gen(1, 16, 8, seed=5, img=128))
+    assert rel_err(out.numpy(), load_golden("g_r50_img128")["logits"]) < 1e-5
