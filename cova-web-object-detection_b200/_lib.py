@@ -59,6 +59,7 @@ SIGNATURES = {
     "cova_stem_fwd": (_I, [_P, _I, _I, _I, _P, _P, _P, _I, _P, _P, _I, _P]),
     "cova_conv3x3_bn_act_fwd": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _I, _I, _P, _P, _I, _P]),
     "cova_pack_conv_weight": (_I, [_P, _I, _I, _I, _I, _P, _P, _P, _P]),
+    "cova_pack_stem_weight": (_I, [_P, _P, _P]),
     "cova_roi_fwd": (_I, [_P, _I, _I, _I, _I, _P, _I, _I, _I, _F, _I, _I, _P, _L, _P, _P]),
     "cova_bbox_enc_fwd": (_I, [_P, _I, _P, _P, _P, _P, _I, _P, _L, _P]),
     "cova_affine_cols_fwd": (_I, [_P, _I, _I, _L, _P, _P, _P, _L, _P]),

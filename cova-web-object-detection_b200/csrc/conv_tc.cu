@@ -6,11 +6,14 @@
 // GEMM view per output tile (8 wide x 16 high = 128 pixels = UMMA M):
 //     D[128 px, 64 cout] = sum over 9 taps (r,s):  A_rs[128 px, 64 cin] * W_rs[64 cin, 64 cout]
 // Activations are NHWC bf16 planes, so a pixel's 64 input channels are exactly one 128-byte swizzle row and
-// "im2col" is nothing but a shifted TMA box: for horizontal tap s one 4-D box {64 c, 8 w, 18 h} at
-// (w0+s-1, h0-1) lands in shared memory as 144 rows x 128 B; the three vertical taps r are the 1024-B-aligned
-// sub-views [r*8, r*8+128) of those rows (r*1024 bytes = one swizzle atom per 8 rows), so one load feeds three
-// taps.  Conv zero padding = TMA out-of-bounds zero fill.  L2->smem traffic is 3*144/128 = 3.4x the tile
-// (a per-tap load would be 9x); HBM traffic stays 1x because neighbouring tiles share halos through L2.
+// "im2col" is nothing but a shifted VIEW of one staged halo patch: ONE 4-D TMA box {64 c, 10 w, 18 h} at
+// (w0-1, h0-1) lands in shared memory as 180 rows x 128 B (row = hh*10 + ww), and tap (r,s) is the UMMA
+// descriptor {start = patch + (r*10+s)*128 B, 8-row-group stride = 10 rows = 1280 B}: M row m = py*8+px reads
+// patch row (py+r)*10 + (px+s).  The hardware applies the 128-B swizzle on absolute shared-memory address bits,
+// so a start that is only 128-B aligned and a non-1024 group stride address the TMA-written data correctly
+// (measured with tools/probe_umma.cu -> profiles/r01a_probe_umma_descriptor.txt).  Conv zero padding = TMA
+// out-of-bounds zero fill.  L2->smem traffic is 180/128 = 1.41x the tile (a per-tap load would be 9x); HBM
+// traffic stays 1x because neighbouring tiles share halos through L2.
 //
 // fp32-parity mode (SPLIT): x = hi + lo (two bf16 planes), w = hi + lo; D = Ahi*Whi + Alo*Whi + Ahi*Wlo with
 // fp32 accumulation in TMEM: ~2^-17 relative per product, i.e. an fp32 convolution to ~1e-5, at 3 MMAs
@@ -21,8 +24,12 @@
 //   warp 1   TMEM alloc + single-thread tcgen05.mma issue; tcgen05.commit releases ring slots / publishes tiles
 //   warps 2-5 epilogue: tcgen05.ld (lane = pixel, column = cout), BN scale/shift, residual, ReLU, NHWC stores
 // TMEM accumulator is double-buffered (2 x 64 columns): the epilogue of tile i overlaps the MMAs of tile i+1.
+// The activation ring holds single PLANES (23 KB slots): per tile the hi plane feeds Ahi*Whi + Ahi*Wlo (72 MMAs),
+// the lo plane Alo*Whi (36 MMAs); 3 slots (split) / 6 slots (bf16) keep >= 2 loads in flight next to the
+// 144 KB / 72 KB resident filter.
 //
-// Bound: tensor pipe in SPLIT mode (108 MMAs x 32 clk = 3456 clk/tile), HBM in bf16 mode.
+// Bound: tensor pipe in SPLIT mode (108 MMAs x 32 clk = 3456 clk/tile); bf16 mode sits between the tensor pipe
+// (1152 clk/tile) and HBM (26 MB in + out per page).
 // Algorithmic work: 2*9*64*64 = 73,728 FLOP per output pixel (7.55 GFLOP per 320x320 page).
 #include "common.cuh"
 #include "ptx.cuh"
@@ -32,8 +39,10 @@ namespace cova {
 
 constexpr int CT_C = 64;                       // Cin = Cout
 constexpr int CT_TW = 8, CT_TH = 16;           // output tile
-constexpr int CT_HALO_ROWS = (CT_TH + 2) * CT_TW;          // 144 smem rows per load
-constexpr int CT_PLANE_BYTES = CT_HALO_ROWS * 128;         // 18,432
+constexpr int CT_HW = CT_TW + 2, CT_HH = CT_TH + 2;        // halo patch 10 x 18 pixels
+constexpr int CT_PATCH_BYTES = CT_HW * CT_HH * 128;        // 23,040 bytes landed per plane load
+constexpr int CT_SLOT_BYTES = 23 * 1024;                   // ring slot (1024-B aligned for the swizzle atoms)
+constexpr int CT_GROUP_STRIDE = CT_HW * 128;               // 8-row-group stride of a tap view: one patch row
 constexpr int CT_W_PLANE_BYTES = 9 * CT_C * 128;           // 73,728 (9 taps x 64 cout rows x 128 B)
 constexpr int CT_THREADS = 192;
 constexpr int CT_TMEM_COLS = 128;              // 2 accumulator buffers x 64 fp32 columns
@@ -41,8 +50,8 @@ constexpr int CT_TMEM_COLS = 128;              // 2 accumulator buffers x 64 fp3
 template <bool SPLIT>
 struct ConvTcCfg {
   static constexpr int NPLANE = SPLIT ? 2 : 1;
-  static constexpr int NSTAGE = SPLIT ? 2 : 6;
-  static constexpr int STAGE_BYTES = CT_PLANE_BYTES * NPLANE;
+  static constexpr int NSTAGE = SPLIT ? 3 : 6;
+  static constexpr int STAGE_BYTES = CT_SLOT_BYTES;
   static constexpr int W_BYTES = CT_W_PLANE_BYTES * NPLANE;
   static constexpr int SMEM_BYTES = W_BYTES + NSTAGE * STAGE_BYTES + 1024 /*tail*/ + 1024 /*align slack*/;
 };
@@ -110,67 +119,71 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_cons
   const uint32_t tmem_base = tail.tmem_base;
 
   if (warp == 0) {
-    // ======================= TMA producer =======================
-    if (lane == 0) {
+    // ======================= TMA producer (warp converged; one elected lane issues) =======================
+    if (ptx::elect_one()) {
       // resident filter: 9 taps x 64 rows per plane, three 192-row boxes each
       ptx::mbar_arrive_expect_tx(&tail.wbar, Cfg::W_BYTES);
       for (int i = 0; i < 3; ++i) {
         ptx::tma_load_2d(sm_w + i * 192 * 128, &tm_w_hi, &tail.wbar, 0, i * 192);
         if (SPLIT) ptx::tma_load_2d(sm_w + CT_W_PLANE_BYTES + i * 192 * 128, &tm_w_lo, &tail.wbar, 0, i * 192);
       }
-      uint32_t stage = 0, phase = 0;
-      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-        const int b = tile / (p.tiles_h * p.tiles_w);
-        const int th = (tile / p.tiles_w) % p.tiles_h, tw = tile % p.tiles_w;
-        const int h0 = th * CT_TH, w0 = tw * CT_TW;
-        for (int s = 0; s < 3; ++s) {
-          ptx::mbar_wait(&tail.empty[stage], phase ^ 1);
-          ptx::mbar_arrive_expect_tx(&tail.full[stage], Cfg::STAGE_BYTES);
-          unsigned char* dst = sm_a + stage * Cfg::STAGE_BYTES;
-          ptx::tma_load_4d(dst, &tm_x_hi, &tail.full[stage], 0, w0 + s - 1, h0 - 1, b);
-          if (SPLIT) ptx::tma_load_4d(dst + CT_PLANE_BYTES, &tm_x_lo, &tail.full[stage], 0, w0 + s - 1, h0 - 1, b);
-          if (++stage == Cfg::NSTAGE) { stage = 0; phase ^= 1; }
+    }
+    __syncwarp();
+    uint32_t stage = 0, phase = 0;
+    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+      const int b = tile / (p.tiles_h * p.tiles_w);
+      const int th = (tile / p.tiles_w) % p.tiles_h, tw = tile % p.tiles_w;
+      const int h0 = th * CT_TH, w0 = tw * CT_TW;
+      for (int pl = 0; pl < Cfg::NPLANE; ++pl) {
+        ptx::mbar_wait(&tail.empty[stage], phase ^ 1);
+        if (ptx::elect_one()) {
+          ptx::mbar_arrive_expect_tx(&tail.full[stage], CT_PATCH_BYTES);
+          ptx::tma_load_4d(sm_a + stage * Cfg::STAGE_BYTES, pl == 0 ? &tm_x_hi : &tm_x_lo, &tail.full[stage], 0, w0 - 1,
+                           h0 - 1, b);
         }
+        __syncwarp();
+        if (++stage == Cfg::NSTAGE) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
-    // ======================= MMA issuer (one thread) =======================
-    if (lane == 0) {
-      constexpr uint32_t idesc = ptx::umma_idesc_bf16(128, CT_C);
-      const uint32_t w_addr = ptx::smem_u32(sm_w), a_addr = ptx::smem_u32(sm_a);
-      ptx::mbar_wait(&tail.wbar, 0);
-      uint32_t stage = 0, phase = 0, it = 0;
-      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
-        const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
-        ptx::mbar_wait(&tail.tmem_empty[acc], acc_phase ^ 1);
+    // ======================= MMA issuer (warp converged; one elected lane issues) =======================
+    // Descriptors differ only in their 14-bit start-address field, so each MMA costs two 32-bit adds on
+    // warp-uniform values (the elect.sync guard lets the compiler keep them in uniform registers; an
+    // `if (lane == 0)` region would wrap every UTCHMMA in a per-lane serialisation loop).
+    constexpr uint32_t idesc = ptx::umma_idesc_bf16(128, CT_C);
+    const uint64_t da0 = ptx::umma_desc_sw128(ptx::smem_u32(sm_a), CT_GROUP_STRIDE);
+    const uint64_t db0 = ptx::umma_desc_sw128(ptx::smem_u32(sm_w), 1024);
+    const uint32_t da_hi32 = (uint32_t)(da0 >> 32), db_hi32 = (uint32_t)(db0 >> 32);
+    const uint32_t da_lo0 = (uint32_t)da0, db_lo0 = (uint32_t)db0;
+    ptx::mbar_wait(&tail.wbar, 0);
+    uint32_t stage = 0, phase = 0, it = 0;
+    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
+      const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
+      ptx::mbar_wait(&tail.tmem_empty[acc], acc_phase ^ 1);
+      ptx::tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * CT_C;
+      for (int pl = 0; pl < Cfg::NPLANE; ++pl) {   // pl 0: A = hi plane (x Whi, x Wlo); pl 1: A = lo plane (x Whi)
+        ptx::mbar_wait(&tail.full[stage], phase);
         ptx::tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * CT_C;
-        uint32_t accumulate = 0;
-        for (int s = 0; s < 3; ++s) {
-          ptx::mbar_wait(&tail.full[stage], phase);
-          ptx::tc_fence_after();
-          const uint32_t a_hi = a_addr + stage * Cfg::STAGE_BYTES;
+        if (ptx::elect_one()) {
+          const uint32_t a_lo = da_lo0 + ((stage * Cfg::STAGE_BYTES) >> 4);
 #pragma unroll
-          for (int r = 0; r < 3; ++r) {
-            const uint32_t w_hi = w_addr + (r * 3 + s) * (CT_C * 128);
+          for (int tap = 0; tap < 9; ++tap) {
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk) {   // 4 x K=16 bf16 (32 B) inside the 128-B swizzle row
-              const uint64_t da_hi = ptx::umma_desc_sw128(a_hi + r * 1024 + kk * 32, 1024);
-              const uint64_t db_hi = ptx::umma_desc_sw128(w_hi + kk * 32, 1024);
-              ptx::umma_bf16(d_tmem, da_hi, db_hi, idesc, accumulate);
-              accumulate = 1;
-              if (SPLIT) {
-                const uint64_t da_lo = ptx::umma_desc_sw128(a_hi + CT_PLANE_BYTES + r * 1024 + kk * 32, 1024);
-                const uint64_t db_lo = ptx::umma_desc_sw128(w_hi + CT_W_PLANE_BYTES + kk * 32, 1024);
-                ptx::umma_bf16(d_tmem, da_lo, db_hi, idesc, 1);
-                ptx::umma_bf16(d_tmem, da_hi, db_lo, idesc, 1);
-              }
+              const uint64_t da = ((uint64_t)da_hi32 << 32) |
+                                  (uint32_t)(a_lo + ((((tap / 3) * CT_HW + (tap % 3)) * 128 + kk * 32) >> 4));
+              const uint32_t b_lo = db_lo0 + ((tap * (CT_C * 128) + kk * 32) >> 4);
+              ptx::umma_bf16(d_tmem, da, ((uint64_t)db_hi32 << 32) | b_lo, idesc, (pl | tap | kk) != 0);
+              if (SPLIT && pl == 0)
+                ptx::umma_bf16(d_tmem, da, ((uint64_t)db_hi32 << 32) | (uint32_t)(b_lo + (CT_W_PLANE_BYTES >> 4)), idesc, 1);
             }
           }
-          ptx::umma_commit(&tail.empty[stage]);          // ring slot free once these MMAs have read it
-          if (s == 2) ptx::umma_commit(&tail.tmem_full[acc]);   // accumulator complete
-          if (++stage == Cfg::NSTAGE) { stage = 0; phase ^= 1; }
+          ptx::umma_commit(&tail.empty[stage]);                           // slot free once these MMAs have read it
+          if (pl == Cfg::NPLANE - 1) ptx::umma_commit(&tail.tmem_full[acc]);   // accumulator complete
         }
+        __syncwarp();
+        if (++stage == Cfg::NSTAGE) { stage = 0; phase ^= 1; }
       }
     }
   } else {
@@ -295,7 +308,7 @@ int conv3x3_tc(const void* x_hi, const void* x_lo, int split, int B, int H, int 
   CUtensorMap tx_hi, tx_lo, tw_hi, tw_lo;
   const uint64_t xd[4] = {(uint64_t)CT_C, (uint64_t)W, (uint64_t)H, (uint64_t)B};
   const uint64_t xs[3] = {(uint64_t)CT_C * 2, (uint64_t)W * CT_C * 2, (uint64_t)H * W * CT_C * 2};
-  const uint32_t xb[4] = {CT_C, CT_TW, CT_TH + 2, 1};
+  const uint32_t xb[4] = {CT_C, CT_HW, CT_HH, 1};
   const uint64_t wd[2] = {(uint64_t)CT_C, (uint64_t)9 * CT_C};
   const uint64_t ws[1] = {(uint64_t)CT_C * 2};
   const uint32_t wb[2] = {CT_C, 192};

@@ -28,7 +28,7 @@ constexpr int GAT_STAGE_BYTES = 96 * 1024;
 __global__ void __launch_bounds__(GAT_THREADS)
 gat_fwd_kernel(const float* __restrict__ whj, int64_t ld_whj, const float* __restrict__ s_vec,
                const float* __restrict__ t_vec, int64_t ld_st, float att_b, float alpha, const int64_t* __restrict__ ctx, int T,
-               int K, int Hd, float* __restrict__ out, int64_t ld_out, float* __restrict__ attn, int stage_ok) {
+               int K, int Hd, float* __restrict__ out, int64_t ld_out, float* __restrict__ attn, int stage_ok, int out_vec) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float* stage = reinterpret_cast<float*>(smem_raw);
   __shared__ uint64_t bar;
@@ -144,7 +144,13 @@ gat_fwd_kernel(const float* __restrict__ whj, int64_t ld_whj, const float* __res
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       const int v = v0 + lane + 32 * q;
-      if (v < nvec) *reinterpret_cast<float4*>(out + (size_t)i * ld_out + 4 * v) = acc[q];
+      if (v >= nvec) continue;
+      float* o = out + (size_t)i * ld_out + 4 * v;
+      if (out_vec) {
+        *reinterpret_cast<float4*>(o) = acc[q];
+      } else {   // output columns not 16-byte aligned (e.g. ctx lands at column n_feat of an odd-width row)
+        o[0] = acc[q].x; o[1] = acc[q].y; o[2] = acc[q].z; o[3] = acc[q].w;
+      }
     }
   }
 }
@@ -160,12 +166,13 @@ extern "C" int cova_gat_fwd(const float* whj, int64_t ld_whj, const float* s, co
   COVA_REQUIRE(whj && s && t && out && (ctx_idx || K == 0), "cova_gat_fwd: null pointer");
   COVA_REQUIRE(ld_st >= 1, "cova_gat_fwd: ld_st must be >= 1");
   COVA_REQUIRE(K >= 1 && K <= GAT_KMAX, "cova_gat_fwd: K=%d outside [1,%d]", K, GAT_KMAX);
-  COVA_REQUIRE(Hd % 4 == 0 && ld_whj % 4 == 0 && ld_out % 4 == 0 && ld_whj >= Hd && ld_out >= Hd,
-               "cova_gat_fwd: Hd/ld must be multiples of 4 (float4 rows)");
-  COVA_REQUIRE(((uintptr_t)whj & 15) == 0 && ((uintptr_t)out & 15) == 0, "cova_gat_fwd: whj/out must be 16-byte aligned");
+  COVA_REQUIRE(Hd % 4 == 0 && ld_whj % 4 == 0 && ld_whj >= Hd && ld_out >= Hd,
+               "cova_gat_fwd: Hd and ld_whj must be multiples of 4 (float4 rows), ld >= Hd");
+  COVA_REQUIRE(((uintptr_t)whj & 15) == 0, "cova_gat_fwd: whj must be 16-byte aligned");
+  const int out_vec = (ld_out % 4 == 0) && (((uintptr_t)out & 15) == 0);
   COVA_CUDA_OK(cudaFuncSetAttribute(gat_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GAT_STAGE_BYTES));
   gat_fwd_kernel<<<ceil_div(T, GAT_E), GAT_THREADS, GAT_STAGE_BYTES, (cudaStream_t)stream>>>(
-      whj, ld_whj, s, t, ld_st, att_b, alpha, ctx_idx, T, K, Hd, out, ld_out, attn, 1);
+      whj, ld_whj, s, t, ld_st, att_b, alpha, ctx_idx, T, K, Hd, out, ld_out, attn, 1, out_vec);
   COVA_LAUNCH_OK();
   return COVA_OK;
 }

@@ -1,0 +1,366 @@
+// A2 stem on the 5th-gen tensor cores: conv 7x7 s2 p3 (3->64) + folded BN + ReLU + maxpool 3x3 s2 p1, ONE kernel
+// (replaces `convnet[0:4]`, `/root/reference/models.py:49-51`, applied `:125`).  NCHW fp32 images in, NHWC planes out.
+//
+// The convolution is an implicit GEMM whose A operand is never materialised ("im2col staged in shared memory"
+// degenerates to staging the raw image rows once):
+//   * converter warps read image rows (NCHW fp32, coalesced along x) and write them to a shared-memory ring as
+//     4-channel bf16 pixels (8 B: c0,c1,c2,0), hi plane and lo plane (x = hi + lo, split-bf16);
+//   * for filter row r the GEMM row of output pixel ox is the 8 input pixels 2ox-3 .. 2ox+4 of image row 2oy+r-3:
+//     32 K-elements (s = 0..7, c = 0..3; the s = 7 and c = 3 weights are zero) that sit CONTIGUOUSLY in the ring row,
+//     16 B further along for each next output pixel (stride 2 x 8 B).  A SWIZZLE_NONE K-major tcgen05 descriptor
+//     with {rows 16 B apart (core matrix), K-chunk stride LBO = 16 B, 8-row-group stride SBO = 128 B} reads exactly
+//     that sliding window - K-chunk 1 of row j aliases K-chunk 0 of row j+1 (tools/probe_umma_noswz.cu).
+//     So one conv row of 128 output pixels = 7 filter rows x 2 MMAs (K = 16 each) on the ring rows, no copies.
+//   * accumulators (128 px x 64 cout fp32) live in TMEM, double buffered; epilogue warps apply BN + ReLU and
+//     max-pool on the fly: horizontal 3-max with warp shuffles (lane = conv pixel), vertical 3-max as a running
+//     maximum in registers while the CTA marches down conv rows; only pooled pixels are written.
+//
+// Work decomposition: CTA = (page, band of pooled rows), processed strip by strip (128 conv columns = 64 pooled
+// columns).  The right-most conv column of strip i is kept per conv row in shared memory and is the left
+// neighbour of strip i+1, so no conv column is recomputed; each band recomputes one conv row (its top halo).
+// HBM traffic: image read once (+2 % strip / +3.5 % band halos), pooled map written once.
+//
+// Bound: tensor pipe in fp32-parity mode (42 MMAs x 32 clk = 1344 clk per 128 conv pixels).
+// Algorithmic work: 2*64*147 FLOP per conv pixel (7.707 GFLOP per 1280x1280 page).
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace cova {
+
+constexpr int SX_TM = 128;                 // conv pixels per MMA tile (one conv-row segment)
+constexpr int SX_NPX = 264;                // staged input pixels per ring row (2*127 + 8 = 262, padded)
+constexpr int SX_ROW_BYTES = SX_NPX * 8;   // 2112 (4 bf16 channels per pixel)
+constexpr int SX_R = 16;                   // ring slots (7 live + 4 in flight + slack)
+constexpr int SX_KCHUNKS = 28;             // 7 filter rows x 4 chunks of 8 K-elements
+constexpr int SX_W_PLANE = SX_KCHUNKS * 64 * 16;   // 28,672 B: [chunk][cout][8] bf16
+constexpr int SX_MAXROWS = 81;             // conv rows per band (2*40 + 1)
+constexpr int SX_ND = 16;                  // tile-row completion barriers
+constexpr int SX_THREADS = 288;            // warp 0 MMA, warps 1-4 epilogue, warps 5-8 converters
+constexpr int SX_TMEM_COLS = 128;
+
+template <bool SPLIT>
+struct StemTcSmem {
+  static constexpr int NPLANE = SPLIT ? 2 : 1;
+  alignas(128) unsigned char w[NPLANE][SX_W_PLANE];
+  alignas(128) unsigned char ring[NPLANE][SX_R][SX_ROW_BYTES];
+  float edge[2][SX_MAXROWS][64];           // right-most conv column of the previous / current strip
+  float xch[2][4][64];                     // lane-31 rows exchanged between the 4 epilogue warps
+  float scale[64], shift[64];
+  uint64_t in_full[SX_R], mma_done[SX_ND], tmem_full[2], tmem_empty[2], wbar;
+  uint32_t tmem_base;
+};
+
+struct StemTcParams {
+  const float* img;
+  int B, H, W, Hc, Wc, Hp, Wp;
+  int bands_per_page, nb;                  // pooled rows per band
+  const unsigned char* w_packed;           // [NPLANE][SX_W_PLANE]
+  const float* bn_scale;
+  const float* bn_shift;
+  void* out0;
+  void* out1;
+};
+
+__device__ __forceinline__ uint64_t desc_noswz(uint32_t addr, uint32_t lbo, uint32_t sbo) {
+  uint64_t d = 0;
+  d |= (uint64_t)((addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)((lbo >> 4) & 0x3FFF) << 16;   // K-chunk (8 elements) stride
+  d |= (uint64_t)((sbo >> 4) & 0x3FFF) << 32;   // 8-row-group stride
+  d |= (uint64_t)1 << 46;                       // version 1; layout_type 0 = SWIZZLE_NONE
+  return d;
+}
+
+template <bool SPLIT, int OUT_DTYPE>
+__global__ void __launch_bounds__(SX_THREADS, 1)
+stem_tc_kernel(const StemTcParams p) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  StemTcSmem<SPLIT>& sm = *reinterpret_cast<StemTcSmem<SPLIT>*>(smem_raw);
+  constexpr int NPLANE = SPLIT ? 2 : 1;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  // ---- band geometry (identical in every role)
+  const int b = blockIdx.x / p.bands_per_page, band = blockIdx.x % p.bands_per_page;
+  const int py0 = band * p.nb, py1 = min(py0 + p.nb, p.Hp);
+  const int oy_begin = py0 > 0 ? 2 * py0 - 1 : 0;
+  const int oy_end = min(2 * py1, p.Hc);             // exclusive
+  const int n_conv = oy_end - oy_begin;              // conv rows per strip
+  const int NQ = 2 * (n_conv - 1) + 7;               // input rows per strip
+  const int y_first = 2 * oy_begin - 3;
+  const int n_strips = (p.Wc + SX_TM - 1) / SX_TM;
+
+  if (threadIdx.x < 64) {
+    sm.scale[threadIdx.x] = p.bn_scale[threadIdx.x];
+    sm.shift[threadIdx.x] = p.bn_shift[threadIdx.x];
+  }
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < SX_R; ++i) ptx::mbar_init(&sm.in_full[i], 1);
+    for (int i = 0; i < SX_ND; ++i) ptx::mbar_init(&sm.mma_done[i], 1);
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(&sm.tmem_full[i], 1);
+      ptx::mbar_init(&sm.tmem_empty[i], 128);
+    }
+    ptx::mbar_init(&sm.wbar, 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 0) {
+    ptx::tmem_alloc(&sm.tmem_base, SX_TMEM_COLS);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = sm.tmem_base;
+  if (n_conv <= 0) goto teardown;
+
+  if (warp == 0) {
+    // ======================= MMA issuer (warp converged; one elected lane issues) =======================
+    if (ptx::elect_one()) {
+      ptx::mbar_arrive_expect_tx(&sm.wbar, NPLANE * SX_W_PLANE);
+      for (int pl = 0; pl < NPLANE; ++pl)
+        ptx::tma_bulk_g2s(sm.w[pl], p.w_packed + (size_t)pl * SX_W_PLANE, SX_W_PLANE, &sm.wbar);
+    }
+    __syncwarp();
+    ptx::mbar_wait(&sm.wbar, 0);
+    constexpr uint32_t idesc = ptx::umma_idesc_bf16(128, 64);
+    const uint64_t da0 = desc_noswz(ptx::smem_u32(&sm.ring[0][0][0]), 16, 128);
+    const uint64_t db0 = desc_noswz(ptx::smem_u32(&sm.w[0][0]), 1024, 128);
+    const uint32_t da_hi32 = (uint32_t)(da0 >> 32), db_hi32 = (uint32_t)(db0 >> 32);
+    const uint32_t da_lo0 = (uint32_t)da0, db_lo0 = (uint32_t)db0;
+    uint32_t t = 0;
+    for (int strip = 0; strip < n_strips; ++strip) {
+      for (int i = 0; i < n_conv; ++i, ++t) {
+        const uint32_t g0 = (uint32_t)strip * NQ + 2 * i;
+        for (int r = (i == 0 ? 0 : 5); r < 7; ++r) {         // rows that are new for this conv row
+          const uint32_t g = g0 + r;
+          ptx::mbar_wait(&sm.in_full[g % SX_R], (g / SX_R) & 1);
+        }
+        const uint32_t acc = t & 1;
+        ptx::mbar_wait(&sm.tmem_empty[acc], ((t >> 1) & 1) ^ 1);
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * 64;
+        if (ptx::elect_one()) {
+#pragma unroll
+          for (int r = 0; r < 7; ++r) {
+            const uint32_t a_lo = da_lo0 + ((((g0 + r) % SX_R) * SX_ROW_BYTES) >> 4);
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {               // s = 0..3 / 4..7 -> 4 pixels = 32 B further
+              const uint64_t da_hi = ((uint64_t)da_hi32 << 32) | (uint32_t)(a_lo + ((half * 32) >> 4));
+              const uint64_t db_hi = ((uint64_t)db_hi32 << 32) | (uint32_t)(db_lo0 + (((r * 4 + half * 2) * 1024) >> 4));
+              ptx::umma_bf16(d_tmem, da_hi, db_hi, idesc, (r | half) != 0);
+              if (SPLIT) {
+                ptx::umma_bf16(d_tmem, da_hi + ((SX_R * SX_ROW_BYTES) >> 4), db_hi, idesc, 1);
+                ptx::umma_bf16(d_tmem, da_hi, db_hi + (SX_W_PLANE >> 4), idesc, 1);
+              }
+            }
+          }
+          ptx::umma_commit(&sm.mma_done[t % SX_ND]);
+          ptx::umma_commit(&sm.tmem_full[acc]);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp <= 4) {
+    // ======================= epilogue: BN + ReLU + 3x3/s2 max-pool =======================
+    const int lg = warp & 3;                       // TMEM lane group this warp may read
+    const int m = lg * 32 + lane;                  // conv column within the strip
+    float acc_v[64];                               // running vertical max of the current pooling window
+    uint32_t t = 0;
+    for (int strip = 0; strip < n_strips; ++strip) {
+      const int ox = strip * SX_TM + m;
+#pragma unroll
+      for (int c = 0; c < 64; ++c) acc_v[c] = 0.f;   // post-ReLU values are >= 0: 0 is the neutral element
+      for (int i = 0; i < n_conv; ++i, ++t) {
+        const int oy = oy_begin + i;
+        const uint32_t acc = t & 1;
+        ptx::mbar_wait(&sm.tmem_full[acc], (t >> 1) & 1);
+        ptx::tc_fence_after();
+        uint32_t raw[4][16];
+        const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + acc * 64;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) ptx::tmem_ld16(taddr + q * 16, raw[q]);
+        ptx::tmem_ld_wait();
+        ptx::tc_fence_before();
+        ptx::mbar_arrive(&sm.tmem_empty[acc]);
+
+        float v[64];
+        const bool in_w = ox < p.Wc;
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int c = q * 16 + j;
+            const float y = fmaxf(fmaf(__uint_as_float(raw[q][j]), sm.scale[c], sm.shift[c]), 0.f);
+            v[c] = in_w ? y : 0.f;
+          }
+        // lane 31 publishes its column for the next warp (and, from the last warp, for the next strip)
+        float* xrow = sm.xch[t & 1][lg];
+        if (lane == 31) {
+#pragma unroll
+          for (int c = 0; c < 64; c += 4) *reinterpret_cast<float4*>(xrow + c) = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
+          if (lg == 3) {
+            float* e = sm.edge[strip & 1][i];
+#pragma unroll
+            for (int c = 0; c < 64; c += 4) *reinterpret_cast<float4*>(e + c) = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
+          }
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        const float* left = lg > 0 ? sm.xch[t & 1][lg - 1] : sm.edge[(strip & 1) ^ 1][i];
+        const bool left_zero = (lg == 0 && strip == 0);            // conv column -1 = pool padding
+        const bool emit = (oy & 1) || (oy == p.Hc - 1);
+        const int py = oy >> 1;
+        const int px = ox >> 1;
+        const bool writer = emit && !(lane & 1) && py >= py0 && py < py1 && px < p.Wp;
+        const size_t opix = (((size_t)b * p.Hp + py) * p.Wp + px) * 64;
+#pragma unroll
+        for (int c8 = 0; c8 < 64; c8 += 8) {
+          float o[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const int c = c8 + e;
+            float l = __shfl_up_sync(0xffffffffu, v[c], 1);
+            const float r = __shfl_down_sync(0xffffffffu, v[c], 1);
+            if (lane == 0) l = left_zero ? 0.f : left[c];
+            const float h = fmaxf(fmaxf(l, v[c]), r);               // horizontal 3-max (valid on even lanes)
+            const float a = fmaxf(acc_v[c], h);
+            o[e] = a;
+            acc_v[c] = (oy & 1) ? h : a;                            // an odd row also opens the next window
+          }
+          if (writer) {
+            if (OUT_DTYPE == COVA_F32) {
+              float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out0) + opix + c8);
+              dst[0] = make_float4(o[0], o[1], o[2], o[3]);
+              dst[1] = make_float4(o[4], o[5], o[6], o[7]);
+            } else {
+              uint32_t hw[4], lw[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                __nv_bfloat16 h0, l0, h1, l1;
+                split_bf16(o[2 * e], h0, l0);
+                split_bf16(o[2 * e + 1], h1, l1);
+                hw[e] = pack_bf16x2(h0, h1);
+                lw[e] = pack_bf16x2(l0, l1);
+              }
+              *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out0) + opix + c8) =
+                  make_uint4(hw[0], hw[1], hw[2], hw[3]);
+              if (OUT_DTYPE == COVA_BF16X2)
+                *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out1) + opix + c8) =
+                    make_uint4(lw[0], lw[1], lw[2], lw[3]);
+            }
+          }
+        }
+      }
+    }
+  } else {
+    // ======================= converters: NCHW fp32 rows -> ring of 4-channel bf16 pixels =======================
+    const int cw = warp - 5;                        // this warp owns input rows g with g % 4 == cw
+    const float* img_b = p.img + (size_t)b * 3 * p.H * p.W;
+    const size_t plane = (size_t)p.H * p.W;
+    const uint32_t n_rows_total = (uint32_t)n_strips * NQ;
+    for (uint32_t g = cw; g < n_rows_total; g += 4) {
+      const int strip = g / NQ, q = g % NQ;
+      const int y = y_first + q;
+      const int x0 = 2 * strip * SX_TM - 3;
+      if (g >= SX_R) {   // the previous occupant of this slot must have been consumed by its last conv row
+        const uint32_t gp = g - SX_R;
+        const int sp = gp / NQ, qp = gp % NQ;
+        const uint32_t t_last = (uint32_t)sp * n_conv + min(qp >> 1, n_conv - 1);
+        ptx::mbar_wait(&sm.mma_done[t_last % SX_ND], (t_last / SX_ND) & 1);
+      }
+      const bool row_ok = y >= 0 && y < p.H;
+      float f[9][3];
+#pragma unroll
+      for (int j = 0; j < 9; ++j) {
+        const int i = lane + 32 * j, x = x0 + i;
+        const bool ok = row_ok && i < SX_NPX && x >= 0 && x < p.W;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) f[j][c] = ok ? __ldg(img_b + c * plane + (size_t)y * p.W + x) : 0.f;
+      }
+      unsigned char* dst_hi = sm.ring[0][g % SX_R];
+#pragma unroll
+      for (int j = 0; j < 9; ++j) {
+        const int i = lane + 32 * j;
+        if (i < SX_NPX) {
+          __nv_bfloat16 h[3], l[3];
+#pragma unroll
+          for (int c = 0; c < 3; ++c) split_bf16(f[j][c], h[c], l[c]);
+          *reinterpret_cast<uint2*>(dst_hi + i * 8) =
+              make_uint2(pack_bf16x2(h[0], h[1]), (uint32_t)__bfloat16_as_ushort(h[2]));
+          if (SPLIT)
+            *reinterpret_cast<uint2*>(dst_hi + SX_R * SX_ROW_BYTES + i * 8) =
+                make_uint2(pack_bf16x2(l[0], l[1]), (uint32_t)__bfloat16_as_ushort(l[2]));
+        }
+      }
+      ptx::fence_proxy_async();      // generic-proxy writes -> visible to tcgen05 (async proxy) reads
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&sm.in_full[g % SX_R]);
+    }
+  }
+
+teardown:
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, SX_TMEM_COLS);
+  }
+}
+
+// OIHW fp32 [64,3,7,7] -> [plane][28 chunks][64 cout][8] bf16, K index = r*32 + s*4 + c (s = 7 and c = 3 are zero)
+__global__ void pack_stem_weight_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= SX_KCHUNKS * 64 * 8) return;
+  const int e = i & 7, co = (i >> 3) & 63, chunk = i >> 9;
+  const int r = chunk >> 2, s = (chunk & 3) * 2 + (e >> 2), c = e & 3;
+  float v = 0.f;
+  if (s < 7 && c < 3) v = w[((co * 3 + c) * 7 + r) * 7 + s];
+  __nv_bfloat16 h, l;
+  split_bf16(v, h, l);
+  out[i] = h;
+  out[SX_KCHUNKS * 64 * 8 + i] = l;
+}
+
+template <bool SPLIT, int OUT_DTYPE>
+static int launch_stem_tc(const StemTcParams& p, int grid, cudaStream_t st) {
+  auto kern = stem_tc_kernel<SPLIT, OUT_DTYPE>;
+  const int smem = (int)sizeof(StemTcSmem<SPLIT>) + 128;
+  COVA_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  kern<<<grid, SX_THREADS, smem, st>>>(p);
+  COVA_LAUNCH_OK();
+  return COVA_OK;
+}
+
+int stem_tc(const float* images, int B, int H, int W, const void* w_packed, const float* bn_scale,
+            const float* bn_shift, int out_dtype, void* out0, void* out1, cudaStream_t st) {
+  StemTcParams p;
+  p.img = images; p.B = B; p.H = H; p.W = W;
+  p.Hc = (H + 6 - 7) / 2 + 1; p.Wc = (W + 6 - 7) / 2 + 1;
+  p.Hp = (p.Hc + 2 - 3) / 2 + 1; p.Wp = (p.Wc + 2 - 3) / 2 + 1;
+  int bands = sm_count() / B;
+  if (bands < 1) bands = 1;
+  if (bands > p.Hp) bands = p.Hp;
+  int nb = ceil_div(p.Hp, bands);
+  const int nb_max = (SX_MAXROWS - 1) / 2;
+  if (nb > nb_max) nb = nb_max;
+  p.nb = nb;
+  p.bands_per_page = ceil_div(p.Hp, nb);
+  p.w_packed = (const unsigned char*)w_packed;
+  p.bn_scale = bn_scale; p.bn_shift = bn_shift;
+  p.out0 = out0; p.out1 = out1;
+  const int grid = B * p.bands_per_page;
+  const bool split = out_dtype != COVA_BF16;   // bf16 output <=> bf16 mode; fp32 / split outputs use the 3-product mode
+  if (split) {
+    if (out_dtype == COVA_F32) return launch_stem_tc<true, COVA_F32>(p, grid, st);
+    return launch_stem_tc<true, COVA_BF16X2>(p, grid, st);
+  }
+  return launch_stem_tc<false, COVA_BF16>(p, grid, st);
+}
+
+}  // namespace cova
+
+extern "C" int cova_pack_stem_weight(const float* w_oihw, void* packed, void* stream) {
+  COVA_REQUIRE(w_oihw && packed, "cova_pack_stem_weight: null pointer");
+  cova::pack_stem_weight_kernel<<<cova::ceil_div(cova::SX_KCHUNKS * 64 * 8, 256), 256, 0, (cudaStream_t)stream>>>(
+      w_oihw, (__nv_bfloat16*)packed);
+  COVA_LAUNCH_OK();
+  return COVA_OK;
+}

@@ -46,6 +46,8 @@ class NativeForward:
         c["act_dtype"] = (BF16X2 if split else BF16) if tc else F32
         cn = m.convnet
         c["stem_w"] = cn[0].weight.detach().float().contiguous()
+        if tc:
+            c["stem_w"] = ops.pack_stem_weight(c["stem_w"])
         c["stem_bn"] = fold_bn(cn[1])
         blocks = []
         for blk in cn[4]:

@@ -277,6 +277,10 @@ class CoVA(nn.Module):
         return self._forward_composite(images, bboxes, additional_feats, context_indices)
 
     def _forward_composite(self, images, bboxes, additional_feats, context_indices):
+        with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):   # fp32 like the reference, not TF32
+            return self._forward_composite_impl(images, bboxes, additional_feats, context_indices)
+
+    def _forward_composite_impl(self, images, bboxes, additional_feats, context_indices):
         visual_feats = self._get_visual_features(images, bboxes)
         bbox_feats = self._get_bbox_features(bboxes)
         additional_feats = self.bn_additional_feat(additional_feats)

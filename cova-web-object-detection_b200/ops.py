@@ -73,6 +73,14 @@ def stem_fwd(images, w, bn_scale, bn_shift, out_dtype=F32, engine=ENGINE_SIMT):
     return out
 
 
+def pack_stem_weight(w_oihw):
+    """OIHW fp32 [64,3,7,7] -> packed split-bf16 filter of the tcgen05 stem ([2,28,64,8] bf16)."""
+    _cuda(w_oihw, torch.float32, "w")
+    out = torch.empty((2, 28, 64, 8), dtype=torch.bfloat16, device=w_oihw.device)
+    _call("cova_pack_stem_weight", w_oihw.contiguous().data_ptr(), out.data_ptr(), _stream())
+    return out
+
+
 def pack_conv_weight(w_oihw, simt=True, tc=True, split=True):
     """OIHW fp32 -> (simt fp32 [kh,kw,Cin,Cout] | None, tc_hi bf16 [kh*kw,Cout,Cin] | None, tc_lo | None)."""
     _cuda(w_oihw, torch.float32, "w")

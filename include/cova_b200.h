@@ -44,10 +44,17 @@ int cova_device_info(int* sm_count, int* max_smem_optin);
  * maxpool 3x3 s2 p1 (`models.py:49-51`, applied `models.py:125`).  ONE fused kernel: the
  * [B,64,H/2,W/2] conv output never reaches HBM.
  *   images  [B,3,H,W] fp32 NCHW (the reference's input contract, `models.py:96`)
- *   w       [64,3,7,7] fp32 OIHW (`convnet.0.weight`), bn_scale/bn_shift [64] folded `convnet.1`
- *   out     NHWC [B,H/4,W/4,64] in `out_dtype` (planes out0/out1)                                   */
-int cova_stem_fwd(const float* images, int B, int H, int W, const float* w, const float* bn_scale,
+ *   w       engine SIMT   : [64,3,7,7] fp32 OIHW (`convnet.0.weight`)
+ *           engine TCGEN05: the split-bf16 K-chunked filter written by cova_pack_stem_weight
+ *   bn_scale/bn_shift [64] folded `convnet.1`
+ *   out     NHWC [B,H/4,W/4,64] in `out_dtype` (planes out0/out1).  TCGEN05: COVA_BF16 output selects the
+ *           single-product bf16 mode, COVA_BF16X2 / COVA_F32 the 3-product fp32-parity mode.            */
+int cova_stem_fwd(const float* images, int B, int H, int W, const void* w, const float* bn_scale,
                   const float* bn_shift, int out_dtype, void* out0, void* out1, int engine, void* stream);
+
+/* OIHW fp32 [64,3,7,7] -> tcgen05 stem filter: bf16 [2 planes (hi, lo)][28 K-chunks][64 cout][8],
+ * K index = r*32 + s*4 + c with zero weights at s = 7 and c = 3 (57,344 bytes).                       */
+int cova_pack_stem_weight(const float* w_oihw, void* packed, void* stream);
 
 /* ---- A2: 3x3 s1 p1 convolution + folded BN (+ residual) (+ ReLU): one BasicBlock half
  * (torchvision BasicBlock.forward; `convnet.4.{b}.conv{1,2}` + `bn{1,2}`), Cin = Cout = 64.
