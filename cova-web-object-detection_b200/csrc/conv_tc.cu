@@ -16,8 +16,14 @@
 // traffic stays 1x because neighbouring tiles share halos through L2.
 //
 // fp32-parity mode (SPLIT): x = hi + lo (two bf16 planes), w = hi + lo; D = Ahi*Whi + Alo*Whi + Ahi*Wlo with
-// fp32 accumulation in TMEM: ~2^-17 relative per product, i.e. an fp32 convolution to ~1e-5, at 3 MMAs
-// per term.  Plain bf16 mode issues the first product only.
+// fp32 accumulation in TMEM: ~2^-17 relative per product, i.e. an fp32 convolution to ~1e-5.
+// Measured (tools/probe_mma_rate.cu, profiles/r01b_probe_mma_rate.txt): an M=128 MMA costs
+// max(N/2, (4096 + 32 N)/128) clk - tcgen05 reads its shared-memory operands at 128 B/clk/SM, so N = 64 is
+// operand-bandwidth bound (48 clk, 66 % of the tensor peak) and N = 128 runs at 99.8 %.  The two products that
+// share A (Ahi*Whi and Ahi*Wlo) are therefore issued as ONE N = 128 MMA against the stacked filter [Whi; Wlo]
+// (the per-tap filter block holds its hi rows then its lo rows), accumulating into 128 TMEM columns that the
+// epilogue folds (col c + col 64+c); Alo*Whi is an N = 64 MMA into the first 64 columns.
+// Per (tap, k-step): 64 + 48 = 112 clk instead of 3 x 48.  Plain bf16 mode issues Ahi*Whi only.
 //
 // Persistent CTAs (grid = #SMs, 1 CTA/SM, 192 threads):
 //   warp 0   TMA producer: all 9 filter taps once (resident, 72 KB per plane), then the activation ring
@@ -28,8 +34,8 @@
 // the lo plane Alo*Whi (36 MMAs); 3 slots (split) / 6 slots (bf16) keep >= 2 loads in flight next to the
 // 144 KB / 72 KB resident filter.
 //
-// Bound: tensor pipe in SPLIT mode (108 MMAs x 32 clk = 3456 clk/tile); bf16 mode sits between the tensor pipe
-// (1152 clk/tile) and HBM (26 MB in + out per page).
+// Bound: tensor pipe / its operand feed: SPLIT 36 x (64 + 48) = 4032 clk per tile, bf16 36 x 48 = 1728 clk per tile
+// (vs 26-52 MB of HBM traffic per page: 1700-3400 clk per tile-equivalent at the measured 6.5 TB/s).
 // Algorithmic work: 2*9*64*64 = 73,728 FLOP per output pixel (7.55 GFLOP per 320x320 page).
 #include "common.cuh"
 #include "ptx.cuh"
@@ -43,16 +49,17 @@ constexpr int CT_HW = CT_TW + 2, CT_HH = CT_TH + 2;        // halo patch 10 x 18
 constexpr int CT_PATCH_BYTES = CT_HW * CT_HH * 128;        // 23,040 bytes landed per plane load
 constexpr int CT_SLOT_BYTES = 23 * 1024;                   // ring slot (1024-B aligned for the swizzle atoms)
 constexpr int CT_GROUP_STRIDE = CT_HW * 128;               // 8-row-group stride of a tap view: one patch row
-constexpr int CT_W_PLANE_BYTES = 9 * CT_C * 128;           // 73,728 (9 taps x 64 cout rows x 128 B)
+constexpr int CT_W_TAP_BYTES = CT_C * 128;                 // 8,192: one tap of one plane (64 cout rows x 128 B)
 constexpr int CT_THREADS = 192;
-constexpr int CT_TMEM_COLS = 128;              // 2 accumulator buffers x 64 fp32 columns
 
 template <bool SPLIT>
 struct ConvTcCfg {
   static constexpr int NPLANE = SPLIT ? 2 : 1;
   static constexpr int NSTAGE = SPLIT ? 3 : 6;
   static constexpr int STAGE_BYTES = CT_SLOT_BYTES;
-  static constexpr int W_BYTES = CT_W_PLANE_BYTES * NPLANE;
+  static constexpr int W_BYTES = 9 * CT_W_TAP_BYTES * NPLANE;   // [tap][plane][64 rows][128 B]
+  static constexpr int ACC_COLS = SPLIT ? 128 : 64;             // fp32 accumulator columns per buffer
+  static constexpr int TMEM_COLS = 2 * ACC_COLS;
   static constexpr int SMEM_BYTES = W_BYTES + NSTAGE * STAGE_BYTES + 1024 /*tail*/ + 1024 /*align slack*/;
 };
 
@@ -110,7 +117,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_cons
     }
   }
   if (warp == 1) {
-    ptx::tmem_alloc(&tail.tmem_base, CT_TMEM_COLS);
+    ptx::tmem_alloc(&tail.tmem_base, Cfg::TMEM_COLS);
     ptx::tmem_relinquish();
   }
   ptx::tc_fence_before();
@@ -121,11 +128,12 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_cons
   if (warp == 0) {
     // ======================= TMA producer (warp converged; one elected lane issues) =======================
     if (ptx::elect_one()) {
-      // resident filter: 9 taps x 64 rows per plane, three 192-row boxes each
+      // resident filter, [tap][plane][64 cout rows][128 B]: a tap's hi rows are followed by its lo rows
       ptx::mbar_arrive_expect_tx(&tail.wbar, Cfg::W_BYTES);
-      for (int i = 0; i < 3; ++i) {
-        ptx::tma_load_2d(sm_w + i * 192 * 128, &tm_w_hi, &tail.wbar, 0, i * 192);
-        if (SPLIT) ptx::tma_load_2d(sm_w + CT_W_PLANE_BYTES + i * 192 * 128, &tm_w_lo, &tail.wbar, 0, i * 192);
+      for (int tap = 0; tap < 9; ++tap) {
+        ptx::tma_load_2d(sm_w + tap * Cfg::NPLANE * CT_W_TAP_BYTES, &tm_w_hi, &tail.wbar, 0, tap * CT_C);
+        if (SPLIT)
+          ptx::tma_load_2d(sm_w + (tap * 2 + 1) * CT_W_TAP_BYTES, &tm_w_lo, &tail.wbar, 0, tap * CT_C);
       }
     }
     __syncwarp();
@@ -150,33 +158,31 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_cons
     // Descriptors differ only in their 14-bit start-address field, so each MMA costs two 32-bit adds on
     // warp-uniform values (the elect.sync guard lets the compiler keep them in uniform registers; an
     // `if (lane == 0)` region would wrap every UTCHMMA in a per-lane serialisation loop).
-    constexpr uint32_t idesc = ptx::umma_idesc_bf16(128, CT_C);
+    constexpr uint32_t idesc64 = ptx::umma_idesc_bf16(128, CT_C);
+    constexpr uint32_t idesc128 = ptx::umma_idesc_bf16(128, 2 * CT_C);
     const uint64_t da0 = ptx::umma_desc_sw128(ptx::smem_u32(sm_a), CT_GROUP_STRIDE);
     const uint64_t db0 = ptx::umma_desc_sw128(ptx::smem_u32(sm_w), 1024);
-    const uint32_t da_hi32 = (uint32_t)(da0 >> 32), db_hi32 = (uint32_t)(db0 >> 32);
-    const uint32_t da_lo0 = (uint32_t)da0, db_lo0 = (uint32_t)db0;
     ptx::mbar_wait(&tail.wbar, 0);
     uint32_t stage = 0, phase = 0, it = 0;
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
       const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
       ptx::mbar_wait(&tail.tmem_empty[acc], acc_phase ^ 1);
       ptx::tc_fence_after();
-      const uint32_t d_tmem = tmem_base + acc * CT_C;
-      for (int pl = 0; pl < Cfg::NPLANE; ++pl) {   // pl 0: A = hi plane (x Whi, x Wlo); pl 1: A = lo plane (x Whi)
+      const uint32_t d_tmem = tmem_base + acc * Cfg::ACC_COLS;
+      for (int pl = 0; pl < Cfg::NPLANE; ++pl) {   // pl 0: A = hi plane x [Whi; Wlo]; pl 1: A = lo plane x Whi
         ptx::mbar_wait(&tail.full[stage], phase);
         ptx::tc_fence_after();
         if (ptx::elect_one()) {
-          const uint32_t a_lo = da_lo0 + ((stage * Cfg::STAGE_BYTES) >> 4);
+          uint64_t da_s = da0 + ((stage * Cfg::STAGE_BYTES) >> 4);
 #pragma unroll
           for (int tap = 0; tap < 9; ++tap) {
+            uint64_t db_t = db0;
+            asm volatile("" : "+l"(da_s), "+l"(db_t));   // keep the 36 x 2 descriptors from being hoisted and spilled
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk) {   // 4 x K=16 bf16 (32 B) inside the 128-B swizzle row
-              const uint64_t da = ((uint64_t)da_hi32 << 32) |
-                                  (uint32_t)(a_lo + ((((tap / 3) * CT_HW + (tap % 3)) * 128 + kk * 32) >> 4));
-              const uint32_t b_lo = db_lo0 + ((tap * (CT_C * 128) + kk * 32) >> 4);
-              ptx::umma_bf16(d_tmem, da, ((uint64_t)db_hi32 << 32) | b_lo, idesc, (pl | tap | kk) != 0);
-              if (SPLIT && pl == 0)
-                ptx::umma_bf16(d_tmem, da, ((uint64_t)db_hi32 << 32) | (uint32_t)(b_lo + (CT_W_PLANE_BYTES >> 4)), idesc, 1);
+              const uint64_t da = da_s + ((((tap / 3) * CT_HW + (tap % 3)) * 128 + kk * 32) >> 4);
+              const uint64_t db = db_t + ((tap * Cfg::NPLANE * CT_W_TAP_BYTES + kk * 32) >> 4);
+              ptx::umma_bf16(d_tmem, da, db, (SPLIT && pl == 0) ? idesc128 : idesc64, (pl | tap | kk) != 0);
             }
           }
           ptx::umma_commit(&tail.empty[stage]);                           // slot free once these MMAs have read it
@@ -217,22 +223,30 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_cons
       ptx::mbar_wait(&tail.tmem_full[acc], acc_phase);
       ptx::tc_fence_after();
       uint32_t v[4][16];
-      const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + acc * CT_C;
+      const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + acc * Cfg::ACC_COLS;
 #pragma unroll
       for (int q = 0; q < 4; ++q) ptx::tmem_ld16(taddr + q * 16, v[q]);
       ptx::tmem_ld_wait();
-      ptx::tc_fence_before();
-      ptx::mbar_arrive(&tail.tmem_empty[acc]);     // accumulator buffer is free for tile it+2
-
-      if (!inb) continue;
       float o[64];
 #pragma unroll
       for (int q = 0; q < 4; ++q)
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const int c = q * 16 + j;
-          o[c] = fmaf(__uint_as_float(v[q][j]), tail.scale[c], tail.shift[c]);
-        }
+        for (int j = 0; j < 16; ++j) o[q * 16 + j] = __uint_as_float(v[q][j]);
+      if (SPLIT) {   // columns 64..127 hold Ahi*Wlo
+#pragma unroll
+        for (int q = 0; q < 4; ++q) ptx::tmem_ld16(taddr + CT_C + q * 16, v[q]);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+#pragma unroll
+          for (int j = 0; j < 16; ++j) o[q * 16 + j] += __uint_as_float(v[q][j]);
+      }
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(&tail.tmem_empty[acc]);     // accumulator buffer is free for tile it+2
+
+      if (!inb) continue;
+#pragma unroll
+      for (int c = 0; c < 64; ++c) o[c] = fmaf(o[c], tail.scale[c], tail.shift[c]);
       if (has_res) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -285,7 +299,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_cons
   __syncthreads();
   if (warp == 1) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc(tmem_base, CT_TMEM_COLS);
+    ptx::tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
   }
 }
 
@@ -311,7 +325,7 @@ int conv3x3_tc(const void* x_hi, const void* x_lo, int split, int B, int H, int 
   const uint32_t xb[4] = {CT_C, CT_HW, CT_HH, 1};
   const uint64_t wd[2] = {(uint64_t)CT_C, (uint64_t)9 * CT_C};
   const uint64_t ws[1] = {(uint64_t)CT_C * 2};
-  const uint32_t wb[2] = {CT_C, 192};
+  const uint32_t wb[2] = {CT_C, CT_C};   // one tap of one plane per load
   int rc;
   if ((rc = make_tmap_bf16(&tx_hi, x_hi, 4, xd, xs, xb))) return rc;
   if ((rc = make_tmap_bf16(&tw_hi, w_hi, 2, wd, ws, wb))) return rc;

@@ -1,0 +1,226 @@
+// Row-major linear layer on the 5th-gen tensor cores, fp32-parity (split-bf16, 3 products, fp32 accumulate in TMEM):
+//     Y[M,N] = act((X[M,K] @ W[N,K]^T + bias) * scale + shift + res)
+// Replaces `nn.Linear` (+ folded BatchNorm1d + ReLU) of `/root/reference/models.py:160-164` (the GAT projections,
+// fused into one extended weight matrix), `:85-87` (decoder.1 + decoder.2 + ReLU).
+//
+// X arrives as fp32 (it is produced by the RoI / GAT kernels); the split into bf16 hi/lo happens on the way into
+// shared memory: converter warps load 128 x 64 fp32 tiles with fully coalesced 16-byte loads and store the two
+// bf16 planes in the K-major 128-byte-swizzled layout tcgen05 expects (chunk16 index XOR (row & 7) on the
+// absolute address - the same rule TMA applies), then fence.proxy.async + mbarrier.  W is pre-split once per
+// weight update (cova_pack_linear_weight) and streamed by TMA.  One CTA = one 128 x 96 output tile
+// (N = 992 -> 11 column tiles x 12 row tiles = 132 CTAs for the decoder: one wave of 148 SMs), 3-stage ring.
+//
+// Bound: tensor pipe (tiny GEMMs: < 1 % of the step's FLOPs); the point is to take them off the CUDA cores.
+#include "common.cuh"
+#include "ptx.cuh"
+#include "tma_host.cuh"
+
+namespace cova {
+
+constexpr int LT_BM = 128, LT_BN = 96, LT_BK = 64, LT_STAGES = 3;
+constexpr int LT_A_PLANE = LT_BM * 128;          // 16 KB
+constexpr int LT_B_PLANE = LT_BN * 128;          // 12 KB
+constexpr int LT_STAGE_BYTES = 2 * LT_A_PLANE + 2 * LT_B_PLANE;   // 56 KB
+constexpr int LT_THREADS = 192;                  // warp 0 TMA, warp 1 MMA, warps 2-5 convert + epilogue
+constexpr int LT_SMEM = LT_STAGES * LT_STAGE_BYTES + 1024 + 1024;
+
+struct LinearTcTail {
+  uint64_t a_full[LT_STAGES], b_full[LT_STAGES], empty[LT_STAGES], acc_full;
+  uint32_t tmem_base;
+};
+
+struct LinearTcParams {
+  const float* x;
+  int64_t ldx;
+  int M, K, N;
+  const float* bias;
+  const float* scale;
+  const float* shift;
+  const float* res;
+  int64_t ldr;
+  int relu;
+  float* y;
+  int64_t ldy;
+};
+
+__global__ void __launch_bounds__(LT_THREADS, 1)
+linear_tc_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo,
+                 const LinearTcParams p) {
+  extern __shared__ unsigned char smem_raw[];
+  const uint32_t raw_addr = ptx::smem_u32(smem_raw);
+  unsigned char* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
+  LinearTcTail& tail = *reinterpret_cast<LinearTcTail*>(smem + LT_STAGES * LT_STAGE_BYTES);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.y * LT_BM, n0 = blockIdx.x * LT_BN;
+  const int nkb = (p.K + LT_BK - 1) / LT_BK;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < LT_STAGES; ++i) {
+      ptx::mbar_init(&tail.a_full[i], 4);     // one arrive per converter warp
+      ptx::mbar_init(&tail.b_full[i], 1);
+      ptx::mbar_init(&tail.empty[i], 1);
+    }
+    ptx::mbar_init(&tail.acc_full, 1);
+    ptx::fence_barrier_init();
+    ptx::prefetch_tensormap(&tm_w_hi);
+    ptx::prefetch_tensormap(&tm_w_lo);
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(&tail.tmem_base, 128);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = tail.tmem_base;
+
+  if (warp == 0) {
+    // ---------------- TMA producer: W tiles (hi, lo) ----------------
+    uint32_t stage = 0, phase = 0;
+    for (int kb = 0; kb < nkb; ++kb) {
+      ptx::mbar_wait(&tail.empty[stage], phase ^ 1);
+      if (ptx::elect_one()) {
+        unsigned char* sb = smem + stage * LT_STAGE_BYTES + 2 * LT_A_PLANE;
+        ptx::mbar_arrive_expect_tx(&tail.b_full[stage], 2 * LT_B_PLANE);
+        ptx::tma_load_2d(sb, &tm_w_hi, &tail.b_full[stage], kb * LT_BK, n0);
+        ptx::tma_load_2d(sb + LT_B_PLANE, &tm_w_lo, &tail.b_full[stage], kb * LT_BK, n0);
+      }
+      __syncwarp();
+      if (++stage == LT_STAGES) { stage = 0; phase ^= 1; }
+    }
+  } else if (warp == 1) {
+    // ---------------- MMA issuer ----------------
+    constexpr uint32_t idesc = ptx::umma_idesc_bf16(LT_BM, LT_BN);
+    const uint64_t d0 = ptx::umma_desc_sw128(ptx::smem_u32(smem), 1024);
+    const uint32_t hi32 = (uint32_t)(d0 >> 32), lo0 = (uint32_t)d0;
+    uint32_t stage = 0, phase = 0;
+    for (int kb = 0; kb < nkb; ++kb) {
+      ptx::mbar_wait(&tail.a_full[stage], phase);
+      ptx::mbar_wait(&tail.b_full[stage], phase);
+      ptx::tc_fence_after();
+      if (ptx::elect_one()) {
+        const uint32_t s_lo = lo0 + ((stage * LT_STAGE_BYTES) >> 4);
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          const uint64_t a_hi = ((uint64_t)hi32 << 32) | (uint32_t)(s_lo + ((kk * 32) >> 4));
+          const uint64_t a_lo = a_hi + (LT_A_PLANE >> 4);
+          const uint64_t b_hi = a_hi + ((2 * LT_A_PLANE) >> 4);
+          const uint64_t b_lo = b_hi + (LT_B_PLANE >> 4);
+          ptx::umma_bf16(tmem_base, a_hi, b_hi, idesc, (kb | kk) != 0);
+          ptx::umma_bf16(tmem_base, a_lo, b_hi, idesc, 1);
+          ptx::umma_bf16(tmem_base, a_hi, b_lo, idesc, 1);
+        }
+        ptx::umma_commit(&tail.empty[stage]);
+        if (kb == nkb - 1) ptx::umma_commit(&tail.acc_full);
+      }
+      __syncwarp();
+      if (++stage == LT_STAGES) { stage = 0; phase ^= 1; }
+    }
+  } else {
+    // ---------------- converters: fp32 X tile -> swizzled bf16 hi/lo planes ----------------
+    const int ct = threadIdx.x - 64;                 // 0..127
+    const int c = ct & 15, r0 = ct >> 4;             // 16-byte fp32 chunk c of rows r0 + 8j
+    uint32_t stage = 0, phase = 0;
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int k = kb * LT_BK + c * 4;
+      float4 v[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const int m = m0 + r0 + 8 * j;
+        v[j] = (m < p.M && k < p.K) ? __ldg(reinterpret_cast<const float4*>(p.x + (size_t)m * p.ldx + k))
+                                    : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      ptx::mbar_wait(&tail.empty[stage], phase ^ 1);
+      unsigned char* sa = smem + stage * LT_STAGE_BYTES;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const int r = r0 + 8 * j;
+        __nv_bfloat16 h[4], l[4];
+        split_bf16(v[j].x, h[0], l[0]); split_bf16(v[j].y, h[1], l[1]);
+        split_bf16(v[j].z, h[2], l[2]); split_bf16(v[j].w, h[3], l[3]);
+        const uint32_t off = r * 128 + (((c >> 1) ^ (r & 7)) << 4) + (c & 1) * 8;   // 128-B swizzle
+        *reinterpret_cast<uint2*>(sa + off) = make_uint2(pack_bf16x2(h[0], h[1]), pack_bf16x2(h[2], h[3]));
+        *reinterpret_cast<uint2*>(sa + LT_A_PLANE + off) = make_uint2(pack_bf16x2(l[0], l[1]), pack_bf16x2(l[2], l[3]));
+      }
+      ptx::fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&tail.a_full[stage]);
+      if (++stage == LT_STAGES) { stage = 0; phase ^= 1; }
+    }
+    // ---------------- epilogue (same warps): TMEM lane group = warp % 4 ----------------
+    const int lg = warp & 3;
+    const int m = m0 + lg * 32 + lane;
+    ptx::mbar_wait(&tail.acc_full, 0);
+    ptx::tc_fence_after();
+#pragma unroll 1
+    for (int q = 0; q < LT_BN / 16; ++q) {
+      uint32_t raw[16];
+      ptx::tmem_ld16(tmem_base + ((uint32_t)(lg * 32) << 16) + q * 16, raw);
+      ptx::tmem_ld_wait();
+      if (m < p.M) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int n = n0 + q * 16 + j;
+          if (n < p.N) {
+            float v = __uint_as_float(raw[j]);
+            if (p.bias) v += p.bias[n];
+            if (p.scale) v = fmaf(v, p.scale[n], p.shift[n]);
+            if (p.res) v += p.res[(size_t)m * p.ldr + n];
+            if (p.relu) v = fmaxf(v, 0.f);
+            p.y[(size_t)m * p.ldy + n] = v;
+          }
+        }
+      }
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, 128);
+  }
+}
+
+// fp32 [N,K] -> bf16 [2][N][K] (hi plane, lo plane)
+__global__ void pack_linear_weight_kernel(const float* __restrict__ w, int64_t n, __nv_bfloat16* __restrict__ out) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    __nv_bfloat16 h, l;
+    split_bf16(w[i], h, l);
+    out[i] = h;
+    out[n + i] = l;
+  }
+}
+
+bool linear_tc_supported(const float* x, int64_t ld_x, int K) {
+  return (K % 8 == 0) && (ld_x % 4 == 0) && (((uintptr_t)x & 15) == 0);
+}
+
+int linear_tc(const float* x, int64_t ld_x, int M, int K, const void* w_packed, int N, const float* bias,
+              const float* scale, const float* shift, const float* res, int64_t ld_res, int relu, float* y,
+              int64_t ld_y, cudaStream_t st) {
+  CUtensorMap tw_hi, tw_lo;
+  const uint64_t wd[2] = {(uint64_t)K, (uint64_t)N};
+  const uint64_t ws[1] = {(uint64_t)K * 2};
+  const uint32_t wb[2] = {LT_BK, LT_BN};
+  const __nv_bfloat16* wp = (const __nv_bfloat16*)w_packed;
+  int rc;
+  if ((rc = make_tmap_bf16(&tw_hi, wp, 2, wd, ws, wb))) return rc;
+  if ((rc = make_tmap_bf16(&tw_lo, wp + (size_t)N * K, 2, wd, ws, wb))) return rc;
+  LinearTcParams p{x, ld_x, M, K, N, bias, scale, shift, res, ld_res, relu, y, ld_y};
+  COVA_CUDA_OK(cudaFuncSetAttribute(linear_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LT_SMEM));
+  dim3 grid(ceil_div(N, LT_BN), ceil_div(M, LT_BM));
+  linear_tc_kernel<<<grid, LT_THREADS, LT_SMEM, st>>>(tw_hi, tw_lo, p);
+  COVA_LAUNCH_OK();
+  return COVA_OK;
+}
+
+}  // namespace cova
+
+extern "C" int cova_pack_linear_weight(const float* w, int N, int K, void* packed, void* stream) {
+  COVA_REQUIRE(w && packed && N > 0 && K > 0, "cova_pack_linear_weight: bad arguments");
+  const int64_t n = (int64_t)N * K;
+  cova::pack_linear_weight_kernel<<<(int)((n + 255) / 256 < 1184 ? (n + 255) / 256 : 1184), 256, 0, (cudaStream_t)stream>>>(
+      w, n, (__nv_bfloat16*)packed);
+  COVA_LAUNCH_OK();
+  return COVA_OK;
+}

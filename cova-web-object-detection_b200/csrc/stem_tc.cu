@@ -20,7 +20,7 @@
 // neighbour of strip i+1, so no conv column is recomputed; each band recomputes one conv row (its top halo).
 // HBM traffic: image read once (+2 % strip / +3.5 % band halos), pooled map written once.
 //
-// Bound: tensor pipe in fp32-parity mode (42 MMAs x 32 clk = 1344 clk per 128 conv pixels).
+// Bound: tensor pipe / operand feed in fp32-parity mode: 14 x (64 + 48) = 1568 clk per 128 conv pixels.
 // Algorithmic work: 2*64*147 FLOP per conv pixel (7.707 GFLOP per 1280x1280 page).
 #include "common.cuh"
 #include "ptx.cuh"
@@ -32,16 +32,17 @@ constexpr int SX_NPX = 264;                // staged input pixels per ring row (
 constexpr int SX_ROW_BYTES = SX_NPX * 8;   // 2112 (4 bf16 channels per pixel)
 constexpr int SX_R = 16;                   // ring slots (7 live + 4 in flight + slack)
 constexpr int SX_KCHUNKS = 28;             // 7 filter rows x 4 chunks of 8 K-elements
-constexpr int SX_W_PLANE = SX_KCHUNKS * 64 * 16;   // 28,672 B: [chunk][cout][8] bf16
+constexpr int SX_W_CHUNK = 2 * 64 * 16;    // 2,048 B: one K-chunk = 64 hi rows then 64 lo rows of 8 bf16
+constexpr int SX_W_BYTES = SX_KCHUNKS * SX_W_CHUNK;   // 57,344 B: [chunk][plane][cout][8] bf16
 constexpr int SX_MAXROWS = 81;             // conv rows per band (2*40 + 1)
 constexpr int SX_ND = 16;                  // tile-row completion barriers
 constexpr int SX_THREADS = 288;            // warp 0 MMA, warps 1-4 epilogue, warps 5-8 converters
-constexpr int SX_TMEM_COLS = 128;
+
 
 template <bool SPLIT>
 struct StemTcSmem {
   static constexpr int NPLANE = SPLIT ? 2 : 1;
-  alignas(128) unsigned char w[NPLANE][SX_W_PLANE];
+  alignas(128) unsigned char w[SX_W_BYTES];   // both planes always (the lo rows are simply unused in bf16 mode)
   alignas(128) unsigned char ring[NPLANE][SX_R][SX_ROW_BYTES];
   float edge[2][SX_MAXROWS][64];           // right-most conv column of the previous / current strip
   float xch[2][4][64];                     // lane-31 rows exchanged between the 4 epilogue warps
@@ -54,7 +55,7 @@ struct StemTcParams {
   const float* img;
   int B, H, W, Hc, Wc, Hp, Wp;
   int bands_per_page, nb;                  // pooled rows per band
-  const unsigned char* w_packed;           // [NPLANE][SX_W_PLANE]
+  const unsigned char* w_packed;           // [28][2][64][8] bf16
   const float* bn_scale;
   const float* bn_shift;
   void* out0;
@@ -75,7 +76,8 @@ __global__ void __launch_bounds__(SX_THREADS, 1)
 stem_tc_kernel(const StemTcParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   StemTcSmem<SPLIT>& sm = *reinterpret_cast<StemTcSmem<SPLIT>*>(smem_raw);
-  constexpr int NPLANE = SPLIT ? 2 : 1;
+  constexpr int ACC_COLS = SPLIT ? 128 : 64;      // fp32 accumulator columns per buffer
+  constexpr int TMEM_COLS = 2 * ACC_COLS;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   // ---- band geometry (identical in every role)
@@ -103,7 +105,7 @@ stem_tc_kernel(const StemTcParams p) {
     ptx::fence_barrier_init();
   }
   if (warp == 0) {
-    ptx::tmem_alloc(&sm.tmem_base, SX_TMEM_COLS);
+    ptx::tmem_alloc(&sm.tmem_base, TMEM_COLS);
     ptx::tmem_relinquish();
   }
   ptx::tc_fence_before();
@@ -115,17 +117,15 @@ stem_tc_kernel(const StemTcParams p) {
   if (warp == 0) {
     // ======================= MMA issuer (warp converged; one elected lane issues) =======================
     if (ptx::elect_one()) {
-      ptx::mbar_arrive_expect_tx(&sm.wbar, NPLANE * SX_W_PLANE);
-      for (int pl = 0; pl < NPLANE; ++pl)
-        ptx::tma_bulk_g2s(sm.w[pl], p.w_packed + (size_t)pl * SX_W_PLANE, SX_W_PLANE, &sm.wbar);
+      ptx::mbar_arrive_expect_tx(&sm.wbar, SX_W_BYTES);
+      ptx::tma_bulk_g2s(sm.w, p.w_packed, SX_W_BYTES, &sm.wbar);
     }
     __syncwarp();
     ptx::mbar_wait(&sm.wbar, 0);
-    constexpr uint32_t idesc = ptx::umma_idesc_bf16(128, 64);
+    // Ahi x [Whi; Wlo] is ONE N = 128 MMA (operand feed: 64 clk instead of 2 x 48, see conv_tc.cu), Alo x Whi N = 64
+    constexpr uint32_t idesc64 = ptx::umma_idesc_bf16(128, 64), idesc128 = ptx::umma_idesc_bf16(128, 128);
     const uint64_t da0 = desc_noswz(ptx::smem_u32(&sm.ring[0][0][0]), 16, 128);
-    const uint64_t db0 = desc_noswz(ptx::smem_u32(&sm.w[0][0]), 1024, 128);
-    const uint32_t da_hi32 = (uint32_t)(da0 >> 32), db_hi32 = (uint32_t)(db0 >> 32);
-    const uint32_t da_lo0 = (uint32_t)da0, db_lo0 = (uint32_t)db0;
+    const uint64_t db0 = desc_noswz(ptx::smem_u32(&sm.w[0]), SX_W_CHUNK, 128);
     uint32_t t = 0;
     for (int strip = 0; strip < n_strips; ++strip) {
       for (int i = 0; i < n_conv; ++i, ++t) {
@@ -137,20 +137,17 @@ stem_tc_kernel(const StemTcParams p) {
         const uint32_t acc = t & 1;
         ptx::mbar_wait(&sm.tmem_empty[acc], ((t >> 1) & 1) ^ 1);
         ptx::tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * 64;
+        const uint32_t d_tmem = tmem_base + acc * ACC_COLS;
         if (ptx::elect_one()) {
 #pragma unroll
           for (int r = 0; r < 7; ++r) {
-            const uint32_t a_lo = da_lo0 + ((((g0 + r) % SX_R) * SX_ROW_BYTES) >> 4);
+            const uint64_t da_r = da0 + ((((g0 + r) % SX_R) * SX_ROW_BYTES) >> 4);
 #pragma unroll
             for (int half = 0; half < 2; ++half) {               // s = 0..3 / 4..7 -> 4 pixels = 32 B further
-              const uint64_t da_hi = ((uint64_t)da_hi32 << 32) | (uint32_t)(a_lo + ((half * 32) >> 4));
-              const uint64_t db_hi = ((uint64_t)db_hi32 << 32) | (uint32_t)(db_lo0 + (((r * 4 + half * 2) * 1024) >> 4));
-              ptx::umma_bf16(d_tmem, da_hi, db_hi, idesc, (r | half) != 0);
-              if (SPLIT) {
-                ptx::umma_bf16(d_tmem, da_hi + ((SX_R * SX_ROW_BYTES) >> 4), db_hi, idesc, 1);
-                ptx::umma_bf16(d_tmem, da_hi, db_hi + (SX_W_PLANE >> 4), idesc, 1);
-              }
+              const uint64_t da_hi = da_r + ((half * 32) >> 4);
+              const uint64_t db = db0 + (((r * 4 + half * 2) * SX_W_CHUNK) >> 4);
+              ptx::umma_bf16(d_tmem, da_hi, db, SPLIT ? idesc128 : idesc64, (r | half) != 0);
+              if (SPLIT) ptx::umma_bf16(d_tmem, da_hi + ((SX_R * SX_ROW_BYTES) >> 4), db, idesc64, 1);
             }
           }
           ptx::umma_commit(&sm.mma_done[t % SX_ND]);
@@ -175,23 +172,33 @@ stem_tc_kernel(const StemTcParams p) {
         ptx::mbar_wait(&sm.tmem_full[acc], (t >> 1) & 1);
         ptx::tc_fence_after();
         uint32_t raw[4][16];
-        const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + acc * 64;
+        const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + acc * ACC_COLS;
 #pragma unroll
         for (int q = 0; q < 4; ++q) ptx::tmem_ld16(taddr + q * 16, raw[q]);
         ptx::tmem_ld_wait();
-        ptx::tc_fence_before();
-        ptx::mbar_arrive(&sm.tmem_empty[acc]);
-
         float v[64];
-        const bool in_w = ox < p.Wc;
 #pragma unroll
         for (int q = 0; q < 4; ++q)
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const int c = q * 16 + j;
-            const float y = fmaxf(fmaf(__uint_as_float(raw[q][j]), sm.scale[c], sm.shift[c]), 0.f);
-            v[c] = in_w ? y : 0.f;
-          }
+          for (int j = 0; j < 16; ++j) v[q * 16 + j] = __uint_as_float(raw[q][j]);
+        if (SPLIT) {   // columns 64..127 hold Ahi*Wlo
+#pragma unroll
+          for (int q = 0; q < 4; ++q) ptx::tmem_ld16(taddr + 64 + q * 16, raw[q]);
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[q * 16 + j] += __uint_as_float(raw[q][j]);
+        }
+        ptx::tc_fence_before();
+        ptx::mbar_arrive(&sm.tmem_empty[acc]);
+
+        const bool in_w = ox < p.Wc;
+#pragma unroll
+        for (int c = 0; c < 64; ++c) {
+          const float y = fmaxf(fmaf(v[c], sm.scale[c], sm.shift[c]), 0.f);
+          v[c] = in_w ? y : 0.f;
+        }
         // lane 31 publishes its column for the next warp (and, from the last warp, for the next strip)
         float* xrow = sm.xch[t & 1][lg];
         if (lane == 31) {
@@ -301,11 +308,11 @@ teardown:
   __syncthreads();
   if (warp == 0) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc(tmem_base, SX_TMEM_COLS);
+    ptx::tmem_dealloc(tmem_base, TMEM_COLS);
   }
 }
 
-// OIHW fp32 [64,3,7,7] -> [plane][28 chunks][64 cout][8] bf16, K index = r*32 + s*4 + c (s = 7 and c = 3 are zero)
+// OIHW fp32 [64,3,7,7] -> [28 chunks][plane][64 cout][8] bf16, K index = r*32 + s*4 + c (s = 7 and c = 3 are zero)
 __global__ void pack_stem_weight_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= SX_KCHUNKS * 64 * 8) return;
@@ -315,8 +322,8 @@ __global__ void pack_stem_weight_kernel(const float* __restrict__ w, __nv_bfloat
   if (s < 7 && c < 3) v = w[((co * 3 + c) * 7 + r) * 7 + s];
   __nv_bfloat16 h, l;
   split_bf16(v, h, l);
-  out[i] = h;
-  out[SX_KCHUNKS * 64 * 8 + i] = l;
+  out[((chunk * 2 + 0) * 64 + co) * 8 + e] = h;
+  out[((chunk * 2 + 1) * 64 + co) * 8 + e] = l;
 }
 
 template <bool SPLIT, int OUT_DTYPE>

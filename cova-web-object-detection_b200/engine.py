@@ -81,7 +81,18 @@ class NativeForward:
         c["dec1"] = (dec[1].weight.detach().float().contiguous(), dec[1].bias.detach().float().contiguous(),
                      *fold_bn(dec[2]))
         c["dec2"] = (dec[5].weight.detach().float().contiguous(), dec[5].bias.detach().float().contiguous())
+        if m.engine == "tcgen05":   # split-bf16 copies for the tensor-core GEMMs
+            c["dec1_p"] = ops.pack_linear_weight(c["dec1"][0])
+            c["dec2_p"] = ops.pack_linear_weight(c["dec2"][0])
+            for g in c.get("gat", []):
+                g["ext_p"] = ops.pack_linear_weight(g["ext"])
         self.c, self._key = c, key
+
+    def _linear(self, x, w, w_packed, *args, **kw):
+        """Tensor-core GEMM when the engine is tcgen05 and the shape meets its contract, CUDA cores otherwise."""
+        if w_packed is not None and ops.linear_tc_ok(x):
+            return ops.linear_fwd(x, w_packed, *args, engine=ENGINE_TCGEN05, **kw)
+        return ops.linear_fwd(x, w, *args, **kw)
 
     @staticmethod
     def _gat_cache(layer):
@@ -143,7 +154,7 @@ class NativeForward:
         self.prepare()
         attn, col = None, 0
         for g in (self.c["gat"] if heads is None else heads):
-            ext = ops.linear_fwd(own, g["ext"])
+            ext = self._linear(own, g["ext"], g.get("ext_p"))
             Hd = g["Hd"]
             attn = ops.gat_fwd(ext[:, :Hd], ext[:, Hd], ext[:, Hd + 1], g["b"], g["alpha"], context_indices,
                                out[:, col:col + Hd], want_attn=want_attn)
@@ -174,8 +185,9 @@ class NativeForward:
         self.own_into(fm, bboxes, additional_feats, comb)
         if m.use_context:
             self.gat_into(comb[:, :m.n_feat], context_indices, comb[:, m.n_feat:])
-        h1 = ops.linear_fwd(comb, self.c["dec1"][0], self.c["dec1"][1], self.c["dec1"][2], self.c["dec1"][3], relu=True)
-        logits = ops.linear_fwd(h1, *self.c["dec2"])
+        c = self.c
+        h1 = self._linear(comb, c["dec1"][0], c.get("dec1_p"), c["dec1"][1], c["dec1"][2], c["dec1"][3], relu=True)
+        logits = self._linear(h1, c["dec2"][0], c.get("dec2_p"), c["dec2"][1])
         if return_intermediates:
             return dict(fm=fm, own=comb[:, :m.n_feat], ctx=comb[:, m.n_feat:], logits=logits)
         return logits

@@ -74,9 +74,9 @@ def stem_fwd(images, w, bn_scale, bn_shift, out_dtype=F32, engine=ENGINE_SIMT):
 
 
 def pack_stem_weight(w_oihw):
-    """OIHW fp32 [64,3,7,7] -> packed split-bf16 filter of the tcgen05 stem ([2,28,64,8] bf16)."""
+    """OIHW fp32 [64,3,7,7] -> packed split-bf16 filter of the tcgen05 stem ([28,2,64,8] bf16)."""
     _cuda(w_oihw, torch.float32, "w")
-    out = torch.empty((2, 28, 64, 8), dtype=torch.bfloat16, device=w_oihw.device)
+    out = torch.empty((28, 2, 64, 8), dtype=torch.bfloat16, device=w_oihw.device)
     _call("cova_pack_stem_weight", w_oihw.contiguous().data_ptr(), out.data_ptr(), _stream())
     return out
 
@@ -140,12 +140,28 @@ def affine_cols_fwd(x, scale, shift, out):
           out.stride(0), _stream())
 
 
+def pack_linear_weight(w):
+    """fp32 [N,K] -> split-bf16 [2,N,K] for the tcgen05 linear engine."""
+    _cuda(w, torch.float32, "w")
+    w = w.contiguous()
+    out = torch.empty((2,) + tuple(w.shape), dtype=torch.bfloat16, device=w.device)
+    _call("cova_pack_linear_weight", w.data_ptr(), w.shape[0], w.shape[1], out.data_ptr(), _stream())
+    return out
+
+
+def linear_tc_ok(x):
+    """Shape/alignment contract of the tcgen05 linear engine (see include/cova_b200.h)."""
+    return x.shape[1] % 8 == 0 and x.stride(0) % 4 == 0 and x.data_ptr() % 16 == 0
+
+
 def linear_fwd(x, w, bias=None, scale=None, shift=None, res=None, relu=False, out=None, engine=ENGINE_SIMT):
-    """Y = act((X @ W^T + bias) * scale + shift + res); x [M,K] (row stride free), w [N,K] contiguous."""
+    """Y = act((X @ W^T + bias) * scale + shift + res); x [M,K] (row stride free);
+    w = fp32 [N,K] (SIMT engine) or the packed split-bf16 [2,N,K] (tcgen05 engine)."""
     _cuda(x, torch.float32, "x")
     M, K = x.shape
-    N = w.shape[0]
-    assert x.stride(1) == 1 and w.is_contiguous() and w.shape[1] == K
+    N = w.shape[-2]
+    assert x.stride(1) == 1 and w.is_contiguous() and w.shape[-1] == K
+    assert (w.dtype == torch.bfloat16 and w.dim() == 3) == (engine == ENGINE_TCGEN05)
     if out is None:
         out = torch.empty((M, N), dtype=torch.float32, device=x.device)
     assert out.stride(1) == 1

@@ -52,7 +52,7 @@ int cova_device_info(int* sm_count, int* max_smem_optin);
 int cova_stem_fwd(const float* images, int B, int H, int W, const void* w, const float* bn_scale,
                   const float* bn_shift, int out_dtype, void* out0, void* out1, int engine, void* stream);
 
-/* OIHW fp32 [64,3,7,7] -> tcgen05 stem filter: bf16 [2 planes (hi, lo)][28 K-chunks][64 cout][8],
+/* OIHW fp32 [64,3,7,7] -> tcgen05 stem filter: bf16 [28 K-chunks][2 planes (hi, lo)][64 cout][8],
  * K index = r*32 + s*4 + c with zero weights at s = 7 and c = 3 (57,344 bytes).                       */
 int cova_pack_stem_weight(const float* w_oihw, void* packed, void* stream);
 
@@ -95,10 +95,15 @@ int cova_affine_cols_fwd(const float* x, int T, int D, int64_t ld_x, const float
 
 /* ---- generic row-major linear layer  Y[M,N] = act((X[M,K] @ W[N,K]^T + bias) * scale + shift + res)
  * (`nn.Linear` = `models.py:160-164` W_i/W_j, `:85`, `:89`; also the 1x1 convolutions of the ResNet-50
- * Bottleneck on NHWC activations, where `res` is the identity branch); bias/scale/shift/res may be NULL. */
-int cova_linear_fwd(const float* x, int64_t ld_x, int M, int K, const float* w, int N, const float* bias,
+ * Bottleneck on NHWC activations, where `res` is the identity branch); bias/scale/shift/res may be NULL.
+ *   w: engine SIMT -> fp32 [N,K];  engine TCGEN05 -> split-bf16 [2][N][K] from cova_pack_linear_weight
+ *      (needs K % 8 == 0, ld_x % 4 == 0, 16-byte aligned x; otherwise COVA_ERR_ARG - call the SIMT engine). */
+int cova_linear_fwd(const float* x, int64_t ld_x, int M, int K, const void* w, int N, const float* bias,
                     const float* scale, const float* shift, const float* res, int64_t ld_res, int relu, float* y,
                     int64_t ld_y, int engine, void* stream);
+
+/* fp32 [N,K] -> bf16 [2][N][K] (hi plane = bf16(w), lo plane = bf16(w - hi)) for the tcgen05 linear engine. */
+int cova_pack_linear_weight(const float* w, int N, int K, void* packed, void* stream);
 
 /* ---- A6: graph-attention gather.  Replaces `GraphAttentionLayer.forward` lines `models.py:180-208`
  * after the once-per-node projections (algebraically identical restructuring):

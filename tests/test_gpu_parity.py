@@ -254,6 +254,26 @@ def test_linear_kernel(M, K, N):
     assert rel_err(t2n(y), O.linear(x.numpy(), w.numpy())) < 1e-5
 
 
+@pytest.mark.parametrize("M,K,N", [(1, 8, 32), (77, 608, 388), (1440, 992, 992), (130, 992, 4), (300, 2720, 200)])
+def test_linear_tcgen05_kernel(M, K, N):
+    """Tensor-core GEMM (in-kernel fp32 -> swizzled split-bf16 conversion of X, TMA-streamed split W) vs oracle:
+    ragged M/N/K tiles, strided X rows (a column slice of a wider buffer), full epilogue."""
+    o = ops()
+    g = torch.Generator().manual_seed(5)
+    xw = torch.randn(M, K + 8, generator=g)
+    x, w = xw[:, :K], torch.randn(N, K, generator=g) / K ** 0.5
+    b, sc, sh = torch.randn(N, generator=g), 0.5 + torch.rand(N, generator=g), torch.randn(N, generator=g)
+    res = torch.randn(M, N, generator=g)
+    want = np.maximum((O.linear(x.numpy(), w.numpy(), b.numpy()) * sc.numpy() + sh.numpy()) + res.numpy(), 0)
+    xd = xw.to(DEV)[:, :K]
+    wp = o.pack_linear_weight(w.to(DEV))
+    y = o.linear_fwd(xd, wp, b.to(DEV), sc.to(DEV), sh.to(DEV), res=res.to(DEV), relu=True, engine=o.ENGINE_TCGEN05)
+    torch.cuda.synchronize()
+    assert rel_err(t2n(y), want) < 3e-5
+    y = o.linear_fwd(xd, wp, engine=o.ENGINE_TCGEN05)
+    assert rel_err(t2n(y), O.linear(x.numpy(), w.numpy())) < 3e-5
+
+
 def test_gat_layer_golden_edge_cases_and_heads():
     """The layer fixture of the live reference: arbitrary (non-window) ids, an all -1 row, partial padding,
     attention weights, and the 2-head composition."""
@@ -433,11 +453,14 @@ def test_train_step_matches_reference_grads():
     loss.backward()
     assert rel_err(t2n(out), g["logits"]) < 1e-4 and abs(float(loss) - float(g["loss"])) < 1e-3 * abs(float(g["loss"]))
     grads = dict(m.named_parameters())
+    gscale = max(float(np.abs(g[k]).max()) for k in g if k.startswith("grad:"))
     for k in [k for k in g if k.startswith("grad:")]:
-        # gat.W_i only shifts every logit of a row by the same s_i, which the softmax ignores wherever LeakyReLU
-        # is linear: its true gradient is ~1e-9 (rounding noise in both implementations) -> absolute floor.
+        # Two parameters have a mathematically ZERO gradient, so both implementations hold rounding noise only:
+        # gat.W_i shifts every logit of a row by the same s_i (softmax-invariant where LeakyReLU is linear) and
+        # decoder.1.bias is removed by the train-mode BatchNorm that follows it -> absolute floor from the
+        # overall gradient scale.
         got, want = t2n(grads[k[5:]].grad), g[k]
-        assert np.abs(got - want).max() < 2e-3 * np.abs(want).max() + 1e-7, k
+        assert np.abs(got - want).max() < 2e-3 * np.abs(want).max() + 1e-6 * gscale, k
     sd = m.state_dict()
     for k in [k for k in g if k.startswith("buf:")]:
         assert rel_err(t2n(sd[k[4:]]), g[k]) < 1e-4, k
