@@ -207,16 +207,14 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_cons
       const size_t pix = ((size_t)b * p.H + oh) * p.W + ow;
 
       // residual prefetch (independent of the accumulator)
-      uint4 rh[8], rl[8];
+      uint32_t rh[4][8], rl[4][8];      // 64 bf16 per plane = 4 x 32-byte sectors
       const bool has_res = p.res_hi != nullptr;
       if (has_res && inb) {
-        const uint4* ph = reinterpret_cast<const uint4*>(p.res_hi + pix * CT_C);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) rh[j] = __ldg(ph + j);
+        for (int j = 0; j < 4; ++j) ld_global_nc_v8(p.res_hi + pix * CT_C + j * 16, rh[j]);
         if (SPLIT) {
-          const uint4* pl = reinterpret_cast<const uint4*>(p.res_lo + pix * CT_C);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) rl[j] = __ldg(pl + j);
+          for (int j = 0; j < 4; ++j) ld_global_nc_v8(p.res_lo + pix * CT_C + j * 16, rl[j]);
         }
       }
 
@@ -249,47 +247,43 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_cons
       for (int c = 0; c < 64; ++c) o[c] = fmaf(o[c], tail.scale[c], tail.shift[c]);
       if (has_res) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const uint32_t wh[4] = {rh[j].x, rh[j].y, rh[j].z, rh[j].w};
+        for (int j = 0; j < 4; ++j)
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            o[j * 8 + 2 * e] += bf16lo_to_f32(wh[e]);
-            o[j * 8 + 2 * e + 1] += bf16hi_to_f32(wh[e]);
-          }
-          if (SPLIT) {
-            const uint32_t wl[4] = {rl[j].x, rl[j].y, rl[j].z, rl[j].w};
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              o[j * 8 + 2 * e] += bf16lo_to_f32(wl[e]);
-              o[j * 8 + 2 * e + 1] += bf16hi_to_f32(wl[e]);
+          for (int e = 0; e < 8; ++e) {
+            o[j * 16 + 2 * e] += bf16lo_to_f32(rh[j][e]);
+            o[j * 16 + 2 * e + 1] += bf16hi_to_f32(rh[j][e]);
+            if (SPLIT) {
+              o[j * 16 + 2 * e] += bf16lo_to_f32(rl[j][e]);
+              o[j * 16 + 2 * e + 1] += bf16hi_to_f32(rl[j][e]);
             }
           }
-        }
       }
       if (p.relu) {
 #pragma unroll
         for (int c = 0; c < 64; ++c) o[c] = fmaxf(o[c], 0.f);
       }
       if (OUT_DTYPE == COVA_F32) {
-        float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.y0) + pix * CT_C);
-#pragma unroll
-        for (int j = 0; j < 16; ++j) dst[j] = make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
-      } else {
-        uint4* dh = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.y0) + pix * CT_C);
-        uint4* dl = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.y1) + pix * CT_C);
+        float* dst = reinterpret_cast<float*>(p.y0) + pix * CT_C;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          uint32_t hw[4], lw[4];
+          uint32_t w8[8];
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            __nv_bfloat16 h0, l0, h1, l1;
-            split_bf16(o[j * 8 + 2 * e], h0, l0);
-            split_bf16(o[j * 8 + 2 * e + 1], h1, l1);
-            hw[e] = pack_bf16x2(h0, h1);
-            lw[e] = pack_bf16x2(l0, l1);
+          for (int e = 0; e < 8; ++e) w8[e] = __float_as_uint(o[j * 8 + e]);
+          st_global_v8(dst + j * 8, w8);
+        }
+      } else {
+        __nv_bfloat16* dh = reinterpret_cast<__nv_bfloat16*>(p.y0) + pix * CT_C;
+        __nv_bfloat16* dl = reinterpret_cast<__nv_bfloat16*>(p.y1) + pix * CT_C;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          uint32_t hw[8], lw[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            if (OUT_DTYPE == COVA_BF16X2) split_bf16x2(o[j * 16 + 2 * e], o[j * 16 + 2 * e + 1], hw[e], lw[e]);
+            else hw[e] = pack2_bf16(o[j * 16 + 2 * e], o[j * 16 + 2 * e + 1]);
           }
-          dh[j] = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-          if (OUT_DTYPE == COVA_BF16X2) dl[j] = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+          st_global_v8(dh + j * 16, hw);
+          if (OUT_DTYPE == COVA_BF16X2) st_global_v8(dl + j * 16, lw);
         }
       }
     }

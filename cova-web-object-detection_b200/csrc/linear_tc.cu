@@ -135,12 +135,12 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_const
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
         const int r = r0 + 8 * j;
-        __nv_bfloat16 h[4], l[4];
-        split_bf16(v[j].x, h[0], l[0]); split_bf16(v[j].y, h[1], l[1]);
-        split_bf16(v[j].z, h[2], l[2]); split_bf16(v[j].w, h[3], l[3]);
+        uint32_t h01, l01, h23, l23;
+        split_bf16x2(v[j].x, v[j].y, h01, l01);
+        split_bf16x2(v[j].z, v[j].w, h23, l23);
         const uint32_t off = r * 128 + (((c >> 1) ^ (r & 7)) << 4) + (c & 1) * 8;   // 128-B swizzle
-        *reinterpret_cast<uint2*>(sa + off) = make_uint2(pack_bf16x2(h[0], h[1]), pack_bf16x2(h[2], h[3]));
-        *reinterpret_cast<uint2*>(sa + LT_A_PLANE + off) = make_uint2(pack_bf16x2(l[0], l[1]), pack_bf16x2(l[2], l[3]));
+        *reinterpret_cast<uint2*>(sa + off) = make_uint2(h01, h23);
+        *reinterpret_cast<uint2*>(sa + LT_A_PLANE + off) = make_uint2(l01, l23);
       }
       ptx::fence_proxy_async();
       __syncwarp();

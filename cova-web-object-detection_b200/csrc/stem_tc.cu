@@ -219,11 +219,11 @@ stem_tc_kernel(const StemTcParams p) {
         const bool writer = emit && !(lane & 1) && py >= py0 && py < py1 && px < p.Wp;
         const size_t opix = (((size_t)b * p.Hp + py) * p.Wp + px) * 64;
 #pragma unroll
-        for (int c8 = 0; c8 < 64; c8 += 8) {
-          float o[8];
+        for (int c16 = 0; c16 < 64; c16 += 16) {
+          float o[16];
 #pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            const int c = c8 + e;
+          for (int e = 0; e < 16; ++e) {
+            const int c = c16 + e;
             float l = __shfl_up_sync(0xffffffffu, v[c], 1);
             const float r = __shfl_down_sync(0xffffffffu, v[c], 1);
             if (lane == 0) l = left_zero ? 0.f : left[c];
@@ -234,24 +234,23 @@ stem_tc_kernel(const StemTcParams p) {
           }
           if (writer) {
             if (OUT_DTYPE == COVA_F32) {
-              float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out0) + opix + c8);
-              dst[0] = make_float4(o[0], o[1], o[2], o[3]);
-              dst[1] = make_float4(o[4], o[5], o[6], o[7]);
-            } else {
-              uint32_t hw[4], lw[4];
+              float* dst = reinterpret_cast<float*>(p.out0) + opix + c16;
 #pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                __nv_bfloat16 h0, l0, h1, l1;
-                split_bf16(o[2 * e], h0, l0);
-                split_bf16(o[2 * e + 1], h1, l1);
-                hw[e] = pack_bf16x2(h0, h1);
-                lw[e] = pack_bf16x2(l0, l1);
+              for (int hlf = 0; hlf < 2; ++hlf) {
+                uint32_t w8[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) w8[e] = __float_as_uint(o[hlf * 8 + e]);
+                st_global_v8(dst + hlf * 8, w8);
               }
-              *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out0) + opix + c8) =
-                  make_uint4(hw[0], hw[1], hw[2], hw[3]);
-              if (OUT_DTYPE == COVA_BF16X2)
-                *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out1) + opix + c8) =
-                    make_uint4(lw[0], lw[1], lw[2], lw[3]);
+            } else {
+              uint32_t hw[8], lw[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                if (OUT_DTYPE == COVA_BF16X2) split_bf16x2(o[2 * e], o[2 * e + 1], hw[e], lw[e]);
+                else hw[e] = pack2_bf16(o[2 * e], o[2 * e + 1]);
+              }
+              st_global_v8(reinterpret_cast<__nv_bfloat16*>(p.out0) + opix + c16, hw);
+              if (OUT_DTYPE == COVA_BF16X2) st_global_v8(reinterpret_cast<__nv_bfloat16*>(p.out1) + opix + c16, lw);
             }
           }
         }
@@ -287,14 +286,11 @@ stem_tc_kernel(const StemTcParams p) {
       for (int j = 0; j < 9; ++j) {
         const int i = lane + 32 * j;
         if (i < SX_NPX) {
-          __nv_bfloat16 h[3], l[3];
-#pragma unroll
-          for (int c = 0; c < 3; ++c) split_bf16(f[j][c], h[c], l[c]);
-          *reinterpret_cast<uint2*>(dst_hi + i * 8) =
-              make_uint2(pack_bf16x2(h[0], h[1]), (uint32_t)__bfloat16_as_ushort(h[2]));
-          if (SPLIT)
-            *reinterpret_cast<uint2*>(dst_hi + SX_R * SX_ROW_BYTES + i * 8) =
-                make_uint2(pack_bf16x2(l[0], l[1]), (uint32_t)__bfloat16_as_ushort(l[2]));
+          uint32_t h01, l01, h2, l2;
+          split_bf16x2(f[j][0], f[j][1], h01, l01);
+          split_bf16x2(f[j][2], 0.f, h2, l2);
+          *reinterpret_cast<uint2*>(dst_hi + i * 8) = make_uint2(h01, h2);
+          if (SPLIT) *reinterpret_cast<uint2*>(dst_hi + SX_R * SX_ROW_BYTES + i * 8) = make_uint2(l01, l2);
         }
       }
       ptx::fence_proxy_async();      // generic-proxy writes -> visible to tcgen05 (async proxy) reads
