@@ -83,9 +83,10 @@ class ClockSampler:
 def build_model(dev):
     import cova_b200.synth as synth
     from cova_b200.models import CoVA
-    m = CoVA((3, 3), IMG, 4, True, 384, 32, 0, 0.2, None, pretrained=False,
+    bk = os.environ.get("COVA_B200_BACKBONE", "resnet18")     # resnet50 = a side experiment, not the headline config
+    m = CoVA((3, 3), IMG, 4, True, 384, 32, 0, 0.2, None, pretrained=False, backbone=bk,
              engine=os.environ.get("COVA_B200_ENGINE", "tcgen05"), precision=os.environ.get("COVA_B200_PRECISION", "fp32"))
-    m.load_state_dict(synth.make_state_dict(123), strict=True)
+    m.load_state_dict(synth.make_state_dict(123, backbone=bk), strict=True)
     return m.to(dev).eval()
 
 
@@ -298,7 +299,7 @@ def main():
         "data": "synthetic",
         "config": {"workload": "configs[1]: batch=16 synthetic 1280x1280 pages per GPU, N=90 boxes, K=24, "
                                "ResNet-18 backbone, inference", "pages_per_gpu_per_step": B_PER_GPU,
-                   "engine": model.engine, "precision": model.precision,
+                   "engine": model.engine, "precision": model.precision, "backbone": model.backbone,
                    "l2": "inputs larger than L2 (315 MB of images per step vs 126 MB L2); no flush needed"},
         "clocks": clocks, "gpu_launches": launches,
         "e2e": {"value": e2e, "unit": "pages/s", "h2d_bytes_per_step": h2d,

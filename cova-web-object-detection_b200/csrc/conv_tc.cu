@@ -28,7 +28,8 @@
 // Persistent CTAs (grid = #SMs, 1 CTA/SM, 192 threads):
 //   warp 0   TMA producer: all 9 filter taps once (resident, 72 KB per plane), then the activation ring
 //   warp 1   TMEM alloc + single-thread tcgen05.mma issue; tcgen05.commit releases ring slots / publishes tiles
-//   warps 2-5 epilogue: tcgen05.ld (lane = pixel, column = cout), BN scale/shift, residual, ReLU, NHWC stores
+//   warps 2-9 epilogue: tcgen05.ld (lane = pixel, column = cout), BN scale/shift, residual, ReLU, NHWC stores;
+//            two warps per TMEM lane group, 32 output channels each (one warp per scheduler was latency-bound)
 // TMEM accumulator is double-buffered (2 x 64 columns): the epilogue of tile i overlaps the MMAs of tile i+1.
 // The activation ring holds single PLANES (23 KB slots): per tile the hi plane feeds Ahi*Whi + Ahi*Wlo (72 MMAs),
 // the lo plane Alo*Whi (36 MMAs); 3 slots (split) / 6 slots (bf16) keep >= 2 loads in flight next to the
@@ -50,7 +51,8 @@ constexpr int CT_PATCH_BYTES = CT_HW * CT_HH * 128;        // 23,040 bytes lande
 constexpr int CT_SLOT_BYTES = 23 * 1024;                   // ring slot (1024-B aligned for the swizzle atoms)
 constexpr int CT_GROUP_STRIDE = CT_HW * 128;               // 8-row-group stride of a tap view: one patch row
 constexpr int CT_W_TAP_BYTES = CT_C * 128;                 // 8,192: one tap of one plane (64 cout rows x 128 B)
-constexpr int CT_THREADS = 192;
+constexpr int CT_THREADS = 320;                 // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue (2 per TMEM lane group)
+constexpr int CT_EPI_THREADS = 256;
 
 template <bool SPLIT>
 struct ConvTcCfg {
@@ -105,7 +107,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_cons
     }
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(&tail.tmem_full[i], 1);
-      ptx::mbar_init(&tail.tmem_empty[i], 128);
+      ptx::mbar_init(&tail.tmem_empty[i], CT_EPI_THREADS);
     }
     ptx::mbar_init(&tail.wbar, 1);
     ptx::fence_barrier_init();
@@ -193,49 +195,64 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_cons
       }
     }
   } else {
-    // ======================= epilogue warps (TMEM lane group = warp % 4) =======================
+    // ======================= epilogue warps (TMEM lane group = warp % 4; channel half = (warp-2)/4) ==========
     const int lg = warp & 3;
+    const int ch0 = ((warp - 2) >> 2) * 32;       // this warp's 32 output channels
     const int m = lg * 32 + lane;                 // accumulator row = pixel within the tile
     const int py = m >> 3, px = m & 7;
-    uint32_t it = 0;
-    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
-      const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
+    // The residual of tile i+1 is requested before tile i is processed (software pipeline): with the loads issued
+    // only one barrier wait ahead, every tile exposed a full DRAM round trip on the epilogue's critical path.
+    const bool has_res = p.res_hi != nullptr;
+    uint32_t rh[2][8], rl[2][8], rh_n[2][8], rl_n[2][8];      // 32 bf16 per plane = 2 x 32-byte sectors
+    auto tile_pix = [&](int tile, bool& inb) -> size_t {
       const int b = tile / (p.tiles_h * p.tiles_w);
       const int th = (tile / p.tiles_w) % p.tiles_h, tw = tile % p.tiles_w;
       const int oh = th * CT_TH + py, ow = tw * CT_TW + px;
-      const bool inb = oh < p.H && ow < p.W;
-      const size_t pix = ((size_t)b * p.H + oh) * p.W + ow;
-
-      // residual prefetch (independent of the accumulator)
-      uint32_t rh[4][8], rl[4][8];      // 64 bf16 per plane = 4 x 32-byte sectors
-      const bool has_res = p.res_hi != nullptr;
-      if (has_res && inb) {
+      inb = oh < p.H && ow < p.W;
+      return (((size_t)b * p.H + oh) * p.W + ow) * CT_C + ch0;
+    };
+    auto load_res = [&](int tile) {
+      bool ok;
+      const size_t px_off = tile_pix(tile, ok);
+      if (has_res && tile < p.n_tiles && ok) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) ld_global_nc_v8(p.res_hi + pix * CT_C + j * 16, rh[j]);
+        for (int j = 0; j < 2; ++j) ld_global_nc_v8(p.res_hi + px_off + j * 16, rh_n[j]);
         if (SPLIT) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) ld_global_nc_v8(p.res_lo + pix * CT_C + j * 16, rl[j]);
+          for (int j = 0; j < 2; ++j) ld_global_nc_v8(p.res_lo + px_off + j * 16, rl_n[j]);
         }
       }
+    };
+    load_res(blockIdx.x);
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
+      const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
+      bool inb;
+      const size_t pix = tile_pix(tile, inb);
+#pragma unroll
+      for (int j = 0; j < 2; ++j)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { rh[j][e] = rh_n[j][e]; rl[j][e] = rl_n[j][e]; }
+      load_res(tile + gridDim.x);
 
       ptx::mbar_wait(&tail.tmem_full[acc], acc_phase);
       ptx::tc_fence_after();
-      uint32_t v[4][16];
-      const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + acc * Cfg::ACC_COLS;
+      uint32_t v[2][16];
+      const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + acc * Cfg::ACC_COLS + ch0;
 #pragma unroll
-      for (int q = 0; q < 4; ++q) ptx::tmem_ld16(taddr + q * 16, v[q]);
+      for (int q = 0; q < 2; ++q) ptx::tmem_ld16(taddr + q * 16, v[q]);
       ptx::tmem_ld_wait();
-      float o[64];
+      float o[32];
 #pragma unroll
-      for (int q = 0; q < 4; ++q)
+      for (int q = 0; q < 2; ++q)
 #pragma unroll
         for (int j = 0; j < 16; ++j) o[q * 16 + j] = __uint_as_float(v[q][j]);
       if (SPLIT) {   // columns 64..127 hold Ahi*Wlo
 #pragma unroll
-        for (int q = 0; q < 4; ++q) ptx::tmem_ld16(taddr + CT_C + q * 16, v[q]);
+        for (int q = 0; q < 2; ++q) ptx::tmem_ld16(taddr + CT_C + q * 16, v[q]);
         ptx::tmem_ld_wait();
 #pragma unroll
-        for (int q = 0; q < 4; ++q)
+        for (int q = 0; q < 2; ++q)
 #pragma unroll
           for (int j = 0; j < 16; ++j) o[q * 16 + j] += __uint_as_float(v[q][j]);
       }
@@ -244,10 +261,10 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_cons
 
       if (!inb) continue;
 #pragma unroll
-      for (int c = 0; c < 64; ++c) o[c] = fmaf(o[c], tail.scale[c], tail.shift[c]);
+      for (int c = 0; c < 32; ++c) o[c] = fmaf(o[c], tail.scale[ch0 + c], tail.shift[ch0 + c]);
       if (has_res) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
+        for (int j = 0; j < 2; ++j)
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
             o[j * 16 + 2 * e] += bf16lo_to_f32(rh[j][e]);
@@ -260,22 +277,22 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_cons
       }
       if (p.relu) {
 #pragma unroll
-        for (int c = 0; c < 64; ++c) o[c] = fmaxf(o[c], 0.f);
+        for (int c = 0; c < 32; ++c) o[c] = fmaxf(o[c], 0.f);
       }
       if (OUT_DTYPE == COVA_F32) {
-        float* dst = reinterpret_cast<float*>(p.y0) + pix * CT_C;
+        float* dst = reinterpret_cast<float*>(p.y0) + pix;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
+        for (int j = 0; j < 4; ++j) {
           uint32_t w8[8];
 #pragma unroll
           for (int e = 0; e < 8; ++e) w8[e] = __float_as_uint(o[j * 8 + e]);
           st_global_v8(dst + j * 8, w8);
         }
       } else {
-        __nv_bfloat16* dh = reinterpret_cast<__nv_bfloat16*>(p.y0) + pix * CT_C;
-        __nv_bfloat16* dl = reinterpret_cast<__nv_bfloat16*>(p.y1) + pix * CT_C;
+        __nv_bfloat16* dh = reinterpret_cast<__nv_bfloat16*>(p.y0) + pix;
+        __nv_bfloat16* dl = reinterpret_cast<__nv_bfloat16*>(p.y1) + pix;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < 2; ++j) {
           uint32_t hw[8], lw[8];
 #pragma unroll
           for (int e = 0; e < 8; ++e) {

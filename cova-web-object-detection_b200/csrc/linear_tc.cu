@@ -39,7 +39,9 @@ struct LinearTcParams {
   const float* res;
   int64_t ldr;
   int relu;
-  float* y;
+  int out_dtype;          // COVA_F32: y0 fp32;  COVA_BF16X2: y0 = hi plane, y1 = lo plane (bf16), ldy in elements
+  void* y0;
+  void* y1;
   int64_t ldy;
 };
 
@@ -152,22 +154,58 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_const
     const int m = m0 + lg * 32 + lane;
     ptx::mbar_wait(&tail.acc_full, 0);
     ptx::tc_fence_after();
+    const bool vec_ok = (p.ldy % 16 == 0) && ((reinterpret_cast<uintptr_t>(p.y0) & 31) == 0) &&
+                        (p.y1 == nullptr || (reinterpret_cast<uintptr_t>(p.y1) & 31) == 0);
 #pragma unroll 1
     for (int q = 0; q < LT_BN / 16; ++q) {
       uint32_t raw[16];
       ptx::tmem_ld16(tmem_base + ((uint32_t)(lg * 32) << 16) + q * 16, raw);
       ptx::tmem_ld_wait();
-      if (m < p.M) {
+      const int nb = n0 + q * 16;
+      if (m < p.M && nb < p.N) {
+        float v[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-          const int n = n0 + q * 16 + j;
+          const int n = nb + j;
+          float x = __uint_as_float(raw[j]);
           if (n < p.N) {
-            float v = __uint_as_float(raw[j]);
-            if (p.bias) v += p.bias[n];
-            if (p.scale) v = fmaf(v, p.scale[n], p.shift[n]);
-            if (p.res) v += p.res[(size_t)m * p.ldr + n];
-            if (p.relu) v = fmaxf(v, 0.f);
-            p.y[(size_t)m * p.ldy + n] = v;
+            if (p.bias) x += p.bias[n];
+            if (p.scale) x = fmaf(x, p.scale[n], p.shift[n]);
+            if (p.res) x += p.res[(size_t)m * p.ldr + n];
+            if (p.relu) x = fmaxf(x, 0.f);
+          }
+          v[j] = x;
+        }
+        const size_t o = (size_t)m * p.ldy + nb;
+        const bool full = nb + 16 <= p.N && vec_ok;
+        if (p.out_dtype == COVA_F32) {
+          float* y = reinterpret_cast<float*>(p.y0);
+          if (full) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              uint32_t w8[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) w8[e] = __float_as_uint(v[h * 8 + e]);
+              st_global_v8(y + o + h * 8, w8);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (nb + j < p.N) y[o + j] = v[j];
+          }
+        } else {
+          __nv_bfloat16* yh = reinterpret_cast<__nv_bfloat16*>(p.y0);
+          __nv_bfloat16* yl = reinterpret_cast<__nv_bfloat16*>(p.y1);
+          if (full) {
+            uint32_t hw[8], lw[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) split_bf16x2(v[2 * e], v[2 * e + 1], hw[e], lw[e]);
+            st_global_v8(yh + o, hw);
+            st_global_v8(yl + o, lw);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (nb + j < p.N) split_bf16(v[j], yh[o + j], yl[o + j]);
           }
         }
       }
@@ -196,8 +234,8 @@ bool linear_tc_supported(const float* x, int64_t ld_x, int K) {
 }
 
 int linear_tc(const float* x, int64_t ld_x, int M, int K, const void* w_packed, int N, const float* bias,
-              const float* scale, const float* shift, const float* res, int64_t ld_res, int relu, float* y,
-              int64_t ld_y, cudaStream_t st) {
+              const float* scale, const float* shift, const float* res, int64_t ld_res, int relu, int out_dtype,
+              void* y0, void* y1, int64_t ld_y, cudaStream_t st) {
   CUtensorMap tw_hi, tw_lo;
   const uint64_t wd[2] = {(uint64_t)K, (uint64_t)N};
   const uint64_t ws[1] = {(uint64_t)K * 2};
@@ -206,7 +244,7 @@ int linear_tc(const float* x, int64_t ld_x, int M, int K, const void* w_packed, 
   int rc;
   if ((rc = make_tmap_bf16(&tw_hi, wp, 2, wd, ws, wb))) return rc;
   if ((rc = make_tmap_bf16(&tw_lo, wp + (size_t)N * K, 2, wd, ws, wb))) return rc;
-  LinearTcParams p{x, ld_x, M, K, N, bias, scale, shift, res, ld_res, relu, y, ld_y};
+  LinearTcParams p{x, ld_x, M, K, N, bias, scale, shift, res, ld_res, relu, out_dtype, y0, y1, ld_y};
   COVA_CUDA_OK(cudaFuncSetAttribute(linear_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LT_SMEM));
   dim3 grid(ceil_div(N, LT_BN), ceil_div(M, LT_BM));
   linear_tc_kernel<<<grid, LT_THREADS, LT_SMEM, st>>>(tw_hi, tw_lo, p);

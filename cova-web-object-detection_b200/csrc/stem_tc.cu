@@ -36,7 +36,8 @@ constexpr int SX_W_CHUNK = 2 * 64 * 16;    // 2,048 B: one K-chunk = 64 hi rows 
 constexpr int SX_W_BYTES = SX_KCHUNKS * SX_W_CHUNK;   // 57,344 B: [chunk][plane][cout][8] bf16
 constexpr int SX_MAXROWS = 81;             // conv rows per band (2*40 + 1)
 constexpr int SX_ND = 16;                  // tile-row completion barriers
-constexpr int SX_THREADS = 288;            // warp 0 MMA, warps 1-4 epilogue, warps 5-8 converters
+constexpr int SX_THREADS = 416;            // warp 0 MMA, warps 1-8 epilogue (2 per TMEM lane group), warps 9-12 converters
+constexpr int SX_EPI_THREADS = 256;
 
 
 template <bool SPLIT>
@@ -99,7 +100,7 @@ stem_tc_kernel(const StemTcParams p) {
     for (int i = 0; i < SX_ND; ++i) ptx::mbar_init(&sm.mma_done[i], 1);
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(&sm.tmem_full[i], 1);
-      ptx::mbar_init(&sm.tmem_empty[i], 128);
+      ptx::mbar_init(&sm.tmem_empty[i], SX_EPI_THREADS);
     }
     ptx::mbar_init(&sm.wbar, 1);
     ptx::fence_barrier_init();
@@ -156,70 +157,71 @@ stem_tc_kernel(const StemTcParams p) {
         __syncwarp();
       }
     }
-  } else if (warp <= 4) {
+  } else if (warp <= 8) {
     // ======================= epilogue: BN + ReLU + 3x3/s2 max-pool =======================
     const int lg = warp & 3;                       // TMEM lane group this warp may read
+    const int ch0 = ((warp - 1) >> 2) * 32;        // this warp's 32 output channels (two warps per lane group)
     const int m = lg * 32 + lane;                  // conv column within the strip
-    float acc_v[64];                               // running vertical max of the current pooling window
+    float acc_v[32];                               // running vertical max of the current pooling window
     uint32_t t = 0;
     for (int strip = 0; strip < n_strips; ++strip) {
       const int ox = strip * SX_TM + m;
 #pragma unroll
-      for (int c = 0; c < 64; ++c) acc_v[c] = 0.f;   // post-ReLU values are >= 0: 0 is the neutral element
+      for (int c = 0; c < 32; ++c) acc_v[c] = 0.f;   // post-ReLU values are >= 0: 0 is the neutral element
       for (int i = 0; i < n_conv; ++i, ++t) {
         const int oy = oy_begin + i;
         const uint32_t acc = t & 1;
         ptx::mbar_wait(&sm.tmem_full[acc], (t >> 1) & 1);
         ptx::tc_fence_after();
-        uint32_t raw[4][16];
-        const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + acc * ACC_COLS;
+        uint32_t raw[2][16];
+        const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + acc * ACC_COLS + ch0;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) ptx::tmem_ld16(taddr + q * 16, raw[q]);
+        for (int q = 0; q < 2; ++q) ptx::tmem_ld16(taddr + q * 16, raw[q]);
         ptx::tmem_ld_wait();
-        float v[64];
+        float v[32];
 #pragma unroll
-        for (int q = 0; q < 4; ++q)
+        for (int q = 0; q < 2; ++q)
 #pragma unroll
           for (int j = 0; j < 16; ++j) v[q * 16 + j] = __uint_as_float(raw[q][j]);
         if (SPLIT) {   // columns 64..127 hold Ahi*Wlo
 #pragma unroll
-          for (int q = 0; q < 4; ++q) ptx::tmem_ld16(taddr + 64 + q * 16, raw[q]);
+          for (int q = 0; q < 2; ++q) ptx::tmem_ld16(taddr + 64 + q * 16, raw[q]);
           ptx::tmem_ld_wait();
 #pragma unroll
-          for (int q = 0; q < 4; ++q)
+          for (int q = 0; q < 2; ++q)
 #pragma unroll
             for (int j = 0; j < 16; ++j) v[q * 16 + j] += __uint_as_float(raw[q][j]);
         }
         ptx::tc_fence_before();
         ptx::mbar_arrive(&sm.tmem_empty[acc]);
 
-        const bool in_w = ox < p.Wc;
 #pragma unroll
-        for (int c = 0; c < 64; ++c) {
-          const float y = fmaxf(fmaf(v[c], sm.scale[c], sm.shift[c]), 0.f);
-          v[c] = in_w ? y : 0.f;
+        for (int c = 0; c < 32; ++c) v[c] = fmaxf(fmaf(v[c], sm.scale[ch0 + c], sm.shift[ch0 + c]), 0.f);
+        if (ox >= p.Wc) {   // conv columns past the image (last, partial strip only) act as pool padding
+#pragma unroll
+          for (int c = 0; c < 32; ++c) v[c] = 0.f;
         }
-        // lane 31 publishes its column for the next warp (and, from the last warp, for the next strip)
-        float* xrow = sm.xch[t & 1][lg];
+        // lane 31 publishes its column for the next warp (and, from the last lane group, for the next strip)
+        float* xrow = sm.xch[t & 1][lg] + ch0;
         if (lane == 31) {
 #pragma unroll
-          for (int c = 0; c < 64; c += 4) *reinterpret_cast<float4*>(xrow + c) = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
+          for (int c = 0; c < 32; c += 4) *reinterpret_cast<float4*>(xrow + c) = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
           if (lg == 3) {
-            float* e = sm.edge[strip & 1][i];
+            float* e = sm.edge[strip & 1][i] + ch0;
 #pragma unroll
-            for (int c = 0; c < 64; c += 4) *reinterpret_cast<float4*>(e + c) = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
+            for (int c = 0; c < 32; c += 4) *reinterpret_cast<float4*>(e + c) = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
           }
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        const float* left = lg > 0 ? sm.xch[t & 1][lg - 1] : sm.edge[(strip & 1) ^ 1][i];
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        const float* left = (lg > 0 ? sm.xch[t & 1][lg - 1] : sm.edge[(strip & 1) ^ 1][i]) + ch0;
         const bool left_zero = (lg == 0 && strip == 0);            // conv column -1 = pool padding
         const bool emit = (oy & 1) || (oy == p.Hc - 1);
         const int py = oy >> 1;
         const int px = ox >> 1;
         const bool writer = emit && !(lane & 1) && py >= py0 && py < py1 && px < p.Wp;
-        const size_t opix = (((size_t)b * p.Hp + py) * p.Wp + px) * 64;
+        const size_t opix = (((size_t)b * p.Hp + py) * p.Wp + px) * 64 + ch0;
 #pragma unroll
-        for (int c16 = 0; c16 < 64; c16 += 16) {
+        for (int c16 = 0; c16 < 32; c16 += 16) {
           float o[16];
 #pragma unroll
           for (int e = 0; e < 16; ++e) {
@@ -258,7 +260,7 @@ stem_tc_kernel(const StemTcParams p) {
     }
   } else {
     // ======================= converters: NCHW fp32 rows -> ring of 4-channel bf16 pixels =======================
-    const int cw = warp - 5;                        // this warp owns input rows g with g % 4 == cw
+    const int cw = warp - 9;                        // this warp owns input rows g with g % 4 == cw
     const float* img_b = p.img + (size_t)b * 3 * p.H * p.W;
     const size_t plane = (size_t)p.H * p.W;
     const uint32_t n_rows_total = (uint32_t)n_strips * NQ;

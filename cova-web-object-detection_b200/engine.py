@@ -40,10 +40,11 @@ class NativeForward:
         if key == self._key:
             return
         m, c = self.m, {}
-        tc = m.engine == "tcgen05" and m.backbone == "resnet18"
-        split = m.precision == "fp32"
+        r50 = m.backbone == "resnet50"
+        tc = m.engine == "tcgen05"
+        split = m.precision == "fp32" or r50          # the ResNet-50 tensor-core path is fp32-parity only
         c["tc"] = tc
-        c["act_dtype"] = (BF16X2 if split else BF16) if tc else F32
+        c["act_dtype"] = F32 if (r50 or not tc) else (BF16X2 if split else BF16)
         cn = m.convnet
         c["stem_w"] = cn[0].weight.detach().float().contiguous()
         if tc:
@@ -58,10 +59,15 @@ class NativeForward:
                     s, hi, lo = ops.pack_conv_weight(conv.weight.detach().float(), simt=not tc, tc=tc, split=split)
                     d[f"w{i}"] = (hi, lo) if tc else (s, None)
                     d[f"bn{i}"] = fold_bn(bn)
-            else:  # Bottleneck: 1x1 convs are row-major GEMMs on NHWC, 3x3 on the CUDA-core engine
+            else:  # Bottleneck: the 1x1 convs are row-major GEMMs on the NHWC pixel rows
                 d["w1"] = blk.conv1.weight.detach().float().flatten(1).contiguous()
-                d["w2"] = ops.pack_conv_weight(blk.conv2.weight.detach().float(), simt=True, tc=False)[0]
+                s2, hi2, lo2 = ops.pack_conv_weight(blk.conv2.weight.detach().float(), simt=not tc, tc=tc, split=True)
+                d["w2"] = (hi2, lo2) if tc else (s2, None)
                 d["w3"] = blk.conv3.weight.detach().float().flatten(1).contiguous()
+                if tc:
+                    d["w1_p"], d["w3_p"] = ops.pack_linear_weight(d["w1"]), ops.pack_linear_weight(d["w3"])
+                    if blk.downsample is not None:
+                        d["wd_p"] = ops.pack_linear_weight(blk.downsample[0].weight.detach().float().flatten(1).contiguous())
                 for i in (1, 2, 3):
                     d[f"bn{i}"] = fold_bn(getattr(blk, f"bn{i}"))
                 if blk.downsample is not None:
@@ -125,16 +131,24 @@ class NativeForward:
                 x = ops.conv3x3_bn_act_fwd(y, d["w2"][0], d["w2"][1], *d["bn2"], res=x, relu=True,
                                            out_dtype=F32 if last else None, engine=eng)
             return x.p0
-        # resnet50 Bottlenecks (CUDA-core fp32 engine)
+        # resnet50 Bottlenecks: 1x1 conv = GEMM over the [B*H*W, C] pixel rows, 3x3 = the BasicBlock kernel
         B, H, W, _ = x.shape
         cur = x.p0.view(B * H * W, 64)
         for d in c["blocks"]:
-            o = ops.linear_fwd(cur, d["w1"], None, *d["bn1"], relu=True)
-            p = ops.Planes.__new__(ops.Planes)
-            p.dtype, p.shape, p.p0, p.p1 = F32, (B, H, W, 64), o.view(B, H, W, 64), None
-            o = ops.conv3x3_bn_act_fwd(p, d["w2"], None, *d["bn2"], relu=True, engine=ENGINE_SIMT).p0.view(B * H * W, 64)
-            idt = ops.linear_fwd(cur, d["wd"], None, *d["bnd"]) if "wd" in d else cur
-            cur = ops.linear_fwd(o, d["w3"], None, *d["bn3"], res=idt, relu=True)
+            if c["tc"]:   # conv1 writes split-bf16 planes straight into the 3x3 tensor-core conv, which returns fp32
+                p = ops.linear_fwd(cur, d["w1_p"], None, *d["bn1"], relu=True, engine=ENGINE_TCGEN05, out_planes=True)
+                p.shape = (B, H, W, 64)
+                o = ops.conv3x3_bn_act_fwd(p, d["w2"][0], d["w2"][1], *d["bn2"], relu=True, out_dtype=F32,
+                                           engine=ENGINE_TCGEN05).p0.view(B * H * W, 64)
+                idt = (ops.linear_fwd(cur, d["wd_p"], None, *d["bnd"], engine=ENGINE_TCGEN05) if "wd" in d else cur)
+                cur = ops.linear_fwd(o, d["w3_p"], None, *d["bn3"], res=idt, relu=True, engine=ENGINE_TCGEN05)
+            else:
+                o = ops.linear_fwd(cur, d["w1"], None, *d["bn1"], relu=True)
+                p = ops.Planes.__new__(ops.Planes)
+                p.dtype, p.shape, p.p0, p.p1 = F32, (B, H, W, 64), o.view(B, H, W, 64), None
+                o = ops.conv3x3_bn_act_fwd(p, d["w2"][0], None, *d["bn2"], relu=True, engine=ENGINE_SIMT).p0.view(B * H * W, 64)
+                idt = ops.linear_fwd(cur, d["wd"], None, *d["bnd"]) if "wd" in d else cur
+                cur = ops.linear_fwd(o, d["w3"], None, *d["bn3"], res=idt, relu=True)
         return cur.view(B, H, W, 256)
 
     def own_into(self, fm, bboxes, additional_feats, comb):

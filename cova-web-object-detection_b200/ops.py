@@ -154,21 +154,27 @@ def linear_tc_ok(x):
     return x.shape[1] % 8 == 0 and x.stride(0) % 4 == 0 and x.data_ptr() % 16 == 0
 
 
-def linear_fwd(x, w, bias=None, scale=None, shift=None, res=None, relu=False, out=None, engine=ENGINE_SIMT):
+def linear_fwd(x, w, bias=None, scale=None, shift=None, res=None, relu=False, out=None, engine=ENGINE_SIMT,
+               out_planes=False):
     """Y = act((X @ W^T + bias) * scale + shift + res); x [M,K] (row stride free);
-    w = fp32 [N,K] (SIMT engine) or the packed split-bf16 [2,N,K] (tcgen05 engine)."""
+    w = fp32 [N,K] (SIMT engine) or the packed split-bf16 [2,N,K] (tcgen05 engine).
+    out_planes=True (tcgen05 only): returns split-bf16 `Planes` [1,1,M,N] instead of an fp32 tensor."""
     _cuda(x, torch.float32, "x")
     M, K = x.shape
     N = w.shape[-2]
     assert x.stride(1) == 1 and w.is_contiguous() and w.shape[-1] == K
     assert (w.dtype == torch.bfloat16 and w.dim() == 3) == (engine == ENGINE_TCGEN05)
-    if out is None:
-        out = torch.empty((M, N), dtype=torch.float32, device=x.device)
-    assert out.stride(1) == 1
+    if out_planes:
+        pl = Planes(BF16X2, (1, 1, M, N), x.device)
+        y0, y1, ldy, odt = pl.p0.data_ptr(), pl.p1.data_ptr(), N, BF16X2
+    else:
+        if out is None:
+            out = torch.empty((M, N), dtype=torch.float32, device=x.device)
+        assert out.stride(1) == 1
+        y0, y1, ldy, odt = out.data_ptr(), 0, out.stride(0), F32
     _call("cova_linear_fwd", x.data_ptr(), x.stride(0), M, K, w.data_ptr(), N, _ptr(bias), _ptr(scale), _ptr(shift),
-          _ptr(res), res.stride(0) if res is not None else 0, int(relu), out.data_ptr(), out.stride(0), engine,
-          _stream())
-    return out
+          _ptr(res), res.stride(0) if res is not None else 0, int(relu), odt, y0, y1, ldy, engine, _stream())
+    return pl if out_planes else out
 
 
 def gat_fwd(whj, s, t, att_b, alpha, ctx_idx, out, want_attn=False):

@@ -99,8 +99,10 @@ int cova_affine_cols_fwd(const float* x, int T, int D, int64_t ld_x, const float
  *   w: engine SIMT -> fp32 [N,K];  engine TCGEN05 -> split-bf16 [2][N][K] from cova_pack_linear_weight
  *      (needs K % 8 == 0, ld_x % 4 == 0, 16-byte aligned x; otherwise COVA_ERR_ARG - call the SIMT engine). */
 int cova_linear_fwd(const float* x, int64_t ld_x, int M, int K, const void* w, int N, const float* bias,
-                    const float* scale, const float* shift, const float* res, int64_t ld_res, int relu, float* y,
-                    int64_t ld_y, int engine, void* stream);
+                    const float* scale, const float* shift, const float* res, int64_t ld_res, int relu,
+                    int out_dtype, void* y0, void* y1, int64_t ld_y, int engine, void* stream);
+/*   out_dtype COVA_F32: y0 = fp32 [M, ld_y];  COVA_BF16X2 (tcgen05 engine only): y0 / y1 = bf16 hi / lo planes
+ *   (ld_y in elements) - feeds cova_conv3x3_bn_act_fwd directly (ResNet-50 conv1 -> conv2).                 */
 
 /* fp32 [N,K] -> bf16 [2][N][K] (hi plane = bf16(w), lo plane = bf16(w - hi)) for the tcgen05 linear engine. */
 int cova_pack_linear_weight(const float* w, int N, int K, void* packed, void* stream);
