@@ -215,12 +215,13 @@ def main():
         with torch.no_grad():
             return model(*dinp)
 
-    def run_e2e(steps):
+    def run_e2e(steps, host=None):
         """Public-API path with HOST buffers: every step copies its own pinned inputs to the device
         (cova_b200.pipeline.prefetch: side-stream H2D one batch ahead of the compute) and reads its logits back."""
         from cova_b200.pipeline import prefetch
+        host = pinned if host is None else host
         with torch.no_grad():
-            for d in prefetch((pinned for _ in range(steps)), dev):
+            for d in prefetch((host for _ in range(steps)), dev):
                 logits_host.copy_(model(*d), non_blocking=True)
 
     def timed(fn, steps, whole=False):
@@ -250,6 +251,10 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
     run_e2e(3)
     ms_e2e = timed(run_e2e, args.steps, whole=True)
+    # SURVEY 8(f) N1 (optional input format): the same pages as raw uint8 pixels, converted v/255 inside the stem
+    pinned_u8 = [(inp[0] * 255).round().to(torch.uint8).pin_memory()] + pinned[1:]
+    run_e2e(3, pinned_u8)
+    ms_e2e_u8 = timed(lambda k: run_e2e(k, pinned_u8), args.steps, whole=True)
 
     pages = B_PER_GPU * world * args.steps
     value, e2e = pages / (ms / 1e3), pages / (ms_e2e / 1e3)
@@ -270,6 +275,10 @@ def main():
         "cova_linear_fwd": ("tensor", 2 * T * (608 * 388 + 992 * 992 + 992 * 4)),
         "cova_bbox_enc_fwd": ("hbm", T * (20 + 32 * 4)),
     }
+    traffic = {}
+    tp = os.path.join(ROOT, "profiles", "traffic_r01.json")    # dram__bytes per launch from the committed ncu capture
+    if os.path.exists(tp) and model.backbone == "resnet18" and model.precision == "fp32" and model.engine == "tcgen05":
+        traffic = {k: v["dram_bytes_per_launch"] for k, v in json.load(open(tp)).items() if not k.startswith("_")}
     kernels = {}
     for n, (msn, cnt) in stages.items():
         kind, work = alg.get(n, ("hbm", 0))
@@ -277,14 +286,15 @@ def main():
         peak = pk["tf_sust"] if kind == "tensor" else pk["hbm"]
         kernels[n] = {"ms_per_step": round(msn, 4), "launches_per_step": cnt, "bound": kind,
                       "achieved": round(ach, 2), "unit": "TFLOP/s" if kind == "tensor" else "GB/s",
-                      "frac": round(ach / peak, 4)}
+                      "frac": round(ach / peak, 4), "traffic": traffic.get(n)}
     dom = max(stages, key=lambda n: stages[n][0])
     kind, work = alg.get(dom, ("hbm", 0))
     n_l = stages[dom][1]
     ach = (work / n_l) / (stages[dom][0] / n_l / 1e3) / (1e12 if kind == "tensor" else 1e9)
     peak = pk["tf_sust"] if kind == "tensor" else pk["hbm"]
     roofline = {"kernel": dom, "bound": kind, "achieved": round(ach, 3), "peak": peak,
-                "unit": "TFLOP/s" if kind == "tensor" else "GB/s", "frac": round(ach / peak, 4), "traffic": None,
+                "unit": "TFLOP/s" if kind == "tensor" else "GB/s", "frac": round(ach / peak, 4),
+                "traffic": traffic.get(dom), "algorithmic_per_launch": work / n_l,
                 "peak_source": pk["src"] + (" (sustained bf16: kernel timed inside the step)" if kind == "tensor" else ""),
                 "share_of_step": round(stages[dom][0] / sum(v[0] for v in stages.values()), 3)}
 
@@ -303,7 +313,12 @@ def main():
                    "l2": "inputs larger than L2 (315 MB of images per step vs 126 MB L2); no flush needed"},
         "clocks": clocks, "gpu_launches": launches,
         "e2e": {"value": e2e, "unit": "pages/s", "h2d_bytes_per_step": h2d,
-                "d2h_bytes_per_step": logits_host.numel() * 4, "ms_per_step": ms_e2e / args.steps},
+                "d2h_bytes_per_step": logits_host.numel() * 4, "ms_per_step": ms_e2e / args.steps,
+                "note": "fp32 NCHW images = the reference's input contract; PCIe-bound (h2d bytes / ms)"},
+        "e2e_uint8_images": {"value": pages / (ms_e2e_u8 / 1e3), "unit": "pages/s",
+                             "h2d_bytes_per_step": sum(t.numel() * t.element_size() for t in pinned_u8),
+                             "ms_per_step": ms_e2e_u8 / args.steps,
+                             "note": "optional input format (SURVEY 8(f) N1): uint8 pixels, v/255 in the stem kernel"},
         "roofline": roofline, "kernels": kernels,
         "cpu_baseline": {"value": cpu_v, "unit": "pages/s", "cores": cores, "kind": "port", "sample": sample},
     }))

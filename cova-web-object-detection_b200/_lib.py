@@ -18,7 +18,7 @@ NVCC_FLAGS = [
     "-Xcompiler", "-fPIC", "-shared", "--cudart", "static",
 ]
 
-F32, BF16, BF16X2 = 0, 1, 2
+F32, BF16, BF16X2, U8 = 0, 1, 2, 3
 ENGINE_SIMT, ENGINE_TCGEN05 = 0, 1
 
 
@@ -56,7 +56,7 @@ SIGNATURES = {
     "cova_abi_version": (_I, []),
     "cova_last_error": (_c.c_char_p, []),
     "cova_device_info": (_I, [_c.POINTER(_I), _c.POINTER(_I)]),
-    "cova_stem_fwd": (_I, [_P, _I, _I, _I, _P, _P, _P, _I, _P, _P, _I, _P]),
+    "cova_stem_fwd": (_I, [_P, _I, _I, _I, _I, _P, _P, _P, _I, _P, _P, _I, _P]),
     "cova_conv3x3_bn_act_fwd": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _I, _I, _P, _P, _I, _P]),
     "cova_pack_conv_weight": (_I, [_P, _I, _I, _I, _I, _P, _P, _P, _P]),
     "cova_pack_stem_weight": (_I, [_P, _P, _P]),

@@ -2,9 +2,9 @@
 #include "common.cuh"
 
 namespace cova {
-int stem_simt(const float* images, int B, int H, int W, const float* w, const float* bn_scale, const float* bn_shift,
-              int out_dtype, void* out0, void* out1, cudaStream_t st);
-int stem_tc(const float* images, int B, int H, int W, const void* w_packed, const float* bn_scale,
+int stem_simt(const void* images, int img_u8, int B, int H, int W, const float* w, const float* bn_scale,
+              const float* bn_shift, int out_dtype, void* out0, void* out1, cudaStream_t st);
+int stem_tc(const void* images, int img_u8, int B, int H, int W, const void* w_packed, const float* bn_scale,
             const float* bn_shift, int out_dtype, void* out0, void* out1, cudaStream_t st);
 int conv3x3_simt(const float* x, int B, int H, int W, const float* w, const float* bn_scale, const float* bn_shift,
                  const float* res, int relu, float* y, cudaStream_t st);
@@ -24,16 +24,19 @@ using namespace cova;
 
 static bool dtype_ok(int d) { return d == COVA_F32 || d == COVA_BF16 || d == COVA_BF16X2; }
 
-extern "C" int cova_stem_fwd(const float* images, int B, int H, int W, const void* w, const float* bn_scale,
+extern "C" int cova_stem_fwd(const void* images, int img_dtype, int B, int H, int W, const void* w, const float* bn_scale,
                              const float* bn_shift, int out_dtype, void* out0, void* out1, int engine, void* stream) {
   COVA_REQUIRE(images && w && bn_scale && bn_shift && out0, "cova_stem_fwd: null pointer");
   COVA_REQUIRE(B > 0 && H >= 7 && W >= 7, "cova_stem_fwd: bad dims B=%d H=%d W=%d", B, H, W);
   COVA_REQUIRE(dtype_ok(out_dtype), "cova_stem_fwd: bad out_dtype %d", out_dtype);
+  COVA_REQUIRE(img_dtype == COVA_F32 || img_dtype == COVA_U8, "cova_stem_fwd: images must be fp32 or uint8");
+  const int u8 = img_dtype == COVA_U8;
   COVA_REQUIRE(out_dtype != COVA_BF16X2 || out1, "cova_stem_fwd: BF16X2 output needs the lo plane");
   COVA_REQUIRE(engine == COVA_ENGINE_SIMT || engine == COVA_ENGINE_TCGEN05, "cova_stem_fwd: bad engine");
   if (engine == COVA_ENGINE_TCGEN05)
-    return stem_tc(images, B, H, W, w, bn_scale, bn_shift, out_dtype, out0, out1, (cudaStream_t)stream);
-  return stem_simt(images, B, H, W, (const float*)w, bn_scale, bn_shift, out_dtype, out0, out1, (cudaStream_t)stream);
+    return stem_tc(images, u8, B, H, W, w, bn_scale, bn_shift, out_dtype, out0, out1, (cudaStream_t)stream);
+  return stem_simt(images, u8, B, H, W, (const float*)w, bn_scale, bn_shift, out_dtype, out0, out1,
+                   (cudaStream_t)stream);
 }
 
 extern "C" int cova_conv3x3_bn_act_fwd(const void* x0, const void* x1, int dtype, int B, int H, int W, int Cin, int Cout,

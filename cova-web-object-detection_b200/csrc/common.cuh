@@ -35,6 +35,13 @@ int max_smem_optin();    // bytes
 
 __host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
+// image pixel fetch: fp32 as is, or uint8 -> v/255 with IEEE division (== torchvision ToTensor, datasets.py:41-45)
+template <bool U8>
+__device__ __forceinline__ float load_pixel(const void* base, size_t idx) {
+  if (U8) return __fdiv_rn((float)__ldg(reinterpret_cast<const unsigned char*>(base) + idx), 255.f);
+  return __ldg(reinterpret_cast<const float*>(base) + idx);
+}
+
 // split-bf16: hi = bf16(x) (RNE), lo = bf16(x - hi)
 __device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
   hi = __float2bfloat16_rn(x);

@@ -26,9 +26,9 @@ struct StemSmem {
   float scale[ST_CO], shift[ST_CO];
 };
 
-template <int OUT_DTYPE>
+template <int OUT_DTYPE, bool U8>
 __global__ void __launch_bounds__(ST_THREADS, 1)
-stem_simt_kernel(const float* __restrict__ img, int B, int H, int W, const float* __restrict__ wgt,
+stem_simt_kernel(const void* __restrict__ img, int B, int H, int W, const float* __restrict__ wgt,
                  const float* __restrict__ bn_scale, const float* __restrict__ bn_shift, void* __restrict__ out0,
                  void* __restrict__ out1, int Hc, int Wc, int Hp, int Wp) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -49,13 +49,13 @@ stem_simt_kernel(const float* __restrict__ img, int B, int H, int W, const float
     sm.shift[tid] = bn_shift[tid];
   }
   // input patch, zero outside the image (conv zero padding)
-  const float* imb = img + (size_t)b * 3 * H * W;
+  const size_t imb = (size_t)b * 3 * H * W;
   for (int i = tid; i < 3 * ST_TI * ST_TI; i += ST_THREADS) {
     int c = i / (ST_TI * ST_TI), rem = i % (ST_TI * ST_TI);
     int r = rem / ST_TI, q = rem % ST_TI;
     int gr = ir0 + r, gc = ic0 + q;
     float v = 0.f;
-    if (gr >= 0 && gr < H && gc >= 0 && gc < W) v = __ldg(imb + ((size_t)c * H + gr) * W + gc);
+    if (gr >= 0 && gr < H && gc >= 0 && gc < W) v = load_pixel<U8>(img, imb + ((size_t)c * H + gr) * W + gc);
     sm.in[c][r][q] = v;
   }
   __syncthreads();
@@ -130,22 +130,24 @@ stem_simt_kernel(const float* __restrict__ img, int B, int H, int W, const float
   }
 }
 
-int stem_simt(const float* images, int B, int H, int W, const float* w, const float* bn_scale, const float* bn_shift,
-              int out_dtype, void* out0, void* out1, cudaStream_t st) {
+int stem_simt(const void* images, int img_u8, int B, int H, int W, const float* w, const float* bn_scale,
+              const float* bn_shift, int out_dtype, void* out0, void* out1, cudaStream_t st) {
   const int Hc = (H + 6 - 7) / 2 + 1, Wc = (W + 6 - 7) / 2 + 1;
   const int Hp = (Hc + 2 - 3) / 2 + 1, Wp = (Wc + 2 - 3) / 2 + 1;
   dim3 grid(ceil_div(Wp, ST_TP), ceil_div(Hp, ST_TP), B);
   const int smem = (int)sizeof(StemSmem);
-#define LAUNCH(DT)                                                                                       \
-  do {                                                                                                   \
-    COVA_CUDA_OK(cudaFuncSetAttribute(stem_simt_kernel<DT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
-    stem_simt_kernel<DT><<<grid, ST_THREADS, smem, st>>>(images, B, H, W, w, bn_scale, bn_shift, out0, out1, Hc, \
-                                                         Wc, Hp, Wp);                                    \
+#define LAUNCH2(DT, U)                                                                                        \
+  do {                                                                                                      \
+    COVA_CUDA_OK(cudaFuncSetAttribute(stem_simt_kernel<DT, U>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
+    stem_simt_kernel<DT, U><<<grid, ST_THREADS, smem, st>>>(images, B, H, W, w, bn_scale, bn_shift, out0, out1, Hc, \
+                                                            Wc, Hp, Wp);                                    \
   } while (0)
+#define LAUNCH(DT) do { if (img_u8) LAUNCH2(DT, true); else LAUNCH2(DT, false); } while (0)
   if (out_dtype == COVA_F32) LAUNCH(COVA_F32);
   else if (out_dtype == COVA_BF16) LAUNCH(COVA_BF16);
   else LAUNCH(COVA_BF16X2);
 #undef LAUNCH
+#undef LAUNCH2
   COVA_LAUNCH_OK();
   return COVA_OK;
 }

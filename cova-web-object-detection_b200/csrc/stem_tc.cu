@@ -53,7 +53,7 @@ struct StemTcSmem {
 };
 
 struct StemTcParams {
-  const float* img;
+  const void* img;
   int B, H, W, Hc, Wc, Hp, Wp;
   int bands_per_page, nb;                  // pooled rows per band
   const unsigned char* w_packed;           // [28][2][64][8] bf16
@@ -72,7 +72,7 @@ __device__ __forceinline__ uint64_t desc_noswz(uint32_t addr, uint32_t lbo, uint
   return d;
 }
 
-template <bool SPLIT, int OUT_DTYPE>
+template <bool SPLIT, int OUT_DTYPE, bool U8>
 __global__ void __launch_bounds__(SX_THREADS, 1)
 stem_tc_kernel(const StemTcParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -261,8 +261,8 @@ stem_tc_kernel(const StemTcParams p) {
   } else {
     // ======================= converters: NCHW fp32 rows -> ring of 4-channel bf16 pixels =======================
     const int cw = warp - 9;                        // this warp owns input rows g with g % 4 == cw
-    const float* img_b = p.img + (size_t)b * 3 * p.H * p.W;
     const size_t plane = (size_t)p.H * p.W;
+    const size_t img_b = (size_t)b * 3 * plane;
     const uint32_t n_rows_total = (uint32_t)n_strips * NQ;
     for (uint32_t g = cw; g < n_rows_total; g += 4) {
       const int strip = g / NQ, q = g % NQ;
@@ -281,7 +281,7 @@ stem_tc_kernel(const StemTcParams p) {
         const int i = lane + 32 * j, x = x0 + i;
         const bool ok = row_ok && i < SX_NPX && x >= 0 && x < p.W;
 #pragma unroll
-        for (int c = 0; c < 3; ++c) f[j][c] = ok ? __ldg(img_b + c * plane + (size_t)y * p.W + x) : 0.f;
+        for (int c = 0; c < 3; ++c) f[j][c] = ok ? load_pixel<U8>(p.img, img_b + c * plane + (size_t)y * p.W + x) : 0.f;
       }
       unsigned char* dst_hi = sm.ring[0][g % SX_R];
 #pragma unroll
@@ -324,9 +324,9 @@ __global__ void pack_stem_weight_kernel(const float* __restrict__ w, __nv_bfloat
   out[((chunk * 2 + 1) * 64 + co) * 8 + e] = l;
 }
 
-template <bool SPLIT, int OUT_DTYPE>
+template <bool SPLIT, int OUT_DTYPE, bool U8>
 static int launch_stem_tc(const StemTcParams& p, int grid, cudaStream_t st) {
-  auto kern = stem_tc_kernel<SPLIT, OUT_DTYPE>;
+  auto kern = stem_tc_kernel<SPLIT, OUT_DTYPE, U8>;
   const int smem = (int)sizeof(StemTcSmem<SPLIT>) + 128;
   COVA_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   kern<<<grid, SX_THREADS, smem, st>>>(p);
@@ -334,7 +334,7 @@ static int launch_stem_tc(const StemTcParams& p, int grid, cudaStream_t st) {
   return COVA_OK;
 }
 
-int stem_tc(const float* images, int B, int H, int W, const void* w_packed, const float* bn_scale,
+int stem_tc(const void* images, int img_u8, int B, int H, int W, const void* w_packed, const float* bn_scale,
             const float* bn_shift, int out_dtype, void* out0, void* out1, cudaStream_t st) {
   StemTcParams p;
   p.img = images; p.B = B; p.H = H; p.W = W;
@@ -353,11 +353,13 @@ int stem_tc(const float* images, int B, int H, int W, const void* w_packed, cons
   p.out0 = out0; p.out1 = out1;
   const int grid = B * p.bands_per_page;
   const bool split = out_dtype != COVA_BF16;   // bf16 output <=> bf16 mode; fp32 / split outputs use the 3-product mode
+#define GO(SP, DT) (img_u8 ? launch_stem_tc<SP, DT, true>(p, grid, st) : launch_stem_tc<SP, DT, false>(p, grid, st))
   if (split) {
-    if (out_dtype == COVA_F32) return launch_stem_tc<true, COVA_F32>(p, grid, st);
-    return launch_stem_tc<true, COVA_BF16X2>(p, grid, st);
+    if (out_dtype == COVA_F32) return GO(true, COVA_F32);
+    return GO(true, COVA_BF16X2);
   }
-  return launch_stem_tc<false, COVA_BF16>(p, grid, st);
+  return GO(false, COVA_BF16);
+#undef GO
 }
 
 }  // namespace cova

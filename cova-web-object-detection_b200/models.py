@@ -273,8 +273,14 @@ class CoVA(nn.Module):
         """images [B,3,img_H,img_H] f32; bboxes [N,5] = [batch_idx,x1,y1,x2,y2]; additional_feats [N,n_add];
         context_indices int64 [N,n_context] (-1 padded) -> logits [N,n_classes] (`models.py:94-122`)."""
         if self._use_native(images, bboxes):
-            return self._native.forward(images.float(), bboxes.float(), additional_feats, context_indices)
+            return self._native.forward(self._img(images), bboxes.float(), additional_feats, context_indices)
         return self._forward_composite(images, bboxes, additional_feats, context_indices)
+
+    @staticmethod
+    def _img(images):
+        """fp32 in [0,1] (the reference contract) or raw uint8 pixels: the native stem converts v/255 itself
+        (bit-identical to `ToTensor`, a quarter of the host->device bytes - SURVEY.md 8(f) N1)."""
+        return images if images.dtype == torch.uint8 else images.float()
 
     def _forward_composite(self, images, bboxes, additional_feats, context_indices):
         with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):   # fp32 like the reference, not TF32
@@ -294,7 +300,9 @@ class CoVA(nn.Module):
     def _get_visual_features(self, images, bboxes):
         """`models.py:124-127` -> [N, C*P*P]."""
         if self._use_native(images, bboxes):
-            return self._native.visual_features(images.float(), bboxes.float())
+            return self._native.visual_features(self._img(images), bboxes.float())
+        if images.dtype == torch.uint8:
+            images = images.float().div(255)
         fm = self.convnet(images).permute(0, 2, 3, 1)                # NCHW -> NHWC view for the native RoI kernel
         if self.roi_mode == "pool":
             return _RoIPoolFn.apply(fm, bboxes.float(), self.roi_output_size, self.spatial_scale)

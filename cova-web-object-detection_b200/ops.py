@@ -4,7 +4,7 @@ CPU path here (the CPU restatement lives in ``oracle/`` and is test infrastructu
 import torch
 
 from . import _lib
-from ._lib import BF16, BF16X2, ENGINE_SIMT, ENGINE_TCGEN05, F32  # noqa: F401
+from ._lib import BF16, BF16X2, ENGINE_SIMT, ENGINE_TCGEN05, F32, U8  # noqa: F401
 
 ENGINES = {"simt": ENGINE_SIMT, "tcgen05": ENGINE_TCGEN05}
 
@@ -59,8 +59,11 @@ def device_info():
 
 
 def stem_fwd(images, w, bn_scale, bn_shift, out_dtype=F32, engine=ENGINE_SIMT):
-    """conv7x7 s2 p3 + BN + ReLU + maxpool3x3 s2 p1; images [B,3,H,W] fp32 NCHW -> Planes [B,H/4,W/4,64]."""
-    _cuda(images, torch.float32, "images")
+    """conv7x7 s2 p3 + BN + ReLU + maxpool3x3 s2 p1; images [B,3,H,W] NCHW, fp32 in [0,1] or uint8 raw pixels
+    (converted as v/255 in the kernel) -> Planes [B,H/4,W/4,64]."""
+    _cuda(images, None, "images")
+    if images.dtype not in (torch.float32, torch.uint8):
+        raise RuntimeError(f"cova_b200: images must be float32 or uint8, got {images.dtype}")
     images = images.contiguous()
     B, C, H, W = images.shape
     if C != 3:
@@ -68,7 +71,7 @@ def stem_fwd(images, w, bn_scale, bn_shift, out_dtype=F32, engine=ENGINE_SIMT):
     Hc, Wc = (H + 6 - 7) // 2 + 1, (W + 6 - 7) // 2 + 1
     Hp, Wp = (Hc + 2 - 3) // 2 + 1, (Wc + 2 - 3) // 2 + 1
     out = Planes(out_dtype, (B, Hp, Wp, 64), images.device)
-    _call("cova_stem_fwd", images.data_ptr(), B, H, W, w.data_ptr(), bn_scale.data_ptr(), bn_shift.data_ptr(),
+    _call("cova_stem_fwd", images.data_ptr(), U8 if images.dtype == torch.uint8 else F32, B, H, W, w.data_ptr(), bn_scale.data_ptr(), bn_shift.data_ptr(),
           out_dtype, out.p0.data_ptr(), _ptr(out.p1), engine, _stream())
     return out
 

@@ -32,7 +32,7 @@ extern "C" {
 #define COVA_ABI_VERSION 1
 
 enum { COVA_OK = 0, COVA_ERR_ARG = 1, COVA_ERR_CUDA = 2, COVA_ERR_UNSUPPORTED = 3 };
-enum { COVA_F32 = 0, COVA_BF16 = 1, COVA_BF16X2 = 2 };
+enum { COVA_F32 = 0, COVA_BF16 = 1, COVA_BF16X2 = 2, COVA_U8 = 3 /* images only */ };
 enum { COVA_ENGINE_SIMT = 0, COVA_ENGINE_TCGEN05 = 1 };
 
 int cova_abi_version(void);
@@ -43,13 +43,16 @@ int cova_device_info(int* sm_count, int* max_smem_optin);
 /* ---- A2: backbone stem.  Replaces `convnet[0:4]` = conv1 7x7 s2 p3 (no bias) -> bn1 -> relu ->
  * maxpool 3x3 s2 p1 (`models.py:49-51`, applied `models.py:125`).  ONE fused kernel: the
  * [B,64,H/2,W/2] conv output never reaches HBM.
- *   images  [B,3,H,W] fp32 NCHW (the reference's input contract, `models.py:96`)
+ *   images  [B,3,H,W] NCHW; img_dtype COVA_F32 = fp32 in [0,1] (the reference's input contract, `models.py:96`)
+ *           or COVA_U8 = raw 8-bit pixels, converted as v/255 (IEEE division) on the way into shared memory -
+ *           bit-identical to `torchvision.transforms.ToTensor` (`datasets.py:41-45`) at a quarter of the
+ *           host->device bytes
  *   w       engine SIMT   : [64,3,7,7] fp32 OIHW (`convnet.0.weight`)
  *           engine TCGEN05: the split-bf16 K-chunked filter written by cova_pack_stem_weight
  *   bn_scale/bn_shift [64] folded `convnet.1`
  *   out     NHWC [B,H/4,W/4,64] in `out_dtype` (planes out0/out1).  TCGEN05: COVA_BF16 output selects the
  *           single-product bf16 mode, COVA_BF16X2 / COVA_F32 the 3-product fp32-parity mode.            */
-int cova_stem_fwd(const float* images, int B, int H, int W, const void* w, const float* bn_scale,
+int cova_stem_fwd(const void* images, int img_dtype, int B, int H, int W, const void* w, const float* bn_scale,
                   const float* bn_shift, int out_dtype, void* out0, void* out1, int engine, void* stream);
 
 /* OIHW fp32 [64,3,7,7] -> tcgen05 stem filter: bf16 [28 K-chunks][2 planes (hi, lo)][64 cout][8],

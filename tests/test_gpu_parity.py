@@ -318,6 +318,21 @@ def test_gat_kernel_shapes_vs_oracle(T, K, Hd):
     assert np.abs(t2n(out) - want).max() < 2e-5 and np.abs(t2n(attn) - want_attn).max() < 5e-6
 
 
+def test_gat_stress_config5_shape():
+    """BASELINE config 5 shape per page group: N=300 boxes/page, K=48, 2 heads of 192 (4 pages here so the
+    as-written oracle stays small): window ids, staged smem path with 56-row windows."""
+    m, sd = make_model("tcgen05", img=128, n_heads=2)
+    own = torch.randn(1200, 608, generator=torch.Generator().manual_seed(3))
+    ci = np.concatenate([synth.context_window(300, 24) + np.where(synth.context_window(300, 24) >= 0, p * 300, 0)
+                         for p in range(4)], 0)
+    heads = [(sd[f"gat.heads.{i}.W_i.weight"], sd[f"gat.heads.{i}.W_j.weight"],
+              sd[f"gat.heads.{i}.attention_layer.weight"], sd[f"gat.heads.{i}.attention_layer.bias"]) for i in range(2)]
+    want = O.gat_multihead(own.numpy(), ci, heads)
+    with torch.no_grad():
+        got = m.gat(own.to(DEV), torch.from_numpy(ci).to(DEV))
+    assert rel_err(t2n(got), want) < 5e-5
+
+
 # ----------------------------------------------------------------------------- whole forward vs the live reference
 ENGINES = [("simt", "fp32", 1e-5, 2e-5), ("tcgen05", "fp32", 1e-4, 1e-4), ("tcgen05", "bf16", 2e-2, 1e-2)]
 
@@ -364,6 +379,21 @@ def test_forward_ragged_pages_golden(engine, precision, tol_fm, tol_logits):
     assert rel_err(t2n(ctx), g["ctx"]) < max(tol_fm, 2e-5) and np.abs(t2n(attn) - g["attn"]).max() < max(tol_fm, 1e-5)
 
 
+def test_uint8_images_equal_totensor_path():
+    """raw uint8 pixels in, v/255 inside the stem == the fp32 `ToTensor` contract, bit for bit,
+    on both engines; logits identical to feeding the converted fp32 images."""
+    g = torch.Generator().manual_seed(21)
+    u8 = torch.randint(0, 256, (2, 3, 256, 256), dtype=torch.uint8, generator=g)
+    f32 = u8.float().div(255)                                  # what ToTensor produces (datasets.py:41-45)
+    _, bboxes, add, ci = synth.gen(2, 12, 8, seed=0, img=256)
+    for engine in ("tcgen05", "simt"):
+        m, _ = make_model(engine, img=256)
+        with torch.no_grad():
+            a = m(u8.to(DEV), bboxes.to(DEV), add.to(DEV), ci.to(DEV))
+            b = m(f32.to(DEV), bboxes.to(DEV), add.to(DEV), ci.to(DEV))
+        assert torch.equal(a, b), engine
+
+
 def test_forward_roi_align_variant_golden():
     g = load_golden("g_align_r18_img256")
     m, _ = make_model("simt", img=256, roi_mode="align")
@@ -408,6 +438,30 @@ def test_forward_constructor_variants_golden():
     with torch.no_grad():
         out = m(images, bboxes, torch.from_numpy(g["additional_feats"]).to(DEV), ci)
     assert rel_err(t2n(out), g["logits"]) < 2e-5
+
+
+@pytest.mark.parametrize("engine,tol", [("tcgen05", 1e-4), ("simt", 2e-5)])
+def test_forward_odd_image_size_and_empty_pages(engine, tol):
+    """img_H = 200 (conv 100, map 50x50: partial stem strips/bands, partial 8x16 conv tiles), a page with ZERO boxes
+    in the middle of the batch, a single-box page, and a batch with no boxes at all."""
+    m, sd = make_model(engine, img=200)
+    inp = synth.gen(4, 0, 8, seed=13, img=200, counts=[7, 0, 1, 5])
+    want = O.cova_forward(sd, *[t.numpy() for t in inp], conv=torch_conv)
+    with torch.no_grad():
+        got = m(*to_dev(inp))
+        none = m(inp[0].to(DEV), torch.empty((0, 5), device=DEV), torch.empty((0, 0), device=DEV),
+                 torch.empty((0, 8), dtype=torch.long, device=DEV))
+    assert got.shape == (13, 4) and rel_err(t2n(got), want) < tol
+    assert none.shape == (0, 4)
+
+
+def test_single_page_single_sm_wave():
+    """B = 1 (fewer tiles than a full persistent wave in the small kernels) at full resolution vs the simt engine."""
+    inp = to_dev(synth.gen(1, 90, 24, seed=4))
+    a, _ = make_model("tcgen05")
+    b, _ = make_model("simt")
+    with torch.no_grad():
+        assert rel_err(t2n(a(*inp)), t2n(b(*inp))) < 1e-4
 
 
 def test_two_head_forward_vs_oracle():
