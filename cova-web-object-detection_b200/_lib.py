@@ -58,6 +58,7 @@ SIGNATURES = {
     "cova_device_info": (_I, [_c.POINTER(_I), _c.POINTER(_I)]),
     "cova_stem_fwd": (_I, [_P, _I, _I, _I, _I, _P, _P, _P, _I, _P, _P, _I, _P]),
     "cova_conv3x3_bn_act_fwd": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _I, _I, _P, _P, _I, _P]),
+    "cova_conv1x1_bn_act_fwd": (_I, [_P, _P, _L, _I, _I, _P, _P, _P, _P, _P, _I, _I, _P, _P, _P]),
     "cova_pack_conv_weight": (_I, [_P, _I, _I, _I, _I, _P, _P, _P, _P]),
     "cova_pack_stem_weight": (_I, [_P, _P, _P]),
     "cova_roi_fwd": (_I, [_P, _I, _I, _I, _I, _P, _I, _I, _I, _F, _I, _I, _P, _L, _P, _P]),

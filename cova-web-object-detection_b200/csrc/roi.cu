@@ -252,12 +252,12 @@ extern "C" int cova_roi_fwd(const float* fm, int B, int Hf, int Wf, int C, const
                             float spatial_scale, int mode, int sampling_ratio, float* out, int64_t ld_out,
                             int32_t* argmax, void* stream) {
   using namespace cova;
-  COVA_REQUIRE(fm && rois && out, "cova_roi_fwd: null pointer");
   COVA_REQUIRE(B > 0 && Hf > 0 && Wf > 0 && PH > 0 && PW > 0 && T >= 0, "cova_roi_fwd: bad dims");
+  if (T == 0) return COVA_OK;   // a batch without boxes: empty (possibly null) rois / out are fine
+  COVA_REQUIRE(fm && rois && out, "cova_roi_fwd: null pointer");
   COVA_REQUIRE(C % ROI_CB == 0, "cova_roi_fwd: C=%d must be a multiple of %d", C, ROI_CB);
   COVA_REQUIRE(ld_out >= (int64_t)C * PH * PW, "cova_roi_fwd: ld_out too small");
   COVA_REQUIRE(mode == 0 || mode == 1, "cova_roi_fwd: mode must be 0 (pool) or 1 (align)");
-  if (T == 0) return COVA_OK;
   cudaStream_t st = (cudaStream_t)stream;
   if (mode == 1) {
     COVA_REQUIRE(argmax == nullptr, "cova_roi_fwd: RoIAlign has no argmax");
@@ -281,9 +281,10 @@ extern "C" int cova_roi_fwd(const float* fm, int B, int Hf, int Wf, int C, const
 
 extern "C" int cova_bbox_enc_fwd(const float* rois, int T, const float* w, const float* b, const float* bn_scale,
                                  const float* bn_shift, int D, float* out, int64_t ld_out, void* stream) {
-  COVA_REQUIRE(rois && w && b && out && D > 0 && T >= 0 && ld_out >= D, "cova_bbox_enc_fwd: bad arguments");
-  COVA_REQUIRE((bn_scale == nullptr) == (bn_shift == nullptr), "cova_bbox_enc_fwd: scale/shift must come together");
+  COVA_REQUIRE(D > 0 && T >= 0, "cova_bbox_enc_fwd: bad dims");
   if (T == 0) return COVA_OK;
+  COVA_REQUIRE(rois && w && b && out && ld_out >= D, "cova_bbox_enc_fwd: bad arguments");
+  COVA_REQUIRE((bn_scale == nullptr) == (bn_shift == nullptr), "cova_bbox_enc_fwd: scale/shift must come together");
   cova::bbox_enc_kernel<<<cova::ceil_div(T * D, 256), 256, 0, (cudaStream_t)stream>>>(rois, T, w, b, bn_scale, bn_shift,
                                                                                    D, out, ld_out);
   COVA_LAUNCH_OK();

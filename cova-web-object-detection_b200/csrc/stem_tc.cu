@@ -48,6 +48,7 @@ struct StemTcSmem {
   float edge[2][SX_MAXROWS][64];           // right-most conv column of the previous / current strip
   float xch[2][4][64];                     // lane-31 rows exchanged between the 4 epilogue warps
   float scale[64], shift[64];
+  uint32_t lut[256];                       // uint8 images: bf16 hi (low half) | bf16 lo (high half) of v/255
   uint64_t in_full[SX_R], mma_done[SX_ND], tmem_full[2], tmem_empty[2], wbar;
   uint32_t tmem_base;
 };
@@ -94,6 +95,11 @@ stem_tc_kernel(const StemTcParams p) {
   if (threadIdx.x < 64) {
     sm.scale[threadIdx.x] = p.bn_scale[threadIdx.x];
     sm.shift[threadIdx.x] = p.bn_shift[threadIdx.x];
+  }
+  if (U8 && threadIdx.x < 256) {   // v/255 with IEEE division == torchvision ToTensor; split once per pixel value
+    __nv_bfloat16 h, l;
+    split_bf16(__fdiv_rn((float)threadIdx.x, 255.f), h, l);
+    sm.lut[threadIdx.x] = pack_bf16x2(h, l);
   }
   if (threadIdx.x == 0) {
     for (int i = 0; i < SX_R; ++i) ptx::mbar_init(&sm.in_full[i], 1);
@@ -275,24 +281,57 @@ stem_tc_kernel(const StemTcParams p) {
         ptx::mbar_wait(&sm.mma_done[t_last % SX_ND], (t_last / SX_ND) & 1);
       }
       const bool row_ok = y >= 0 && y < p.H;
-      float f[9][3];
-#pragma unroll
-      for (int j = 0; j < 9; ++j) {
-        const int i = lane + 32 * j, x = x0 + i;
-        const bool ok = row_ok && i < SX_NPX && x >= 0 && x < p.W;
-#pragma unroll
-        for (int c = 0; c < 3; ++c) f[j][c] = ok ? load_pixel<U8>(p.img, img_b + c * plane + (size_t)y * p.W + x) : 0.f;
-      }
       unsigned char* dst_hi = sm.ring[0][g % SX_R];
+      if (U8 && (p.W & 3) == 0) {
+        // uint8 fast path: x0 - 1 is a multiple of 4, so the row segment is 67 aligned 4-pixel words per channel
+        // (9 word loads per lane instead of 27 byte loads); the value -> (hi, lo) bf16 split comes from the LUT.
+        const unsigned char* img8 = reinterpret_cast<const unsigned char*>(p.img) + img_b;
+        uint32_t wv[3][3];
 #pragma unroll
-      for (int j = 0; j < 9; ++j) {
-        const int i = lane + 32 * j;
-        if (i < SX_NPX) {
-          uint32_t h01, l01, h2, l2;
-          split_bf16x2(f[j][0], f[j][1], h01, l01);
-          split_bf16x2(f[j][2], 0.f, h2, l2);
-          *reinterpret_cast<uint2*>(dst_hi + i * 8) = make_uint2(h01, h2);
-          if (SPLIT) *reinterpret_cast<uint2*>(dst_hi + SX_R * SX_ROW_BYTES + i * 8) = make_uint2(l01, l2);
+        for (int j = 0; j < 3; ++j) {
+          const int wi = lane + 32 * j, xw = x0 - 1 + 4 * wi;
+          const bool ok = row_ok && wi < 67 && xw >= 0 && xw < p.W;
+#pragma unroll
+          for (int c = 0; c < 3; ++c)
+            wv[j][c] = ok ? __ldg(reinterpret_cast<const uint32_t*>(img8 + c * plane + (size_t)y * p.W + xw)) : 0u;
+        }
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          const int wi = lane + 32 * j;
+          if (wi < 67) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const int i = 4 * wi + k - 1;                 // pixel index in the ring row
+              if (i >= 0 && i < SX_NPX) {
+                const uint32_t l0 = sm.lut[(wv[j][0] >> (8 * k)) & 255u], l1 = sm.lut[(wv[j][1] >> (8 * k)) & 255u],
+                               l2 = sm.lut[(wv[j][2] >> (8 * k)) & 255u];
+                *reinterpret_cast<uint2*>(dst_hi + i * 8) = make_uint2(__byte_perm(l0, l1, 0x5410), l2 & 0xffffu);
+                if (SPLIT)
+                  *reinterpret_cast<uint2*>(dst_hi + SX_R * SX_ROW_BYTES + i * 8) =
+                      make_uint2(__byte_perm(l0, l1, 0x7632), l2 >> 16);
+              }
+            }
+          }
+        }
+      } else {
+        float f[9][3];
+#pragma unroll
+        for (int j = 0; j < 9; ++j) {
+          const int i = lane + 32 * j, x = x0 + i;
+          const bool ok = row_ok && i < SX_NPX && x >= 0 && x < p.W;
+#pragma unroll
+          for (int c = 0; c < 3; ++c) f[j][c] = ok ? load_pixel<U8>(p.img, img_b + c * plane + (size_t)y * p.W + x) : 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < 9; ++j) {
+          const int i = lane + 32 * j;
+          if (i < SX_NPX) {
+            uint32_t h01, l01, h2, l2;
+            split_bf16x2(f[j][0], f[j][1], h01, l01);
+            split_bf16x2(f[j][2], 0.f, h2, l2);
+            *reinterpret_cast<uint2*>(dst_hi + i * 8) = make_uint2(h01, h2);
+            if (SPLIT) *reinterpret_cast<uint2*>(dst_hi + SX_R * SX_ROW_BYTES + i * 8) = make_uint2(l01, l2);
+          }
         }
       }
       ptx::fence_proxy_async();      // generic-proxy writes -> visible to tcgen05 (async proxy) reads

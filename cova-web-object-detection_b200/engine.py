@@ -44,7 +44,7 @@ class NativeForward:
         tc = m.engine == "tcgen05"
         split = m.precision == "fp32" or r50          # the ResNet-50 tensor-core path is fp32-parity only
         c["tc"] = tc
-        c["act_dtype"] = F32 if (r50 or not tc) else (BF16X2 if split else BF16)
+        c["act_dtype"] = (BF16X2 if split else BF16) if tc else F32
         cn = m.convnet
         c["stem_w"] = cn[0].weight.detach().float().contiguous()
         if tc:
@@ -131,24 +131,26 @@ class NativeForward:
                 x = ops.conv3x3_bn_act_fwd(y, d["w2"][0], d["w2"][1], *d["bn2"], res=x, relu=True,
                                            out_dtype=F32 if last else None, engine=eng)
             return x.p0
-        # resnet50 Bottlenecks: 1x1 conv = GEMM over the [B*H*W, C] pixel rows, 3x3 = the BasicBlock kernel
+        # resnet50 Bottlenecks
+        nb = len(c["blocks"])
+        if c["tc"]:   # split-bf16 planes end to end: 1x1 convs = persistent tcgen05 GEMMs over the pixel rows
+            for bi, d in enumerate(c["blocks"]):
+                o = ops.conv1x1_bn_act_fwd(x, d["w1_p"], *d["bn1"], relu=True)
+                o = ops.conv3x3_bn_act_fwd(o, d["w2"][0], d["w2"][1], *d["bn2"], relu=True, engine=ENGINE_TCGEN05)
+                idt = ops.conv1x1_bn_act_fwd(x, d["wd_p"], *d["bnd"], relu=False) if "wd_p" in d else x
+                x = ops.conv1x1_bn_act_fwd(o, d["w3_p"], *d["bn3"], res=idt, relu=True,
+                                           out_dtype=F32 if bi == nb - 1 else BF16X2)
+            return x.p0
+        # CUDA-core fp32 engine: 1x1 conv = GEMM over the [B*H*W, C] pixel rows
         B, H, W, _ = x.shape
         cur = x.p0.view(B * H * W, 64)
         for d in c["blocks"]:
-            if c["tc"]:   # conv1 writes split-bf16 planes straight into the 3x3 tensor-core conv, which returns fp32
-                p = ops.linear_fwd(cur, d["w1_p"], None, *d["bn1"], relu=True, engine=ENGINE_TCGEN05, out_planes=True)
-                p.shape = (B, H, W, 64)
-                o = ops.conv3x3_bn_act_fwd(p, d["w2"][0], d["w2"][1], *d["bn2"], relu=True, out_dtype=F32,
-                                           engine=ENGINE_TCGEN05).p0.view(B * H * W, 64)
-                idt = (ops.linear_fwd(cur, d["wd_p"], None, *d["bnd"], engine=ENGINE_TCGEN05) if "wd" in d else cur)
-                cur = ops.linear_fwd(o, d["w3_p"], None, *d["bn3"], res=idt, relu=True, engine=ENGINE_TCGEN05)
-            else:
-                o = ops.linear_fwd(cur, d["w1"], None, *d["bn1"], relu=True)
-                p = ops.Planes.__new__(ops.Planes)
-                p.dtype, p.shape, p.p0, p.p1 = F32, (B, H, W, 64), o.view(B, H, W, 64), None
-                o = ops.conv3x3_bn_act_fwd(p, d["w2"][0], None, *d["bn2"], relu=True, engine=ENGINE_SIMT).p0.view(B * H * W, 64)
-                idt = ops.linear_fwd(cur, d["wd"], None, *d["bnd"]) if "wd" in d else cur
-                cur = ops.linear_fwd(o, d["w3"], None, *d["bn3"], res=idt, relu=True)
+            o = ops.linear_fwd(cur, d["w1"], None, *d["bn1"], relu=True)
+            p = ops.Planes.__new__(ops.Planes)
+            p.dtype, p.shape, p.p0, p.p1 = F32, (B, H, W, 64), o.view(B, H, W, 64), None
+            o = ops.conv3x3_bn_act_fwd(p, d["w2"][0], None, *d["bn2"], relu=True, engine=ENGINE_SIMT).p0.view(B * H * W, 64)
+            idt = ops.linear_fwd(cur, d["wd"], None, *d["bnd"]) if "wd" in d else cur
+            cur = ops.linear_fwd(o, d["w3"], None, *d["bn3"], res=idt, relu=True)
         return cur.view(B, H, W, 256)
 
     def own_into(self, fm, bboxes, additional_feats, comb):

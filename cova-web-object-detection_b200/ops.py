@@ -109,6 +109,17 @@ def conv3x3_bn_act_fwd(x, w_a, w_b, bn_scale, bn_shift, res=None, relu=True, out
     return y
 
 
+def conv1x1_bn_act_fwd(x, w_packed, bn_scale, bn_shift, res=None, relu=True, out_dtype=BF16X2):
+    """ResNet-50 Bottleneck 1x1 conv + folded BN (+ residual) (+ ReLU) on split-bf16 NHWC Planes (tcgen05)."""
+    B, H, W, Cin = x.shape
+    Cout = w_packed.shape[1]
+    y = Planes(out_dtype, (B, H, W, Cout), x.p0.device)
+    _call("cova_conv1x1_bn_act_fwd", x.p0.data_ptr(), x.p1.data_ptr(), B * H * W, Cin, Cout, w_packed.data_ptr(),
+          bn_scale.data_ptr(), bn_shift.data_ptr(), _ptr(res.p0) if res is not None else 0,
+          _ptr(res.p1) if res is not None else 0, int(relu), out_dtype, y.p0.data_ptr(), _ptr(y.p1), _stream())
+    return y
+
+
 def roi_fwd(fm, rois, P, spatial_scale, out, mode="pool", sampling_ratio=2, want_argmax=False):
     """fm NHWC fp32 [B,Hf,Wf,C]; rois [T,5]; writes out[:, :C*PH*PW] (out may be a wider row-major buffer)."""
     _cuda(fm, torch.float32, "fm")

@@ -16,16 +16,17 @@ class _Slot:
 
 
 def _stage(slot, batch, device, stream):
-    if slot.pinned is None or any(p.shape != t.shape or p.dtype != t.dtype for p, t in zip(slot.pinned, batch)):
-        slot.pinned = [torch.empty(t.shape, dtype=t.dtype).pin_memory() for t in batch]
-        slot.dev = [torch.empty(t.shape, dtype=t.dtype, device=device) for t in batch]
-    for p, t in zip(slot.pinned, batch):
-        if t.is_pinned():
-            continue
-        p.copy_(t)
     with torch.cuda.stream(stream):
+        # The device buffers are first written on the COPY stream, so they must come from that stream's pool:
+        # a block the caching allocator hands out for the compute stream may still be in use by kernels that are
+        # queued there (stream-ordered reuse is only safe on the stream that freed it).
+        if slot.dev is None or any(d.shape != t.shape or d.dtype != t.dtype for d, t in zip(slot.dev, batch)):
+            slot.dev = [torch.empty(t.shape, dtype=t.dtype, device=device) for t in batch]
+            slot.pinned = [None if t.is_pinned() else torch.empty(t.shape, dtype=t.dtype).pin_memory() for t in batch]
         for d, p, t in zip(slot.dev, slot.pinned, batch):
-            d.copy_(t if t.is_pinned() else p, non_blocking=True)
+            if p is not None:
+                p.copy_(t)
+            d.copy_(t if p is None else p, non_blocking=True)
         slot.event = torch.cuda.Event()
         slot.event.record(stream)
 
@@ -61,7 +62,10 @@ def prefetch(batches, device, depth=2):
             break
     while pending:
         s, batch = pending.pop(0)
-        torch.cuda.current_stream(device).wait_event(slots[s].event)
+        compute = torch.cuda.current_stream(device)
+        compute.wait_event(slots[s].event)
+        for t in slots[s].dev:
+            t.record_stream(compute)     # freed blocks must also wait for the consumer's kernels
         dev_iter = iter(slots[s].dev)
         yield tuple(next(dev_iter) if isinstance(t, torch.Tensor) else t for t in batch)
         ev = torch.cuda.Event()

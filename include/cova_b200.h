@@ -69,6 +69,14 @@ int cova_conv3x3_bn_act_fwd(const void* x0, const void* x1, int dtype, int B, in
                             const void* res0, const void* res1, int relu, int out_dtype, void* y0, void* y1,
                             int engine, void* stream);
 
+/* ---- A2 (ResNet-50): 1x1 convolution + folded BN (+ residual) (+ ReLU) over NHWC split-bf16 planes =
+ * torchvision Bottleneck.forward conv1 / conv3 / downsample.  x planes [M, Cin], M = B*H*W pixel rows;
+ * w = cova_pack_linear_weight of the [Cout, Cin] filter; residual planes [M, Cout]; output split planes
+ * (COVA_BF16X2: y0 = hi, y1 = lo) or fp32 (COVA_F32: y0).  Built for 64->64, 64->256, 256->64.          */
+int cova_conv1x1_bn_act_fwd(const void* x_hi, const void* x_lo, int64_t M, int Cin, int Cout, const void* w_packed,
+                            const float* bn_scale, const float* bn_shift, const void* res_hi, const void* res_lo,
+                            int relu, int out_dtype, void* y0, void* y1, void* stream);
+
 /* Repack an OIHW fp32 conv weight [Cout,Cin,kh,kw] for the engines above.
  *   simt_out  : fp32 [kh][kw][Cin][Cout]                       (may be NULL)
  *   tc_hi/lo  : bf16 [kh*kw][Cout][Cin] hi/lo split            (may be NULL)                         */

@@ -96,6 +96,22 @@ def test_stem_tcgen05_kernel(out_dtype, B, H):
     assert rel_err(t2n(out.float()), ref) < {"f32": 3e-5, "bf16x2": 5e-5, "bf16": 6e-3}[out_dtype]
 
 
+@pytest.mark.parametrize("W", [104, 102])
+def test_stem_tcgen05_uint8_images(W):
+    """uint8 pixels: the aligned 4-pixel-word + LUT converter (W % 4 == 0) and the byte fallback (W % 4 != 0)."""
+    o = ops()
+    g = torch.Generator().manual_seed(3)
+    u8 = torch.randint(0, 256, (2, 3, W, W), dtype=torch.uint8, generator=g)
+    w = torch.randn(64, 3, 7, 7, generator=g) * 0.1
+    scale, shift = 0.5 + torch.rand(64, generator=g), 0.1 * torch.randn(64, generator=g)
+    ref = O.conv2d_nchw(u8.float().div(255).numpy(), w.numpy(), 2, 3)
+    ref = ref * scale.numpy().reshape(1, -1, 1, 1) + shift.numpy().reshape(1, -1, 1, 1)
+    ref = O.maxpool3x3s2p1(np.maximum(ref, 0)).transpose(0, 2, 3, 1)
+    out = o.stem_fwd(u8.to(DEV), o.pack_stem_weight(w.to(DEV)), scale.to(DEV), shift.to(DEV), out_dtype=o.F32,
+                     engine=o.ENGINE_TCGEN05)
+    assert rel_err(t2n(out.p0), ref) < 3e-5
+
+
 def test_stem_tcgen05_full_size_vs_simt():
     """1280x1280 (5 strips x 9 bands per page): the tensor-core stem against the exact-fp32 CUDA-core stem."""
     o = ops()
@@ -411,6 +427,31 @@ def test_forward_resnet50_golden(engine, tol):
         r = m._native.forward(*to_dev(synth.gen(1, 16, 8, seed=5, img=128)), return_intermediates=True)
     assert rel_err(t2n(r["fm"]).transpose(0, 3, 1, 2), g["fm"]) < tol
     assert rel_err(t2n(r["logits"]), g["logits"]) < 2.5 * tol
+
+
+@pytest.mark.parametrize("cin,cout,with_res,out", [(64, 64, False, "planes"), (64, 256, True, "planes"),
+                                                  (256, 64, False, "planes"), (64, 256, True, "f32")])
+def test_conv1x1_tcgen05_kernel(cin, cout, with_res, out):
+    """ResNet-50 Bottleneck 1x1 convs on split planes vs the oracle conv (ragged M: 2 x 37 x 45 pixel rows)."""
+    o = ops()
+    g = torch.Generator().manual_seed(9)
+    B, H, W = 2, 37, 45
+    x = torch.randn(B, H, W, cin, generator=g)
+    w = torch.randn(cout, cin, 1, 1, generator=g) / cin ** 0.5
+    sc, sh = 0.5 + torch.rand(cout, generator=g), 0.1 * torch.randn(cout, generator=g)
+    res = torch.randn(B, H, W, cout, generator=g)
+    ref = torch_conv(x.permute(0, 3, 1, 2).numpy(), w.numpy(), 1, 0).transpose(0, 2, 3, 1) * sc.numpy() + sh.numpy()
+    if with_res:
+        ref = ref + res.numpy()
+    ref = np.maximum(ref, 0)
+    xp, rp = o.Planes(o.BF16X2, x.shape, DEV), o.Planes(o.BF16X2, res.shape, DEV)
+    for pl, t in ((xp, x), (rp, res)):
+        hi, lo = _split(t)
+        pl.p0.copy_(hi); pl.p1.copy_(lo)
+    y = o.conv1x1_bn_act_fwd(xp, o.pack_linear_weight(w.flatten(1).to(DEV)), sc.to(DEV), sh.to(DEV),
+                             res=rp if with_res else None, relu=True, out_dtype=o.F32 if out == "f32" else o.BF16X2)
+    torch.cuda.synchronize()
+    assert rel_err(t2n(y.float()), ref) < 5e-5
 
 
 def test_linear_tcgen05_split_plane_output():

@@ -46,6 +46,7 @@ def test_argument_validation_returns_error_not_crash(built_lib):
     L = built_lib.lib()
     rc = L.cova_roi_fwd(None, 1, 8, 8, 64, None, 1, 3, 3, 0.25, 0, 2, None, 576, None, None)
     assert rc == 1 and b"null" in L.cova_last_error()
+    assert L.cova_roi_fwd(None, 1, 8, 8, 64, None, 0, 3, 3, 0.25, 0, 2, None, 576, None, None) == 0   # no boxes: no-op
     rc = L.cova_gat_fwd(1, 384, 1, 1, 1, 0.0, 0.2, 1, 4, 500, 384, 1, 384, None, None)
     assert rc == 1 and b"K=500" in L.cova_last_error()
 
