@@ -62,11 +62,13 @@ SIGNATURES = {
     "cova_pack_conv_weight": (_I, [_P, _I, _I, _I, _I, _P, _P, _P, _P]),
     "cova_pack_stem_weight": (_I, [_P, _P, _P]),
     "cova_roi_fwd": (_I, [_P, _I, _I, _I, _I, _P, _I, _I, _I, _F, _I, _I, _P, _L, _P, _P]),
+    "cova_roi_pool_bwd": (_I, [_P, _L, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P]),
     "cova_bbox_enc_fwd": (_I, [_P, _I, _P, _P, _P, _P, _I, _P, _L, _P]),
     "cova_affine_cols_fwd": (_I, [_P, _I, _I, _L, _P, _P, _P, _L, _P]),
     "cova_linear_fwd": (_I, [_P, _L, _I, _I, _P, _I, _P, _P, _P, _P, _L, _I, _I, _P, _P, _L, _I, _P]),
     "cova_pack_linear_weight": (_I, [_P, _I, _I, _P, _P]),
     "cova_gat_fwd": (_I, [_P, _L, _P, _P, _L, _F, _F, _P, _I, _I, _I, _P, _L, _P, _P]),
+    "cova_gat_bwd": (_I, [_P, _L, _P, _L, _P, _P, _L, _F, _F, _P, _P, _I, _I, _I, _P, _L, _P, _P, _L, _P, _P]),
 }
 
 _lib = None

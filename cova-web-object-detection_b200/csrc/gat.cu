@@ -155,7 +155,103 @@ gat_fwd_kernel(const float* __restrict__ whj, int64_t ld_whj, const float* __res
   }
 }
 
+// Backward of the gather (A9, `train.py:59`).  One warp per element i, same lane <-> neighbour mapping as the forward.
+// With G = dL/dout_i:  dalpha_k = G . whj[c_k];  d whj[c_k] += alpha_k G (atomics: a node is the neighbour of ~K
+// elements);  de_k = alpha_k (dalpha_k - sum_k' alpha_k' dalpha_k');  dz_k = de_k * LeakyReLU'(s_i + t_c + b)
+// (0 for padded neighbours);  ds_i = sum_k dz_k;  dt[c_k] += dz_k;  db += sum_k dz_k.
+// The projections' own backward (GEMMs against W_i / W_j / a) stays with autograd.
+__global__ void __launch_bounds__(GAT_THREADS)
+gat_bwd_kernel(const float* __restrict__ gout, int64_t ld_go, const float* __restrict__ whj, int64_t ld_whj,
+               const float* __restrict__ s_vec, const float* __restrict__ t_vec, int64_t ld_st, float att_b, float alpha,
+               const int64_t* __restrict__ ctx, const float* __restrict__ attn, int T, int K, int Hd,
+               float* __restrict__ d_whj, int64_t ld_dw, float* __restrict__ d_s, float* __restrict__ d_t, int64_t ld_dst,
+               float* __restrict__ d_b) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int i = blockIdx.x * GAT_E + warp;
+  if (i >= T) return;
+  const int nvec = Hd >> 2;
+  float4 g[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int v = lane + 32 * q;
+    g[q] = v < nvec ? __ldg(reinterpret_cast<const float4*>(gout + (size_t)i * ld_go) + v) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  int cid[GAT_KMAX / 32];
+  float a[GAT_KMAX / 32], da[GAT_KMAX / 32];
+#pragma unroll
+  for (int j = 0; j < GAT_KMAX / 32; ++j) {
+    const int k = lane + 32 * j;
+    cid[j] = k < K ? (int)ctx[(size_t)i * K + k] : -1;
+    a[j] = k < K ? attn[(size_t)i * K + k] : 0.f;
+    da[j] = 0.f;
+  }
+#pragma unroll
+  for (int j = 0; j < GAT_KMAX / 32; ++j) {
+    if (32 * j >= K) break;
+    const int kend = min(32, K - 32 * j);
+    for (int kk = 0; kk < kend; ++kk) {
+      const int c = __shfl_sync(0xffffffffu, cid[j], kk);
+      const float ak = __shfl_sync(0xffffffffu, a[j], kk);
+      if (c < 0) continue;                                  // zero row: no gradient anywhere
+      const float4* row = reinterpret_cast<const float4*>(whj + (size_t)c * ld_whj);
+      float* drow = d_whj + (size_t)c * ld_dw;
+      float dot = 0.f;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int v = lane + 32 * q;
+        if (v < nvec) {
+          const float4 x = __ldg(row + v);
+          dot += g[q].x * x.x + g[q].y * x.y + g[q].z * x.z + g[q].w * x.w;
+          atomicAdd(drow + 4 * v + 0, ak * g[q].x);
+          atomicAdd(drow + 4 * v + 1, ak * g[q].y);
+          atomicAdd(drow + 4 * v + 2, ak * g[q].z);
+          atomicAdd(drow + 4 * v + 3, ak * g[q].w);
+        }
+      }
+      dot = warp_sum(dot);
+      if (lane == kk) da[j] = dot;
+    }
+  }
+  float sdot = 0.f;
+#pragma unroll
+  for (int j = 0; j < GAT_KMAX / 32; ++j) sdot += a[j] * da[j];
+  sdot = warp_sum(sdot);
+  const float si = s_vec[(size_t)i * ld_st];
+  float dsum = 0.f;
+#pragma unroll
+  for (int j = 0; j < GAT_KMAX / 32; ++j) {
+    const int k = lane + 32 * j;
+    if (k < K && cid[j] >= 0) {
+      const float z = si + __ldg(t_vec + (size_t)cid[j] * ld_st) + att_b;
+      const float dz = a[j] * (da[j] - sdot) * (z > 0.f ? 1.f : alpha);
+      dsum += dz;
+      atomicAdd(d_t + (size_t)cid[j] * ld_dst, dz);
+    }
+  }
+  dsum = warp_sum(dsum);
+  if (lane == 0) {
+    d_s[(size_t)i * ld_dst] = dsum;     // s_i only feeds element i: plain store
+    atomicAdd(d_b, dsum);
+  }
+}
+
 }  // namespace cova
+
+extern "C" int cova_gat_bwd(const float* grad_out, int64_t ld_go, const float* whj, int64_t ld_whj, const float* s,
+                            const float* t, int64_t ld_st, float att_b, float alpha, const int64_t* ctx_idx,
+                            const float* attn, int T, int K, int Hd, float* d_whj, int64_t ld_dw, float* d_s, float* d_t,
+                            int64_t ld_dst, float* d_b, void* stream) {
+  using namespace cova;
+  COVA_REQUIRE(T >= 0 && K >= 1 && K <= GAT_KMAX && Hd > 0 && Hd % 4 == 0 && Hd <= 512, "cova_gat_bwd: bad dims");
+  if (T == 0) return COVA_OK;
+  COVA_REQUIRE(grad_out && whj && s && t && ctx_idx && attn && d_whj && d_s && d_t && d_b, "cova_gat_bwd: null pointer");
+  COVA_REQUIRE(ld_go % 4 == 0 && ld_whj % 4 == 0 && ((uintptr_t)grad_out & 15) == 0 && ((uintptr_t)whj & 15) == 0,
+               "cova_gat_bwd: grad_out / whj rows must be 16-byte aligned");
+  gat_bwd_kernel<<<ceil_div(T, GAT_E), GAT_THREADS, 0, (cudaStream_t)stream>>>(
+      grad_out, ld_go, whj, ld_whj, s, t, ld_st, att_b, alpha, ctx_idx, attn, T, K, Hd, d_whj, ld_dw, d_s, d_t, ld_dst, d_b);
+  COVA_LAUNCH_OK();
+  return COVA_OK;
+}
 
 extern "C" int cova_gat_fwd(const float* whj, int64_t ld_whj, const float* s, const float* t, int64_t ld_st, float att_b,
                             float alpha, const int64_t* ctx_idx, int T, int K, int Hd, float* out, int64_t ld_out,

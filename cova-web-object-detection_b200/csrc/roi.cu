@@ -217,6 +217,24 @@ roi_align_kernel(const float* __restrict__ fm, int Hf, int Wf, int C, const floa
   }
 }
 
+// RoIPool backward (torchvision roi_pool backward): every pooled output sends its gradient to its arg-max pixel.
+// Bins of one box overlap by up to a pixel and boxes overlap freely, so several outputs hit the same pixel:
+// fp32 atomicAdd (RED.ADD.F32) into the zero-initialised NHWC gradient map.
+__global__ void roi_pool_bwd_kernel(const float* __restrict__ grad_out, int64_t ld_go, const int32_t* __restrict__ argmax,
+                                    const float* __restrict__ rois, int T, int C, int nbins, int Hf, int Wf,
+                                    float* __restrict__ grad_fm) {
+  const int64_t n = (int64_t)T * C * nbins;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int idx = argmax[i];
+    if (idx < 0) continue;                         // empty bin: no gradient
+    const int t = (int)(i / ((int64_t)C * nbins));
+    const int r = (int)(i % ((int64_t)C * nbins));
+    const int c = r / nbins;
+    const int b = (int)rois[(size_t)t * 5];
+    atomicAdd(grad_fm + ((size_t)b * Hf * Wf + idx) * C + c, grad_out[(size_t)t * ld_go + r]);
+  }
+}
+
 // [x1,y1,w,h,w/h] -> Linear(5,D) -> folded BN1d -> ReLU; one thread per (box, d)
 __global__ void bbox_enc_kernel(const float* __restrict__ rois, int T, const float* __restrict__ w,
                                 const float* __restrict__ bias, const float* __restrict__ scale,
@@ -275,6 +293,19 @@ extern "C" int cova_roi_fwd(const float* fm, int B, int Hf, int Wf, int C, const
       roi_pool_kernel<false><<<grid, ROI_THREADS, smem, st>>>(fm, Hf, Wf, C, rois, PH, PW, spatial_scale, out, ld_out, argmax);
     }
   }
+  COVA_LAUNCH_OK();
+  return COVA_OK;
+}
+
+extern "C" int cova_roi_pool_bwd(const float* grad_out, int64_t ld_go, const int32_t* argmax, const float* rois, int T,
+                                 int C, int PH, int PW, int B, int Hf, int Wf, float* grad_fm, void* stream) {
+  COVA_REQUIRE(T >= 0 && C > 0 && PH > 0 && PW > 0 && B > 0 && Hf > 0 && Wf > 0, "cova_roi_pool_bwd: bad dims");
+  if (T == 0) return COVA_OK;
+  COVA_REQUIRE(grad_out && argmax && rois && grad_fm && ld_go >= (int64_t)C * PH * PW, "cova_roi_pool_bwd: bad arguments");
+  const int64_t n = (int64_t)T * C * PH * PW;
+  const int blocks = (int)((n + 255) / 256 < 148 * 16 ? (n + 255) / 256 : 148 * 16);
+  cova::roi_pool_bwd_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(grad_out, ld_go, argmax, rois, T, C, PH * PW, Hf, Wf,
+                                                                     grad_fm);
   COVA_LAUNCH_OK();
   return COVA_OK;
 }

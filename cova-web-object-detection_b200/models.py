@@ -110,8 +110,8 @@ def _try_load_pretrained(convnet, backbone):
 
 # ----------------------------------------------------------------------------- RoI autograd (training path)
 class _RoIPoolFn(torch.autograd.Function):
-    """Native RoIPool forward (NHWC fp32 feature map) with the scatter-add backward of torchvision's
-    roi_pool (every output's gradient goes to its arg-max pixel)."""
+    """Native RoIPool forward (NHWC fp32 feature map, arg-max kept) and native backward (atomic scatter-add of
+    every output's gradient to its arg-max pixel, as torchvision's roi_pool backward)."""
 
     @staticmethod
     def forward(ctx, fm_nhwc, rois, P, scale):
@@ -125,17 +125,31 @@ class _RoIPoolFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad_out):
         argmax, rois = ctx.saved_tensors
-        B, Hf, Wf, C = ctx.shape
-        T = rois.shape[0]
-        g = grad_out.reshape(T, C, -1)
-        am = argmax.reshape(T, C, -1).long()
-        valid = am >= 0
-        b = rois[:, 0].long().view(T, 1, 1)
-        c = torch.arange(C, device=g.device).view(1, C, 1)
-        flat = ((b * Hf * Wf + am.clamp_min(0)) * C + c)
-        grad_fm = torch.zeros(B * Hf * Wf * C, dtype=g.dtype, device=g.device)
-        grad_fm.index_add_(0, flat[valid], g[valid])
-        return grad_fm.view(B, Hf, Wf, C), None, None, None
+        return ops.roi_pool_bwd(grad_out.float(), argmax, rois, ctx.shape), None, None, None
+
+
+class _GatGatherFn(torch.autograd.Function):
+    """Native fused neighbour gather / masked softmax / weighted sum (cova_gat_fwd) with its native backward
+    (cova_gat_bwd).  Input `ext` = [W_j h | a_i.W_i h | a_j.W_j h | pad] comes from a differentiable GEMM, so the
+    gradients of W_i, W_j and the attention vector flow through autograd."""
+
+    @staticmethod
+    def forward(ctx, ext, bias, ctx_idx, Hd, alpha):
+        ext = ext.contiguous()
+        out = torch.empty((ext.shape[0], Hd), dtype=torch.float32, device=ext.device)
+        b = float(bias.detach().item())
+        attn = ops.gat_fwd(ext[:, :Hd], ext[:, Hd], ext[:, Hd + 1], b, alpha, ctx_idx, out, want_attn=True)
+        ctx.save_for_backward(ext, ctx_idx, attn)
+        ctx.meta = (Hd, b, alpha)
+        ctx.mark_non_differentiable(attn)
+        return out, attn
+
+    @staticmethod
+    def backward(ctx, grad_out, _grad_attn):
+        ext, ctx_idx, attn = ctx.saved_tensors
+        Hd, b, alpha = ctx.meta
+        d_ext, d_b = ops.gat_bwd(grad_out.float(), ext, Hd, b, alpha, ctx_idx, attn)
+        return d_ext, d_b, None, None, None
 
 
 # ----------------------------------------------------------------------------- GAT
@@ -173,7 +187,17 @@ class GraphAttentionLayer(nn.Module):
         return (out, attn) if return_attn_wts else out
 
     def _forward_composite(self, h_i, context_indices, return_attn_wts=False):
-        """Autograd path: project each node once, gather, masked softmax (same algebra as the native kernel)."""
+        """Autograd path: the projections are one differentiable GEMM against [W_j ; a_i W_i ; a_j W_j] (the same
+        restructuring as the inference path), the gather / softmax / weighted sum and its backward are the native
+        kernels.  COVA_B200_GAT_TRAIN=torch selects the pure PyTorch-operator formulation below instead."""
+        if os.environ.get("COVA_B200_GAT_TRAIN", "native") != "torch":
+            Hd = self.hidden_dim
+            a = self.attention_layer.weight[0]
+            pad = torch.zeros((2, self.in_features), dtype=h_i.dtype, device=h_i.device)
+            ext_w = torch.cat((self.W_j.weight, (a[:Hd] @ self.W_i.weight)[None], (a[Hd:] @ self.W_j.weight)[None], pad), 0)
+            out, attn = _GatGatherFn.apply(F.linear(h_i, ext_w), self.attention_layer.bias, context_indices, Hd,
+                                           float(self.leakyrelu.negative_slope))
+            return (out, attn) if return_attn_wts else out
         N, K = context_indices.shape
         Hd = self.hidden_dim
         a = self.attention_layer.weight[0]

@@ -135,6 +135,19 @@ def roi_fwd(fm, rois, P, spatial_scale, out, mode="pool", sampling_ratio=2, want
     return argmax
 
 
+def roi_pool_bwd(grad_out, argmax, rois, fm_shape):
+    """Scatter-add of the pooled gradients [T, C*PH*PW] to their arg-max pixels -> NHWC fp32 [B,Hf,Wf,C]."""
+    _cuda(grad_out, torch.float32, "grad_out")
+    B, Hf, Wf, C = fm_shape
+    T, _, PH, PW = argmax.shape
+    if grad_out.stride(1) != 1:
+        grad_out = grad_out.contiguous()
+    grad_fm = torch.zeros(fm_shape, dtype=torch.float32, device=grad_out.device)
+    _call("cova_roi_pool_bwd", grad_out.data_ptr(), grad_out.stride(0) if T else C * PH * PW, _ptr(argmax),
+          _ptr(rois.contiguous()), T, C, PH, PW, B, Hf, Wf, grad_fm.data_ptr(), _stream())
+    return grad_fm
+
+
 def bbox_enc_fwd(rois, w, b, bn_scale, bn_shift, out):
     _cuda(rois, torch.float32, "bboxes")
     rois = rois.contiguous()
@@ -202,3 +215,18 @@ def gat_fwd(whj, s, t, att_b, alpha, ctx_idx, out, want_attn=False):
     _call("cova_gat_fwd", whj.data_ptr(), whj.stride(0), s.data_ptr(), t.data_ptr(), s.stride(0), float(att_b),
           float(alpha), ctx_idx.data_ptr(), T, K, Hd, out.data_ptr(), out.stride(0), _ptr(attn), _stream())
     return attn
+
+
+def gat_bwd(grad_out, ext, Hd, att_b, alpha, ctx_idx, attn):
+    """Backward of `gat_fwd` for ext = [whj | s | t | pad] ([T, Hd+4]): returns (d_ext [T,Hd+4], d_bias [1])."""
+    _cuda(grad_out, torch.float32, "grad_out")
+    grad_out = grad_out.contiguous()
+    ctx_idx = ctx_idx.contiguous()
+    T, K = ctx_idx.shape
+    d_ext = torch.zeros_like(ext)
+    d_b = torch.zeros(1, dtype=torch.float32, device=ext.device)
+    ld = ext.stride(0)
+    _call("cova_gat_bwd", grad_out.data_ptr(), grad_out.stride(0), ext.data_ptr(), ld, ext[:, Hd].data_ptr(),
+          ext[:, Hd + 1].data_ptr(), ld, float(att_b), float(alpha), ctx_idx.data_ptr(), attn.data_ptr(), T, K, Hd,
+          d_ext.data_ptr(), ld, d_ext[:, Hd].data_ptr(), d_ext[:, Hd + 1].data_ptr(), ld, d_b.data_ptr(), _stream())
+    return d_ext, d_b

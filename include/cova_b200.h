@@ -92,6 +92,11 @@ int cova_roi_fwd(const float* fm, int B, int Hf, int Wf, int C, const float* roi
                  float spatial_scale, int mode, int sampling_ratio, float* out, int64_t ld_out, int32_t* argmax,
                  void* stream);
 
+/* ---- A4 backward (A9, `train.py:59`): scatter-add of the pooled gradients to their arg-max pixels
+ * (torchvision roi_pool backward).  grad_fm: NHWC fp32 [B,Hf,Wf,C], ZEROED by the caller; argmax from cova_roi_fwd. */
+int cova_roi_pool_bwd(const float* grad_out, int64_t ld_go, const int32_t* argmax, const float* rois, int T, int C,
+                      int PH, int PW, int B, int Hf, int Wf, float* grad_fm, void* stream);
+
 /* ---- A5: positional encoder.  Replaces `_get_bbox_features` + `bbox_feat_encoder`
  * (`models.py:129-148`, `:65-70`): [x1,y1,w,h,w/h] -> Linear(5,D) -> folded BN1d -> ReLU.
  * Writes out[t*ld_out + d], d < D (so it can land at column C*P*P of the `own` row: the concat of
@@ -128,6 +133,13 @@ int cova_pack_linear_weight(const float* w, int N, int K, void* packed, void* st
 int cova_gat_fwd(const float* whj, int64_t ld_whj, const float* s, const float* t, int64_t ld_st, float att_b,
                  float alpha, const int64_t* ctx_idx, int T, int K, int Hd, float* out, int64_t ld_out, float* attn,
                  void* stream);
+
+/* ---- A6 backward (A9): gradients of cova_gat_fwd w.r.t. whj, s, t and the bias, given grad_out [T,Hd] and the
+ * attention weights saved by the forward.  d_whj / d_t / d_b are accumulated with atomics and must be ZEROED by the
+ * caller; d_s is overwritten.  d_s / d_t: element i at [i*ld_dst].                                           */
+int cova_gat_bwd(const float* grad_out, int64_t ld_go, const float* whj, int64_t ld_whj, const float* s, const float* t,
+                 int64_t ld_st, float att_b, float alpha, const int64_t* ctx_idx, const float* attn, int T, int K, int Hd,
+                 float* d_whj, int64_t ld_dw, float* d_s, float* d_t, int64_t ld_dst, float* d_b, void* stream);
 
 #ifdef __cplusplus
 }

@@ -589,6 +589,50 @@ def test_train_step_matches_reference_grads():
     assert rel_err(t2n(a), t2n(b)) < 1e-4
 
 
+def test_roi_pool_backward_kernel_vs_torch_scatter():
+    """Native RoIPool backward == an index_add over the arg-max indices (overlapping bins/boxes collide)."""
+    o = ops()
+    g = torch.Generator().manual_seed(17)
+    fm = torch.randn(2, 40, 48, 64, generator=g).to(DEV)
+    _, bboxes, _, _ = synth.gen(2, 30, 8, seed=17, img=160)
+    bboxes = bboxes.to(DEV)
+    out = torch.empty((60, 576), device=DEV)
+    am = o.roi_fwd(fm, bboxes, (3, 3), 0.25, out, want_argmax=True)
+    go = torch.randn(60, 576, generator=g).to(DEV)
+    got = o.roi_pool_bwd(go, am, bboxes, fm.shape)
+    amf = am.reshape(60, 64, 9).long()
+    valid = amf >= 0
+    flat = ((bboxes[:, 0].long().view(60, 1, 1) * 40 * 48 + amf.clamp_min(0)) * 64 + torch.arange(64, device=DEV).view(1, 64, 1))
+    want = torch.zeros(fm.numel(), device=DEV, dtype=torch.float64)
+    want.index_add_(0, flat[valid], go.reshape(60, 64, 9)[valid].double())
+    assert rel_err(t2n(got).reshape(-1), want.cpu().numpy()) < 1e-5
+
+
+def test_gat_backward_kernel_vs_autograd():
+    """Native GAT gather backward vs PyTorch autograd of the operator formulation (arbitrary ids, padding, an
+    all -1 row), for the layer's input and all four parameters."""
+    from cova_b200.models import GraphAttentionLayer
+    import os
+    g = torch.Generator().manual_seed(23)
+    h = torch.randn(50, 96, generator=g).to(DEV)
+    ci = torch.randint(-1, 50, (50, 12), generator=g)
+    ci[5] = -1
+    ci = ci.to(DEV)
+    go = torch.randn(50, 64, generator=g).to(DEV)
+    layer = GraphAttentionLayer(96, 64).to(DEV)
+    grads = {}
+    for mode in ("native", "torch"):
+        os.environ["COVA_B200_GAT_TRAIN"] = mode
+        x = h.clone().requires_grad_(True)
+        layer.zero_grad()
+        out = layer(x, ci)
+        (out * go).sum().backward()
+        grads[mode] = [out.detach(), x.grad] + [p.grad.clone() for p in layer.parameters()]
+    os.environ.pop("COVA_B200_GAT_TRAIN")
+    for a, b in zip(grads["native"], grads["torch"]):
+        assert rel_err(t2n(a), t2n(b)) < 2e-4 or float(b.abs().max()) < 1e-6
+
+
 def test_inputs_rejected_loudly():
     o = ops()
     with pytest.raises(RuntimeError, match="CUDA tensor"):
