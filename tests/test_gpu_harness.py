@@ -1,0 +1,96 @@
+"""GPU: the reference's training / evaluation harness semantics against the drop-in model.
+
+`/root/reference` does not exist on the GPU box, so this restates - call for call - what `train.py:train_model`
+(:9-96) and `train.py:evaluate_model` (:99-171) do with the model: `.to(device)`, `.train()` / `.eval()`, Adam +
+StepLR(gamma=1) + CrossEntropyLoss(reduction="sum") (`main.py:133-139`), `loss.backward()`, per-image top-k accuracy
+from raw logits via `argsort(dim=0)`, `state_dict()` save / `load_state_dict()` restore of the best epoch."""
+import copy
+import warnings
+
+import numpy as np
+import pytest
+import torch
+
+import cova_b200.synth as synth
+
+pytestmark = pytest.mark.gpu
+warnings.filterwarnings("ignore")
+DEV = torch.device("cuda:0")
+
+
+def make_loader(n_batches, B, N, K, img, seed):
+    out = []
+    for i in range(n_batches):
+        images, bboxes, add, ci, labels = synth.gen(B, N, K, seed=seed + i, img=img, with_labels=True)
+        out.append((np.array([f"img{i}_{j}" for j in range(B)]), images, bboxes, add, ci, labels))
+    return out
+
+
+@torch.no_grad()
+def evaluate_model(model, loader, k=1):                      # train.py:99-171
+    model.eval()
+    n_classes = model.n_classes
+    img_acc = []
+    for _, images, bboxes, add, ci, labels in loader:
+        labels = labels.to(DEV)
+        output = model(images.to(DEV), bboxes.to(DEV), add.to(DEV), ci.to(DEV))      # native kernels (no_grad + eval)
+        batch_indices = torch.unique(bboxes[:, 0]).long()
+        for index in batch_indices:                                                  # train.py:131-154
+            img_indices = (bboxes[:, 0] == index).to(DEV)
+            labels_img, output_img = labels[img_indices].view(-1, 1), output[img_indices]
+            indexes = torch.arange(labels_img.shape[0], device=DEV).view(-1, 1)
+            top_k = torch.argsort(output_img, dim=0)[output_img.shape[0] - k:]
+            correct = [float(indexes[labels_img == c].view(-1)[0] in top_k[:, c]) if (labels_img == c).any() else 1.0
+                       for c in range(1, n_classes)]
+            img_acc.append(correct)
+    return np.array(img_acc).mean(0) * 100
+
+
+def test_train_eval_cycle_like_reference_harness():
+    from cova_b200.models import CoVA
+    torch.manual_seed(123)
+    model = CoVA((3, 3), 256, 4, True, 384, 32, 0, 0.2, ["BG", "Price", "Title", "Image"], pretrained=False).to(DEV)
+    assert model.n_classes == 4 and list(model.class_names)[1] == "Price"
+    train_loader = make_loader(3, 4, 20, 8, 256, seed=100)
+    val_loader = make_loader(1, 4, 20, 8, 256, seed=200)
+    optimizer = torch.optim.Adam(model.parameters(), lr=5e-4, weight_decay=1e-3)       # main.py:133-135
+    scheduler = torch.optim.lr_scheduler.StepLR(optimizer, step_size=100, gamma=1)     # main.py:136-138
+    criterion = torch.nn.CrossEntropyLoss(reduction="sum").to(DEV)                     # main.py:139
+
+    losses, best, best_sd = [], -1.0, None
+    for epoch in range(4):
+        model.train()                                                                  # train.py:27
+        epoch_loss = 0.0
+        for _, images, bboxes, add, ci, labels in train_loader:
+            labels = labels.to(DEV)
+            optimizer.zero_grad()
+            output = model(images.to(DEV), bboxes.to(DEV), add.to(DEV), ci.to(DEV))    # train.py:47-52 (autograd path)
+            assert output.shape == (labels.shape[0], 4) and output.requires_grad
+            predictions = output.argmax(dim=1)
+            _ = (predictions == labels).sum().item()
+            loss = criterion(output, labels)
+            epoch_loss += loss.item()
+            loss.backward()
+            optimizer.step()
+        scheduler.step()
+        losses.append(epoch_loss)
+        acc = evaluate_model(model, val_loader).mean()                                 # train.py:72-78
+        if acc >= best:
+            best, best_sd = acc, copy.deepcopy(model.state_dict())                     # train.py:84 (torch.save)
+    assert losses[-1] < losses[0], losses
+    assert all(p.grad is not None for p in model.parameters())
+
+    # restore the best checkpoint into a FRESH model (train.py:94, evaluate.py:198) and reproduce its logits exactly
+    fresh = CoVA((3, 3), 256, 4, True, 384, 32, 0, 0.2, None, pretrained=False).to(DEV)
+    fresh.load_state_dict(best_sd)
+    model.load_state_dict(best_sd)
+    model.eval(); fresh.eval()
+    _, images, bboxes, add, ci, _ = val_loader[0]
+    with torch.no_grad():
+        a = model(images.to(DEV), bboxes.to(DEV), add.to(DEV), ci.to(DEV))
+        b = fresh(images.to(DEV), bboxes.to(DEV), add.to(DEV), ci.to(DEV))
+    assert torch.equal(a, b)
+    # eval-mode native logits agree with the eval-mode autograd composite (same weights, running statistics)
+    with torch.enable_grad():
+        c = model(images.to(DEV), bboxes.to(DEV), add.to(DEV), ci.to(DEV))
+    assert float((a - c).abs().max()) < 1e-3 * float(c.abs().max())
