@@ -12,8 +12,9 @@
 //     that sliding window - K-chunk 1 of row j aliases K-chunk 0 of row j+1 (tools/probe_umma_noswz.cu).
 //     So one conv row of 128 output pixels = 7 filter rows x 2 MMAs (K = 16 each) on the ring rows, no copies.
 //   * accumulators (128 px x 64 cout fp32) live in TMEM, double buffered; epilogue warps apply BN + ReLU and
-//     max-pool on the fly: horizontal 3-max with warp shuffles (lane = conv pixel), vertical 3-max as a running
-//     maximum in registers while the CTA marches down conv rows; only pooled pixels are written.
+//     max-pool on the fly: vertical 3-max as a per-lane running maximum in registers while the CTA marches down conv
+//     rows, then one horizontal 3-max with warp shuffles (lane = conv pixel) per pooled row; only pooled pixels are
+//     written.  ReLU is folded into the maximum (the running maximum starts from 0).
 //
 // Work decomposition: CTA = (page, band of pooled rows), processed strip by strip (128 conv columns = 64 pooled
 // columns).  The right-most conv column of strip i is kept per conv row in shared memory and is the left
@@ -36,8 +37,10 @@ constexpr int SX_W_CHUNK = 2 * 64 * 16;    // 2,048 B: one K-chunk = 64 hi rows 
 constexpr int SX_W_BYTES = SX_KCHUNKS * SX_W_CHUNK;   // 57,344 B: [chunk][plane][cout][8] bf16
 constexpr int SX_MAXROWS = 81;             // conv rows per band (2*40 + 1)
 constexpr int SX_ND = 16;                  // tile-row completion barriers
-constexpr int SX_THREADS = 416;            // warp 0 MMA, warps 1-8 epilogue (2 per TMEM lane group), warps 9-12 converters
-constexpr int SX_EPI_THREADS = 256;
+constexpr int SX_EPI_WARPS = 16;            // 4 per TMEM lane group, 16 output channels each
+constexpr int SX_EPI_THREADS = SX_EPI_WARPS * 32;
+constexpr int SX_CH = 64 / (SX_EPI_WARPS / 4);   // channels per epilogue warp
+constexpr int SX_THREADS = 32 * (1 + SX_EPI_WARPS + 4);   // warp 0 MMA, epilogue warps, 4 converter warps
 
 
 template <bool SPLIT>
@@ -163,99 +166,104 @@ stem_tc_kernel(const StemTcParams p) {
         __syncwarp();
       }
     }
-  } else if (warp <= 8) {
+  } else if (warp <= SX_EPI_WARPS) {
     // ======================= epilogue: BN + ReLU + 3x3/s2 max-pool =======================
     const int lg = warp & 3;                       // TMEM lane group this warp may read
-    const int ch0 = ((warp - 1) >> 2) * 32;        // this warp's 32 output channels (two warps per lane group)
+    const int ch0 = ((warp - 1) >> 2) * SX_CH;     // this warp's output channels (SX_EPI_WARPS/4 warps per lane group)
     const int m = lg * 32 + lane;                  // conv column within the strip
-    float acc_v[32];                               // running vertical max of the current pooling window
+    float acc_v[SX_CH];                            // running vertical max of the current pooling window
     uint32_t t = 0;
     for (int strip = 0; strip < n_strips; ++strip) {
       const int ox = strip * SX_TM + m;
+      // ReLU is folded into the pooling: max(0, max_window(bn(x))) == max_window(relu(bn(x))), and 0 is also what
+      // pool padding contributes after ReLU - so the running maximum simply starts from 0.
 #pragma unroll
-      for (int c = 0; c < 32; ++c) acc_v[c] = 0.f;   // post-ReLU values are >= 0: 0 is the neutral element
+      for (int c = 0; c < SX_CH; ++c) acc_v[c] = 0.f;
       for (int i = 0; i < n_conv; ++i, ++t) {
         const int oy = oy_begin + i;
         const uint32_t acc = t & 1;
         ptx::mbar_wait(&sm.tmem_full[acc], (t >> 1) & 1);
         ptx::tc_fence_after();
-        uint32_t raw[2][16];
+        uint32_t raw[SX_CH];
+        float v[SX_CH];
         const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + acc * ACC_COLS + ch0;
-#pragma unroll
-        for (int q = 0; q < 2; ++q) ptx::tmem_ld16(taddr + q * 16, raw[q]);
+        ptx::tmem_ld16(taddr, *reinterpret_cast<uint32_t(*)[16]>(raw));
         ptx::tmem_ld_wait();
-        float v[32];
 #pragma unroll
-        for (int q = 0; q < 2; ++q)
-#pragma unroll
-          for (int j = 0; j < 16; ++j) v[q * 16 + j] = __uint_as_float(raw[q][j]);
+        for (int j = 0; j < SX_CH; ++j) v[j] = __uint_as_float(raw[j]);
         if (SPLIT) {   // columns 64..127 hold Ahi*Wlo
-#pragma unroll
-          for (int q = 0; q < 2; ++q) ptx::tmem_ld16(taddr + 64 + q * 16, raw[q]);
+          ptx::tmem_ld16(taddr + 64, *reinterpret_cast<uint32_t(*)[16]>(raw));
           ptx::tmem_ld_wait();
 #pragma unroll
-          for (int q = 0; q < 2; ++q)
-#pragma unroll
-            for (int j = 0; j < 16; ++j) v[q * 16 + j] += __uint_as_float(raw[q][j]);
+          for (int j = 0; j < SX_CH; ++j) v[j] += __uint_as_float(raw[j]);
         }
         ptx::tc_fence_before();
         ptx::mbar_arrive(&sm.tmem_empty[acc]);
 
 #pragma unroll
-        for (int c = 0; c < 32; ++c) v[c] = fmaxf(fmaf(v[c], sm.scale[ch0 + c], sm.shift[ch0 + c]), 0.f);
+        for (int c = 0; c < SX_CH; ++c) v[c] = fmaf(v[c], sm.scale[ch0 + c], sm.shift[ch0 + c]);   // BN; ReLU comes with the max
         if (ox >= p.Wc) {   // conv columns past the image (last, partial strip only) act as pool padding
 #pragma unroll
-          for (int c = 0; c < 32; ++c) v[c] = 0.f;
+          for (int c = 0; c < SX_CH; ++c) v[c] = 0.f;
         }
+        // Pooling order: vertical first (a per-lane running maximum over the window's conv rows - no cross-lane
+        // traffic), horizontal once per POOLED row.  max is associative, so this equals the 3x3 window maximum, and it
+        // halves the shuffles, the lane-31 exchange and the epilogue barrier (they dominated the epilogue).
+        const bool odd = oy & 1;
+        const bool emit = odd || (oy == p.Hc - 1);                 // the conv row that completes pooled row py
+        if (!emit) {
+#pragma unroll
+          for (int c = 0; c < SX_CH; ++c) acc_v[c] = fmaxf(acc_v[c], v[c]);
+          continue;
+        }
+        float w[SX_CH];
+#pragma unroll
+        for (int c = 0; c < SX_CH; ++c) w[c] = fmaxf(acc_v[c], v[c]);        // column maximum of the window (>= 0: ReLU)
         // lane 31 publishes its column for the next warp (and, from the last lane group, for the next strip)
-        float* xrow = sm.xch[t & 1][lg] + ch0;
+        const int py = oy >> 1;
+        float* xrow = sm.xch[py & 1][lg] + ch0;
         if (lane == 31) {
 #pragma unroll
-          for (int c = 0; c < 32; c += 4) *reinterpret_cast<float4*>(xrow + c) = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
+          for (int c = 0; c < SX_CH; c += 4) *reinterpret_cast<float4*>(xrow + c) = make_float4(w[c], w[c + 1], w[c + 2], w[c + 3]);
           if (lg == 3) {
             float* e = sm.edge[strip & 1][i] + ch0;
 #pragma unroll
-            for (int c = 0; c < 32; c += 4) *reinterpret_cast<float4*>(e + c) = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
+            for (int c = 0; c < SX_CH; c += 4) *reinterpret_cast<float4*>(e + c) = make_float4(w[c], w[c + 1], w[c + 2], w[c + 3]);
           }
         }
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        const float* left = (lg > 0 ? sm.xch[t & 1][lg - 1] : sm.edge[(strip & 1) ^ 1][i]) + ch0;
+        asm volatile("bar.sync 1, %0;" ::"n"(SX_EPI_THREADS) : "memory");
+        const float* left = (lg > 0 ? sm.xch[py & 1][lg - 1] : sm.edge[(strip & 1) ^ 1][i]) + ch0;
         const bool left_zero = (lg == 0 && strip == 0);            // conv column -1 = pool padding
-        const bool emit = (oy & 1) || (oy == p.Hc - 1);
-        const int py = oy >> 1;
         const int px = ox >> 1;
-        const bool writer = emit && !(lane & 1) && py >= py0 && py < py1 && px < p.Wp;
+        const bool writer = !(lane & 1) && py >= py0 && py < py1 && px < p.Wp;
         const size_t opix = (((size_t)b * p.Hp + py) * p.Wp + px) * 64 + ch0;
+        float o[SX_CH];
 #pragma unroll
-        for (int c16 = 0; c16 < 32; c16 += 16) {
-          float o[16];
+        for (int c = 0; c < SX_CH; ++c) {
+          float l = __shfl_up_sync(0xffffffffu, w[c], 1);
+          const float r = __shfl_down_sync(0xffffffffu, w[c], 1);
+          if (lane == 0) l = left_zero ? 0.f : left[c];
+          o[c] = fmaxf(fmaxf(l, w[c]), r);                        // horizontal 3-max (valid on even lanes)
+          acc_v[c] = fmaxf(v[c], 0.f);                            // an odd conv row also opens pooled row py + 1
+        }
+        if (writer) {
+          if (OUT_DTYPE == COVA_F32) {
+            float* dst = reinterpret_cast<float*>(p.out0) + opix;
 #pragma unroll
-          for (int e = 0; e < 16; ++e) {
-            const int c = c16 + e;
-            float l = __shfl_up_sync(0xffffffffu, v[c], 1);
-            const float r = __shfl_down_sync(0xffffffffu, v[c], 1);
-            if (lane == 0) l = left_zero ? 0.f : left[c];
-            const float h = fmaxf(fmaxf(l, v[c]), r);               // horizontal 3-max (valid on even lanes)
-            const float a = fmaxf(acc_v[c], h);
-            o[e] = a;
-            acc_v[c] = (oy & 1) ? h : a;                            // an odd row also opens the next window
-          }
-          if (writer) {
-            if (OUT_DTYPE == COVA_F32) {
-              float* dst = reinterpret_cast<float*>(p.out0) + opix + c16;
+            for (int hlf = 0; hlf < SX_CH / 8; ++hlf) {
+              uint32_t w8[8];
 #pragma unroll
-              for (int hlf = 0; hlf < 2; ++hlf) {
-                uint32_t w8[8];
+              for (int e = 0; e < 8; ++e) w8[e] = __float_as_uint(o[hlf * 8 + e]);
+              st_global_v8(dst + hlf * 8, w8);
+            }
+          } else {
 #pragma unroll
-                for (int e = 0; e < 8; ++e) w8[e] = __float_as_uint(o[hlf * 8 + e]);
-                st_global_v8(dst + hlf * 8, w8);
-              }
-            } else {
+            for (int c16 = 0; c16 < SX_CH; c16 += 16) {
               uint32_t hw[8], lw[8];
 #pragma unroll
               for (int e = 0; e < 8; ++e) {
-                if (OUT_DTYPE == COVA_BF16X2) split_bf16x2(o[2 * e], o[2 * e + 1], hw[e], lw[e]);
-                else hw[e] = pack2_bf16(o[2 * e], o[2 * e + 1]);
+                if (OUT_DTYPE == COVA_BF16X2) split_bf16x2(o[c16 + 2 * e], o[c16 + 2 * e + 1], hw[e], lw[e]);
+                else hw[e] = pack2_bf16(o[c16 + 2 * e], o[c16 + 2 * e + 1]);
               }
               st_global_v8(reinterpret_cast<__nv_bfloat16*>(p.out0) + opix + c16, hw);
               if (OUT_DTYPE == COVA_BF16X2) st_global_v8(reinterpret_cast<__nv_bfloat16*>(p.out1) + opix + c16, lw);
@@ -266,7 +274,7 @@ stem_tc_kernel(const StemTcParams p) {
     }
   } else {
     // ======================= converters: NCHW fp32 rows -> ring of 4-channel bf16 pixels =======================
-    const int cw = warp - 9;                        // this warp owns input rows g with g % 4 == cw
+    const int cw = warp - 1 - SX_EPI_WARPS;         // this warp owns input rows g with g % 4 == cw
     const size_t plane = (size_t)p.H * p.W;
     const size_t img_b = (size_t)b * 3 * plane;
     const uint32_t n_rows_total = (uint32_t)n_strips * NQ;
