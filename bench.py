@@ -23,7 +23,13 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 warnings.filterwarnings("ignore")
 
-B_PER_GPU, N_BOXES, K_CTX, IMG = 16, 90, 24, 1280
+# Headline workload = BASELINE.json configs[1].  The COVA_B200_* environment overrides exist for side experiments
+# (configs 3-5 shapes: ResNet-50, N=300, K=48, 2 heads); a run with any override says so in `config`.
+B_PER_GPU = int(os.environ.get("COVA_B200_B", 16))
+N_BOXES = int(os.environ.get("COVA_B200_N", 90))
+K_CTX = int(os.environ.get("COVA_B200_K", 24))
+N_HEADS = int(os.environ.get("COVA_B200_HEADS", 1))
+IMG = 1280
 CONV_FLOP_PER_PAGE = 2 * 9 * 64 * 64 * 320 * 320          # one 3x3 64->64 conv on the 320x320 map
 STEM_FLOP_PER_PAGE = 2 * 64 * 147 * 640 * 640
 
@@ -84,9 +90,9 @@ def build_model(dev):
     import cova_b200.synth as synth
     from cova_b200.models import CoVA
     bk = os.environ.get("COVA_B200_BACKBONE", "resnet18")     # resnet50 = a side experiment, not the headline config
-    m = CoVA((3, 3), IMG, 4, True, 384, 32, 0, 0.2, None, pretrained=False, backbone=bk,
+    m = CoVA((3, 3), IMG, 4, True, 384, 32, 0, 0.2, None, pretrained=False, backbone=bk, n_heads=N_HEADS,
              engine=os.environ.get("COVA_B200_ENGINE", "tcgen05"), precision=os.environ.get("COVA_B200_PRECISION", "fp32"))
-    m.load_state_dict(synth.make_state_dict(123, backbone=bk), strict=True)
+    m.load_state_dict(synth.make_state_dict(123, backbone=bk, n_heads=N_HEADS), strict=True)
     return m.to(dev).eval()
 
 
@@ -183,6 +189,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--skip-cpu", action="store_true", help="side experiments: do not time the CPU port")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "native" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
@@ -299,7 +306,7 @@ def main():
                 "share_of_step": round(stages[dom][0] / sum(v[0] for v in stages.values()), 3)}
 
     cores = os.cpu_count() or 1
-    cpu_v, sample = cpu_baseline(cores)
+    cpu_v, sample = (None, "skipped (--skip-cpu)") if args.skip_cpu else cpu_baseline(cores)
     h2d = sum(t.numel() * t.element_size() for t in pinned)
     print(json.dumps({
         "metric": "webpages/sec", "value": value, "unit": "pages/s", "n_gpus": world, "steps": args.steps,
@@ -308,8 +315,12 @@ def main():
         if model.engine == "tcgen05" else "f32",
         "data": "synthetic",
         "config": {"workload": "configs[1]: batch=16 synthetic 1280x1280 pages per GPU, N=90 boxes, K=24, "
-                               "ResNet-18 backbone, inference", "pages_per_gpu_per_step": B_PER_GPU,
+                               "ResNet-18 backbone, inference" if (B_PER_GPU, N_BOXES, K_CTX, N_HEADS, model.backbone) ==
+                               (16, 90, 24, 1, "resnet18") else "side experiment (COVA_B200_* overrides), inference",
+                   "pages_per_gpu_per_step": B_PER_GPU,
                    "engine": model.engine, "precision": model.precision, "backbone": model.backbone,
+                   "boxes_per_page": N_BOXES, "neighbours": K_CTX, "gat_heads": N_HEADS,
+                   "headline": (B_PER_GPU, N_BOXES, K_CTX, N_HEADS, model.backbone) == (16, 90, 24, 1, "resnet18"),
                    "l2": "inputs larger than L2 (315 MB of images per step vs 126 MB L2); no flush needed"},
         "clocks": clocks, "gpu_launches": launches,
         "e2e": {"value": e2e, "unit": "pages/s", "h2d_bytes_per_step": h2d,

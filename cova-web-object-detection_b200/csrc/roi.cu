@@ -180,12 +180,20 @@ __device__ __forceinline__ float4 bilinear4(const float* __restrict__ base, int 
   return r;
 }
 
-// One CTA = one box; 16 lanes x float4 = one 64-channel block of one bin; items (bin, channel block) are
-// spread over the 16 half-warps of the CTA.
+// 16 lanes x float4 = one 64-channel block of one (box, bin); the T*P*P*(C/64) items are spread evenly over all
+// half-warps of the grid (a CTA-per-box layout left 7 of 16 half-warps idle for 3x3 bins and was latency-bound).
 __global__ void __launch_bounds__(ROI_THREADS)
-roi_align_kernel(const float* __restrict__ fm, int Hf, int Wf, int C, const float* __restrict__ rois, int PH,
+roi_align_kernel(const float* __restrict__ fm, int Hf, int Wf, int C, const float* __restrict__ rois, int T, int PH,
                  int PW, float scale, int sampling_ratio, float* __restrict__ out, int64_t ld_out) {
-  const int t = blockIdx.x;
+  const int nbins = PH * PW, ncb = C / ROI_CB;
+  const int64_t n_items = (int64_t)T * nbins * ncb;
+  const int64_t item = (int64_t)blockIdx.x * (ROI_THREADS / 16) + (threadIdx.x >> 4);
+  if (item >= n_items) return;
+  const int c4 = (threadIdx.x & 15) * 4;
+  const int t = (int)(item / (nbins * ncb));
+  const int rem = (int)(item % (nbins * ncb));
+  const int bin = rem % nbins, cb = (rem / nbins) * ROI_CB;
+  const int ph = bin / PW, pw = bin % PW;
   const float* roi = rois + (size_t)t * 5;
   const int b = (int)roi[0];
   const float x1 = roi[1] * scale, y1 = roi[2] * scale, x2 = roi[3] * scale, y2 = roi[4] * scale;
@@ -194,27 +202,21 @@ roi_align_kernel(const float* __restrict__ fm, int Hf, int Wf, int C, const floa
   const int gh = sampling_ratio > 0 ? sampling_ratio : (int)ceilf(rh / (float)PH);
   const int gw = sampling_ratio > 0 ? sampling_ratio : (int)ceilf(rw / (float)PW);
   const float cnt = (float)max(gh * gw, 1);
-  const int nbins = PH * PW, ncb = C / ROI_CB;
-  const int hw = threadIdx.x >> 4, c4 = (threadIdx.x & 15) * 4;
-  const float* base = fm + (size_t)b * Hf * Wf * C;
-  for (int item = hw; item < nbins * ncb; item += ROI_THREADS / 16) {
-    const int bin = item % nbins, cb = (item / nbins) * ROI_CB;
-    const int ph = bin / PW, pw = bin % PW;
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int iy = 0; iy < gh; ++iy) {
-      const float y = y1 + (float)ph * bh + ((float)iy + 0.5f) * bh / (float)gh;
-      for (int ix = 0; ix < gw; ++ix) {
-        const float x = x1 + (float)pw * bw + ((float)ix + 0.5f) * bw / (float)gw;
-        const float4 v = bilinear4(base + cb + c4, Hf, Wf, C, y, x);
-        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
-      }
+  const float* base = fm + (size_t)b * Hf * Wf * C + cb + c4;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int iy = 0; iy < gh; ++iy) {
+    const float y = y1 + (float)ph * bh + ((float)iy + 0.5f) * bh / (float)gh;
+    for (int ix = 0; ix < gw; ++ix) {
+      const float x = x1 + (float)pw * bw + ((float)ix + 0.5f) * bw / (float)gw;
+      const float4 v = bilinear4(base, Hf, Wf, C, y, x);
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
     }
-    float* o = out + (size_t)t * ld_out + (size_t)(cb + c4) * nbins + bin;
-    o[0] = acc.x / cnt;
-    o[nbins] = acc.y / cnt;
-    o[2 * nbins] = acc.z / cnt;
-    o[3 * nbins] = acc.w / cnt;
   }
+  float* o = out + (size_t)t * ld_out + (size_t)(cb + c4) * nbins + bin;
+  o[0] = acc.x / cnt;
+  o[nbins] = acc.y / cnt;
+  o[2 * nbins] = acc.z / cnt;
+  o[3 * nbins] = acc.w / cnt;
 }
 
 // RoIPool backward (torchvision roi_pool backward): every pooled output sends its gradient to its arg-max pixel.
@@ -279,7 +281,9 @@ extern "C" int cova_roi_fwd(const float* fm, int B, int Hf, int Wf, int C, const
   cudaStream_t st = (cudaStream_t)stream;
   if (mode == 1) {
     COVA_REQUIRE(argmax == nullptr, "cova_roi_fwd: RoIAlign has no argmax");
-    roi_align_kernel<<<T, ROI_THREADS, 0, st>>>(fm, Hf, Wf, C, rois, PH, PW, spatial_scale, sampling_ratio, out, ld_out);
+    const int64_t n_items = (int64_t)T * PH * PW * (C / ROI_CB);
+    roi_align_kernel<<<(unsigned)((n_items + ROI_THREADS / 16 - 1) / (ROI_THREADS / 16)), ROI_THREADS, 0, st>>>(
+        fm, Hf, Wf, C, rois, T, PH, PW, spatial_scale, sampling_ratio, out, ld_out);
   } else {
     const size_t one = (size_t)ROI_WARPS * PH * PW * ROI_CB * 4;
     const size_t smem = argmax ? 2 * one : one;

@@ -1,0 +1,56 @@
+"""Micro-benchmarks of the HBM-bound tail kernels (RoIPool, RoIAlign, GAT gather) at BASELINE config 2 and config 5
+shapes: CUDA events on the launching stream, L2 flushed between iterations (256 MB scratch write), algorithmic
+bytes per SURVEY.md 8(d).  Output -> profiles/."""
+import json, os, sys, warnings
+import numpy as np
+import torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+warnings.filterwarnings("ignore")
+import bench
+import cova_b200.synth as synth
+from cova_b200 import ops
+
+dev = torch.device("cuda", 0)
+HBM = bench.peaks()["hbm"]
+scratch = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+
+
+def timeit(fn, iters=20):
+    for _ in range(3):
+        fn()
+    ts = []
+    for _ in range(iters):
+        scratch.zero_()                      # flush L2 (126 MB)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); fn(); e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    return float(np.median(ts))
+
+
+def report(name, ms, bytes_alg):
+    gbs = bytes_alg / ms / 1e6
+    print(f"{name:58s} {ms*1e3:9.1f} us   {bytes_alg/1e6:9.1f} MB algorithmic   {gbs:8.0f} GB/s = {gbs/HBM:5.1%} of measured HBM copy peak")
+
+
+for (B, N, K, C, tag) in [(16, 90, 24, 64, "config 2 (B=16, N=90, K=24, C=64)"), (16, 300, 48, 64, "config 5 per GPU (B=16, N=300, K=48, C=64)")]:
+    _, bboxes, _, ci = synth.gen(B, N, K, seed=1, img=64)          # boxes/ids only (tiny images)
+    bboxes = bboxes.clone(); g = torch.Generator().manual_seed(1)
+    T = B * N
+    w = 16 + torch.rand(T, generator=g) * (512 - 16); h = 8 + torch.rand(T, generator=g) * (256 - 8)
+    x1 = torch.rand(T, generator=g) * (1280 - w); y1 = torch.rand(T, generator=g) * (1280 - h)
+    bboxes[:, 1], bboxes[:, 2], bboxes[:, 3], bboxes[:, 4] = x1, y1, x1 + w, y1 + h
+    fm = torch.randn(B, 320, 320, C, device=dev)
+    bb = bboxes.to(dev)
+    out = torch.empty((T, C * 9 + 416), device=dev)
+    ms = timeit(lambda: ops.roi_fwd(fm, bb, (3, 3), 0.25, out))
+    report(f"RoIPool   {tag}", ms, bench.roi_bytes(bboxes, C=C))
+    ms = timeit(lambda: ops.roi_fwd(fm, bb, (3, 3), 0.25, out, mode="align"))
+    report(f"RoIAlign  {tag}", ms, T * 9 * 4 * 4 * C * 4 + T * C * 9 * 4)
+    for heads in (1, 2):
+        Hd = 384 // heads
+        ext = torch.randn(T, Hd + 4, device=dev)
+        cid = ci.to(dev)
+        o = torch.empty((T, 992), device=dev)
+        ms = timeit(lambda: ops.gat_fwd(ext[:, :Hd], ext[:, Hd], ext[:, Hd + 1], 0.1, 0.2, cid, o[:, 608:608 + Hd]))
+        report(f"GAT gather {heads} head(s) x {Hd}  {tag}", ms * heads, heads * (T * K * Hd * 4 + T * Hd * 4 + T * K * 8))
