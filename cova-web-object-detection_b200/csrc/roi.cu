@@ -180,8 +180,30 @@ __device__ __forceinline__ float4 bilinear4(const float* __restrict__ base, int 
   return r;
 }
 
+// Branch-free form of the same sample: 4 tap offsets (pixels) + 4 weights; a sample outside [-1, size] gets zero
+// weights on a valid address, so all taps of all samples can be loaded back to back.
+struct BilinearTaps {
+  int o[4];
+  float w[4];
+};
+__device__ __forceinline__ BilinearTaps bilinear_taps(int Hf, int Wf, float y, float x) {
+  BilinearTaps t;
+  const bool valid = !(y < -1.0f || y > (float)Hf || x < -1.0f || x > (float)Wf);
+  y = fminf(fmaxf(y, 0.f), (float)Hf);
+  x = fminf(fmaxf(x, 0.f), (float)Wf);
+  int yl = (int)y, xl = (int)x, yh, xh;
+  if (yl >= Hf - 1) { yh = yl = Hf - 1; y = (float)yl; } else { yh = yl + 1; }
+  if (xl >= Wf - 1) { xh = xl = Wf - 1; x = (float)xl; } else { xh = xl + 1; }
+  const float ly = y - (float)yl, lx = x - (float)xl, hy = 1.f - ly, hx = 1.f - lx;
+  const float m = valid ? 1.f : 0.f;
+  t.w[0] = hy * hx * m; t.w[1] = hy * lx * m; t.w[2] = ly * hx * m; t.w[3] = ly * lx * m;
+  t.o[0] = yl * Wf + xl; t.o[1] = yl * Wf + xh; t.o[2] = yh * Wf + xl; t.o[3] = yh * Wf + xh;
+  return t;
+}
+
 // 16 lanes x float4 = one 64-channel block of one (box, bin); the T*P*P*(C/64) items are spread evenly over all
 // half-warps of the grid (a CTA-per-box layout left 7 of 16 half-warps idle for 3x3 bins and was latency-bound).
+template <int G>   // G = sampling_ratio when it is a compile-time 2 (all 16 bilinear taps in flight at once), 0 = runtime
 __global__ void __launch_bounds__(ROI_THREADS)
 roi_align_kernel(const float* __restrict__ fm, int Hf, int Wf, int C, const float* __restrict__ rois, int T, int PH,
                  int PW, float scale, int sampling_ratio, float* __restrict__ out, int64_t ld_out) {
@@ -199,17 +221,40 @@ roi_align_kernel(const float* __restrict__ fm, int Hf, int Wf, int C, const floa
   const float x1 = roi[1] * scale, y1 = roi[2] * scale, x2 = roi[3] * scale, y2 = roi[4] * scale;
   const float rw = fmaxf(x2 - x1, 1.f), rh = fmaxf(y2 - y1, 1.f);
   const float bh = rh / (float)PH, bw = rw / (float)PW;
-  const int gh = sampling_ratio > 0 ? sampling_ratio : (int)ceilf(rh / (float)PH);
-  const int gw = sampling_ratio > 0 ? sampling_ratio : (int)ceilf(rw / (float)PW);
+  const int gh = G > 0 ? G : (sampling_ratio > 0 ? sampling_ratio : (int)ceilf(rh / (float)PH));
+  const int gw = G > 0 ? G : (sampling_ratio > 0 ? sampling_ratio : (int)ceilf(rw / (float)PW));
   const float cnt = (float)max(gh * gw, 1);
   const float* base = fm + (size_t)b * Hf * Wf * C + cb + c4;
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int iy = 0; iy < gh; ++iy) {
-    const float y = y1 + (float)ph * bh + ((float)iy + 0.5f) * bh / (float)gh;
-    for (int ix = 0; ix < gw; ++ix) {
-      const float x = x1 + (float)pw * bw + ((float)ix + 0.5f) * bw / (float)gw;
-      const float4 v = bilinear4(base, Hf, Wf, C, y, x);
-      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+  if (G > 0) {
+    constexpr int NS = G > 0 ? G * G : 1;
+    BilinearTaps tp[NS];
+    float4 v[NS][4];
+#pragma unroll
+    for (int i = 0; i < NS; ++i) {
+      const float y = y1 + (float)ph * bh + ((float)(i / (G > 0 ? G : 1)) + 0.5f) * bh / (float)G;
+      const float x = x1 + (float)pw * bw + ((float)(i % (G > 0 ? G : 1)) + 0.5f) * bw / (float)G;
+      tp[i] = bilinear_taps(Hf, Wf, y, x);
+    }
+#pragma unroll
+    for (int i = 0; i < NS; ++i)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) v[i][k] = __ldg(reinterpret_cast<const float4*>(base + (size_t)tp[i].o[k] * C));
+#pragma unroll
+    for (int i = 0; i < NS; ++i) {   // per sample w1*v1 + w2*v2 + w3*v3 + w4*v4, samples summed in order (as torchvision)
+      acc.x += tp[i].w[0] * v[i][0].x + tp[i].w[1] * v[i][1].x + tp[i].w[2] * v[i][2].x + tp[i].w[3] * v[i][3].x;
+      acc.y += tp[i].w[0] * v[i][0].y + tp[i].w[1] * v[i][1].y + tp[i].w[2] * v[i][2].y + tp[i].w[3] * v[i][3].y;
+      acc.z += tp[i].w[0] * v[i][0].z + tp[i].w[1] * v[i][1].z + tp[i].w[2] * v[i][2].z + tp[i].w[3] * v[i][3].z;
+      acc.w += tp[i].w[0] * v[i][0].w + tp[i].w[1] * v[i][1].w + tp[i].w[2] * v[i][2].w + tp[i].w[3] * v[i][3].w;
+    }
+  } else {
+    for (int iy = 0; iy < gh; ++iy) {
+      const float y = y1 + (float)ph * bh + ((float)iy + 0.5f) * bh / (float)gh;
+      for (int ix = 0; ix < gw; ++ix) {
+        const float x = x1 + (float)pw * bw + ((float)ix + 0.5f) * bw / (float)gw;
+        const float4 v = bilinear4(base, Hf, Wf, C, y, x);
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+      }
     }
   }
   float* o = out + (size_t)t * ld_out + (size_t)(cb + c4) * nbins + bin;
@@ -282,8 +327,12 @@ extern "C" int cova_roi_fwd(const float* fm, int B, int Hf, int Wf, int C, const
   if (mode == 1) {
     COVA_REQUIRE(argmax == nullptr, "cova_roi_fwd: RoIAlign has no argmax");
     const int64_t n_items = (int64_t)T * PH * PW * (C / ROI_CB);
-    roi_align_kernel<<<(unsigned)((n_items + ROI_THREADS / 16 - 1) / (ROI_THREADS / 16)), ROI_THREADS, 0, st>>>(
-        fm, Hf, Wf, C, rois, T, PH, PW, spatial_scale, sampling_ratio, out, ld_out);
+    const unsigned grid = (unsigned)((n_items + ROI_THREADS / 16 - 1) / (ROI_THREADS / 16));
+    if (sampling_ratio == 2)
+      roi_align_kernel<2><<<grid, ROI_THREADS, 0, st>>>(fm, Hf, Wf, C, rois, T, PH, PW, spatial_scale, 2, out, ld_out);
+    else
+      roi_align_kernel<0><<<grid, ROI_THREADS, 0, st>>>(fm, Hf, Wf, C, rois, T, PH, PW, spatial_scale, sampling_ratio,
+                                                       out, ld_out);
   } else {
     const size_t one = (size_t)ROI_WARPS * PH * PW * ROI_CB * 4;
     const size_t smem = argmax ? 2 * one : one;
