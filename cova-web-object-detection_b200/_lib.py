@@ -68,6 +68,7 @@ SIGNATURES = {
     "cova_linear_fwd": (_I, [_P, _L, _I, _I, _P, _I, _P, _P, _P, _P, _L, _I, _I, _P, _P, _L, _I, _P]),
     "cova_pack_linear_weight": (_I, [_P, _I, _I, _P, _P]),
     "cova_gat_fwd": (_I, [_P, _L, _P, _P, _L, _F, _F, _P, _I, _I, _I, _P, _L, _P, _P]),
+    "cova_gat_multihead_fwd": (_I, [_P, _L, _I, _I, _c.POINTER(_F), _F, _P, _I, _I, _P, _L, _P, _P]),
     "cova_gat_bwd": (_I, [_P, _L, _P, _L, _P, _P, _L, _F, _F, _P, _P, _I, _I, _I, _P, _L, _P, _P, _L, _P, _P]),
 }
 

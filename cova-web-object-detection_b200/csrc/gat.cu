@@ -24,11 +24,22 @@ constexpr int GAT_E = 8;                 // elements (= warps) per CTA
 constexpr int GAT_THREADS = GAT_E * 32;
 constexpr int GAT_KMAX = 128;            // neighbours per element handled by one warp (4 per lane)
 constexpr int GAT_STAGE_BYTES = 96 * 1024;
+constexpr int GAT_MAX_HEADS = 8;
+struct GatBias { float b[GAT_MAX_HEADS]; };
 
 __global__ void __launch_bounds__(GAT_THREADS)
 gat_fwd_kernel(const float* __restrict__ whj, int64_t ld_whj, const float* __restrict__ s_vec,
-               const float* __restrict__ t_vec, int64_t ld_st, float att_b, float alpha, const int64_t* __restrict__ ctx, int T,
+               const float* __restrict__ t_vec, int64_t ld_st, GatBias att_b_h, float alpha, const int64_t* __restrict__ ctx, int T,
                int K, int Hd, float* __restrict__ out, int64_t ld_out, float* __restrict__ attn, int stage_ok, int out_vec) {
+  // blockIdx.y = attention head: head h reads whj columns [h*Hd, (h+1)*Hd), s/t at +2h, writes out
+  // columns [h*Hd, (h+1)*Hd) and attention weights [h][T][K]
+  const int head = blockIdx.y;
+  whj += (size_t)head * Hd;
+  s_vec += 2 * head;
+  t_vec += 2 * head;
+  out += (size_t)head * Hd;
+  if (attn != nullptr) attn += (size_t)head * T * K;
+  const float att_b = att_b_h.b[head];
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float* stage = reinterpret_cast<float*>(smem_raw);
   __shared__ uint64_t bar;
@@ -253,6 +264,28 @@ extern "C" int cova_gat_bwd(const float* grad_out, int64_t ld_go, const float* w
   return COVA_OK;
 }
 
+extern "C" int cova_gat_multihead_fwd(const float* ext, int64_t ld_ext, int Hd, int n_heads, const float* h_att_b,
+                                      float alpha, const int64_t* ctx_idx, int T, int K, float* out, int64_t ld_out,
+                                      float* attn, void* stream) {
+  using namespace cova;
+  COVA_REQUIRE(T >= 0 && K >= 0 && Hd > 0 && n_heads >= 1 && n_heads <= GAT_MAX_HEADS, "cova_gat_multihead_fwd: bad dims");
+  if (T == 0) return COVA_OK;
+  COVA_REQUIRE(ext && h_att_b && out && ctx_idx, "cova_gat_multihead_fwd: null pointer");
+  COVA_REQUIRE(K >= 1 && K <= GAT_KMAX, "cova_gat_multihead_fwd: K=%d outside [1,%d]", K, GAT_KMAX);
+  COVA_REQUIRE(Hd % 4 == 0 && ld_ext % 4 == 0 && ld_ext >= (int64_t)n_heads * (Hd + 2) && ld_out >= (int64_t)n_heads * Hd,
+               "cova_gat_multihead_fwd: Hd and ld_ext must be multiples of 4; ext = [whj_0..whj_H-1 | s_0 t_0 .. | pad]");
+  COVA_REQUIRE(((uintptr_t)ext & 15) == 0, "cova_gat_multihead_fwd: ext must be 16-byte aligned");
+  const int out_vec = (ld_out % 4 == 0) && (((uintptr_t)out & 15) == 0);
+  GatBias bias;
+  for (int h = 0; h < GAT_MAX_HEADS; ++h) bias.b[h] = h < n_heads ? h_att_b[h] : 0.f;
+  const float* st = ext + (size_t)n_heads * Hd;
+  COVA_CUDA_OK(cudaFuncSetAttribute(gat_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GAT_STAGE_BYTES));
+  gat_fwd_kernel<<<dim3(ceil_div(T, GAT_E), n_heads), GAT_THREADS, GAT_STAGE_BYTES, (cudaStream_t)stream>>>(
+      ext, ld_ext, st, st + 1, ld_ext, bias, alpha, ctx_idx, T, K, Hd, out, ld_out, attn, 1, out_vec);
+  COVA_LAUNCH_OK();
+  return COVA_OK;
+}
+
 extern "C" int cova_gat_fwd(const float* whj, int64_t ld_whj, const float* s, const float* t, int64_t ld_st, float att_b,
                             float alpha, const int64_t* ctx_idx, int T, int K, int Hd, float* out, int64_t ld_out,
                             float* attn, void* stream) {
@@ -267,8 +300,10 @@ extern "C" int cova_gat_fwd(const float* whj, int64_t ld_whj, const float* s, co
   COVA_REQUIRE(((uintptr_t)whj & 15) == 0, "cova_gat_fwd: whj must be 16-byte aligned");
   const int out_vec = (ld_out % 4 == 0) && (((uintptr_t)out & 15) == 0);
   COVA_CUDA_OK(cudaFuncSetAttribute(gat_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GAT_STAGE_BYTES));
+  GatBias bias;
+  for (int h = 0; h < GAT_MAX_HEADS; ++h) bias.b[h] = att_b;
   gat_fwd_kernel<<<ceil_div(T, GAT_E), GAT_THREADS, GAT_STAGE_BYTES, (cudaStream_t)stream>>>(
-      whj, ld_whj, s, t, ld_st, att_b, alpha, ctx_idx, T, K, Hd, out, ld_out, attn, 1, out_vec);
+      whj, ld_whj, s, t, ld_st, bias, alpha, ctx_idx, T, K, Hd, out, ld_out, attn, 1, out_vec);
   COVA_LAUNCH_OK();
   return COVA_OK;
 }

@@ -83,6 +83,14 @@ class NativeForward:
             c["add_bn"] = fold_bn(m.bn_additional_feat)
         if m.use_context:
             c["gat"] = [self._gat_cache(h) for h in m.gat_heads()]
+            if len(c["gat"]) > 1:   # all heads: ONE projection GEMM [W_j(0);..;W_j(H-1); s_0;t_0;..] and ONE gather launch
+                Hd = c["gat"][0]["Hd"]
+                rows = [g["ext"][:Hd] for g in c["gat"]] + [g["ext"][Hd:Hd + 2] for g in c["gat"]]
+                ext = torch.cat(rows, 0)
+                pad = (-ext.shape[0]) % 4
+                if pad:
+                    ext = torch.cat((ext, torch.zeros((pad, ext.shape[1]), device=ext.device)), 0)
+                c["gat_mh"] = dict(ext=ext.contiguous(), Hd=Hd, b=[g["b"] for g in c["gat"]], alpha=c["gat"][0]["alpha"])
         dec = m.decoder
         c["dec1"] = (dec[1].weight.detach().float().contiguous(), dec[1].bias.detach().float().contiguous(),
                      *fold_bn(dec[2]))
@@ -90,7 +98,7 @@ class NativeForward:
         if m.engine == "tcgen05":   # split-bf16 copies for the tensor-core GEMMs
             c["dec1_p"] = ops.pack_linear_weight(c["dec1"][0])
             c["dec2_p"] = ops.pack_linear_weight(c["dec2"][0])
-            for g in c.get("gat", []):
+            for g in c.get("gat", []) + ([c["gat_mh"]] if "gat_mh" in c else []):
                 g["ext_p"] = ops.pack_linear_weight(g["ext"])
         self.c, self._key = c, key
 
@@ -168,6 +176,10 @@ class NativeForward:
     def gat_into(self, own, context_indices, out, want_attn=False, heads=None):
         """A6: own [T,n_feat] (strided view ok) -> out [T, hidden] ; returns attn of the (single) head or None."""
         self.prepare()
+        if heads is None and "gat_mh" in self.c:
+            g = self.c["gat_mh"]
+            ext = self._linear(own, g["ext"], g.get("ext_p"))
+            return ops.gat_multihead_fwd(ext, g["Hd"], g["b"], g["alpha"], context_indices, out, want_attn=want_attn)
         attn, col = None, 0
         for g in (self.c["gat"] if heads is None else heads):
             ext = self._linear(own, g["ext"], g.get("ext_p"))

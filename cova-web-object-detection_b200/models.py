@@ -222,6 +222,23 @@ class MultiHeadGAT(nn.Module):
         self.heads = nn.ModuleList(GraphAttentionLayer(in_features, hidden_dim // n_heads) for _ in range(n_heads))
 
     def forward(self, h_i, context_indices, return_attn_wts=False):
+        if h_i.is_cuda and not (torch.is_grad_enabled() and (h_i.requires_grad or any(p.requires_grad for p in self.parameters()))):
+            # inference: one projection GEMM + one gather launch for all heads
+            key = tuple((p.data_ptr(), p._version) for p in self.parameters())
+            if getattr(self, "_native", None) is None or self._native[0] != key:
+                caches = [NativeForward._gat_cache(h) for h in self.heads]
+                Hd = caches[0]["Hd"]
+                ext = torch.cat([g["ext"][:Hd] for g in caches] + [g["ext"][Hd:Hd + 2] for g in caches], 0)
+                pad = (-ext.shape[0]) % 4
+                if pad:
+                    ext = torch.cat((ext, torch.zeros((pad, ext.shape[1]), device=ext.device)), 0)
+                self._native = (key, dict(ext=ext.contiguous(), Hd=Hd, b=[g["b"] for g in caches], alpha=caches[0]["alpha"]))
+            g = self._native[1]
+            h = h_i.float() if h_i.stride(-1) == 1 else h_i.float().contiguous()
+            out = torch.empty((h.shape[0], g["Hd"] * len(self.heads)), dtype=torch.float32, device=h.device)
+            attn = ops.gat_multihead_fwd(ops.linear_fwd(h, g["ext"]), g["Hd"], g["b"], g["alpha"], context_indices, out,
+                                         want_attn=return_attn_wts)
+            return (out, attn.permute(1, 0, 2)) if return_attn_wts else out
         outs = [h(h_i, context_indices, return_attn_wts) for h in self.heads]
         if return_attn_wts:
             return torch.cat([o[0] for o in outs], 1), torch.stack([o[1] for o in outs], 1)

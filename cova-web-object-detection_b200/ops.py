@@ -217,6 +217,21 @@ def gat_fwd(whj, s, t, att_b, alpha, ctx_idx, out, want_attn=False):
     return attn
 
 
+def gat_multihead_fwd(ext, Hd, att_b, alpha, ctx_idx, out, want_attn=False):
+    """All heads in one launch.  ext [T, >= H*(Hd+2)] = [whj_0..whj_{H-1} | s_0 t_0 s_1 t_1 ..]; att_b = list of H floats;
+    out [T, H*Hd] (row stride free).  Returns attention weights [H,T,K] or None."""
+    _cuda(ctx_idx, torch.int64, "context_indices")
+    ctx_idx = ctx_idx.contiguous()
+    T, K = ctx_idx.shape
+    H = len(att_b)
+    assert ext.stride(1) == 1 and out.stride(1) == 1
+    attn = torch.empty((H, T, K), dtype=torch.float32, device=ext.device) if want_attn else None
+    b = (_lib._F * H)(*[float(x) for x in att_b])
+    _call("cova_gat_multihead_fwd", ext.data_ptr(), ext.stride(0), Hd, H, b, float(alpha), ctx_idx.data_ptr(), T, K,
+          out.data_ptr(), out.stride(0), _ptr(attn), _stream())
+    return attn
+
+
 def gat_bwd(grad_out, ext, Hd, att_b, alpha, ctx_idx, attn):
     """Backward of `gat_fwd` for ext = [whj | s | t | pad] ([T, Hd+4]): returns (d_ext [T,Hd+4], d_bias [1])."""
     _cuda(grad_out, torch.float32, "grad_out")

@@ -134,6 +134,12 @@ int cova_gat_fwd(const float* whj, int64_t ld_whj, const float* s, const float* 
                  float alpha, const int64_t* ctx_idx, int T, int K, int Hd, float* out, int64_t ld_out, float* attn,
                  void* stream);
 
+/* Multi-head form (one launch, grid.y = head): ext [T, ld_ext] = [whj_0 .. whj_{H-1} (Hd columns each) |
+ * s_0 t_0 s_1 t_1 .. | pad] as produced by ONE projection GEMM; h_att_b = HOST array of the H attention biases;
+ * out [T, H*Hd] (heads concatenated on dim 1); attn (optional) [H, T, K].                                      */
+int cova_gat_multihead_fwd(const float* ext, int64_t ld_ext, int Hd, int n_heads, const float* h_att_b, float alpha,
+                           const int64_t* ctx_idx, int T, int K, float* out, int64_t ld_out, float* attn, void* stream);
+
 /* ---- A6 backward (A9): gradients of cova_gat_fwd w.r.t. whj, s, t and the bias, given grad_out [T,Hd] and the
  * attention weights saved by the forward.  d_whj / d_t / d_b are accumulated with atomics and must be ZEROED by the
  * caller; d_s is overwritten.  d_s / d_t: element i at [i*ld_dst].                                           */

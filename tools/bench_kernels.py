@@ -52,5 +52,6 @@ for (B, N, K, C, tag) in [(16, 90, 24, 64, "config 2 (B=16, N=90, K=24, C=64)"),
         ext = torch.randn(T, Hd + 4, device=dev)
         cid = ci.to(dev)
         o = torch.empty((T, 992), device=dev)
-        ms = timeit(lambda: ops.gat_fwd(ext[:, :Hd], ext[:, Hd], ext[:, Hd + 1], 0.1, 0.2, cid, o[:, 608:608 + Hd]))
-        report(f"GAT gather {heads} head(s) x {Hd}  {tag}", ms * heads, heads * (T * K * Hd * 4 + T * Hd * 4 + T * K * 8))
+        ext = torch.randn(T, heads * Hd + 4, device=dev)
+        ms = timeit(lambda: ops.gat_multihead_fwd(ext, Hd, [0.1] * heads, 0.2, cid, o[:, 608:]))
+        report(f"GAT gather {heads} head(s) x {Hd} (one launch)  {tag}", ms, heads * (T * K * Hd * 4 + T * Hd * 4 + T * K * 8))
