@@ -56,6 +56,8 @@ SIGNATURES = {
     "cova_abi_version": (_I, []),
     "cova_last_error": (_c.c_char_p, []),
     "cova_device_info": (_I, [_c.POINTER(_I), _c.POINTER(_I)]),
+    "cova_set_knob": (_I, [_I, _I]),
+    "cova_debug_buffer": (_I, [_P, _L]),
     "cova_stem_fwd": (_I, [_P, _I, _I, _I, _I, _P, _P, _P, _I, _P, _P, _I, _P]),
     "cova_conv3x3_bn_act_fwd": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _I, _I, _P, _P, _I, _P]),
     "cova_conv1x1_bn_act_fwd": (_I, [_P, _P, _L, _I, _I, _P, _P, _P, _P, _P, _I, _I, _P, _P, _P]),

@@ -32,6 +32,8 @@ void set_error(const char* fmt, ...);
 
 int sm_count();          // of the current device (cached)
 int max_smem_optin();    // bytes
+int knob(int id, int dflt);                       // cova_set_knob value, or `dflt` when unset (< 0)
+unsigned long long* debug_words(long long need);  // cova_debug_buffer pointer if it holds >= need words, else NULL
 
 __host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
@@ -71,6 +73,17 @@ __device__ __forceinline__ void st_global_v8(void* p, const uint32_t (&v)[8]) {
 }
 __device__ __forceinline__ void ld_global_nc_v8(const void* p, uint32_t (&v)[8]) {
   asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "l"(p));
+}
+
+__device__ __forceinline__ void ld_global_v8(const void* p, uint32_t (&v)[8]) {
+  asm volatile("ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "l"(p));
+}
+__device__ __forceinline__ void ld_global_na_v8(const void* p, uint32_t (&v)[8]) {
+  asm volatile("ld.global.L1::no_allocate.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
                : "l"(p));
 }

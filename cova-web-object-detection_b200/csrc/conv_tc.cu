@@ -79,7 +79,23 @@ struct ConvTcParams {
   const __nv_bfloat16* res_lo;
   void* y0;
   void* y1;
+  int pf_tiles;       // TMA producer: L2-prefetch the halo boxes of the tile this many iterations ahead (0 = off)
+  int res_load;       // residual loads: 0 = ld.global.nc, 1 = ld.global, 2 = ld.global.L1::no_allocate (default: the
+                      // one-sector-per-line access pattern thrashes L1 line allocation; measured -13 % cycles)
+  int res_pf_tiles;   // epilogue: L2-prefetch the residual rows this many iterations ahead (0 = off; 1 is the register prefetch)
+  unsigned long long* dbg;   // optional per-CTA wait-cycle counters (cova_debug_buffer)
 };
+
+// mbarrier wait that adds the cycles spent to `acc` when instrumentation is on
+__device__ __forceinline__ void mbar_wait_t(uint64_t* bar, uint32_t parity, bool timed, unsigned long long& acc) {
+  if (timed) {
+    const long long t0 = clock64();
+    ptx::mbar_wait(bar, parity);
+    acc += (unsigned long long)(clock64() - t0);
+  } else {
+    ptx::mbar_wait(bar, parity);
+  }
+}
 
 template <bool SPLIT, int OUT_DTYPE>
 __global__ void __launch_bounds__(CT_THREADS, 1)
@@ -95,6 +111,9 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_cons
   ConvTcTail& tail = *reinterpret_cast<ConvTcTail*>(smem + Cfg::W_BYTES + Cfg::NSTAGE * Cfg::STAGE_BYTES);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool timed = p.dbg != nullptr;
+  const long long t_start = timed ? clock64() : 0;
+  unsigned long long wc0 = 0, wc1 = 0;   // wait-cycle counters of this warp's role
 
   if (threadIdx.x < CT_C) {
     tail.scale[threadIdx.x] = p.bn_scale[threadIdx.x];
@@ -144,8 +163,16 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_cons
       const int b = tile / (p.tiles_h * p.tiles_w);
       const int th = (tile / p.tiles_w) % p.tiles_h, tw = tile % p.tiles_w;
       const int h0 = th * CT_TH, w0 = tw * CT_TW;
+      const int pft = tile + p.pf_tiles * (int)gridDim.x;
+      if (p.pf_tiles > 0 && pft < p.n_tiles && ptx::elect_one()) {   // warm L2 for a later iteration's halo boxes
+        const int pb = pft / (p.tiles_h * p.tiles_w);
+        const int ph0 = ((pft / p.tiles_w) % p.tiles_h) * CT_TH, pw0 = (pft % p.tiles_w) * CT_TW;
+        ptx::tma_prefetch_4d(&tm_x_hi, 0, pw0 - 1, ph0 - 1, pb);
+        if (SPLIT) ptx::tma_prefetch_4d(&tm_x_lo, 0, pw0 - 1, ph0 - 1, pb);
+      }
+      __syncwarp();
       for (int pl = 0; pl < Cfg::NPLANE; ++pl) {
-        ptx::mbar_wait(&tail.empty[stage], phase ^ 1);
+        mbar_wait_t(&tail.empty[stage], phase ^ 1, timed, wc0);
         if (ptx::elect_one()) {
           ptx::mbar_arrive_expect_tx(&tail.full[stage], CT_PATCH_BYTES);
           ptx::tma_load_4d(sm_a + stage * Cfg::STAGE_BYTES, pl == 0 ? &tm_x_hi : &tm_x_lo, &tail.full[stage], 0, w0 - 1,
@@ -155,6 +182,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_cons
         if (++stage == Cfg::NSTAGE) { stage = 0; phase ^= 1; }
       }
     }
+    if (timed && lane == 0) atomicAdd(p.dbg + blockIdx.x * 8 + 2, wc0);
   } else if (warp == 1) {
     // ======================= MMA issuer (warp converged; one elected lane issues) =======================
     // Descriptors differ only in their 14-bit start-address field, so each MMA costs two 32-bit adds on
@@ -168,11 +196,11 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_cons
     uint32_t stage = 0, phase = 0, it = 0;
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
       const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
-      ptx::mbar_wait(&tail.tmem_empty[acc], acc_phase ^ 1);
+      mbar_wait_t(&tail.tmem_empty[acc], acc_phase ^ 1, timed, wc1);
       ptx::tc_fence_after();
       const uint32_t d_tmem = tmem_base + acc * Cfg::ACC_COLS;
       for (int pl = 0; pl < Cfg::NPLANE; ++pl) {   // pl 0: A = hi plane x [Whi; Wlo]; pl 1: A = lo plane x Whi
-        ptx::mbar_wait(&tail.full[stage], phase);
+        mbar_wait_t(&tail.full[stage], phase, timed, wc0);
         ptx::tc_fence_after();
         if (ptx::elect_one()) {
           uint64_t da_s = da0 + ((stage * Cfg::STAGE_BYTES) >> 4);
@@ -193,6 +221,11 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_cons
         __syncwarp();
         if (++stage == Cfg::NSTAGE) { stage = 0; phase ^= 1; }
       }
+    }
+    if (timed && lane == 0) {
+      atomicAdd(p.dbg + blockIdx.x * 8 + 0, wc0);
+      atomicAdd(p.dbg + blockIdx.x * 8 + 1, wc1);
+      atomicAdd(p.dbg + blockIdx.x * 8 + 5, (unsigned long long)it);
     }
   } else {
     // ======================= epilogue warps (TMEM lane group = warp % 4; channel half = (warp-2)/4) ==========
@@ -215,15 +248,40 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_cons
       bool ok;
       const size_t px_off = tile_pix(tile, ok);
       if (has_res && tile < p.n_tiles && ok) {
+        if (p.res_load == 1) {
 #pragma unroll
-        for (int j = 0; j < 2; ++j) ld_global_nc_v8(p.res_hi + px_off + j * 16, rh_n[j]);
-        if (SPLIT) {
+          for (int j = 0; j < 2; ++j) ld_global_v8(p.res_hi + px_off + j * 16, rh_n[j]);
+          if (SPLIT) {
 #pragma unroll
-          for (int j = 0; j < 2; ++j) ld_global_nc_v8(p.res_lo + px_off + j * 16, rl_n[j]);
+            for (int j = 0; j < 2; ++j) ld_global_v8(p.res_lo + px_off + j * 16, rl_n[j]);
+          }
+        } else if (p.res_load == 2) {
+#pragma unroll
+          for (int j = 0; j < 2; ++j) ld_global_na_v8(p.res_hi + px_off + j * 16, rh_n[j]);
+          if (SPLIT) {
+#pragma unroll
+            for (int j = 0; j < 2; ++j) ld_global_na_v8(p.res_lo + px_off + j * 16, rl_n[j]);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 2; ++j) ld_global_nc_v8(p.res_hi + px_off + j * 16, rh_n[j]);
+          if (SPLIT) {
+#pragma unroll
+            for (int j = 0; j < 2; ++j) ld_global_nc_v8(p.res_lo + px_off + j * 16, rl_n[j]);
+          }
         }
       }
     };
+    auto prefetch_res = [&](int tile) {   // L2 only: one 64-byte half row per thread and plane
+      bool ok;
+      const size_t px_off = tile_pix(tile, ok);
+      if (tile < p.n_tiles && ok) {
+        ptx::prefetch_l2(p.res_hi + px_off);
+        if (SPLIT) ptx::prefetch_l2(p.res_lo + px_off);
+      }
+    };
     load_res(blockIdx.x);
+    const bool res_pf = has_res && p.res_pf_tiles > 1;
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
       const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
@@ -234,8 +292,9 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_cons
 #pragma unroll
         for (int e = 0; e < 8; ++e) { rh[j][e] = rh_n[j][e]; rl[j][e] = rl_n[j][e]; }
       load_res(tile + gridDim.x);
+      if (res_pf) prefetch_res(tile + p.res_pf_tiles * (int)gridDim.x);
 
-      ptx::mbar_wait(&tail.tmem_full[acc], acc_phase);
+      mbar_wait_t(&tail.tmem_full[acc], acc_phase, timed && warp == 2, wc0);
       ptx::tc_fence_after();
       uint32_t v[2][16];
       const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + acc * Cfg::ACC_COLS + ch0;
@@ -306,8 +365,10 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_cons
     }
   }
 
+  if (timed && warp == 2 && lane == 0) atomicAdd(p.dbg + blockIdx.x * 8 + 3, wc0);
   ptx::tc_fence_before();
   __syncthreads();
+  if (timed && threadIdx.x == 0) atomicAdd(p.dbg + blockIdx.x * 8 + 4, (unsigned long long)(clock64() - t_start));
   if (warp == 1) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
@@ -356,6 +417,10 @@ int conv3x3_tc(const void* x_hi, const void* x_lo, int split, int B, int H, int 
   p.res_hi = (const __nv_bfloat16*)res_hi;
   p.res_lo = (const __nv_bfloat16*)res_lo;
   p.y0 = y0; p.y1 = y1;
+  p.pf_tiles = knob(COVA_KNOB_CONV_L2_PREFETCH, 0);
+  p.res_pf_tiles = knob(COVA_KNOB_CONV_RES_PREFETCH, 1);
+  p.res_load = knob(COVA_KNOB_CONV_RES_LOAD, 2);
+  p.dbg = debug_words(8LL * sm_count());
 #define DISPATCH(SP)                                                                               \
   switch (out_dtype) {                                                                             \
     case COVA_F32: return launch_conv_tc<SP, COVA_F32>(tx_hi, tx_lo, tw_hi, tw_lo, p, st);         \

@@ -40,7 +40,7 @@ constexpr int SX_ND = 16;                  // tile-row completion barriers
 constexpr int SX_EPI_WARPS = 16;            // 4 per TMEM lane group, 16 output channels each
 constexpr int SX_EPI_THREADS = SX_EPI_WARPS * 32;
 constexpr int SX_CH = 64 / (SX_EPI_WARPS / 4);   // channels per epilogue warp
-constexpr int SX_THREADS = 32 * (1 + SX_EPI_WARPS + 4);   // warp 0 MMA, epilogue warps, 4 converter warps
+constexpr int sx_threads(int ncv) { return 32 * (1 + SX_EPI_WARPS + ncv); }   // warp 0 MMA, epilogue warps, ncv converter warps
 
 
 template <bool SPLIT>
@@ -65,6 +65,8 @@ struct StemTcParams {
   const float* bn_shift;
   void* out0;
   void* out1;
+  unsigned long long* dbg;                 // optional wait-cycle counters (cova_debug_buffer), 8 words per CTA
+  int pf_rows;                             // converter warps L2-prefetch the image row they will load this many turns ahead
 };
 
 __device__ __forceinline__ uint64_t desc_noswz(uint32_t addr, uint32_t lbo, uint32_t sbo) {
@@ -76,8 +78,8 @@ __device__ __forceinline__ uint64_t desc_noswz(uint32_t addr, uint32_t lbo, uint
   return d;
 }
 
-template <bool SPLIT, int OUT_DTYPE, bool U8>
-__global__ void __launch_bounds__(SX_THREADS, 1)
+template <bool SPLIT, int OUT_DTYPE, bool U8, int NCV>
+__global__ void __launch_bounds__(sx_threads(NCV), 1)
 stem_tc_kernel(const StemTcParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   StemTcSmem<SPLIT>& sm = *reinterpret_cast<StemTcSmem<SPLIT>*>(smem_raw);
@@ -137,15 +139,21 @@ stem_tc_kernel(const StemTcParams p) {
     const uint64_t da0 = desc_noswz(ptx::smem_u32(&sm.ring[0][0][0]), 16, 128);
     const uint64_t db0 = desc_noswz(ptx::smem_u32(&sm.w[0]), SX_W_CHUNK, 128);
     uint32_t t = 0;
+    const bool timed = p.dbg != nullptr;
+    const long long t_start = timed ? clock64() : 0;
+    long long wt0 = 0, wt1 = 0;
     for (int strip = 0; strip < n_strips; ++strip) {
       for (int i = 0; i < n_conv; ++i, ++t) {
         const uint32_t g0 = (uint32_t)strip * NQ + 2 * i;
+        long long c0 = timed ? clock64() : 0;
         for (int r = (i == 0 ? 0 : 5); r < 7; ++r) {         // rows that are new for this conv row
           const uint32_t g = g0 + r;
           ptx::mbar_wait(&sm.in_full[g % SX_R], (g / SX_R) & 1);
         }
         const uint32_t acc = t & 1;
+        if (timed) { const long long c1 = clock64(); wt0 += c1 - c0; c0 = c1; }
         ptx::mbar_wait(&sm.tmem_empty[acc], ((t >> 1) & 1) ^ 1);
+        if (timed) wt1 += clock64() - c0;
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * ACC_COLS;
         if (ptx::elect_one()) {
@@ -165,6 +173,13 @@ stem_tc_kernel(const StemTcParams p) {
         }
         __syncwarp();
       }
+    }
+    if (timed && lane == 0) {
+      unsigned long long* d = p.dbg + (size_t)blockIdx.x * 8;
+      atomicAdd(d + 0, (unsigned long long)wt0);
+      atomicAdd(d + 1, (unsigned long long)wt1);
+      atomicAdd(d + 4, (unsigned long long)(clock64() - t_start));
+      atomicAdd(d + 5, (unsigned long long)t);
     }
   } else if (warp <= SX_EPI_WARPS) {
     // ======================= epilogue: BN + ReLU + 3x3/s2 max-pool =======================
@@ -274,11 +289,11 @@ stem_tc_kernel(const StemTcParams p) {
     }
   } else {
     // ======================= converters: NCHW fp32 rows -> ring of 4-channel bf16 pixels =======================
-    const int cw = warp - 1 - SX_EPI_WARPS;         // this warp owns input rows g with g % 4 == cw
+    const int cw = warp - 1 - SX_EPI_WARPS;         // this warp owns input rows g with g % NCV == cw
     const size_t plane = (size_t)p.H * p.W;
     const size_t img_b = (size_t)b * 3 * plane;
     const uint32_t n_rows_total = (uint32_t)n_strips * NQ;
-    for (uint32_t g = cw; g < n_rows_total; g += 4) {
+    for (uint32_t g = cw; g < n_rows_total; g += NCV) {
       const int strip = g / NQ, q = g % NQ;
       const int y = y_first + q;
       const int x0 = 2 * strip * SX_TM - 3;
@@ -290,6 +305,20 @@ stem_tc_kernel(const StemTcParams p) {
       }
       const bool row_ok = y >= 0 && y < p.H;
       unsigned char* dst_hi = sm.ring[0][g % SX_R];
+      if (p.pf_rows > 0) {   // warm L2 for a later row of this warp: one 128-byte line per lane (3 channels x <= 10 lines)
+        const uint32_t gn = g + (uint32_t)(NCV * p.pf_rows);
+        if (gn < n_rows_total) {
+          const int yn = y_first + (int)(gn % NQ);
+          const int xn = 2 * (int)(gn / NQ) * SX_TM - 3;
+          const int esz = U8 ? 1 : 4, per_line = 128 / esz;
+          const int c = lane / 10, j = lane % 10;
+          const int x = xn + j * per_line;
+          if (c < 3 && yn >= 0 && yn < p.H && x < p.W && x + per_line > 0 && j * per_line < SX_NPX + per_line) {
+            const size_t idx = img_b + c * plane + (size_t)yn * p.W + (x < 0 ? 0 : x);
+            ptx::prefetch_l2(reinterpret_cast<const unsigned char*>(p.img) + idx * esz);
+          }
+        }
+      }
       if (U8 && (p.W & 3) == 0) {
         // uint8 fast path: x0 - 1 is a multiple of 4, so the row segment is 67 aligned 4-pixel words per channel
         // (9 word loads per lane instead of 27 byte loads); the value -> (hi, lo) bf16 split comes from the LUT.
@@ -371,14 +400,19 @@ __global__ void pack_stem_weight_kernel(const float* __restrict__ w, __nv_bfloat
   out[((chunk * 2 + 1) * 64 + co) * 8 + e] = l;
 }
 
-template <bool SPLIT, int OUT_DTYPE, bool U8>
-static int launch_stem_tc(const StemTcParams& p, int grid, cudaStream_t st) {
-  auto kern = stem_tc_kernel<SPLIT, OUT_DTYPE, U8>;
+template <bool SPLIT, int OUT_DTYPE, bool U8, int NCV>
+static int launch_stem_tc_n(const StemTcParams& p, int grid, cudaStream_t st) {
+  auto kern = stem_tc_kernel<SPLIT, OUT_DTYPE, U8, NCV>;
   const int smem = (int)sizeof(StemTcSmem<SPLIT>) + 128;
   COVA_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  kern<<<grid, SX_THREADS, smem, st>>>(p);
+  kern<<<grid, sx_threads(NCV), smem, st>>>(p);
   COVA_LAUNCH_OK();
   return COVA_OK;
+}
+template <bool SPLIT, int OUT_DTYPE, bool U8>
+static int launch_stem_tc(const StemTcParams& p, int grid, cudaStream_t st) {
+  if (knob(COVA_KNOB_STEM_CONVERTERS, 8) >= 8) return launch_stem_tc_n<SPLIT, OUT_DTYPE, U8, 8>(p, grid, st);
+  return launch_stem_tc_n<SPLIT, OUT_DTYPE, U8, 4>(p, grid, st);
 }
 
 int stem_tc(const void* images, int img_u8, int B, int H, int W, const void* w_packed, const float* bn_scale,
@@ -398,6 +432,8 @@ int stem_tc(const void* images, int img_u8, int B, int H, int W, const void* w_p
   p.w_packed = (const unsigned char*)w_packed;
   p.bn_scale = bn_scale; p.bn_shift = bn_shift;
   p.out0 = out0; p.out1 = out1;
+  p.pf_rows = knob(COVA_KNOB_STEM_L2_PREFETCH, 1);
+  p.dbg = debug_words(8LL * B * p.bands_per_page);
   const int grid = B * p.bands_per_page;
   const bool split = out_dtype != COVA_BF16;   // bf16 output <=> bf16 mode; fp32 / split outputs use the 3-product mode
 #define GO(SP, DT) (img_u8 ? launch_stem_tc<SP, DT, true>(p, grid, st) : launch_stem_tc<SP, DT, false>(p, grid, st))

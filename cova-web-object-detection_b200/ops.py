@@ -58,6 +58,19 @@ def device_info():
     return sm.value, smem.value
 
 
+KNOBS = {"conv_l2_prefetch": 0, "conv_res_prefetch": 1, "stem_l2_prefetch": 2, "stem_converters": 5, "conv_res_load": 6}
+
+
+def set_knob(name, value):
+    """Tuning knob of the library (include/cova_b200.h COVA_KNOB_*); value < 0 restores the default."""
+    _lib.check(_lib.lib().cova_set_knob(KNOBS[name], int(value)), "cova_set_knob")
+
+
+def debug_buffer(t):
+    """Attach (or detach with None) a CUDA int64 tensor the instrumented kernels add their wait-cycle counters to."""
+    _lib.check(_lib.lib().cova_debug_buffer(_ptr(t), 0 if t is None else t.numel()), "cova_debug_buffer")
+
+
 def stem_fwd(images, w, bn_scale, bn_shift, out_dtype=F32, engine=ENGINE_SIMT):
     """conv7x7 s2 p3 + BN + ReLU + maxpool3x3 s2 p1; images [B,3,H,W] NCHW, fp32 in [0,1] or uint8 raw pixels
     (converted as v/255 in the kernel) -> Planes [B,H/4,W/4,64]."""

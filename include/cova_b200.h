@@ -40,6 +40,22 @@ const char* cova_last_error(void);
 /* SM count / max dynamic smem of the current device (host query; used to size persistent grids). */
 int cova_device_info(int* sm_count, int* max_smem_optin);
 
+/* ---- Tuning / diagnostics (process-global, host side; not needed for correct results).
+ * cova_set_knob: value < 0 restores the built-in default.
+ *   COVA_KNOB_CONV_L2_PREFETCH   3x3 conv: tiles ahead for which the TMA producer issues an L2 prefetch of the halo
+ *                                boxes (0 = off)
+ *   COVA_KNOB_CONV_RES_PREFETCH  3x3 conv: tiles ahead for which the epilogue L2-prefetches the residual rows
+ *   COVA_KNOB_STEM_L2_PREFETCH   stem: image rows ahead to L2-prefetch (0 = off)
+ *   COVA_KNOB_STEM_CONVERTERS    stem: converter warps per CTA (4 or 8)
+ *   COVA_KNOB_CONV_RES_LOAD      3x3 conv residual loads: 0 = ld.global.nc, 1 = ld.global, 2 = L1::no_allocate
+ * cova_debug_buffer: a caller-owned device array of uint64 words; kernels that support it (the 3x3 tensor-core conv:
+ *   8 words per CTA = cycles the MMA issuer waited for operands / for a free accumulator, the TMA producer for a free
+ *   ring slot, epilogue warp 2 for a finished accumulator, CTA total, tiles) add their counters.  NULL disables. */
+enum { COVA_KNOB_CONV_L2_PREFETCH = 0, COVA_KNOB_CONV_RES_PREFETCH = 1, COVA_KNOB_STEM_L2_PREFETCH = 2,
+       COVA_KNOB_STEM_CONVERTERS = 5, COVA_KNOB_CONV_RES_LOAD = 6, COVA_KNOB_COUNT = 8 };
+int cova_set_knob(int id, int value);
+int cova_debug_buffer(void* dev_words, int64_t n_words);
+
 /* ---- A2: backbone stem.  Replaces `convnet[0:4]` = conv1 7x7 s2 p3 (no bias) -> bn1 -> relu ->
  * maxpool 3x3 s2 p1 (`models.py:49-51`, applied `models.py:125`).  ONE fused kernel: the
  * [B,64,H/2,W/2] conv output never reaches HBM.
