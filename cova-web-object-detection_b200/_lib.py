@@ -49,7 +49,7 @@ def build(force=False, verbose=False):
 
 
 _c = ctypes
-_P, _I, _L, _F = _c.c_void_p, _c.c_int, _c.c_int64, _c.c_float
+_P, _I, _L, _F, _D = _c.c_void_p, _c.c_int, _c.c_int64, _c.c_float, _c.c_double
 
 # name -> (restype, argtypes); must list every symbol include/cova_b200.h declares
 SIGNATURES = {
@@ -72,6 +72,10 @@ SIGNATURES = {
     "cova_gat_fwd": (_I, [_P, _L, _P, _P, _L, _F, _F, _P, _I, _I, _I, _P, _L, _P, _P]),
     "cova_gat_multihead_fwd": (_I, [_P, _L, _I, _I, _c.POINTER(_F), _F, _P, _I, _I, _P, _L, _P, _P]),
     "cova_gat_bwd": (_I, [_P, _L, _P, _L, _P, _P, _L, _F, _F, _P, _P, _I, _I, _I, _P, _L, _P, _P, _L, _P, _P]),
+    "cova_ce_sum_fwd_bwd": (_I, [_P, _L, _P, _I, _I, _L, _P, _P, _P, _L, _P, _P]),
+    "cova_adam_step": (_I, [_P, _P, _P, _P, _L, _D, _D, _D, _D, _D, _I, _D, _P]),
+    "cova_topk_hits": (_I, [_P, _L, _P, _P, _I, _I, _I, _P, _P]),
+    "cova_build_batch": (_I, [_P, _I, _I, _I, _P, _P, _P, _P]),
 }
 
 _lib = None

@@ -32,7 +32,7 @@ class NativeForward:
     # ------------------------------------------------------------------ caches
     def _state_key(self):
         m = self.m
-        return (m.engine, m.precision) + tuple((t.data_ptr(), t._version) for t in
+        return (m.engine, m.precision, ops.param_generation) + tuple((t.data_ptr(), t._version) for t in
                                                list(m.parameters()) + list(m.buffers()))
 
     def prepare(self):

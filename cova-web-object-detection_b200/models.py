@@ -172,7 +172,7 @@ class GraphAttentionLayer(nn.Module):
             raise RuntimeError("cova_b200: GraphAttentionLayer needs CUDA tensors (no CPU path)")
         if torch.is_grad_enabled() and (h_i.requires_grad or any(p.requires_grad for p in self.parameters())):
             return self._forward_composite(h_i, context_indices, return_attn_wts)
-        key = tuple((p.data_ptr(), p._version) for p in self.parameters())
+        key = (ops.param_generation,) + tuple((p.data_ptr(), p._version) for p in self.parameters())
         if self._native is None or self._native[0] != key:
             self._native = (key, NativeForward._gat_cache(self))
         g = self._native[1]
@@ -224,7 +224,7 @@ class MultiHeadGAT(nn.Module):
     def forward(self, h_i, context_indices, return_attn_wts=False):
         if h_i.is_cuda and not (torch.is_grad_enabled() and (h_i.requires_grad or any(p.requires_grad for p in self.parameters()))):
             # inference: one projection GEMM + one gather launch for all heads
-            key = tuple((p.data_ptr(), p._version) for p in self.parameters())
+            key = (ops.param_generation,) + tuple((p.data_ptr(), p._version) for p in self.parameters())
             if getattr(self, "_native", None) is None or self._native[0] != key:
                 caches = [NativeForward._gat_cache(h) for h in self.heads]
                 Hd = caches[0]["Hd"]

@@ -258,3 +258,73 @@ def gat_bwd(grad_out, ext, Hd, att_b, alpha, ctx_idx, attn):
           ext[:, Hd + 1].data_ptr(), ld, float(att_b), float(alpha), ctx_idx.data_ptr(), attn.data_ptr(), T, K, Hd,
           d_ext.data_ptr(), ld, d_ext[:, Hd].data_ptr(), d_ext[:, Hd + 1].data_ptr(), ld, d_b.data_ptr(), _stream())
     return d_ext, d_b
+
+
+# ------------------------------------------------------------------ callers either side of the forward (A9, N1-N3)
+# bumped by every native in-place parameter update (the Adam kernel writes through raw pointers, which does not touch
+# Tensor._version): engine.NativeForward keys its derived weight caches on it
+param_generation = 0
+
+
+def ce_sum_fwd_bwd(logits, labels, want_grad=True, want_correct=False, ignore_index=-100):
+    """CrossEntropyLoss(reduction="sum") forward + d loss/d logits (+ number of argmax hits) in one launch.
+    Returns (loss [1] fp32, dlogits [T,C] or None, n_correct [1] int32 or None)."""
+    _cuda(logits, torch.float32, "logits")
+    _cuda(labels, torch.int64, "labels")
+    if logits.stride(1) != 1:
+        logits = logits.contiguous()
+    labels = labels.contiguous()
+    T, C = logits.shape
+    dev = logits.device
+    ws = torch.empty(1, dtype=torch.float64, device=dev)
+    loss = torch.empty(1, dtype=torch.float32, device=dev)
+    dl = torch.empty((T, C), dtype=torch.float32, device=dev) if want_grad else None
+    nc = torch.empty(1, dtype=torch.int32, device=dev) if want_correct else None
+    _call("cova_ce_sum_fwd_bwd", logits.data_ptr(), logits.stride(0) if T else C, labels.data_ptr(), T, C,
+          int(ignore_index), ws.data_ptr(), loss.data_ptr(), _ptr(dl), C, _ptr(nc), _stream())
+    return loss, dl, nc
+
+
+def adam_step(param, grad, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, weight_decay, step, grad_scale=1.0):
+    """One torch.optim.Adam step over flat fp32 buffers (in place)."""
+    global param_generation
+    for t, n in ((param, "param"), (grad, "grad"), (exp_avg, "exp_avg"), (exp_avg_sq, "exp_avg_sq")):
+        _cuda(t, torch.float32, n)
+        assert t.is_contiguous() and t.numel() == param.numel()
+    _call("cova_adam_step", param.data_ptr(), grad.data_ptr(), exp_avg.data_ptr(), exp_avg_sq.data_ptr(), param.numel(),
+          float(lr), float(beta1), float(beta2), float(eps), float(weight_decay), int(step), float(grad_scale), _stream())
+    param_generation += 1
+
+
+def topk_hits(logits, labels, page_offsets, k=1):
+    """evaluate_model's top-k test for every (page, class): int32 [B, C] (column 0 unused; -1 = class absent)."""
+    _cuda(logits, torch.float32, "logits")
+    _cuda(labels, torch.int64, "labels")
+    _cuda(page_offsets, torch.int32, "page_offsets")
+    if logits.stride(1) != 1:
+        logits = logits.contiguous()
+    B, C = page_offsets.numel() - 1, logits.shape[1]
+    hits = torch.zeros((B, C), dtype=torch.int32, device=logits.device)
+    _call("cova_topk_hits", logits.data_ptr(), logits.stride(0) if logits.shape[0] else C, labels.contiguous().data_ptr(),
+          page_offsets.contiguous().data_ptr(), B, C, int(k), hits.data_ptr(), _stream())
+    return hits
+
+
+def build_batch(page_offsets, context_size, boxes_xywh=None):
+    """Device-side batch assembly from per-page row offsets (int32 [B+1]): returns (bboxes [T,5] or None,
+    context_indices int64 [T, 2*context_size])."""
+    _cuda(page_offsets, torch.int32, "page_offsets")
+    page_offsets = page_offsets.contiguous()
+    B = page_offsets.numel() - 1
+    if boxes_xywh is not None:
+        _cuda(boxes_xywh, torch.float32, "boxes_xywh")
+        boxes_xywh = boxes_xywh.contiguous()
+        T = boxes_xywh.shape[0]
+    else:
+        T = int(page_offsets[-1].item())
+    dev = page_offsets.device
+    ctx = torch.empty((T, 2 * context_size), dtype=torch.int64, device=dev)
+    bb = torch.empty((T, 5), dtype=torch.float32, device=dev) if boxes_xywh is not None else None
+    _call("cova_build_batch", page_offsets.data_ptr(), B, T, int(context_size), _ptr(boxes_xywh), _ptr(bb),
+          ctx.data_ptr() if context_size > 0 else 0, _stream())
+    return bb, ctx

@@ -163,6 +163,42 @@ int cova_gat_bwd(const float* grad_out, int64_t ld_go, const float* whj, int64_t
                  int64_t ld_st, float att_b, float alpha, const int64_t* ctx_idx, const float* attn, int T, int K, int Hd,
                  float* d_whj, int64_t ld_dw, float* d_s, float* d_t, int64_t ld_dst, float* d_b, void* stream);
 
+/* ================= callers either side of the forward ================= */
+
+/* ---- A9 / N2: `nn.CrossEntropyLoss(reduction="sum")` (`main.py:139`, `train.py:56`) forward AND gradient w.r.t. the
+ * logits in one pass, plus the `(output.argmax(1) == labels).sum()` of `train.py:53-54`.
+ *   logits [T, n_cls] fp32 (row stride ld), labels int64 [T]; rows whose label equals ignore_index (torch default -100)
+ *   or lies outside [0, n_cls) contribute neither loss nor gradient.
+ *   ws_acc : caller-owned scratch, one double (device); loss: [1] fp32, overwritten
+ *   dlogits: optional [T, n_cls] (row stride ld_d) = softmax(logits) - onehot(labels)  (d loss / d logits)
+ *   n_correct: optional [1] int32, overwritten.                                                          */
+int cova_ce_sum_fwd_bwd(const float* logits, int64_t ld, const int64_t* labels, int T, int n_cls, int64_t ignore_index,
+                        double* ws_acc, float* loss, float* dlogits, int64_t ld_d, int* n_correct, void* stream);
+
+/* ---- A9 / N2: one `torch.optim.Adam` step (amsgrad off; L2 weight decay folded into the gradient, `main.py:133-135`,
+ * `train.py:60`) over ONE flat fp32 bucket of n elements - the bucket the NCCL gradient all-reduce uses, so a whole
+ * model steps in one launch.  grad is multiplied by grad_scale first (1.0; 1/world for mean-reduced data parallelism).
+ * Hyper-parameters are doubles (torch keeps them as Python floats and derives 1-beta, the bias corrections and
+ * lr/bc1 in double).  `step` is the 1-based step count AFTER the increment, as in torch.                                     */
+int cova_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, double lr, double beta1,
+                   double beta2, double eps, double weight_decay, int step, double grad_scale, void* stream);
+
+/* ---- N3: the top-k test of `evaluate_model` (`train.py:131-154`) for every page and class in one launch.
+ *   page_offsets int32 [B+1]: rows of page b are [page_offsets[b], page_offsets[b+1]) (pages are contiguous row ranges,
+ *   `datasets.py:170-181`).  hits int32 [B, n_cls]: column c >= 1 = 1 if the first row labelled c is among the k rows
+ *   with the largest logit[:, c] of its page (ties ranked as a stable ascending argsort), 0 if not, -1 if the page has
+ *   no row labelled c (the reference raises there); column 0 is not written.                             */
+int cova_topk_hits(const float* logits, int64_t ld, const int64_t* labels, const int* page_offsets, int B, int n_cls,
+                   int k, int* hits, void* stream);
+
+/* ---- N1: batch assembly on the device from per-page box counts: the +-context_size pre-order window of
+ * `WebDataset.__getitem__` (`datasets.py:117-128`: left neighbours, then right neighbours, right-padded with -1) made
+ * batch-global as `custom_collate_fn` does (`datasets.py:175`), and - when raw [x,y,w,h] boxes are given - the collated
+ * box rows [page, x1, y1, x1+w, y1+h] (`datasets.py:114-115`, `:172-174`).
+ *   context_indices int64 [T, 2*context_size]; boxes_xywh [T,4] / bboxes [T,5] both NULL or both set.      */
+int cova_build_batch(const int* page_offsets, int B, int T, int context_size, const float* boxes_xywh, float* bboxes,
+                     int64_t* context_indices, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

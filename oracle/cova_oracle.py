@@ -289,3 +289,72 @@ def cova_forward(sd, images, bboxes, additional_feats, context_indices, roi_outp
     if return_intermediates:
         return dict(fm=fm, visual=vis, own=own, ctx=ctx, logits=logits)
     return logits
+
+
+# ----------------------------------------------------------------------------- callers either side of the forward
+def ce_sum(logits, labels, ignore_index=-100):
+    """`nn.CrossEntropyLoss(reduction="sum")` (`/root/reference/main.py:139`, applied `train.py:56`) and the arg-max
+    hit count of `train.py:53-54`.  Returns (loss, d loss / d logits, n_correct)."""
+    x = np.asarray(logits, np.float64)
+    y = np.asarray(labels, np.int64)
+    live = (y != ignore_index) & (y >= 0) & (y < x.shape[1])
+    m = x.max(1, keepdims=True)
+    lse = m[:, 0] + np.log(np.exp(x - m).sum(1))
+    yy = np.where(live, y, 0)
+    li = (lse - x[np.arange(len(y)), yy]) * live
+    d = np.exp(x - lse[:, None])
+    d[np.arange(len(y)), yy] -= 1.0
+    d *= live[:, None]
+    n_correct = int(((x.argmax(1) == y) & live).sum())
+    return np.float32(li.sum()), d.astype(np.float32), n_correct
+
+
+def adam_step(p, g, m, v, lr, beta1, beta2, eps, weight_decay, step):
+    """One `torch.optim.Adam` step (`main.py:133-135`, `train.py:60`; amsgrad off) in fp32, the single-tensor
+    formulation of torch/optim/adam.py: L2 decay folded into the gradient, lerp first moment, bias corrections as
+    Python floats.  Returns new (p, m, v)."""
+    f = np.float32
+    p, g, m, v = (np.asarray(a, np.float32) for a in (p, g, m, v))
+    g = g + f(weight_decay) * p
+    m = m + f(1.0 - beta1) * (g - m)
+    v = f(beta2) * v + f(1.0 - beta2) * g * g
+    bc1, bc2 = 1.0 - beta1 ** step, 1.0 - beta2 ** step
+    denom = np.sqrt(v) / f(np.sqrt(bc2)) + f(eps)
+    p = p - f(lr / bc1) * (m / denom)
+    return p.astype(np.float32), m.astype(np.float32), v.astype(np.float32)
+
+
+def topk_hits(logits, labels, page_offsets, k=1):
+    """The per-image / per-class loop of `evaluate_model` (`train.py:131-154`): for class c >= 1 the first row of the
+    page labelled c (`:146`) must be among `argsort(output_img, dim=0)[n-k:]` (`:141-143`; taken as a stable ascending
+    sort).  int32 [B, C]; column 0 unused, -1 where the page has no row labelled c (the reference raises there)."""
+    logits, labels = np.asarray(logits, np.float32), np.asarray(labels)
+    B, C = len(page_offsets) - 1, logits.shape[1]
+    hits = np.zeros((B, C), np.int32)
+    for b in range(B):
+        r0, r1 = int(page_offsets[b]), int(page_offsets[b + 1])
+        out, lab = logits[r0:r1], labels[r0:r1]
+        top = np.argsort(out, axis=0, kind="stable")[max(out.shape[0] - k, 0):]
+        for c in range(1, C):
+            rows = np.nonzero(lab == c)[0]
+            hits[b, c] = -1 if len(rows) == 0 else int(rows[0] in top[:, c])
+    return hits
+
+
+def build_batch(boxes_per_page, context_size, boxes_xywh=None):
+    """`WebDataset.__getitem__`'s context window (`datasets.py:117-128`) and `custom_collate_fn`'s batch-index column /
+    batch-global ids (`datasets.py:170-178`), from the per-page box counts.  Returns (bboxes [T,5] or None,
+    context_indices int64 [T, 2*context_size])."""
+    cs = context_size
+    ctx, bb, seen = [], [], 0
+    for page, n in enumerate(boxes_per_page):
+        for i in range(n):
+            c = list(range(max(0, i - cs), i)) + list(range(i + 1, min(n, i + cs + 1)))
+            ctx.append([j + seen for j in c] + [-1] * (2 * cs - len(c)))
+        if boxes_xywh is not None:
+            b = np.asarray(boxes_xywh[seen:seen + n], np.float32).copy()
+            b[:, 2:] += b[:, :2]
+            bb.append(np.concatenate((np.full((n, 1), page, np.float32), b), 1))
+        seen += n
+    ctx = np.asarray(ctx, np.int64).reshape(seen, 2 * cs)
+    return (np.concatenate(bb) if bb else None), ctx

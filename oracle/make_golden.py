@@ -192,6 +192,85 @@ def train_fixture():
          **{"buf:" + k: v.numpy() for k, v in m.state_dict().items() if "running" in k})
 
 
+def tail_fixture():
+    """The callers either side of the forward, run live: torch's CE(sum) + Adam (what `main.py:133-139` constructs),
+    the reference's own `train.evaluate_model` (`train.py:99-171`) and `datasets.custom_collate_fn`
+    (`datasets.py:141-190`).  The per-item context window is the literal loop of `datasets.py:120-127` (that method
+    also opens image files, which do not exist here)."""
+    import datasets as ref_ds
+    import train as ref_train
+    g = torch.Generator().manual_seed(11)
+    # ---- CE(sum) forward / gradient, arg-max hits
+    logits = (torch.randn(53, 4, generator=g) * 3).requires_grad_(True)
+    labels = torch.randint(0, 4, (53,), generator=g)
+    labels[5] = -100                                   # torch's default ignore_index
+    loss = torch.nn.CrossEntropyLoss(reduction="sum")(logits, labels)
+    loss.backward()
+    ce = dict(ce_logits=logits.detach().numpy(), ce_labels=labels.numpy(), ce_loss=np.float32(loss.item()),
+              ce_grad=logits.grad.numpy(), ce_correct=np.int64((logits.argmax(1) == labels).sum().item()))
+    # ---- Adam(lr, weight_decay): 4 steps on a 1003-element parameter with fresh gradients each step
+    p = torch.nn.Parameter(torch.randn(1003, generator=g))
+    opt = torch.optim.Adam([p], lr=5e-4, weight_decay=1e-3)
+    grads = torch.randn(4, 1003, generator=g)
+    adam = dict(adam_p0=p.detach().numpy().copy(), adam_grads=grads.numpy())
+    for i in range(4):
+        p.grad = grads[i].clone()
+        opt.step()
+        adam["adam_p%d" % (i + 1)] = p.detach().numpy().copy()
+    adam["adam_m4"] = opt.state[p]["exp_avg"].numpy().copy()
+    adam["adam_v4"] = opt.state[p]["exp_avg_sq"].numpy().copy()
+    # ---- custom_collate_fn on ragged pages (context window: datasets.py:120-127 verbatim)
+    counts, cs = [7, 1, 12, 30, 2], 4
+    items, raw = [], []
+    for pi, n in enumerate(counts):
+        xywh = torch.rand(n, 4, generator=g) * 200 + 1
+        raw.append(xywh)
+        bb = xywh.clone()
+        bb[:, 2:] += bb[:, :2]                         # datasets.py:114-115
+        context_indices = []
+        for i in range(n):
+            context = list(range(max(0, i - cs), i)) + list(range(i + 1, min(n, i + cs + 1)))
+            context_indices.append(context + [-1] * (2 * cs - len(context)))
+        items.append((pi, torch.zeros(3, 4, 4), bb, torch.empty(n, 0), torch.LongTensor(context_indices),
+                      torch.zeros(n, dtype=torch.long)))
+    _, _, cb, _, cci, _ = ref_ds.custom_collate_fn(items)
+    coll = dict(coll_counts=np.asarray(counts), coll_cs=np.int64(cs), coll_xywh=torch.cat(raw).numpy(),
+                coll_bboxes=cb.numpy(), coll_ctx=cci.numpy())
+    # ---- evaluate_model (reference, unmodified) on preset logits: 3 batches of ragged pages, k = 1 and 3
+    class Fake(torch.nn.Module):
+        n_classes, class_names = 4, ["BG", "price", "title", "image"]
+
+        def __init__(self, outs):
+            super().__init__()
+            self.outs, self.i = outs, 0
+
+        def forward(self, *a):
+            self.i += 1
+            return self.outs[self.i - 1]
+    batches, outs, ev = [], [], {}
+    img = 0
+    for bi, cnts in enumerate([[9, 14, 5], [33], [6, 6]]):
+        bb, lab = [], []
+        for pi, n in enumerate(cnts):
+            l = torch.zeros(n, dtype=torch.long)
+            l[torch.randperm(n, generator=g)[:3]] = torch.tensor([1, 2, 3])
+            bb.append(torch.cat((torch.full((n, 1), float(pi)), torch.rand(n, 4, generator=g)), 1))
+            lab.append(l)
+        T = sum(cnts)
+        out = torch.randn(T, 4, generator=g)
+        out[::3, 1] = out[0, 1]                        # ties inside a column
+        batches.append((np.arange(img, img + len(cnts)), torch.zeros(len(cnts), 3, 4, 4), torch.cat(bb), torch.empty(T, 0),
+                        torch.zeros(T, 0, dtype=torch.long), torch.cat(lab)))
+        outs.append(out)
+        img += len(cnts)
+        ev["ev_bboxes%d" % bi], ev["ev_labels%d" % bi], ev["ev_logits%d" % bi] = batches[-1][2].numpy(), batches[-1][5].numpy(), out.numpy()
+    for k in (1, 3):
+        ia, ca = ref_train.evaluate_model(Fake(outs), batches, "cpu", k, "VAL", "/tmp/cova_golden_log.txt")
+        ev["ev_img_acc_k%d" % k], ev["ev_class_acc_k%d" % k] = ia, ca
+    save("g_tail", **ce, **adam, **coll, **ev)
+
+
 if __name__ == "__main__":
     main()
     train_fixture()
+    tail_fixture()

@@ -130,3 +130,41 @@ def test_torch_port_matches_golden():
         assert rel_err(out.numpy(), load_golden(name)["logits"]) < 5e-6
     out = TP.forward(synth.make_state_dict(123, backbone="resnet50"), *synth.gen(1, 16, 8, seed=5, img=128))
     assert rel_err(out.numpy(), load_golden("g_r50_img128")["logits"]) < 1e-5
+
+
+# ----------------------------------------------------------------------------- callers either side of the forward
+def test_tail_ce_sum_matches_torch():
+    g = load_golden("g_tail")
+    loss, grad, nc = O.ce_sum(g["ce_logits"], g["ce_labels"])
+    assert abs(float(loss) - float(g["ce_loss"])) <= 2e-6 * abs(float(g["ce_loss"]))
+    assert np.abs(grad - g["ce_grad"]).max() < 1e-6
+    assert nc == int(g["ce_correct"])
+
+
+def test_tail_adam_matches_torch():
+    g = load_golden("g_tail")
+    p, m, v = g["adam_p0"], np.zeros(1003, np.float32), np.zeros(1003, np.float32)
+    for i in range(4):
+        p, m, v = O.adam_step(p, g["adam_grads"][i], m, v, 5e-4, 0.9, 0.999, 1e-8, 1e-3, i + 1)
+        assert np.abs(p - g["adam_p%d" % (i + 1)]).max() < 2e-7
+    assert rel_err(m, g["adam_m4"]) < 1e-6 and rel_err(v, g["adam_v4"]) < 1e-6
+
+
+def test_tail_build_batch_matches_collate():
+    g = load_golden("g_tail")
+    bb, ctx = O.build_batch(list(g["coll_counts"]), int(g["coll_cs"]), g["coll_xywh"])
+    assert np.array_equal(ctx, g["coll_ctx"])
+    assert np.array_equal(bb, g["coll_bboxes"])
+
+
+def test_tail_topk_hits_matches_evaluate_model():
+    g = load_golden("g_tail")
+    for k in (1, 3):
+        rows = []
+        for bi in range(3):
+            page = g["ev_bboxes%d" % bi][:, 0].astype(np.int64)
+            off = np.concatenate(([0], np.cumsum(np.bincount(page))))
+            rows.append(O.topk_hits(g["ev_logits%d" % bi], g["ev_labels%d" % bi], off, k))
+        hits = np.concatenate(rows)
+        assert np.array_equal(hits[:, 1:], g["ev_img_acc_k%d" % k][:, 1:])
+        assert np.allclose(hits[:, 1:].mean(0) * 100, g["ev_class_acc_k%d" % k][1:])
