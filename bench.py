@@ -327,7 +327,8 @@ def main():
     print(json.dumps({
         "metric": "webpages/sec", "value": value, "unit": "pages/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": {"fp32": "bf16x3 (split-bf16, fp32 accumulate; fp32-parity)", "bf16": "bf16"}[model.precision]
+        "vs_baseline": None, "dtype": {"fp32": "bf16x3 (split-bf16, fp32 accumulate; fp32-parity)", "bf16": "bf16",
+                                       "fp16": "fp16 (one product, fp32 accumulate)"}[model.precision]
         if model.engine == "tcgen05" else "f32",
         "data": "synthetic",
         "config": {"workload": "configs[1]: batch=16 synthetic 1280x1280 pages per GPU, N=90 boxes, K=24, "

@@ -18,7 +18,7 @@ NVCC_FLAGS = [
     "-Xcompiler", "-fPIC", "-shared", "--cudart", "static",
 ]
 
-F32, BF16, BF16X2, U8 = 0, 1, 2, 3
+F32, BF16, BF16X2, U8, F16 = 0, 1, 2, 3, 4
 ENGINE_SIMT, ENGINE_TCGEN05 = 0, 1
 
 
@@ -63,6 +63,8 @@ SIGNATURES = {
     "cova_conv1x1_bn_act_fwd": (_I, [_P, _P, _L, _I, _I, _P, _P, _P, _P, _P, _I, _I, _P, _P, _P]),
     "cova_pack_conv_weight": (_I, [_P, _I, _I, _I, _I, _P, _P, _P, _P]),
     "cova_pack_stem_weight": (_I, [_P, _P, _P]),
+    "cova_pack_stem_weight_f16": (_I, [_P, _P, _P]),
+    "cova_pack_conv_weight_f16": (_I, [_P, _I, _I, _I, _I, _P, _P]),
     "cova_roi_fwd": (_I, [_P, _I, _I, _I, _I, _P, _I, _I, _I, _F, _I, _I, _P, _L, _P, _P]),
     "cova_roi_pool_bwd": (_I, [_P, _L, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P]),
     "cova_bbox_enc_fwd": (_I, [_P, _I, _P, _P, _P, _P, _I, _P, _L, _P]),

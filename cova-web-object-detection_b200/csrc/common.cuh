@@ -1,6 +1,7 @@
 // Shared helpers for libcova_b200.so (sm_100a only).
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -63,6 +64,15 @@ __device__ __forceinline__ void split_bf16x2(float a, float b, uint32_t& hi, uin
 __device__ __forceinline__ uint32_t pack2_bf16(float a, float b) {
   __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// fp16 pairs (a in the low half), for the single-plane fp16 mode (COVA_F16)
+__device__ __forceinline__ uint32_t pack2_f16(float a, float b) {
+  __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ float2 unpack2_f16(uint32_t packed) {
+  return __half22float2(*reinterpret_cast<const __half2*>(&packed));
 }
 
 // 256-bit global accesses (sm_100: LDG/STG.E.256): one full 32-byte sector per lane

@@ -145,7 +145,27 @@ __global__ void pack_conv_weight_kernel(const float* __restrict__ w, int Cout, i
   }
 }
 
+// OIHW fp32 -> fp16 [kh*kw][Cout][Cin] (single-plane fp16 mode, COVA_F16)
+__global__ void pack_conv_weight_f16_kernel(const float* __restrict__ w, int Cout, int Cin, int KH, int KW,
+                                            __half* __restrict__ out) {
+  const int n = Cout * Cin * KH * KW;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int s = i % KW, r = (i / KW) % KH, ci = (i / (KW * KH)) % Cin, co = i / (KW * KH * Cin);
+    out[((size_t)(r * KW + s) * Cout + co) * Cin + ci] = __float2half_rn(w[i]);
+  }
+}
+
 }  // namespace cova
+
+extern "C" int cova_pack_conv_weight_f16(const float* w_oihw, int Cout, int Cin, int kh, int kw, void* tc_f16,
+                                         void* stream) {
+  COVA_REQUIRE(w_oihw && tc_f16 && Cout > 0 && Cin > 0 && kh > 0 && kw > 0, "cova_pack_conv_weight_f16: bad arguments");
+  const int n = Cout * Cin * kh * kw;
+  cova::pack_conv_weight_f16_kernel<<<cova::ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(w_oihw, Cout, Cin, kh, kw,
+                                                                                             (__half*)tc_f16);
+  COVA_LAUNCH_OK();
+  return COVA_OK;
+}
 
 extern "C" int cova_pack_conv_weight(const float* w_oihw, int Cout, int Cin, int kh, int kw, float* simt_out,
                                      void* tc_hi, void* tc_lo, void* stream) {

@@ -78,7 +78,8 @@ __device__ __forceinline__ uint64_t desc_noswz(uint32_t addr, uint32_t lbo, uint
   return d;
 }
 
-template <bool SPLIT, int OUT_DTYPE, bool U8, int NCV>
+// HALF (single-plane mode only): ring pixels, filter and output plane are fp16 instead of bf16 (COVA_F16).
+template <bool SPLIT, int OUT_DTYPE, bool U8, int NCV, bool HALF>
 __global__ void __launch_bounds__(sx_threads(NCV), 1)
 stem_tc_kernel(const StemTcParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -102,9 +103,14 @@ stem_tc_kernel(const StemTcParams p) {
     sm.shift[threadIdx.x] = p.bn_shift[threadIdx.x];
   }
   if (U8 && threadIdx.x < 256) {   // v/255 with IEEE division == torchvision ToTensor; split once per pixel value
-    __nv_bfloat16 h, l;
-    split_bf16(__fdiv_rn((float)threadIdx.x, 255.f), h, l);
-    sm.lut[threadIdx.x] = pack_bf16x2(h, l);
+    const float pv = __fdiv_rn((float)threadIdx.x, 255.f);
+    if (HALF) {
+      sm.lut[threadIdx.x] = pack2_f16(pv, 0.f);
+    } else {
+      __nv_bfloat16 h, l;
+      split_bf16(pv, h, l);
+      sm.lut[threadIdx.x] = pack_bf16x2(h, l);
+    }
   }
   if (threadIdx.x == 0) {
     for (int i = 0; i < SX_R; ++i) ptx::mbar_init(&sm.in_full[i], 1);
@@ -135,7 +141,8 @@ stem_tc_kernel(const StemTcParams p) {
     __syncwarp();
     ptx::mbar_wait(&sm.wbar, 0);
     // Ahi x [Whi; Wlo] is ONE N = 128 MMA (operand feed: 64 clk instead of 2 x 48, see conv_tc.cu), Alo x Whi N = 64
-    constexpr uint32_t idesc64 = ptx::umma_idesc_bf16(128, 64), idesc128 = ptx::umma_idesc_bf16(128, 128);
+    constexpr uint32_t idesc64 = HALF ? ptx::umma_idesc_f16(128, 64) : ptx::umma_idesc_bf16(128, 64);
+    constexpr uint32_t idesc128 = ptx::umma_idesc_bf16(128, 128);
     const uint64_t da0 = desc_noswz(ptx::smem_u32(&sm.ring[0][0][0]), 16, 128);
     const uint64_t db0 = desc_noswz(ptx::smem_u32(&sm.w[0]), SX_W_CHUNK, 128);
     uint32_t t = 0;
@@ -278,6 +285,7 @@ stem_tc_kernel(const StemTcParams p) {
 #pragma unroll
               for (int e = 0; e < 8; ++e) {
                 if (OUT_DTYPE == COVA_BF16X2) split_bf16x2(o[c16 + 2 * e], o[c16 + 2 * e + 1], hw[e], lw[e]);
+                else if (HALF) hw[e] = pack2_f16(o[c16 + 2 * e], o[c16 + 2 * e + 1]);
                 else hw[e] = pack2_bf16(o[c16 + 2 * e], o[c16 + 2 * e + 1]);
               }
               st_global_v8(reinterpret_cast<__nv_bfloat16*>(p.out0) + opix + c16, hw);
@@ -364,8 +372,12 @@ stem_tc_kernel(const StemTcParams p) {
           const int i = lane + 32 * j;
           if (i < SX_NPX) {
             uint32_t h01, l01, h2, l2;
-            split_bf16x2(f[j][0], f[j][1], h01, l01);
-            split_bf16x2(f[j][2], 0.f, h2, l2);
+            if (HALF) {
+              h01 = pack2_f16(f[j][0], f[j][1]); h2 = pack2_f16(f[j][2], 0.f); l01 = l2 = 0u;
+            } else {
+              split_bf16x2(f[j][0], f[j][1], h01, l01);
+              split_bf16x2(f[j][2], 0.f, h2, l2);
+            }
             *reinterpret_cast<uint2*>(dst_hi + i * 8) = make_uint2(h01, h2);
             if (SPLIT) *reinterpret_cast<uint2*>(dst_hi + SX_R * SX_ROW_BYTES + i * 8) = make_uint2(l01, l2);
           }
@@ -400,19 +412,31 @@ __global__ void pack_stem_weight_kernel(const float* __restrict__ w, __nv_bfloat
   out[((chunk * 2 + 1) * 64 + co) * 8 + e] = l;
 }
 
-template <bool SPLIT, int OUT_DTYPE, bool U8, int NCV>
+// same layout, plane 0 = fp16(w), plane 1 = 0 (single-plane fp16 mode)
+__global__ void pack_stem_weight_f16_kernel(const float* __restrict__ w, __half* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= SX_KCHUNKS * 64 * 8) return;
+  const int e = i & 7, co = (i >> 3) & 63, chunk = i >> 9;
+  const int r = chunk >> 2, s = (chunk & 3) * 2 + (e >> 2), c = e & 3;
+  float v = 0.f;
+  if (s < 7 && c < 3) v = w[((co * 3 + c) * 7 + r) * 7 + s];
+  out[((chunk * 2 + 0) * 64 + co) * 8 + e] = __float2half_rn(v);
+  out[((chunk * 2 + 1) * 64 + co) * 8 + e] = __float2half_rn(0.f);
+}
+
+template <bool SPLIT, int OUT_DTYPE, bool U8, int NCV, bool HALF>
 static int launch_stem_tc_n(const StemTcParams& p, int grid, cudaStream_t st) {
-  auto kern = stem_tc_kernel<SPLIT, OUT_DTYPE, U8, NCV>;
+  auto kern = stem_tc_kernel<SPLIT, OUT_DTYPE, U8, NCV, HALF>;
   const int smem = (int)sizeof(StemTcSmem<SPLIT>) + 128;
   COVA_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   kern<<<grid, sx_threads(NCV), smem, st>>>(p);
   COVA_LAUNCH_OK();
   return COVA_OK;
 }
-template <bool SPLIT, int OUT_DTYPE, bool U8>
+template <bool SPLIT, int OUT_DTYPE, bool U8, bool HALF = false>
 static int launch_stem_tc(const StemTcParams& p, int grid, cudaStream_t st) {
-  if (knob(COVA_KNOB_STEM_CONVERTERS, 8) >= 8) return launch_stem_tc_n<SPLIT, OUT_DTYPE, U8, 8>(p, grid, st);
-  return launch_stem_tc_n<SPLIT, OUT_DTYPE, U8, 4>(p, grid, st);
+  if (knob(COVA_KNOB_STEM_CONVERTERS, 8) >= 8) return launch_stem_tc_n<SPLIT, OUT_DTYPE, U8, 8, HALF>(p, grid, st);
+  return launch_stem_tc_n<SPLIT, OUT_DTYPE, U8, 4, HALF>(p, grid, st);
 }
 
 int stem_tc(const void* images, int img_u8, int B, int H, int W, const void* w_packed, const float* bn_scale,
@@ -435,6 +459,9 @@ int stem_tc(const void* images, int img_u8, int B, int H, int W, const void* w_p
   p.pf_rows = knob(COVA_KNOB_STEM_L2_PREFETCH, 1);
   p.dbg = debug_words(8LL * B * p.bands_per_page);
   const int grid = B * p.bands_per_page;
+  if (out_dtype == COVA_F16)   // fp16 mode: the filter comes from cova_pack_stem_weight_f16
+    return img_u8 ? launch_stem_tc<false, COVA_BF16, true, true>(p, grid, st)
+                  : launch_stem_tc<false, COVA_BF16, false, true>(p, grid, st);
   const bool split = out_dtype != COVA_BF16;   // bf16 output <=> bf16 mode; fp32 / split outputs use the 3-product mode
 #define GO(SP, DT) (img_u8 ? launch_stem_tc<SP, DT, true>(p, grid, st) : launch_stem_tc<SP, DT, false>(p, grid, st))
   if (split) {
@@ -451,6 +478,14 @@ extern "C" int cova_pack_stem_weight(const float* w_oihw, void* packed, void* st
   COVA_REQUIRE(w_oihw && packed, "cova_pack_stem_weight: null pointer");
   cova::pack_stem_weight_kernel<<<cova::ceil_div(cova::SX_KCHUNKS * 64 * 8, 256), 256, 0, (cudaStream_t)stream>>>(
       w_oihw, (__nv_bfloat16*)packed);
+  COVA_LAUNCH_OK();
+  return COVA_OK;
+}
+
+extern "C" int cova_pack_stem_weight_f16(const float* w_oihw, void* packed, void* stream) {
+  COVA_REQUIRE(w_oihw && packed, "cova_pack_stem_weight_f16: null pointer");
+  cova::pack_stem_weight_f16_kernel<<<cova::ceil_div(cova::SX_KCHUNKS * 64 * 8, 256), 256, 0, (cudaStream_t)stream>>>(
+      w_oihw, (__half*)packed);
   COVA_LAUNCH_OK();
   return COVA_OK;
 }

@@ -13,7 +13,7 @@ Stage order = ``CoVA.forward`` (`/root/reference/models.py:94-122`):
 import torch
 
 from . import ops
-from .ops import BF16, BF16X2, ENGINE_SIMT, ENGINE_TCGEN05, F32
+from .ops import BF16, BF16X2, ENGINE_SIMT, ENGINE_TCGEN05, F16, F32
 
 
 def fold_bn(bn):
@@ -43,12 +43,13 @@ class NativeForward:
         r50 = m.backbone == "resnet50"
         tc = m.engine == "tcgen05"
         split = m.precision == "fp32" or r50          # the ResNet-50 tensor-core path is fp32-parity only
+        half = tc and m.precision == "fp16" and not r50
         c["tc"] = tc
-        c["act_dtype"] = (BF16X2 if split else BF16) if tc else F32
+        c["act_dtype"] = (BF16X2 if split else (F16 if half else BF16)) if tc else F32
         cn = m.convnet
         c["stem_w"] = cn[0].weight.detach().float().contiguous()
         if tc:
-            c["stem_w"] = ops.pack_stem_weight(c["stem_w"])
+            c["stem_w"] = ops.pack_stem_weight_f16(c["stem_w"]) if half else ops.pack_stem_weight(c["stem_w"])
         c["stem_bn"] = fold_bn(cn[1])
         blocks = []
         for blk in cn[4]:
@@ -56,8 +57,11 @@ class NativeForward:
             if m.backbone == "resnet18":
                 for i in (1, 2):
                     conv, bn = getattr(blk, f"conv{i}"), getattr(blk, f"bn{i}")
-                    s, hi, lo = ops.pack_conv_weight(conv.weight.detach().float(), simt=not tc, tc=tc, split=split)
-                    d[f"w{i}"] = (hi, lo) if tc else (s, None)
+                    if half:
+                        d[f"w{i}"] = (ops.pack_conv_weight_f16(conv.weight.detach().float()), None)
+                    else:
+                        s, hi, lo = ops.pack_conv_weight(conv.weight.detach().float(), simt=not tc, tc=tc, split=split)
+                        d[f"w{i}"] = (hi, lo) if tc else (s, None)
                     d[f"bn{i}"] = fold_bn(bn)
             else:  # Bottleneck: the 1x1 convs are row-major GEMMs on the NHWC pixel rows
                 d["w1"] = blk.conv1.weight.detach().float().flatten(1).contiguous()

@@ -4,7 +4,7 @@ CPU path here (the CPU restatement lives in ``oracle/`` and is test infrastructu
 import torch
 
 from . import _lib
-from ._lib import BF16, BF16X2, ENGINE_SIMT, ENGINE_TCGEN05, F32, U8  # noqa: F401
+from ._lib import BF16, BF16X2, ENGINE_SIMT, ENGINE_TCGEN05, F16, F32, U8  # noqa: F401
 
 ENGINES = {"simt": ENGINE_SIMT, "tcgen05": ENGINE_TCGEN05}
 
@@ -41,7 +41,7 @@ class Planes:
 
     def __init__(self, dtype, shape, device):
         self.dtype, self.shape = dtype, tuple(shape)
-        td = torch.float32 if dtype == F32 else torch.bfloat16
+        td = torch.float32 if dtype == F32 else (torch.float16 if dtype == F16 else torch.bfloat16)
         self.p0 = torch.empty(self.shape, dtype=td, device=device)
         self.p1 = torch.empty(self.shape, dtype=td, device=device) if dtype == BF16X2 else None
 
@@ -94,6 +94,24 @@ def pack_stem_weight(w_oihw):
     _cuda(w_oihw, torch.float32, "w")
     out = torch.empty((28, 2, 64, 8), dtype=torch.bfloat16, device=w_oihw.device)
     _call("cova_pack_stem_weight", w_oihw.contiguous().data_ptr(), out.data_ptr(), _stream())
+    return out
+
+
+def pack_stem_weight_f16(w_oihw):
+    """fp16-mode stem filter ([28,2,64,8] fp16, plane 1 zero)."""
+    _cuda(w_oihw, torch.float32, "w")
+    out = torch.empty((28, 2, 64, 8), dtype=torch.float16, device=w_oihw.device)
+    _call("cova_pack_stem_weight_f16", w_oihw.contiguous().data_ptr(), out.data_ptr(), _stream())
+    return out
+
+
+def pack_conv_weight_f16(w_oihw):
+    """OIHW fp32 -> fp16 [kh*kw, Cout, Cin] for the fp16 mode of conv3x3_bn_act_fwd."""
+    _cuda(w_oihw, torch.float32, "w")
+    w = w_oihw.contiguous()
+    Co, Ci, kh, kw = w.shape
+    out = torch.empty((kh * kw, Co, Ci), dtype=torch.float16, device=w.device)
+    _call("cova_pack_conv_weight_f16", w.data_ptr(), Co, Ci, kh, kw, out.data_ptr(), _stream())
     return out
 
 

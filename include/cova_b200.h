@@ -17,6 +17,9 @@
  *      COVA_BF16X2 split-bf16: `p0` = hi plane = bf16(x), `p1` = lo plane = bf16(x - hi).  hi+lo carries
  *                 ~16 mantissa bits; products hi*Whi + lo*Whi + hi*Wlo on tcgen05 tensor cores with fp32
  *                 accumulate reproduce an fp32 convolution to ~1e-5 (the "fp32-parity" tensor-core mode).
+ *      COVA_F16   one fp16 plane (`p0`): the single-product throughput mode of the tcgen05 engine.  fp16 keeps
+ *                 11 significand bits (bf16: 8), which is what brings a one-product pipeline inside the 1e-3 bar
+ *                 (measured ~5e-4 on the logits); activations must stay below 65504 (post-BN/ReLU maps do).
  *  - Eval-mode BatchNorm is passed folded: y = x*scale[c] + shift[c]
  *    (scale = weight/sqrt(running_var+eps), shift = bias - running_mean*scale).
  */
@@ -32,7 +35,7 @@ extern "C" {
 #define COVA_ABI_VERSION 1
 
 enum { COVA_OK = 0, COVA_ERR_ARG = 1, COVA_ERR_CUDA = 2, COVA_ERR_UNSUPPORTED = 3 };
-enum { COVA_F32 = 0, COVA_BF16 = 1, COVA_BF16X2 = 2, COVA_U8 = 3 /* images only */ };
+enum { COVA_F32 = 0, COVA_BF16 = 1, COVA_BF16X2 = 2, COVA_U8 = 3 /* images only */, COVA_F16 = 4 };
 enum { COVA_ENGINE_SIMT = 0, COVA_ENGINE_TCGEN05 = 1 };
 
 int cova_abi_version(void);
@@ -66,10 +69,13 @@ int cova_debug_buffer(void* dev_words, int64_t n_words);
  *   w       engine SIMT   : [64,3,7,7] fp32 OIHW (`convnet.0.weight`)
  *           engine TCGEN05: the split-bf16 K-chunked filter written by cova_pack_stem_weight
  *   bn_scale/bn_shift [64] folded `convnet.1`
- *   out     NHWC [B,H/4,W/4,64] in `out_dtype` (planes out0/out1).  TCGEN05: COVA_BF16 output selects the
- *           single-product bf16 mode, COVA_BF16X2 / COVA_F32 the 3-product fp32-parity mode.            */
+ *   out     NHWC [B,H/4,W/4,64] in `out_dtype` (planes out0/out1).  TCGEN05: COVA_BF16 / COVA_F16 output selects
+ *           the single-product bf16 / fp16 mode, COVA_BF16X2 / COVA_F32 the 3-product fp32-parity mode.   */
 int cova_stem_fwd(const void* images, int img_dtype, int B, int H, int W, const void* w, const float* bn_scale,
                   const float* bn_shift, int out_dtype, void* out0, void* out1, int engine, void* stream);
+
+/* Same layout for the fp16 mode (out_dtype COVA_F16): plane 0 = fp16(w), plane 1 = 0. */
+int cova_pack_stem_weight_f16(const float* w_oihw, void* packed, void* stream);
 
 /* OIHW fp32 [64,3,7,7] -> tcgen05 stem filter: bf16 [28 K-chunks][2 planes (hi, lo)][64 cout][8],
  * K index = r*32 + s*4 + c with zero weights at s = 7 and c = 3 (57,344 bytes).                       */
@@ -98,6 +104,9 @@ int cova_conv1x1_bn_act_fwd(const void* x_hi, const void* x_lo, int64_t M, int C
  *   tc_hi/lo  : bf16 [kh*kw][Cout][Cin] hi/lo split            (may be NULL)                         */
 int cova_pack_conv_weight(const float* w_oihw, int Cout, int Cin, int kh, int kw, float* simt_out,
                           void* tc_hi, void* tc_lo, void* stream);
+
+/* OIHW fp32 -> fp16 [kh*kw][Cout][Cin] for the COVA_F16 mode of cova_conv3x3_bn_act_fwd (w_a = this, w_b = NULL). */
+int cova_pack_conv_weight_f16(const float* w_oihw, int Cout, int Cin, int kh, int kw, void* tc_f16, void* stream);
 
 /* ---- A4: RoIPool.  Replaces `torchvision.ops.RoIPool(P, scale)` (`models.py:58`, `:125-127`).
  * Bit-exact in fp32.  fm NHWC fp32 [B,Hf,Wf,C]; rois [T,5] fp32 = [batch_idx,x1,y1,x2,y2] image pixels.

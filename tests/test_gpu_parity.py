@@ -4,6 +4,7 @@ the live reference (``tests/golden``).  Tolerances (max|a-b| / max|b| unless sta
   * RoIPool ....................................... bit-exact
   * exact-fp32 engine (simt), every stage ......... 1e-5
   * tcgen05 fp32-parity mode (split-bf16 x3) ...... 1e-4 on the feature map, 1e-4 on logits
+  * tcgen05 fp16 mode (one fp16 product) .......... 2e-3 on the feature map, 1e-3 on logits (= BASELINE.json's bar)
   * tcgen05 bf16 mode ............................. 2e-2 on the feature map, 1e-2 on logits.  Measured 3-4e-3 on
     logits: single-pass bf16 does NOT meet BASELINE.json's 1e-3 bar, which is why the fp32-parity mode is the
     default and the one bench.py measures.
@@ -72,7 +73,7 @@ def test_stem_kernel(out_dtype):
     assert rel_err(t2n(out.float()), ref) < (1e-5 if out_dtype == "f32" else 3e-5)
 
 
-@pytest.mark.parametrize("out_dtype", ["f32", "bf16x2", "bf16"])
+@pytest.mark.parametrize("out_dtype", ["f32", "bf16x2", "bf16", "f16"])
 @pytest.mark.parametrize("B,H", [(2, 104), (1, 260), (3, 64)])
 def test_stem_tcgen05_kernel(out_dtype, B, H):
     """Tensor-core stem (ring of raw image rows + sliding-window descriptors + fused pooling) vs the oracle.
@@ -84,16 +85,19 @@ def test_stem_tcgen05_kernel(out_dtype, B, H):
     scale, shift = 0.5 + torch.rand(64, generator=g), 0.1 * torch.randn(64, generator=g)
     if out_dtype == "bf16":   # single-product mode: the oracle sees the bf16-rounded image and filter
         ref = O.conv2d_nchw(img.bfloat16().float().numpy(), w.bfloat16().float().numpy(), 2, 3)
+    elif out_dtype == "f16":  # fp16 mode: fp16-rounded image and filter
+        ref = O.conv2d_nchw(img.half().float().numpy(), w.half().float().numpy(), 2, 3)
     else:
         ref = O.conv2d_nchw(img.numpy(), w.numpy(), 2, 3)
     ref = ref * scale.numpy().reshape(1, -1, 1, 1) + shift.numpy().reshape(1, -1, 1, 1)
     ref = O.maxpool3x3s2p1(np.maximum(ref, 0)).transpose(0, 2, 3, 1)
-    wp = o.pack_stem_weight(w.to(DEV))
+    wp = o.pack_stem_weight_f16(w.to(DEV)) if out_dtype == "f16" else o.pack_stem_weight(w.to(DEV))
     out = o.stem_fwd(img.to(DEV), wp, scale.to(DEV), shift.to(DEV),
-                     out_dtype={"f32": o.F32, "bf16x2": o.BF16X2, "bf16": o.BF16}[out_dtype], engine=o.ENGINE_TCGEN05)
+                     out_dtype={"f32": o.F32, "bf16x2": o.BF16X2, "bf16": o.BF16, "f16": o.F16}[out_dtype],
+                     engine=o.ENGINE_TCGEN05)
     torch.cuda.synchronize()
     assert out.shape == ref.shape
-    assert rel_err(t2n(out.float()), ref) < {"f32": 3e-5, "bf16x2": 5e-5, "bf16": 6e-3}[out_dtype]
+    assert rel_err(t2n(out.float()), ref) < {"f32": 3e-5, "bf16x2": 5e-5, "bf16": 6e-3, "f16": 6e-4}[out_dtype]
 
 
 @pytest.mark.parametrize("W", [104, 102])
@@ -157,31 +161,36 @@ def _split(t):
     return hi, lo
 
 
-@pytest.mark.parametrize("mode,out", [("split", "f32"), ("split", "bf16x2"), ("bf16", "bf16"), ("bf16", "f32")])
+@pytest.mark.parametrize("mode,out", [("split", "f32"), ("split", "bf16x2"), ("bf16", "bf16"), ("bf16", "f32"),
+                                      ("f16", "f16"), ("f16", "f32")])
 @pytest.mark.parametrize("shape", [(1, 16, 8), (2, 37, 45), (1, 80, 64)])
 def test_conv3x3_tcgen05_kernel(mode, out, shape):
     """tcgen05 implicit-GEMM conv vs the oracle conv; shapes cover 1 tile, ragged tiles, multi-tile."""
     o = ops()
     B, H, W = shape
     x, w, scale, shift, res, ref = _conv_case(3, B, H, W, True)
-    split = mode == "split"
-    _, whi, wlo = o.pack_conv_weight(w.to(DEV), simt=False, tc=True, split=split)
-    dt = o.BF16X2 if split else o.BF16
+    split, half = mode == "split", mode == "f16"
+    if half:
+        whi, wlo = o.pack_conv_weight_f16(w.to(DEV)), None
+    else:
+        _, whi, wlo = o.pack_conv_weight(w.to(DEV), simt=False, tc=True, split=split)
+    dt = o.BF16X2 if split else (o.F16 if half else o.BF16)
     xp, rp = o.Planes(dt, x.shape, DEV), o.Planes(dt, x.shape, DEV)
     for p, t in ((xp, x), (rp, res)):
         hi, lo = _split(t)
-        p.p0.copy_(hi)
+        p.p0.copy_(t.half() if half else hi)
         if split:
             p.p1.copy_(lo)
-    if not split:   # oracle sees what the kernel sees: bf16-rounded input, residual and weights
-        xq, rq, wq = x.bfloat16().float(), res.bfloat16().float(), w.bfloat16().float()
+    if not split:   # oracle sees what the kernel sees: bf16- (fp16-) rounded input, residual and weights
+        q = (lambda t: t.half().float()) if half else (lambda t: t.bfloat16().float())
+        xq, rq, wq = q(x), q(res), q(w)
         ref = torch_conv(xq.permute(0, 3, 1, 2).numpy(), wq.numpy(), 1, 1).transpose(0, 2, 3, 1)
         ref = np.maximum(ref * scale.numpy() + shift.numpy() + rq.numpy(), 0)
-    od = {"f32": o.F32, "bf16": o.BF16, "bf16x2": o.BF16X2}[out]
+    od = {"f32": o.F32, "bf16": o.BF16, "bf16x2": o.BF16X2, "f16": o.F16}[out]
     y = o.conv3x3_bn_act_fwd(xp, whi, wlo, scale.to(DEV), shift.to(DEV), res=rp, relu=True, out_dtype=od,
                              engine=o.ENGINE_TCGEN05)
     torch.cuda.synchronize()
-    tol = {"f32": 3e-5, "bf16x2": 5e-5, "bf16": 6e-3}[out]   # bf16 out: one bf16 rounding of the result
+    tol = {"f32": 3e-5, "bf16x2": 5e-5, "bf16": 6e-3, "f16": 6e-4}[out]   # bf16 / fp16 out: one rounding of the result
     assert rel_err(t2n(y.float()), ref) < tol
 
 
@@ -350,7 +359,9 @@ def test_gat_stress_config5_shape():
 
 
 # ----------------------------------------------------------------------------- whole forward vs the live reference
-ENGINES = [("simt", "fp32", 1e-5, 2e-5), ("tcgen05", "fp32", 1e-4, 1e-4), ("tcgen05", "bf16", 2e-2, 1e-2)]
+# fp16 mode: the logits tolerance IS BASELINE.json's bar (1e-3); measured ~5e-4 (profiles/r01l_precision_modes.txt)
+ENGINES = [("simt", "fp32", 1e-5, 2e-5), ("tcgen05", "fp32", 1e-4, 1e-4), ("tcgen05", "bf16", 2e-2, 1e-2),
+           ("tcgen05", "fp16", 2e-3, 1e-3)]
 
 
 @pytest.mark.parametrize("engine,precision,tol_fm,tol_logits", ENGINES)
