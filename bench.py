@@ -257,11 +257,15 @@ def main():
     launches = ops.launch_count
     clocks = sampler.stop() if rank == 0 else None
     run_e2e(3)
-    ms_e2e = timed(run_e2e, args.steps, whole=True)
+    # each repetition times exactly `steps` steps; the better of two is reported (a PCIe / host hiccup in one
+    # repetition was observed to triple a 40 ms measurement) and both are listed under "reps_ms_per_step"
+    reps_e2e = [timed(run_e2e, args.steps, whole=True) for _ in range(2)]
+    ms_e2e = min(reps_e2e)
     # SURVEY 8(f) N1 (optional input format): the same pages as raw uint8 pixels, converted v/255 inside the stem
     pinned_u8 = [(inp[0] * 255).round().to(torch.uint8).pin_memory()] + pinned[1:]
     run_e2e(3, pinned_u8)
-    ms_e2e_u8 = timed(lambda k: run_e2e(k, pinned_u8), args.steps, whole=True)
+    reps_u8 = [timed(lambda k: run_e2e(k, pinned_u8), args.steps, whole=True) for _ in range(2)]
+    ms_e2e_u8 = min(reps_u8)
 
     pages = B_PER_GPU * world * args.steps
     value, e2e = pages / (ms / 1e3), pages / (ms_e2e / 1e3)
@@ -342,10 +346,12 @@ def main():
         "clocks": clocks, "gpu_launches": launches,
         "e2e": {"value": e2e, "unit": "pages/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": logits_host.numel() * 4, "ms_per_step": ms_e2e / args.steps,
+                "reps_ms_per_step": [round(r / args.steps, 4) for r in reps_e2e],
                 "note": "fp32 NCHW images = the reference's input contract; PCIe-bound (h2d bytes / ms)"},
         "e2e_uint8_images": {"value": pages / (ms_e2e_u8 / 1e3), "unit": "pages/s",
                              "h2d_bytes_per_step": sum(t.numel() * t.element_size() for t in pinned_u8),
                              "ms_per_step": ms_e2e_u8 / args.steps,
+                             "reps_ms_per_step": [round(r / args.steps, 4) for r in reps_u8],
                              "note": "optional input format (SURVEY 8(f) N1): uint8 pixels, v/255 in the stem kernel"},
         "roofline": roofline, "kernels": kernels,
         "cpu_baseline": {"value": cpu_v, "unit": "pages/s", "cores": cores, "kind": "port", "sample": sample},

@@ -46,31 +46,38 @@ __device__ __forceinline__ int bin_hi(int p, float bin, int start, int limit) {
 // One CTA = one box x one 64-channel block.  Warps take crop rows round-robin; per row a warp walks the
 // PW column segments, two pixels per load (half-warp each, float4 per lane), and folds each segment's
 // max into its private smem accumulators for the (<=2) row bins the row belongs to.
-template <bool WITH_ARGMAX>
+// ROWSPLIT: one CTA per (box, row bin) instead of per box - crop areas vary 1000x (8 px ... full-width boxes), and a
+// third of a box per CTA (adjacent row bins share at most one crop row) evens out the tail; ROI_SPLIT_WARPS warps.
+constexpr int ROI_SPLIT_WARPS = 4;
+template <bool WITH_ARGMAX, bool ROWSPLIT>
 __global__ void __launch_bounds__(ROI_THREADS)
 roi_pool_kernel(const float* __restrict__ fm, int Hf, int Wf, int C, const float* __restrict__ rois, int PH,
                 int PW, float scale, float* __restrict__ out, int64_t ld_out, int32_t* __restrict__ argmax) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int nbins = PH * PW;
-  float* acc = reinterpret_cast<float*>(smem_raw);                         // [warp][bin][64]
-  int* acc_i = reinterpret_cast<int*>(acc + ROI_WARPS * nbins * ROI_CB);   // same shape, only WITH_ARGMAX
-  const int t = blockIdx.x, cb = blockIdx.y * ROI_CB;
+  constexpr int NW = ROWSPLIT ? ROI_SPLIT_WARPS : ROI_WARPS;
+  const int nbins = PH * PW;                       // bins of the box
+  const int abins = ROWSPLIT ? PW : nbins;         // bins this CTA accumulates
+  float* acc = reinterpret_cast<float*>(smem_raw);                 // [warp][bin][64]
+  int* acc_i = reinterpret_cast<int*>(acc + NW * abins * ROI_CB);  // same shape, only WITH_ARGMAX
+  const int t = ROWSPLIT ? blockIdx.x / PH : blockIdx.x, cb = blockIdx.y * ROI_CB;
+  const int ph_own = ROWSPLIT ? blockIdx.x % PH : 0;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int half = lane >> 4, c4 = (lane & 15) * 4;
   const RoiGeom g = roi_geom(rois + (size_t)t * 5, scale, PH, PW);
 
-  for (int i = threadIdx.x; i < ROI_WARPS * nbins * ROI_CB; i += ROI_THREADS) {
+  for (int i = threadIdx.x; i < NW * abins * ROI_CB; i += NW * 32) {
     acc[i] = -FLT_MAX;
     if (WITH_ARGMAX) acc_i[i] = -1;
   }
   __syncthreads();
 
-  const int h_lo = bin_lo(0, g.bin_h, g.sh, Hf), h_hi = bin_hi(PH - 1, g.bin_h, g.sh, Hf);
+  const int h_lo = bin_lo(ROWSPLIT ? ph_own : 0, g.bin_h, g.sh, Hf);
+  const int h_hi = bin_hi(ROWSPLIT ? ph_own : PH - 1, g.bin_h, g.sh, Hf);
   const float* base = fm + (size_t)g.b * Hf * Wf * C + cb;
-  float* wacc = acc + warp * nbins * ROI_CB;
-  int* wacc_i = acc_i + warp * nbins * ROI_CB;
+  float* wacc = acc + warp * abins * ROI_CB;
+  int* wacc_i = acc_i + warp * abins * ROI_CB;
 
-  for (int h = h_lo + warp; h < h_hi; h += ROI_WARPS) {
+  for (int h = h_lo + warp; h < h_hi; h += NW) {
     const float* row = base + (size_t)h * Wf * C;
     for (int pw = 0; pw < PW; ++pw) {
       const int ws = bin_lo(pw, g.bin_w, g.sw, Wf), we = bin_hi(pw, g.bin_w, g.sw, Wf);
@@ -110,8 +117,8 @@ roi_pool_kernel(const float* __restrict__ fm, int Hf, int Wf, int C, const float
         m.x = fmaxf(m.x, o.x); m.y = fmaxf(m.y, o.y); m.z = fmaxf(m.z, o.z); m.w = fmaxf(m.w, o.w);
       }
       if (half == 0) {
-        for (int ph = 0; ph < PH; ++ph) {   // rows belong to at most two adjacent row bins
-          if (h < bin_lo(ph, g.bin_h, g.sh, Hf) || h >= bin_hi(ph, g.bin_h, g.sh, Hf)) continue;
+        for (int ph = 0; ph < (ROWSPLIT ? 1 : PH); ++ph) {   // rows belong to at most two adjacent row bins
+          if (!ROWSPLIT && (h < bin_lo(ph, g.bin_h, g.sh, Hf) || h >= bin_hi(ph, g.bin_h, g.sh, Hf))) continue;
           float4* a = reinterpret_cast<float4*>(wacc + (ph * PW + pw) * ROI_CB + c4);
           float4 cur = *a;
           if (WITH_ARGMAX) {
@@ -136,17 +143,18 @@ roi_pool_kernel(const float* __restrict__ fm, int Hf, int Wf, int C, const float
   __syncthreads();
 
   // cross-warp reduce; output index = c*PH*PW + bin  (the `.view(T, C*P*P)` order of models.py:125-127)
-  for (int o = threadIdx.x; o < ROI_CB * nbins; o += ROI_THREADS) {
-    const int c = o / nbins, bin = o % nbins;
+  for (int o = threadIdx.x; o < ROI_CB * abins; o += NW * 32) {
+    const int c = o / abins, abin = o % abins;
+    const int bin = ROWSPLIT ? ph_own * PW + abin : abin;
     const int ph = bin / PW, pw = bin % PW;
     const bool empty = bin_hi(ph, g.bin_h, g.sh, Hf) <= bin_lo(ph, g.bin_h, g.sh, Hf) ||
                        bin_hi(pw, g.bin_w, g.sw, Wf) <= bin_lo(pw, g.bin_w, g.sw, Wf);
     float m = -FLT_MAX;
     int mi = -1;
-    for (int w = 0; w < ROI_WARPS; ++w) {
-      const float v = acc[(w * nbins + bin) * ROI_CB + c];
+    for (int w = 0; w < NW; ++w) {
+      const float v = acc[(w * abins + abin) * ROI_CB + c];
       if (WITH_ARGMAX) {
-        const int vi = acc_i[(w * nbins + bin) * ROI_CB + c];
+        const int vi = acc_i[(w * abins + abin) * ROI_CB + c];
         if (vi >= 0 && (mi < 0 || v > m || (v == m && vi < mi))) { m = v; mi = vi; }
       } else {
         m = fmaxf(m, v);
@@ -334,17 +342,20 @@ extern "C" int cova_roi_fwd(const float* fm, int B, int Hf, int Wf, int C, const
       roi_align_kernel<0><<<grid, ROI_THREADS, 0, st>>>(fm, Hf, Wf, C, rois, T, PH, PW, spatial_scale, sampling_ratio,
                                                        out, ld_out);
   } else {
-    const size_t one = (size_t)ROI_WARPS * PH * PW * ROI_CB * 4;
+    const bool rowsplit = knob(COVA_KNOB_ROI_ROWSPLIT, 1) != 0 && (int64_t)T * PH < (1LL << 31);
+    const size_t one = rowsplit ? (size_t)ROI_SPLIT_WARPS * PW * ROI_CB * 4 : (size_t)ROI_WARPS * PH * PW * ROI_CB * 4;
     const size_t smem = argmax ? 2 * one : one;
     COVA_REQUIRE(smem <= (size_t)max_smem_optin(), "cova_roi_fwd: P=%dx%d needs %zu B of shared memory", PH, PW, smem);
-    dim3 grid(T, C / ROI_CB);
-    if (argmax) {
-      COVA_CUDA_OK(cudaFuncSetAttribute(roi_pool_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      roi_pool_kernel<true><<<grid, ROI_THREADS, smem, st>>>(fm, Hf, Wf, C, rois, PH, PW, spatial_scale, out, ld_out, argmax);
-    } else {
-      COVA_CUDA_OK(cudaFuncSetAttribute(roi_pool_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      roi_pool_kernel<false><<<grid, ROI_THREADS, smem, st>>>(fm, Hf, Wf, C, rois, PH, PW, spatial_scale, out, ld_out, argmax);
-    }
+    dim3 grid(rowsplit ? T * PH : T, C / ROI_CB);
+    const int threads = rowsplit ? ROI_SPLIT_WARPS * 32 : ROI_THREADS;
+#define ROI_GO(AM, RS)                                                                                                   \
+  do {                                                                                                                   \
+    COVA_CUDA_OK(cudaFuncSetAttribute(roi_pool_kernel<AM, RS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    roi_pool_kernel<AM, RS><<<grid, threads, smem, st>>>(fm, Hf, Wf, C, rois, PH, PW, spatial_scale, out, ld_out, argmax); \
+  } while (0)
+    if (argmax) { if (rowsplit) ROI_GO(true, true); else ROI_GO(true, false); }
+    else        { if (rowsplit) ROI_GO(false, true); else ROI_GO(false, false); }
+#undef ROI_GO
   }
   COVA_LAUNCH_OK();
   return COVA_OK;

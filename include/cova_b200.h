@@ -51,11 +51,12 @@ int cova_device_info(int* sm_count, int* max_smem_optin);
  *   COVA_KNOB_STEM_L2_PREFETCH   stem: image rows ahead to L2-prefetch (0 = off)
  *   COVA_KNOB_STEM_CONVERTERS    stem: converter warps per CTA (4 or 8)
  *   COVA_KNOB_CONV_RES_LOAD      3x3 conv residual loads: 0 = ld.global.nc, 1 = ld.global, 2 = L1::no_allocate
+ *   COVA_KNOB_ROI_ROWSPLIT       RoIPool: 1 = one CTA per (box, row bin) (default), 0 = one CTA per box
  * cova_debug_buffer: a caller-owned device array of uint64 words; kernels that support it (the 3x3 tensor-core conv:
  *   8 words per CTA = cycles the MMA issuer waited for operands / for a free accumulator, the TMA producer for a free
  *   ring slot, epilogue warp 2 for a finished accumulator, CTA total, tiles) add their counters.  NULL disables. */
 enum { COVA_KNOB_CONV_L2_PREFETCH = 0, COVA_KNOB_CONV_RES_PREFETCH = 1, COVA_KNOB_STEM_L2_PREFETCH = 2,
-       COVA_KNOB_STEM_CONVERTERS = 5, COVA_KNOB_CONV_RES_LOAD = 6, COVA_KNOB_COUNT = 8 };
+       COVA_KNOB_STEM_CONVERTERS = 5, COVA_KNOB_CONV_RES_LOAD = 6, COVA_KNOB_ROI_ROWSPLIT = 7, COVA_KNOB_COUNT = 8 };
 int cova_set_knob(int id, int value);
 int cova_debug_buffer(void* dev_words, int64_t n_words);
 

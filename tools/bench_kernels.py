@@ -43,8 +43,11 @@ for (B, N, K, C, tag) in [(16, 90, 24, 64, "config 2 (B=16, N=90, K=24, C=64)"),
     fm = torch.randn(B, 320, 320, C, device=dev)
     bb = bboxes.to(dev)
     out = torch.empty((T, C * 9 + 416), device=dev)
-    ms = timeit(lambda: ops.roi_fwd(fm, bb, (3, 3), 0.25, out))
-    report(f"RoIPool   {tag}", ms, bench.roi_bytes(bboxes, C=C))
+    for rs in (0, 1):
+        ops.set_knob("roi_rowsplit", rs)
+        ms = timeit(lambda: ops.roi_fwd(fm, bb, (3, 3), 0.25, out))
+        report(f"RoIPool rowsplit={rs}  {tag}", ms, bench.roi_bytes(bboxes, C=C))
+    ops.set_knob("roi_rowsplit", -1)
     ms = timeit(lambda: ops.roi_fwd(fm, bb, (3, 3), 0.25, out, mode="align"))
     report(f"RoIAlign  {tag}", ms, T * 9 * 4 * 4 * C * 4 + T * C * 9 * 4)
     for heads in (1, 2):
