@@ -144,3 +144,36 @@ def test_native_tail_trains_like_torch_tail():
         d = (p - q).abs()
         assert float((d > 2e-4 + 5e-3 * float(p.abs().max())).float().mean()) < 2e-3, n
         assert float(d.mean()) < 2e-5 + 1e-3 * float(p.abs().mean()), n
+
+
+def test_batched_attention_export_matches_page_at_a_time(tmp_path):
+    """N4: `cova_b200.attn_export` on a batch of 3 ragged pages writes, per page, the csv the reference script
+    (`extract_attn_wts_and_visualize.py:89-150`, restated here page at a time with the oracle's GAT) would write."""
+    from cova_b200.attn_export import export_attention
+    from cova_b200.models import CoVA
+    from oracle import cova_oracle as O
+    model = CoVA((3, 3), 128, 4, True, 384, 32, 0, 0.2, None, pretrained=False)
+    sd = synth.make_state_dict(123)
+    model.load_state_dict(sd, strict=True)
+    model = model.to(DEV).eval()
+    counts = [14, 5, 23]
+    images, bboxes, add, ci, labels = synth.gen(3, 0, 8, seed=21, img=128, counts=counts, with_labels=True)
+    files = export_attention(model, [(["a", "b", "c"], images, bboxes, add, ci, labels)], DEV, str(tmp_path))
+    nsd = {k: v.numpy() for k, v in sd.items()}
+    r0 = 0
+    for pi, n in enumerate(counts):                     # the reference loop: batch of ONE page, page-local ids
+        bb = bboxes[r0:r0 + n].clone(); bb[:, 0] = 0
+        cl = ci[r0:r0 + n].clone(); cl[cl >= 0] -= r0
+        lab = labels[r0:r0 + n].numpy()
+        out = O.cova_forward(nsd, images[pi:pi + 1].numpy(), bb.numpy(), add[r0:r0 + n].numpy(), cl.numpy(),
+                             return_intermediates=True)
+        coords = bb[:, 1:].numpy().copy(); coords[:, 2:] -= coords[:, :2]
+        padded = np.concatenate((coords, np.zeros((1, 4), np.float32)))
+        ctx_coords = padded[cl.numpy().reshape(-1)].reshape(n, -1)
+        _, attn = O.gat(out["own"], cl.numpy(), nsd["gat.W_i.weight"], nsd["gat.W_j.weight"],
+                        nsd["gat.attention_layer.weight"], nsd["gat.attention_layer.bias"], return_attn_wts=True)
+        want = np.concatenate((coords, lab.reshape(-1, 1).astype(np.float32), ctx_coords, attn), 1)[lab > 0]
+        got = np.loadtxt(files[pi], delimiter=",", ndmin=2)
+        assert got.shape == want.shape == (3, 5 + 8 * 4 + 8)
+        assert np.abs(got - want).max() <= 1.01e-3       # both rounded to 3 decimals by the csv format
+        r0 += n
