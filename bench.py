@@ -267,6 +267,23 @@ def main():
     reps_u8 = [timed(lambda k: run_e2e(k, pinned_u8), args.steps, whole=True) for _ in range(2)]
     ms_e2e_u8 = min(reps_u8)
 
+    # side measurement (not the headline): the one-product fp16 mode on the same inputs - logits within 5-7e-4 of the
+    # live-reference fixtures (profiles/r01l_precision_modes.txt), i.e. inside the 1e-3 bar but without the 50x margin
+    # of the fp32-parity mode that `value` is measured in
+    ms_fp16 = None
+    if model.engine == "tcgen05" and model.precision == "fp32" and model.backbone == "resnet18":
+        os.environ["COVA_B200_PRECISION"] = "fp16"
+        m16 = build_model(dev)
+        os.environ["COVA_B200_PRECISION"] = "fp32"
+
+        def step16():
+            with torch.no_grad():
+                return m16(*dinp)
+        for _ in range(args.warmup):
+            step16()
+        ms_fp16 = timed(step16, args.steps)
+        del m16
+
     pages = B_PER_GPU * world * args.steps
     value, e2e = pages / (ms / 1e3), pages / (ms_e2e / 1e3)
     if rank != 0:
@@ -353,6 +370,10 @@ def main():
                              "ms_per_step": ms_e2e_u8 / args.steps,
                              "reps_ms_per_step": [round(r / args.steps, 4) for r in reps_u8],
                              "note": "optional input format (SURVEY 8(f) N1): uint8 pixels, v/255 in the stem kernel"},
+        "throughput_mode_fp16": None if ms_fp16 is None else {
+            "value": pages / (ms_fp16 / 1e3), "unit": "pages/s", "ms_per_step": ms_fp16 / args.steps,
+            "note": "precision='fp16' (one fp16 product per MMA): max rel. error of the logits vs the live-reference "
+                    "fixtures 5-7e-4 (bar 1e-3); side measurement, not the headline"},
         "roofline": roofline, "kernels": kernels,
         "cpu_baseline": {"value": cpu_v, "unit": "pages/s", "cores": cores, "kind": "port", "sample": sample},
     }))
