@@ -203,6 +203,8 @@ def main():
     from cova_b200 import ops
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    from cova_b200.pipeline import bind_to_gpu_numa
+    numa_cores = bind_to_gpu_numa(local) if world > 1 else None     # pinned buffers on the GPU's own NUMA node
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
@@ -359,6 +361,7 @@ def main():
                    "engine": model.engine, "precision": model.precision, "backbone": model.backbone,
                    "boxes_per_page": N_BOXES, "neighbours": K_CTX, "gat_heads": N_HEADS,
                    "headline": (B_PER_GPU, N_BOXES, K_CTX, N_HEADS, model.backbone) == (16, 90, 24, 1, "resnet18"),
+                   "cpu_affinity": None if numa_cores is None else "%d cores local to the GPU (NVML)" % len(numa_cores),
                    "l2": "inputs larger than L2 (315 MB of images per step vs 126 MB L2); no flush needed"},
         "clocks": clocks, "gpu_launches": launches,
         "e2e": {"value": e2e, "unit": "pages/s", "h2d_bytes_per_step": h2d,

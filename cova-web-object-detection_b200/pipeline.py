@@ -7,7 +7,30 @@ than the forward itself, so the copy of batch i+1 must overlap the compute of ba
 buffers and copied on a side stream one batch ahead; the consumer's stream waits on the copy's event, so results
 are identical to the synchronous `.to(device)` calls.  Optional - the stock loop keeps working without it.
 """
+import os
+
 import torch
+
+
+def bind_to_gpu_numa(device_index):
+    """Pin this process to the CPU cores NVML reports as local to GPU `device_index` (one process per GPU): pinned
+    host buffers are then first-touched on the GPU's own NUMA node, so on a two-socket box the host->device copies
+    of 8 ranks do not cross the inter-socket link.  Returns the core list, or None when NVML / affinity is unavailable
+    (nothing changes then).  Call it before allocating pinned memory."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(int(device_index))
+        n_words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, n_words)
+        cores = [64 * w + b for w, m in enumerate(mask) for b in range(64) if (int(m) >> b) & 1]
+        cores = [c for c in cores if c in os.sched_getaffinity(0)]
+        if cores:
+            os.sched_setaffinity(0, cores)
+            return cores
+    except Exception:
+        pass
+    return None
 
 
 class _Slot:

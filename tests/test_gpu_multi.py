@@ -60,6 +60,34 @@ dist.all_gather(gathered, got)
 same = all(torch.equal(g, gathered[0]) for g in gathered)
 print(f"RANK {rank} inference_ok={ok_inf} grad_rel_err={err:.2e} identical_across_ranks={same} n={got.numel()}", flush=True)
 assert ok_inf and err < 1e-4 and same and got.numel() == 1616485
+# ---- native tail, data parallel: shard gradient -> all-reduce(SUM) of FlatAdam's bucket -> ONE Adam launch per rank;
+#      every rank must hold the parameters a single process gets from the summed gradient
+from cova_b200.train_ops import CrossEntropyLossSum, FlatAdam
+m = model().eval()
+opt = FlatAdam(m.parameters(), lr=5e-4, weight_decay=1e-3)
+ncrit = CrossEntropyLossSum()
+opt.zero_grad()
+with torch.enable_grad():
+    ncrit(m(*[t.to(dev) for t in sh[:4]]), sh[4].to(dev)).backward()
+opt.allreduce_grads()
+opt.step()
+ref = model().eval()
+ropt = torch.optim.Adam(ref.parameters(), lr=5e-4, weight_decay=1e-3)
+ropt.zero_grad()
+with torch.enable_grad():
+    for r in range(world):
+        s = shard_batch(*batch, rank=r, world=world)
+        crit(ref(*[t.to(dev) for t in s[:4]]), s[4].to(dev)).backward()
+ropt.step()
+flat = opt._flat[0]["p"][:opt._flat[0]["n"]]
+ref_flat = torch.cat([p.detach().reshape(-1) for p in ref.parameters()])
+moved = float((ref_flat - torch.cat([p.detach().reshape(-1) for p in model().parameters()])).abs().max())
+bad = float(((flat - ref_flat).abs() > 1e-4).float().mean())          # elements whose gradient is atomics-order noise
+gathered = [torch.empty_like(flat) for _ in range(world)]
+dist.all_gather(gathered, flat.contiguous())
+same_p = all(torch.equal(g, gathered[0]) for g in gathered)
+print(f"RANK {rank} flat_adam moved={moved:.2e} frac_off={bad:.2e} params_identical_across_ranks={same_p}", flush=True)
+assert moved > 1e-4 and bad < 2e-3 and same_p
 dist.destroy_process_group()
 '''
 
@@ -74,3 +102,4 @@ def test_two_rank_nccl_sharding_and_grad_allreduce(tmp_path):
     print(r.stdout[-2000:])
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert r.stdout.count("inference_ok=True") == 2
+    assert r.stdout.count("params_identical_across_ranks=True") == 2
