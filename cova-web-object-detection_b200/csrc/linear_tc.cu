@@ -123,15 +123,18 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_const
     const int ct = threadIdx.x - 64;                 // 0..127
     const int c = ct & 15, r0 = ct >> 4;             // 16-byte fp32 chunk c of rows r0 + 8j
     uint32_t stage = 0, phase = 0;
-    for (int kb = 0; kb < nkb; ++kb) {
+    // Register double buffering: the loads of k-block kb+1 are in flight while k-block kb is converted (with one
+    // block in flight the kernel was a chain of 10-16 exposed L2 round trips).
+    auto load_tile = [&](int kb, float4(&v)[16]) {
       const int k = kb * LT_BK + c * 4;
-      float4 v[16];
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
         const int m = m0 + r0 + 8 * j;
         v[j] = (m < p.M && k < p.K) ? __ldg(reinterpret_cast<const float4*>(p.x + (size_t)m * p.ldx + k))
                                     : make_float4(0.f, 0.f, 0.f, 0.f);
       }
+    };
+    auto convert_tile = [&](const float4(&v)[16]) {
       ptx::mbar_wait(&tail.empty[stage], phase ^ 1);
       unsigned char* sa = smem + stage * LT_STAGE_BYTES;
 #pragma unroll
@@ -148,6 +151,16 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_const
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&tail.a_full[stage]);
       if (++stage == LT_STAGES) { stage = 0; phase ^= 1; }
+    };
+    float4 va[16], vb[16];
+    load_tile(0, va);
+    for (int kb = 0; kb < nkb; kb += 2) {
+      if (kb + 1 < nkb) load_tile(kb + 1, vb);
+      convert_tile(va);
+      if (kb + 1 < nkb) {
+        if (kb + 2 < nkb) load_tile(kb + 2, va);
+        convert_tile(vb);
+      }
     }
     // ---------------- epilogue (same warps): TMEM lane group = warp % 4 ----------------
     const int lg = warp & 3;
