@@ -358,6 +358,44 @@ stem_tc_kernel(const StemTcParams p) {
             }
           }
         }
+      } else if (!U8 && (p.W & 3) == 0 && (reinterpret_cast<uintptr_t>(p.img) & 15) == 0) {
+        // fp32 fast path: x0 - 1 is a multiple of 4, so the row segment is 67 aligned float4 per channel
+        // (9 x LDG.128 per lane instead of 27 x LDG.32 - the converters were what the MMA issuer waited for)
+        const float* imgf = reinterpret_cast<const float*>(p.img) + img_b;
+        float4 fv[3][3];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          const int wi = lane + 32 * j, xw = x0 - 1 + 4 * wi;
+          const bool ok = row_ok && wi < 67 && xw >= 0 && xw < p.W;
+#pragma unroll
+          for (int c = 0; c < 3; ++c)
+            fv[j][c] = ok ? __ldg(reinterpret_cast<const float4*>(imgf + c * plane + (size_t)y * p.W + xw))
+                          : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          const int wi = lane + 32 * j;
+          if (wi < 67) {
+            const float* c0 = &fv[j][0].x;
+            const float* c1 = &fv[j][1].x;
+            const float* c2 = &fv[j][2].x;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const int i = 4 * wi + k - 1;                 // pixel index in the ring row
+              if (i >= 0 && i < SX_NPX) {
+                uint32_t h01, l01, h2, l2;
+                if (HALF) {
+                  h01 = pack2_f16(c0[k], c1[k]); h2 = pack2_f16(c2[k], 0.f); l01 = l2 = 0u;
+                } else {
+                  split_bf16x2(c0[k], c1[k], h01, l01);
+                  split_bf16x2(c2[k], 0.f, h2, l2);
+                }
+                *reinterpret_cast<uint2*>(dst_hi + i * 8) = make_uint2(h01, h2);
+                if (SPLIT) *reinterpret_cast<uint2*>(dst_hi + SX_R * SX_ROW_BYTES + i * 8) = make_uint2(l01, l2);
+              }
+            }
+          }
+        }
       } else {
         float f[9][3];
 #pragma unroll

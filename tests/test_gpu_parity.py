@@ -74,10 +74,11 @@ def test_stem_kernel(out_dtype):
 
 
 @pytest.mark.parametrize("out_dtype", ["f32", "bf16x2", "bf16", "f16"])
-@pytest.mark.parametrize("B,H", [(2, 104), (1, 260), (3, 64)])
+@pytest.mark.parametrize("B,H", [(2, 104), (1, 260), (3, 64), (1, 102)])
 def test_stem_tcgen05_kernel(out_dtype, B, H):
     """Tensor-core stem (ring of raw image rows + sliding-window descriptors + fused pooling) vs the oracle.
-    Sizes: partial strips/bands (104), two strips (260 -> 130 conv columns), more pages than bands (3 x 64)."""
+    Sizes: partial strips/bands (104), two strips (260 -> 130 conv columns), more pages than bands (3 x 64), a width
+    that is not a multiple of 4 (102: the scalar converter path instead of the float4 one)."""
     o = ops()
     g = torch.Generator().manual_seed(1)
     img = torch.rand(B, 3, H, H, generator=g)
