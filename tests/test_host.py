@@ -169,3 +169,14 @@ def test_grad_allreduce_sum_world2_gloo(tmp_path):
         gs = torch.autograd.grad(loss, list(lin.parameters()))
         tot += torch.cat([g.flatten() for g in gs])
     assert torch.allclose(g0, tot, rtol=1e-5, atol=1e-6)
+
+
+def test_native_tail_fails_loudly_on_cpu_tensors():
+    """The callers either side of the forward have no CPU path either: criterion and optimizer raise on CPU inputs."""
+    import pytest as _pytest
+    import torch
+    from cova_b200.train_ops import CrossEntropyLossSum, FlatAdam
+    with _pytest.raises(RuntimeError, match="CUDA"):
+        CrossEntropyLossSum()(torch.zeros(3, 4), torch.zeros(3, dtype=torch.long))
+    with _pytest.raises(RuntimeError, match="CUDA"):
+        FlatAdam([torch.nn.Parameter(torch.zeros(5))], lr=1e-3)
