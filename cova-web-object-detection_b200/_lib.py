@@ -63,6 +63,7 @@ SIGNATURES = {
     "cova_conv1x1_bn_act_fwd": (_I, [_P, _P, _L, _I, _I, _P, _P, _P, _P, _P, _I, _I, _P, _P, _P]),
     "cova_pack_conv_weight": (_I, [_P, _I, _I, _I, _I, _P, _P, _P, _P]),
     "cova_pack_stem_weight": (_I, [_P, _P, _P]),
+    "cova_stem_conv_raw_fwd": (_I, [_P, _I, _I, _I, _I, _P, _P, _P]),
     "cova_pack_stem_weight_f16": (_I, [_P, _P, _P]),
     "cova_pack_conv_weight_f16": (_I, [_P, _I, _I, _I, _I, _P, _P]),
     "cova_roi_fwd": (_I, [_P, _I, _I, _I, _I, _P, _I, _I, _I, _F, _I, _I, _P, _L, _P, _P]),
@@ -78,6 +79,13 @@ SIGNATURES = {
     "cova_adam_step": (_I, [_P, _P, _P, _P, _L, _D, _D, _D, _D, _D, _I, _D, _P]),
     "cova_topk_hits": (_I, [_P, _L, _P, _P, _I, _I, _I, _P, _P]),
     "cova_build_batch": (_I, [_P, _I, _I, _I, _P, _P, _P, _P]),
+    "cova_bn_train_stats": (_I, [_P, _L, _I, _P, _P]),
+    "cova_bn_train_finalize": (_I, [_P, _L, _I, _F, _F, _P, _P, _P, _P, _P]),
+    "cova_bn_act_fwd": (_I, [_P, _L, _I, _P, _P, _P, _P, _P, _I, _P, _P, _P, _P]),
+    "cova_split_planes": (_I, [_P, _L, _P, _P, _P]),
+    "cova_bn_act_bwd": (_I, [_P, _P, _P, _L, _I, _P, _P, _P, _P, _I, _P, _P, _P, _P, _P, _P]),
+    "cova_maxpool3x3s2_fwd": (_I, [_P, _I, _I, _I, _I, _P, _P, _P, _P, _P]),
+    "cova_maxpool3x3s2_bwd": (_I, [_P, _P, _I, _I, _I, _I, _P, _P]),
 }
 
 _lib = None

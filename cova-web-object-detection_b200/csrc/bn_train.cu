@@ -1,0 +1,359 @@
+// A2 / A9, training mode: BatchNorm2d with BATCH statistics (+ residual) (+ ReLU), forward and backward, and the
+// stem's maxpool 3x3 s2 p1 forward / backward, on NHWC fp32 maps.  Replaces, on the autograd path
+// (`/root/reference/train.py:45-60`), what torchvision's `BasicBlock.forward` / `Bottleneck.forward` run through
+// `nn.BatchNorm2d` in `model.train()` (`models.py:49-51`, `train.py:27`): biased batch variance over (B,H,W) per
+// channel, eps 1e-5, running statistics updated with momentum 0.1 (unbiased variance) - SURVEY.md row A2.
+// Profiled motivation (tools/prof_train.py): cuDNN's NCHW spatial-BN kernels were 29 ms of a 61 ms train step and
+// `max_pool_backward_nchw` another 4.4 ms; these are plain HBM-bound passes:
+//   forward : reduce (sum x, sum x^2)  ->  finalize (mean, 1/sqrt(var+eps), running stats)  ->  apply (+res)(+ReLU)
+//   backward: reduce (sum g, sum g*xhat), g = dy * [y > 0]  ->  apply dx = gamma*inv*(g - S1/M - xhat*S2/M), dres = g
+// Layout: x [M = B*H*W pixels][C channels], C a power of two in [4, 1024]; a thread owns one float4 channel group and
+// strides over pixels, so every warp load is 512 contiguous bytes.  Partial sums are fp32 per thread (a few hundred
+// values), combined in double (smem tree + one double atomic per channel and CTA): var = E[x^2] - mean^2 is evaluated
+// in double.
+#include <float.h>
+
+#include "common.cuh"
+
+namespace cova {
+
+constexpr int BN_THREADS = 256;
+
+__device__ __forceinline__ float bn_val(float x, float mean, float inv, float g, float b) {
+  return (x - mean) * inv * g + b;     // torch: (x - mean) * invstd * weight + bias
+}
+
+// MODE 0: a = sum x, b = sum x^2.   MODE 1: a = sum g, b = sum g * xhat with g = dy * [y > 0] (y recomputed).
+template <int MODE>
+__global__ void __launch_bounds__(BN_THREADS)
+bn_reduce_kernel(const float* __restrict__ x, const float* __restrict__ dy, const float* __restrict__ res, int64_t M,
+                 int C, const float* __restrict__ mean, const float* __restrict__ invstd,
+                 const float* __restrict__ gamma, const float* __restrict__ beta, int relu, double* __restrict__ ws) {
+  extern __shared__ __align__(16) float red[];                       // [2][rows][C]
+  const int c4n = C >> 2, rows = BN_THREADS / c4n;
+  const int cg = threadIdx.x % c4n, prow = threadIdx.x / c4n;
+  const int c0 = 4 * cg;
+  float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+  float4 mu = a, iv = a, ga = a, be = a;
+  if (MODE == 1) {
+    mu = *reinterpret_cast<const float4*>(mean + c0);
+    iv = *reinterpret_cast<const float4*>(invstd + c0);
+    ga = *reinterpret_cast<const float4*>(gamma + c0);
+    be = *reinterpret_cast<const float4*>(beta + c0);
+  }
+  const int64_t stride = (int64_t)gridDim.x * rows;
+#pragma unroll 4
+  for (int64_t p = (int64_t)blockIdx.x * rows + prow; p < M; p += stride) {
+    const float4 xv = __ldg(reinterpret_cast<const float4*>(x + p * C + c0));
+    if (MODE == 0) {
+      a.x += xv.x; a.y += xv.y; a.z += xv.z; a.w += xv.w;
+      b.x = fmaf(xv.x, xv.x, b.x); b.y = fmaf(xv.y, xv.y, b.y); b.z = fmaf(xv.z, xv.z, b.z); b.w = fmaf(xv.w, xv.w, b.w);
+    } else {
+      float4 g = __ldg(reinterpret_cast<const float4*>(dy + p * C + c0));
+      const float4 xh = make_float4((xv.x - mu.x) * iv.x, (xv.y - mu.y) * iv.y, (xv.z - mu.z) * iv.z, (xv.w - mu.w) * iv.w);
+      if (relu) {
+        float4 y = make_float4(bn_val(xv.x, mu.x, iv.x, ga.x, be.x), bn_val(xv.y, mu.y, iv.y, ga.y, be.y),
+                               bn_val(xv.z, mu.z, iv.z, ga.z, be.z), bn_val(xv.w, mu.w, iv.w, ga.w, be.w));
+        if (res != nullptr) {
+          const float4 r = __ldg(reinterpret_cast<const float4*>(res + p * C + c0));
+          y.x += r.x; y.y += r.y; y.z += r.z; y.w += r.w;
+        }
+        g.x = y.x > 0.f ? g.x : 0.f; g.y = y.y > 0.f ? g.y : 0.f;
+        g.z = y.z > 0.f ? g.z : 0.f; g.w = y.w > 0.f ? g.w : 0.f;
+      }
+      a.x += g.x; a.y += g.y; a.z += g.z; a.w += g.w;
+      b.x = fmaf(g.x, xh.x, b.x); b.y = fmaf(g.y, xh.y, b.y); b.z = fmaf(g.z, xh.z, b.z); b.w = fmaf(g.w, xh.w, b.w);
+    }
+  }
+  float* ra = red + (size_t)prow * C + c0;
+  float* rb = red + (size_t)(rows + prow) * C + c0;
+  *reinterpret_cast<float4*>(ra) = a;
+  *reinterpret_cast<float4*>(rb) = b;
+  __syncthreads();
+  for (int c = threadIdx.x; c < 2 * C; c += BN_THREADS) {
+    const int which = c / C, ch = c % C;
+    double s = 0.0;
+    for (int r = 0; r < rows; ++r) s += (double)red[(size_t)(which * rows + r) * C + ch];
+    atomicAdd(ws + c, s);
+  }
+}
+
+// mean / invstd from the sums, running statistics like torch (momentum on the UNBIASED variance)
+__global__ void bn_finalize_kernel(const double* __restrict__ ws, int64_t M, int C, float eps, float momentum,
+                                   float* __restrict__ mean, float* __restrict__ invstd, float* __restrict__ rmean,
+                                   float* __restrict__ rvar) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const double m = ws[c] / (double)M;
+  double var = ws[C + c] / (double)M - m * m;
+  if (var < 0.0) var = 0.0;
+  mean[c] = (float)m;
+  invstd[c] = (float)(1.0 / sqrt(var + (double)eps));
+  if (rmean != nullptr) {
+    const double unb = M > 1 ? var * (double)M / (double)(M - 1) : var;
+    rmean[c] = (1.f - momentum) * rmean[c] + momentum * (float)m;
+    rvar[c] = (1.f - momentum) * rvar[c] + momentum * (float)unb;
+  }
+}
+
+__global__ void __launch_bounds__(BN_THREADS)
+bn_act_fwd_kernel(const float* __restrict__ x, int64_t n4, int C, const float* __restrict__ mean,
+                  const float* __restrict__ invstd, const float* __restrict__ gamma, const float* __restrict__ beta,
+                  const float* __restrict__ res, int relu, float* __restrict__ y, __nv_bfloat16* __restrict__ y_hi,
+                  __nv_bfloat16* __restrict__ y_lo) {
+  const int c4n = C >> 2;
+  for (int64_t i = (int64_t)blockIdx.x * BN_THREADS + threadIdx.x; i < n4; i += (int64_t)gridDim.x * BN_THREADS) {
+    const int c0 = 4 * (int)(i % c4n);
+    const float4 xv = __ldg(reinterpret_cast<const float4*>(x) + i);
+    const float4 mu = *reinterpret_cast<const float4*>(mean + c0), iv = *reinterpret_cast<const float4*>(invstd + c0);
+    const float4 ga = *reinterpret_cast<const float4*>(gamma + c0), be = *reinterpret_cast<const float4*>(beta + c0);
+    float4 o = make_float4(bn_val(xv.x, mu.x, iv.x, ga.x, be.x), bn_val(xv.y, mu.y, iv.y, ga.y, be.y),
+                           bn_val(xv.z, mu.z, iv.z, ga.z, be.z), bn_val(xv.w, mu.w, iv.w, ga.w, be.w));
+    if (res != nullptr) {
+      const float4 r = __ldg(reinterpret_cast<const float4*>(res) + i);
+      o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+    }
+    if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+    reinterpret_cast<float4*>(y)[i] = o;
+    if (y_hi != nullptr) {
+      uint32_t h01, l01, h23, l23;
+      split_bf16x2(o.x, o.y, h01, l01);
+      split_bf16x2(o.z, o.w, h23, l23);
+      *reinterpret_cast<uint2*>(y_hi + i * 4) = make_uint2(h01, h23);
+      *reinterpret_cast<uint2*>(y_lo + i * 4) = make_uint2(l01, l23);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(BN_THREADS)
+bn_act_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ res, int64_t n4,
+                  int64_t M, int C, const float* __restrict__ mean, const float* __restrict__ invstd,
+                  const float* __restrict__ gamma, const float* __restrict__ beta, int relu,
+                  const double* __restrict__ ws, float* __restrict__ dx, float* __restrict__ dres,
+                  float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  extern __shared__ __align__(16) float sums[];                      // [2][C]: S1/M, S2/M
+  const int c4n = C >> 2;
+  if (blockIdx.x == 0) {                               // parameter gradients: dbeta = S1, dgamma = S2
+    for (int c = threadIdx.x; c < C; c += BN_THREADS) {
+      if (dbeta != nullptr) dbeta[c] = (float)ws[c];
+      if (dgamma != nullptr) dgamma[c] = (float)ws[C + c];
+    }
+  }
+  for (int c = threadIdx.x; c < 2 * C; c += BN_THREADS) sums[c] = (float)(ws[c] / (double)M);
+  __syncthreads();
+  for (int64_t i = (int64_t)blockIdx.x * BN_THREADS + threadIdx.x; i < n4; i += (int64_t)gridDim.x * BN_THREADS) {
+    const int c0 = 4 * (int)(i % c4n);
+    const float4 xv = __ldg(reinterpret_cast<const float4*>(x) + i);
+    float4 g = __ldg(reinterpret_cast<const float4*>(dy) + i);
+    const float4 mu = *reinterpret_cast<const float4*>(mean + c0), iv = *reinterpret_cast<const float4*>(invstd + c0);
+    const float4 ga = *reinterpret_cast<const float4*>(gamma + c0), be = *reinterpret_cast<const float4*>(beta + c0);
+    const float4 xh = make_float4((xv.x - mu.x) * iv.x, (xv.y - mu.y) * iv.y, (xv.z - mu.z) * iv.z, (xv.w - mu.w) * iv.w);
+    if (relu) {
+      float4 y = make_float4(bn_val(xv.x, mu.x, iv.x, ga.x, be.x), bn_val(xv.y, mu.y, iv.y, ga.y, be.y),
+                             bn_val(xv.z, mu.z, iv.z, ga.z, be.z), bn_val(xv.w, mu.w, iv.w, ga.w, be.w));
+      if (res != nullptr) {
+        const float4 r = __ldg(reinterpret_cast<const float4*>(res) + i);
+        y.x += r.x; y.y += r.y; y.z += r.z; y.w += r.w;
+      }
+      g.x = y.x > 0.f ? g.x : 0.f; g.y = y.y > 0.f ? g.y : 0.f;
+      g.z = y.z > 0.f ? g.z : 0.f; g.w = y.w > 0.f ? g.w : 0.f;
+    }
+    if (dres != nullptr) reinterpret_cast<float4*>(dres)[i] = g;
+    const float4 s1 = *reinterpret_cast<const float4*>(sums + c0), s2 = *reinterpret_cast<const float4*>(sums + C + c0);
+    float4 o;
+    o.x = ga.x * iv.x * (g.x - s1.x - xh.x * s2.x);
+    o.y = ga.y * iv.y * (g.y - s1.y - xh.y * s2.y);
+    o.z = ga.z * iv.z * (g.z - s1.z - xh.z * s2.z);
+    o.w = ga.w * iv.w * (g.w - s1.w - xh.w * s2.w);
+    reinterpret_cast<float4*>(dx)[i] = o;
+  }
+}
+
+// ---------------------------------------------------------------- maxpool 3x3 s2 p1, NHWC
+// window of output (oh, ow): rows 2oh-1 .. 2oh+1, cols 2ow-1 .. 2ow+1 clipped to the map; scan order rows then
+// columns, first maximum wins (strict >) - torch's max_pool2d_with_indices rule, which decides where the gradient
+// goes.  The forward stores the winner's position inside the (unclipped) window as one byte per output element
+// (code = r*3 + s); the backward is a gather over the <= 2 x 2 windows that contain an input pixel: compare codes,
+// no rescans, no atomics.
+__device__ __forceinline__ void split4(const float4 v, __nv_bfloat16* hi, __nv_bfloat16* lo, size_t idx) {
+  uint32_t h01, l01, h23, l23;
+  split_bf16x2(v.x, v.y, h01, l01);
+  split_bf16x2(v.z, v.w, h23, l23);
+  *reinterpret_cast<uint2*>(hi + idx) = make_uint2(h01, h23);
+  *reinterpret_cast<uint2*>(lo + idx) = make_uint2(l01, l23);
+}
+
+__global__ void __launch_bounds__(256)
+maxpool_fwd_kernel(const float* __restrict__ x, int B, int H, int W, int C, int Ho, int Wo, float* __restrict__ y,
+                   unsigned char* __restrict__ code, __nv_bfloat16* __restrict__ y_hi, __nv_bfloat16* __restrict__ y_lo) {
+  const int c4n = C >> 2;
+  const int64_t n = (int64_t)B * Ho * Wo * c4n;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int cg = (int)(i % c4n);
+    const int64_t pix = i / c4n;
+    const int ow = (int)(pix % Wo), oh = (int)((pix / Wo) % Ho), b = (int)(pix / ((int64_t)Wo * Ho));
+    float4 m = make_float4(-FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX);
+    int4 mi = make_int4(-1, -1, -1, -1);
+    for (int r = 0; r < 3; ++r) {
+      const int h = 2 * oh - 1 + r;
+      if (h < 0 || h >= H) continue;
+      for (int s2 = 0; s2 < 3; ++s2) {
+        const int w = 2 * ow - 1 + s2;
+        if (w < 0 || w >= W) continue;
+        const float4 v = __ldg(reinterpret_cast<const float4*>(x + (((size_t)b * H + h) * W + w) * C) + cg);
+        const int k = r * 3 + s2;
+        if (v.x > m.x || mi.x < 0) { m.x = v.x; mi.x = k; }
+        if (v.y > m.y || mi.y < 0) { m.y = v.y; mi.y = k; }
+        if (v.z > m.z || mi.z < 0) { m.z = v.z; mi.z = k; }
+        if (v.w > m.w || mi.w < 0) { m.w = v.w; mi.w = k; }
+      }
+    }
+    reinterpret_cast<float4*>(y)[i] = m;
+    if (code != nullptr) reinterpret_cast<uchar4*>(code)[i] = make_uchar4(mi.x, mi.y, mi.z, mi.w);
+    if (y_hi != nullptr) split4(m, y_hi, y_lo, (size_t)i * 4);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+maxpool_bwd_kernel(const unsigned char* __restrict__ code, const float* __restrict__ dy, int B, int H, int W, int C, int Ho,
+                   int Wo, float* __restrict__ dx) {
+  const int c4n = C >> 2;
+  const int64_t n = (int64_t)B * H * W * c4n;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int cg = (int)(i % c4n);
+    const int64_t pix = i / c4n;
+    const int w0 = (int)(pix % W), h0 = (int)((pix / W) % H), b = (int)(pix / ((int64_t)W * H));
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int oh_hi = (h0 + 1) >> 1, ow_hi = (w0 + 1) >> 1;     // == h0 >> 1 for even h0: one window per axis
+    for (int oh = h0 >> 1; oh <= oh_hi; ++oh) {
+      if (oh >= Ho) continue;
+      for (int ow = w0 >> 1; ow <= ow_hi; ++ow) {
+        if (ow >= Wo) continue;
+        const int me = (h0 - (2 * oh - 1)) * 3 + (w0 - (2 * ow - 1));
+        const size_t o = (((size_t)b * Ho + oh) * Wo + ow) * c4n + cg;
+        const uchar4 k = __ldg(reinterpret_cast<const uchar4*>(code) + o);
+        const float4 g = __ldg(reinterpret_cast<const float4*>(dy) + o);
+        if (k.x == me) acc.x += g.x;
+        if (k.y == me) acc.y += g.y;
+        if (k.z == me) acc.z += g.z;
+        if (k.w == me) acc.w += g.w;
+      }
+    }
+    reinterpret_cast<float4*>(dx)[i] = acc;
+  }
+}
+
+// fp32 -> split-bf16 planes (hi = bf16(x), lo = bf16(x - hi)): the operand format of the tensor-core convolutions
+__global__ void __launch_bounds__(256)
+split_planes_kernel(const float* __restrict__ x, int64_t n4, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x)
+    split4(__ldg(reinterpret_cast<const float4*>(x) + i), hi, lo, (size_t)i * 4);
+}
+
+static bool bn_c_ok(int C) { return C >= 4 && C <= 1024 && (C & (C - 1)) == 0; }
+static int ew_grid(int64_t n, int threads) {
+  int64_t b = (n + threads - 1) / threads;
+  const int64_t cap = (int64_t)sm_count() * 16;
+  return (int)(b < cap ? (b > 0 ? b : 1) : cap);
+}
+
+}  // namespace cova
+
+using namespace cova;
+
+extern "C" int cova_bn_train_stats(const float* x, int64_t M, int C, double* ws, void* stream) {
+  COVA_REQUIRE(x && ws && M > 0, "cova_bn_train_stats: bad arguments");
+  COVA_REQUIRE(bn_c_ok(C), "cova_bn_train_stats: C=%d must be a power of two in [4, 1024]", C);
+  COVA_REQUIRE(((uintptr_t)x & 15) == 0, "cova_bn_train_stats: x must be 16-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  COVA_CUDA_OK(cudaMemsetAsync(ws, 0, 2 * C * sizeof(double), st));
+  const int rows = BN_THREADS / (C / 4);
+  const size_t smem = (size_t)2 * rows * C * sizeof(float);
+  int64_t grid = (M + rows - 1) / rows;
+  if (grid > (int64_t)sm_count() * 8) grid = (int64_t)sm_count() * 8;
+  bn_reduce_kernel<0><<<(int)grid, BN_THREADS, smem, st>>>(x, nullptr, nullptr, M, C, nullptr, nullptr, nullptr, nullptr, 0,
+                                                           ws);
+  COVA_LAUNCH_OK();
+  return COVA_OK;
+}
+
+extern "C" int cova_bn_train_finalize(const double* ws, int64_t M, int C, float eps, float momentum, float* mean,
+                                      float* invstd, float* running_mean, float* running_var, void* stream) {
+  COVA_REQUIRE(ws && mean && invstd && M > 0 && C > 0, "cova_bn_train_finalize: bad arguments");
+  COVA_REQUIRE((running_mean == nullptr) == (running_var == nullptr), "cova_bn_train_finalize: running stats come together");
+  bn_finalize_kernel<<<ceil_div(C, 128), 128, 0, (cudaStream_t)stream>>>(ws, M, C, eps, momentum, mean, invstd, running_mean,
+                                                                        running_var);
+  COVA_LAUNCH_OK();
+  return COVA_OK;
+}
+
+extern "C" int cova_bn_act_fwd(const float* x, int64_t M, int C, const float* mean, const float* invstd,
+                               const float* gamma, const float* beta, const float* res, int relu, float* y,
+                               void* y_hi, void* y_lo, void* stream) {
+  COVA_REQUIRE(x && y && mean && invstd && gamma && beta && M > 0, "cova_bn_act_fwd: bad arguments");
+  COVA_REQUIRE(bn_c_ok(C), "cova_bn_act_fwd: C=%d must be a power of two in [4, 1024]", C);
+  COVA_REQUIRE((((uintptr_t)x | (uintptr_t)y | (uintptr_t)res | (uintptr_t)y_hi | (uintptr_t)y_lo) & 15) == 0,
+               "cova_bn_act_fwd: 16-byte alignment");
+  COVA_REQUIRE((y_hi == nullptr) == (y_lo == nullptr), "cova_bn_act_fwd: the split planes come together");
+  const int64_t n4 = M * (C / 4);
+  bn_act_fwd_kernel<<<ew_grid(n4, BN_THREADS), BN_THREADS, 0, (cudaStream_t)stream>>>(x, n4, C, mean, invstd, gamma, beta,
+                                                                                     res, relu, y, (__nv_bfloat16*)y_hi,
+                                                                                     (__nv_bfloat16*)y_lo);
+  COVA_LAUNCH_OK();
+  return COVA_OK;
+}
+
+extern "C" int cova_bn_act_bwd(const float* dy, const float* x, const float* res, int64_t M, int C, const float* mean,
+                               const float* invstd, const float* gamma, const float* beta, int relu, double* ws,
+                               float* dx, float* dres, float* dgamma, float* dbeta, void* stream) {
+  COVA_REQUIRE(dy && x && dx && ws && mean && invstd && gamma && beta && M > 0, "cova_bn_act_bwd: bad arguments");
+  COVA_REQUIRE(bn_c_ok(C), "cova_bn_act_bwd: C=%d must be a power of two in [4, 1024]", C);
+  COVA_REQUIRE((((uintptr_t)dy | (uintptr_t)x | (uintptr_t)res | (uintptr_t)dx | (uintptr_t)dres) & 15) == 0,
+               "cova_bn_act_bwd: 16-byte alignment");
+  cudaStream_t st = (cudaStream_t)stream;
+  COVA_CUDA_OK(cudaMemsetAsync(ws, 0, 2 * C * sizeof(double), st));
+  const int rows = BN_THREADS / (C / 4);
+  const size_t smem = (size_t)2 * rows * C * sizeof(float);
+  int64_t grid = (M + rows - 1) / rows;
+  if (grid > (int64_t)sm_count() * 8) grid = (int64_t)sm_count() * 8;
+  bn_reduce_kernel<1><<<(int)grid, BN_THREADS, smem, st>>>(x, dy, res, M, C, mean, invstd, gamma, beta, relu, ws);
+  COVA_LAUNCH_OK();
+  const int64_t n4 = M * (C / 4);
+  bn_act_bwd_kernel<<<ew_grid(n4, BN_THREADS), BN_THREADS, 2 * C * sizeof(float), st>>>(dy, x, res, n4, M, C, mean, invstd, gamma, beta, relu, ws,
+                                                                    dx, dres, dgamma, dbeta);
+  COVA_LAUNCH_OK();
+  return COVA_OK;
+}
+
+extern "C" int cova_maxpool3x3s2_fwd(const float* x, int B, int H, int W, int C, float* y, unsigned char* code, void* y_hi,
+                                     void* y_lo, void* stream) {
+  COVA_REQUIRE(x && y && B > 0 && H > 0 && W > 0 && C > 0 && C % 4 == 0, "cova_maxpool3x3s2_fwd: bad arguments");
+  COVA_REQUIRE((((uintptr_t)x | (uintptr_t)y | (uintptr_t)y_hi | (uintptr_t)y_lo) & 15) == 0 && ((uintptr_t)code & 3) == 0,
+               "cova_maxpool3x3s2_fwd: alignment");
+  COVA_REQUIRE((y_hi == nullptr) == (y_lo == nullptr), "cova_maxpool3x3s2_fwd: the split planes come together");
+  const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
+  const int64_t n = (int64_t)B * Ho * Wo * (C / 4);
+  maxpool_fwd_kernel<<<ew_grid(n, 256), 256, 0, (cudaStream_t)stream>>>(x, B, H, W, C, Ho, Wo, y, code, (__nv_bfloat16*)y_hi,
+                                                                        (__nv_bfloat16*)y_lo);
+  COVA_LAUNCH_OK();
+  return COVA_OK;
+}
+
+extern "C" int cova_maxpool3x3s2_bwd(const unsigned char* code, const float* dy, int B, int H, int W, int C, float* dx,
+                                     void* stream) {
+  COVA_REQUIRE(code && dy && dx && B > 0 && H > 0 && W > 0 && C > 0 && C % 4 == 0, "cova_maxpool3x3s2_bwd: bad arguments");
+  COVA_REQUIRE((((uintptr_t)dy | (uintptr_t)dx) & 15) == 0 && ((uintptr_t)code & 3) == 0, "cova_maxpool3x3s2_bwd: alignment");
+  const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
+  const int64_t n = (int64_t)B * H * W * (C / 4);
+  maxpool_bwd_kernel<<<ew_grid(n, 256), 256, 0, (cudaStream_t)stream>>>(code, dy, B, H, W, C, Ho, Wo, dx);
+  COVA_LAUNCH_OK();
+  return COVA_OK;
+}
+
+extern "C" int cova_split_planes(const float* x, int64_t n, void* hi, void* lo, void* stream) {
+  COVA_REQUIRE(x && hi && lo && n > 0 && n % 4 == 0, "cova_split_planes: n must be a positive multiple of 4");
+  COVA_REQUIRE((((uintptr_t)x & 15) | ((uintptr_t)hi & 7) | ((uintptr_t)lo & 7)) == 0, "cova_split_planes: alignment");
+  split_planes_kernel<<<ew_grid(n / 4, 256), 256, 0, (cudaStream_t)stream>>>(x, n / 4, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo);
+  COVA_LAUNCH_OK();
+  return COVA_OK;
+}

@@ -65,6 +65,7 @@ struct StemTcParams {
   const float* bn_shift;
   void* out0;
   void* out1;
+  float* raw_out;                          // training mode: un-normalised, un-pooled conv output [B,Hc,Wc,64] fp32 (or NULL)
   unsigned long long* dbg;                 // optional wait-cycle counters (cova_debug_buffer), 8 words per CTA
   int pf_rows;                             // converter warps L2-prefetch the image row they will load this many turns ahead
 };
@@ -99,8 +100,8 @@ stem_tc_kernel(const StemTcParams p) {
   const int n_strips = (p.Wc + SX_TM - 1) / SX_TM;
 
   if (threadIdx.x < 64) {
-    sm.scale[threadIdx.x] = p.bn_scale[threadIdx.x];
-    sm.shift[threadIdx.x] = p.bn_shift[threadIdx.x];
+    sm.scale[threadIdx.x] = p.raw_out ? 1.f : p.bn_scale[threadIdx.x];
+    sm.shift[threadIdx.x] = p.raw_out ? 0.f : p.bn_shift[threadIdx.x];
   }
   if (U8 && threadIdx.x < 256) {   // v/255 with IEEE division == torchvision ToTensor; split once per pixel value
     const float pv = __fdiv_rn((float)threadIdx.x, 255.f);
@@ -222,6 +223,21 @@ stem_tc_kernel(const StemTcParams p) {
         ptx::tc_fence_before();
         ptx::mbar_arrive(&sm.tmem_empty[acc]);
 
+        if (p.raw_out != nullptr) {
+          // training mode (BatchNorm needs batch statistics of THIS tensor): write the raw conv row and skip the
+          // pooling.  A band recomputes the conv row above it as pooling halo; only the owner band writes a row.
+          if (oy >= 2 * py0 && ox < p.Wc) {
+            float* dst = p.raw_out + (((size_t)b * p.Hc + oy) * p.Wc + ox) * 64 + ch0;
+#pragma unroll
+            for (int hlf = 0; hlf < SX_CH / 8; ++hlf) {
+              uint32_t w8[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) w8[e] = __float_as_uint(v[hlf * 8 + e]);
+              st_global_v8(dst + hlf * 8, w8);
+            }
+          }
+          continue;
+        }
 #pragma unroll
         for (int c = 0; c < SX_CH; ++c) v[c] = fmaf(v[c], sm.scale[ch0 + c], sm.shift[ch0 + c]);   // BN; ReLU comes with the max
         if (ox >= p.Wc) {   // conv columns past the image (last, partial strip only) act as pool padding
@@ -477,9 +493,10 @@ static int launch_stem_tc(const StemTcParams& p, int grid, cudaStream_t st) {
   return launch_stem_tc_n<SPLIT, OUT_DTYPE, U8, 4, HALF>(p, grid, st);
 }
 
-int stem_tc(const void* images, int img_u8, int B, int H, int W, const void* w_packed, const float* bn_scale,
-            const float* bn_shift, int out_dtype, void* out0, void* out1, cudaStream_t st) {
+static int stem_tc_impl(const void* images, int img_u8, int B, int H, int W, const void* w_packed, const float* bn_scale,
+                        const float* bn_shift, int out_dtype, void* out0, void* out1, cudaStream_t st, float* raw_out) {
   StemTcParams p;
+  p.raw_out = raw_out;
   p.img = images; p.B = B; p.H = H; p.W = W;
   p.Hc = (H + 6 - 7) / 2 + 1; p.Wc = (W + 6 - 7) / 2 + 1;
   p.Hp = (p.Hc + 2 - 3) / 2 + 1; p.Wp = (p.Wc + 2 - 3) / 2 + 1;
@@ -510,6 +527,11 @@ int stem_tc(const void* images, int img_u8, int B, int H, int W, const void* w_p
 #undef GO
 }
 
+int stem_tc(const void* images, int img_u8, int B, int H, int W, const void* w_packed, const float* bn_scale,
+            const float* bn_shift, int out_dtype, void* out0, void* out1, cudaStream_t st) {
+  return stem_tc_impl(images, img_u8, B, H, W, w_packed, bn_scale, bn_shift, out_dtype, out0, out1, st, nullptr);
+}
+
 }  // namespace cova
 
 extern "C" int cova_pack_stem_weight(const float* w_oihw, void* packed, void* stream) {
@@ -526,4 +548,15 @@ extern "C" int cova_pack_stem_weight_f16(const float* w_oihw, void* packed, void
       w_oihw, (__half*)packed);
   COVA_LAUNCH_OK();
   return COVA_OK;
+}
+
+// A2, training mode: conv1 alone (7x7 s2 p3, fp32-parity tensor-core mode) -> [B, H/2, W/2, 64] fp32 NHWC, no BN, no
+// ReLU, no pooling: nn.BatchNorm2d in train mode needs the batch statistics of this tensor (`train.py:27`).
+extern "C" int cova_stem_conv_raw_fwd(const void* images, int img_dtype, int B, int H, int W, const void* w_packed,
+                                      float* out, void* stream) {
+  COVA_REQUIRE(images && w_packed && out && B > 0 && H >= 7 && W >= 7, "cova_stem_conv_raw_fwd: bad arguments");
+  COVA_REQUIRE(img_dtype == COVA_F32 || img_dtype == COVA_U8, "cova_stem_conv_raw_fwd: images must be fp32 or uint8");
+  COVA_REQUIRE(((uintptr_t)out & 31) == 0, "cova_stem_conv_raw_fwd: out must be 32-byte aligned");
+  return cova::stem_tc_impl(images, img_dtype == COVA_U8, B, H, W, w_packed, nullptr, nullptr, COVA_F32, out, nullptr,
+                            (cudaStream_t)stream, out);
 }

@@ -353,7 +353,11 @@ class CoVA(nn.Module):
             return self._native.visual_features(self._img(images), bboxes.float())
         if images.dtype == torch.uint8:
             images = images.float().div(255)
-        fm = self.convnet(images).permute(0, 2, 3, 1)                # NCHW -> NHWC view for the native RoI kernel
+        if self.training and os.environ.get("COVA_B200_TRAIN_BACKBONE", "native") != "torch":
+            from .train_backbone import feature_map_train          # NHWC end to end, native BatchNorm / maxpool
+            fm = feature_map_train(self.convnet, images)
+        else:
+            fm = self.convnet(images).permute(0, 2, 3, 1)            # NCHW -> NHWC view for the native RoI kernel
         if self.roi_mode == "pool":
             return _RoIPoolFn.apply(fm, bboxes.float(), self.roi_output_size, self.spatial_scale)
         import torchvision   # RoIAlign backward is not written yet: library op on the autograd path only

@@ -346,3 +346,94 @@ def build_batch(page_offsets, context_size, boxes_xywh=None):
     _call("cova_build_batch", page_offsets.data_ptr(), B, T, int(context_size), _ptr(boxes_xywh), _ptr(bb),
           ctx.data_ptr() if context_size > 0 else 0, _stream())
     return bb, ctx
+
+
+# ------------------------------------------------------------------ training-mode backbone pieces (bn_train.cu)
+def _nhwc(t, name):
+    _cuda(t, torch.float32, name)
+    if not t.is_contiguous():
+        raise RuntimeError(f"cova_b200: `{name}` must be a contiguous NHWC fp32 tensor")
+    return t
+
+
+def _planes_like(x):
+    pl = Planes.__new__(Planes)
+    pl.dtype, pl.shape = BF16X2, tuple(x.shape)
+    pl.p0 = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    pl.p1 = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    return pl
+
+
+def split_planes(x):
+    """fp32 NHWC tensor -> split-bf16 `Planes` (hi = bf16(x), lo = bf16(x - hi))."""
+    _nhwc(x, "x")
+    pl = _planes_like(x)
+    _call("cova_split_planes", x.data_ptr(), x.numel(), pl.p0.data_ptr(), pl.p1.data_ptr(), _stream())
+    return pl
+
+
+def stem_conv_raw_fwd(images, w_packed):
+    """conv1 alone (training mode): images [B,3,H,W] fp32 / uint8 NCHW -> raw conv output [B,H/2,W/2,64] fp32 NHWC."""
+    _cuda(images, None, "images")
+    images = images.contiguous()
+    B, C, H, W = images.shape
+    out = torch.empty((B, (H - 1) // 2 + 1, (W - 1) // 2 + 1, 64), dtype=torch.float32, device=images.device)
+    _call("cova_stem_conv_raw_fwd", images.data_ptr(), U8 if images.dtype == torch.uint8 else F32, B, H, W,
+          w_packed.data_ptr(), out.data_ptr(), _stream())
+    return out
+
+
+def bn_train_fwd(x, gamma, beta, running_mean, running_var, momentum, eps, res=None, relu=True, want_planes=False):
+    """BatchNorm2d with batch statistics (+ residual) (+ ReLU) on an NHWC fp32 map x [..., C]; updates the running
+    statistics in place (pass None to skip).  Returns (y, mean [C], invstd [C], split-bf16 Planes of y or None)."""
+    _nhwc(x, "x")
+    C = x.shape[-1]
+    M = x.numel() // C
+    dev = x.device
+    ws = torch.empty(2 * C, dtype=torch.float64, device=dev)
+    mean, inv = torch.empty(C, dtype=torch.float32, device=dev), torch.empty(C, dtype=torch.float32, device=dev)
+    y = torch.empty_like(x)
+    pl = _planes_like(x) if want_planes else None
+    _call("cova_bn_train_stats", x.data_ptr(), M, C, ws.data_ptr(), _stream())
+    _call("cova_bn_train_finalize", ws.data_ptr(), M, C, float(eps), float(momentum), mean.data_ptr(), inv.data_ptr(),
+          _ptr(running_mean), _ptr(running_var), _stream())
+    _call("cova_bn_act_fwd", x.data_ptr(), M, C, mean.data_ptr(), inv.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
+          _ptr(None if res is None else _nhwc(res, "res")), int(relu), y.data_ptr(),
+          pl.p0.data_ptr() if pl else 0, pl.p1.data_ptr() if pl else 0, _stream())
+    return y, mean, inv, pl
+
+
+def bn_train_bwd(dy, x, mean, invstd, gamma, beta, res=None, relu=True, want_dres=False):
+    """Backward of `bn_train_fwd`: returns (dx, dres or None, dgamma [C], dbeta [C])."""
+    _nhwc(dy, "dy"); _nhwc(x, "x")
+    C = x.shape[-1]
+    M = x.numel() // C
+    dev = x.device
+    ws = torch.empty(2 * C, dtype=torch.float64, device=dev)
+    dx = torch.empty_like(x)
+    dres = torch.empty_like(x) if want_dres else None
+    dg, db = torch.empty(C, dtype=torch.float32, device=dev), torch.empty(C, dtype=torch.float32, device=dev)
+    _call("cova_bn_act_bwd", dy.data_ptr(), x.data_ptr(), _ptr(res), M, C, mean.data_ptr(), invstd.data_ptr(),
+          gamma.data_ptr(), beta.data_ptr(), int(relu), ws.data_ptr(), dx.data_ptr(), _ptr(dres), dg.data_ptr(),
+          db.data_ptr(), _stream())
+    return dx, dres, dg, db
+
+
+def maxpool3x3s2_fwd(x, want_planes=False):
+    """nn.MaxPool2d(3, 2, 1) on an NHWC fp32 map [B,H,W,C]: returns (y, winner codes uint8 like y, Planes of y or None)."""
+    _nhwc(x, "x")
+    B, H, W, C = x.shape
+    y = torch.empty((B, (H - 1) // 2 + 1, (W - 1) // 2 + 1, C), dtype=torch.float32, device=x.device)
+    code = torch.empty(y.shape, dtype=torch.uint8, device=x.device)
+    pl = _planes_like(y) if want_planes else None
+    _call("cova_maxpool3x3s2_fwd", x.data_ptr(), B, H, W, C, y.data_ptr(), code.data_ptr(),
+          pl.p0.data_ptr() if pl else 0, pl.p1.data_ptr() if pl else 0, _stream())
+    return y, code, pl
+
+
+def maxpool3x3s2_bwd(code, dy, in_shape):
+    _nhwc(dy, "dy")
+    B, H, W, C = in_shape
+    dx = torch.empty(in_shape, dtype=torch.float32, device=dy.device)
+    _call("cova_maxpool3x3s2_bwd", code.data_ptr(), dy.data_ptr(), B, H, W, C, dx.data_ptr(), _stream())
+    return dx

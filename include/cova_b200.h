@@ -75,6 +75,12 @@ int cova_debug_buffer(void* dev_words, int64_t n_words);
 int cova_stem_fwd(const void* images, int img_dtype, int B, int H, int W, const void* w, const float* bn_scale,
                   const float* bn_shift, int out_dtype, void* out0, void* out1, int engine, void* stream);
 
+/* Training mode (A9): conv1 ALONE in the fp32-parity tensor-core mode -> out [B, Hc, Wc, 64] fp32 NHWC (Hc = (H-1)/2+1),
+ * no BN / ReLU / pooling: BatchNorm with batch statistics needs this tensor itself (`train.py:27`).  w = the
+ * cova_pack_stem_weight filter.                                                                          */
+int cova_stem_conv_raw_fwd(const void* images, int img_dtype, int B, int H, int W, const void* w_packed, float* out,
+                           void* stream);
+
 /* Same layout for the fp16 mode (out_dtype COVA_F16): plane 0 = fp16(w), plane 1 = 0. */
 int cova_pack_stem_weight_f16(const float* w_oihw, void* packed, void* stream);
 
@@ -208,6 +214,38 @@ int cova_topk_hits(const float* logits, int64_t ld, const int64_t* labels, const
  *   context_indices int64 [T, 2*context_size]; boxes_xywh [T,4] / bboxes [T,5] both NULL or both set.      */
 int cova_build_batch(const int* page_offsets, int B, int T, int context_size, const float* boxes_xywh, float* bboxes,
                      int64_t* context_indices, void* stream);
+
+/* ---- A2 / A9, training mode: BatchNorm2d with BATCH statistics (+ residual) (+ ReLU) on NHWC fp32 maps x [M, C]
+ * (M = B*H*W, C a power of two in [4, 1024]) - what torchvision's BasicBlock / Bottleneck run through nn.BatchNorm2d
+ * under `model.train()` (`train.py:27`): biased variance for the normalisation, running statistics updated with
+ * momentum on the unbiased variance.  ws: caller-owned scratch of 2*C doubles.
+ *   cova_bn_train_stats    ws = [sum x | sum x^2]
+ *   cova_bn_train_finalize mean, invstd = 1/sqrt(var+eps) (fp32 [C]); running_mean / running_var updated in place (or NULL)
+ *   cova_bn_act_fwd        y = [relu]((x - mean) * invstd * gamma + beta [+ res])
+ *   cova_bn_act_bwd        g = dy * [y > 0] (y recomputed);  dx = gamma*invstd*(g - mean(g) - xhat*mean(g*xhat));
+ *                          dres = g (optional);  dgamma = sum g*xhat;  dbeta = sum g                              */
+int cova_bn_train_stats(const float* x, int64_t M, int C, double* ws, void* stream);
+int cova_bn_train_finalize(const double* ws, int64_t M, int C, float eps, float momentum, float* mean, float* invstd,
+                           float* running_mean, float* running_var, void* stream);
+int cova_bn_act_fwd(const float* x, int64_t M, int C, const float* mean, const float* invstd, const float* gamma,
+                    const float* beta, const float* res, int relu, float* y, void* y_hi, void* y_lo, void* stream);
+/*   y_hi / y_lo (optional, both or neither): the same result as split-bf16 planes - the operand format of the
+ *   tensor-core convolution that consumes it (cova_conv3x3_bn_act_fwd with COVA_BF16X2 input).                    */
+int cova_bn_act_bwd(const float* dy, const float* x, const float* res, int64_t M, int C, const float* mean,
+                    const float* invstd, const float* gamma, const float* beta, int relu, double* ws, float* dx,
+                    float* dres, float* dgamma, float* dbeta, void* stream);
+
+/* ---- A2 / A9: the stem's `nn.MaxPool2d(3, 2, 1)` on NHWC fp32 maps, forward and backward (the gradient of an output
+ * goes to the FIRST maximum of its window in row-major scan order, as torch's max_pool2d_with_indices).
+ * x [B,H,W,C] -> y [B,(H-1)/2+1,(W-1)/2+1,C]; code (optional, uint8, same shape as y) = position r*3+s of the winner
+ * inside the window, which is all the backward needs; y_hi / y_lo optional split-bf16 planes of y.
+ * dx [B,H,W,C] is overwritten (gather over the <= 2x2 windows containing a pixel: no atomics, no rescans).          */
+int cova_maxpool3x3s2_fwd(const float* x, int B, int H, int W, int C, float* y, unsigned char* code, void* y_hi,
+                          void* y_lo, void* stream);
+int cova_maxpool3x3s2_bwd(const unsigned char* code, const float* dy, int B, int H, int W, int C, float* dx, void* stream);
+
+/* fp32 [n] -> split-bf16 planes hi = bf16(x), lo = bf16(x - hi) (n % 4 == 0). */
+int cova_split_planes(const float* x, int64_t n, void* hi, void* lo, void* stream);
 
 #ifdef __cplusplus
 }

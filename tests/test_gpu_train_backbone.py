@@ -1,0 +1,148 @@
+"""GPU parity of the training-mode backbone pieces (bn_train.cu) through the C ABI against torch's own operators - the
+library the reference calls for these ops (`nn.BatchNorm2d` in train mode, `nn.MaxPool2d(3, 2, 1)`) -
+on the same seeded inputs, forward values, running statistics and every gradient.  Tolerances (max|a-b| / max|b|):
+BatchNorm 2e-5 (statistics are combined in double here, in fp32 Welford by torch); maxpool bit-exact, including the
+first-maximum tie rule that decides where the gradient goes (ReLU'd maps are full of tied zeros).  The integrated train
+step is pinned by `test_gpu_parity.py::test_train_step_matches_reference_grads` (live-reference fixture)."""
+import warnings
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import rel_err
+
+pytestmark = pytest.mark.gpu
+warnings.filterwarnings("ignore")
+DEV = "cuda:0"
+
+
+def n(t):
+    return t.detach().float().cpu().numpy()
+
+
+@pytest.mark.parametrize("shape,relu,with_res", [((2, 9, 7, 64), True, False), ((3, 16, 20, 64), True, True),
+                                                 ((1, 5, 5, 256), False, False), ((2, 12, 12, 256), True, True),
+                                                 ((1, 1, 3, 8), True, False)])
+def test_bn_train_fwd_bwd_vs_torch(shape, relu, with_res, monkeypatch):
+    from cova_b200.train_backbone import _bn_act
+    monkeypatch.setenv("COVA_B200_TRAIN_CONV", "tcgen05")       # so that the split planes are requested for C = 64
+    g = torch.Generator().manual_seed(sum(shape))
+    C = shape[-1]
+    x = (torch.randn(shape, generator=g) * 2 + 0.5).to(DEV).requires_grad_(True)
+    res = torch.randn(shape, generator=g).to(DEV).requires_grad_(True) if with_res else None
+    bn = torch.nn.BatchNorm2d(C).to(DEV).train()
+    with torch.no_grad():
+        bn.weight.copy_(torch.rand(C, generator=g) + 0.5); bn.bias.copy_(torch.randn(C, generator=g) * 0.2)
+        bn.running_mean.copy_(torch.randn(C, generator=g)); bn.running_var.copy_(torch.rand(C, generator=g) + 0.5)
+    ref_bn = torch.nn.BatchNorm2d(C).to(DEV).train()
+    ref_bn.load_state_dict(bn.state_dict())
+    dy = torch.randn(shape, generator=g).to(DEV)
+
+    y, planes = _bn_act(x, bn, res=res, relu=relu, planes_for=torch.nn.Conv2d(64, 64, 3, 1, 1, bias=False) if C == 64 else None)
+    y.backward(dy)
+    if C == 64:                                   # the split-bf16 planes of y feed the tensor-core convolution
+        assert rel_err(n(planes[0].float() + planes[1].float()), n(y)) < 2e-5
+    got = [n(y), n(x.grad), n(bn.weight.grad), n(bn.bias.grad), n(bn.running_mean), n(bn.running_var)]
+    got_res = n(res.grad) if with_res else None
+
+    x2 = x.detach().clone().requires_grad_(True)
+    r2 = res.detach().clone().requires_grad_(True) if with_res else None
+    z = ref_bn(x2.permute(0, 3, 1, 2)).permute(0, 2, 3, 1)
+    if with_res:
+        z = z + r2
+    if relu:
+        z = F.relu(z)
+    z.backward(dy)
+    want = [n(z), n(x2.grad), n(ref_bn.weight.grad), n(ref_bn.bias.grad), n(ref_bn.running_mean), n(ref_bn.running_var)]
+    for a, b, name in zip(got, want, ["y", "dx", "dgamma", "dbeta", "running_mean", "running_var"]):
+        assert rel_err(a, b) < 2e-5, (name, rel_err(a, b))
+    if with_res:
+        assert rel_err(got_res, n(r2.grad)) < 2e-5
+    assert int(bn.num_batches_tracked) == int(ref_bn.num_batches_tracked) == 1
+
+
+@pytest.mark.parametrize("shape", [(2, 8, 8, 64), (1, 9, 13, 64), (2, 1, 7, 8), (1, 640, 40, 64)])
+def test_maxpool_fwd_bwd_vs_torch_with_ties(shape):
+    from cova_b200.train_backbone import _MaxPoolFn
+    g = torch.Generator().manual_seed(shape[1] * 31 + shape[2])
+    x = F.relu(torch.randn(shape, generator=g)).round(decimals=1).to(DEV).requires_grad_(True)   # ~60 % exact zeros, ties
+    y, hi, lo = _MaxPoolFn.apply(x, True)
+    assert rel_err(n(hi.float() + lo.float()), n(y)) < 2e-5
+    dy = torch.randn(y.shape, generator=g).to(DEV)
+    y.backward(dy)
+    x2 = x.detach().clone().requires_grad_(True)
+    z = F.max_pool2d(x2.permute(0, 3, 1, 2), 3, 2, 1).permute(0, 2, 3, 1)
+    z.backward(dy)
+    assert np.array_equal(n(y), n(z))
+    assert np.array_equal(n(x.grad), n(x2.grad))
+
+
+@pytest.mark.parametrize("backbone,conv,tol", [("resnet18", "cudnn", 2e-3), ("resnet50", "cudnn", 6e-2),
+                                               ("resnet18", "tcgen05", 0.15)])
+def test_train_backbone_matches_torch_composite(backbone, conv, tol, monkeypatch):
+    """Whole train-mode step on both paths of the same model: native BatchNorm / maxpool (NHWC) vs the PyTorch-operator
+    composite (`COVA_B200_TRAIN_BACKBONE=torch`): logits, loss gradients of every parameter, BatchNorm buffers."""
+    import copy
+    import cova_b200.synth as synth
+    from cova_b200.models import CoVA
+    # ResNet-18 / cudnn: every gradient agrees to ~5e-6 (tools/diag_train_grads.py).  ResNet-50: the last Bottleneck
+    # agrees to 5e-6 as well, but the gradient that leaves it through cuDNN's NHWC dgrad of the 1x1 convolutions (a
+    # tensor-op fp32 kernel) differs from the NCHW algorithm by ~1e-3, and the train-mode BatchNorms upstream amplify
+    # that to 0.3-3 % - library behaviour on the interim path, hence the loose bound.
+    # conv="tcgen05": forward convolutions on the tensor cores (1e-5 on the activations); the decoder's train-mode
+    # BatchNorm1d over 24 boxes amplifies that to percent-level gradient deviations (train_backbone.tc_forward_convs),
+    # hence the loose bound there and the exact library forward as the default
+    monkeypatch.setenv("COVA_B200_TRAIN_CONV", conv)
+    m1 = CoVA((3, 3), 128, 4, True, 384, 32, 0, 0.0, None, pretrained=False, backbone=backbone)
+    m1.load_state_dict(synth.make_state_dict(123, backbone=backbone), strict=True)
+    m1 = m1.to(DEV).train()
+    m2 = copy.deepcopy(m1)
+    inp = [t.to(DEV) for t in synth.gen(2, 12, 8, seed=8, img=128, with_labels=True)]
+    crit = torch.nn.CrossEntropyLoss(reduction="sum")
+    with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):     # both library backwards in plain fp32
+        out1 = m1(*inp[:4]); crit(out1, inp[4]).backward()
+        monkeypatch.setenv("COVA_B200_TRAIN_BACKBONE", "torch")
+        out2 = m2(*inp[:4]); crit(out2, inp[4]).backward()
+    assert rel_err(n(out1), n(out2)) < 1e-4
+    monkeypatch.delenv("COVA_B200_TRAIN_BACKBONE")
+    gmax = max(float(p.grad.abs().max()) for p in m2.parameters())
+    for (name, p1), p2 in zip(m1.named_parameters(), m2.parameters()):
+        # a bias in front of a BatchNorm has an exactly-zero true gradient: compare against the global gradient scale
+        scale = max(float(p2.grad.abs().max()), 1e-4 * gmax)
+        err = float((p1.grad - p2.grad).abs().max()) / scale
+        assert err < tol, (name, err)
+    for (name, b1), b2 in zip(m1.named_buffers(), m2.buffers()):
+        assert rel_err(n(b1), n(b2)) < 1e-4, name
+
+
+def test_stem_conv_raw_and_conv3x3_functions_vs_torch():
+    """The native forward convolutions of the training path (conv1 raw output; 3x3 from split planes) and their
+    library backward, against F.conv2d + autograd in fp32."""
+    from cova_b200 import ops
+    from cova_b200.train_backbone import _Conv3x3Fn, _StemConvFn
+    g = torch.Generator().manual_seed(4)
+    with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
+        img = torch.rand(2, 3, 104, 136, generator=g).to(DEV)
+        w1 = (torch.randn(64, 3, 7, 7, generator=g) * 0.1).to(DEV).requires_grad_(True)
+        y = _StemConvFn.apply(img, w1)
+        dy = torch.randn(y.shape, generator=g).to(DEV)
+        y.backward(dy)
+        w1r = w1.detach().clone().requires_grad_(True)
+        yr = F.conv2d(img, w1r, None, 2, 3).permute(0, 2, 3, 1)
+        yr.backward(dy)
+        assert y.shape == yr.shape and rel_err(n(y), n(yr)) < 3e-5
+        assert rel_err(n(w1.grad), n(w1r.grad)) < 2e-3          # library wgrad may run in TF32
+
+        x = torch.randn(2, 37, 45, 64, generator=g).to(DEV).requires_grad_(True)
+        w = (torch.randn(64, 64, 3, 3, generator=g) * 0.05).to(DEV).requires_grad_(True)
+        pl = ops.split_planes(x.detach())
+        y = _Conv3x3Fn.apply(x, pl.p0, pl.p1, w)
+        dy = torch.randn(y.shape, generator=g).to(DEV)
+        y.backward(dy)
+        xr, wr = x.detach().clone().requires_grad_(True), w.detach().clone().requires_grad_(True)
+        yr = F.conv2d(xr.permute(0, 3, 1, 2), wr, None, 1, 1).permute(0, 2, 3, 1)
+        yr.backward(dy)
+        assert rel_err(n(y), n(yr)) < 3e-5
+        assert rel_err(n(x.grad), n(xr.grad)) < 2e-3 and rel_err(n(w.grad), n(wr.grad)) < 2e-3

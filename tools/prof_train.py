@@ -1,0 +1,22 @@
+import os, sys, warnings
+import torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+warnings.filterwarnings("ignore")
+import cova_b200.synth as synth
+from cova_b200.models import CoVA
+from cova_b200.train_ops import CrossEntropyLossSum, FlatAdam
+from torch.profiler import profile, ProfilerActivity
+dev = torch.device("cuda", 0)
+m = CoVA((3, 3), 1280, 4, True, 384, 32, 0, 0.2, None, pretrained=False)
+m.load_state_dict(synth.make_state_dict(123), strict=True)
+m = m.to(dev).train()
+opt = FlatAdam(m.parameters(), lr=5e-4, weight_decay=1e-3)
+crit = CrossEntropyLossSum().to(dev)
+inp = [t.to(dev) for t in synth.gen(16, 90, 24, seed=1, with_labels=True)]
+def step():
+    opt.zero_grad(); loss = crit(m(*inp[:4]), inp[4]); loss.backward(); opt.step()
+for _ in range(2): step()
+torch.cuda.synchronize()
+with profile(activities=[ProfilerActivity.CUDA]) as prof:
+    step(); torch.cuda.synchronize()
+print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=25, max_name_column_width=90))
