@@ -307,13 +307,13 @@ def main():
     }
     traffic = {}
     tp = os.path.join(ROOT, "profiles", "traffic_r01.json")    # dram__bytes per launch from the committed ncu capture
-    if os.path.exists(tp) and model.backbone == "resnet18" and model.precision == "fp32" and model.engine == "tcgen05":
+    if os.path.exists(tp) and model.backbone == "resnet18" and model.precision in ("fp32", "fp32x") and model.engine == "tcgen05":
         traffic = {k: v["dram_bytes_per_launch"] for k, v in json.load(open(tp)).items() if not k.startswith("_")}
     # Tensor-core FLOPs actually ISSUED per algorithmic FLOP: the fp32-parity mode runs 3 bf16 products per fp32
     # product (x*w ~ hi*Whi + lo*Whi + hi*Wlo); the stem additionally pads K from 147 to 7 rows x 32 (sliding-window
     # operand).  `executed` = algorithmic rate x this factor = what the tensor pipe delivers, measured against the same
     # sustained cuBLAS bf16 peak (both run at the 1000 W power cap: profiles/r01k_power_clocks.txt).
-    split = model.engine == "tcgen05" and model.precision == "fp32"
+    split = model.engine == "tcgen05" and model.precision in ("fp32", "fp32x")
     exec_factor = {"cova_conv3x3_bn_act_fwd": 3.0 if split else 1.0,
                    "cova_stem_fwd": (3.0 if split else 1.0) * 224.0 / 147.0,
                    "cova_linear_fwd": 3.0} if model.engine == "tcgen05" else {}
@@ -351,7 +351,8 @@ def main():
         "metric": "webpages/sec", "value": value, "unit": "pages/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": {"fp32": "bf16x3 (split-bf16, fp32 accumulate; fp32-parity)", "bf16": "bf16",
-                                       "fp16": "fp16 (one product, fp32 accumulate)"}[model.precision]
+                                       "fp16": "fp16 (one product, fp32 accumulate)",
+                                       "fp32x": "fp16x3 (split-fp16, fp32 accumulate; fp32-parity)"}[model.precision]
         if model.engine == "tcgen05" else "f32",
         "data": "synthetic",
         "config": {"workload": "configs[1]: batch=16 synthetic 1280x1280 pages per GPU, N=90 boxes, K=24, "

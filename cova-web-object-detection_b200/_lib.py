@@ -18,7 +18,7 @@ NVCC_FLAGS = [
     "-Xcompiler", "-fPIC", "-shared", "--cudart", "static",
 ]
 
-F32, BF16, BF16X2, U8, F16 = 0, 1, 2, 3, 4
+F32, BF16, BF16X2, U8, F16, F16X2 = 0, 1, 2, 3, 4, 5
 ENGINE_SIMT, ENGINE_TCGEN05 = 0, 1
 
 
@@ -63,9 +63,11 @@ SIGNATURES = {
     "cova_conv1x1_bn_act_fwd": (_I, [_P, _P, _L, _I, _I, _P, _P, _P, _P, _P, _I, _I, _P, _P, _P]),
     "cova_pack_conv_weight": (_I, [_P, _I, _I, _I, _I, _P, _P, _P, _P]),
     "cova_pack_stem_weight": (_I, [_P, _P, _P]),
-    "cova_stem_conv_raw_fwd": (_I, [_P, _I, _I, _I, _I, _P, _P, _P]),
+    "cova_stem_conv_raw_fwd": (_I, [_P, _I, _I, _I, _I, _P, _I, _P, _P]),
     "cova_pack_stem_weight_f16": (_I, [_P, _P, _P]),
+    "cova_pack_stem_weight_f16x2": (_I, [_P, _P, _P]),
     "cova_pack_conv_weight_f16": (_I, [_P, _I, _I, _I, _I, _P, _P]),
+    "cova_pack_conv_weight_f16x2": (_I, [_P, _I, _I, _I, _I, _P, _P, _P]),
     "cova_roi_fwd": (_I, [_P, _I, _I, _I, _I, _P, _I, _I, _I, _F, _I, _I, _P, _L, _P, _P]),
     "cova_roi_pool_bwd": (_I, [_P, _L, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P]),
     "cova_bbox_enc_fwd": (_I, [_P, _I, _P, _P, _P, _P, _I, _P, _L, _P]),
@@ -81,10 +83,10 @@ SIGNATURES = {
     "cova_build_batch": (_I, [_P, _I, _I, _I, _P, _P, _P, _P]),
     "cova_bn_train_stats": (_I, [_P, _L, _I, _P, _P]),
     "cova_bn_train_finalize": (_I, [_P, _L, _I, _F, _F, _P, _P, _P, _P, _P]),
-    "cova_bn_act_fwd": (_I, [_P, _L, _I, _P, _P, _P, _P, _P, _I, _P, _P, _P, _P]),
-    "cova_split_planes": (_I, [_P, _L, _P, _P, _P]),
+    "cova_bn_act_fwd": (_I, [_P, _L, _I, _P, _P, _P, _P, _P, _I, _P, _P, _P, _I, _P]),
+    "cova_split_planes": (_I, [_P, _L, _P, _P, _I, _P]),
     "cova_bn_act_bwd": (_I, [_P, _P, _P, _L, _I, _P, _P, _P, _P, _I, _P, _P, _P, _P, _P, _P]),
-    "cova_maxpool3x3s2_fwd": (_I, [_P, _I, _I, _I, _I, _P, _P, _P, _P, _P]),
+    "cova_maxpool3x3s2_fwd": (_I, [_P, _I, _I, _I, _I, _P, _P, _P, _P, _I, _P]),
     "cova_maxpool3x3s2_bwd": (_I, [_P, _P, _I, _I, _I, _I, _P, _P]),
 }
 

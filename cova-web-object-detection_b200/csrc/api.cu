@@ -22,7 +22,9 @@ int linear_tc(const float* x, int64_t ld_x, int M, int K, const void* w_packed, 
 
 using namespace cova;
 
-static bool dtype_ok(int d) { return d == COVA_F32 || d == COVA_BF16 || d == COVA_BF16X2 || d == COVA_F16; }
+static bool dtype_ok(int d) {
+  return d == COVA_F32 || d == COVA_BF16 || d == COVA_BF16X2 || d == COVA_F16 || d == COVA_F16X2;
+}
 
 extern "C" int cova_stem_fwd(const void* images, int img_dtype, int B, int H, int W, const void* w, const float* bn_scale,
                              const float* bn_shift, int out_dtype, void* out0, void* out1, int engine, void* stream) {
@@ -31,9 +33,10 @@ extern "C" int cova_stem_fwd(const void* images, int img_dtype, int B, int H, in
   COVA_REQUIRE(dtype_ok(out_dtype), "cova_stem_fwd: bad out_dtype %d", out_dtype);
   COVA_REQUIRE(img_dtype == COVA_F32 || img_dtype == COVA_U8, "cova_stem_fwd: images must be fp32 or uint8");
   const int u8 = img_dtype == COVA_U8;
-  COVA_REQUIRE(out_dtype != COVA_BF16X2 || out1, "cova_stem_fwd: BF16X2 output needs the lo plane");
+  COVA_REQUIRE((out_dtype != COVA_BF16X2 && out_dtype != COVA_F16X2) || out1, "cova_stem_fwd: split output needs the lo plane");
   COVA_REQUIRE(engine == COVA_ENGINE_SIMT || engine == COVA_ENGINE_TCGEN05, "cova_stem_fwd: bad engine");
-  COVA_REQUIRE(out_dtype != COVA_F16 || engine == COVA_ENGINE_TCGEN05, "cova_stem_fwd: fp16 planes are a tcgen05-engine mode");
+  COVA_REQUIRE((out_dtype != COVA_F16 && out_dtype != COVA_F16X2) || engine == COVA_ENGINE_TCGEN05,
+               "cova_stem_fwd: fp16 planes are a tcgen05-engine mode");
   if (engine == COVA_ENGINE_TCGEN05)
     return stem_tc(images, u8, B, H, W, w, bn_scale, bn_shift, out_dtype, out0, out1, (cudaStream_t)stream);
   return stem_simt(images, u8, B, H, W, (const float*)w, bn_scale, bn_shift, out_dtype, out0, out1,
@@ -55,14 +58,14 @@ extern "C" int cova_conv3x3_bn_act_fwd(const void* x0, const void* x1, int dtype
                         (float*)y0, st);
   }
   COVA_REQUIRE(engine == COVA_ENGINE_TCGEN05, "cova_conv3x3_bn_act_fwd: bad engine %d", engine);
-  COVA_REQUIRE(dtype == COVA_BF16 || dtype == COVA_BF16X2 || dtype == COVA_F16,
-               "cova_conv3x3_bn_act_fwd: tcgen05 engine takes bf16 / split-bf16 / fp16 planes");
-  const int split = dtype == COVA_BF16X2, half = dtype == COVA_F16;
-  COVA_REQUIRE(half ? (out_dtype == COVA_F16 || out_dtype == COVA_F32) : out_dtype != COVA_F16,
-               "cova_conv3x3_bn_act_fwd: fp16 planes in <=> fp16 planes (or fp32) out");
+  COVA_REQUIRE(dtype == COVA_BF16 || dtype == COVA_BF16X2 || dtype == COVA_F16 || dtype == COVA_F16X2,
+               "cova_conv3x3_bn_act_fwd: tcgen05 engine takes bf16 / split-bf16 / fp16 / split-fp16 planes");
+  const int split = dtype == COVA_BF16X2 || dtype == COVA_F16X2, half = dtype == COVA_F16 || dtype == COVA_F16X2;
+  COVA_REQUIRE(out_dtype == COVA_F32 || out_dtype == dtype,
+               "cova_conv3x3_bn_act_fwd: tcgen05 output is fp32 or the input's plane format");
   COVA_REQUIRE(!split || (x1 && w_b), "cova_conv3x3_bn_act_fwd: BF16X2 needs lo planes for x and w");
   COVA_REQUIRE(!split || !res0 || res1, "cova_conv3x3_bn_act_fwd: BF16X2 residual needs its lo plane");
-  COVA_REQUIRE(out_dtype != COVA_BF16X2 || y1, "cova_conv3x3_bn_act_fwd: BF16X2 output needs the lo plane");
+  COVA_REQUIRE((out_dtype != COVA_BF16X2 && out_dtype != COVA_F16X2) || y1, "cova_conv3x3_bn_act_fwd: split output needs the lo plane");
   return conv3x3_tc(x0, x1, split, half, B, H, W, w_a, w_b, bn_scale, bn_shift, res0, res1, relu, out_dtype, y0, y1, st);
 }
 

@@ -23,6 +23,20 @@ __device__ __forceinline__ float bn_val(float x, float mean, float inv, float g,
   return (x - mean) * inv * g + b;     // torch: (x - mean) * invstd * weight + bias
 }
 
+// fp32 float4 -> split planes (bf16 hi/lo, or fp16 hi/lo when f16 != 0); both formats are 16 bits per element
+__device__ __forceinline__ void split4(const float4 v, __nv_bfloat16* hi, __nv_bfloat16* lo, size_t idx, int f16 = 0) {
+  uint32_t h01, l01, h23, l23;
+  if (f16) {
+    split_f16x2(v.x, v.y, h01, l01);
+    split_f16x2(v.z, v.w, h23, l23);
+  } else {
+    split_bf16x2(v.x, v.y, h01, l01);
+    split_bf16x2(v.z, v.w, h23, l23);
+  }
+  *reinterpret_cast<uint2*>(hi + idx) = make_uint2(h01, h23);
+  *reinterpret_cast<uint2*>(lo + idx) = make_uint2(l01, l23);
+}
+
 // MODE 0: a = sum x, b = sum x^2.   MODE 1: a = sum g, b = sum g * xhat with g = dy * [y > 0] (y recomputed).
 template <int MODE>
 __global__ void __launch_bounds__(BN_THREADS)
@@ -100,7 +114,7 @@ __global__ void __launch_bounds__(BN_THREADS)
 bn_act_fwd_kernel(const float* __restrict__ x, int64_t n4, int C, const float* __restrict__ mean,
                   const float* __restrict__ invstd, const float* __restrict__ gamma, const float* __restrict__ beta,
                   const float* __restrict__ res, int relu, float* __restrict__ y, __nv_bfloat16* __restrict__ y_hi,
-                  __nv_bfloat16* __restrict__ y_lo) {
+                  __nv_bfloat16* __restrict__ y_lo, int f16) {
   const int c4n = C >> 2;
   for (int64_t i = (int64_t)blockIdx.x * BN_THREADS + threadIdx.x; i < n4; i += (int64_t)gridDim.x * BN_THREADS) {
     const int c0 = 4 * (int)(i % c4n);
@@ -115,13 +129,7 @@ bn_act_fwd_kernel(const float* __restrict__ x, int64_t n4, int C, const float* _
     }
     if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
     reinterpret_cast<float4*>(y)[i] = o;
-    if (y_hi != nullptr) {
-      uint32_t h01, l01, h23, l23;
-      split_bf16x2(o.x, o.y, h01, l01);
-      split_bf16x2(o.z, o.w, h23, l23);
-      *reinterpret_cast<uint2*>(y_hi + i * 4) = make_uint2(h01, h23);
-      *reinterpret_cast<uint2*>(y_lo + i * 4) = make_uint2(l01, l23);
-    }
+    if (y_hi != nullptr) split4(o, y_hi, y_lo, (size_t)i * 4, f16);
   }
 }
 
@@ -175,17 +183,10 @@ bn_act_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, con
 // goes.  The forward stores the winner's position inside the (unclipped) window as one byte per output element
 // (code = r*3 + s); the backward is a gather over the <= 2 x 2 windows that contain an input pixel: compare codes,
 // no rescans, no atomics.
-__device__ __forceinline__ void split4(const float4 v, __nv_bfloat16* hi, __nv_bfloat16* lo, size_t idx) {
-  uint32_t h01, l01, h23, l23;
-  split_bf16x2(v.x, v.y, h01, l01);
-  split_bf16x2(v.z, v.w, h23, l23);
-  *reinterpret_cast<uint2*>(hi + idx) = make_uint2(h01, h23);
-  *reinterpret_cast<uint2*>(lo + idx) = make_uint2(l01, l23);
-}
-
 __global__ void __launch_bounds__(256)
 maxpool_fwd_kernel(const float* __restrict__ x, int B, int H, int W, int C, int Ho, int Wo, float* __restrict__ y,
-                   unsigned char* __restrict__ code, __nv_bfloat16* __restrict__ y_hi, __nv_bfloat16* __restrict__ y_lo) {
+                   unsigned char* __restrict__ code, __nv_bfloat16* __restrict__ y_hi, __nv_bfloat16* __restrict__ y_lo,
+                   int f16) {
   const int c4n = C >> 2;
   const int64_t n = (int64_t)B * Ho * Wo * c4n;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
@@ -210,7 +211,7 @@ maxpool_fwd_kernel(const float* __restrict__ x, int B, int H, int W, int C, int 
     }
     reinterpret_cast<float4*>(y)[i] = m;
     if (code != nullptr) reinterpret_cast<uchar4*>(code)[i] = make_uchar4(mi.x, mi.y, mi.z, mi.w);
-    if (y_hi != nullptr) split4(m, y_hi, y_lo, (size_t)i * 4);
+    if (y_hi != nullptr) split4(m, y_hi, y_lo, (size_t)i * 4, f16);
   }
 }
 
@@ -245,9 +246,10 @@ maxpool_bwd_kernel(const unsigned char* __restrict__ code, const float* __restri
 
 // fp32 -> split-bf16 planes (hi = bf16(x), lo = bf16(x - hi)): the operand format of the tensor-core convolutions
 __global__ void __launch_bounds__(256)
-split_planes_kernel(const float* __restrict__ x, int64_t n4, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
+split_planes_kernel(const float* __restrict__ x, int64_t n4, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
+                    int f16) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x)
-    split4(__ldg(reinterpret_cast<const float4*>(x) + i), hi, lo, (size_t)i * 4);
+    split4(__ldg(reinterpret_cast<const float4*>(x) + i), hi, lo, (size_t)i * 4, f16);
 }
 
 static bool bn_c_ok(int C) { return C >= 4 && C <= 1024 && (C & (C - 1)) == 0; }
@@ -289,7 +291,8 @@ extern "C" int cova_bn_train_finalize(const double* ws, int64_t M, int C, float 
 
 extern "C" int cova_bn_act_fwd(const float* x, int64_t M, int C, const float* mean, const float* invstd,
                                const float* gamma, const float* beta, const float* res, int relu, float* y,
-                               void* y_hi, void* y_lo, void* stream) {
+                               void* y_hi, void* y_lo, int planes_dtype, void* stream) {
+  COVA_REQUIRE(planes_dtype == COVA_BF16X2 || planes_dtype == COVA_F16X2, "cova_bn_act_fwd: planes are split-bf16 or split-fp16");
   COVA_REQUIRE(x && y && mean && invstd && gamma && beta && M > 0, "cova_bn_act_fwd: bad arguments");
   COVA_REQUIRE(bn_c_ok(C), "cova_bn_act_fwd: C=%d must be a power of two in [4, 1024]", C);
   COVA_REQUIRE((((uintptr_t)x | (uintptr_t)y | (uintptr_t)res | (uintptr_t)y_hi | (uintptr_t)y_lo) & 15) == 0,
@@ -298,7 +301,8 @@ extern "C" int cova_bn_act_fwd(const float* x, int64_t M, int C, const float* me
   const int64_t n4 = M * (C / 4);
   bn_act_fwd_kernel<<<ew_grid(n4, BN_THREADS), BN_THREADS, 0, (cudaStream_t)stream>>>(x, n4, C, mean, invstd, gamma, beta,
                                                                                      res, relu, y, (__nv_bfloat16*)y_hi,
-                                                                                     (__nv_bfloat16*)y_lo);
+                                                                                     (__nv_bfloat16*)y_lo,
+                                                                                     planes_dtype == COVA_F16X2);
   COVA_LAUNCH_OK();
   return COVA_OK;
 }
@@ -326,7 +330,8 @@ extern "C" int cova_bn_act_bwd(const float* dy, const float* x, const float* res
 }
 
 extern "C" int cova_maxpool3x3s2_fwd(const float* x, int B, int H, int W, int C, float* y, unsigned char* code, void* y_hi,
-                                     void* y_lo, void* stream) {
+                                     void* y_lo, int planes_dtype, void* stream) {
+  COVA_REQUIRE(planes_dtype == COVA_BF16X2 || planes_dtype == COVA_F16X2, "cova_maxpool3x3s2_fwd: planes are split-bf16 or split-fp16");
   COVA_REQUIRE(x && y && B > 0 && H > 0 && W > 0 && C > 0 && C % 4 == 0, "cova_maxpool3x3s2_fwd: bad arguments");
   COVA_REQUIRE((((uintptr_t)x | (uintptr_t)y | (uintptr_t)y_hi | (uintptr_t)y_lo) & 15) == 0 && ((uintptr_t)code & 3) == 0,
                "cova_maxpool3x3s2_fwd: alignment");
@@ -334,7 +339,7 @@ extern "C" int cova_maxpool3x3s2_fwd(const float* x, int B, int H, int W, int C,
   const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
   const int64_t n = (int64_t)B * Ho * Wo * (C / 4);
   maxpool_fwd_kernel<<<ew_grid(n, 256), 256, 0, (cudaStream_t)stream>>>(x, B, H, W, C, Ho, Wo, y, code, (__nv_bfloat16*)y_hi,
-                                                                        (__nv_bfloat16*)y_lo);
+                                                                        (__nv_bfloat16*)y_lo, planes_dtype == COVA_F16X2);
   COVA_LAUNCH_OK();
   return COVA_OK;
 }
@@ -350,10 +355,12 @@ extern "C" int cova_maxpool3x3s2_bwd(const unsigned char* code, const float* dy,
   return COVA_OK;
 }
 
-extern "C" int cova_split_planes(const float* x, int64_t n, void* hi, void* lo, void* stream) {
+extern "C" int cova_split_planes(const float* x, int64_t n, void* hi, void* lo, int planes_dtype, void* stream) {
+  COVA_REQUIRE(planes_dtype == COVA_BF16X2 || planes_dtype == COVA_F16X2, "cova_split_planes: planes are split-bf16 or split-fp16");
   COVA_REQUIRE(x && hi && lo && n > 0 && n % 4 == 0, "cova_split_planes: n must be a positive multiple of 4");
   COVA_REQUIRE((((uintptr_t)x & 15) | ((uintptr_t)hi & 7) | ((uintptr_t)lo & 7)) == 0, "cova_split_planes: alignment");
-  split_planes_kernel<<<ew_grid(n / 4, 256), 256, 0, (cudaStream_t)stream>>>(x, n / 4, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo);
+  split_planes_kernel<<<ew_grid(n / 4, 256), 256, 0, (cudaStream_t)stream>>>(x, n / 4, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo,
+                                                                            planes_dtype == COVA_F16X2);
   COVA_LAUNCH_OK();
   return COVA_OK;
 }

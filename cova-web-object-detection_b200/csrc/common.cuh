@@ -75,6 +75,18 @@ __device__ __forceinline__ float2 unpack2_f16(uint32_t packed) {
   return __half22float2(*reinterpret_cast<const __half2*>(&packed));
 }
 
+// split-fp16 ("fp16x3" mode): hi = f16(x), lo = f16(x - hi) carries 22 significand bits (split-bf16: 16), so the same
+// three tensor-core products reproduce an fp32 convolution to ~1e-6 instead of ~1e-5.  Filters are pre-scaled by
+// SPLIT_F16_WSCALE (a power of two, undone exactly in the epilogue) so that their lo plane stays a NORMAL fp16 number.
+constexpr float SPLIT_F16_WSCALE = 256.f;
+__device__ __forceinline__ void split_f16x2(float a, float b, uint32_t& hi, uint32_t& lo) {
+  __half2 h = __floats2half2_rn(a, b);
+  hi = *reinterpret_cast<uint32_t*>(&h);
+  const float2 hf = __half22float2(h);
+  __half2 l = __floats2half2_rn(a - hf.x, b - hf.y);
+  lo = *reinterpret_cast<uint32_t*>(&l);
+}
+
 // 256-bit global accesses (sm_100: LDG/STG.E.256): one full 32-byte sector per lane
 __device__ __forceinline__ void st_global_v8(void* p, const uint32_t (&v)[8]) {
   asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]),

@@ -155,7 +155,31 @@ __global__ void pack_conv_weight_f16_kernel(const float* __restrict__ w, int Cou
   }
 }
 
+// OIHW fp32 -> split-fp16 [kh*kw][Cout][Cin] planes of SPLIT_F16_WSCALE * w (COVA_F16X2 mode)
+__global__ void pack_conv_weight_f16x2_kernel(const float* __restrict__ w, int Cout, int Cin, int KH, int KW,
+                                              __half* __restrict__ hi, __half* __restrict__ lo) {
+  const int n = Cout * Cin * KH * KW;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int s = i % KW, r = (i / KW) % KH, ci = (i / (KW * KH)) % Cin, co = i / (KW * KH * Cin);
+    const float v = w[i] * SPLIT_F16_WSCALE;
+    const __half h = __float2half_rn(v);
+    const size_t o = ((size_t)(r * KW + s) * Cout + co) * Cin + ci;
+    hi[o] = h;
+    lo[o] = __float2half_rn(v - __half2float(h));
+  }
+}
+
 }  // namespace cova
+
+extern "C" int cova_pack_conv_weight_f16x2(const float* w_oihw, int Cout, int Cin, int kh, int kw, void* tc_hi, void* tc_lo,
+                                           void* stream) {
+  COVA_REQUIRE(w_oihw && tc_hi && tc_lo && Cout > 0 && Cin > 0 && kh > 0 && kw > 0, "cova_pack_conv_weight_f16x2: bad arguments");
+  const int n = Cout * Cin * kh * kw;
+  cova::pack_conv_weight_f16x2_kernel<<<cova::ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(
+      w_oihw, Cout, Cin, kh, kw, (__half*)tc_hi, (__half*)tc_lo);
+  COVA_LAUNCH_OK();
+  return COVA_OK;
+}
 
 extern "C" int cova_pack_conv_weight_f16(const float* w_oihw, int Cout, int Cin, int kh, int kw, void* tc_f16,
                                          void* stream) {

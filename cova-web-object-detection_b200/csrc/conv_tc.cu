@@ -97,8 +97,10 @@ __device__ __forceinline__ void mbar_wait_t(uint64_t* bar, uint32_t parity, bool
   }
 }
 
-// HALF (single-plane mode only): the plane and the filter are fp16 (11-bit significand: ~8x tighter than bf16 -
-// measured ~5e-4 on the logits, inside BASELINE.json's 1e-3 bar, at one product per MMA), COVA_F16.
+// HALF: the planes and the filter are fp16 instead of bf16.  !SPLIT: COVA_F16, one product per MMA (11-bit significand:
+// ~8x tighter than bf16 - measured ~5e-4 on the logits, inside BASELINE.json's 1e-3 bar).  SPLIT: COVA_F16X2, the same
+// three products on split-fp16 planes (22 significand bits: an fp32 convolution to ~1e-6); the filter comes scaled by
+// SPLIT_F16_WSCALE, undone in the epilogue's scale.
 template <bool SPLIT, int OUT_DTYPE, bool HALF>
 __global__ void __launch_bounds__(CT_THREADS, 1)
 conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ CUtensorMap tm_x_lo,
@@ -118,7 +120,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_cons
   unsigned long long wc0 = 0, wc1 = 0;   // wait-cycle counters of this warp's role
 
   if (threadIdx.x < CT_C) {
-    tail.scale[threadIdx.x] = p.bn_scale[threadIdx.x];
+    tail.scale[threadIdx.x] = p.bn_scale[threadIdx.x] * ((SPLIT && HALF) ? 1.f / SPLIT_F16_WSCALE : 1.f);
     tail.shift[threadIdx.x] = p.bn_shift[threadIdx.x];
   }
   if (warp == 0 && lane == 0) {
@@ -191,7 +193,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_cons
     // warp-uniform values (the elect.sync guard lets the compiler keep them in uniform registers; an
     // `if (lane == 0)` region would wrap every UTCHMMA in a per-lane serialisation loop).
     constexpr uint32_t idesc64 = HALF ? ptx::umma_idesc_f16(128, CT_C) : ptx::umma_idesc_bf16(128, CT_C);
-    constexpr uint32_t idesc128 = ptx::umma_idesc_bf16(128, 2 * CT_C);
+    constexpr uint32_t idesc128 = HALF ? ptx::umma_idesc_f16(128, 2 * CT_C) : ptx::umma_idesc_bf16(128, 2 * CT_C);
     const uint64_t da0 = ptx::umma_desc_sw128(ptx::smem_u32(sm_a), CT_GROUP_STRIDE);
     const uint64_t db0 = ptx::umma_desc_sw128(ptx::smem_u32(sm_w), 1024);
     ptx::mbar_wait(&tail.wbar, 0);
@@ -332,6 +334,11 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_cons
               const float2 r2 = unpack2_f16(rh[j][e]);
               o[j * 16 + 2 * e] += r2.x;
               o[j * 16 + 2 * e + 1] += r2.y;
+              if (SPLIT) {
+                const float2 l2 = unpack2_f16(rl[j][e]);
+                o[j * 16 + 2 * e] += l2.x;
+                o[j * 16 + 2 * e + 1] += l2.y;
+              }
               continue;
             }
             o[j * 16 + 2 * e] += bf16lo_to_f32(rh[j][e]);
@@ -363,7 +370,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_cons
           uint32_t hw[8], lw[8];
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
-            if (OUT_DTYPE == COVA_BF16X2) split_bf16x2(o[j * 16 + 2 * e], o[j * 16 + 2 * e + 1], hw[e], lw[e]);
+            if (OUT_DTYPE == COVA_BF16X2 && HALF) split_f16x2(o[j * 16 + 2 * e], o[j * 16 + 2 * e + 1], hw[e], lw[e]);
+            else if (OUT_DTYPE == COVA_BF16X2) split_bf16x2(o[j * 16 + 2 * e], o[j * 16 + 2 * e + 1], hw[e], lw[e]);
             else if (HALF) hw[e] = pack2_f16(o[j * 16 + 2 * e], o[j * 16 + 2 * e + 1]);
             else hw[e] = pack2_bf16(o[j * 16 + 2 * e], o[j * 16 + 2 * e + 1]);
           }
@@ -435,6 +443,10 @@ int conv3x3_tc(const void* x_hi, const void* x_lo, int split, int half, int B, i
     case COVA_F32: return launch_conv_tc<SP, COVA_F32>(tx_hi, tx_lo, tw_hi, tw_lo, p, st);         \
     case COVA_BF16: return launch_conv_tc<SP, COVA_BF16>(tx_hi, tx_lo, tw_hi, tw_lo, p, st);       \
     default: return launch_conv_tc<SP, COVA_BF16X2>(tx_hi, tx_lo, tw_hi, tw_lo, p, st);            \
+  }
+  if (half && split) {   // split-fp16 planes in; split-fp16 planes or fp32 out (stored through the COVA_BF16X2 code path)
+    if (out_dtype == COVA_F32) return launch_conv_tc<true, COVA_F32, true>(tx_hi, tx_lo, tw_hi, tw_lo, p, st);
+    return launch_conv_tc<true, COVA_BF16X2, true>(tx_hi, tx_lo, tw_hi, tw_lo, p, st);
   }
   if (half) {   // fp16 plane in; fp16 plane or fp32 out (out_dtype COVA_F16 is stored through the COVA_BF16 code path)
     if (out_dtype == COVA_F32) return launch_conv_tc<false, COVA_F32, true>(tx_hi, tx_lo, tw_hi, tw_lo, p, st);

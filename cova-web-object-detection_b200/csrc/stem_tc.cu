@@ -100,12 +100,16 @@ stem_tc_kernel(const StemTcParams p) {
   const int n_strips = (p.Wc + SX_TM - 1) / SX_TM;
 
   if (threadIdx.x < 64) {
-    sm.scale[threadIdx.x] = p.raw_out ? 1.f : p.bn_scale[threadIdx.x];
+    sm.scale[threadIdx.x] = (p.raw_out ? 1.f : p.bn_scale[threadIdx.x]) * ((SPLIT && HALF) ? 1.f / SPLIT_F16_WSCALE : 1.f);
     sm.shift[threadIdx.x] = p.raw_out ? 0.f : p.bn_shift[threadIdx.x];
   }
   if (U8 && threadIdx.x < 256) {   // v/255 with IEEE division == torchvision ToTensor; split once per pixel value
     const float pv = __fdiv_rn((float)threadIdx.x, 255.f);
-    if (HALF) {
+    if (HALF && SPLIT) {
+      uint32_t h, l;
+      split_f16x2(pv, 0.f, h, l);
+      sm.lut[threadIdx.x] = (h & 0xffffu) | (l << 16);
+    } else if (HALF) {
       sm.lut[threadIdx.x] = pack2_f16(pv, 0.f);
     } else {
       __nv_bfloat16 h, l;
@@ -143,7 +147,7 @@ stem_tc_kernel(const StemTcParams p) {
     ptx::mbar_wait(&sm.wbar, 0);
     // Ahi x [Whi; Wlo] is ONE N = 128 MMA (operand feed: 64 clk instead of 2 x 48, see conv_tc.cu), Alo x Whi N = 64
     constexpr uint32_t idesc64 = HALF ? ptx::umma_idesc_f16(128, 64) : ptx::umma_idesc_bf16(128, 64);
-    constexpr uint32_t idesc128 = ptx::umma_idesc_bf16(128, 128);
+    constexpr uint32_t idesc128 = HALF ? ptx::umma_idesc_f16(128, 128) : ptx::umma_idesc_bf16(128, 128);
     const uint64_t da0 = desc_noswz(ptx::smem_u32(&sm.ring[0][0][0]), 16, 128);
     const uint64_t db0 = desc_noswz(ptx::smem_u32(&sm.w[0]), SX_W_CHUNK, 128);
     uint32_t t = 0;
@@ -232,7 +236,8 @@ stem_tc_kernel(const StemTcParams p) {
             for (int hlf = 0; hlf < SX_CH / 8; ++hlf) {
               uint32_t w8[8];
 #pragma unroll
-              for (int e = 0; e < 8; ++e) w8[e] = __float_as_uint(v[hlf * 8 + e]);
+              for (int e = 0; e < 8; ++e)
+                w8[e] = __float_as_uint((SPLIT && HALF) ? v[hlf * 8 + e] * (1.f / SPLIT_F16_WSCALE) : v[hlf * 8 + e]);
               st_global_v8(dst + hlf * 8, w8);
             }
           }
@@ -300,7 +305,8 @@ stem_tc_kernel(const StemTcParams p) {
               uint32_t hw[8], lw[8];
 #pragma unroll
               for (int e = 0; e < 8; ++e) {
-                if (OUT_DTYPE == COVA_BF16X2) split_bf16x2(o[c16 + 2 * e], o[c16 + 2 * e + 1], hw[e], lw[e]);
+                if (OUT_DTYPE == COVA_BF16X2 && HALF) split_f16x2(o[c16 + 2 * e], o[c16 + 2 * e + 1], hw[e], lw[e]);
+                else if (OUT_DTYPE == COVA_BF16X2) split_bf16x2(o[c16 + 2 * e], o[c16 + 2 * e + 1], hw[e], lw[e]);
                 else if (HALF) hw[e] = pack2_f16(o[c16 + 2 * e], o[c16 + 2 * e + 1]);
                 else hw[e] = pack2_bf16(o[c16 + 2 * e], o[c16 + 2 * e + 1]);
               }
@@ -400,7 +406,10 @@ stem_tc_kernel(const StemTcParams p) {
               const int i = 4 * wi + k - 1;                 // pixel index in the ring row
               if (i >= 0 && i < SX_NPX) {
                 uint32_t h01, l01, h2, l2;
-                if (HALF) {
+                if (HALF && SPLIT) {
+                  split_f16x2(c0[k], c1[k], h01, l01);
+                  split_f16x2(c2[k], 0.f, h2, l2);
+                } else if (HALF) {
                   h01 = pack2_f16(c0[k], c1[k]); h2 = pack2_f16(c2[k], 0.f); l01 = l2 = 0u;
                 } else {
                   split_bf16x2(c0[k], c1[k], h01, l01);
@@ -426,7 +435,10 @@ stem_tc_kernel(const StemTcParams p) {
           const int i = lane + 32 * j;
           if (i < SX_NPX) {
             uint32_t h01, l01, h2, l2;
-            if (HALF) {
+            if (HALF && SPLIT) {
+              split_f16x2(f[j][0], f[j][1], h01, l01);
+              split_f16x2(f[j][2], 0.f, h2, l2);
+            } else if (HALF) {
               h01 = pack2_f16(f[j][0], f[j][1]); h2 = pack2_f16(f[j][2], 0.f); l01 = l2 = 0u;
             } else {
               split_bf16x2(f[j][0], f[j][1], h01, l01);
@@ -478,6 +490,19 @@ __global__ void pack_stem_weight_f16_kernel(const float* __restrict__ w, __half*
   out[((chunk * 2 + 1) * 64 + co) * 8 + e] = __float2half_rn(0.f);
 }
 
+// split-fp16 filter: planes hi = f16(256 w), lo = f16(256 w - hi)
+__global__ void pack_stem_weight_f16x2_kernel(const float* __restrict__ w, __half* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= SX_KCHUNKS * 64 * 8) return;
+  const int e = i & 7, co = (i >> 3) & 63, chunk = i >> 9;
+  const int r = chunk >> 2, s = (chunk & 3) * 2 + (e >> 2), c = e & 3;
+  float v = 0.f;
+  if (s < 7 && c < 3) v = w[((co * 3 + c) * 7 + r) * 7 + s] * SPLIT_F16_WSCALE;
+  const __half h = __float2half_rn(v);
+  out[((chunk * 2 + 0) * 64 + co) * 8 + e] = h;
+  out[((chunk * 2 + 1) * 64 + co) * 8 + e] = __float2half_rn(v - __half2float(h));
+}
+
 template <bool SPLIT, int OUT_DTYPE, bool U8, int NCV, bool HALF>
 static int launch_stem_tc_n(const StemTcParams& p, int grid, cudaStream_t st) {
   auto kern = stem_tc_kernel<SPLIT, OUT_DTYPE, U8, NCV, HALF>;
@@ -494,7 +519,8 @@ static int launch_stem_tc(const StemTcParams& p, int grid, cudaStream_t st) {
 }
 
 static int stem_tc_impl(const void* images, int img_u8, int B, int H, int W, const void* w_packed, const float* bn_scale,
-                        const float* bn_shift, int out_dtype, void* out0, void* out1, cudaStream_t st, float* raw_out) {
+                        const float* bn_shift, int out_dtype, void* out0, void* out1, cudaStream_t st, float* raw_out,
+                        bool split_f16 = false) {
   StemTcParams p;
   p.raw_out = raw_out;
   p.img = images; p.B = B; p.H = H; p.W = W;
@@ -517,6 +543,12 @@ static int stem_tc_impl(const void* images, int img_u8, int B, int H, int W, con
   if (out_dtype == COVA_F16)   // fp16 mode: the filter comes from cova_pack_stem_weight_f16
     return img_u8 ? launch_stem_tc<false, COVA_BF16, true, true>(p, grid, st)
                   : launch_stem_tc<false, COVA_BF16, false, true>(p, grid, st);
+  if (out_dtype == COVA_F16X2 || split_f16)   // split-fp16 mode: the filter comes from cova_pack_stem_weight_f16x2
+    return out_dtype == COVA_F32
+               ? (img_u8 ? launch_stem_tc<true, COVA_F32, true, true>(p, grid, st)
+                         : launch_stem_tc<true, COVA_F32, false, true>(p, grid, st))
+               : (img_u8 ? launch_stem_tc<true, COVA_BF16X2, true, true>(p, grid, st)
+                         : launch_stem_tc<true, COVA_BF16X2, false, true>(p, grid, st));
   const bool split = out_dtype != COVA_BF16;   // bf16 output <=> bf16 mode; fp32 / split outputs use the 3-product mode
 #define GO(SP, DT) (img_u8 ? launch_stem_tc<SP, DT, true>(p, grid, st) : launch_stem_tc<SP, DT, false>(p, grid, st))
   if (split) {
@@ -553,10 +585,19 @@ extern "C" int cova_pack_stem_weight_f16(const float* w_oihw, void* packed, void
 // A2, training mode: conv1 alone (7x7 s2 p3, fp32-parity tensor-core mode) -> [B, H/2, W/2, 64] fp32 NHWC, no BN, no
 // ReLU, no pooling: nn.BatchNorm2d in train mode needs the batch statistics of this tensor (`train.py:27`).
 extern "C" int cova_stem_conv_raw_fwd(const void* images, int img_dtype, int B, int H, int W, const void* w_packed,
-                                      float* out, void* stream) {
+                                      int w_dtype, float* out, void* stream) {
+  COVA_REQUIRE(w_dtype == COVA_BF16X2 || w_dtype == COVA_F16X2, "cova_stem_conv_raw_fwd: w_dtype is the packed filter's format");
   COVA_REQUIRE(images && w_packed && out && B > 0 && H >= 7 && W >= 7, "cova_stem_conv_raw_fwd: bad arguments");
   COVA_REQUIRE(img_dtype == COVA_F32 || img_dtype == COVA_U8, "cova_stem_conv_raw_fwd: images must be fp32 or uint8");
   COVA_REQUIRE(((uintptr_t)out & 31) == 0, "cova_stem_conv_raw_fwd: out must be 32-byte aligned");
   return cova::stem_tc_impl(images, img_dtype == COVA_U8, B, H, W, w_packed, nullptr, nullptr, COVA_F32, out, nullptr,
-                            (cudaStream_t)stream, out);
+                            (cudaStream_t)stream, out, w_dtype == COVA_F16X2);
+}
+
+extern "C" int cova_pack_stem_weight_f16x2(const float* w_oihw, void* packed, void* stream) {
+  COVA_REQUIRE(w_oihw && packed, "cova_pack_stem_weight_f16x2: null pointer");
+  cova::pack_stem_weight_f16x2_kernel<<<cova::ceil_div(cova::SX_KCHUNKS * 64 * 8, 256), 256, 0, (cudaStream_t)stream>>>(
+      w_oihw, (__half*)packed);
+  COVA_LAUNCH_OK();
+  return COVA_OK;
 }

@@ -13,7 +13,7 @@ Stage order = ``CoVA.forward`` (`/root/reference/models.py:94-122`):
 import torch
 
 from . import ops
-from .ops import BF16, BF16X2, ENGINE_SIMT, ENGINE_TCGEN05, F16, F32
+from .ops import BF16, BF16X2, ENGINE_SIMT, ENGINE_TCGEN05, F16, F16X2, F32
 
 
 def fold_bn(bn):
@@ -42,14 +42,16 @@ class NativeForward:
         m, c = self.m, {}
         r50 = m.backbone == "resnet50"
         tc = m.engine == "tcgen05"
-        split = m.precision == "fp32" or r50          # the ResNet-50 tensor-core path is fp32-parity only
+        split = m.precision in ("fp32", "fp32x") or r50   # the ResNet-50 tensor-core path is split-bf16 only
         half = tc and m.precision == "fp16" and not r50
+        split16 = tc and m.precision == "fp32x" and not r50          # split-fp16 ("fp16x3"): ResNet-18 stack
         c["tc"] = tc
-        c["act_dtype"] = (BF16X2 if split else (F16 if half else BF16)) if tc else F32
+        c["act_dtype"] = ((F16X2 if split16 else BF16X2) if split else (F16 if half else BF16)) if tc else F32
         cn = m.convnet
         c["stem_w"] = cn[0].weight.detach().float().contiguous()
         if tc:
-            c["stem_w"] = ops.pack_stem_weight_f16(c["stem_w"]) if half else ops.pack_stem_weight(c["stem_w"])
+            c["stem_w"] = (ops.pack_stem_weight_f16(c["stem_w"]) if half else
+                           ops.pack_stem_weight_f16x2(c["stem_w"]) if split16 else ops.pack_stem_weight(c["stem_w"]))
         c["stem_bn"] = fold_bn(cn[1])
         blocks = []
         for blk in cn[4]:
@@ -59,6 +61,8 @@ class NativeForward:
                     conv, bn = getattr(blk, f"conv{i}"), getattr(blk, f"bn{i}")
                     if half:
                         d[f"w{i}"] = (ops.pack_conv_weight_f16(conv.weight.detach().float()), None)
+                    elif split16:
+                        d[f"w{i}"] = ops.pack_conv_weight_f16x2(conv.weight.detach().float())
                     else:
                         s, hi, lo = ops.pack_conv_weight(conv.weight.detach().float(), simt=not tc, tc=tc, split=split)
                         d[f"w{i}"] = (hi, lo) if tc else (s, None)

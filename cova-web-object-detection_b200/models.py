@@ -6,7 +6,8 @@ constructor arguments, ``forward`` signature, attributes and ``state_dict`` keys
 Execution:
   * inference (``torch.no_grad()``, ``model.eval()``, CUDA tensors) runs the hand-written sm_100a kernels of
     ``libcova_b200.so`` through ``engine.NativeForward`` - engine ``"tcgen05"`` (tensor-core convolutions,
-    precision ``"fp32"`` = split-bf16 3-product fp32-parity mode, ``"fp16"`` = one fp16 product (ResNet-18 backbone;
+    precision ``"fp32"`` = split-bf16 3-product fp32-parity mode (1e-5), ``"fp32x"`` = the same three products on
+    split-fp16 planes (22 significand bits: ~1e-6, same cost; ResNet-18 stack), ``"fp16"`` = one fp16 product (ResNet-18 backbone;
     ~5e-4 on the logits, inside the 1e-3 bar), or ``"bf16"`` (3-4e-3: outside the bar)) or ``"simt"`` (exact fp32
     CUDA cores).
   * anything that needs autograd (``train.py:45-60``) or batch statistics runs a PyTorch-operator composite
@@ -267,8 +268,8 @@ class CoVA(nn.Module):
         self.roi_mode = roi_mode
         self.engine = engine or os.environ.get("COVA_B200_ENGINE", "tcgen05")
         self.precision = precision or os.environ.get("COVA_B200_PRECISION", "fp32")
-        if self.engine not in ("tcgen05", "simt") or self.precision not in ("fp32", "bf16", "fp16") or roi_mode not in ("pool", "align"):
-            raise ValueError("engine in {tcgen05, simt}, precision in {fp32, bf16, fp16}, roi_mode in {pool, align}")
+        if self.engine not in ("tcgen05", "simt") or self.precision not in ("fp32", "fp32x", "bf16", "fp16") or roi_mode not in ("pool", "align"):
+            raise ValueError("engine in {tcgen05, simt}, precision in {fp32, fp32x, bf16, fp16}, roi_mode in {pool, align}")
 
         ##### REPRESENTATION NETWORK (RN) #####
         self.convnet, C = _truncated_resnet(backbone)

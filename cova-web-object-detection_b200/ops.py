@@ -4,7 +4,7 @@ CPU path here (the CPU restatement lives in ``oracle/`` and is test infrastructu
 import torch
 
 from . import _lib
-from ._lib import BF16, BF16X2, ENGINE_SIMT, ENGINE_TCGEN05, F16, F32, U8  # noqa: F401
+from ._lib import BF16, BF16X2, ENGINE_SIMT, ENGINE_TCGEN05, F16, F16X2, F32, U8  # noqa: F401
 
 ENGINES = {"simt": ENGINE_SIMT, "tcgen05": ENGINE_TCGEN05}
 
@@ -41,9 +41,9 @@ class Planes:
 
     def __init__(self, dtype, shape, device):
         self.dtype, self.shape = dtype, tuple(shape)
-        td = torch.float32 if dtype == F32 else (torch.float16 if dtype == F16 else torch.bfloat16)
+        td = torch.float32 if dtype == F32 else (torch.float16 if dtype in (F16, F16X2) else torch.bfloat16)
         self.p0 = torch.empty(self.shape, dtype=td, device=device)
-        self.p1 = torch.empty(self.shape, dtype=td, device=device) if dtype == BF16X2 else None
+        self.p1 = torch.empty(self.shape, dtype=td, device=device) if dtype in (BF16X2, F16X2) else None
 
     def float(self):
         """fp32 NHWC view of the value (hi + lo for split-bf16)."""
@@ -103,6 +103,25 @@ def pack_stem_weight_f16(w_oihw):
     out = torch.empty((28, 2, 64, 8), dtype=torch.float16, device=w_oihw.device)
     _call("cova_pack_stem_weight_f16", w_oihw.contiguous().data_ptr(), out.data_ptr(), _stream())
     return out
+
+
+def pack_stem_weight_f16x2(w_oihw):
+    """split-fp16 stem filter ([28,2,64,8] fp16: hi / lo planes of 256*w)."""
+    _cuda(w_oihw, torch.float32, "w")
+    out = torch.empty((28, 2, 64, 8), dtype=torch.float16, device=w_oihw.device)
+    _call("cova_pack_stem_weight_f16x2", w_oihw.contiguous().data_ptr(), out.data_ptr(), _stream())
+    return out
+
+
+def pack_conv_weight_f16x2(w_oihw):
+    """OIHW fp32 -> (hi, lo) fp16 [kh*kw, Cout, Cin] planes of 256*w for the split-fp16 mode."""
+    _cuda(w_oihw, torch.float32, "w")
+    w = w_oihw.contiguous()
+    Co, Ci, kh, kw = w.shape
+    hi = torch.empty((kh * kw, Co, Ci), dtype=torch.float16, device=w.device)
+    lo = torch.empty_like(hi)
+    _call("cova_pack_conv_weight_f16x2", w.data_ptr(), Co, Ci, kh, kw, hi.data_ptr(), lo.data_ptr(), _stream())
+    return hi, lo
 
 
 def pack_conv_weight_f16(w_oihw):
@@ -356,34 +375,32 @@ def _nhwc(t, name):
     return t
 
 
-def _planes_like(x):
-    pl = Planes.__new__(Planes)
-    pl.dtype, pl.shape = BF16X2, tuple(x.shape)
-    pl.p0 = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
-    pl.p1 = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
-    return pl
+def _planes_like(x, dtype=BF16X2):
+    return Planes(dtype, tuple(x.shape), x.device)
 
 
-def split_planes(x):
-    """fp32 NHWC tensor -> split-bf16 `Planes` (hi = bf16(x), lo = bf16(x - hi))."""
+def split_planes(x, dtype=BF16X2):
+    """fp32 NHWC tensor -> split `Planes` (hi = r(x), lo = r(x - hi); r = bf16 for BF16X2, fp16 for F16X2)."""
     _nhwc(x, "x")
-    pl = _planes_like(x)
-    _call("cova_split_planes", x.data_ptr(), x.numel(), pl.p0.data_ptr(), pl.p1.data_ptr(), _stream())
+    pl = _planes_like(x, dtype)
+    _call("cova_split_planes", x.data_ptr(), x.numel(), pl.p0.data_ptr(), pl.p1.data_ptr(), dtype, _stream())
     return pl
 
 
 def stem_conv_raw_fwd(images, w_packed):
-    """conv1 alone (training mode): images [B,3,H,W] fp32 / uint8 NCHW -> raw conv output [B,H/2,W/2,64] fp32 NHWC."""
+    """conv1 alone (training mode): images [B,3,H,W] fp32 / uint8 NCHW -> raw conv output [B,H/2,W/2,64] fp32 NHWC.
+    w_packed from pack_stem_weight (bf16: split-bf16 products) or pack_stem_weight_f16x2 (fp16: split-fp16)."""
     _cuda(images, None, "images")
     images = images.contiguous()
     B, C, H, W = images.shape
     out = torch.empty((B, (H - 1) // 2 + 1, (W - 1) // 2 + 1, 64), dtype=torch.float32, device=images.device)
     _call("cova_stem_conv_raw_fwd", images.data_ptr(), U8 if images.dtype == torch.uint8 else F32, B, H, W,
-          w_packed.data_ptr(), out.data_ptr(), _stream())
+          w_packed.data_ptr(), F16X2 if w_packed.dtype == torch.float16 else BF16X2, out.data_ptr(), _stream())
     return out
 
 
-def bn_train_fwd(x, gamma, beta, running_mean, running_var, momentum, eps, res=None, relu=True, want_planes=False):
+def bn_train_fwd(x, gamma, beta, running_mean, running_var, momentum, eps, res=None, relu=True, want_planes=False,
+                 planes_dtype=BF16X2):
     """BatchNorm2d with batch statistics (+ residual) (+ ReLU) on an NHWC fp32 map x [..., C]; updates the running
     statistics in place (pass None to skip).  Returns (y, mean [C], invstd [C], split-bf16 Planes of y or None)."""
     _nhwc(x, "x")
@@ -393,13 +410,13 @@ def bn_train_fwd(x, gamma, beta, running_mean, running_var, momentum, eps, res=N
     ws = torch.empty(2 * C, dtype=torch.float64, device=dev)
     mean, inv = torch.empty(C, dtype=torch.float32, device=dev), torch.empty(C, dtype=torch.float32, device=dev)
     y = torch.empty_like(x)
-    pl = _planes_like(x) if want_planes else None
+    pl = _planes_like(x, planes_dtype) if want_planes else None
     _call("cova_bn_train_stats", x.data_ptr(), M, C, ws.data_ptr(), _stream())
     _call("cova_bn_train_finalize", ws.data_ptr(), M, C, float(eps), float(momentum), mean.data_ptr(), inv.data_ptr(),
           _ptr(running_mean), _ptr(running_var), _stream())
     _call("cova_bn_act_fwd", x.data_ptr(), M, C, mean.data_ptr(), inv.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
           _ptr(None if res is None else _nhwc(res, "res")), int(relu), y.data_ptr(),
-          pl.p0.data_ptr() if pl else 0, pl.p1.data_ptr() if pl else 0, _stream())
+          pl.p0.data_ptr() if pl else 0, pl.p1.data_ptr() if pl else 0, planes_dtype, _stream())
     return y, mean, inv, pl
 
 
@@ -419,15 +436,15 @@ def bn_train_bwd(dy, x, mean, invstd, gamma, beta, res=None, relu=True, want_dre
     return dx, dres, dg, db
 
 
-def maxpool3x3s2_fwd(x, want_planes=False):
+def maxpool3x3s2_fwd(x, want_planes=False, planes_dtype=BF16X2):
     """nn.MaxPool2d(3, 2, 1) on an NHWC fp32 map [B,H,W,C]: returns (y, winner codes uint8 like y, Planes of y or None)."""
     _nhwc(x, "x")
     B, H, W, C = x.shape
     y = torch.empty((B, (H - 1) // 2 + 1, (W - 1) // 2 + 1, C), dtype=torch.float32, device=x.device)
     code = torch.empty(y.shape, dtype=torch.uint8, device=x.device)
-    pl = _planes_like(y) if want_planes else None
+    pl = _planes_like(y, planes_dtype) if want_planes else None
     _call("cova_maxpool3x3s2_fwd", x.data_ptr(), B, H, W, C, y.data_ptr(), code.data_ptr(),
-          pl.p0.data_ptr() if pl else 0, pl.p1.data_ptr() if pl else 0, _stream())
+          pl.p0.data_ptr() if pl else 0, pl.p1.data_ptr() if pl else 0, planes_dtype, _stream())
     return y, code, pl
 
 

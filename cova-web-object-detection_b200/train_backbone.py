@@ -2,8 +2,8 @@
 `model.train()` (`train.py:27`), i.e. BatchNorm with BATCH statistics and autograd, NHWC end to end.
 
 Native (libcova_b200.so): every FORWARD convolution that has a tensor-core kernel here - conv1 (`cova_stem_conv_raw_fwd`)
-and the 3x3 64->64 convolutions (`cova_conv3x3_bn_act_fwd` with an identity epilogue), both in the fp32-parity
-split-bf16 mode; BatchNorm(batch statistics) + residual + ReLU forward / backward (`cova_bn_train_*`, `cova_bn_act_*`),
+and the 3x3 64->64 convolutions (`cova_conv3x3_bn_act_fwd` with an identity epilogue), both in the split-fp16
+three-product mode (activations to ~1e-6); BatchNorm(batch statistics) + residual + ReLU forward / backward (`cova_bn_train_*`, `cova_bn_act_*`),
 which also emit the split planes the next convolution consumes; the stem's maxpool forward / backward.
 Library, interim: the convolutions' BACKWARD (dgrad / wgrad) through
 `aten.convolution_backward` (cuDNN), and the ResNet-50 1x1 convolutions.
@@ -16,7 +16,7 @@ import torch
 import torch.nn.functional as F
 
 from . import ops
-from .ops import ENGINE_TCGEN05, F32
+from .ops import ENGINE_TCGEN05, F16X2, F32
 
 _CONST = {}
 
@@ -40,7 +40,7 @@ class _BnActFn(torch.autograd.Function):
         track = bn.track_running_stats and bn.running_mean is not None
         y, mean, inv, pl = ops.bn_train_fwd(x, gamma.detach(), beta.detach(), bn.running_mean if track else None,
                                             bn.running_var if track else None, mom, bn.eps, res=res_c, relu=relu,
-                                            want_planes=want_planes)
+                                            want_planes=want_planes, planes_dtype=F16X2)
         if track and bn.num_batches_tracked is not None:
             bn.num_batches_tracked += 1
         ctx.save_for_backward(x, mean, inv, gamma.detach(), beta.detach(), res_c if (relu and res is not None) else None)
@@ -63,7 +63,7 @@ class _MaxPoolFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, want_planes):
         x = x.contiguous()
-        y, code, pl = ops.maxpool3x3s2_fwd(x, want_planes=want_planes)
+        y, code, pl = ops.maxpool3x3s2_fwd(x, want_planes=want_planes, planes_dtype=F16X2)
         ctx.save_for_backward(code)
         ctx.in_shape = tuple(x.shape)
         if pl is None:
@@ -78,12 +78,15 @@ class _MaxPoolFn(torch.autograd.Function):
 
 
 def _conv_bwd(dy_nhwc, x_nchw, weight, stride, padding, need_input):
-    """Library backward of a convolution (cuDNN dgrad / wgrad through ATen).  fp32 by default, like the reference;
-    COVA_B200_TRAIN_TF32=1 lets cuDNN use TF32 tensor cores here (gradients to ~1e-3 instead of ~1e-6)."""
-    tf32 = os.environ.get("COVA_B200_TRAIN_TF32", "0") == "1"
-    with torch.backends.cudnn.flags(enabled=True, allow_tf32=tf32):
-        gi, gw, _ = torch.ops.aten.convolution_backward(dy_nhwc.permute(0, 3, 1, 2), x_nchw, weight, None, stride,
-                                                        padding, [1, 1], False, [0, 0], 1, [need_input, True, False])
+    """Library backward of a convolution (cuDNN dgrad / wgrad through ATen) under the process's own cuDNN flags - the
+    same policy as the backward of an `F.conv2d` in the all-library path; COVA_B200_TRAIN_TF32=1 forces TF32 on."""
+    args = (dy_nhwc.permute(0, 3, 1, 2), x_nchw, weight, None, stride, padding, [1, 1], False, [0, 0], 1,
+            [need_input, True, False])
+    if os.environ.get("COVA_B200_TRAIN_TF32", "0") == "1":
+        with torch.backends.cudnn.flags(enabled=True, allow_tf32=True):
+            gi, gw, _ = torch.ops.aten.convolution_backward(*args)
+    else:
+        gi, gw, _ = torch.ops.aten.convolution_backward(*args)
     return gi, gw
 
 
@@ -92,7 +95,7 @@ class _StemConvFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, images, weight):
-        out = ops.stem_conv_raw_fwd(images, ops.pack_stem_weight(weight.detach().float().contiguous()))
+        out = ops.stem_conv_raw_fwd(images, ops.pack_stem_weight_f16x2(weight.detach().float().contiguous()))
         ctx.save_for_backward(images, weight)
         return out
 
@@ -111,8 +114,8 @@ class _Conv3x3Fn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, x_hi, x_lo, weight):
         pl = ops.Planes.__new__(ops.Planes)
-        pl.dtype, pl.shape, pl.p0, pl.p1 = ops.BF16X2, tuple(x.shape), x_hi, x_lo
-        _, w_hi, w_lo = ops.pack_conv_weight(weight.detach().float(), simt=False, tc=True, split=True)
+        pl.dtype, pl.shape, pl.p0, pl.p1 = F16X2, tuple(x.shape), x_hi, x_lo
+        w_hi, w_lo = ops.pack_conv_weight_f16x2(weight.detach().float())
         one, zero = _ones_zeros(x.device)
         y = ops.conv3x3_bn_act_fwd(pl, w_hi, w_lo, one, zero, res=None, relu=False, out_dtype=F32, engine=ENGINE_TCGEN05)
         ctx.save_for_backward(x, weight)
@@ -126,12 +129,13 @@ class _Conv3x3Fn(torch.autograd.Function):
 
 
 def tc_forward_convs():
-    """COVA_B200_TRAIN_CONV=tcgen05 runs the training FORWARD convolutions on the tensor cores (fp32-parity split-bf16
-    mode: activations to ~1e-5).  Default "cudnn" = plain fp32 library convolutions: with train-mode BatchNorm1d over
-    only T boxes in the decoder, a 1e-5 perturbation of the feature map is amplified by 1/sqrt(var + eps) of
-    near-constant features, and on the 24-box live-reference fixture the GRADIENTS then deviate by 1-2 % (forward
-    logits still agree to 3e-5) - outside the 2e-3 gradient bar, so the exact path stays the default."""
-    return os.environ.get("COVA_B200_TRAIN_CONV", "cudnn") == "tcgen05"
+    """The training FORWARD convolutions run on the tensor cores in the split-fp16 three-product mode (default;
+    COVA_B200_TRAIN_CONV=cudnn selects plain fp32 library convolutions instead).  Precision matters here more than on
+    the inference path: the decoder's train-mode BatchNorm1d makes the GRADIENTS jump by 1-2 % when the feature map is
+    perturbed at the 1e-5 level (measured both with the split-bf16 forward and with 1e-5 noise injected into the
+    all-library path, profiles/r01l_train_grad_conditioning.txt), while the split-fp16 forward (logits to 5e-6) leaves
+    every gradient within 1.2e-5 of the live-reference fixture - the same as the all-library path."""
+    return os.environ.get("COVA_B200_TRAIN_CONV", "tcgen05") == "tcgen05"
 
 
 def _tc_conv_ok(conv):

@@ -20,6 +20,10 @@
  *      COVA_F16   one fp16 plane (`p0`): the single-product throughput mode of the tcgen05 engine.  fp16 keeps
  *                 11 significand bits (bf16: 8), which is what brings a one-product pipeline inside the 1e-3 bar
  *                 (measured ~5e-4 on the logits); activations must stay below 65504 (post-BN/ReLU maps do).
+ *      COVA_F16X2 split-fp16: `p0` = f16(x), `p1` = f16(x - p0): 22 significand bits, so the same three tensor-core
+ *                 products reproduce an fp32 convolution to ~1e-6 (split-bf16: ~1e-5) at the same cost ("fp16x3").
+ *                 Filters of this mode are packed pre-scaled by 256 (undone exactly in the kernels' epilogue) so that
+ *                 their lo plane stays a normal fp16 number.
  *  - Eval-mode BatchNorm is passed folded: y = x*scale[c] + shift[c]
  *    (scale = weight/sqrt(running_var+eps), shift = bias - running_mean*scale).
  */
@@ -35,7 +39,7 @@ extern "C" {
 #define COVA_ABI_VERSION 1
 
 enum { COVA_OK = 0, COVA_ERR_ARG = 1, COVA_ERR_CUDA = 2, COVA_ERR_UNSUPPORTED = 3 };
-enum { COVA_F32 = 0, COVA_BF16 = 1, COVA_BF16X2 = 2, COVA_U8 = 3 /* images only */, COVA_F16 = 4 };
+enum { COVA_F32 = 0, COVA_BF16 = 1, COVA_BF16X2 = 2, COVA_U8 = 3 /* images only */, COVA_F16 = 4, COVA_F16X2 = 5 };
 enum { COVA_ENGINE_SIMT = 0, COVA_ENGINE_TCGEN05 = 1 };
 
 int cova_abi_version(void);
@@ -71,18 +75,21 @@ int cova_debug_buffer(void* dev_words, int64_t n_words);
  *           engine TCGEN05: the split-bf16 K-chunked filter written by cova_pack_stem_weight
  *   bn_scale/bn_shift [64] folded `convnet.1`
  *   out     NHWC [B,H/4,W/4,64] in `out_dtype` (planes out0/out1).  TCGEN05: COVA_BF16 / COVA_F16 output selects
- *           the single-product bf16 / fp16 mode, COVA_BF16X2 / COVA_F32 the 3-product fp32-parity mode.   */
+ *           the single-product bf16 / fp16 mode, COVA_BF16X2 / COVA_F32 the 3-product split-bf16 mode, COVA_F16X2
+ *           the 3-product split-fp16 mode (filter from cova_pack_stem_weight_f16x2).                      */
 int cova_stem_fwd(const void* images, int img_dtype, int B, int H, int W, const void* w, const float* bn_scale,
                   const float* bn_shift, int out_dtype, void* out0, void* out1, int engine, void* stream);
 
 /* Training mode (A9): conv1 ALONE in the fp32-parity tensor-core mode -> out [B, Hc, Wc, 64] fp32 NHWC (Hc = (H-1)/2+1),
  * no BN / ReLU / pooling: BatchNorm with batch statistics needs this tensor itself (`train.py:27`).  w = the
  * cova_pack_stem_weight filter.                                                                          */
-int cova_stem_conv_raw_fwd(const void* images, int img_dtype, int B, int H, int W, const void* w_packed, float* out,
-                           void* stream);
+int cova_stem_conv_raw_fwd(const void* images, int img_dtype, int B, int H, int W, const void* w_packed, int w_dtype,
+                           float* out, void* stream);   /* w_dtype: COVA_BF16X2 (cova_pack_stem_weight) or COVA_F16X2 */
 
 /* Same layout for the fp16 mode (out_dtype COVA_F16): plane 0 = fp16(w), plane 1 = 0. */
 int cova_pack_stem_weight_f16(const float* w_oihw, void* packed, void* stream);
+/* Same layout for the split-fp16 mode (out_dtype COVA_F16X2): planes of 256*w. */
+int cova_pack_stem_weight_f16x2(const float* w_oihw, void* packed, void* stream);
 
 /* OIHW fp32 [64,3,7,7] -> tcgen05 stem filter: bf16 [28 K-chunks][2 planes (hi, lo)][64 cout][8],
  * K index = r*32 + s*4 + c with zero weights at s = 7 and c = 3 (57,344 bytes).                       */
@@ -114,6 +121,9 @@ int cova_pack_conv_weight(const float* w_oihw, int Cout, int Cin, int kh, int kw
 
 /* OIHW fp32 -> fp16 [kh*kw][Cout][Cin] for the COVA_F16 mode of cova_conv3x3_bn_act_fwd (w_a = this, w_b = NULL). */
 int cova_pack_conv_weight_f16(const float* w_oihw, int Cout, int Cin, int kh, int kw, void* tc_f16, void* stream);
+/* OIHW fp32 -> split-fp16 planes [kh*kw][Cout][Cin] of 256*w for the COVA_F16X2 mode (w_a = hi, w_b = lo). */
+int cova_pack_conv_weight_f16x2(const float* w_oihw, int Cout, int Cin, int kh, int kw, void* tc_hi, void* tc_lo,
+                                void* stream);
 
 /* ---- A4: RoIPool.  Replaces `torchvision.ops.RoIPool(P, scale)` (`models.py:58`, `:125-127`).
  * Bit-exact in fp32.  fm NHWC fp32 [B,Hf,Wf,C]; rois [T,5] fp32 = [batch_idx,x1,y1,x2,y2] image pixels.
@@ -228,9 +238,10 @@ int cova_bn_train_stats(const float* x, int64_t M, int C, double* ws, void* stre
 int cova_bn_train_finalize(const double* ws, int64_t M, int C, float eps, float momentum, float* mean, float* invstd,
                            float* running_mean, float* running_var, void* stream);
 int cova_bn_act_fwd(const float* x, int64_t M, int C, const float* mean, const float* invstd, const float* gamma,
-                    const float* beta, const float* res, int relu, float* y, void* y_hi, void* y_lo, void* stream);
-/*   y_hi / y_lo (optional, both or neither): the same result as split-bf16 planes - the operand format of the
- *   tensor-core convolution that consumes it (cova_conv3x3_bn_act_fwd with COVA_BF16X2 input).                    */
+                    const float* beta, const float* res, int relu, float* y, void* y_hi, void* y_lo, int planes_dtype,
+                    void* stream);
+/*   y_hi / y_lo (optional, both or neither): the same result as split planes in `planes_dtype` (COVA_BF16X2 or
+ *   COVA_F16X2) - the operand format of the tensor-core convolution that consumes it.                              */
 int cova_bn_act_bwd(const float* dy, const float* x, const float* res, int64_t M, int C, const float* mean,
                     const float* invstd, const float* gamma, const float* beta, int relu, double* ws, float* dx,
                     float* dres, float* dgamma, float* dbeta, void* stream);
@@ -241,11 +252,11 @@ int cova_bn_act_bwd(const float* dy, const float* x, const float* res, int64_t M
  * inside the window, which is all the backward needs; y_hi / y_lo optional split-bf16 planes of y.
  * dx [B,H,W,C] is overwritten (gather over the <= 2x2 windows containing a pixel: no atomics, no rescans).          */
 int cova_maxpool3x3s2_fwd(const float* x, int B, int H, int W, int C, float* y, unsigned char* code, void* y_hi,
-                          void* y_lo, void* stream);
+                          void* y_lo, int planes_dtype, void* stream);
 int cova_maxpool3x3s2_bwd(const unsigned char* code, const float* dy, int B, int H, int W, int C, float* dx, void* stream);
 
-/* fp32 [n] -> split-bf16 planes hi = bf16(x), lo = bf16(x - hi) (n % 4 == 0). */
-int cova_split_planes(const float* x, int64_t n, void* hi, void* lo, void* stream);
+/* fp32 [n] -> split planes hi = r(x), lo = r(x - hi), r = bf16 (COVA_BF16X2) or fp16 (COVA_F16X2) rounding (n % 4 == 0). */
+int cova_split_planes(const float* x, int64_t n, void* hi, void* lo, int planes_dtype, void* stream);
 
 #ifdef __cplusplus
 }

@@ -80,7 +80,7 @@ def test_maxpool_fwd_bwd_vs_torch_with_ties(shape):
 
 
 @pytest.mark.parametrize("backbone,conv,tol", [("resnet18", "cudnn", 2e-3), ("resnet50", "cudnn", 6e-2),
-                                               ("resnet18", "tcgen05", 0.15)])
+                                               ("resnet18", "tcgen05", 2e-3)])
 def test_train_backbone_matches_torch_composite(backbone, conv, tol, monkeypatch):
     """Whole train-mode step on both paths of the same model: native BatchNorm / maxpool (NHWC) vs the PyTorch-operator
     composite (`COVA_B200_TRAIN_BACKBONE=torch`): logits, loss gradients of every parameter, BatchNorm buffers."""
@@ -91,9 +91,7 @@ def test_train_backbone_matches_torch_composite(backbone, conv, tol, monkeypatch
     # agrees to 5e-6 as well, but the gradient that leaves it through cuDNN's NHWC dgrad of the 1x1 convolutions (a
     # tensor-op fp32 kernel) differs from the NCHW algorithm by ~1e-3, and the train-mode BatchNorms upstream amplify
     # that to 0.3-3 % - library behaviour on the interim path, hence the loose bound.
-    # conv="tcgen05": forward convolutions on the tensor cores (1e-5 on the activations); the decoder's train-mode
-    # BatchNorm1d over 24 boxes amplifies that to percent-level gradient deviations (train_backbone.tc_forward_convs),
-    # hence the loose bound there and the exact library forward as the default
+    # conv="tcgen05" (the default): forward convolutions on the tensor cores, split-fp16 three-product mode
     monkeypatch.setenv("COVA_B200_TRAIN_CONV", conv)
     m1 = CoVA((3, 3), 128, 4, True, 384, 32, 0, 0.0, None, pretrained=False, backbone=backbone)
     m1.load_state_dict(synth.make_state_dict(123, backbone=backbone), strict=True)
@@ -137,7 +135,7 @@ def test_stem_conv_raw_and_conv3x3_functions_vs_torch():
 
         x = torch.randn(2, 37, 45, 64, generator=g).to(DEV).requires_grad_(True)
         w = (torch.randn(64, 64, 3, 3, generator=g) * 0.05).to(DEV).requires_grad_(True)
-        pl = ops.split_planes(x.detach())
+        pl = ops.split_planes(x.detach(), ops.F16X2)
         y = _Conv3x3Fn.apply(x, pl.p0, pl.p1, w)
         dy = torch.randn(y.shape, generator=g).to(DEV)
         y.backward(dy)
