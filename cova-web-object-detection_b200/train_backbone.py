@@ -103,6 +103,9 @@ class _StemConvFn(torch.autograd.Function):
     def backward(ctx, dy):
         images, weight = ctx.saved_tensors
         x = images.float().div(255) if images.dtype == torch.uint8 else images
+        # the gradient arrives NHWC: give cuDNN the (3-channel, cheap) image in channels_last as well, otherwise it
+        # transposes the 1.7 GB gradient map to NCHW first (3.9 ms of a 21 ms step)
+        x = x.contiguous(memory_format=torch.channels_last)
         _, gw = _conv_bwd(dy.contiguous(), x, weight, [2, 2], [3, 3], False)
         return None, gw
 
