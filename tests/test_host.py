@@ -180,3 +180,17 @@ def test_native_tail_fails_loudly_on_cpu_tensors():
         CrossEntropyLossSum()(torch.zeros(3, 4), torch.zeros(3, dtype=torch.long))
     with _pytest.raises(RuntimeError, match="CUDA"):
         FlatAdam([torch.nn.Parameter(torch.zeros(5))], lr=1e-3)
+
+
+def test_page_offsets_and_numa_binding_host_logic():
+    """Host-side helpers of the native callers: page offsets of a collated batch (pages are contiguous row ranges,
+    `datasets.py:170-181`) and the NUMA binding helper (returns None instead of raising when NVML has no device)."""
+    import torch
+    from cova_b200.pipeline import bind_to_gpu_numa
+    from cova_b200.train_ops import page_offsets_of
+    bb = torch.zeros(9, 5)
+    bb[:, 0] = torch.tensor([0, 0, 0, 1, 2, 2, 2, 2, 2]).float()
+    assert page_offsets_of(bb).tolist() == [0, 3, 4, 9]
+    assert page_offsets_of(torch.zeros(0, 5)).tolist() == [0]
+    cores = bind_to_gpu_numa(0)
+    assert cores is None or (isinstance(cores, list) and len(cores) > 0)
