@@ -35,12 +35,30 @@ STEM_FLOP_PER_PAGE = 2 * 64 * 147 * 640 * 640
 
 
 def peaks():
+    """Measured roofline denominators (driver-written MEASURED_PEAKS.json) or the profiling guide's fallback."""
+    fallback = dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, src="fallback")
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.exists(p):
+    if not os.path.exists(p):
+        return fallback
+    try:
         d = json.load(open(p))
-        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sust=d.get("bf16_tflops_sustained", d["bf16_tflops"]),
-                    src="measured")
-    return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, src="fallback")
+
+        def pick(*names):
+            for n in names:
+                if n in d and isinstance(d[n], (int, float)):
+                    return float(d[n])
+            for k, v in d.items():                      # tolerate renamed keys: match on substrings
+                if isinstance(v, (int, float)) and all(t in k.lower() for t in names[0].split("_")[:1]):
+                    return float(v)
+            return None
+        hbm = pick("hbm_gbs", "hbm_gb_s", "hbm_GBs", "hbm")
+        burst = pick("bf16_tflops", "bf16_tflops_burst", "bf16")
+        sust = pick("bf16_tflops_sustained", "bf16_sustained_tflops") or burst
+        if hbm and burst:
+            return dict(hbm=hbm, tf_burst=burst, tf_sust=sust, src="measured")
+    except Exception:
+        pass
+    return fallback
 
 
 class ClockSampler:

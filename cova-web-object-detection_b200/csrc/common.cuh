@@ -67,8 +67,10 @@ __device__ __forceinline__ uint32_t pack2_bf16(float a, float b) {
 }
 
 // fp16 pairs (a in the low half), for the single-plane fp16 mode (COVA_F16)
+// fp16 saturates at +-65504 instead of overflowing to inf (an inf would poison the whole accumulator row downstream)
+__device__ __forceinline__ float sat_f16(float x) { return fminf(fmaxf(x, -65504.f), 65504.f); }
 __device__ __forceinline__ uint32_t pack2_f16(float a, float b) {
-  __half2 h = __floats2half2_rn(a, b);
+  __half2 h = __floats2half2_rn(sat_f16(a), sat_f16(b));
   return *reinterpret_cast<uint32_t*>(&h);
 }
 __device__ __forceinline__ float2 unpack2_f16(uint32_t packed) {
@@ -80,10 +82,10 @@ __device__ __forceinline__ float2 unpack2_f16(uint32_t packed) {
 // SPLIT_F16_WSCALE (a power of two, undone exactly in the epilogue) so that their lo plane stays a NORMAL fp16 number.
 constexpr float SPLIT_F16_WSCALE = 256.f;
 __device__ __forceinline__ void split_f16x2(float a, float b, uint32_t& hi, uint32_t& lo) {
-  __half2 h = __floats2half2_rn(a, b);
+  __half2 h = __floats2half2_rn(sat_f16(a), sat_f16(b));
   hi = *reinterpret_cast<uint32_t*>(&h);
   const float2 hf = __half22float2(h);
-  __half2 l = __floats2half2_rn(a - hf.x, b - hf.y);
+  __half2 l = __floats2half2_rn(sat_f16(a - hf.x), sat_f16(b - hf.y));
   lo = *reinterpret_cast<uint32_t*>(&l);
 }
 
