@@ -68,7 +68,7 @@ __device__ __forceinline__ uint32_t pack2_bf16(float a, float b) {
 
 // fp16 pairs (a in the low half), for the single-plane fp16 mode (COVA_F16)
 // fp16 saturates at +-65504 instead of overflowing to inf (an inf would poison the whole accumulator row downstream)
-__device__ __forceinline__ float sat_f16(float x) { return fminf(fmaxf(x, -65504.f), 65504.f); }
+__device__ __forceinline__ float sat_f16(float x) { return x != x ? x : fminf(fmaxf(x, -65504.f), 65504.f); }   // NaN stays NaN
 __device__ __forceinline__ uint32_t pack2_f16(float a, float b) {
   __half2 h = __floats2half2_rn(sat_f16(a), sat_f16(b));
   return *reinterpret_cast<uint32_t*>(&h);
