@@ -34,6 +34,7 @@ class _BnActFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, gamma, beta, res, bn, relu, want_planes):
+        ctx.set_materialize_grads(False)      # no zero-filled 400 MB "gradients" for the non-differentiable planes
         x = x.contiguous()
         res_c = None if res is None else res.contiguous()
         mom = 0.1 if bn.momentum is None else bn.momentum
@@ -53,6 +54,8 @@ class _BnActFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dy, _dhi, _dlo):
         x, mean, inv, gamma, beta, res = ctx.saved_tensors
+        if dy is None:
+            dy = torch.zeros_like(x)
         want_dres = ctx.has_res and ctx.needs_input_grad[3]
         dx, dres, dg, db = ops.bn_train_bwd(dy.contiguous(), x, mean, inv, gamma, beta, res=res, relu=ctx.relu,
                                             want_dres=want_dres)
@@ -62,6 +65,7 @@ class _BnActFn(torch.autograd.Function):
 class _MaxPoolFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, want_planes):
+        ctx.set_materialize_grads(False)
         x = x.contiguous()
         y, code, pl = ops.maxpool3x3s2_fwd(x, want_planes=want_planes, planes_dtype=F16X2)
         ctx.save_for_backward(code)
@@ -74,6 +78,8 @@ class _MaxPoolFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dy, _dhi, _dlo):
         (code,) = ctx.saved_tensors
+        if dy is None:
+            return None, None
         return ops.maxpool3x3s2_bwd(code, dy.contiguous(), ctx.in_shape), None
 
 
