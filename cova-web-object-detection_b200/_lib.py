@@ -88,6 +88,8 @@ SIGNATURES = {
     "cova_bn_act_bwd": (_I, [_P, _P, _P, _L, _I, _P, _P, _P, _P, _I, _P, _P, _P, _P, _P, _P]),
     "cova_maxpool3x3s2_fwd": (_I, [_P, _I, _I, _I, _I, _P, _P, _P, _P, _I, _P]),
     "cova_maxpool3x3s2_bwd": (_I, [_P, _P, _I, _I, _I, _I, _P, _P]),
+    "cova_bn_relu_pool_fwd": (_I, [_P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _I, _P]),
+    "cova_bn_relu_pool_bwd": (_I, [_P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
 }
 
 _lib = None

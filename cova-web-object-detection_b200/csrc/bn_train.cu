@@ -252,6 +252,127 @@ split_planes_kernel(const float* __restrict__ x, int64_t n4, __nv_bfloat16* __re
     split4(__ldg(reinterpret_cast<const float4*>(x) + i), hi, lo, (size_t)i * 4, f16);
 }
 
+// ---------------------------------------------------------------- stem: BatchNorm(batch stats) + ReLU + maxpool, fused
+// The normalised [B,H,W,C] map between bn1 and the maxpool (1.7 GB at B=16) is never written: the forward pools
+// relu(bn(x)) on the fly from the raw conv1 output, the backward re-derives each input pixel's gradient from the
+// pooled gradient and the winner codes inside the BatchNorm reduction / apply passes.
+__global__ void __launch_bounds__(256)
+bn_relu_pool_fwd_kernel(const float* __restrict__ x, int B, int H, int W, int C, int Ho, int Wo,
+                        const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ gamma,
+                        const float* __restrict__ beta, float* __restrict__ y, unsigned char* __restrict__ code,
+                        __nv_bfloat16* __restrict__ y_hi, __nv_bfloat16* __restrict__ y_lo, int f16) {
+  const int c4n = C >> 2;
+  const int64_t n = (int64_t)B * Ho * Wo * c4n;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int cg = (int)(i % c4n), c0 = 4 * cg;
+    const int64_t pix = i / c4n;
+    const int ow = (int)(pix % Wo), oh = (int)((pix / Wo) % Ho), b = (int)(pix / ((int64_t)Wo * Ho));
+    const float4 mu = *reinterpret_cast<const float4*>(mean + c0), iv = *reinterpret_cast<const float4*>(invstd + c0);
+    const float4 ga = *reinterpret_cast<const float4*>(gamma + c0), be = *reinterpret_cast<const float4*>(beta + c0);
+    float4 m = make_float4(-FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX);
+    int4 mi = make_int4(-1, -1, -1, -1);
+    for (int r = 0; r < 3; ++r) {
+      const int h = 2 * oh - 1 + r;
+      if (h < 0 || h >= H) continue;
+      for (int s2 = 0; s2 < 3; ++s2) {
+        const int w = 2 * ow - 1 + s2;
+        if (w < 0 || w >= W) continue;
+        const float4 xv = __ldg(reinterpret_cast<const float4*>(x + (((size_t)b * H + h) * W + w) * C) + cg);
+        const float4 v = make_float4(fmaxf(bn_val(xv.x, mu.x, iv.x, ga.x, be.x), 0.f), fmaxf(bn_val(xv.y, mu.y, iv.y, ga.y, be.y), 0.f),
+                                     fmaxf(bn_val(xv.z, mu.z, iv.z, ga.z, be.z), 0.f), fmaxf(bn_val(xv.w, mu.w, iv.w, ga.w, be.w), 0.f));
+        const int k = r * 3 + s2;
+        if (v.x > m.x || mi.x < 0) { m.x = v.x; mi.x = k; }
+        if (v.y > m.y || mi.y < 0) { m.y = v.y; mi.y = k; }
+        if (v.z > m.z || mi.z < 0) { m.z = v.z; mi.z = k; }
+        if (v.w > m.w || mi.w < 0) { m.w = v.w; mi.w = k; }
+      }
+    }
+    reinterpret_cast<float4*>(y)[i] = m;
+    reinterpret_cast<uchar4*>(code)[i] = make_uchar4(mi.x, mi.y, mi.z, mi.w);
+    if (y_hi != nullptr) split4(m, y_hi, y_lo, (size_t)i * 4, f16);
+  }
+}
+
+// gradient that reaches input pixel (b, h0, w0) of the pooled map through the <= 2 x 2 windows it won
+__device__ __forceinline__ float4 pool_gather(const unsigned char* __restrict__ code, const float* __restrict__ dyp, int b,
+                                              int h0, int w0, int cg, int c4n, int Ho, int Wo) {
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  const int oh_hi = (h0 + 1) >> 1, ow_hi = (w0 + 1) >> 1;
+  for (int oh = h0 >> 1; oh <= oh_hi; ++oh) {
+    if (oh >= Ho) continue;
+    for (int ow = w0 >> 1; ow <= ow_hi; ++ow) {
+      if (ow >= Wo) continue;
+      const int me = (h0 - (2 * oh - 1)) * 3 + (w0 - (2 * ow - 1));
+      const size_t o = (((size_t)b * Ho + oh) * Wo + ow) * c4n + cg;
+      const uchar4 k = __ldg(reinterpret_cast<const uchar4*>(code) + o);
+      const float4 g = __ldg(reinterpret_cast<const float4*>(dyp) + o);
+      if (k.x == me) acc.x += g.x;
+      if (k.y == me) acc.y += g.y;
+      if (k.z == me) acc.z += g.z;
+      if (k.w == me) acc.w += g.w;
+    }
+  }
+  return acc;
+}
+
+// PASS 0: ws = [sum g | sum g*xhat];  PASS 1: dx = gamma*inv*(g - S1/M - xhat*S2/M), dgamma / dbeta from ws
+template <int PASS>
+__global__ void __launch_bounds__(BN_THREADS)
+bn_relu_pool_bwd_kernel(const float* __restrict__ x, const unsigned char* __restrict__ code, const float* __restrict__ dyp,
+                        int B, int H, int W, int C, int Ho, int Wo, const float* __restrict__ mean,
+                        const float* __restrict__ invstd, const float* __restrict__ gamma, const float* __restrict__ beta,
+                        double* __restrict__ ws, float* __restrict__ dx, float* __restrict__ dgamma,
+                        float* __restrict__ dbeta) {
+  extern __shared__ __align__(16) float sm[];           // PASS 0: [2][rows][C] partial sums; PASS 1: [2][C] S1/M, S2/M
+  const int c4n = C >> 2, rows = BN_THREADS / c4n;
+  const int cg = threadIdx.x % c4n, prow = threadIdx.x / c4n, c0 = 4 * cg;
+  const int64_t M = (int64_t)B * H * W;
+  const float4 mu = *reinterpret_cast<const float4*>(mean + c0), iv = *reinterpret_cast<const float4*>(invstd + c0);
+  const float4 ga = *reinterpret_cast<const float4*>(gamma + c0), be = *reinterpret_cast<const float4*>(beta + c0);
+  if (PASS == 1) {
+    if (blockIdx.x == 0)
+      for (int c = threadIdx.x; c < C; c += BN_THREADS) { dbeta[c] = (float)ws[c]; dgamma[c] = (float)ws[C + c]; }
+    for (int c = threadIdx.x; c < 2 * C; c += BN_THREADS) sm[c] = (float)(ws[c] / (double)M);
+    __syncthreads();
+  }
+  float4 a = make_float4(0.f, 0.f, 0.f, 0.f), bsum = a;
+  const int64_t stride = (int64_t)gridDim.x * rows;
+  for (int64_t p = (int64_t)blockIdx.x * rows + prow; p < M; p += stride) {
+    const int w0 = (int)(p % W), h0 = (int)((p / W) % H), b = (int)(p / ((int64_t)W * H));
+    const float4 xv = __ldg(reinterpret_cast<const float4*>(x + p * C + c0));
+    float4 g = pool_gather(code, dyp, b, h0, w0, cg, c4n, Ho, Wo);
+    const float4 xh = make_float4((xv.x - mu.x) * iv.x, (xv.y - mu.y) * iv.y, (xv.z - mu.z) * iv.z, (xv.w - mu.w) * iv.w);
+    g.x = bn_val(xv.x, mu.x, iv.x, ga.x, be.x) > 0.f ? g.x : 0.f;
+    g.y = bn_val(xv.y, mu.y, iv.y, ga.y, be.y) > 0.f ? g.y : 0.f;
+    g.z = bn_val(xv.z, mu.z, iv.z, ga.z, be.z) > 0.f ? g.z : 0.f;
+    g.w = bn_val(xv.w, mu.w, iv.w, ga.w, be.w) > 0.f ? g.w : 0.f;
+    if (PASS == 0) {
+      a.x += g.x; a.y += g.y; a.z += g.z; a.w += g.w;
+      bsum.x = fmaf(g.x, xh.x, bsum.x); bsum.y = fmaf(g.y, xh.y, bsum.y);
+      bsum.z = fmaf(g.z, xh.z, bsum.z); bsum.w = fmaf(g.w, xh.w, bsum.w);
+    } else {
+      const float4 s1 = *reinterpret_cast<const float4*>(sm + c0), s2 = *reinterpret_cast<const float4*>(sm + C + c0);
+      float4 o;
+      o.x = ga.x * iv.x * (g.x - s1.x - xh.x * s2.x);
+      o.y = ga.y * iv.y * (g.y - s1.y - xh.y * s2.y);
+      o.z = ga.z * iv.z * (g.z - s1.z - xh.z * s2.z);
+      o.w = ga.w * iv.w * (g.w - s1.w - xh.w * s2.w);
+      *reinterpret_cast<float4*>(dx + p * C + c0) = o;
+    }
+  }
+  if (PASS == 0) {
+    *reinterpret_cast<float4*>(sm + (size_t)prow * C + c0) = a;
+    *reinterpret_cast<float4*>(sm + (size_t)(rows + prow) * C + c0) = bsum;
+    __syncthreads();
+    for (int c = threadIdx.x; c < 2 * C; c += BN_THREADS) {
+      const int which = c / C, ch = c % C;
+      double t = 0.0;
+      for (int r = 0; r < rows; ++r) t += (double)sm[(size_t)(which * rows + r) * C + ch];
+      atomicAdd(ws + c, t);
+    }
+  }
+}
+
 static bool bn_c_ok(int C) { return C >= 4 && C <= 1024 && (C & (C - 1)) == 0; }
 static int ew_grid(int64_t n, int threads) {
   int64_t b = (n + threads - 1) / threads;
@@ -361,6 +482,48 @@ extern "C" int cova_split_planes(const float* x, int64_t n, void* hi, void* lo, 
   COVA_REQUIRE((((uintptr_t)x & 15) | ((uintptr_t)hi & 7) | ((uintptr_t)lo & 7)) == 0, "cova_split_planes: alignment");
   split_planes_kernel<<<ew_grid(n / 4, 256), 256, 0, (cudaStream_t)stream>>>(x, n / 4, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo,
                                                                             planes_dtype == COVA_F16X2);
+  COVA_LAUNCH_OK();
+  return COVA_OK;
+}
+
+extern "C" int cova_bn_relu_pool_fwd(const float* x, int B, int H, int W, int C, const float* mean, const float* invstd,
+                                     const float* gamma, const float* beta, float* y, unsigned char* code, void* y_hi,
+                                     void* y_lo, int planes_dtype, void* stream) {
+  COVA_REQUIRE(x && y && code && mean && invstd && gamma && beta && B > 0 && H > 0 && W > 0, "cova_bn_relu_pool_fwd: bad arguments");
+  COVA_REQUIRE(bn_c_ok(C), "cova_bn_relu_pool_fwd: C=%d must be a power of two in [4, 1024]", C);
+  COVA_REQUIRE((y_hi == nullptr) == (y_lo == nullptr), "cova_bn_relu_pool_fwd: the split planes come together");
+  COVA_REQUIRE(planes_dtype == COVA_BF16X2 || planes_dtype == COVA_F16X2, "cova_bn_relu_pool_fwd: planes are split-bf16 or split-fp16");
+  COVA_REQUIRE((((uintptr_t)x | (uintptr_t)y | (uintptr_t)y_hi | (uintptr_t)y_lo) & 15) == 0 && ((uintptr_t)code & 3) == 0,
+               "cova_bn_relu_pool_fwd: alignment");
+  const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
+  const int64_t n = (int64_t)B * Ho * Wo * (C / 4);
+  bn_relu_pool_fwd_kernel<<<ew_grid(n, 256), 256, 0, (cudaStream_t)stream>>>(
+      x, B, H, W, C, Ho, Wo, mean, invstd, gamma, beta, y, code, (__nv_bfloat16*)y_hi, (__nv_bfloat16*)y_lo,
+      planes_dtype == COVA_F16X2);
+  COVA_LAUNCH_OK();
+  return COVA_OK;
+}
+
+extern "C" int cova_bn_relu_pool_bwd(const float* x, const unsigned char* code, const float* dy_pooled, int B, int H, int W,
+                                     int C, const float* mean, const float* invstd, const float* gamma, const float* beta,
+                                     double* ws, float* dx, float* dgamma, float* dbeta, void* stream) {
+  COVA_REQUIRE(x && code && dy_pooled && ws && dx && dgamma && dbeta && mean && invstd && gamma && beta && B > 0 && H > 0 && W > 0,
+               "cova_bn_relu_pool_bwd: bad arguments");
+  COVA_REQUIRE(bn_c_ok(C), "cova_bn_relu_pool_bwd: C=%d must be a power of two in [4, 1024]", C);
+  COVA_REQUIRE((((uintptr_t)x | (uintptr_t)dy_pooled | (uintptr_t)dx) & 15) == 0 && ((uintptr_t)code & 3) == 0,
+               "cova_bn_relu_pool_bwd: alignment");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
+  COVA_CUDA_OK(cudaMemsetAsync(ws, 0, 2 * C * sizeof(double), st));
+  const int rows = BN_THREADS / (C / 4);
+  const int64_t M = (int64_t)B * H * W;
+  int64_t grid = (M + rows - 1) / rows;
+  if (grid > (int64_t)sm_count() * 8) grid = (int64_t)sm_count() * 8;
+  bn_relu_pool_bwd_kernel<0><<<(int)grid, BN_THREADS, (size_t)2 * rows * C * sizeof(float), st>>>(
+      x, code, dy_pooled, B, H, W, C, Ho, Wo, mean, invstd, gamma, beta, ws, nullptr, nullptr, nullptr);
+  COVA_LAUNCH_OK();
+  bn_relu_pool_bwd_kernel<1><<<(int)grid, BN_THREADS, (size_t)2 * C * sizeof(float), st>>>(
+      x, code, dy_pooled, B, H, W, C, Ho, Wo, mean, invstd, gamma, beta, ws, dx, dgamma, dbeta);
   COVA_LAUNCH_OK();
   return COVA_OK;
 }

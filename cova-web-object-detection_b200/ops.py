@@ -454,3 +454,38 @@ def maxpool3x3s2_bwd(code, dy, in_shape):
     dx = torch.empty(in_shape, dtype=torch.float32, device=dy.device)
     _call("cova_maxpool3x3s2_bwd", code.data_ptr(), dy.data_ptr(), B, H, W, C, dx.data_ptr(), _stream())
     return dx
+
+
+def bn_relu_pool_fwd(x, gamma, beta, running_mean, running_var, momentum, eps, want_planes=False, planes_dtype=BF16X2):
+    """Stem of the training path, fused: BatchNorm2d(batch statistics) + ReLU + MaxPool2d(3,2,1) of the raw conv1 output
+    x [B,H,W,C] NHWC fp32 without writing the normalised map.  Returns (y pooled, codes uint8, mean, invstd, Planes|None)."""
+    _nhwc(x, "x")
+    B, H, W, C = x.shape
+    M = B * H * W
+    dev = x.device
+    ws = torch.empty(2 * C, dtype=torch.float64, device=dev)
+    mean, inv = torch.empty(C, dtype=torch.float32, device=dev), torch.empty(C, dtype=torch.float32, device=dev)
+    _call("cova_bn_train_stats", x.data_ptr(), M, C, ws.data_ptr(), _stream())
+    _call("cova_bn_train_finalize", ws.data_ptr(), M, C, float(eps), float(momentum), mean.data_ptr(), inv.data_ptr(),
+          _ptr(running_mean), _ptr(running_var), _stream())
+    y = torch.empty((B, (H - 1) // 2 + 1, (W - 1) // 2 + 1, C), dtype=torch.float32, device=dev)
+    code = torch.empty(y.shape, dtype=torch.uint8, device=dev)
+    pl = _planes_like(y, planes_dtype) if want_planes else None
+    _call("cova_bn_relu_pool_fwd", x.data_ptr(), B, H, W, C, mean.data_ptr(), inv.data_ptr(), gamma.data_ptr(),
+          beta.data_ptr(), y.data_ptr(), code.data_ptr(), pl.p0.data_ptr() if pl else 0, pl.p1.data_ptr() if pl else 0,
+          planes_dtype, _stream())
+    return y, code, mean, inv, pl
+
+
+def bn_relu_pool_bwd(x, code, dy_pooled, mean, invstd, gamma, beta):
+    """Backward of `bn_relu_pool_fwd`: returns (dx of the raw conv1 output, dgamma, dbeta)."""
+    _nhwc(x, "x"); _nhwc(dy_pooled, "dy")
+    B, H, W, C = x.shape
+    dev = x.device
+    ws = torch.empty(2 * C, dtype=torch.float64, device=dev)
+    dx = torch.empty_like(x)
+    dg, db = torch.empty(C, dtype=torch.float32, device=dev), torch.empty(C, dtype=torch.float32, device=dev)
+    _call("cova_bn_relu_pool_bwd", x.data_ptr(), code.data_ptr(), dy_pooled.data_ptr(), B, H, W, C, mean.data_ptr(),
+          invstd.data_ptr(), gamma.data_ptr(), beta.data_ptr(), ws.data_ptr(), dx.data_ptr(), dg.data_ptr(), db.data_ptr(),
+          _stream())
+    return dx, dg, db

@@ -62,6 +62,36 @@ class _BnActFn(torch.autograd.Function):
         return dx, dg, db, dres, None, None, None
 
 
+class _BnReluPoolFn(torch.autograd.Function):
+    """The stem after conv1, fused: (y, y_hi, y_lo) = maxpool3x3s2p1(relu(BN_batchstats(x))) on NHWC fp32.  The
+    normalised map between bn1 and the maxpool (1.7 GB at B=16) is never written, forward or backward."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, bn, want_planes):
+        ctx.set_materialize_grads(False)
+        x = x.contiguous()
+        mom = 0.1 if bn.momentum is None else bn.momentum
+        track = bn.track_running_stats and bn.running_mean is not None
+        y, code, mean, inv, pl = ops.bn_relu_pool_fwd(x, gamma.detach(), beta.detach(), bn.running_mean if track else None,
+                                                      bn.running_var if track else None, mom, bn.eps,
+                                                      want_planes=want_planes, planes_dtype=F16X2)
+        if track and bn.num_batches_tracked is not None:
+            bn.num_batches_tracked += 1
+        ctx.save_for_backward(x, code, mean, inv, gamma.detach(), beta.detach())
+        if pl is None:
+            return y, None, None
+        ctx.mark_non_differentiable(pl.p0, pl.p1)
+        return y, pl.p0, pl.p1
+
+    @staticmethod
+    def backward(ctx, dy, _dhi, _dlo):
+        x, code, mean, inv, gamma, beta = ctx.saved_tensors
+        if dy is None:
+            return None, None, None, None, None
+        dx, dg, db = ops.bn_relu_pool_bwd(x, code, dy.contiguous(), mean, inv, gamma, beta)
+        return dx, dg, db, None, None
+
+
 class _MaxPoolFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, want_planes):
@@ -178,9 +208,15 @@ def feature_map_train(convnet, images):
     else:
         img = images.float().div(255) if images.dtype == torch.uint8 else images.float()
         x = _conv(img.permute(0, 2, 3, 1).contiguous(), None, convnet[0])
-    x, _ = _bn_act(x, convnet[1], relu=True)                                                              # bn1 + relu
     want = _tc_conv_ok(first)
-    x, hi, lo = _MaxPoolFn.apply(x, want)                                                                 # maxpool
+    # COVA_B200_TRAIN_STEM_FUSED=1: bn1 + ReLU + maxpool in one forward / two backward kernels that never write the
+    # normalised 640x640 map nor its gradient (3.4 GB less memory at B=16).  Measured no faster than the separate
+    # passes (19.2 vs 18.1 ms/step: the backward gather is index-math bound), so it is a memory option, off by default.
+    if os.environ.get("COVA_B200_TRAIN_STEM_FUSED", "0") == "1":
+        x, hi, lo = _BnReluPoolFn.apply(x, convnet[1].weight, convnet[1].bias, convnet[1], want)          # bn1+relu+maxpool
+    else:
+        x, _ = _bn_act(x, convnet[1], relu=True)                                                          # bn1 + relu
+        x, hi, lo = _MaxPoolFn.apply(x, want)                                                             # maxpool
     xp = (hi, lo) if want else None
     for bi, blk in enumerate(blocks):                                   # layer1
         nxt = blocks[bi + 1].conv1 if bi + 1 < len(blocks) else None

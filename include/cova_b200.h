@@ -255,6 +255,17 @@ int cova_maxpool3x3s2_fwd(const float* x, int B, int H, int W, int C, float* y, 
                           void* y_lo, int planes_dtype, void* stream);
 int cova_maxpool3x3s2_bwd(const unsigned char* code, const float* dy, int B, int H, int W, int C, float* dx, void* stream);
 
+/* ---- A2 / A9: the stem's bn1 + ReLU + maxpool FUSED for the training path: the normalised [B,H,W,C] map between them
+ * (1.7 GB at B=16) is never written.  Forward: mean / invstd from cova_bn_train_stats + _finalize of the raw conv1
+ * output x; y [B,Ho,Wo,C] = maxpool3x3s2p1(relu(bn(x))), winner codes, optional split planes.  Backward: from the pooled
+ * gradient and the codes, dx of the raw conv1 output and dgamma / dbeta (ws: 2*C doubles of scratch).              */
+int cova_bn_relu_pool_fwd(const float* x, int B, int H, int W, int C, const float* mean, const float* invstd,
+                          const float* gamma, const float* beta, float* y, unsigned char* code, void* y_hi, void* y_lo,
+                          int planes_dtype, void* stream);
+int cova_bn_relu_pool_bwd(const float* x, const unsigned char* code, const float* dy_pooled, int B, int H, int W, int C,
+                          const float* mean, const float* invstd, const float* gamma, const float* beta, double* ws,
+                          float* dx, float* dgamma, float* dbeta, void* stream);
+
 /* fp32 [n] -> split planes hi = r(x), lo = r(x - hi), r = bf16 (COVA_BF16X2) or fp16 (COVA_F16X2) rounding (n % 4 == 0). */
 int cova_split_planes(const float* x, int64_t n, void* hi, void* lo, int planes_dtype, void* stream);
 

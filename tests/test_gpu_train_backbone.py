@@ -144,3 +144,29 @@ def test_stem_conv_raw_and_conv3x3_functions_vs_torch():
         yr.backward(dy)
         assert rel_err(n(y), n(yr)) < 3e-5
         assert rel_err(n(x.grad), n(xr.grad)) < 2e-3 and rel_err(n(w.grad), n(wr.grad)) < 2e-3
+
+
+@pytest.mark.parametrize("shape", [(2, 8, 8, 64), (1, 9, 13, 64), (2, 33, 20, 64), (1, 1, 7, 8)])
+def test_fused_bn_relu_pool_vs_torch(shape):
+    """The fused stem tail of the training path (bn1 + ReLU + maxpool without the intermediate map) against
+    nn.BatchNorm2d(train) -> relu -> max_pool2d(3, 2, 1) and autograd: values, running statistics, all gradients."""
+    from cova_b200.train_backbone import _BnReluPoolFn
+    g = torch.Generator().manual_seed(shape[1] * 7 + shape[2])
+    C = shape[-1]
+    x = (torch.randn(shape, generator=g) * 1.5 - 0.3).to(DEV).requires_grad_(True)
+    bn = torch.nn.BatchNorm2d(C).to(DEV).train()
+    with torch.no_grad():
+        bn.weight.copy_(torch.rand(C, generator=g) + 0.5); bn.bias.copy_(torch.randn(C, generator=g) * 0.3)
+    ref_bn = torch.nn.BatchNorm2d(C).to(DEV).train()
+    ref_bn.load_state_dict(bn.state_dict())
+    y, hi, lo = _BnReluPoolFn.apply(x, bn.weight, bn.bias, bn, True)
+    dy = torch.randn(y.shape, generator=g).to(DEV)
+    y.backward(dy)
+    x2 = x.detach().clone().requires_grad_(True)
+    z = F.max_pool2d(F.relu(ref_bn(x2.permute(0, 3, 1, 2))), 3, 2, 1).permute(0, 2, 3, 1)
+    z.backward(dy)
+    assert y.shape == z.shape and rel_err(n(y), n(z)) < 2e-5
+    assert rel_err(n(hi.float() + lo.float()), n(y)) < 2e-6            # split-fp16 planes of the pooled map
+    assert rel_err(n(x.grad), n(x2.grad)) < 5e-5
+    assert rel_err(n(bn.weight.grad), n(ref_bn.weight.grad)) < 5e-5 and rel_err(n(bn.bias.grad), n(ref_bn.bias.grad)) < 5e-5
+    assert rel_err(n(bn.running_mean), n(ref_bn.running_mean)) < 2e-5 and rel_err(n(bn.running_var), n(ref_bn.running_var)) < 2e-5
