@@ -52,7 +52,7 @@ struct StemTcSmem {
   float xch[2][4][64];                     // lane-31 rows exchanged between the 4 epilogue warps
   float scale[64], shift[64];
   uint32_t lut[256];                       // uint8 images: bf16 hi (low half) | bf16 lo (high half) of v/255
-  uint64_t in_full[SX_R], mma_done[SX_ND], tmem_full[2], tmem_empty[2], wbar;
+  uint64_t in_full[SX_R], pair_full[SX_ND], mma_done[SX_ND], tmem_full[2], tmem_empty[2], wbar;
   uint32_t tmem_base;
 };
 
@@ -119,7 +119,10 @@ stem_tc_kernel(const StemTcParams p) {
   }
   if (threadIdx.x == 0) {
     for (int i = 0; i < SX_R; ++i) ptx::mbar_init(&sm.in_full[i], 1);
-    for (int i = 0; i < SX_ND; ++i) ptx::mbar_init(&sm.mma_done[i], 1);
+    for (int i = 0; i < SX_ND; ++i) {
+      ptx::mbar_init(&sm.mma_done[i], 1);
+      ptx::mbar_init(&sm.pair_full[i], 2);       // the two input rows that are new for one conv row
+    }
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(&sm.tmem_full[i], 1);
       ptx::mbar_init(&sm.tmem_empty[i], SX_EPI_THREADS);
@@ -158,10 +161,16 @@ stem_tc_kernel(const StemTcParams p) {
       for (int i = 0; i < n_conv; ++i, ++t) {
         const uint32_t g0 = (uint32_t)strip * NQ + 2 * i;
         long long c0 = timed ? clock64() : 0;
-        for (int r = (i == 0 ? 0 : 5); r < 7; ++r) {         // rows that are new for this conv row
-          const uint32_t g = g0 + r;
-          ptx::mbar_wait(&sm.in_full[g % SX_R], (g / SX_R) & 1);
+        // Rows that are new for this conv row: 2i+5 and 2i+6 arrive on ONE pair barrier (a ready mbarrier check costs
+        // the issuing thread ~170 clk, and there were two per conv row); the first conv row of a strip also needs
+        // rows 0..4, which keep their per-slot barriers.
+        if (i == 0) {
+          for (int r = 0; r < 5; ++r) {
+            const uint32_t g = g0 + r;
+            ptx::mbar_wait(&sm.in_full[g % SX_R], (g / SX_R) & 1);
+          }
         }
+        ptx::mbar_wait(&sm.pair_full[t % SX_ND], (t / SX_ND) & 1);
         const uint32_t acc = t & 1;
         if (timed) { const long long c1 = clock64(); wt0 += c1 - c0; c0 = c1; }
         ptx::mbar_wait(&sm.tmem_empty[acc], ((t >> 1) & 1) ^ 1);
@@ -451,7 +460,13 @@ stem_tc_kernel(const StemTcParams p) {
       }
       ptx::fence_proxy_async();      // generic-proxy writes -> visible to tcgen05 (async proxy) reads
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(&sm.in_full[g % SX_R]);
+      if (lane == 0) {
+        ptx::mbar_arrive(&sm.in_full[g % SX_R]);
+        if (q >= 5) {                                  // first needed by conv row (q - 5) / 2 of this strip
+          const uint32_t tq = (uint32_t)strip * n_conv + ((q - 5) >> 1);
+          ptx::mbar_arrive(&sm.pair_full[tq % SX_ND]);
+        }
+      }
     }
   }
 
