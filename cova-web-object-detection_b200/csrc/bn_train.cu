@@ -56,8 +56,21 @@ bn_reduce_kernel(const float* __restrict__ x, const float* __restrict__ dy, cons
     be = *reinterpret_cast<const float4*>(beta + c0);
   }
   const int64_t stride = (int64_t)gridDim.x * rows;
-#pragma unroll 4
-  for (int64_t p = (int64_t)blockIdx.x * rows + prow; p < M; p += stride) {
+  int64_t p = (int64_t)blockIdx.x * rows + prow;
+  if (MODE == 0) {   // statistics pass: four independent loads in flight per thread (a plain loop ran at 4 TB/s)
+    for (; p + 3 * stride < M; p += 4 * stride) {
+      float4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = __ldg(reinterpret_cast<const float4*>(x + (p + u * stride) * C + c0));
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        a.x += v[u].x; a.y += v[u].y; a.z += v[u].z; a.w += v[u].w;
+        b.x = fmaf(v[u].x, v[u].x, b.x); b.y = fmaf(v[u].y, v[u].y, b.y);
+        b.z = fmaf(v[u].z, v[u].z, b.z); b.w = fmaf(v[u].w, v[u].w, b.w);
+      }
+    }
+  }
+  for (; p < M; p += stride) {
     const float4 xv = __ldg(reinterpret_cast<const float4*>(x + p * C + c0));
     if (MODE == 0) {
       a.x += xv.x; a.y += xv.y; a.z += xv.z; a.w += xv.w;
@@ -183,16 +196,19 @@ bn_act_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, con
 // goes.  The forward stores the winner's position inside the (unclipped) window as one byte per output element
 // (code = r*3 + s); the backward is a gather over the <= 2 x 2 windows that contain an input pixel: compare codes,
 // no rescans, no atomics.
+// IdxT = uint32_t whenever the element count fits (64-bit div / mod per element made these kernels index-math bound:
+// the backward ran at 1.7 TB/s)
+template <typename IdxT>
 __global__ void __launch_bounds__(256)
 maxpool_fwd_kernel(const float* __restrict__ x, int B, int H, int W, int C, int Ho, int Wo, float* __restrict__ y,
                    unsigned char* __restrict__ code, __nv_bfloat16* __restrict__ y_hi, __nv_bfloat16* __restrict__ y_lo,
                    int f16) {
-  const int c4n = C >> 2;
-  const int64_t n = (int64_t)B * Ho * Wo * c4n;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+  const IdxT c4n = (IdxT)(C >> 2);
+  const IdxT n = (IdxT)B * Ho * Wo * c4n;
+  for (IdxT i = (IdxT)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (IdxT)gridDim.x * blockDim.x) {
     const int cg = (int)(i % c4n);
-    const int64_t pix = i / c4n;
-    const int ow = (int)(pix % Wo), oh = (int)((pix / Wo) % Ho), b = (int)(pix / ((int64_t)Wo * Ho));
+    const IdxT pix = i / c4n;
+    const int ow = (int)(pix % (IdxT)Wo), oh = (int)((pix / (IdxT)Wo) % (IdxT)Ho), b = (int)(pix / ((IdxT)Wo * Ho));
     float4 m = make_float4(-FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX);
     int4 mi = make_int4(-1, -1, -1, -1);
     for (int r = 0; r < 3; ++r) {
@@ -215,15 +231,16 @@ maxpool_fwd_kernel(const float* __restrict__ x, int B, int H, int W, int C, int 
   }
 }
 
+template <typename IdxT>
 __global__ void __launch_bounds__(256)
 maxpool_bwd_kernel(const unsigned char* __restrict__ code, const float* __restrict__ dy, int B, int H, int W, int C, int Ho,
                    int Wo, float* __restrict__ dx) {
-  const int c4n = C >> 2;
-  const int64_t n = (int64_t)B * H * W * c4n;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+  const IdxT c4n = (IdxT)(C >> 2);
+  const IdxT n = (IdxT)B * H * W * c4n;
+  for (IdxT i = (IdxT)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (IdxT)gridDim.x * blockDim.x) {
     const int cg = (int)(i % c4n);
-    const int64_t pix = i / c4n;
-    const int w0 = (int)(pix % W), h0 = (int)((pix / W) % H), b = (int)(pix / ((int64_t)W * H));
+    const IdxT pix = i / c4n;
+    const int w0 = (int)(pix % (IdxT)W), h0 = (int)((pix / (IdxT)W) % (IdxT)H), b = (int)(pix / ((IdxT)W * H));
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     const int oh_hi = (h0 + 1) >> 1, ow_hi = (w0 + 1) >> 1;     // == h0 >> 1 for even h0: one window per axis
     for (int oh = h0 >> 1; oh <= oh_hi; ++oh) {
@@ -231,7 +248,7 @@ maxpool_bwd_kernel(const unsigned char* __restrict__ code, const float* __restri
       for (int ow = w0 >> 1; ow <= ow_hi; ++ow) {
         if (ow >= Wo) continue;
         const int me = (h0 - (2 * oh - 1)) * 3 + (w0 - (2 * ow - 1));
-        const size_t o = (((size_t)b * Ho + oh) * Wo + ow) * c4n + cg;
+        const size_t o = (((size_t)b * Ho + oh) * Wo + ow) * (size_t)c4n + cg;
         const uchar4 k = __ldg(reinterpret_cast<const uchar4*>(code) + o);
         const float4 g = __ldg(reinterpret_cast<const float4*>(dy) + o);
         if (k.x == me) acc.x += g.x;
@@ -459,8 +476,12 @@ extern "C" int cova_maxpool3x3s2_fwd(const float* x, int B, int H, int W, int C,
   COVA_REQUIRE((y_hi == nullptr) == (y_lo == nullptr), "cova_maxpool3x3s2_fwd: the split planes come together");
   const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
   const int64_t n = (int64_t)B * Ho * Wo * (C / 4);
-  maxpool_fwd_kernel<<<ew_grid(n, 256), 256, 0, (cudaStream_t)stream>>>(x, B, H, W, C, Ho, Wo, y, code, (__nv_bfloat16*)y_hi,
-                                                                        (__nv_bfloat16*)y_lo, planes_dtype == COVA_F16X2);
+  if (n < (1LL << 31))
+    maxpool_fwd_kernel<uint32_t><<<ew_grid(n, 256), 256, 0, (cudaStream_t)stream>>>(
+        x, B, H, W, C, Ho, Wo, y, code, (__nv_bfloat16*)y_hi, (__nv_bfloat16*)y_lo, planes_dtype == COVA_F16X2);
+  else
+    maxpool_fwd_kernel<int64_t><<<ew_grid(n, 256), 256, 0, (cudaStream_t)stream>>>(
+        x, B, H, W, C, Ho, Wo, y, code, (__nv_bfloat16*)y_hi, (__nv_bfloat16*)y_lo, planes_dtype == COVA_F16X2);
   COVA_LAUNCH_OK();
   return COVA_OK;
 }
@@ -471,7 +492,10 @@ extern "C" int cova_maxpool3x3s2_bwd(const unsigned char* code, const float* dy,
   COVA_REQUIRE((((uintptr_t)dy | (uintptr_t)dx) & 15) == 0 && ((uintptr_t)code & 3) == 0, "cova_maxpool3x3s2_bwd: alignment");
   const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
   const int64_t n = (int64_t)B * H * W * (C / 4);
-  maxpool_bwd_kernel<<<ew_grid(n, 256), 256, 0, (cudaStream_t)stream>>>(code, dy, B, H, W, C, Ho, Wo, dx);
+  if (n < (1LL << 31))
+    maxpool_bwd_kernel<uint32_t><<<ew_grid(n, 256), 256, 0, (cudaStream_t)stream>>>(code, dy, B, H, W, C, Ho, Wo, dx);
+  else
+    maxpool_bwd_kernel<int64_t><<<ew_grid(n, 256), 256, 0, (cudaStream_t)stream>>>(code, dy, B, H, W, C, Ho, Wo, dx);
   COVA_LAUNCH_OK();
   return COVA_OK;
 }
