@@ -10,10 +10,12 @@ Execution:
     split-fp16 planes (22 significand bits: ~1e-6, same cost; ResNet-18 stack), ``"fp16"`` = one fp16 product (ResNet-18 backbone;
     ~5e-4 on the logits, inside the 1e-3 bar), or ``"bf16"`` (3-4e-3: outside the bar)) or ``"simt"`` (exact fp32
     CUDA cores).
-  * anything that needs autograd (``train.py:45-60``) or batch statistics runs a PyTorch-operator composite
-    of the same arithmetic with the native RoIPool forward (own backward).  That composite is library code
-    (cuDNN/cuBLAS), kept so the unmodified training loop works; hand-written backward kernels are the next
-    round's work.
+  * anything that needs autograd (``train.py:45-60``) runs the autograd path.  In ``model.train()`` the backbone goes
+    through ``train_backbone.feature_map_train`` (NHWC end to end: tensor-core forward convolutions in the split-fp16
+    three-product mode, native BatchNorm(batch statistics) + residual + ReLU and maxpool, forward and backward); RoIPool
+    and the GAT gather have native forward / backward kernels.  The convolutions' backward, the small linear layers and
+    BatchNorm1d are PyTorch operators (cuDNN / cuBLAS = library code, interim - DESIGN.md section 9).  With autograd on
+    in ``eval()`` mode (running statistics) the backbone is the plain PyTorch module.
   * non-CUDA inputs raise: this package has no CPU path.
 
 Extra keyword-only constructor arguments (all with reference-preserving defaults):
