@@ -5,7 +5,9 @@ Native (libcova_b200.so): every FORWARD convolution that has a tensor-core kerne
 and the 3x3 64->64 convolutions (`cova_conv3x3_bn_act_fwd` with an identity epilogue), both in the split-fp16
 three-product mode (activations to ~1e-6); BatchNorm(batch statistics) + residual + ReLU forward / backward (`cova_bn_train_*`, `cova_bn_act_*`),
 which also emit the split planes the next convolution consumes; the stem's maxpool forward / backward.
-Library, interim: the convolutions' BACKWARD (dgrad / wgrad) through
+The dgrad of those 3x3 convolutions is native as well: the same tcgen05 kernel run on the split-fp16 planes of the
+output gradient with the rotated, channel-swapped filter.
+Library, interim: the convolutions' wgrad (and conv1's, which needs no dgrad) through
 `aten.convolution_backward` (cuDNN), and the ResNet-50 1x1 convolutions.
 
 Profile that motivated this (tools/prof_train.py, B=16, before): cuDNN BatchNorm 29 ms, fp32 forward convolutions
@@ -163,8 +165,20 @@ class _Conv3x3Fn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dy):
         x, weight = ctx.saved_tensors
-        gi, gw = _conv_bwd(dy.contiguous(), x.permute(0, 3, 1, 2), weight, [1, 1], [1, 1], True)
-        return gi.permute(0, 2, 3, 1), None, None, gw
+        dy = dy.contiguous()
+        if os.environ.get("COVA_B200_TRAIN_DGRAD", "native") != "native" or not ctx.needs_input_grad[0]:
+            gi, gw = _conv_bwd(dy, x.permute(0, 3, 1, 2), weight, [1, 1], [1, 1], ctx.needs_input_grad[0])
+            return (gi.permute(0, 2, 3, 1) if gi is not None else None), None, None, gw
+        # dgrad on the tensor cores: the gradient w.r.t. the input of a 3x3 s1 p1 convolution IS a 3x3 s1 p1 convolution
+        # of the output gradient with the filter rotated by 180 degrees and its channel axes swapped - the same
+        # tcgen05 kernel, same split-fp16 three-product mode (dX to ~1e-6; cuDNN's TF32 dgrad gives ~1e-3)
+        w_rot = weight.detach().float().flip(2, 3).transpose(0, 1).contiguous()
+        w_hi, w_lo = ops.pack_conv_weight_f16x2(w_rot)
+        one, zero = _ones_zeros(dy.device)
+        gi = ops.conv3x3_bn_act_fwd(ops.split_planes(dy, F16X2), w_hi, w_lo, one, zero, res=None, relu=False,
+                                    out_dtype=F32, engine=ENGINE_TCGEN05).p0
+        _, gw = _conv_bwd(dy, x.permute(0, 3, 1, 2), weight, [1, 1], [1, 1], False)      # wgrad: library
+        return gi, None, None, gw
 
 
 def tc_forward_convs():
