@@ -13,7 +13,8 @@ Execution:
   * anything that needs autograd (``train.py:45-60``) runs the autograd path.  In ``model.train()`` the backbone goes
     through ``train_backbone.feature_map_train`` (NHWC end to end: tensor-core forward convolutions in the split-fp16
     three-product mode, native BatchNorm(batch statistics) + residual + ReLU and maxpool, forward and backward); RoIPool
-    and the GAT gather have native forward / backward kernels.  The convolutions' backward, the small linear layers and
+    and the GAT gather have native forward / backward kernels, the 3x3 convolutions a native dgrad.  The convolutions'
+    wgrad, the small linear layers and
     BatchNorm1d are PyTorch operators (cuDNN / cuBLAS = library code, interim - DESIGN.md section 9).  With autograd on
     in ``eval()`` mode (running statistics) the backbone is the plain PyTorch module.
   * non-CUDA inputs raise: this package has no CPU path.
