@@ -358,3 +358,56 @@ def build_batch(boxes_per_page, context_size, boxes_xywh=None):
         seen += n
     ctx = np.asarray(ctx, np.int64).reshape(seen, 2 * cs)
     return (np.concatenate(bb) if bb else None), ctx
+
+
+# ----------------------------------------------------------------------------- training-mode backbone pieces (A9)
+def bn_act_train(x, weight, bias, res=None, relu=True, eps=1e-5):
+    """Train-mode `nn.BatchNorm2d` (+ residual) (+ ReLU) on an NCHW map, as torchvision's BasicBlock / Bottleneck run
+    it under `model.train()` (`/root/reference/train.py:27`): returns (y, batch mean, biased batch variance)."""
+    x = np.asarray(x, np.float64)
+    m = x.mean(axis=(0, 2, 3))
+    v = x.var(axis=(0, 2, 3))
+    y = (x - m.reshape(1, -1, 1, 1)) / np.sqrt(v.reshape(1, -1, 1, 1) + eps)
+    y = y * np.asarray(weight, np.float64).reshape(1, -1, 1, 1) + np.asarray(bias, np.float64).reshape(1, -1, 1, 1)
+    if res is not None:
+        y = y + np.asarray(res, np.float64)
+    if relu:
+        y = np.maximum(y, 0.0)
+    return y.astype(F32), m.astype(F32), v.astype(F32)
+
+
+def bn_act_train_backward(dy, x, weight, bias, res=None, relu=True, eps=1e-5):
+    """Gradient of `bn_act_train` (what autograd computes for `train.py:59`): g = dy * [y > 0];
+    dx = w / sqrt(v + eps) * (g - mean(g) - xhat * mean(g * xhat)); dres = g; dweight = sum g * xhat; dbias = sum g."""
+    x = np.asarray(x, np.float64)
+    g = np.asarray(dy, np.float64).copy()
+    w = np.asarray(weight, np.float64).reshape(1, -1, 1, 1)
+    b = np.asarray(bias, np.float64).reshape(1, -1, 1, 1)
+    m = x.mean(axis=(0, 2, 3), keepdims=True)
+    inv = 1.0 / np.sqrt(x.var(axis=(0, 2, 3), keepdims=True) + eps)
+    xh = (x - m) * inv
+    if relu:
+        y = xh * w + b + (0.0 if res is None else np.asarray(res, np.float64))
+        g *= y > 0
+    s1 = g.mean(axis=(0, 2, 3), keepdims=True)
+    s2 = (g * xh).mean(axis=(0, 2, 3), keepdims=True)
+    dx = w * inv * (g - s1 - xh * s2)
+    return dx.astype(F32), g.astype(F32), (g * xh).sum(axis=(0, 2, 3)).astype(F32), g.sum(axis=(0, 2, 3)).astype(F32)
+
+
+def maxpool3x3s2p1_backward(x, dy):
+    """Gradient of `nn.MaxPool2d(3, 2, 1)`: each output's gradient goes to the FIRST maximum of its window in
+    row-major scan order (torch's max_pool2d_with_indices rule; ReLU'd maps are full of tied zeros)."""
+    x, dy = np.asarray(x, F32), np.asarray(dy, F32)
+    B, C, H, W = x.shape
+    Ho, Wo = dy.shape[2], dy.shape[3]
+    dx = np.zeros_like(x)
+    for oh in range(Ho):
+        for ow in range(Wo):
+            h0, h1, w0, w1 = max(2 * oh - 1, 0), min(2 * oh + 2, H), max(2 * ow - 1, 0), min(2 * ow + 2, W)
+            win = x[:, :, h0:h1, w0:w1].reshape(B, C, -1)
+            k = win.argmax(axis=2)                        # first maximum
+            hh, ww = h0 + k // (w1 - w0), w0 + k % (w1 - w0)
+            bi, ci = np.meshgrid(np.arange(B), np.arange(C), indexing="ij")
+            np.add.at(dx, (bi, ci, hh, ww), dy[:, :, oh, ow])
+    return dx

@@ -170,3 +170,40 @@ def test_fused_bn_relu_pool_vs_torch(shape):
     assert rel_err(n(x.grad), n(x2.grad)) < 5e-5
     assert rel_err(n(bn.weight.grad), n(ref_bn.weight.grad)) < 5e-5 and rel_err(n(bn.bias.grad), n(ref_bn.bias.grad)) < 5e-5
     assert rel_err(n(bn.running_mean), n(ref_bn.running_mean)) < 2e-5 and rel_err(n(bn.running_var), n(ref_bn.running_var)) < 2e-5
+
+
+def _oracle_train_expect(x_nhwc, res_nhwc, w, b, dy_nhwc):
+    """Oracle side of `test_train_kernels_vs_oracle` (numpy, NCHW inside): BN(batch stats)+res+ReLU forward/backward and
+    maxpool forward/backward of that output."""
+    from oracle import cova_oracle as O
+    t = lambda a: None if a is None else np.ascontiguousarray(a.transpose(0, 3, 1, 2))
+    back = lambda a: np.ascontiguousarray(a.transpose(0, 2, 3, 1))
+    y, m, v = O.bn_act_train(t(x_nhwc), w, b, t(res_nhwc), True)
+    dx, dres, dw, db = O.bn_act_train_backward(t(dy_nhwc), t(x_nhwc), w, b, t(res_nhwc), True)
+    yp = O.maxpool3x3s2p1(y)
+    dyp = np.linspace(-1, 1, yp.size, dtype=np.float32).reshape(yp.shape)
+    dpool = O.maxpool3x3s2p1_backward(y, dyp)
+    return dict(y=back(y), dx=back(dx), dres=back(dres), dw=dw, db=db, yp=back(yp), dyp=back(dyp), dpool=back(dpool))
+
+
+def test_train_kernels_vs_oracle():
+    """The training-path kernels through the C ABI against the ORACLE restatements (`oracle/cova_oracle.py`:
+    bn_act_train[_backward], maxpool3x3s2p1[_backward], themselves pinned to torch on CPU in tests/test_oracle.py)."""
+    from cova_b200 import ops
+    g = torch.Generator().manual_seed(12)
+    shape = (2, 10, 13, 64)
+    x = (torch.randn(shape, generator=g) * 2 + 0.5)
+    res = torch.randn(shape, generator=g)
+    w, b = torch.rand(64, generator=g) + 0.5, torch.randn(64, generator=g) * 0.2
+    dy = torch.randn(shape, generator=g)
+    want = _oracle_train_expect(x.numpy(), res.numpy(), w.numpy(), b.numpy(), dy.numpy())
+    xd, rd, wd, bd, dyd = (t.to(DEV) for t in (x, res, w, b, dy))
+    y, mean, inv, _ = ops.bn_train_fwd(xd, wd, bd, None, None, 0.1, 1e-5, res=rd, relu=True)
+    dx, dres, dw, db = ops.bn_train_bwd(dyd, xd, mean, inv, wd, bd, res=rd, relu=True, want_dres=True)
+    assert rel_err(n(y), want["y"]) < 2e-5 and rel_err(n(dx), want["dx"]) < 5e-5 and rel_err(n(dres), want["dres"]) < 2e-5
+    assert rel_err(n(dw), want["dw"]) < 5e-5 and rel_err(n(db), want["db"]) < 5e-5
+    yd = torch.from_numpy(want["y"]).to(DEV)                     # pool the ORACLE's y so that ties are identical
+    yp, code, _ = ops.maxpool3x3s2_fwd(yd)
+    assert np.array_equal(n(yp), want["yp"])
+    dpool = ops.maxpool3x3s2_bwd(code, torch.from_numpy(want["dyp"]).to(DEV), tuple(yd.shape))
+    assert np.array_equal(n(dpool), want["dpool"])

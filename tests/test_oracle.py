@@ -168,3 +168,50 @@ def test_tail_topk_hits_matches_evaluate_model():
         hits = np.concatenate(rows)
         assert np.array_equal(hits[:, 1:], g["ev_img_acc_k%d" % k][:, 1:])
         assert np.allclose(hits[:, 1:].mean(0) * 100, g["ev_class_acc_k%d" % k][1:])
+
+
+# ----------------------------------------------------------------------------- training-mode backbone pieces (A9)
+def _train_case(seed, shape=(2, 8, 9, 11), with_res=True):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(shape, generator=g) * 2 + 0.5
+    res = torch.randn(shape, generator=g) if with_res else None
+    w, b = torch.rand(shape[1], generator=g) + 0.5, torch.randn(shape[1], generator=g) * 0.2
+    dy = torch.randn(shape, generator=g)
+    return x, res, w, b, dy
+
+
+@pytest.mark.parametrize("with_res,relu", [(True, True), (False, True), (False, False)])
+def test_train_bn_act_oracle_matches_torch(with_res, relu):
+    """oracle.bn_act_train / _backward against torch's own BatchNorm2d(train) + autograd (the library the reference
+    calls for these ops): forward, batch statistics, every gradient."""
+    x, res, w, b, dy = _train_case(3, with_res=with_res)
+    xt = x.clone().requires_grad_(True)
+    rt = res.clone().requires_grad_(True) if with_res else None
+    bn = torch.nn.BatchNorm2d(x.shape[1]).train()
+    with torch.no_grad():
+        bn.weight.copy_(w); bn.bias.copy_(b)
+    z = bn(xt)
+    if with_res:
+        z = z + rt
+    if relu:
+        z = torch.relu(z)
+    z.backward(dy)
+    y, m, v = O.bn_act_train(x.numpy(), w.numpy(), b.numpy(), None if res is None else res.numpy(), relu)
+    dx, dres, dw, db = O.bn_act_train_backward(dy.numpy(), x.numpy(), w.numpy(), b.numpy(),
+                                               None if res is None else res.numpy(), relu)
+    assert rel_err(y, z.detach().numpy()) < 2e-6
+    assert rel_err(m, x.mean((0, 2, 3)).numpy()) < 2e-6 and rel_err(v, x.var((0, 2, 3), unbiased=False).numpy()) < 2e-6
+    assert rel_err(dx, xt.grad.numpy()) < 2e-5
+    assert rel_err(dw, bn.weight.grad.numpy()) < 2e-5 and rel_err(db, bn.bias.grad.numpy()) < 2e-5
+    if with_res:
+        assert rel_err(dres, rt.grad.numpy()) < 2e-6
+
+
+def test_train_maxpool_backward_oracle_matches_torch_with_ties():
+    g = torch.Generator().manual_seed(5)
+    x = torch.relu(torch.randn(2, 5, 9, 12, generator=g)).round(decimals=1).requires_grad_(True)   # tied zeros
+    y = torch.nn.functional.max_pool2d(x, 3, 2, 1)
+    dy = torch.randn(y.shape, generator=g)
+    y.backward(dy)
+    assert np.array_equal(O.maxpool3x3s2p1(x.detach().numpy()), y.detach().numpy())
+    assert np.array_equal(O.maxpool3x3s2p1_backward(x.detach().numpy(), dy.numpy()), x.grad.numpy())
