@@ -137,6 +137,7 @@ def main():
 
     # ---- g_gat: the layer alone incl. edge cases (all -1 row, partial pads, arbitrary ids) and D3 heads
     g = torch.Generator().manual_seed(11)
+    torch.manual_seed(11)      # the layers below draw their weights from the global RNG: seeded, so that the file regenerates
     layer = ref.GraphAttentionLayer(96, 64)
     h = torch.randn(40, 96, generator=g)
     ci = torch.randint(-1, 40, (40, 10), generator=g)
@@ -270,7 +271,92 @@ def tail_fixture():
     save("g_tail", **ce, **adam, **coll, **ev)
 
 
+class _RefMultiHead(torch.nn.Module):
+    """SURVEY D3: H independent reference `GraphAttentionLayer(n_feat, hidden // H)` on the same inputs, outputs
+    concatenated on dim 1 (state_dict keys `gat.heads.{i}.*`)."""
+
+    def __init__(self, n_feat, hidden, n_heads):
+        super().__init__()
+        self.heads = torch.nn.ModuleList(ref.GraphAttentionLayer(n_feat, hidden // n_heads) for _ in range(n_heads))
+
+    def forward(self, h, ci, return_attn_wts=False):
+        outs = [hd(h, ci, return_attn_wts) for hd in self.heads]
+        if return_attn_wts:
+            return torch.cat([o[0] for o in outs], 1), torch.stack([o[1] for o in outs], 1)
+        return torch.cat(outs, 1)
+
+
+def build_ref_multihead(backbone, img, n_heads, seed=123):
+    _backbone["name"] = backbone
+    m = ref.CoVA((3, 3), img, 4, True, 384, 32, 0, 0.2, None)
+    m.gat = _RefMultiHead(m.n_feat, 384, n_heads)
+    sd = synth.make_state_dict(seed, backbone=backbone, n_heads=n_heads)
+    m.load_state_dict(sd, strict=True)
+    return m, sd
+
+
+@torch.no_grad()
+def config_fixtures():
+    """The BASELINE.json configs at their full shapes, on the very inputs `bench.py` times (rank 0: seed 1)."""
+    torch.set_num_threads(8)
+    # ---- g_c2: config 2 = B=16 pages of 1280^2, N=90, K=24, ResNet-18, eval (the headline workload)
+    m, _ = build_ref(img=1280)
+    m.eval()
+    inp = synth.gen(16, 90, 24, seed=1)
+    fm = m.convnet(inp[0])
+    vis = m.roi_pool(fm, inp[1]).view(inp[1].shape[0], m.n_visual_feat)
+    logits = m(*inp)
+    save("g_c2_r18_b16", logits=logits.numpy(), fm_sample=fm[:, :, ::16, ::16].numpy().copy(),
+         visual_sample=vis[::7].numpy().copy())
+    del fm, vis
+    # ---- g_r50_ragged: ResNet-50 at 256^2 / 320^2-class sizes with ragged pages (multi-strip stem, multi-tile pw_tc)
+    m, _ = build_ref(backbone="resnet50", img=320)
+    m.eval()
+    inp = synth.gen(3, 0, 24, seed=14, img=320, counts=[17, 2, 40])
+    r = intermediates(m, inp)
+    r["fm_sample"] = r.pop("fm")[:, :, ::4, ::4].copy()
+    for k in ("visual", "own", "ctx", "attn", "bbox"):
+        r.pop(k, None)
+    save("g_r50_ragged_img320", **r)
+    # ---- g_c5: config 5 shape = ResNet-50, N=300, K=48, 2-head GAT, 1280^2 (2 pages)
+    m, _ = build_ref_multihead("resnet50", 1280, 2)
+    m.eval()
+    inp = synth.gen(2, 300, 48, seed=1)
+    fm = m.convnet(inp[0])
+    logits = m(*inp)
+    save("g_c5_r50_n300_k48_h2", logits=logits.numpy(), fm_sample=fm[:, :, ::16, ::16].numpy().copy())
+    _backbone["name"] = "resnet18"
+
+
+@torch.enable_grad()
+def train_fixture_r50():
+    """Config 3/4 semantics at a CPU-sized shape: ResNet-50 backbone, train mode (batch-statistics BatchNorm, dropout
+    off), CE(sum), every backbone gradient + a few of the head's (`train.py:45-60`, `main.py:139`)."""
+    torch.set_num_threads(8)
+    m, _ = build_ref(backbone="resnet50", img=192, drop=0.0)
+    m.train()
+    images, bboxes, add, ci, labels = synth.gen(2, 14, 8, seed=15, img=192, with_labels=True)
+    out = m(images, bboxes, add, ci)
+    loss = torch.nn.CrossEntropyLoss(reduction="sum")(out, labels)
+    loss.backward()
+    grads = {n: p.grad.numpy() for n, p in m.named_parameters()}
+    keep = [k for k in grads if k.startswith("convnet.")] + ["gat.W_j.weight", "gat.attention_layer.weight",
+                                                             "bbox_feat_encoder.0.weight", "decoder.5.weight"]
+    save("g_train_r50_img192", logits=out.detach().numpy(), loss=np.float32(loss.item()), labels=labels.numpy(),
+         **{"grad:" + k: (grads[k] if grads[k].size < 400000 else grads[k][:, ::8].copy()) for k in keep},
+         **{"buf:" + k: v.numpy() for k, v in m.state_dict().items() if "running" in k})
+    _backbone["name"] = "resnet18"
+
+
 if __name__ == "__main__":
-    main()
-    train_fixture()
-    tail_fixture()
+    which = sys.argv[1:] or ["main", "train", "tail", "configs", "train_r50"]
+    if "main" in which:
+        main()
+    if "train" in which:
+        train_fixture()
+    if "tail" in which:
+        tail_fixture()
+    if "configs" in which:
+        config_fixtures()
+    if "train_r50" in which:
+        train_fixture_r50()

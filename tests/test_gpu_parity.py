@@ -433,12 +433,62 @@ def test_uint8_images_equal_totensor_path():
         assert torch.equal(a, b), engine
 
 
-def test_forward_roi_align_variant_golden():
+@pytest.mark.parametrize("engine,precision,tol", [("simt", "fp32", 2e-5), ("tcgen05", "fp32", 1e-4), ("tcgen05", "fp32x", 2e-5)])
+def test_forward_roi_align_variant_golden(engine, precision, tol):
+    """D1 variant (the RoI op north_star names): whole forward with RoIAlign on every engine vs the live reference with
+    line 58's module swapped for torchvision's RoIAlign."""
     g = load_golden("g_align_r18_img256")
-    m, _ = make_model("simt", img=256, roi_mode="align")
+    m, _ = make_model(engine, precision, img=256, roi_mode="align")
+    inp = to_dev(synth.gen(2, 20, 8, seed=4, img=256))
     with torch.no_grad():
-        logits = m(*to_dev(synth.gen(2, 20, 8, seed=4, img=256)))
-    assert rel_err(t2n(logits), g["logits"]) < 2e-5
+        logits = m(*inp)
+        vis = m._get_visual_features(inp[0], inp[1])
+    assert rel_err(t2n(vis), g["visual"]) < tol
+    assert rel_err(t2n(logits), g["logits"]) < tol
+
+
+# ----------------------------------------------------------------------------- the BASELINE.json configs at full shape
+@pytest.mark.parametrize("engine,precision,tol_fm,tol_logits", ENGINES)
+def test_forward_config2_golden(engine, precision, tol_fm, tol_logits):
+    """BASELINE config 2 on the very inputs bench.py times (B=16 pages of 1280^2, N=90, K=24, seed 1): logits [1440,4],
+    a strided sample of the feature map and of the RoI features against the live reference."""
+    g = load_golden("g_c2_r18_b16")
+    m, _ = make_model(engine, precision)
+    inp = to_dev(synth.gen(16, 90, 24, seed=1))
+    with torch.no_grad():
+        r = m._native.forward(*inp, return_intermediates=True)
+        logits = m(*inp)
+    assert rel_err(t2n(r["fm"]).transpose(0, 3, 1, 2)[:, :, ::16, ::16], g["fm_sample"]) < tol_fm
+    assert rel_err(t2n(r["own"][::7, :576]), g["visual_sample"]) < tol_fm
+    assert logits.shape == (1440, 4) and rel_err(t2n(logits), g["logits"]) < tol_logits
+    # element-wise figure beside the tensor-scale one: |a-b| / max(|b|, 1 % of the tensor scale)
+    want = g["logits"].astype(np.float64)
+    elt = np.abs(t2n(logits) - want) / np.maximum(np.abs(want), 1e-2 * np.abs(want).max())
+    assert elt.max() < 20 * tol_logits
+
+
+@pytest.mark.parametrize("engine,tol", [("simt", 2e-5), ("tcgen05", 1e-4)])
+def test_forward_resnet50_ragged_golden(engine, tol):
+    """ResNet-50 (D2) at 320^2 with ragged pages 17 / 2 / 40: multi-strip stem, multi-tile 1x1 GEMMs, F = 2336."""
+    g = load_golden("g_r50_ragged_img320")
+    m, _ = make_model(engine, img=320, backbone="resnet50")
+    inp = to_dev(synth.gen(3, 0, 24, seed=14, img=320, counts=[17, 2, 40]))
+    with torch.no_grad():
+        r = m._native.forward(*inp, return_intermediates=True)
+    assert rel_err(t2n(r["fm"]).transpose(0, 3, 1, 2)[:, :, ::4, ::4], g["fm_sample"]) < tol
+    assert rel_err(t2n(r["logits"]), g["logits"]) < 2.5 * tol
+
+
+def test_forward_config5_golden():
+    """BASELINE config 5 shape (ResNet-50, N=300 boxes/page, K=48, 2-head GAT, 1280^2; 2 pages) on the tensor-core
+    engine vs the live reference composed as SURVEY D3 defines it."""
+    g = load_golden("g_c5_r50_n300_k48_h2")
+    m, _ = make_model("tcgen05", backbone="resnet50", n_heads=2)
+    inp = to_dev(synth.gen(2, 300, 48, seed=1))
+    with torch.no_grad():
+        r = m._native.forward(*inp, return_intermediates=True)
+    assert rel_err(t2n(r["fm"]).transpose(0, 3, 1, 2)[:, :, ::16, ::16], g["fm_sample"]) < 1e-4
+    assert r["logits"].shape == (600, 4) and rel_err(t2n(r["logits"]), g["logits"]) < 2.5e-4
 
 
 @pytest.mark.parametrize("engine,tol", [("simt", 2e-5), ("tcgen05", 1e-4)])
@@ -610,6 +660,35 @@ def test_train_step_matches_reference_grads():
         m.engine = "simt"
         b = m(images, bboxes, add, ci)
     assert rel_err(t2n(a), t2n(b)) < 1e-4
+
+
+def test_train_step_resnet50_matches_reference_grads():
+    """Configs 3/4 semantics (ResNet-50 backbone, train mode, CE(sum)) against the LIVE reference: logits, loss, every
+    backbone gradient, BatchNorm buffers (`train.py:45-60`).  Gradient bound 2e-3 of each tensor's scale (+ a floor
+    from the global scale for the mathematically-zero ones)."""
+    from cova_b200.models import CoVA
+    g = load_golden("g_train_r50_img192")
+    m = CoVA((3, 3), 192, 4, True, 384, 32, 0, 0.0, None, pretrained=False, backbone="resnet50")
+    m.load_state_dict(synth.make_state_dict(123, backbone="resnet50"), strict=True)
+    m = m.to(DEV).train()
+    images, bboxes, add, ci, labels = to_dev(synth.gen(2, 14, 8, seed=15, img=192, with_labels=True))
+    out = m(images, bboxes, add, ci)
+    loss = torch.nn.CrossEntropyLoss(reduction="sum")(out, labels)
+    loss.backward()
+    assert rel_err(t2n(out), g["logits"]) < 1e-4 and abs(float(loss) - float(g["loss"])) < 1e-3 * abs(float(g["loss"]))
+    grads = dict(m.named_parameters())
+    gscale = max(float(np.abs(g[k]).max()) for k in g if k.startswith("grad:"))
+    worst = {}
+    for k in [k for k in g if k.startswith("grad:")]:
+        got, want = t2n(grads[k[5:]].grad), g[k]
+        if got.shape != want.shape:
+            got = got[:, ::8]
+        worst[k] = np.abs(got - want).max() / (np.abs(want).max() + 1e-3 * gscale)
+    bad = {k: v for k, v in worst.items() if v > 2e-3}
+    assert not bad, bad
+    sd = m.state_dict()
+    for k in [k for k in g if k.startswith("buf:")]:
+        assert rel_err(t2n(sd[k[4:]]), g[k]) < 1e-4, k
 
 
 def test_roi_pool_backward_kernel_vs_torch_scatter():

@@ -132,6 +132,18 @@ def test_torch_port_matches_golden():
     assert rel_err(out.numpy(), load_golden("g_r50_img128")["logits"]) < 1e-5
 
 
+def test_torch_port_matches_config_goldens():
+    """The port on the BASELINE configs at full shape (fixtures frozen from the live reference on the inputs bench.py
+    times): config 2 (B=16, 1280^2, N=90, K=24) restricted to its first 4 pages - pages are independent in eval mode,
+    which is itself asserted here - and the config-5 shape (ResNet-50, N=300, K=48, 2 heads)."""
+    from oracle import torch_port as TP
+    images, bboxes, add, ci = synth.gen(16, 90, 24, seed=1)
+    out = TP.forward(synth.make_state_dict(123), images[:4], bboxes[:360], add[:360], ci[:360])
+    assert rel_err(out.numpy(), load_golden("g_c2_r18_b16")["logits"][:360]) < 5e-6
+    out = TP.forward(synth.make_state_dict(123, backbone="resnet50", n_heads=2), *synth.gen(2, 300, 48, seed=1))
+    assert rel_err(out.numpy(), load_golden("g_c5_r50_n300_k48_h2")["logits"]) < 1e-5
+
+
 # ----------------------------------------------------------------------------- callers either side of the forward
 def test_tail_ce_sum_matches_torch():
     g = load_golden("g_tail")
