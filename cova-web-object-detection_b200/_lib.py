@@ -35,16 +35,38 @@ def _stale():
 
 
 def build(force=False, verbose=False):
-    """Compile every ``csrc/*.cu`` into ``libcova_b200.so`` (nvcc cross-compiles without a GPU)."""
+    """Compile every ``csrc/*.cu`` into ``libcova_b200.so`` (nvcc cross-compiles without a GPU).  One nvcc per source
+    (in parallel, objects under ``csrc/build/``, recompiled only when the source or a header changed), then one link."""
     if not force and not _stale():
         return LIB_PATH
+    from concurrent.futures import ThreadPoolExecutor
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + sources()
+    objdir = os.path.join(_CSRC, "build")
+    os.makedirs(objdir, exist_ok=True)
+    hdrs = glob.glob(os.path.join(_CSRC, "*.cuh")) + [HEADER]
+    hdr_t = max(os.path.getmtime(h) for h in hdrs)
+    cflags = [f for f in NVCC_FLAGS if f not in ("-shared", "--cudart", "static")]
+    logs = []
+
+    def one(src):
+        obj = os.path.join(objdir, os.path.basename(src)[:-3] + ".o")
+        if not force and os.path.exists(obj) and os.path.getmtime(obj) > max(os.path.getmtime(src), hdr_t):
+            return obj
+        cmd = [nvcc] + cflags + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", obj, src]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + r.stdout + r.stderr)
+        logs.append(r.stderr)
+        return obj
+
+    with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
+        objs = list(ex.map(one, sources()))
+    cmd = [nvcc] + NVCC_FLAGS + ["-o", LIB_PATH] + objs
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + r.stdout + r.stderr)
+        raise RuntimeError("link failed:\n" + " ".join(cmd) + "\n" + r.stdout + r.stderr)
     if verbose:
-        print(r.stderr)
+        print("\n".join(logs))
     return LIB_PATH
 
 
@@ -70,6 +92,7 @@ SIGNATURES = {
     "cova_pack_conv_weight_f16x2": (_I, [_P, _I, _I, _I, _I, _P, _P, _P]),
     "cova_roi_fwd": (_I, [_P, _I, _I, _I, _I, _P, _I, _I, _I, _F, _I, _I, _P, _L, _P, _P]),
     "cova_roi_pool_bwd": (_I, [_P, _L, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P]),
+    "cova_roi_align_bwd": (_I, [_P, _L, _P, _I, _I, _I, _I, _F, _I, _I, _I, _I, _P, _P]),
     "cova_bbox_enc_fwd": (_I, [_P, _I, _P, _P, _P, _P, _I, _P, _L, _P]),
     "cova_affine_cols_fwd": (_I, [_P, _I, _I, _L, _P, _P, _P, _L, _P]),
     "cova_linear_fwd": (_I, [_P, _L, _I, _I, _P, _I, _P, _P, _P, _P, _L, _I, _I, _P, _P, _L, _I, _P]),

@@ -51,7 +51,10 @@ gat_fwd_kernel(const float* __restrict__ whj, int64_t ld_whj, const float* __res
   for (int j = 0; j < GAT_KMAX / 32; ++j) {
     const int k = lane + 32 * j;
     int c = -1;
-    if (live && k < K) c = (int)ctx[(size_t)i * K + k];
+    if (live && k < K) {
+      const int64_t c64 = ctx[(size_t)i * K + k];
+      c = (c64 >= 0 && c64 < T) ? (int)c64 : -1;     // an id outside [0, T) is treated as padding, not dereferenced
+    }
     cid[j] = c;
     if (c >= 0) { lo = min(lo, c); hi = max(hi, c); }
   }
@@ -194,7 +197,8 @@ gat_bwd_kernel(const float* __restrict__ gout, int64_t ld_go, const float* __res
 #pragma unroll
   for (int j = 0; j < GAT_KMAX / 32; ++j) {
     const int k = lane + 32 * j;
-    cid[j] = k < K ? (int)ctx[(size_t)i * K + k] : -1;
+    const int64_t c64 = k < K ? ctx[(size_t)i * K + k] : -1;
+    cid[j] = (c64 >= 0 && c64 < T) ? (int)c64 : -1;
     a[j] = k < K ? attn[(size_t)i * K + k] : 0.f;
     da[j] = 0.f;
   }

@@ -24,12 +24,15 @@ struct RoiGeom {
 };
 
 // box edge quantisation of torchvision's roi_pool kernel: C round() of the fp32 product
-__device__ __forceinline__ RoiGeom roi_geom(const float* __restrict__ roi, float scale, int PH, int PW) {
+// A batch index outside [0, B) (never produced by the loader, `datasets.py:170-177`) selects no page: the box is moved
+// fully outside the map, so every bin is empty -> output 0, arg-max -1, no gradient - instead of an out-of-bounds read.
+__device__ __forceinline__ RoiGeom roi_geom(const float* __restrict__ roi, float scale, int PH, int PW, int B) {
   RoiGeom g;
   g.b = (int)roi[0];
   g.sw = (int)roundf(roi[1] * scale);
   g.sh = (int)roundf(roi[2] * scale);
-  const int ew = (int)roundf(roi[3] * scale), eh = (int)roundf(roi[4] * scale);
+  int ew = (int)roundf(roi[3] * scale), eh = (int)roundf(roi[4] * scale);
+  if (g.b < 0 || g.b >= B) { g.b = 0; g.sw = g.sh = ew = eh = 1 << 28; }
   g.rw = max(ew - g.sw + 1, 1);
   g.rh = max(eh - g.sh + 1, 1);
   g.bin_h = (float)g.rh / (float)PH;
@@ -51,7 +54,7 @@ __device__ __forceinline__ int bin_hi(int p, float bin, int start, int limit) {
 constexpr int ROI_SPLIT_WARPS = 4;
 template <bool WITH_ARGMAX, bool ROWSPLIT>
 __global__ void __launch_bounds__(ROI_THREADS)
-roi_pool_kernel(const float* __restrict__ fm, int Hf, int Wf, int C, const float* __restrict__ rois, int PH,
+roi_pool_kernel(const float* __restrict__ fm, int B, int Hf, int Wf, int C, const float* __restrict__ rois, int PH,
                 int PW, float scale, float* __restrict__ out, int64_t ld_out, int32_t* __restrict__ argmax) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int NW = ROWSPLIT ? ROI_SPLIT_WARPS : ROI_WARPS;
@@ -63,7 +66,7 @@ roi_pool_kernel(const float* __restrict__ fm, int Hf, int Wf, int C, const float
   const int ph_own = ROWSPLIT ? blockIdx.x % PH : 0;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int half = lane >> 4, c4 = (lane & 15) * 4;
-  const RoiGeom g = roi_geom(rois + (size_t)t * 5, scale, PH, PW);
+  const RoiGeom g = roi_geom(rois + (size_t)t * 5, scale, PH, PW, B);
 
   for (int i = threadIdx.x; i < NW * abins * ROI_CB; i += NW * 32) {
     acc[i] = -FLT_MAX;
@@ -213,7 +216,7 @@ __device__ __forceinline__ BilinearTaps bilinear_taps(int Hf, int Wf, float y, f
 // half-warps of the grid (a CTA-per-box layout left 7 of 16 half-warps idle for 3x3 bins and was latency-bound).
 template <int G>   // G = sampling_ratio when it is a compile-time 2 (all 16 bilinear taps in flight at once), 0 = runtime
 __global__ void __launch_bounds__(ROI_THREADS)
-roi_align_kernel(const float* __restrict__ fm, int Hf, int Wf, int C, const float* __restrict__ rois, int T, int PH,
+roi_align_kernel(const float* __restrict__ fm, int B, int Hf, int Wf, int C, const float* __restrict__ rois, int T, int PH,
                  int PW, float scale, int sampling_ratio, float* __restrict__ out, int64_t ld_out) {
   const int nbins = PH * PW, ncb = C / ROI_CB;
   const int64_t n_items = (int64_t)T * nbins * ncb;
@@ -226,15 +229,17 @@ roi_align_kernel(const float* __restrict__ fm, int Hf, int Wf, int C, const floa
   const int ph = bin / PW, pw = bin % PW;
   const float* roi = rois + (size_t)t * 5;
   const int b = (int)roi[0];
+  const bool page_ok = b >= 0 && b < B;              // a batch index outside [0, B): zeros, not an out-of-bounds read
   const float x1 = roi[1] * scale, y1 = roi[2] * scale, x2 = roi[3] * scale, y2 = roi[4] * scale;
   const float rw = fmaxf(x2 - x1, 1.f), rh = fmaxf(y2 - y1, 1.f);
   const float bh = rh / (float)PH, bw = rw / (float)PW;
   const int gh = G > 0 ? G : (sampling_ratio > 0 ? sampling_ratio : (int)ceilf(rh / (float)PH));
   const int gw = G > 0 ? G : (sampling_ratio > 0 ? sampling_ratio : (int)ceilf(rw / (float)PW));
   const float cnt = (float)max(gh * gw, 1);
-  const float* base = fm + (size_t)b * Hf * Wf * C + cb + c4;
+  const float* base = fm + (size_t)(page_ok ? b : 0) * Hf * Wf * C + cb + c4;
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (G > 0) {
+  if (!page_ok) {
+  } else if (G > 0) {
     constexpr int NS = G > 0 ? G * G : 1;
     BilinearTaps tp[NS];
     float4 v[NS][4];
@@ -272,11 +277,53 @@ roi_align_kernel(const float* __restrict__ fm, int Hf, int Wf, int C, const floa
   o[3 * nbins] = acc.w / cnt;
 }
 
+// RoIAlign backward (torchvision roi_align backward): every output bin spreads grad / (gh*gw) over the 4 bilinear taps
+// of each of its samples.  Same work split as the forward (16 lanes x float4 = one 64-channel block of one (box, bin));
+// boxes and samples overlap freely -> vector fp32 atomics (RED.ADD.F32x4) into the zero-initialised NHWC gradient map.
+__global__ void __launch_bounds__(ROI_THREADS)
+roi_align_bwd_kernel(const float* __restrict__ grad_out, int64_t ld_go, const float* __restrict__ rois, int T, int C, int PH,
+                     int PW, float scale, int sampling_ratio, int B, int Hf, int Wf, float* __restrict__ grad_fm) {
+  const int nbins = PH * PW, ncb = C / ROI_CB;
+  const int64_t n_items = (int64_t)T * nbins * ncb;
+  const int64_t item = (int64_t)blockIdx.x * (ROI_THREADS / 16) + (threadIdx.x >> 4);
+  if (item >= n_items) return;
+  const int c4 = (threadIdx.x & 15) * 4;
+  const int t = (int)(item / (nbins * ncb));
+  const int rem = (int)(item % (nbins * ncb));
+  const int bin = rem % nbins, cb = (rem / nbins) * ROI_CB;
+  const int ph = bin / PW, pw = bin % PW;
+  const float* roi = rois + (size_t)t * 5;
+  const int b = (int)roi[0];
+  if (b < 0 || b >= B) return;
+  const float x1 = roi[1] * scale, y1 = roi[2] * scale, x2 = roi[3] * scale, y2 = roi[4] * scale;
+  const float rw = fmaxf(x2 - x1, 1.f), rh = fmaxf(y2 - y1, 1.f);
+  const float bh = rh / (float)PH, bw = rw / (float)PW;
+  const int gh = sampling_ratio > 0 ? sampling_ratio : (int)ceilf(rh / (float)PH);
+  const int gw = sampling_ratio > 0 ? sampling_ratio : (int)ceilf(rw / (float)PW);
+  const float cnt = (float)max(gh * gw, 1);
+  const float* go = grad_out + (size_t)t * ld_go + (size_t)(cb + c4) * nbins + bin;
+  const float4 g = make_float4(go[0] / cnt, go[nbins] / cnt, go[2 * nbins] / cnt, go[3 * nbins] / cnt);
+  float* base = grad_fm + (size_t)b * Hf * Wf * C + cb + c4;
+  for (int iy = 0; iy < gh; ++iy) {
+    const float y = y1 + (float)ph * bh + ((float)iy + 0.5f) * bh / (float)gh;
+    for (int ix = 0; ix < gw; ++ix) {
+      const float x = x1 + (float)pw * bw + ((float)ix + 0.5f) * bw / (float)gw;
+      const BilinearTaps tp = bilinear_taps(Hf, Wf, y, x);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float w = tp.w[k];
+        if (w != 0.f)
+          atomicAdd(reinterpret_cast<float4*>(base + (size_t)tp.o[k] * C), make_float4(w * g.x, w * g.y, w * g.z, w * g.w));
+      }
+    }
+  }
+}
+
 // RoIPool backward (torchvision roi_pool backward): every pooled output sends its gradient to its arg-max pixel.
 // Bins of one box overlap by up to a pixel and boxes overlap freely, so several outputs hit the same pixel:
 // fp32 atomicAdd (RED.ADD.F32) into the zero-initialised NHWC gradient map.
 __global__ void roi_pool_bwd_kernel(const float* __restrict__ grad_out, int64_t ld_go, const int32_t* __restrict__ argmax,
-                                    const float* __restrict__ rois, int T, int C, int nbins, int Hf, int Wf,
+                                    const float* __restrict__ rois, int T, int C, int nbins, int B, int Hf, int Wf,
                                     float* __restrict__ grad_fm) {
   const int64_t n = (int64_t)T * C * nbins;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
@@ -286,6 +333,7 @@ __global__ void roi_pool_bwd_kernel(const float* __restrict__ grad_out, int64_t 
     const int r = (int)(i % ((int64_t)C * nbins));
     const int c = r / nbins;
     const int b = (int)rois[(size_t)t * 5];
+    if (b < 0 || b >= B) continue;
     atomicAdd(grad_fm + ((size_t)b * Hf * Wf + idx) * C + c, grad_out[(size_t)t * ld_go + r]);
   }
 }
@@ -337,9 +385,9 @@ extern "C" int cova_roi_fwd(const float* fm, int B, int Hf, int Wf, int C, const
     const int64_t n_items = (int64_t)T * PH * PW * (C / ROI_CB);
     const unsigned grid = (unsigned)((n_items + ROI_THREADS / 16 - 1) / (ROI_THREADS / 16));
     if (sampling_ratio == 2)
-      roi_align_kernel<2><<<grid, ROI_THREADS, 0, st>>>(fm, Hf, Wf, C, rois, T, PH, PW, spatial_scale, 2, out, ld_out);
+      roi_align_kernel<2><<<grid, ROI_THREADS, 0, st>>>(fm, B, Hf, Wf, C, rois, T, PH, PW, spatial_scale, 2, out, ld_out);
     else
-      roi_align_kernel<0><<<grid, ROI_THREADS, 0, st>>>(fm, Hf, Wf, C, rois, T, PH, PW, spatial_scale, sampling_ratio,
+      roi_align_kernel<0><<<grid, ROI_THREADS, 0, st>>>(fm, B, Hf, Wf, C, rois, T, PH, PW, spatial_scale, sampling_ratio,
                                                        out, ld_out);
   } else {
     const bool rowsplit = knob(COVA_KNOB_ROI_ROWSPLIT, 1) != 0 && (int64_t)T * PH < (1LL << 31);
@@ -351,7 +399,7 @@ extern "C" int cova_roi_fwd(const float* fm, int B, int Hf, int Wf, int C, const
 #define ROI_GO(AM, RS)                                                                                                   \
   do {                                                                                                                   \
     COVA_CUDA_OK(cudaFuncSetAttribute(roi_pool_kernel<AM, RS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    roi_pool_kernel<AM, RS><<<grid, threads, smem, st>>>(fm, Hf, Wf, C, rois, PH, PW, spatial_scale, out, ld_out, argmax); \
+    roi_pool_kernel<AM, RS><<<grid, threads, smem, st>>>(fm, B, Hf, Wf, C, rois, PH, PW, spatial_scale, out, ld_out, argmax); \
   } while (0)
     if (argmax) { if (rowsplit) ROI_GO(true, true); else ROI_GO(true, false); }
     else        { if (rowsplit) ROI_GO(false, true); else ROI_GO(false, false); }
@@ -368,8 +416,24 @@ extern "C" int cova_roi_pool_bwd(const float* grad_out, int64_t ld_go, const int
   COVA_REQUIRE(grad_out && argmax && rois && grad_fm && ld_go >= (int64_t)C * PH * PW, "cova_roi_pool_bwd: bad arguments");
   const int64_t n = (int64_t)T * C * PH * PW;
   const int blocks = (int)((n + 255) / 256 < 148 * 16 ? (n + 255) / 256 : 148 * 16);
-  cova::roi_pool_bwd_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(grad_out, ld_go, argmax, rois, T, C, PH * PW, Hf, Wf,
-                                                                     grad_fm);
+  cova::roi_pool_bwd_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(grad_out, ld_go, argmax, rois, T, C, PH * PW, B, Hf,
+                                                                     Wf, grad_fm);
+  COVA_LAUNCH_OK();
+  return COVA_OK;
+}
+
+extern "C" int cova_roi_align_bwd(const float* grad_out, int64_t ld_go, const float* rois, int T, int C, int PH, int PW,
+                                  float spatial_scale, int sampling_ratio, int B, int Hf, int Wf, float* grad_fm,
+                                  void* stream) {
+  using namespace cova;
+  COVA_REQUIRE(T >= 0 && C > 0 && PH > 0 && PW > 0 && B > 0 && Hf > 0 && Wf > 0, "cova_roi_align_bwd: bad dims");
+  if (T == 0) return COVA_OK;
+  COVA_REQUIRE(grad_out && rois && grad_fm && ld_go >= (int64_t)C * PH * PW, "cova_roi_align_bwd: bad arguments");
+  COVA_REQUIRE(C % ROI_CB == 0 && ((uintptr_t)grad_fm & 15) == 0, "cova_roi_align_bwd: C must be a multiple of %d, grad_fm 16-B aligned", ROI_CB);
+  const int64_t n_items = (int64_t)T * PH * PW * (C / ROI_CB);
+  const unsigned grid = (unsigned)((n_items + ROI_THREADS / 16 - 1) / (ROI_THREADS / 16));
+  roi_align_bwd_kernel<<<grid, ROI_THREADS, 0, (cudaStream_t)stream>>>(grad_out, ld_go, rois, T, C, PH, PW, spatial_scale,
+                                                                      sampling_ratio, B, Hf, Wf, grad_fm);
   COVA_LAUNCH_OK();
   return COVA_OK;
 }

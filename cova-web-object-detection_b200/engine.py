@@ -35,6 +35,12 @@ class NativeForward:
         return (m.engine, m.precision, ops.param_generation) + tuple((t.data_ptr(), t._version) for t in
                                                list(m.parameters()) + list(m.buffers()))
 
+    def invalidate(self):
+        """Drop the derived weight caches (folded BN, packed filters, GAT matrix).  Needed after writes that bypass
+        `Tensor._version` (`p.data.copy_`, raw-pointer updates by foreign code); the native optimizer and the native
+        BatchNorm already signal theirs through `ops.param_generation`."""
+        self._key = None
+
     def prepare(self):
         key = self._state_key()
         if key == self._key:
@@ -172,7 +178,7 @@ class NativeForward:
     def own_into(self, fm, bboxes, additional_feats, comb):
         """A4 + A5 + A5b: fill comb[:, :n_feat] (visual | bbox | additional)."""
         c, m = self.c, self.m
-        scale = fm.shape[1] / m.img_H
+        scale = m.spatial_scale                                      # fixed at construction like models.py:56
         ops.roi_fwd(fm, bboxes, m.roi_output_size, scale, comb, mode=m.roi_mode, sampling_ratio=2)
         col = m.n_visual_feat
         if m.bbox_hidden_dim > 0:
@@ -201,8 +207,7 @@ class NativeForward:
         """`CoVA._get_visual_features` (`models.py:124-127`)."""
         fm = self.feature_map(images)
         out = torch.empty((bboxes.shape[0], self.m.n_visual_feat), dtype=torch.float32, device=fm.device)
-        scale = fm.shape[1] / self.m.img_H
-        ops.roi_fwd(fm, bboxes, self.m.roi_output_size, scale, out, mode=self.m.roi_mode)
+        ops.roi_fwd(fm, bboxes, self.m.roi_output_size, self.m.spatial_scale, out, mode=self.m.roi_mode)
         return out
 
     def bbox_features(self, bboxes):

@@ -133,28 +133,48 @@ class _RoIPoolFn(torch.autograd.Function):
         return ops.roi_pool_bwd(grad_out.float(), argmax, rois, ctx.shape), None, None, None
 
 
-class _GatGatherFn(torch.autograd.Function):
-    """Native fused neighbour gather / masked softmax / weighted sum (cova_gat_fwd) with its native backward
-    (cova_gat_bwd).  Input `ext` = [W_j h | a_i.W_i h | a_j.W_j h | pad] comes from a differentiable GEMM, so the
-    gradients of W_i, W_j and the attention vector flow through autograd."""
+class _RoIAlignFn(torch.autograd.Function):
+    """Native RoIAlign(P, scale, sampling_ratio=2, aligned=False) forward and backward (the RoI op
+    BASELINE.json's north_star names; atomic scatter of the 4 bilinear taps of every sample, as torchvision's)."""
 
     @staticmethod
-    def forward(ctx, ext, bias, ctx_idx, Hd, alpha):
+    def forward(ctx, fm_nhwc, rois, P, scale):
+        B, Hf, Wf, C = fm_nhwc.shape
+        out = torch.empty((rois.shape[0], C * P[0] * P[1]), dtype=torch.float32, device=fm_nhwc.device)
+        ops.roi_fwd(fm_nhwc.contiguous(), rois, P, scale, out, mode="align", sampling_ratio=2)
+        ctx.save_for_backward(rois)
+        ctx.meta = ((B, Hf, Wf, C), P, scale)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        (rois,) = ctx.saved_tensors
+        shape, P, scale = ctx.meta
+        return ops.roi_align_bwd(grad_out.float(), rois, P, scale, shape, 2), None, None, None
+
+
+class _GatGatherFn(torch.autograd.Function):
+    """Native fused neighbour gather / masked softmax / weighted sum (cova_gat_fwd) with its native backward
+    (cova_gat_bwd).  Input `ext` = [W_j h | a_i.W_i h + b | a_j.W_j h | pad] comes from a differentiable GEMM whose bias
+    row carries the attention bias b, so the gradients of W_i, W_j, the attention vector and b flow through autograd
+    and no scalar has to be read back to the host (the kernels get att_b = 0)."""
+
+    @staticmethod
+    def forward(ctx, ext, ctx_idx, Hd, alpha):
         ext = ext.contiguous()
         out = torch.empty((ext.shape[0], Hd), dtype=torch.float32, device=ext.device)
-        b = float(bias.detach().item())
-        attn = ops.gat_fwd(ext[:, :Hd], ext[:, Hd], ext[:, Hd + 1], b, alpha, ctx_idx, out, want_attn=True)
+        attn = ops.gat_fwd(ext[:, :Hd], ext[:, Hd], ext[:, Hd + 1], 0.0, alpha, ctx_idx, out, want_attn=True)
         ctx.save_for_backward(ext, ctx_idx, attn)
-        ctx.meta = (Hd, b, alpha)
+        ctx.meta = (Hd, alpha)
         ctx.mark_non_differentiable(attn)
         return out, attn
 
     @staticmethod
     def backward(ctx, grad_out, _grad_attn):
         ext, ctx_idx, attn = ctx.saved_tensors
-        Hd, b, alpha = ctx.meta
-        d_ext, d_b = ops.gat_bwd(grad_out.float(), ext, Hd, b, alpha, ctx_idx, attn)
-        return d_ext, d_b, None, None, None
+        Hd, alpha = ctx.meta
+        d_ext, _ = ops.gat_bwd(grad_out.float(), ext, Hd, 0.0, alpha, ctx_idx, attn)
+        return d_ext, None, None, None
 
 
 # ----------------------------------------------------------------------------- GAT
@@ -200,7 +220,9 @@ class GraphAttentionLayer(nn.Module):
             a = self.attention_layer.weight[0]
             pad = torch.zeros((2, self.in_features), dtype=h_i.dtype, device=h_i.device)
             ext_w = torch.cat((self.W_j.weight, (a[:Hd] @ self.W_i.weight)[None], (a[Hd:] @ self.W_j.weight)[None], pad), 0)
-            out, attn = _GatGatherFn.apply(F.linear(h_i, ext_w), self.attention_layer.bias, context_indices, Hd,
+            zb = torch.zeros(Hd + 4, dtype=h_i.dtype, device=h_i.device)
+            ext_b = torch.cat((zb[:Hd], self.attention_layer.bias, zb[:3]))      # b rides in the s column
+            out, attn = _GatGatherFn.apply(F.linear(h_i, ext_w, ext_b), context_indices, Hd,
                                            float(self.leakyrelu.negative_slope))
             return (out, attn) if return_attn_wts else out
         N, K = context_indices.shape
@@ -305,6 +327,15 @@ class CoVA(nn.Module):
         self._native = NativeForward(self)
         print("Model Parameters:", count_parameters(self))
 
+    def invalidate_native_cache(self):
+        """Call after modifying parameters / buffers through `.data` or raw pointers (writes `Tensor._version` cannot
+        see): the native inference path rebuilds its packed / folded weight copies on the next forward."""
+        self._native.invalidate()
+        for h in (self.gat_heads() if self.use_context else []):
+            h._native = None
+        if self.use_context and hasattr(self.gat, "heads"):
+            self.gat._native = None
+
     def gat_heads(self):
         return list(self.gat.heads) if isinstance(self.gat, MultiHeadGAT) else [self.gat]
 
@@ -364,9 +395,7 @@ class CoVA(nn.Module):
             fm = self.convnet(images).permute(0, 2, 3, 1)            # NCHW -> NHWC view for the native RoI kernel
         if self.roi_mode == "pool":
             return _RoIPoolFn.apply(fm, bboxes.float(), self.roi_output_size, self.spatial_scale)
-        import torchvision   # RoIAlign backward is not written yet: library op on the autograd path only
-        return torchvision.ops.roi_align(fm.permute(0, 3, 1, 2), bboxes, self.roi_output_size, self.spatial_scale,
-                                         2, False).reshape(bboxes.shape[0], self.n_visual_feat)
+        return _RoIAlignFn.apply(fm, bboxes.float(), self.roi_output_size, self.spatial_scale)
 
     def _get_bbox_features(self, bboxes):
         """`models.py:129-148`: [x,y,w,h,asp_ratio] -> bbox_hidden_dim features (or [N,0])."""

@@ -198,6 +198,20 @@ def roi_pool_bwd(grad_out, argmax, rois, fm_shape):
     return grad_fm
 
 
+def roi_align_bwd(grad_out, rois, P, spatial_scale, fm_shape, sampling_ratio=2):
+    """Backward of RoIAlign(P, scale, sampling_ratio, aligned=False): [T, C*PH*PW] -> NHWC fp32 [B,Hf,Wf,C]."""
+    _cuda(grad_out, torch.float32, "grad_out")
+    B, Hf, Wf, C = fm_shape
+    PH, PW = P
+    T = rois.shape[0]
+    if grad_out.stride(1) != 1:
+        grad_out = grad_out.contiguous()
+    grad_fm = torch.zeros(fm_shape, dtype=torch.float32, device=grad_out.device)
+    _call("cova_roi_align_bwd", grad_out.data_ptr(), grad_out.stride(0) if T else C * PH * PW, _ptr(rois.contiguous()), T, C,
+          PH, PW, float(spatial_scale), int(sampling_ratio), B, Hf, Wf, grad_fm.data_ptr(), _stream())
+    return grad_fm
+
+
 def bbox_enc_fwd(rois, w, b, bn_scale, bn_shift, out):
     _cuda(rois, torch.float32, "bboxes")
     rois = rois.contiguous()
@@ -414,6 +428,9 @@ def bn_train_fwd(x, gamma, beta, running_mean, running_var, momentum, eps, res=N
     _call("cova_bn_train_stats", x.data_ptr(), M, C, ws.data_ptr(), _stream())
     _call("cova_bn_train_finalize", ws.data_ptr(), M, C, float(eps), float(momentum), mean.data_ptr(), inv.data_ptr(),
           _ptr(running_mean), _ptr(running_var), _stream())
+    if running_mean is not None:          # raw-pointer buffer update: tell the derived-weight caches
+        global param_generation
+        param_generation += 1
     _call("cova_bn_act_fwd", x.data_ptr(), M, C, mean.data_ptr(), inv.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
           _ptr(None if res is None else _nhwc(res, "res")), int(relu), y.data_ptr(),
           pl.p0.data_ptr() if pl else 0, pl.p1.data_ptr() if pl else 0, planes_dtype, _stream())

@@ -42,6 +42,11 @@ class _Slot:
 
 
 def _stage(slot, batch, device, stream):
+    # The slot's pinned staging buffers are about to be overwritten by the HOST: the asynchronous H2D copy issued from
+    # them for an earlier batch must have completed (a stream-side wait_event only orders the GPU work and may leave
+    # that copy still queued when the host runs ahead, e.g. an inference loop with no per-batch sync).
+    if slot.event is not None:
+        slot.event.synchronize()
     with torch.cuda.stream(stream):
         # The device buffers are first written on the COPY stream, so they must come from that stream's pool:
         # a block the caching allocator hands out for the compute stream may still be in use by kernels that are

@@ -30,6 +30,16 @@ def _ones_zeros(device):
     return _CONST[k]
 
 
+def _momentum(bn, track):
+    """nn.BatchNorm's exponential_average_factor: `momentum`, or the cumulative average 1 / num_batches_tracked (counted
+    after this batch) when momentum is None."""
+    if bn.momentum is not None:
+        return bn.momentum
+    if track and bn.num_batches_tracked is not None:
+        return 1.0 / float(int(bn.num_batches_tracked) + 1)
+    return 0.0
+
+
 class _BnActFn(torch.autograd.Function):
     """(y, y_hi, y_lo) = [relu](BN_batchstats(x) [+ res]) on NHWC fp32; running statistics updated like nn.BatchNorm2d.
     The planes are the split-bf16 copy of y for the tensor-core convolution that follows (or None)."""
@@ -39,8 +49,8 @@ class _BnActFn(torch.autograd.Function):
         ctx.set_materialize_grads(False)      # no zero-filled 400 MB "gradients" for the non-differentiable planes
         x = x.contiguous()
         res_c = None if res is None else res.contiguous()
-        mom = 0.1 if bn.momentum is None else bn.momentum
         track = bn.track_running_stats and bn.running_mean is not None
+        mom = _momentum(bn, track)
         y, mean, inv, pl = ops.bn_train_fwd(x, gamma.detach(), beta.detach(), bn.running_mean if track else None,
                                             bn.running_var if track else None, mom, bn.eps, res=res_c, relu=relu,
                                             want_planes=want_planes, planes_dtype=F16X2)
@@ -72,8 +82,8 @@ class _BnReluPoolFn(torch.autograd.Function):
     def forward(ctx, x, gamma, beta, bn, want_planes):
         ctx.set_materialize_grads(False)
         x = x.contiguous()
-        mom = 0.1 if bn.momentum is None else bn.momentum
         track = bn.track_running_stats and bn.running_mean is not None
+        mom = _momentum(bn, track)
         y, code, mean, inv, pl = ops.bn_relu_pool_fwd(x, gamma.detach(), beta.detach(), bn.running_mean if track else None,
                                                       bn.running_var if track else None, mom, bn.eps,
                                                       want_planes=want_planes, planes_dtype=F16X2)

@@ -105,12 +105,58 @@ class FlatAdam(torch.optim.Optimizer):
                  for f in self._flat if f is not None]
         return works if async_op else None
 
+    def _adopt_stray_grads(self):
+        """`model.zero_grad()` (set_to_none=True is torch's default) or `p.grad = None` makes autograd allocate a fresh
+        gradient outside the bucket: copy it in and re-point `p.grad`, instead of stepping on a stale (zero) bucket."""
+        for g, f in zip(self.param_groups, self._flat):
+            if f is None:
+                continue
+            off = 0
+            base = f["g"].data_ptr()
+            for p in g["params"]:
+                if not p.requires_grad:
+                    continue
+                k = p.numel()
+                view = f["g"][off:off + k].view(p.shape)
+                if p.grad is None:
+                    view.zero_()
+                    p.grad = view
+                elif p.grad.data_ptr() != base + 4 * off:
+                    view.copy_(p.grad)
+                    p.grad = view
+                if p.data_ptr() != f["p"].data_ptr() + 4 * off:      # e.g. model.to(...) / p.data = ... after construction
+                    f["p"][off:off + k].copy_(p.detach().reshape(-1))
+                    p.data = f["p"][off:off + k].view(p.shape)
+                off += k
+
+    def load_state_dict(self, state_dict):
+        """torch's Adam layout in (`step`, `exp_avg`, `exp_avg_sq` per parameter), copied INTO the flat moment buffers the
+        kernel reads (the inherited method would replace `state[p]` with detached copies the kernel never sees)."""
+        super().load_state_dict(state_dict)
+        for g, f in zip(self.param_groups, self._flat):
+            if f is None:
+                continue
+            off = 0
+            for p in g["params"]:
+                if not p.requires_grad:
+                    continue
+                k = p.numel()
+                st = self.state.get(p, {})
+                if "exp_avg" in st:
+                    f["m"][off:off + k].copy_(st["exp_avg"].reshape(-1).to(f["m"].device))
+                    f["v"][off:off + k].copy_(st["exp_avg_sq"].reshape(-1).to(f["v"].device))
+                    f["step"].fill_(float(st["step"]))
+                self.state[p] = dict(step=f["step"], exp_avg=f["m"][off:off + k].view(p.shape),
+                                     exp_avg_sq=f["v"][off:off + k].view(p.shape))
+                off += k
+
     @torch.no_grad()
     def step(self, closure=None):
         loss = None
         if closure is not None:
             with torch.enable_grad():
                 loss = closure()
+        self._adopt_stray_grads()
         for g, f in zip(self.param_groups, self._flat):
             if f is None:
                 continue

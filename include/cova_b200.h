@@ -139,6 +139,12 @@ int cova_roi_fwd(const float* fm, int B, int Hf, int Wf, int C, const float* roi
 int cova_roi_pool_bwd(const float* grad_out, int64_t ld_go, const int32_t* argmax, const float* rois, int T, int C,
                       int PH, int PW, int B, int Hf, int Wf, float* grad_fm, void* stream);
 
+/* ---- A4' backward (D1 variant on the train path): torchvision roi_align backward - every output bin adds
+ * grad / (gh*gw) x bilinear weight to the 4 taps of each of its samples (fp32 vector atomics).  grad_fm: NHWC fp32
+ * [B,Hf,Wf,C], ZEROED by the caller, 16-byte aligned; C a multiple of 64; aligned=False semantics as the forward. */
+int cova_roi_align_bwd(const float* grad_out, int64_t ld_go, const float* rois, int T, int C, int PH, int PW,
+                       float spatial_scale, int sampling_ratio, int B, int Hf, int Wf, float* grad_fm, void* stream);
+
 /* ---- A5: positional encoder.  Replaces `_get_bbox_features` + `bbox_feat_encoder`
  * (`models.py:129-148`, `:65-70`): [x1,y1,w,h,w/h] -> Linear(5,D) -> folded BN1d -> ReLU.
  * Writes out[t*ld_out + d], d < D (so it can land at column C*P*P of the `own` row: the concat of

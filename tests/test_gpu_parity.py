@@ -710,6 +710,60 @@ def test_roi_pool_backward_kernel_vs_torch_scatter():
     assert rel_err(t2n(got).reshape(-1), want.cpu().numpy()) < 1e-5
 
 
+@pytest.mark.parametrize("P", [(3, 3), (7, 7), (2, 5)])
+def test_roi_align_backward_kernel_vs_torchvision(P):
+    """Native RoIAlign backward (atomic scatter of the bilinear taps) vs torchvision.ops.roi_align's autograd - the op
+    the reference model would call with line 58 swapped - on the adversarial boxes of g_roi (negative
+    coordinates, sub-pixel boxes, boxes outside the map), C = 64."""
+    import torchvision
+    from cova_b200.models import _RoIAlignFn
+    g = load_golden("g_roi")
+    gen = torch.Generator().manual_seed(31)
+    fm = torch.randn(2, 64, 40, 48, generator=gen).to(DEV)
+    boxes = torch.from_numpy(g["boxes"]).to(DEV)
+    go = torch.randn(boxes.shape[0], 64 * P[0] * P[1], generator=gen).to(DEV)
+    a = fm.permute(0, 2, 3, 1).contiguous().requires_grad_(True)
+    out = _RoIAlignFn.apply(a, boxes, P, 0.25)
+    out.backward(go)
+    b = fm.clone().requires_grad_(True)
+    ref = torchvision.ops.roi_align(b, boxes, P, 0.25, 2, False).reshape(boxes.shape[0], -1)
+    ref.backward(go)
+    assert rel_err(t2n(out), t2n(ref)) < 3e-5
+    assert rel_err(t2n(a.grad).transpose(0, 3, 1, 2), t2n(b.grad)) < 2e-5
+
+
+def test_out_of_range_indices_are_safe():
+    """A batch index outside [0, B) or a context id outside [0, T) (never produced by the reference's loader) must not
+    read or write out of bounds: such a box pools to zeros and gets no gradient, such a neighbour counts as padding."""
+    o = ops()
+    g = torch.Generator().manual_seed(5)
+    fm = torch.randn(2, 20, 24, 64, generator=g).to(DEV)
+    _, bboxes, _, _ = synth.gen(2, 6, 4, seed=5, img=80)
+    bad = bboxes.clone()
+    bad[3, 0], bad[7, 0] = 9.0, -2.0
+    for mode in ("pool", "align"):
+        out_ok, out_bad = torch.empty((12, 576), device=DEV), torch.empty((12, 576), device=DEV)
+        o.roi_fwd(fm, bboxes.to(DEV), (3, 3), 0.25, out_ok, mode=mode)
+        am = o.roi_fwd(fm, bad.to(DEV), (3, 3), 0.25, out_bad, mode=mode, want_argmax=(mode == "pool"))
+        keep = [i for i in range(12) if i not in (3, 7)]
+        assert torch.equal(out_ok[keep], out_bad[keep]) and float(out_bad[[3, 7]].abs().max()) == 0.0
+        go = torch.ones((12, 576), device=DEV)
+        gfm = (o.roi_pool_bwd(go, am, bad.to(DEV), fm.shape) if mode == "pool"
+               else o.roi_align_bwd(go, bad.to(DEV), (3, 3), 0.25, fm.shape))
+        assert torch.isfinite(gfm).all()
+    T, K, Hd = 10, 6, 32
+    whj, s, t = torch.randn(T, Hd, generator=g).to(DEV), torch.randn(T, generator=g).to(DEV), torch.randn(T, generator=g).to(DEV)
+    ci = torch.randint(-1, T, (T, K), generator=g)
+    ci_bad = ci.clone()
+    ci_pad = ci.clone()
+    ci_bad[2, 1], ci_pad[2, 1] = T + 5, -1
+    ci_bad[4, 0], ci_pad[4, 0] = 1 << 40, -1
+    a, b = torch.empty((T, Hd), device=DEV), torch.empty((T, Hd), device=DEV)
+    o.gat_fwd(whj, s, t, 0.1, 0.2, ci_bad.to(DEV), a)
+    o.gat_fwd(whj, s, t, 0.1, 0.2, ci_pad.to(DEV), b)
+    assert torch.equal(a, b)
+
+
 def test_gat_backward_kernel_vs_autograd():
     """Native GAT gather backward vs PyTorch autograd of the operator formulation (arbitrary ids, padding, an
     all -1 row), for the layer's input and all four parameters."""
