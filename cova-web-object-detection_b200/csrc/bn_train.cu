@@ -269,6 +269,47 @@ split_planes_kernel(const float* __restrict__ x, int64_t n4, __nv_bfloat16* __re
     split4(__ldg(reinterpret_cast<const float4*>(x) + i), hi, lo, (size_t)i * 4, f16);
 }
 
+// max |x| of a map, as the bit pattern of a non-negative float (monotonic in the value): one atomicMax per CTA
+__global__ void __launch_bounds__(256)
+absmax_kernel(const float* __restrict__ x, int64_t n4, unsigned int* __restrict__ out_bits) {
+  float m = 0.f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(x) + i);
+    m = fmaxf(m, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));   // fmaxf drops NaNs
+  }
+  m = warp_max(m);
+  __shared__ float sm[8];
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x < 8) {
+    m = sm[threadIdx.x];
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffu, m, o));
+    if (threadIdx.x == 0) atomicMax(out_bits, __float_as_uint(m));
+  }
+}
+
+// power-of-two scale that brings max|x| into [2^target, 2^(target+1)); 1 for a zero / non-finite maximum
+__device__ __forceinline__ float pow2_scale(unsigned int amax_bits, int target_log2) {
+  const int e = (int)(amax_bits >> 23) & 0xff;
+  if (e == 0 || e == 0xff) return 1.f;
+  int se = 127 + target_log2 - (e - 127);
+  se = min(max(se, 1), 254);
+  return __uint_as_float((unsigned int)se << 23);
+}
+
+__global__ void __launch_bounds__(256)
+split_planes_scaled_kernel(const float* __restrict__ x, int64_t n4, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
+                           int f16, const unsigned int* __restrict__ amax_bits, int target_log2, float* __restrict__ inv_vec) {
+  const float s = pow2_scale(__ldg(amax_bits), target_log2);
+  if (blockIdx.x == 0) inv_vec[threadIdx.x] = 1.f / s;               // 256 copies of 1/s (exact: s is a power of two)
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    float4 v = __ldg(reinterpret_cast<const float4*>(x) + i);
+    v.x *= s; v.y *= s; v.z *= s; v.w *= s;
+    split4(v, hi, lo, (size_t)i * 4, f16);
+  }
+}
+
 // ---------------------------------------------------------------- stem: BatchNorm(batch stats) + ReLU + maxpool, fused
 // The normalised [B,H,W,C] map between bn1 and the maxpool (1.7 GB at B=16) is never written: the forward pools
 // relu(bn(x)) on the fly from the raw conv1 output, the backward re-derives each input pixel's gradient from the
@@ -506,6 +547,22 @@ extern "C" int cova_split_planes(const float* x, int64_t n, void* hi, void* lo, 
   COVA_REQUIRE((((uintptr_t)x & 15) | ((uintptr_t)hi & 7) | ((uintptr_t)lo & 7)) == 0, "cova_split_planes: alignment");
   split_planes_kernel<<<ew_grid(n / 4, 256), 256, 0, (cudaStream_t)stream>>>(x, n / 4, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo,
                                                                             planes_dtype == COVA_F16X2);
+  COVA_LAUNCH_OK();
+  return COVA_OK;
+}
+
+extern "C" int cova_split_planes_scaled(const float* x, int64_t n, void* hi, void* lo, int planes_dtype, int target_log2,
+                                        unsigned int* ws, float* inv_scale_vec, void* stream) {
+  COVA_REQUIRE(planes_dtype == COVA_BF16X2 || planes_dtype == COVA_F16X2, "cova_split_planes_scaled: planes are split-bf16 or split-fp16");
+  COVA_REQUIRE(x && hi && lo && ws && inv_scale_vec && n > 0 && n % 4 == 0, "cova_split_planes_scaled: n must be a positive multiple of 4");
+  COVA_REQUIRE((((uintptr_t)x & 15) | ((uintptr_t)hi & 7) | ((uintptr_t)lo & 7)) == 0, "cova_split_planes_scaled: alignment");
+  COVA_REQUIRE(target_log2 >= -14 && target_log2 <= 14, "cova_split_planes_scaled: target_log2 out of range");
+  cudaStream_t st = (cudaStream_t)stream;
+  COVA_CUDA_OK(cudaMemsetAsync(ws, 0, sizeof(unsigned int), st));
+  absmax_kernel<<<ew_grid(n / 4, 256), 256, 0, st>>>(x, n / 4, ws);
+  COVA_LAUNCH_OK();
+  split_planes_scaled_kernel<<<ew_grid(n / 4, 256), 256, 0, st>>>(x, n / 4, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo,
+                                                                  planes_dtype == COVA_F16X2, ws, target_log2, inv_scale_vec);
   COVA_LAUNCH_OK();
   return COVA_OK;
 }

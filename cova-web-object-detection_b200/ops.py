@@ -58,7 +58,7 @@ def device_info():
     return sm.value, smem.value
 
 
-KNOBS = {"conv_l2_prefetch": 0, "conv_res_prefetch": 1, "stem_l2_prefetch": 2, "stem_converters": 5, "conv_res_load": 6, "roi_rowsplit": 7}
+KNOBS = {"wgrad_drain": 8, "conv_l2_prefetch": 0, "conv_res_prefetch": 1, "stem_l2_prefetch": 2, "stem_converters": 5, "conv_res_load": 6, "roi_rowsplit": 7}
 
 
 def set_knob(name, value):
@@ -399,6 +399,32 @@ def split_planes(x, dtype=BF16X2):
     pl = _planes_like(x, dtype)
     _call("cova_split_planes", x.data_ptr(), x.numel(), pl.p0.data_ptr(), pl.p1.data_ptr(), dtype, _stream())
     return pl
+
+
+def split_planes_scaled(x, dtype=F16X2, target_log2=10):
+    """Gradient map -> split `Planes` of x * s with a per-tensor power-of-two s chosen on the device (no host sync), and
+    the [256] vector of 1/s the consuming kernel multiplies back in.  Returns (Planes, inv_scale_vec)."""
+    _nhwc(x, "x")
+    pl = _planes_like(x, dtype)
+    ws = torch.empty(1, dtype=torch.int32, device=x.device)
+    inv = torch.empty(256, dtype=torch.float32, device=x.device)
+    _call("cova_split_planes_scaled", x.data_ptr(), x.numel(), pl.p0.data_ptr(), pl.p1.data_ptr(), dtype, int(target_log2),
+          ws.data_ptr(), inv.data_ptr(), _stream())
+    return pl, inv
+
+
+def conv3x3_wgrad(x_planes, dy_planes, inv_scale=None):
+    """Weight gradient [64,64,3,3] (OIHW fp32) of a 3x3 s1 p1 64->64 convolution from the split planes of its input and of
+    its (scaled) output gradient; inv_scale = device tensor holding 1/s of the dy planes (or None)."""
+    B, H, W, C = x_planes.shape
+    if C != 64 or tuple(dy_planes.shape) != (B, H, W, 64) or x_planes.dtype != dy_planes.dtype:
+        raise RuntimeError("cova_b200: conv3x3_wgrad needs [B,H,W,64] split planes of one format for x and dy")
+    dev = x_planes.p0.device
+    ws = torch.empty(9 * 64 * 64, dtype=torch.float32, device=dev)
+    dw = torch.empty((64, 64, 3, 3), dtype=torch.float32, device=dev)
+    _call("cova_conv3x3_wgrad", x_planes.p0.data_ptr(), x_planes.p1.data_ptr(), dy_planes.p0.data_ptr(), dy_planes.p1.data_ptr(),
+          B, H, W, x_planes.dtype, _ptr(inv_scale), ws.data_ptr(), dw.data_ptr(), _stream())
+    return dw
 
 
 def stem_conv_raw_fwd(images, w_packed):

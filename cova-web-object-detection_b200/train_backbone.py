@@ -125,15 +125,14 @@ class _MaxPoolFn(torch.autograd.Function):
         return ops.maxpool3x3s2_bwd(code, dy.contiguous(), ctx.in_shape), None
 
 
-def _conv_bwd(dy_nhwc, x_nchw, weight, stride, padding, need_input):
-    """Library backward of a convolution (cuDNN dgrad / wgrad through ATen) under the process's own cuDNN flags - the
-    same policy as the backward of an `F.conv2d` in the all-library path; COVA_B200_TRAIN_TF32=1 forces TF32 on."""
+def _conv_bwd(dy_nhwc, x_nchw, weight, stride, padding, need_input, want_w=True):
+    """Library backward of a convolution (cuDNN dgrad / wgrad through ATen) in plain fp32: TF32 is switched OFF here
+    whatever the process default is (torch's default lets cuDNN use TF32 - narrower than the reference's CPU fp32);
+    COVA_B200_TRAIN_TF32=1 turns it on for speed comparisons."""
     args = (dy_nhwc.permute(0, 3, 1, 2), x_nchw, weight, None, stride, padding, [1, 1], False, [0, 0], 1,
-            [need_input, True, False])
-    if os.environ.get("COVA_B200_TRAIN_TF32", "0") == "1":
-        with torch.backends.cudnn.flags(enabled=True, allow_tf32=True):
-            gi, gw, _ = torch.ops.aten.convolution_backward(*args)
-    else:
+            [need_input, want_w, False])
+    tf32 = os.environ.get("COVA_B200_TRAIN_TF32", "0") == "1"
+    with torch.backends.cudnn.flags(enabled=True, allow_tf32=tf32):
         gi, gw, _ = torch.ops.aten.convolution_backward(*args)
     return gi, gw
 
@@ -159,8 +158,12 @@ class _StemConvFn(torch.autograd.Function):
 
 
 class _Conv3x3Fn(torch.autograd.Function):
-    """3x3 s1 p1 64->64 convolution (no bias) forward on the tensor cores from split-bf16 planes; raw fp32 NHWC output.
-    Backward = library dgrad + wgrad on the fp32 copy of the same activation."""
+    """3x3 s1 p1 64->64 convolution (no bias), forward, dgrad and wgrad on the tensor cores from split-fp16 planes.
+    The output gradient is split ONCE into planes scaled by a per-tensor power of two (chosen on the device from max|dy|:
+    gradient magnitudes shrink as the sum-reduced loss converges, and unscaled fp16 planes would floor them at 2^-25);
+    dgrad = the forward kernel on those planes with the rotated, channel-swapped filter and 1/s as its epilogue scale;
+    wgrad = the pixel-contraction kernel (wgrad_tc.cu) on the planes of x and dy, 1/s applied when the sum is finalised.
+    COVA_B200_TRAIN_DGRAD / COVA_B200_TRAIN_WGRAD = library select cuDNN (fp32, TF32 off) for comparison runs."""
 
     @staticmethod
     def forward(ctx, x, x_hi, x_lo, weight):
@@ -169,26 +172,71 @@ class _Conv3x3Fn(torch.autograd.Function):
         w_hi, w_lo = ops.pack_conv_weight_f16x2(weight.detach().float())
         one, zero = _ones_zeros(x.device)
         y = ops.conv3x3_bn_act_fwd(pl, w_hi, w_lo, one, zero, res=None, relu=False, out_dtype=F32, engine=ENGINE_TCGEN05)
-        ctx.save_for_backward(x, weight)
+        native_w = os.environ.get("COVA_B200_TRAIN_WGRAD", "native") == "native"
+        ctx.native_w = native_w
+        if native_w:
+            ctx.save_for_backward(x_hi, x_lo, weight)        # the planes the forward consumed are the wgrad operand
+        else:
+            ctx.save_for_backward(x, weight)
+        ctx.x_shape = tuple(x.shape)
         return y.p0
 
     @staticmethod
     def backward(ctx, dy):
-        x, weight = ctx.saved_tensors
         dy = dy.contiguous()
-        if os.environ.get("COVA_B200_TRAIN_DGRAD", "native") != "native" or not ctx.needs_input_grad[0]:
-            gi, gw = _conv_bwd(dy, x.permute(0, 3, 1, 2), weight, [1, 1], [1, 1], ctx.needs_input_grad[0])
-            return (gi.permute(0, 2, 3, 1) if gi is not None else None), None, None, gw
-        # dgrad on the tensor cores: the gradient w.r.t. the input of a 3x3 s1 p1 convolution IS a 3x3 s1 p1 convolution
-        # of the output gradient with the filter rotated by 180 degrees and its channel axes swapped - the same
-        # tcgen05 kernel, same split-fp16 three-product mode (dX to ~1e-6; cuDNN's TF32 dgrad gives ~1e-3)
-        w_rot = weight.detach().float().flip(2, 3).transpose(0, 1).contiguous()
-        w_hi, w_lo = ops.pack_conv_weight_f16x2(w_rot)
-        one, zero = _ones_zeros(dy.device)
-        gi = ops.conv3x3_bn_act_fwd(ops.split_planes(dy, F16X2), w_hi, w_lo, one, zero, res=None, relu=False,
-                                    out_dtype=F32, engine=ENGINE_TCGEN05).p0
-        _, gw = _conv_bwd(dy, x.permute(0, 3, 1, 2), weight, [1, 1], [1, 1], False)      # wgrad: library
+        native_d = os.environ.get("COVA_B200_TRAIN_DGRAD", "native") == "native"
+        if ctx.native_w:
+            x_hi, x_lo, weight = ctx.saved_tensors
+            x = None
+        else:
+            x, weight = ctx.saved_tensors
+        need_dx = ctx.needs_input_grad[0]
+        gi = gw = None
+        dyp = inv = None
+        if ctx.native_w or (native_d and need_dx):
+            dyp, inv = ops.split_planes_scaled(dy, F16X2)
+        if need_dx:
+            if native_d:
+                # dgrad on the tensor cores: the gradient w.r.t. the input of a 3x3 s1 p1 convolution IS a 3x3 s1 p1
+                # convolution of the output gradient with the filter rotated by 180 degrees and its channel axes swapped
+                w_rot = weight.detach().float().flip(2, 3).transpose(0, 1).contiguous()
+                w_hi, w_lo = ops.pack_conv_weight_f16x2(w_rot)
+                _, zero = _ones_zeros(dy.device)
+                gi = ops.conv3x3_bn_act_fwd(dyp, w_hi, w_lo, inv[:64], zero, res=None, relu=False, out_dtype=F32,
+                                            engine=ENGINE_TCGEN05).p0
+            else:
+                xs = x if x is not None else (x_hi.float() + x_lo.float())
+                gi, _ = _conv_bwd(dy, xs.permute(0, 3, 1, 2), weight, [1, 1], [1, 1], True, want_w=False)
+                gi = gi.permute(0, 2, 3, 1)
+        if ctx.native_w:
+            xp = ops.Planes.__new__(ops.Planes)
+            xp.dtype, xp.shape, xp.p0, xp.p1 = F16X2, ctx.x_shape, x_hi, x_lo
+            gw = ops.conv3x3_wgrad(xp, dyp, inv)
+        else:
+            _, gw = _conv_bwd(dy, x.permute(0, 3, 1, 2), weight, [1, 1], [1, 1], False)
         return gi, None, None, gw
+
+
+class _LibConvFn(torch.autograd.Function):
+    """A convolution that has no kernel of this library yet (interim): cuDNN through ATen on NHWC views, forward AND
+    backward pinned to plain fp32 (the backward of an `F.conv2d` would otherwise run under whatever TF32 flag is current
+    when `loss.backward()` executes)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, stride, padding):
+        tf32 = os.environ.get("COVA_B200_TRAIN_TF32", "0") == "1"
+        with torch.backends.cudnn.flags(enabled=True, allow_tf32=tf32):
+            y = F.conv2d(x.permute(0, 3, 1, 2), weight, None, stride, padding)             # channels_last in and out
+        ctx.save_for_backward(x, weight)
+        ctx.meta = (list(stride), list(padding))
+        return y.permute(0, 2, 3, 1)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight = ctx.saved_tensors
+        stride, padding = ctx.meta
+        gi, gw = _conv_bwd(dy.contiguous(), x.permute(0, 3, 1, 2), weight, stride, padding, ctx.needs_input_grad[0])
+        return (gi.permute(0, 2, 3, 1) if gi is not None else None), gw, None, None
 
 
 def tc_forward_convs():
@@ -212,8 +260,7 @@ def _conv(x, planes, conv):
     """x NHWC fp32 (+ its split planes, or None) -> raw conv output NHWC fp32."""
     if planes is not None and _tc_conv_ok(conv):
         return _Conv3x3Fn.apply(x, planes[0], planes[1], conv.weight)
-    y = F.conv2d(x.permute(0, 3, 1, 2), conv.weight, None, conv.stride, conv.padding)     # cuDNN, channels_last
-    return y.permute(0, 2, 3, 1)
+    return _LibConvFn.apply(x, conv.weight, tuple(conv.stride), tuple(conv.padding))
 
 
 def _bn_act(x, bn, res=None, relu=True, planes_for=None):

@@ -56,11 +56,13 @@ int cova_device_info(int* sm_count, int* max_smem_optin);
  *   COVA_KNOB_STEM_CONVERTERS    stem: converter warps per CTA (4 or 8)
  *   COVA_KNOB_CONV_RES_LOAD      3x3 conv residual loads: 0 = ld.global.nc, 1 = ld.global, 2 = L1::no_allocate
  *   COVA_KNOB_ROI_ROWSPLIT       RoIPool: 1 = one CTA per (box, row bin) (default), 0 = one CTA per box
+ *   COVA_KNOB_WGRAD_DRAIN        wgrad kernels: pixel tiles accumulated in TMEM between two drains to the global fp32 sum
  * cova_debug_buffer: a caller-owned device array of uint64 words; kernels that support it (the 3x3 tensor-core conv:
  *   8 words per CTA = cycles the MMA issuer waited for operands / for a free accumulator, the TMA producer for a free
  *   ring slot, epilogue warp 2 for a finished accumulator, CTA total, tiles) add their counters.  NULL disables. */
 enum { COVA_KNOB_CONV_L2_PREFETCH = 0, COVA_KNOB_CONV_RES_PREFETCH = 1, COVA_KNOB_STEM_L2_PREFETCH = 2,
-       COVA_KNOB_STEM_CONVERTERS = 5, COVA_KNOB_CONV_RES_LOAD = 6, COVA_KNOB_ROI_ROWSPLIT = 7, COVA_KNOB_COUNT = 8 };
+       COVA_KNOB_STEM_CONVERTERS = 5, COVA_KNOB_CONV_RES_LOAD = 6, COVA_KNOB_ROI_ROWSPLIT = 7, COVA_KNOB_WGRAD_DRAIN = 8,
+       COVA_KNOB_COUNT = 9 };
 int cova_set_knob(int id, int value);
 int cova_debug_buffer(void* dev_words, int64_t n_words);
 
@@ -274,6 +276,24 @@ int cova_bn_relu_pool_bwd(const float* x, const unsigned char* code, const float
 
 /* fp32 [n] -> split planes hi = r(x), lo = r(x - hi), r = bf16 (COVA_BF16X2) or fp16 (COVA_F16X2) rounding (n % 4 == 0). */
 int cova_split_planes(const float* x, int64_t n, void* hi, void* lo, int planes_dtype, void* stream);
+
+/* The same with a per-tensor power-of-two scale chosen on the device, for GRADIENT maps (their magnitude shrinks as the
+ * sum-reduced loss converges; unscaled split-fp16 planes carry an absolute floor of 2^-25): s = 2^(target_log2 -
+ * floor(log2(max|x|))), hi/lo = split(x * s), so max|x*s| lies in [2^target_log2, 2^(target_log2+1)).  The consumer
+ * undoes it exactly with inv_scale_vec (256 floats, all = 1/s), e.g. as the epilogue `bn_scale` of the dgrad
+ * convolution or the `inv_scale` of the wgrad kernels.  ws: 4 bytes of device scratch (the max|x| bits).
+ * All-zero / non-finite maxima give s = 1.                                                                            */
+int cova_split_planes_scaled(const float* x, int64_t n, void* hi, void* lo, int planes_dtype, int target_log2,
+                             unsigned int* ws, float* inv_scale_vec, void* stream);
+
+/* ---- A9 (`loss.backward()`, `train.py:59`): weight gradient of a 3x3 s1 p1 64->64 convolution (torchvision BasicBlock
+ * conv1/conv2, Bottleneck conv2) on the tensor cores, contraction over the B*H*W pixels of NHWC split planes:
+ *   dw[co][ci][r][s] = inv_scale * sum_{b,h,w} x[b,h+r-1,w+s-1,ci] * dy[b,h,w,co]     (zero padding)
+ * x_hi/x_lo: split planes of the convolution's input (what the forward consumed); dy_hi/dy_lo: split planes of the output
+ * gradient (cova_split_planes_scaled); inv_scale: device float (1/s of the dy planes) or NULL; ws: 9*64*64 floats of
+ * device scratch (zeroed here); dw_oihw: [64,64,3,3] fp32, overwritten.                                              */
+int cova_conv3x3_wgrad(const void* x_hi, const void* x_lo, const void* dy_hi, const void* dy_lo, int B, int H, int W,
+                       int planes_dtype, const float* inv_scale, float* ws, float* dw_oihw, void* stream);
 
 #ifdef __cplusplus
 }

@@ -146,6 +146,43 @@ def test_stem_conv_raw_and_conv3x3_functions_vs_torch():
         assert rel_err(n(x.grad), n(xr.grad)) < 2e-3 and rel_err(n(w.grad), n(wr.grad)) < 2e-3
 
 
+@pytest.mark.parametrize("B,H,W", [(1, 16, 8), (2, 37, 45), (3, 80, 64), (1, 7, 5)])
+@pytest.mark.parametrize("mag", [1.0, 1e-6])
+def test_conv3x3_wgrad_tcgen05_vs_fp64(B, H, W, mag):
+    """Native wgrad (pixel-contraction tcgen05 kernel on MN-major split-fp16 planes, two taps per MMA) against a
+    float64 convolution_backward: single tile, ragged multi-tile shapes (partial tiles on both edges), a map smaller than
+    one tile; output gradients of magnitude 1 and 1e-6 (the scaled planes must keep the small ones)."""
+    from cova_b200 import ops
+    g = torch.Generator().manual_seed(B * 1000 + H * 10 + W)
+    x = torch.randn(B, H, W, 64, generator=g).to(DEV)
+    dy = (torch.randn(B, H, W, 64, generator=g) * mag).to(DEV)
+    xp = ops.split_planes(x, ops.F16X2)
+    dyp, inv = ops.split_planes_scaled(dy, ops.F16X2)
+    assert rel_err(n((dyp.p0.float() + dyp.p1.float()) * inv[0]), n(dy)) < 1e-6       # 22 bits whatever the magnitude
+    gw = ops.conv3x3_wgrad(xp, dyp, inv)
+    w = torch.zeros(64, 64, 3, 3, dtype=torch.float64, device=DEV)
+    _, want, _ = torch.ops.aten.convolution_backward(dy.double().permute(0, 3, 1, 2), x.double().permute(0, 3, 1, 2), w, None,
+                                                     [1, 1], [1, 1], [1, 1], False, [0, 0], 1, [False, True, False])
+    assert rel_err(n(gw), want.cpu().numpy()) < 3e-6
+
+
+def test_conv3x3_dgrad_small_gradients():
+    """dgrad of tiny output gradients (|dy| ~ 1e-6) keeps its relative accuracy (scaled split-fp16 planes)."""
+    from cova_b200.train_backbone import _Conv3x3Fn
+    from cova_b200 import ops
+    g = torch.Generator().manual_seed(77)
+    x = torch.randn(2, 24, 24, 64, generator=g).to(DEV).requires_grad_(True)
+    w = (torch.randn(64, 64, 3, 3, generator=g) * 0.05).to(DEV).requires_grad_(True)
+    pl = ops.split_planes(x.detach(), ops.F16X2)
+    y = _Conv3x3Fn.apply(x, pl.p0, pl.p1, w)
+    dy = (torch.randn(y.shape, generator=g) * 1e-6).to(DEV)
+    y.backward(dy)
+    xr, wr = x.detach().double().requires_grad_(True), w.detach().double().requires_grad_(True)
+    yr = F.conv2d(xr.permute(0, 3, 1, 2), wr, None, 1, 1).permute(0, 2, 3, 1)
+    yr.backward(dy.double())
+    assert rel_err(n(x.grad), xr.grad.cpu().numpy()) < 5e-6 and rel_err(n(w.grad), wr.grad.cpu().numpy()) < 5e-6
+
+
 @pytest.mark.parametrize("shape", [(2, 8, 8, 64), (1, 9, 13, 64), (2, 33, 20, 64), (1, 1, 7, 8)])
 def test_fused_bn_relu_pool_vs_torch(shape):
     """The fused stem tail of the training path (bn1 + ReLU + maxpool without the intermediate map) against
