@@ -48,7 +48,9 @@ struct PwCfg {
   static constexpr int SMEM = W_BYTES + PW_NSTAGE * PW_STAGE + 2 * COUT * 4 + 1024 + 1024;
 };
 
-template <int KB, int COUT, int OUT_DTYPE>
+// HALF: split-fp16 planes and filter (training path: forward and dgrad in the three-product fp16 mode; the filter comes
+// scaled by SPLIT_F16_WSCALE, which the caller folds into bn_scale); fp32 output, no residual.
+template <int KB, int COUT, int OUT_DTYPE, bool HALF = false>
 __global__ void __launch_bounds__(PW_THREADS, 1)
 pw_tc_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ CUtensorMap tm_x_lo,
              const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo, const PwParams p) {
@@ -114,8 +116,9 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant_
     }
   } else if (warp == 1) {
     // ---------------- MMA issuer ----------------
-    constexpr uint32_t idesc_n = ptx::umma_idesc_bf16(128, COUT);
-    constexpr uint32_t idesc_2n = ptx::umma_idesc_bf16(128, COUT == 64 ? 128 : 256);
+    constexpr uint32_t idesc_n = HALF ? ptx::umma_idesc_f16(128, COUT) : ptx::umma_idesc_bf16(128, COUT);
+    constexpr uint32_t idesc_2n = HALF ? ptx::umma_idesc_f16(128, COUT == 64 ? 128 : 256)
+                                       : ptx::umma_idesc_bf16(128, COUT == 64 ? 128 : 256);
     const uint64_t da0 = ptx::umma_desc_sw128(ptx::smem_u32(sm_a), 1024);
     const uint64_t db0 = ptx::umma_desc_sw128(ptx::smem_u32(sm_w), 1024);
     ptx::mbar_wait(&tail.wbar, 0);
@@ -245,11 +248,11 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant_
   }
 }
 
-template <int KB, int COUT, int OUT_DTYPE>
+template <int KB, int COUT, int OUT_DTYPE, bool HALF = false>
 static int launch_pw(const CUtensorMap& xh, const CUtensorMap& xl, const CUtensorMap& wh, const CUtensorMap& wl,
                      const PwParams& p, cudaStream_t st) {
   using Cfg = PwCfg<KB, COUT>;
-  auto kern = pw_tc_kernel<KB, COUT, OUT_DTYPE>;
+  auto kern = pw_tc_kernel<KB, COUT, OUT_DTYPE, HALF>;
   COVA_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
   const int grid = p.n_tiles < sm_count() ? p.n_tiles : sm_count();
   kern<<<grid, PW_THREADS, Cfg::SMEM, st>>>(xh, xl, wh, wl, p);
@@ -259,10 +262,27 @@ static int launch_pw(const CUtensorMap& xh, const CUtensorMap& xl, const CUtenso
 
 }  // namespace cova
 
+static int pw_run(const void* x_hi, const void* x_lo, int64_t M, int Cin, int Cout, const void* w_packed, const float* bn_scale,
+                  const float* bn_shift, const void* res_hi, const void* res_lo, int relu, int out_dtype, void* y0, void* y1,
+                  bool half, void* stream);
+
 extern "C" int cova_conv1x1_bn_act_fwd(const void* x_hi, const void* x_lo, int64_t M, int Cin, int Cout,
                                        const void* w_packed, const float* bn_scale, const float* bn_shift,
                                        const void* res_hi, const void* res_lo, int relu, int out_dtype, void* y0,
                                        void* y1, void* stream) {
+  return pw_run(x_hi, x_lo, M, Cin, Cout, w_packed, bn_scale, bn_shift, res_hi, res_lo, relu, out_dtype, y0, y1, false, stream);
+}
+
+extern "C" int cova_conv1x1_raw_fwd(const void* x_hi, const void* x_lo, int planes_dtype, int64_t M, int Cin, int Cout,
+                                    const void* w_packed, const float* scale, const float* zero_shift, float* y, void* stream) {
+  COVA_REQUIRE(planes_dtype == COVA_F16X2 || planes_dtype == COVA_BF16X2, "cova_conv1x1_raw_fwd: planes are split-fp16 or split-bf16");
+  return pw_run(x_hi, x_lo, M, Cin, Cout, w_packed, scale, zero_shift, nullptr, nullptr, 0, COVA_F32, y, nullptr,
+                planes_dtype == COVA_F16X2, stream);
+}
+
+static int pw_run(const void* x_hi, const void* x_lo, int64_t M, int Cin, int Cout, const void* w_packed, const float* bn_scale,
+                  const float* bn_shift, const void* res_hi, const void* res_lo, int relu, int out_dtype, void* y0, void* y1,
+                  bool half, void* stream) {
   using namespace cova;
   COVA_REQUIRE(x_hi && x_lo && w_packed && bn_scale && bn_shift && y0, "cova_conv1x1_bn_act_fwd: null pointer");
   COVA_REQUIRE((Cin == 64 && (Cout == 64 || Cout == 256)) || (Cin == 256 && Cout == 64),
@@ -290,8 +310,9 @@ extern "C" int cova_conv1x1_bn_act_fwd(const void* x_hi, const void* x_lo, int64
   p.res_hi = (const __nv_bfloat16*)res_hi; p.res_lo = (const __nv_bfloat16*)res_lo;
   p.y0 = y0; p.y1 = y1;
   cudaStream_t st = (cudaStream_t)stream;
-#define GO(KB, CO) (out_dtype == COVA_F32 ? launch_pw<KB, CO, COVA_F32>(tx_hi, tx_lo, tw_hi, tw_lo, p, st) \
-                                          : launch_pw<KB, CO, COVA_BF16X2>(tx_hi, tx_lo, tw_hi, tw_lo, p, st))
+#define GO(KB, CO) (half ? launch_pw<KB, CO, COVA_F32, true>(tx_hi, tx_lo, tw_hi, tw_lo, p, st)          \
+                    : out_dtype == COVA_F32 ? launch_pw<KB, CO, COVA_F32>(tx_hi, tx_lo, tw_hi, tw_lo, p, st) \
+                                            : launch_pw<KB, CO, COVA_BF16X2>(tx_hi, tx_lo, tw_hi, tw_lo, p, st))
   if (Cin == 64 && Cout == 64) return GO(1, 64);
   if (Cin == 64) return GO(1, 256);
   return GO(4, 64);

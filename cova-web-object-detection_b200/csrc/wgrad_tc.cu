@@ -234,6 +234,13 @@ __global__ void wgrad_finalize_kernel(const float* __restrict__ ws, const float*
   dw[i] = ws[((size_t)t * Cin + ci) * Cout + co] * s;
 }
 
+int launch_wgrad_finalize(const float* ws, const float* inv_scale, float mult, int taps, int Cin, int Cout, float* dw,
+                          cudaStream_t st) {
+  wgrad_finalize_kernel<<<ceil_div(taps * Cin * Cout, 256), 256, 0, st>>>(ws, inv_scale, mult, taps, Cin, Cout, dw);
+  COVA_LAUNCH_OK();
+  return COVA_OK;
+}
+
 }  // namespace cova
 
 extern "C" int cova_conv3x3_wgrad(const void* x_hi, const void* x_lo, const void* dy_hi, const void* dy_lo, int B, int H, int W,
@@ -276,7 +283,5 @@ extern "C" int cova_conv3x3_wgrad(const void* x_hi, const void* x_lo, const void
     kern<<<grid, WG_THREADS, WG_SMEM_BYTES, st>>>(tx_hi, tx_lo, td_hi, td_lo, p);
   }
   COVA_LAUNCH_OK();
-  wgrad_finalize_kernel<<<ceil_div(9 * WG_C * WG_C, 256), 256, 0, st>>>(ws, inv_scale, 1.f, 9, WG_C, WG_C, dw_oihw);
-  COVA_LAUNCH_OK();
-  return COVA_OK;
+  return launch_wgrad_finalize(ws, inv_scale, 1.f, 9, WG_C, WG_C, dw_oihw, st);
 }

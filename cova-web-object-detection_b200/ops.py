@@ -427,6 +427,57 @@ def conv3x3_wgrad(x_planes, dy_planes, inv_scale=None):
     return dw
 
 
+def pack_linear_weight_f16x2(w):
+    """fp32 [N,K] -> split-fp16 [2,N,K] planes of 256*w (the 1x1 convolutions of the training path)."""
+    _cuda(w, torch.float32, "w")
+    w = w.contiguous()
+    N, K = w.shape
+    out = torch.empty((2, N, K), dtype=torch.float16, device=w.device)
+    _call("cova_pack_conv_weight_f16x2", w.data_ptr(), N, K, 1, 1, out[0].data_ptr(), out[1].data_ptr(), _stream())
+    return out
+
+
+_W256 = {}
+
+
+def _inv256(device):
+    k = str(device)
+    if k not in _W256:
+        _W256[k] = (torch.full((256,), 1.0 / 256.0, device=device), torch.zeros(256, device=device))
+    return _W256[k]
+
+
+def conv1x1_raw_fwd(x_planes, w_packed, scale=None):
+    """1x1 convolution of split-fp16 NHWC planes [..., Cin] with `pack_linear_weight_f16x2(w [Cout,Cin])` -> raw fp32
+    [..., Cout].  `scale` ([>= Cout] device floats, e.g. the 1/s of scaled gradient planes) multiplies the result."""
+    Cin = x_planes.shape[-1]
+    Cout = w_packed.shape[1]
+    M = 1
+    for d in x_planes.shape[:-1]:
+        M *= d
+    dev = x_planes.p0.device
+    inv, zero = _inv256(dev)
+    sc = inv if scale is None else scale[:256] * (1.0 / 256.0)
+    y = torch.empty(tuple(x_planes.shape[:-1]) + (Cout,), dtype=torch.float32, device=dev)
+    _call("cova_conv1x1_raw_fwd", x_planes.p0.data_ptr(), x_planes.p1.data_ptr(), x_planes.dtype, M, Cin, Cout,
+          w_packed.data_ptr(), sc.data_ptr(), zero.data_ptr(), y.data_ptr(), _stream())
+    return y
+
+
+def conv1x1_wgrad(x_planes, dy_planes, inv_scale=None):
+    """Weight gradient [Cout, Cin, 1, 1] of a 1x1 convolution from the split planes of its input and output gradient."""
+    Cin, Cout = x_planes.shape[-1], dy_planes.shape[-1]
+    M = 1
+    for d in x_planes.shape[:-1]:
+        M *= d
+    dev = x_planes.p0.device
+    ws = torch.empty(Cin * Cout, dtype=torch.float32, device=dev)
+    dw = torch.empty((Cout, Cin, 1, 1), dtype=torch.float32, device=dev)
+    _call("cova_conv1x1_wgrad", x_planes.p0.data_ptr(), x_planes.p1.data_ptr(), dy_planes.p0.data_ptr(), dy_planes.p1.data_ptr(),
+          M, Cin, Cout, x_planes.dtype, _ptr(inv_scale), ws.data_ptr(), dw.data_ptr(), _stream())
+    return dw
+
+
 def stem_conv_raw_fwd(images, w_packed):
     """conv1 alone (training mode): images [B,3,H,W] fp32 / uint8 NCHW -> raw conv output [B,H/2,W/2,64] fp32 NHWC.
     w_packed from pack_stem_weight (bf16: split-bf16 products) or pack_stem_weight_f16x2 (fp16: split-fp16)."""

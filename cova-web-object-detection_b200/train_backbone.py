@@ -217,6 +217,38 @@ class _Conv3x3Fn(torch.autograd.Function):
         return gi, None, None, gw
 
 
+def _planes(dtype, shape, hi, lo):
+    pl = ops.Planes.__new__(ops.Planes)
+    pl.dtype, pl.shape, pl.p0, pl.p1 = dtype, tuple(shape), hi, lo
+    return pl
+
+
+class _Conv1x1Fn(torch.autograd.Function):
+    """ResNet-50 Bottleneck 1x1 convolution (conv1 / conv3 / downsample; 64->64, 64->256, 256->64), forward, dgrad and wgrad
+    on the tensor cores in the split-fp16 three-product mode: forward = persistent GEMM over the pixel rows of the input
+    planes (pw_tc.cu), dgrad = the same kernel with the transposed filter on the scaled planes of the output gradient,
+    wgrad = the pixel-contraction kernel (pw_wgrad_tc.cu)."""
+
+    @staticmethod
+    def forward(ctx, x, x_hi, x_lo, weight):
+        w2 = weight.detach().float().flatten(1)
+        y = ops.conv1x1_raw_fwd(_planes(F16X2, x.shape, x_hi, x_lo), ops.pack_linear_weight_f16x2(w2))
+        ctx.save_for_backward(x_hi, x_lo, weight)
+        ctx.x_shape = tuple(x.shape)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x_hi, x_lo, weight = ctx.saved_tensors
+        dyp, inv = ops.split_planes_scaled(dy.contiguous(), F16X2)
+        gi = None
+        if ctx.needs_input_grad[0]:
+            wt = weight.detach().float().flatten(1).t().contiguous()                  # [Cin, Cout]: dX = dY W
+            gi = ops.conv1x1_raw_fwd(dyp, ops.pack_linear_weight_f16x2(wt), scale=inv)
+        gw = ops.conv1x1_wgrad(_planes(F16X2, ctx.x_shape, x_hi, x_lo), dyp, inv)
+        return gi, None, None, gw
+
+
 class _LibConvFn(torch.autograd.Function):
     """A convolution that has no kernel of this library yet (interim): cuDNN through ATen on NHWC views, forward AND
     backward pinned to plain fp32 (the backward of an `F.conv2d` would otherwise run under whatever TF32 flag is current
@@ -250,22 +282,30 @@ def tc_forward_convs():
 
 
 def _tc_conv_ok(conv):
-    if not tc_forward_convs():
-        return False
-    return (conv.kernel_size == (3, 3) and conv.stride == (1, 1) and conv.padding == (1, 1) and conv.in_channels == 64
-            and conv.out_channels == 64 and conv.bias is None and conv.groups == 1)
+    """3 = the 3x3 64->64 kernel, 1 = the 1x1 kernels (64->64, 64->256, 256->64), 0 = no tensor-core kernel here."""
+    if not tc_forward_convs() or conv.bias is not None or conv.groups != 1 or conv.stride != (1, 1):
+        return 0
+    if conv.kernel_size == (3, 3) and conv.padding == (1, 1) and conv.in_channels == 64 and conv.out_channels == 64:
+        return 3
+    if (conv.kernel_size == (1, 1) and conv.padding == (0, 0) and os.environ.get("COVA_B200_TRAIN_CONV1X1", "native") == "native"
+            and (conv.in_channels, conv.out_channels) in ((64, 64), (64, 256), (256, 64))):
+        return 1
+    return 0
 
 
 def _conv(x, planes, conv):
     """x NHWC fp32 (+ its split planes, or None) -> raw conv output NHWC fp32."""
-    if planes is not None and _tc_conv_ok(conv):
+    kind = _tc_conv_ok(conv) if planes is not None else 0
+    if kind == 3:
         return _Conv3x3Fn.apply(x, planes[0], planes[1], conv.weight)
+    if kind == 1:
+        return _Conv1x1Fn.apply(x, planes[0], planes[1], conv.weight)
     return _LibConvFn.apply(x, conv.weight, tuple(conv.stride), tuple(conv.padding))
 
 
 def _bn_act(x, bn, res=None, relu=True, planes_for=None):
     """Returns (y, planes or None); planes are produced when the consumer `planes_for` is a tensor-core convolution."""
-    want = planes_for is not None and _tc_conv_ok(planes_for)
+    want = planes_for is not None and bool(_tc_conv_ok(planes_for))
     y, hi, lo = _BnActFn.apply(x, bn.weight, bn.bias, res, bn, relu, want)
     return y, ((hi, lo) if want else None)
 
@@ -279,7 +319,7 @@ def feature_map_train(convnet, images):
     else:
         img = images.float().div(255) if images.dtype == torch.uint8 else images.float()
         x = _conv(img.permute(0, 2, 3, 1).contiguous(), None, convnet[0])
-    want = _tc_conv_ok(first)
+    want = bool(_tc_conv_ok(first))
     # COVA_B200_TRAIN_STEM_FUSED=1: bn1 + ReLU + maxpool in one forward / two backward kernels that never write the
     # normalised 640x640 map nor its gradient (3.4 GB less memory at B=16).  Measured no faster than the separate
     # passes (19.2 vs 18.1 ms/step: the backward gather is index-math bound), so it is a memory option, off by default.
@@ -293,12 +333,12 @@ def feature_map_train(convnet, images):
         nxt = blocks[bi + 1].conv1 if bi + 1 < len(blocks) else None
         if hasattr(blk, "conv3"):                                       # Bottleneck (torchvision resnet.py:143-163)
             o, op = _bn_act(_conv(x, xp, blk.conv1), blk.bn1, planes_for=blk.conv2)
-            o, _ = _bn_act(_conv(o, op, blk.conv2), blk.bn2)
+            o, op = _bn_act(_conv(o, op, blk.conv2), blk.bn2, planes_for=blk.conv3)
             if blk.downsample is None:
                 idt = x
             else:
-                idt, _ = _bn_act(_conv(x, None, blk.downsample[0]), blk.downsample[1], relu=False)
-            x, xp = _bn_act(_conv(o, None, blk.conv3), blk.bn3, res=idt, planes_for=nxt)
+                idt, _ = _bn_act(_conv(x, xp, blk.downsample[0]), blk.downsample[1], relu=False)
+            x, xp = _bn_act(_conv(o, op, blk.conv3), blk.bn3, res=idt, planes_for=nxt)
         else:                                                           # BasicBlock (resnet.py:89-105)
             o, op = _bn_act(_conv(x, xp, blk.conv1), blk.bn1, planes_for=blk.conv2)
             x, xp = _bn_act(_conv(o, op, blk.conv2), blk.bn2, res=x, planes_for=nxt)

@@ -295,6 +295,17 @@ int cova_split_planes_scaled(const float* x, int64_t n, void* hi, void* lo, int 
 int cova_conv3x3_wgrad(const void* x_hi, const void* x_lo, const void* dy_hi, const void* dy_lo, int B, int H, int W,
                        int planes_dtype, const float* inv_scale, float* ws, float* dw_oihw, void* stream);
 
+/* ---- A9 / SURVEY D2 (ResNet-50 Bottleneck 1x1 convolutions on the train path, torchvision `Bottleneck.forward`):
+ * cova_conv1x1_raw_fwd: y[m][co] = scale[co] * sum_ci x[m][ci] * w[co][ci] + zero_shift[co]  (fp32 rows, no activation)
+ *   from split planes (COVA_F16X2: w_packed = [2][Cout][Cin] fp16 hi/lo of 256*w, fold 1/256 into `scale`; COVA_BF16X2:
+ *   cova_pack_linear_weight).  Forward (w) and dgrad (the transposed filter on the planes of dy) of a 1x1 convolution.
+ * cova_conv1x1_wgrad: dw[co][ci] = inv_scale * sum_m dy[m][co] * x[m][ci] from the split planes of x and dy
+ *   (ws: Cin*Cout floats of device scratch, zeroed here).  Both built for 64->64, 64->256, 256->64.                   */
+int cova_conv1x1_raw_fwd(const void* x_hi, const void* x_lo, int planes_dtype, int64_t M, int Cin, int Cout,
+                         const void* w_packed, const float* scale, const float* zero_shift, float* y, void* stream);
+int cova_conv1x1_wgrad(const void* x_hi, const void* x_lo, const void* dy_hi, const void* dy_lo, int64_t M, int Cin,
+                       int Cout, int planes_dtype, const float* inv_scale, float* ws, float* dw, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -331,20 +331,39 @@ def config_fixtures():
 @torch.enable_grad()
 def train_fixture_r50():
     """Config 3/4 semantics at a CPU-sized shape: ResNet-50 backbone, train mode (batch-statistics BatchNorm, dropout
-    off), CE(sum), every backbone gradient + a few of the head's (`train.py:45-60`, `main.py:139`)."""
+    off), CE(sum), every backbone gradient + a few of the head's (`train.py:45-60`, `main.py:139`).
+
+    Conditioning: a ReLU / max-pool / RoIPool decision on an element that sits within rounding of a tie flips between
+    two correct implementations (about one element per million per 1e-6 of noise), and when that element carries a large
+    gradient every parameter gradient upstream moves by ~1 % (measured: tools/diag_train_grads.py, profiles/r02_*).
+    The fixture therefore uses the first input seed for which the reference's OWN float32 and float64 gradients agree to
+    2e-5 on every tensor - a sample with no decision inside fp32 noise - and records that deviation."""
     torch.set_num_threads(8)
-    m, _ = build_ref(backbone="resnet50", img=192, drop=0.0)
-    m.train()
-    images, bboxes, add, ci, labels = synth.gen(2, 14, 8, seed=15, img=192, with_labels=True)
-    out = m(images, bboxes, add, ci)
-    loss = torch.nn.CrossEntropyLoss(reduction="sum")(out, labels)
-    loss.backward()
-    grads = {n: p.grad.numpy() for n, p in m.named_parameters()}
+    for seed in range(15, 60):
+        m, _ = build_ref(backbone="resnet50", img=192, drop=0.0)
+        m.train()
+        images, bboxes, add, ci, labels = synth.gen(2, 14, 8, seed=seed, img=192, with_labels=True)
+        out = m(images, bboxes, add, ci)
+        loss = torch.nn.CrossEntropyLoss(reduction="sum")(out, labels)
+        loss.backward()
+        grads = {n: p.grad.numpy() for n, p in m.named_parameters()}
+        bufs = {"buf:" + k: v.numpy().copy() for k, v in m.state_dict().items() if "running" in k}
+        m64, _ = build_ref(backbone="resnet50", img=192, drop=0.0)
+        m64 = m64.double().train()
+        out64 = m64(images.double(), bboxes.double(), add.double(), ci)
+        torch.nn.CrossEntropyLoss(reduction="sum")(out64, labels).backward()
+        dev = max(float(np.abs(grads[n] - p.grad.numpy()).max() / max(np.abs(p.grad.numpy()).max(), 1e-30))
+                  for n, p in m64.named_parameters() if n.startswith("convnet."))
+        print("train_fixture_r50: seed %d, fp32-vs-fp64 reference gradients (backbone, max over tensors) %.2e" % (seed, dev))
+        if dev < 2e-5:
+            break
+    else:
+        raise RuntimeError("no well-conditioned seed found")
     keep = [k for k in grads if k.startswith("convnet.")] + ["gat.W_j.weight", "gat.attention_layer.weight",
                                                              "bbox_feat_encoder.0.weight", "decoder.5.weight"]
     save("g_train_r50_img192", logits=out.detach().numpy(), loss=np.float32(loss.item()), labels=labels.numpy(),
-         **{"grad:" + k: (grads[k] if grads[k].size < 400000 else grads[k][:, ::8].copy()) for k in keep},
-         **{"buf:" + k: v.numpy() for k, v in m.state_dict().items() if "running" in k})
+         seed=np.int64(seed), ref_fp32_vs_fp64=np.float64(dev),
+         **{"grad:" + k: (grads[k] if grads[k].size < 400000 else grads[k][:, ::8].copy()) for k in keep}, **bufs)
     _backbone["name"] = "resnet18"
 
 

@@ -671,7 +671,9 @@ def test_train_step_resnet50_matches_reference_grads():
     m = CoVA((3, 3), 192, 4, True, 384, 32, 0, 0.0, None, pretrained=False, backbone="resnet50")
     m.load_state_dict(synth.make_state_dict(123, backbone="resnet50"), strict=True)
     m = m.to(DEV).train()
-    images, bboxes, add, ci, labels = to_dev(synth.gen(2, 14, 8, seed=15, img=192, with_labels=True))
+    # input seed = the first one for which the reference's own fp32 and fp64 gradients agree (no ReLU / pooling decision
+    # inside rounding noise; oracle/make_golden.py:train_fixture_r50, profiles/r02_train_grad_conditioning_r50.txt)
+    images, bboxes, add, ci, labels = to_dev(synth.gen(2, 14, 8, seed=int(g["seed"]), img=192, with_labels=True))
     out = m(images, bboxes, add, ci)
     loss = torch.nn.CrossEntropyLoss(reduction="sum")(out, labels)
     loss.backward()
@@ -684,8 +686,16 @@ def test_train_step_resnet50_matches_reference_grads():
         if got.shape != want.shape:
             got = got[:, ::8]
         worst[k] = np.abs(got - want).max() / (np.abs(want).max() + 1e-3 * gscale)
-    bad = {k: v for k, v in worst.items() if v > 2e-3}
+    # Two bounds.  (1) Every tensor within 5e-3: a single ReLU / pooling decision on an element within rounding of a tie
+    # still flips between this path and the reference (~1 element per million per 1e-6 of noise; measured with
+    # tools/diag_train_grads.py: one element after block 0's bn2 here), and everything upstream of it moves by up to
+    # ~0.3 %; the reference's own fp32-vs-fp64 gradients move by 0.3-9 % on 16 of 17 input seeds for the same reason
+    # (profiles/r02_train_grad_conditioning_r50.txt).  (2) Everything not upstream of such an element - at least 70 % of
+    # the tensors - agrees to 5e-5, which is what pins the kernels (wgrad / dgrad / BatchNorm backward).
+    bad = {k: v for k, v in worst.items() if v > 5e-3}
     assert not bad, bad
+    tight = [k for k, v in worst.items() if v <= 5e-5]
+    assert len(tight) >= 0.7 * len(worst), sorted(worst.items(), key=lambda kv: -kv[1])[:12]
     sd = m.state_dict()
     for k in [k for k in g if k.startswith("buf:")]:
         assert rel_err(t2n(sd[k[4:]]), g[k]) < 1e-4, k

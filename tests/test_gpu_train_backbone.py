@@ -166,6 +166,29 @@ def test_conv3x3_wgrad_tcgen05_vs_fp64(B, H, W, mag):
     assert rel_err(n(gw), want.cpu().numpy()) < 3e-6
 
 
+@pytest.mark.parametrize("cin,cout", [(64, 64), (64, 256), (256, 64)])
+@pytest.mark.parametrize("shape,mag", [((2, 37, 45), 1.0), ((1, 5, 9), 1e-6), ((3, 64, 96), 1.0)])
+def test_conv1x1_train_function_vs_fp64(cin, cout, shape, mag):
+    """ResNet-50 Bottleneck 1x1 convolutions of the training path (forward, dgrad and wgrad on tcgen05, split-fp16) against
+    float64: ragged pixel counts (partial 128-row forward tiles / 64-row wgrad tiles), tiny gradients."""
+    from cova_b200 import ops
+    from cova_b200.train_backbone import _Conv1x1Fn
+    B, H, W = shape
+    g = torch.Generator().manual_seed(cin + cout + H)
+    x = torch.randn(B, H, W, cin, generator=g).to(DEV).requires_grad_(True)
+    w = (torch.randn(cout, cin, 1, 1, generator=g) / cin ** 0.5).to(DEV).requires_grad_(True)
+    pl = ops.split_planes(x.detach(), ops.F16X2)
+    y = _Conv1x1Fn.apply(x, pl.p0, pl.p1, w)
+    dy = (torch.randn(B, H, W, cout, generator=g) * mag).to(DEV)
+    y.backward(dy)
+    xr, wr = x.detach().double().requires_grad_(True), w.detach().double().requires_grad_(True)
+    yr = F.conv2d(xr.permute(0, 3, 1, 2), wr).permute(0, 2, 3, 1)
+    yr.backward(dy.double())
+    assert rel_err(n(y), yr.detach().cpu().numpy()) < 3e-6
+    assert rel_err(n(x.grad), xr.grad.cpu().numpy()) < 3e-6
+    assert rel_err(n(w.grad), wr.grad.cpu().numpy()) < 3e-6
+
+
 def test_conv3x3_dgrad_small_gradients():
     """dgrad of tiny output gradients (|dy| ~ 1e-6) keeps its relative accuracy (scaled split-fp16 planes)."""
     from cova_b200.train_backbone import _Conv3x3Fn
