@@ -111,6 +111,7 @@ SIGNATURES = {
     "cova_split_planes_scaled": (_I, [_P, _L, _P, _P, _I, _I, _P, _P, _P]),
     "cova_conv3x3_wgrad": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P]),
     "cova_conv1x1_raw_fwd": (_I, [_P, _P, _I, _L, _I, _I, _P, _P, _P, _P, _P]),
+    "cova_stem_wgrad": (_I, [_P, _I, _I, _I, _I, _P, _P, _I, _P, _P, _P, _P]),
     "cova_conv1x1_wgrad": (_I, [_P, _P, _P, _P, _L, _I, _I, _I, _P, _P, _P, _P]),
     "cova_bn_act_bwd": (_I, [_P, _P, _P, _L, _I, _P, _P, _P, _P, _I, _P, _P, _P, _P, _P, _P]),
     "cova_maxpool3x3s2_fwd": (_I, [_P, _I, _I, _I, _I, _P, _P, _P, _P, _I, _P]),

@@ -490,6 +490,23 @@ def stem_conv_raw_fwd(images, w_packed):
     return out
 
 
+def stem_wgrad(images, dy_planes, inv_scale=None):
+    """Weight gradient [64,3,7,7] (OIHW fp32) of conv1 (7x7 s2 p3) from the forward's images ([B,3,H,W] fp32 / uint8 NCHW)
+    and the split planes [B,Hc,Wc,64] of the (scaled) output gradient; inv_scale = device tensor holding 1/s (or None)."""
+    _cuda(images, None, "images")
+    images = images.contiguous()
+    B, C, H, W = images.shape
+    Hc, Wc = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    if C != 3 or tuple(dy_planes.shape) != (B, Hc, Wc, 64) or dy_planes.dtype not in (F16X2, BF16X2):
+        raise RuntimeError("cova_b200: stem_wgrad needs [B,3,H,W] images and [B,H/2,W/2,64] split planes of dy")
+    dev = images.device
+    ws = torch.empty(64 * 224, dtype=torch.float32, device=dev)
+    dw = torch.empty((64, 3, 7, 7), dtype=torch.float32, device=dev)
+    _call("cova_stem_wgrad", images.data_ptr(), U8 if images.dtype == torch.uint8 else F32, B, H, W, dy_planes.p0.data_ptr(),
+          dy_planes.p1.data_ptr(), dy_planes.dtype, _ptr(inv_scale), ws.data_ptr(), dw.data_ptr(), _stream())
+    return dw
+
+
 def bn_train_fwd(x, gamma, beta, running_mean, running_var, momentum, eps, res=None, relu=True, want_planes=False,
                  planes_dtype=BF16X2):
     """BatchNorm2d with batch statistics (+ residual) (+ ReLU) on an NHWC fp32 map x [..., C]; updates the running

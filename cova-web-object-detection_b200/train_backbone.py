@@ -138,7 +138,8 @@ def _conv_bwd(dy_nhwc, x_nchw, weight, stride, padding, need_input, want_w=True)
 
 
 class _StemConvFn(torch.autograd.Function):
-    """conv1 (7x7 s2 p3, no bias) forward on the tensor cores, raw fp32 NHWC output; backward = library wgrad."""
+    """conv1 (7x7 s2 p3, no bias) forward and wgrad on the tensor cores (raw fp32 NHWC output; the image needs no gradient).
+    COVA_B200_TRAIN_WGRAD=library selects cuDNN (fp32, TF32 off) for comparison runs."""
 
     @staticmethod
     def forward(ctx, images, weight):
@@ -149,6 +150,10 @@ class _StemConvFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dy):
         images, weight = ctx.saved_tensors
+        if os.environ.get("COVA_B200_TRAIN_WGRAD", "native") == "native":
+            # pixel-contraction tcgen05 kernel on the raw image rows and the scaled split-fp16 planes of dy (stem_wgrad_tc.cu)
+            dyp, inv = ops.split_planes_scaled(dy.contiguous(), F16X2)
+            return None, ops.stem_wgrad(images, dyp, inv)
         x = images.float().div(255) if images.dtype == torch.uint8 else images
         # the gradient arrives NHWC: give cuDNN the (3-channel, cheap) image in channels_last as well, otherwise it
         # transposes the 1.7 GB gradient map to NCHW first (3.9 ms of a 21 ms step)

@@ -306,6 +306,15 @@ int cova_conv1x1_raw_fwd(const void* x_hi, const void* x_lo, int planes_dtype, i
 int cova_conv1x1_wgrad(const void* x_hi, const void* x_lo, const void* dy_hi, const void* dy_lo, int64_t M, int Cin,
                        int Cout, int planes_dtype, const float* inv_scale, float* ws, float* dw, void* stream);
 
+/* ---- A9: weight gradient of conv1 (7x7 s2 p3, 3->64, `convnet[0]`, /root/reference/models.py:49-51; it needs no dgrad)
+ * on the tensor cores, contraction over the B*Hc*Wc output pixels (stem_wgrad_tc.cu):
+ *   dw[co][c][r][s] = inv_scale * sum_{b,oy,ox} dy[b,oy,ox,co] * x[b,c,2oy+r-3,2ox+s-3]      (zero padding)
+ * images: the forward's input, NCHW fp32 (or uint8, read as v/255); dy_hi/dy_lo: split planes [B,Hc,Wc,64] of the output
+ * gradient (cova_split_planes_scaled); inv_scale: device float (1/s of the dy planes) or NULL; ws: 64*224 floats of device
+ * scratch (zeroed here); dw_oihw: [64,3,7,7] fp32, overwritten.                                                       */
+int cova_stem_wgrad(const void* images, int img_dtype, int B, int H, int W, const void* dy_hi, const void* dy_lo,
+                    int planes_dtype, const float* inv_scale, float* ws, float* dw_oihw, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -166,6 +166,34 @@ def test_conv3x3_wgrad_tcgen05_vs_fp64(B, H, W, mag):
     assert rel_err(n(gw), want.cpu().numpy()) < 3e-6
 
 
+@pytest.mark.parametrize("B,H,W,u8", [(1, 32, 32, False), (2, 74, 90, False), (1, 512, 512, False), (2, 64, 48, True),
+                                      (3, 37, 41, False), (1, 300, 260, True)])
+@pytest.mark.parametrize("mag", [1.0, 1e-6])
+def test_stem_wgrad_tcgen05_vs_fp64(B, H, W, u8, mag):
+    """Native conv1 (7x7 s2 p3) wgrad - pixel-contraction tcgen05 kernel: dY split planes as the MN-major SWIZZLE_128B
+    operand, raw image rows as an MN-major SWIZZLE_NONE sliding-window operand, seven N = 32 MMAs per K-step - against a
+    float64 convolution_backward: one band / several bands and strips, odd sizes (partial strips, W % 4 != 0 -> the generic
+    converter path), uint8 images, output gradients of magnitude 1 and 1e-6."""
+    from cova_b200 import ops
+    g = torch.Generator().manual_seed(B * 1000 + H * 10 + W)
+    if u8:
+        img = torch.randint(0, 256, (B, 3, H, W), generator=g, dtype=torch.uint8).to(DEV)
+        x64 = img.double() / 255
+    else:
+        img = torch.rand(B, 3, H, W, generator=g).to(DEV)
+        x64 = img.double()
+    Hc, Wc = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    dy = (torch.randn(B, Hc, Wc, 64, generator=g) * mag).to(DEV)
+    dyp, inv = ops.split_planes_scaled(dy, ops.F16X2)
+    gw = ops.stem_wgrad(img, dyp, inv)
+    w = torch.zeros(64, 3, 7, 7, dtype=torch.float64, device=DEV)
+    _, want, _ = torch.ops.aten.convolution_backward(dy.double().permute(0, 3, 1, 2), x64, w, None, [2, 2], [3, 3], [1, 1],
+                                                     False, [0, 0], 1, [False, True, False])
+    assert rel_err(n(gw), want.cpu().numpy()) < 3e-6
+    gw2 = ops.stem_wgrad(img, ops.split_planes(dy, ops.BF16X2))                      # unscaled split-bf16 planes of dy
+    assert rel_err(n(gw2), want.cpu().numpy()) < 3e-5
+
+
 @pytest.mark.parametrize("cin,cout", [(64, 64), (64, 256), (256, 64)])
 @pytest.mark.parametrize("shape,mag", [((2, 37, 45), 1.0), ((1, 5, 9), 1e-6), ((3, 64, 96), 1.0)])
 def test_conv1x1_train_function_vs_fp64(cin, cout, shape, mag):
