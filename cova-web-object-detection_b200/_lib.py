@@ -114,6 +114,7 @@ SIGNATURES = {
     "cova_stem_wgrad": (_I, [_P, _I, _I, _I, _I, _P, _P, _I, _P, _P, _P, _P]),
     "cova_conv1x1_wgrad": (_I, [_P, _P, _P, _P, _L, _I, _I, _I, _P, _P, _P, _P]),
     "cova_bn_act_bwd": (_I, [_P, _P, _P, _L, _I, _P, _P, _P, _P, _I, _P, _P, _P, _P, _P, _P]),
+    "cova_bn_act_bwd_planes": (_I, [_P, _P, _P, _L, _I, _P, _P, _P, _P, _I, _P, _P, _P, _P, _I, _I, _P, _P, _P, _P, _P]),
     "cova_maxpool3x3s2_fwd": (_I, [_P, _I, _I, _I, _I, _P, _P, _P, _P, _I, _P]),
     "cova_maxpool3x3s2_bwd": (_I, [_P, _P, _I, _I, _I, _I, _P, _P]),
     "cova_bn_relu_pool_fwd": (_I, [_P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _I, _P]),

@@ -37,19 +37,33 @@ __device__ __forceinline__ void split4(const float4 v, __nv_bfloat16* hi, __nv_b
   *reinterpret_cast<uint2*>(lo + idx) = make_uint2(l01, l23);
 }
 
+// power-of-two scale that brings max|x| into [2^target, 2^(target+1)); 1 for a zero / non-finite maximum
+__device__ __forceinline__ float pow2_scale(unsigned int amax_bits, int target_log2) {
+  const int e = (int)(amax_bits >> 23) & 0xff;
+  if (e == 0 || e == 0xff) return 1.f;
+  int se = 127 + target_log2 - (e - 127);
+  se = min(max(se, 1), 254);
+  return __uint_as_float((unsigned int)se << 23);
+}
+
 // MODE 0: a = sum x, b = sum x^2.   MODE 1: a = sum g, b = sum g * xhat with g = dy * [y > 0] (y recomputed).
+// MODE 2: MODE 1 + wmax[c] = max |x - mean| per channel and wmax[C] = max |g| (bit patterns of non-negative floats): what
+// bounds |dx| before dx exists, so that the apply pass can emit SCALED split-fp16 planes directly (bn_act_bwd_kernel<true>).
 template <int MODE>
 __global__ void __launch_bounds__(BN_THREADS)
 bn_reduce_kernel(const float* __restrict__ x, const float* __restrict__ dy, const float* __restrict__ res, int64_t M,
                  int C, const float* __restrict__ mean, const float* __restrict__ invstd,
-                 const float* __restrict__ gamma, const float* __restrict__ beta, int relu, double* __restrict__ ws) {
+                 const float* __restrict__ gamma, const float* __restrict__ beta, int relu, double* __restrict__ ws,
+                 unsigned int* __restrict__ wmax = nullptr) {
   extern __shared__ __align__(16) float red[];                       // [2][rows][C]
   const int c4n = C >> 2, rows = BN_THREADS / c4n;
   const int cg = threadIdx.x % c4n, prow = threadIdx.x / c4n;
   const int c0 = 4 * cg;
   float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
   float4 mu = a, iv = a, ga = a, be = a;
-  if (MODE == 1) {
+  float4 mx = a;
+  float gm = 0.f;
+  if (MODE >= 1) {
     mu = *reinterpret_cast<const float4*>(mean + c0);
     iv = *reinterpret_cast<const float4*>(invstd + c0);
     ga = *reinterpret_cast<const float4*>(gamma + c0);
@@ -90,6 +104,11 @@ bn_reduce_kernel(const float* __restrict__ x, const float* __restrict__ dy, cons
       }
       a.x += g.x; a.y += g.y; a.z += g.z; a.w += g.w;
       b.x = fmaf(g.x, xh.x, b.x); b.y = fmaf(g.y, xh.y, b.y); b.z = fmaf(g.z, xh.z, b.z); b.w = fmaf(g.w, xh.w, b.w);
+      if (MODE == 2) {
+        mx.x = fmaxf(mx.x, fabsf(xv.x - mu.x)); mx.y = fmaxf(mx.y, fabsf(xv.y - mu.y));
+        mx.z = fmaxf(mx.z, fabsf(xv.z - mu.z)); mx.w = fmaxf(mx.w, fabsf(xv.w - mu.w));
+        gm = fmaxf(gm, fmaxf(fmaxf(fabsf(g.x), fabsf(g.y)), fmaxf(fabsf(g.z), fabsf(g.w))));
+      }
     }
   }
   float* ra = red + (size_t)prow * C + c0;
@@ -102,6 +121,18 @@ bn_reduce_kernel(const float* __restrict__ x, const float* __restrict__ dy, cons
     double s = 0.0;
     for (int r = 0; r < rows; ++r) s += (double)red[(size_t)(which * rows + r) * C + ch];
     atomicAdd(ws + c, s);
+  }
+  if (MODE == 2) {
+    __syncthreads();
+    *reinterpret_cast<float4*>(ra) = mx;
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += BN_THREADS) {
+      float m = 0.f;
+      for (int r = 0; r < rows; ++r) m = fmaxf(m, red[(size_t)r * C + c]);
+      atomicMax(wmax + c, __float_as_uint(m));
+    }
+    gm = warp_max(gm);
+    if ((threadIdx.x & 31) == 0) atomicMax(wmax + C, __float_as_uint(gm));
   }
 }
 
@@ -141,18 +172,27 @@ bn_act_fwd_kernel(const float* __restrict__ x, int64_t n4, int C, const float* _
       o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
     }
     if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-    reinterpret_cast<float4*>(y)[i] = o;
+    if (y != nullptr) reinterpret_cast<float4*>(y)[i] = o;
     if (y_hi != nullptr) split4(o, y_hi, y_lo, (size_t)i * 4, f16);
   }
 }
 
+// PLANES = false: dx as fp32.  PLANES = true: dx as SCALED split planes (hi, lo) of dx * s, s = the power of two that brings
+// an upper bound of max|dx| - computed here from the reduce pass's maxima: |dx| <= |gamma inv| (max|g| + |S1/M| +
+// max|xhat| |S2/M|) - into [2^target, 2^(target+1)); block 0 publishes 256 copies of 1/s for the consuming convolution
+// kernels (dgrad epilogue scale / wgrad finalize).  The fp32 gradient map is never written nor re-read for the split.
+template <bool PLANES>
 __global__ void __launch_bounds__(BN_THREADS)
 bn_act_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ res, int64_t n4,
                   int64_t M, int C, const float* __restrict__ mean, const float* __restrict__ invstd,
                   const float* __restrict__ gamma, const float* __restrict__ beta, int relu,
                   const double* __restrict__ ws, float* __restrict__ dx, float* __restrict__ dres,
-                  float* __restrict__ dgamma, float* __restrict__ dbeta) {
+                  float* __restrict__ dgamma, float* __restrict__ dbeta, const unsigned int* __restrict__ wmax,
+                  __nv_bfloat16* __restrict__ dx_hi, __nv_bfloat16* __restrict__ dx_lo, int f16, int target_log2,
+                  float* __restrict__ inv_vec) {
   extern __shared__ __align__(16) float sums[];                      // [2][C]: S1/M, S2/M
+  __shared__ float s_red[BN_THREADS / 32];
+  __shared__ float s_scale;
   const int c4n = C >> 2;
   if (blockIdx.x == 0) {                               // parameter gradients: dbeta = S1, dgamma = S2
     for (int c = threadIdx.x; c < C; c += BN_THREADS) {
@@ -162,6 +202,26 @@ bn_act_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, con
   }
   for (int c = threadIdx.x; c < 2 * C; c += BN_THREADS) sums[c] = (float)(ws[c] / (double)M);
   __syncthreads();
+  float scale = 1.f;
+  if (PLANES) {
+    const float gmax = __uint_as_float(wmax[C]);
+    float bound = 0.f;
+    for (int c = threadIdx.x; c < C; c += BN_THREADS) {
+      const float iv = invstd[c];
+      bound = fmaxf(bound, fabsf(gamma[c] * iv) * (gmax + fabsf(sums[c]) + __uint_as_float(wmax[c]) * iv * fabsf(sums[C + c])));
+    }
+    bound = warp_max(bound);
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = bound;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float m = 0.f;
+      for (int w = 0; w < BN_THREADS / 32; ++w) m = fmaxf(m, s_red[w]);
+      s_scale = pow2_scale(__float_as_uint(m), target_log2);
+    }
+    __syncthreads();
+    scale = s_scale;
+    if (blockIdx.x == 0) inv_vec[threadIdx.x] = 1.f / scale;
+  }
   for (int64_t i = (int64_t)blockIdx.x * BN_THREADS + threadIdx.x; i < n4; i += (int64_t)gridDim.x * BN_THREADS) {
     const int c0 = 4 * (int)(i % c4n);
     const float4 xv = __ldg(reinterpret_cast<const float4*>(x) + i);
@@ -186,7 +246,12 @@ bn_act_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, con
     o.y = ga.y * iv.y * (g.y - s1.y - xh.y * s2.y);
     o.z = ga.z * iv.z * (g.z - s1.z - xh.z * s2.z);
     o.w = ga.w * iv.w * (g.w - s1.w - xh.w * s2.w);
-    reinterpret_cast<float4*>(dx)[i] = o;
+    if (PLANES) {
+      o.x *= scale; o.y *= scale; o.z *= scale; o.w *= scale;
+      split4(o, dx_hi, dx_lo, (size_t)i * 4, f16);
+    } else {
+      reinterpret_cast<float4*>(dx)[i] = o;
+    }
   }
 }
 
@@ -287,15 +352,6 @@ absmax_kernel(const float* __restrict__ x, int64_t n4, unsigned int* __restrict_
     for (int o = 4; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffu, m, o));
     if (threadIdx.x == 0) atomicMax(out_bits, __float_as_uint(m));
   }
-}
-
-// power-of-two scale that brings max|x| into [2^target, 2^(target+1)); 1 for a zero / non-finite maximum
-__device__ __forceinline__ float pow2_scale(unsigned int amax_bits, int target_log2) {
-  const int e = (int)(amax_bits >> 23) & 0xff;
-  if (e == 0 || e == 0xff) return 1.f;
-  int se = 127 + target_log2 - (e - 127);
-  se = min(max(se, 1), 254);
-  return __uint_as_float((unsigned int)se << 23);
 }
 
 __global__ void __launch_bounds__(256)
@@ -472,7 +528,7 @@ extern "C" int cova_bn_act_fwd(const float* x, int64_t M, int C, const float* me
                                const float* gamma, const float* beta, const float* res, int relu, float* y,
                                void* y_hi, void* y_lo, int planes_dtype, void* stream) {
   COVA_REQUIRE(planes_dtype == COVA_BF16X2 || planes_dtype == COVA_F16X2, "cova_bn_act_fwd: planes are split-bf16 or split-fp16");
-  COVA_REQUIRE(x && y && mean && invstd && gamma && beta && M > 0, "cova_bn_act_fwd: bad arguments");
+  COVA_REQUIRE(x && (y || y_hi) && mean && invstd && gamma && beta && M > 0, "cova_bn_act_fwd: bad arguments");
   COVA_REQUIRE(bn_c_ok(C), "cova_bn_act_fwd: C=%d must be a power of two in [4, 1024]", C);
   COVA_REQUIRE((((uintptr_t)x | (uintptr_t)y | (uintptr_t)res | (uintptr_t)y_hi | (uintptr_t)y_lo) & 15) == 0,
                "cova_bn_act_fwd: 16-byte alignment");
@@ -502,8 +558,36 @@ extern "C" int cova_bn_act_bwd(const float* dy, const float* x, const float* res
   bn_reduce_kernel<1><<<(int)grid, BN_THREADS, smem, st>>>(x, dy, res, M, C, mean, invstd, gamma, beta, relu, ws);
   COVA_LAUNCH_OK();
   const int64_t n4 = M * (C / 4);
-  bn_act_bwd_kernel<<<ew_grid(n4, BN_THREADS), BN_THREADS, 2 * C * sizeof(float), st>>>(dy, x, res, n4, M, C, mean, invstd, gamma, beta, relu, ws,
-                                                                    dx, dres, dgamma, dbeta);
+  bn_act_bwd_kernel<false><<<ew_grid(n4, BN_THREADS), BN_THREADS, 2 * C * sizeof(float), st>>>(
+      dy, x, res, n4, M, C, mean, invstd, gamma, beta, relu, ws, dx, dres, dgamma, dbeta, nullptr, nullptr, nullptr, 0, 0, nullptr);
+  COVA_LAUNCH_OK();
+  return COVA_OK;
+}
+
+extern "C" int cova_bn_act_bwd_planes(const float* dy, const float* x, const float* res, int64_t M, int C, const float* mean,
+                                      const float* invstd, const float* gamma, const float* beta, int relu, double* ws,
+                                      unsigned int* ws_max, void* dx_hi, void* dx_lo, int planes_dtype, int target_log2,
+                                      float* inv_scale_vec, float* dres, float* dgamma, float* dbeta, void* stream) {
+  COVA_REQUIRE(dy && x && dx_hi && dx_lo && ws && ws_max && inv_scale_vec && mean && invstd && gamma && beta && M > 0,
+               "cova_bn_act_bwd_planes: bad arguments");
+  COVA_REQUIRE(bn_c_ok(C), "cova_bn_act_bwd_planes: C=%d must be a power of two in [4, 1024]", C);
+  COVA_REQUIRE(planes_dtype == COVA_BF16X2 || planes_dtype == COVA_F16X2, "cova_bn_act_bwd_planes: planes are split-bf16 or split-fp16");
+  COVA_REQUIRE(target_log2 >= -14 && target_log2 <= 14, "cova_bn_act_bwd_planes: target_log2 out of range");
+  COVA_REQUIRE((((uintptr_t)dy | (uintptr_t)x | (uintptr_t)res | (uintptr_t)dres) & 15) == 0 &&
+                   (((uintptr_t)dx_hi | (uintptr_t)dx_lo) & 7) == 0, "cova_bn_act_bwd_planes: alignment");
+  cudaStream_t st = (cudaStream_t)stream;
+  COVA_CUDA_OK(cudaMemsetAsync(ws, 0, 2 * C * sizeof(double), st));
+  COVA_CUDA_OK(cudaMemsetAsync(ws_max, 0, (C + 1) * sizeof(unsigned int), st));
+  const int rows = BN_THREADS / (C / 4);
+  const size_t smem = (size_t)2 * rows * C * sizeof(float);
+  int64_t grid = (M + rows - 1) / rows;
+  if (grid > (int64_t)sm_count() * 8) grid = (int64_t)sm_count() * 8;
+  bn_reduce_kernel<2><<<(int)grid, BN_THREADS, smem, st>>>(x, dy, res, M, C, mean, invstd, gamma, beta, relu, ws, ws_max);
+  COVA_LAUNCH_OK();
+  const int64_t n4 = M * (C / 4);
+  bn_act_bwd_kernel<true><<<ew_grid(n4, BN_THREADS), BN_THREADS, 2 * C * sizeof(float), st>>>(
+      dy, x, res, n4, M, C, mean, invstd, gamma, beta, relu, ws, nullptr, dres, dgamma, dbeta, ws_max, (__nv_bfloat16*)dx_hi,
+      (__nv_bfloat16*)dx_lo, planes_dtype == COVA_F16X2, target_log2, inv_scale_vec);
   COVA_LAUNCH_OK();
   return COVA_OK;
 }

@@ -508,7 +508,7 @@ def stem_wgrad(images, dy_planes, inv_scale=None):
 
 
 def bn_train_fwd(x, gamma, beta, running_mean, running_var, momentum, eps, res=None, relu=True, want_planes=False,
-                 planes_dtype=BF16X2):
+                 planes_dtype=BF16X2, want_y=True):
     """BatchNorm2d with batch statistics (+ residual) (+ ReLU) on an NHWC fp32 map x [..., C]; updates the running
     statistics in place (pass None to skip).  Returns (y, mean [C], invstd [C], split-bf16 Planes of y or None)."""
     _nhwc(x, "x")
@@ -517,7 +517,7 @@ def bn_train_fwd(x, gamma, beta, running_mean, running_var, momentum, eps, res=N
     dev = x.device
     ws = torch.empty(2 * C, dtype=torch.float64, device=dev)
     mean, inv = torch.empty(C, dtype=torch.float32, device=dev), torch.empty(C, dtype=torch.float32, device=dev)
-    y = torch.empty_like(x)
+    y = torch.empty_like(x) if (want_y or not want_planes) else None
     pl = _planes_like(x, planes_dtype) if want_planes else None
     _call("cova_bn_train_stats", x.data_ptr(), M, C, ws.data_ptr(), _stream())
     _call("cova_bn_train_finalize", ws.data_ptr(), M, C, float(eps), float(momentum), mean.data_ptr(), inv.data_ptr(),
@@ -526,7 +526,7 @@ def bn_train_fwd(x, gamma, beta, running_mean, running_var, momentum, eps, res=N
         global param_generation
         param_generation += 1
     _call("cova_bn_act_fwd", x.data_ptr(), M, C, mean.data_ptr(), inv.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
-          _ptr(None if res is None else _nhwc(res, "res")), int(relu), y.data_ptr(),
+          _ptr(None if res is None else _nhwc(res, "res")), int(relu), _ptr(y),
           pl.p0.data_ptr() if pl else 0, pl.p1.data_ptr() if pl else 0, planes_dtype, _stream())
     return y, mean, inv, pl
 
@@ -545,6 +545,26 @@ def bn_train_bwd(dy, x, mean, invstd, gamma, beta, res=None, relu=True, want_dre
           gamma.data_ptr(), beta.data_ptr(), int(relu), ws.data_ptr(), dx.data_ptr(), _ptr(dres), dg.data_ptr(),
           db.data_ptr(), _stream())
     return dx, dres, dg, db
+
+
+def bn_train_bwd_planes(dy, x, mean, invstd, gamma, beta, res=None, relu=True, want_dres=False, planes_dtype=F16X2,
+                        target_log2=10):
+    """Backward of `bn_train_fwd` with dx emitted as scaled split planes for the tensor-core dgrad / wgrad kernels:
+    returns (Planes of dx * s, inv_scale_vec [256] = 1/s, dres or None, dgamma [C], dbeta [C])."""
+    _nhwc(dy, "dy"); _nhwc(x, "x")
+    C = x.shape[-1]
+    M = x.numel() // C
+    dev = x.device
+    ws = torch.empty(2 * C, dtype=torch.float64, device=dev)
+    wmax = torch.empty(C + 1, dtype=torch.int32, device=dev)
+    pl = _planes_like(x, planes_dtype)
+    inv = torch.empty(256, dtype=torch.float32, device=dev)
+    dres = torch.empty_like(x) if want_dres else None
+    dg, db = torch.empty(C, dtype=torch.float32, device=dev), torch.empty(C, dtype=torch.float32, device=dev)
+    _call("cova_bn_act_bwd_planes", dy.data_ptr(), x.data_ptr(), _ptr(res), M, C, mean.data_ptr(), invstd.data_ptr(),
+          gamma.data_ptr(), beta.data_ptr(), int(relu), ws.data_ptr(), wmax.data_ptr(), pl.p0.data_ptr(), pl.p1.data_ptr(),
+          planes_dtype, int(target_log2), inv.data_ptr(), _ptr(dres), dg.data_ptr(), db.data_ptr(), _stream())
+    return pl, inv, dres, dg, db
 
 
 def maxpool3x3s2_fwd(x, want_planes=False, planes_dtype=BF16X2):

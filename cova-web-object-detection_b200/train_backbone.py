@@ -315,7 +315,7 @@ def _bn_act(x, bn, res=None, relu=True, planes_for=None):
     return y, ((hi, lo) if want else None)
 
 
-def feature_map_train(convnet, images):
+def feature_map_train_modular(convnet, images):
     """`convnet(images)` (`models.py:125`) in training mode -> NHWC fp32 feature map [B, H/4, W/4, C]."""
     blocks = list(convnet[4])
     first = blocks[0].conv1
@@ -348,3 +348,177 @@ def feature_map_train(convnet, images):
             o, op = _bn_act(_conv(x, xp, blk.conv1), blk.bn1, planes_for=blk.conv2)
             x, xp = _bn_act(_conv(o, op, blk.conv2), blk.bn2, res=x, planes_for=nxt)
     return x
+
+
+# ----------------------------------------------------------------------------- whole-backbone autograd function
+class _Unit:
+    """Saved state of one conv -> BatchNorm(batch statistics) (+ residual) (+ ReLU) unit of the backbone."""
+    __slots__ = ("kind", "xin", "weight", "bn", "raw", "mean", "inv", "res", "relu", "has_res", "y", "planes", "x_shape")
+
+
+def _unit_fwd(kind, xin, conv, bn, res=None, relu=True, want_y=True, want_planes=False):
+    """kind "stem": xin = images; 3 / 1: xin = split-fp16 Planes of the input map.  Returns the unit (y fp32 and / or the
+    split planes of y for the tensor-core convolution that follows)."""
+    u = _Unit()
+    u.kind, u.xin, u.weight, u.bn, u.relu, u.has_res = kind, xin, conv.weight, bn, relu, res is not None
+    w = conv.weight.detach().float()
+    if kind == "stem":
+        u.raw = ops.stem_conv_raw_fwd(xin, ops.pack_stem_weight_f16x2(w.contiguous()))
+    elif kind == 3:
+        w_hi, w_lo = ops.pack_conv_weight_f16x2(w)
+        one, zero = _ones_zeros(w.device)
+        u.raw = ops.conv3x3_bn_act_fwd(xin, w_hi, w_lo, one, zero, res=None, relu=False, out_dtype=F32, engine=ENGINE_TCGEN05).p0
+    else:
+        u.raw = ops.conv1x1_raw_fwd(xin, ops.pack_linear_weight_f16x2(w.flatten(1)))
+    track = bn.track_running_stats and bn.running_mean is not None
+    mom = _momentum(bn, track)
+    u.res = res if (relu and res is not None) else None
+    u.y, u.mean, u.inv, u.planes = ops.bn_train_fwd(u.raw, bn.weight.detach(), bn.bias.detach(), bn.running_mean if track else None,
+                                                    bn.running_var if track else None, mom, bn.eps, res=res, relu=relu,
+                                                    want_planes=want_planes, planes_dtype=F16X2, want_y=want_y)
+    if track and bn.num_batches_tracked is not None:
+        bn.num_batches_tracked += 1
+    return u
+
+
+def _unit_bwd(u, dy, need_dx=True):
+    """dy = gradient of the unit's output (fp32 NHWC).  BatchNorm backward emits the gradient of the raw convolution output
+    directly as scaled split-fp16 planes (no fp32 map, no max / split passes); dgrad and wgrad consume them on the tensor
+    cores.  Returns (dx fp32 or None, dw, dgamma, dbeta, dres or None)."""
+    bn = u.bn
+    dyp, inv, dres, dg, db = ops.bn_train_bwd_planes(dy, u.raw, u.mean, u.inv, bn.weight.detach(), bn.bias.detach(), res=u.res,
+                                                     relu=u.relu, want_dres=u.has_res, planes_dtype=F16X2)
+    w = u.weight.detach().float()
+    dx = None
+    if u.kind == "stem":
+        dw = ops.stem_wgrad(u.xin, dyp, inv)
+    elif u.kind == 3:
+        if need_dx:
+            w_hi, w_lo = ops.pack_conv_weight_f16x2(w.flip(2, 3).transpose(0, 1).contiguous())
+            _, zero = _ones_zeros(dy.device)
+            dx = ops.conv3x3_bn_act_fwd(dyp, w_hi, w_lo, inv[:64], zero, res=None, relu=False, out_dtype=F32,
+                                        engine=ENGINE_TCGEN05).p0
+        dw = ops.conv3x3_wgrad(u.xin, dyp, inv)
+    else:
+        if need_dx:
+            dx = ops.conv1x1_raw_fwd(dyp, ops.pack_linear_weight_f16x2(w.flatten(1).t().contiguous()), scale=inv)
+        dw = ops.conv1x1_wgrad(u.xin, dyp, inv)
+    u.raw = u.res = u.xin = u.mean = u.inv = None        # release the unit's saved maps as the backward walks up the network
+    return dx, dw, dg, db, dres
+
+
+class _BackboneFn(torch.autograd.Function):
+    """`convnet(images)` in training mode as ONE autograd node: every convolution (forward, dgrad, wgrad) on the tensor
+    cores in the split-fp16 three-product mode, BatchNorm(batch statistics) + residual + ReLU and the maxpool as the native
+    NHWC passes, maps handed from kernel to kernel in the format the consumer reads (split planes for a convolution, fp32
+    for a residual / the pooled map / RoIPool).  Parameters arrive as (conv.weight, bn.weight, bn.bias) per unit, in unit order."""
+
+    @staticmethod
+    def forward(ctx, images, convnet, *params):
+        blocks = list(convnet[4])
+        units = []
+        stem = _unit_fwd("stem", images, convnet[0], convnet[1], relu=True, want_y=True)
+        units.append(stem)
+        x, code, xp = ops.maxpool3x3s2_fwd(stem.y, want_planes=True, planes_dtype=F16X2)
+        ctx.pool = (code, tuple(stem.y.shape))
+        stem.y = None                                            # the 640^2 map is not needed again (ReLU mask comes from raw)
+        plan = []
+        for bi, blk in enumerate(blocks):
+            last = bi + 1 == len(blocks)
+            if hasattr(blk, "conv3"):                            # Bottleneck (torchvision resnet.py:143-163)
+                u1 = _unit_fwd(1, xp, blk.conv1, blk.bn1, want_y=False, want_planes=True)
+                u2 = _unit_fwd(3, u1.planes, blk.conv2, blk.bn2, want_y=False, want_planes=True)
+                ud = None
+                if blk.downsample is not None:
+                    ud = _unit_fwd(1, xp, blk.downsample[0], blk.downsample[1], relu=False, want_y=True)
+                u3 = _unit_fwd(1, u2.planes, blk.conv3, blk.bn3, res=(x if ud is None else ud.y), want_y=True, want_planes=not last)
+                group = [u1, u2, u3] + ([ud] if ud is not None else [])
+                x, xp = u3.y, u3.planes
+            else:                                                # BasicBlock (resnet.py:89-105)
+                u1 = _unit_fwd(3, xp, blk.conv1, blk.bn1, want_y=False, want_planes=True)
+                u2 = _unit_fwd(3, u1.planes, blk.conv2, blk.bn2, res=x, want_y=True, want_planes=not last)
+                group = [u1, u2]
+                x, xp = u2.y, u2.planes
+            plan.append((len(units), len(group), hasattr(blk, "conv3"), blk.downsample is not None))
+            units.extend(group)
+        for u in units:            # outputs live on only where a consumer holds them: `xin` (planes), `res` (fp32 residual), the caller (x)
+            u.y = u.planes = None
+        ctx.units, ctx.plan = units, plan
+        return x
+
+    @staticmethod
+    def backward(ctx, g):
+        units, plan = ctx.units, ctx.plan
+        grads = [None] * len(units)
+        g = g.contiguous()
+        for start, n, bottleneck, has_ds in reversed(plan):
+            us = units[start:start + n]
+            if bottleneck:
+                d3, *p3, dres = _unit_bwd(us[2], g)
+                d2, *p2, _ = _unit_bwd(us[1], d3)
+                d1, *p1, _ = _unit_bwd(us[0], d2)
+                grads[start + 2], grads[start + 1], grads[start] = p3, p2, p1
+                if has_ds:
+                    dd, *pd, _ = _unit_bwd(us[3], dres)
+                    grads[start + 3] = pd
+                    g = d1.add_(dd)
+                else:
+                    g = d1.add_(dres)
+            else:
+                d2, *p2, dres = _unit_bwd(us[1], g)
+                d1, *p1, _ = _unit_bwd(us[0], d2)
+                grads[start + 1], grads[start] = p2, p1
+                g = d1.add_(dres)
+        code, shape = ctx.pool
+        g = ops.maxpool3x3s2_bwd(code, g, shape)
+        _, *p0, _ = _unit_bwd(units[0], g, need_dx=False)
+        grads[0] = p0
+        flat = []
+        for dw, dg, db in grads:
+            flat += [dw, dg, db]
+        ctx.units = ctx.plan = ctx.pool = None
+        return (None, None) + tuple(gr if need else None for gr, need in zip(flat, ctx.needs_input_grad[2:]))
+
+
+def _fused_ok(convnet):
+    if not tc_forward_convs() or os.environ.get("COVA_B200_TRAIN_BACKBONE", "native") == "modular":
+        return False
+    if os.environ.get("COVA_B200_TRAIN_WGRAD", "native") != "native" or os.environ.get("COVA_B200_TRAIN_DGRAD", "native") != "native":
+        return False
+    c0 = convnet[0]
+    if not (c0.kernel_size == (7, 7) and c0.stride == (2, 2) and c0.padding == (3, 3) and c0.bias is None
+            and c0.in_channels == 3 and c0.out_channels == 64):
+        return False
+    for blk in convnet[4]:
+        convs = [(blk.conv1, 1 if hasattr(blk, "conv3") else 3), (blk.conv2, 3)]
+        if hasattr(blk, "conv3"):
+            convs.append((blk.conv3, 1))
+        if blk.downsample is not None:
+            convs.append((blk.downsample[0], 1))
+        if any(_tc_conv_ok(c) != k for c, k in convs):
+            return False
+    return True
+
+
+def _unit_params(convnet):
+    mods = [(convnet[0], convnet[1])]
+    for blk in convnet[4]:
+        mods += [(blk.conv1, blk.bn1), (blk.conv2, blk.bn2)]
+        if hasattr(blk, "conv3"):
+            mods.append((blk.conv3, blk.bn3))
+        if blk.downsample is not None:
+            mods.append((blk.downsample[0], blk.downsample[1]))
+    out = []
+    for conv, bn in mods:
+        out += [conv.weight, bn.weight, bn.bias]
+    return out
+
+
+def feature_map_train(convnet, images):
+    """`convnet(images)` (`models.py:125`) in training mode -> NHWC fp32 feature map [B, H/4, W/4, C].  Default: the
+    whole-backbone autograd node (`_BackboneFn`); COVA_B200_TRAIN_BACKBONE=modular (or any library-convolution switch)
+    selects the per-operator autograd functions above."""
+    if _fused_ok(convnet) and all(p is not None for p in _unit_params(convnet)):
+        img = images if images.dtype == torch.uint8 else images.float()
+        return _BackboneFn.apply(img, convnet, *_unit_params(convnet))
+    return feature_map_train_modular(convnet, images)

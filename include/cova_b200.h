@@ -249,10 +249,19 @@ int cova_bn_act_fwd(const float* x, int64_t M, int C, const float* mean, const f
                     const float* beta, const float* res, int relu, float* y, void* y_hi, void* y_lo, int planes_dtype,
                     void* stream);
 /*   y_hi / y_lo (optional, both or neither): the same result as split planes in `planes_dtype` (COVA_BF16X2 or
- *   COVA_F16X2) - the operand format of the tensor-core convolution that consumes it.                              */
+ *   COVA_F16X2) - the operand format of the tensor-core convolution that consumes it; y may be NULL when only the
+ *   planes are wanted (a map whose single consumer is a tensor-core convolution).                                   */
 int cova_bn_act_bwd(const float* dy, const float* x, const float* res, int64_t M, int C, const float* mean,
                     const float* invstd, const float* gamma, const float* beta, int relu, double* ws, float* dx,
                     float* dres, float* dgamma, float* dbeta, void* stream);
+/* The same backward with dx emitted directly as SCALED split planes (hi, lo) of dx * s for the tensor-core dgrad / wgrad
+ * kernels that consume it (no fp32 gradient map, no separate max / split passes): s = the power of two that brings an upper
+ * bound of max|dx| (from per-channel max|x - mean| and max|g| gathered in the reduction pass) into
+ * [2^target_log2, 2^(target_log2+1)); inv_scale_vec receives 256 copies of 1/s.  ws: 2*C doubles, ws_max: C+1 words.  */
+int cova_bn_act_bwd_planes(const float* dy, const float* x, const float* res, int64_t M, int C, const float* mean,
+                           const float* invstd, const float* gamma, const float* beta, int relu, double* ws,
+                           unsigned int* ws_max, void* dx_hi, void* dx_lo, int planes_dtype, int target_log2,
+                           float* inv_scale_vec, float* dres, float* dgamma, float* dbeta, void* stream);
 
 /* ---- A2 / A9: the stem's `nn.MaxPool2d(3, 2, 1)` on NHWC fp32 maps, forward and backward (the gradient of an output
  * goes to the FIRST maximum of its window in row-major scan order, as torch's max_pool2d_with_indices).
