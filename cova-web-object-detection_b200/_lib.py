@@ -19,7 +19,7 @@ NVCC_FLAGS = [
 ]
 
 F32, BF16, BF16X2, U8, F16, F16X2 = 0, 1, 2, 3, 4, 5
-ENGINE_SIMT, ENGINE_TCGEN05 = 0, 1
+ENGINE_SIMT, ENGINE_TCGEN05, ENGINE_TCGEN05_F16X2 = 0, 1, 2
 
 
 def sources():

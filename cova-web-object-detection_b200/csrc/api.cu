@@ -17,7 +17,7 @@ int linear_simt(const float* x, int64_t ld_x, int M, int K, const float* w, int 
 bool linear_tc_supported(const float* x, int64_t ld_x, int K);
 int linear_tc(const float* x, int64_t ld_x, int M, int K, const void* w_packed, int N, const float* bias,
               const float* scale, const float* shift, const float* res, int64_t ld_res, int relu, int out_dtype,
-              void* y0, void* y1, int64_t ld_y, cudaStream_t st);
+              void* y0, void* y1, int64_t ld_y, cudaStream_t st, bool half);
 }  // namespace cova
 
 using namespace cova;
@@ -76,16 +76,17 @@ extern "C" int cova_linear_fwd(const float* x, int64_t ld_x, int M, int K, const
   if (M == 0) return COVA_OK;
   COVA_REQUIRE(x && w && y0 && ld_x >= K && ld_y >= N, "cova_linear_fwd: bad arguments");
   COVA_REQUIRE((scale == nullptr) == (shift == nullptr), "cova_linear_fwd: scale/shift must come together");
-  COVA_REQUIRE(engine == COVA_ENGINE_SIMT || engine == COVA_ENGINE_TCGEN05, "cova_linear_fwd: bad engine");
+  COVA_REQUIRE(engine == COVA_ENGINE_SIMT || engine == COVA_ENGINE_TCGEN05 || engine == COVA_ENGINE_TCGEN05_F16X2,
+               "cova_linear_fwd: bad engine");
   COVA_REQUIRE(!res || ld_res >= N, "cova_linear_fwd: ld_res too small");
   COVA_REQUIRE(out_dtype == COVA_F32 || (out_dtype == COVA_BF16X2 && y1 && engine == COVA_ENGINE_TCGEN05),
                "cova_linear_fwd: output is fp32, or split-bf16 planes (y0 = hi, y1 = lo) on the tcgen05 engine");
-  if (engine == COVA_ENGINE_TCGEN05) {
+  if (engine != COVA_ENGINE_SIMT) {
     COVA_REQUIRE(linear_tc_supported(x, ld_x, K),
                  "cova_linear_fwd: the tcgen05 engine needs K %% 8 == 0, ld_x %% 4 == 0 and a 16-byte aligned x "
                  "(K=%d, ld_x=%lld); use the SIMT engine for this shape", K, (long long)ld_x);
     return linear_tc(x, ld_x, M, K, w, N, bias, scale, shift, res, ld_res, relu, out_dtype, y0, y1, ld_y,
-                     (cudaStream_t)stream);
+                     (cudaStream_t)stream, engine == COVA_ENGINE_TCGEN05_F16X2);
   }
   return linear_simt(x, ld_x, M, K, (const float*)w, N, bias, scale, shift, res, ld_res, relu, (float*)y0, ld_y,
                      (cudaStream_t)stream);

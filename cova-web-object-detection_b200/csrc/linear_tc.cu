@@ -45,6 +45,10 @@ struct LinearTcParams {
   int64_t ldy;
 };
 
+// HALF: split-fp16 operands (hi = f16(x), lo = f16(x - hi): 22 significand bits; W packed x256 by
+// cova_pack_conv_weight_f16x2, undone in the epilogue) instead of split-bf16 (16 bits) - the training forward, whose
+// gradients are discontinuous in the forward precision at the 1e-5 level.
+template <bool HALF>
 __global__ void __launch_bounds__(LT_THREADS, 1)
 linear_tc_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo,
                  const LinearTcParams p) {
@@ -92,7 +96,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_const
     }
   } else if (warp == 1) {
     // ---------------- MMA issuer ----------------
-    constexpr uint32_t idesc = ptx::umma_idesc_bf16(LT_BM, LT_BN);
+    constexpr uint32_t idesc = HALF ? ptx::umma_idesc_f16(LT_BM, LT_BN) : ptx::umma_idesc_bf16(LT_BM, LT_BN);
     const uint64_t d0 = ptx::umma_desc_sw128(ptx::smem_u32(smem), 1024);
     const uint32_t hi32 = (uint32_t)(d0 >> 32), lo0 = (uint32_t)d0;
     uint32_t stage = 0, phase = 0;
@@ -141,8 +145,13 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_const
       for (int j = 0; j < 16; ++j) {
         const int r = r0 + 8 * j;
         uint32_t h01, l01, h23, l23;
-        split_bf16x2(v[j].x, v[j].y, h01, l01);
-        split_bf16x2(v[j].z, v[j].w, h23, l23);
+        if (HALF) {
+          split_f16x2(v[j].x, v[j].y, h01, l01);
+          split_f16x2(v[j].z, v[j].w, h23, l23);
+        } else {
+          split_bf16x2(v[j].x, v[j].y, h01, l01);
+          split_bf16x2(v[j].z, v[j].w, h23, l23);
+        }
         const uint32_t off = r * 128 + (((c >> 1) ^ (r & 7)) << 4) + (c & 1) * 8;   // 128-B swizzle
         *reinterpret_cast<uint2*>(sa + off) = make_uint2(h01, h23);
         *reinterpret_cast<uint2*>(sa + LT_A_PLANE + off) = make_uint2(l01, l23);
@@ -181,6 +190,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_const
         for (int j = 0; j < 16; ++j) {
           const int n = nb + j;
           float x = __uint_as_float(raw[j]);
+          if (HALF) x *= 1.f / SPLIT_F16_WSCALE;
           if (n < p.N) {
             if (p.bias) x += p.bias[n];
             if (p.scale) x = fmaf(x, p.scale[n], p.shift[n]);
@@ -248,7 +258,7 @@ bool linear_tc_supported(const float* x, int64_t ld_x, int K) {
 
 int linear_tc(const float* x, int64_t ld_x, int M, int K, const void* w_packed, int N, const float* bias,
               const float* scale, const float* shift, const float* res, int64_t ld_res, int relu, int out_dtype,
-              void* y0, void* y1, int64_t ld_y, cudaStream_t st) {
+              void* y0, void* y1, int64_t ld_y, cudaStream_t st, bool half) {
   CUtensorMap tw_hi, tw_lo;
   const uint64_t wd[2] = {(uint64_t)K, (uint64_t)N};
   const uint64_t ws[1] = {(uint64_t)K * 2};
@@ -258,9 +268,14 @@ int linear_tc(const float* x, int64_t ld_x, int M, int K, const void* w_packed, 
   if ((rc = make_tmap_bf16(&tw_hi, wp, 2, wd, ws, wb))) return rc;
   if ((rc = make_tmap_bf16(&tw_lo, wp + (size_t)N * K, 2, wd, ws, wb))) return rc;
   LinearTcParams p{x, ld_x, M, K, N, bias, scale, shift, res, ld_res, relu, out_dtype, y0, y1, ld_y};
-  COVA_CUDA_OK(cudaFuncSetAttribute(linear_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LT_SMEM));
   dim3 grid(ceil_div(N, LT_BN), ceil_div(M, LT_BM));
-  linear_tc_kernel<<<grid, LT_THREADS, LT_SMEM, st>>>(tw_hi, tw_lo, p);
+  if (half) {
+    COVA_CUDA_OK(cudaFuncSetAttribute(linear_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, LT_SMEM));
+    linear_tc_kernel<true><<<grid, LT_THREADS, LT_SMEM, st>>>(tw_hi, tw_lo, p);
+  } else {
+    COVA_CUDA_OK(cudaFuncSetAttribute(linear_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, LT_SMEM));
+    linear_tc_kernel<false><<<grid, LT_THREADS, LT_SMEM, st>>>(tw_hi, tw_lo, p);
+  }
   COVA_LAUNCH_OK();
   return COVA_OK;
 }

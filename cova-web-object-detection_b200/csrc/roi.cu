@@ -24,15 +24,12 @@ struct RoiGeom {
 };
 
 // box edge quantisation of torchvision's roi_pool kernel: C round() of the fp32 product
-// A batch index outside [0, B) (never produced by the loader, `datasets.py:170-177`) selects no page: the box is moved
-// fully outside the map, so every bin is empty -> output 0, arg-max -1, no gradient - instead of an out-of-bounds read.
-__device__ __forceinline__ RoiGeom roi_geom(const float* __restrict__ roi, float scale, int PH, int PW, int B) {
+__device__ __forceinline__ RoiGeom roi_geom(const float* __restrict__ roi, float scale, int PH, int PW) {
   RoiGeom g;
   g.b = (int)roi[0];
   g.sw = (int)roundf(roi[1] * scale);
   g.sh = (int)roundf(roi[2] * scale);
-  int ew = (int)roundf(roi[3] * scale), eh = (int)roundf(roi[4] * scale);
-  if (g.b < 0 || g.b >= B) { g.b = 0; g.sw = g.sh = ew = eh = 1 << 28; }
+  const int ew = (int)roundf(roi[3] * scale), eh = (int)roundf(roi[4] * scale);
   g.rw = max(ew - g.sw + 1, 1);
   g.rh = max(eh - g.sh + 1, 1);
   g.bin_h = (float)g.rh / (float)PH;
@@ -54,8 +51,8 @@ __device__ __forceinline__ int bin_hi(int p, float bin, int start, int limit) {
 constexpr int ROI_SPLIT_WARPS = 4;
 template <bool WITH_ARGMAX, bool ROWSPLIT>
 __global__ void __launch_bounds__(ROI_THREADS)
-roi_pool_kernel(const float* __restrict__ fm, int B, int Hf, int Wf, int C, const float* __restrict__ rois, int PH,
-                int PW, float scale, float* __restrict__ out, int64_t ld_out, int32_t* __restrict__ argmax) {
+roi_pool_kernel(const float* __restrict__ fm, int Hf, int Wf, int C, const float* __restrict__ rois, int PH,
+                int PW, float scale, float* __restrict__ out, int64_t ld_out, int32_t* __restrict__ argmax, int B) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int NW = ROWSPLIT ? ROI_SPLIT_WARPS : ROI_WARPS;
   const int nbins = PH * PW;                       // bins of the box
@@ -66,7 +63,7 @@ roi_pool_kernel(const float* __restrict__ fm, int B, int Hf, int Wf, int C, cons
   const int ph_own = ROWSPLIT ? blockIdx.x % PH : 0;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int half = lane >> 4, c4 = (lane & 15) * 4;
-  const RoiGeom g = roi_geom(rois + (size_t)t * 5, scale, PH, PW, B);
+  const RoiGeom g = roi_geom(rois + (size_t)t * 5, scale, PH, PW);
 
   for (int i = threadIdx.x; i < NW * abins * ROI_CB; i += NW * 32) {
     acc[i] = -FLT_MAX;
@@ -76,7 +73,8 @@ roi_pool_kernel(const float* __restrict__ fm, int B, int Hf, int Wf, int C, cons
 
   const int h_lo = bin_lo(ROWSPLIT ? ph_own : 0, g.bin_h, g.sh, Hf);
   const int h_hi = bin_hi(ROWSPLIT ? ph_own : PH - 1, g.bin_h, g.sh, Hf);
-  const float* base = fm + (size_t)g.b * Hf * Wf * C + cb;
+  const int bq = min(max(g.b, 0), B - 1);
+  const float* base = fm + (size_t)bq * Hf * Wf * C + cb;
   float* wacc = acc + warp * abins * ROI_CB;
   int* wacc_i = acc_i + warp * abins * ROI_CB;
 
@@ -166,6 +164,18 @@ roi_pool_kernel(const float* __restrict__ fm, int B, int Hf, int Wf, int C, cons
     if (empty) { m = 0.f; mi = -1; }
     out[(size_t)t * ld_out + (size_t)(cb + c) * nbins + bin] = m;
     if (WITH_ARGMAX) argmax[((size_t)t * C + cb + c) * nbins + bin] = mi;
+  }
+  // A batch index outside [0, B) (never produced by the loader, `datasets.py:170-177`) selects no page: the box was pooled
+  // from a clamped (in-bounds) page above; its outputs are overwritten here with 0 / arg-max -1 (no gradient) by the same
+  // threads that wrote them.  Kept OUT of the loop above on purpose: folding the test into `empty` cost the row-split
+  // kernel 30 % (136 -> 178 us at config 2, tools/bench_kernels.py) through the compiler's register allocation.
+  if ((unsigned)(int)__ldg(rois + (size_t)t * 5) >= (unsigned)B) {
+    for (int o = threadIdx.x; o < ROI_CB * abins; o += NW * 32) {
+      const int c = o / abins, abin = o % abins;
+      const int bin = ROWSPLIT ? ph_own * PW + abin : abin;
+      out[(size_t)t * ld_out + (size_t)(cb + c) * nbins + bin] = 0.f;
+      if (WITH_ARGMAX) argmax[((size_t)t * C + cb + c) * nbins + bin] = -1;
+    }
   }
 }
 
@@ -399,7 +409,7 @@ extern "C" int cova_roi_fwd(const float* fm, int B, int Hf, int Wf, int C, const
 #define ROI_GO(AM, RS)                                                                                                   \
   do {                                                                                                                   \
     COVA_CUDA_OK(cudaFuncSetAttribute(roi_pool_kernel<AM, RS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    roi_pool_kernel<AM, RS><<<grid, threads, smem, st>>>(fm, B, Hf, Wf, C, rois, PH, PW, spatial_scale, out, ld_out, argmax); \
+    roi_pool_kernel<AM, RS><<<grid, threads, smem, st>>>(fm, Hf, Wf, C, rois, PH, PW, spatial_scale, out, ld_out, argmax, B); \
   } while (0)
     if (argmax) { if (rowsplit) ROI_GO(true, true); else ROI_GO(true, false); }
     else        { if (rowsplit) ROI_GO(false, true); else ROI_GO(false, false); }

@@ -177,6 +177,59 @@ class _GatGatherFn(torch.autograd.Function):
         return d_ext, None, None, None
 
 
+class _LinearFn(torch.autograd.Function):
+    """`nn.Linear` on the autograd path (`models.py:65-70,82-90,160-164` under `train.py:45-60`) without cuBLAS: forward,
+    dX = dY W and dW = dY^T X all run the library's own GEMM kernel (`cova_linear_fwd`: tcgen05 split-bf16 three-product,
+    or the exact CUDA-core engine when K % 8 != 0 - the 5-feature bbox encoder, the 4-class output layer)."""
+
+    @staticmethod
+    def _mm(a, b_nk, bias=None, precise=False):
+        """a [M,K] @ b_nk[N,K]^T (+ bias) through cova_linear_fwd.  precise = split-fp16 operands (22 bits; the forward:
+        the gradients of the train-mode BatchNorm1d that follows jump by 1-2 % when its input moves at the 1e-5 level),
+        else split-bf16 (16 bits, full fp32 range: the gradient GEMMs)."""
+        a = a.contiguous()
+        b_nk = b_nk.contiguous()
+        if ops.linear_tc_ok(a):
+            if precise:
+                return ops.linear_fwd(a, ops.pack_linear_weight_f16x2(b_nk), bias=bias, engine=ops.ENGINE_TCGEN05_F16X2)
+            return ops.linear_fwd(a, ops.pack_linear_weight(b_nk), bias=bias, engine=ops.ENGINE_TCGEN05)
+        return ops.linear_fwd(a, b_nk, bias=bias, engine=ops.ENGINE_SIMT)
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        x = x.float()
+        ctx.save_for_backward(x, weight)
+        ctx.has_bias = bias is not None
+        return _LinearFn._mm(x, weight.detach().float(), None if bias is None else bias.detach().float().contiguous(),
+                             precise=True)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight = ctx.saved_tensors
+        dy = dy.float().contiguous()
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = _LinearFn._mm(dy, weight.detach().float().t())                 # [M,N] @ [K,N]^T
+        if ctx.needs_input_grad[1]:
+            dw = _LinearFn._mm(dy.t(), x.t())                                   # [N,M] @ [K,M]^T
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = dy.sum(0)
+        return dx, dw, db
+
+
+def _native_linear(x, weight, bias):
+    if os.environ.get("COVA_B200_TRAIN_LINEAR", "native") == "native" and x.is_cuda and x.shape[0] > 0:
+        return _LinearFn.apply(x, weight, bias)
+    return F.linear(x, weight, bias)
+
+
+def _run_sequential(seq, x):
+    """`seq(x)` with every nn.Linear routed through `_LinearFn` (same modules, same parameters, same order)."""
+    for mod in seq:
+        x = _native_linear(x, mod.weight, mod.bias) if isinstance(mod, nn.Linear) else mod(x)
+    return x
+
+
 # ----------------------------------------------------------------------------- GAT
 class GraphAttentionLayer(nn.Module):
     """Simple GAT layer, similar to https://arxiv.org/abs/1710.10903 (`/root/reference/models.py:151-212`)."""
@@ -222,7 +275,7 @@ class GraphAttentionLayer(nn.Module):
             ext_w = torch.cat((self.W_j.weight, (a[:Hd] @ self.W_i.weight)[None], (a[Hd:] @ self.W_j.weight)[None], pad), 0)
             zb = torch.zeros(Hd + 4, dtype=h_i.dtype, device=h_i.device)
             ext_b = torch.cat((zb[:Hd], self.attention_layer.bias, zb[:3]))      # b rides in the s column
-            out, attn = _GatGatherFn.apply(F.linear(h_i, ext_w, ext_b), context_indices, Hd,
+            out, attn = _GatGatherFn.apply(_native_linear(h_i, ext_w, ext_b), context_indices, Hd,
                                            float(self.leakyrelu.negative_slope))
             return (out, attn) if return_attn_wts else out
         N, K = context_indices.shape
@@ -380,7 +433,7 @@ class CoVA(nn.Module):
             context_representation = self.gat(own_features, context_indices)
         else:
             context_representation = own_features[:, :0]
-        return self.decoder(torch.cat((own_features, context_representation), dim=1))
+        return _run_sequential(self.decoder, torch.cat((own_features, context_representation), dim=1))
 
     def _get_visual_features(self, images, bboxes):
         """`models.py:124-127` -> [N, C*P*P]."""
@@ -406,4 +459,4 @@ class CoVA(nn.Module):
         f = bboxes[:, 1:].clone()
         f[:, 2:] -= f[:, :2]
         f = torch.cat((f, (f[:, 2] / f[:, 3]).view(-1, 1)), dim=1)
-        return self.bbox_feat_encoder(f)
+        return _run_sequential(self.bbox_feat_encoder, f)

@@ -4,7 +4,7 @@ CPU path here (the CPU restatement lives in ``oracle/`` and is test infrastructu
 import torch
 
 from . import _lib
-from ._lib import BF16, BF16X2, ENGINE_SIMT, ENGINE_TCGEN05, F16, F16X2, F32, U8  # noqa: F401
+from ._lib import BF16, BF16X2, ENGINE_SIMT, ENGINE_TCGEN05, ENGINE_TCGEN05_F16X2, F16, F16X2, F32, U8  # noqa: F401
 
 ENGINES = {"simt": ENGINE_SIMT, "tcgen05": ENGINE_TCGEN05}
 
@@ -254,7 +254,7 @@ def linear_fwd(x, w, bias=None, scale=None, shift=None, res=None, relu=False, ou
     M, K = x.shape
     N = w.shape[-2]
     assert x.stride(1) == 1 and w.is_contiguous() and w.shape[-1] == K
-    assert (w.dtype == torch.bfloat16 and w.dim() == 3) == (engine == ENGINE_TCGEN05)
+    assert (w.dtype == (torch.float16 if engine == ENGINE_TCGEN05_F16X2 else torch.bfloat16) and w.dim() == 3) == (engine != ENGINE_SIMT)
     if out_planes:
         pl = Planes(BF16X2, (1, 1, M, N), x.device)
         y0, y1, ldy, odt = pl.p0.data_ptr(), pl.p1.data_ptr(), N, BF16X2

@@ -40,7 +40,8 @@ extern "C" {
 
 enum { COVA_OK = 0, COVA_ERR_ARG = 1, COVA_ERR_CUDA = 2, COVA_ERR_UNSUPPORTED = 3 };
 enum { COVA_F32 = 0, COVA_BF16 = 1, COVA_BF16X2 = 2, COVA_U8 = 3 /* images only */, COVA_F16 = 4, COVA_F16X2 = 5 };
-enum { COVA_ENGINE_SIMT = 0, COVA_ENGINE_TCGEN05 = 1 };
+enum { COVA_ENGINE_SIMT = 0, COVA_ENGINE_TCGEN05 = 1,
+       COVA_ENGINE_TCGEN05_F16X2 = 2 /* cova_linear_fwd only: split-fp16 operands, w from cova_pack_conv_weight_f16x2(w, N, K, 1, 1) */ };
 
 int cova_abi_version(void);
 const char* cova_last_error(void);
@@ -163,7 +164,9 @@ int cova_affine_cols_fwd(const float* x, int T, int D, int64_t ld_x, const float
  * (`nn.Linear` = `models.py:160-164` W_i/W_j, `:85`, `:89`; also the 1x1 convolutions of the ResNet-50
  * Bottleneck on NHWC activations, where `res` is the identity branch); bias/scale/shift/res may be NULL.
  *   w: engine SIMT -> fp32 [N,K];  engine TCGEN05 -> split-bf16 [2][N][K] from cova_pack_linear_weight
- *      (needs K % 8 == 0, ld_x % 4 == 0, 16-byte aligned x; otherwise COVA_ERR_ARG - call the SIMT engine). */
+ *      (needs K % 8 == 0, ld_x % 4 == 0, 16-byte aligned x; otherwise COVA_ERR_ARG - call the SIMT engine);
+ *      engine TCGEN05_F16X2 -> split-fp16 [2][N][K] of 256*w (cova_pack_conv_weight_f16x2 with kh = kw = 1): 22 instead
+ *      of 16 significand bits, same cost - the training forward (x must stay below 65504).                          */
 int cova_linear_fwd(const float* x, int64_t ld_x, int M, int K, const void* w, int N, const float* bias,
                     const float* scale, const float* shift, const float* res, int64_t ld_res, int relu,
                     int out_dtype, void* y0, void* y1, int64_t ld_y, int engine, void* stream);

@@ -7,16 +7,18 @@ from cova_b200.models import CoVA
 from cova_b200.train_ops import CrossEntropyLossSum, FlatAdam
 from torch.profiler import profile, ProfilerActivity
 dev = torch.device("cuda", 0)
-m = CoVA((3, 3), 1280, 4, True, 384, 32, 0, 0.2, None, pretrained=False)
-m.load_state_dict(synth.make_state_dict(123), strict=True)
+bk = os.environ.get("BACKBONE", "resnet18")
+B = int(os.environ.get("B", "16"))
+m = CoVA((3, 3), 1280, 4, True, 384, 32, 0, 0.2, None, pretrained=False, backbone=bk)
+m.load_state_dict(synth.make_state_dict(123, backbone=bk), strict=True)
 m = m.to(dev).train()
 opt = FlatAdam(m.parameters(), lr=5e-4, weight_decay=1e-3)
 crit = CrossEntropyLossSum().to(dev)
-inp = [t.to(dev) for t in synth.gen(16, 90, 24, seed=1, with_labels=True)]
+inp = [t.to(dev) for t in synth.gen(B, 90, 24, seed=1, with_labels=True)]
 def step():
     opt.zero_grad(); loss = crit(m(*inp[:4]), inp[4]); loss.backward(); opt.step()
 for _ in range(2): step()
 torch.cuda.synchronize()
 with profile(activities=[ProfilerActivity.CUDA]) as prof:
     step(); torch.cuda.synchronize()
-print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=25, max_name_column_width=90))
+print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=int(os.environ.get("ROWS", "25")), max_name_column_width=90))
