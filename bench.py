@@ -181,6 +181,8 @@ def _alg_table(roi_b):
         "cova_bn_train_stats": lambda a: ("hbm", 4.0 * i(a[1]) * i(a[2])),
         "cova_bn_act_fwd": lambda a: ("hbm", 4.0 * i(a[1]) * i(a[2]) * (2 + (1 if a[7] else 0) + (1 if a[10] else 0))),
         "cova_bn_act_bwd": lambda a: ("hbm", 4.0 * i(a[3]) * i(a[4]) * (2 * (2 + (1 if a[2] else 0)) + 1 + (1 if a[12] else 0))),
+        # two passes over (x, dy [, res]) + the scaled split planes of dx (4 B/elt) [+ dres]
+        "cova_bn_act_bwd_planes": lambda a: ("hbm", 4.0 * i(a[3]) * i(a[4]) * (2 * (2 + (1 if a[2] else 0)) + 1 + (1 if a[17] else 0))),
         "cova_maxpool3x3s2_fwd": lambda a: ("hbm", 4.0 * i(a[1]) * i(a[2]) * i(a[3]) * i(a[4]) * (1 + 0.25 * (1.25 + (1 if a[7] else 0)))),
         "cova_maxpool3x3s2_bwd": lambda a: ("hbm", 4.0 * i(a[2]) * i(a[3]) * i(a[4]) * i(a[5]) * (1 + 0.25 * 1.25)),
         "cova_split_planes": lambda a: ("hbm", 8.0 * i(a[1])),
@@ -449,7 +451,7 @@ class Runner:
         split = m.precision in ("fp32", "fp32x") or self.train or m.backbone == "resnet50"
         f = 3.0 if split else 1.0
         return {"cova_conv3x3_bn_act_fwd": f, "cova_stem_fwd": f * 224.0 / 147.0, "cova_stem_conv_raw_fwd": f * 224.0 / 147.0,
-                "cova_linear_fwd": 3.0, "cova_conv3x3_wgrad": 3.5, "cova_stem_wgrad": 4.0 * 224.0 / 147.0}
+                "cova_linear_fwd": 3.0, "cova_conv3x3_wgrad": 3.5, "cova_stem_wgrad": 14 * 2.0 * 128 * 32 * 16 / (16 * 2.0 * 64 * 147)}
 
 
 def measure(cfg, dev, rank, world, dist, args, sample_clocks, full):

@@ -19,6 +19,9 @@ def step():
     opt.zero_grad(); loss = crit(m(*inp[:4]), inp[4]); loss.backward(); opt.step()
 for _ in range(2): step()
 torch.cuda.synchronize()
+if os.environ.get("NCU") == "1":          # ncu --profile-from-start off: one step between cudaProfilerStart / Stop
+    torch.cuda.cudart().cudaProfilerStart(); step(); torch.cuda.synchronize(); torch.cuda.cudart().cudaProfilerStop()
+    sys.exit(0)
 with profile(activities=[ProfilerActivity.CUDA]) as prof:
     step(); torch.cuda.synchronize()
 print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=int(os.environ.get("ROWS", "25")), max_name_column_width=90))
