@@ -37,16 +37,18 @@ IMG = 1280
 CONFIGS = {
     2: dict(B=16, N=90, K=24, heads=1, backbone="resnet18", mode="infer",
             workload="configs[1]: batch=16 synthetic 1280x1280 pages per GPU, N=90 boxes, K=24, ResNet-18 backbone, inference"),
-    3: dict(B=64, N=90, K=24, heads=1, backbone="resnet50", mode="train",
-            workload="configs[2]: batch=64 synthetic 1280x1280 pages per GPU, N=90, K=24, ResNet-50 backbone, train step "
+    3: dict(B=64, N=90, K=24, heads=1, backbone="resnet50", mode="train", precision="bf16",
+            workload="configs[2]: batch=64 synthetic 1280x1280 pages per GPU, N=90, K=24, ResNet-50 backbone bf16, train step "
                      "(forward + CE(sum) + backward + gradient all-reduce + Adam)"),
-    4: dict(B=32, N=90, K=24, heads=1, backbone="resnet50", mode="train",
+    4: dict(B=32, N=90, K=24, heads=1, backbone="resnet50", mode="train", precision="bf16",
             workload="configs[3]: batch=256 over 8 GPUs = 32 synthetic 1280x1280 pages per GPU, N=90, K=24, ResNet-50 backbone, "
                      "train step with the NCCL gradient all-reduce(SUM)"),
     5: dict(B=16, N=300, K=48, heads=2, backbone="resnet50", mode="infer",
             workload="configs[4] stress: batch=128 over 8 GPUs = 16 synthetic 1280x1280 pages per GPU, N=300 boxes, K=48, "
                      "2-head GAT, ResNet-50 backbone, inference"),
 }
+TRAIN_DTYPES = {"bf16": "bf16 maps / gradient maps, one bf16 tensor-core product (fp32 accumulate); fp32 statistics, parameters, weight gradients",
+                "fp32": "fp16x3 forward / dgrad / wgrad convolutions (split-fp16, fp32 accumulate; fp32-parity), fp32 maps"}
 DTYPES = {"fp32": "bf16x3 (split-bf16, fp32 accumulate; fp32-parity)", "bf16": "bf16",
           "fp16": "fp16 (one product, fp32 accumulate)", "fp32x": "fp16x3 (split-fp16, fp32 accumulate; fp32-parity)"}
 
@@ -142,7 +144,7 @@ def build_model(dev, cfg, precision=None):
     from cova_b200.models import CoVA
     m = CoVA((3, 3), IMG, 4, True, 384, 32, 0, 0.2, None, pretrained=False, backbone=cfg["backbone"], n_heads=cfg["heads"],
              engine=os.environ.get("COVA_B200_ENGINE", "tcgen05"),
-             precision=precision or os.environ.get("COVA_B200_PRECISION", "fp32"))
+             precision=precision or os.environ.get("COVA_B200_PRECISION") or cfg.get("precision", "fp32"))
     m.load_state_dict(synth.make_state_dict(123, backbone=cfg["backbone"], n_heads=cfg["heads"]), strict=True)
     return m.to(dev)
 
@@ -162,13 +164,14 @@ def roi_bytes(bboxes, C=64, P=3, scale=0.25, Hf=320, Wf=320):
 # ("tensor", FLOP) for the contraction kernels, ("hbm", bytes) for the streaming ones (SURVEY 8(d) per-unit figures).
 def _alg_table(roi_b):
     i = int
+    es = lambda code: 2 if int(code) == 1 else 4
     return {
         "cova_stem_fwd": lambda a: ("tensor", 2.0 * 64 * 147 * i(a[2]) * (i(a[3]) // 2) * (i(a[4]) // 2)),
         "cova_stem_conv_raw_fwd": lambda a: ("tensor", 2.0 * 64 * 147 * i(a[2]) * (i(a[3]) // 2) * (i(a[4]) // 2)),
         "cova_conv3x3_bn_act_fwd": lambda a: ("tensor", 2.0 * 9 * i(a[6]) * i(a[7]) * i(a[3]) * i(a[4]) * i(a[5])),
         "cova_conv3x3_wgrad": lambda a: ("tensor", 2.0 * 9 * 64 * 64 * i(a[4]) * i(a[5]) * i(a[6])),
         "cova_stem_wgrad": lambda a: ("tensor", 2.0 * 64 * 147 * i(a[2]) * (i(a[3]) // 2) * (i(a[4]) // 2)),
-        "cova_conv1x1_wgrad": lambda a: ("hbm", 4.0 * i(a[4]) * (i(a[5]) + i(a[6]))),
+        "cova_conv1x1_wgrad": lambda a: ("hbm", (2.0 if i(a[7]) == 1 else 4.0) * i(a[4]) * (i(a[5]) + i(a[6]))),
         # 1x1 convs over split planes: 4 B/elt in (hi+lo), 4 B/elt out, + residual planes
         "cova_conv1x1_bn_act_fwd": lambda a: ("hbm", float(i(a[2])) * (4 * i(a[3]) + 4 * i(a[4]) + (4 * i(a[4]) if a[8] else 0))),
         "cova_roi_fwd": lambda a: ("hbm", roi_b * i(a[4]) / 64.0) if i(a[10]) == 0 else
@@ -185,6 +188,16 @@ def _alg_table(roi_b):
         "cova_bn_act_bwd_planes": lambda a: ("hbm", 4.0 * i(a[3]) * i(a[4]) * (2 * (2 + (1 if a[2] else 0)) + 1 + (1 if a[17] else 0))),
         "cova_maxpool3x3s2_fwd": lambda a: ("hbm", 4.0 * i(a[1]) * i(a[2]) * i(a[3]) * i(a[4]) * (1 + 0.25 * (1.25 + (1 if a[7] else 0)))),
         "cova_maxpool3x3s2_bwd": lambda a: ("hbm", 4.0 * i(a[2]) * i(a[3]) * i(a[4]) * i(a[5]) * (1 + 0.25 * 1.25)),
+        # typed (bf16 training mode) passes: element sizes from the dtype codes (0 = fp32, 1 = bf16)
+        "cova_bn_train_stats_t": lambda a: ("hbm", float(es(a[1])) * i(a[2]) * i(a[3])),
+        "cova_bn_act_fwd_t": lambda a: ("hbm", float(i(a[2])) * i(a[3]) * (es(a[1]) * (1 + (1 if a[8] else 0)) + es(a[11]))),
+        "cova_bn_act_bwd_t": lambda a: ("hbm", float(i(a[5])) * i(a[6]) * (2 * (es(a[1]) + es(a[4]) * (1 + (1 if a[3] else 0)))
+                                                                         + es(a[4]) * (1 + (1 if a[14] else 0)))),
+        "cova_maxpool3x3s2_fwd_t": lambda a: ("hbm", float(es(a[1])) * i(a[2]) * i(a[3]) * i(a[4]) * i(a[5]) * 1.25 + 0.25 * i(a[2]) * i(a[3]) * i(a[4]) * i(a[5])),
+        "cova_maxpool3x3s2_bwd_t": lambda a: ("hbm", float(es(a[2])) * i(a[3]) * i(a[4]) * i(a[5]) * i(a[6]) * 1.25 + 0.25 * i(a[3]) * i(a[4]) * i(a[5]) * i(a[6])),
+        "cova_stem_conv_raw_fwd_bf16": lambda a: ("tensor", 2.0 * 64 * 147 * i(a[2]) * (i(a[3]) // 2) * (i(a[4]) // 2)),
+        # 1x1 convolutions of the training path: planes in (4 B/elt split, 2 B/elt bf16), rows out (fp32 / bf16)
+        "cova_conv1x1_raw_fwd": lambda a: ("hbm", float(i(a[3])) * (i(a[4]) + i(a[5])) * (2 if i(a[2]) == 1 else 4)),
         "cova_split_planes": lambda a: ("hbm", 8.0 * i(a[1])),
         "cova_split_planes_scaled": lambda a: ("hbm", 12.0 * i(a[1])),
         "cova_adam_step": lambda a: ("hbm", 28.0 * i(a[4])),
@@ -448,9 +461,10 @@ class Runner:
         m = self.model
         if m.engine != "tcgen05":
             return {}
-        split = m.precision in ("fp32", "fp32x") or self.train or m.backbone == "resnet50"
+        split = (m.precision in ("fp32", "fp32x") or self.train or m.backbone == "resnet50") and not (self.train and m.precision == "bf16")
         f = 3.0 if split else 1.0
         return {"cova_conv3x3_bn_act_fwd": f, "cova_stem_fwd": f * 224.0 / 147.0, "cova_stem_conv_raw_fwd": f * 224.0 / 147.0,
+                "cova_stem_conv_raw_fwd_bf16": 224.0 / 147.0,
                 "cova_linear_fwd": 3.0, "cova_conv3x3_wgrad": 3.5, "cova_stem_wgrad": 14 * 2.0 * 128 * 32 * 16 / (16 * 2.0 * 64 * 147)}
 
 
@@ -495,6 +509,21 @@ def measure(cfg, dev, rank, world, dist, args, sample_clocks, full):
     r.run_e2e(2, pinned_u8)
     reps_u8 = [r.timed(lambda k: r.run_e2e(k, pinned_u8), steps, whole=True) for _ in range(3 if full else 1)]
     out.update(ms_e2e_u8=min(reps_u8), reps_u8=reps_u8, h2d_u8=r.h2d_bytes(pinned_u8))
+    out["ms_train_fp32"] = None
+    if r.train and r.model.precision == "bf16" and world == 1:
+        # side measurement (single rank only: no collective inside a try block): the same train step in the fp32-parity mode
+        torch.cuda.empty_cache()
+        r32 = Runner(dict(cfg, precision="fp32"), dev, rank, world, dist)
+        try:
+            for _ in range(2):
+                r32.step_resident()
+            n32 = 3
+            out["ms_train_fp32"] = r32.timed(r32.step_resident, n32) / n32
+        except Exception as e:   # pragma: no cover  (memory: the fp32 maps of B=64 need ~100 GB)
+            out["ms_train_fp32"] = None
+            out["train_fp32_error"] = "%s: %s" % (type(e).__name__, str(e).splitlines()[0][:120])
+        del r32
+        torch.cuda.empty_cache()
     out["ms_fp16"] = None
     if full and not r.train and r.model.engine == "tcgen05" and r.model.precision == "fp32" and cfg["backbone"] == "resnet18":
         # side measurement (not the headline): the one-product fp16 mode on the same inputs - logits within 5-7e-4 of the
@@ -531,11 +560,15 @@ def summarize_other(res, world, pk):
          "pages_per_gpu_per_step": cfg["B"], "n_gpus": world, "gpu_launches": res["launches"],
          "collective": ("NCCL all-reduce(SUM) of the flat fp32 gradient bucket inside every step" if (cfg["mode"] == "train" and world > 1)
                         else "none (single rank)" if cfg["mode"] == "train" else "none (pages are independent)"),
-         "dtype": ("fp16x3 forward / dgrad / wgrad convolutions (split-fp16, fp32 accumulate), fp32 elsewhere" if cfg["mode"] == "train"
+         "dtype": (TRAIN_DTYPES.get(res["precision"], TRAIN_DTYPES["fp32"]) if cfg["mode"] == "train"
                    else DTYPES.get(res["precision"], res["precision"])),
          "e2e": {"value": pages / (res["ms_e2e"] / 1e3), "unit": "pages/s", "h2d_bytes_per_step": res["h2d"],
                  "d2h_bytes_per_step": res["d2h"], "ms_per_step": res["ms_e2e"] / res["steps"]},
          "e2e_uint8_images": {"value": pages / (res["ms_e2e_u8"] / 1e3), "unit": "pages/s", "h2d_bytes_per_step": res["h2d_u8"]}}
+    if res.get("ms_train_fp32"):
+        d["fp32_parity_mode"] = {"value": cfg["B"] * world / (res["ms_train_fp32"] / 1e3), "unit": "pages/s", "ms_per_step": res["ms_train_fp32"],
+                                 "note": "same train step with fp32 maps and split-fp16 three-product convolutions (every gradient within "
+                                         "1.2e-5 of the live-reference fixture); side measurement, 3 steps"}
     if "stages" in res:
         d["roofline"] = roofline_of(res["stages"], pk, res["exec_factor"], {})
         tot = sum(v[0] for v in res["stages"].values())
@@ -626,7 +659,7 @@ def main():
         "metric": "webpages/sec", "value": value, "unit": "pages/s", "n_gpus": world, "steps": steps,
         "warmup": head["warmup"], "ms_per_step": head["ms"] / steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None,
-        "dtype": ("fp16x3 convolutions (split-fp16, fp32 accumulate), fp32 elsewhere" if cfg["mode"] == "train" else
+        "dtype": (TRAIN_DTYPES.get(model.precision, TRAIN_DTYPES["fp32"]) if cfg["mode"] == "train" else
                   DTYPES.get(model.precision, model.precision)) if model.engine == "tcgen05" else "f32",
         "data": "synthetic",
         "config": {"workload": cfg["workload"], "config_id": cfg["id"], "mode": cfg["mode"],
@@ -651,6 +684,9 @@ def main():
                              "aggregate_h2d_gb_s": agg_h2d(head["ms_e2e_u8"], head["h2d_u8"]),
                              "note": "optional input format (SURVEY 8(f) N1; the PNGs of datasets.py:96-97 are uint8): raw "
                                      "pixels, v/255 in the stem kernel, bit-identical logits"},
+        "fp32_parity_mode": None if not head.get("ms_train_fp32") else {
+            "value": cfg["B"] * world / (head["ms_train_fp32"] / 1e3), "unit": "pages/s", "ms_per_step": head["ms_train_fp32"],
+            "note": "same train step with fp32 maps and split-fp16 three-product convolutions; side measurement, 3 steps"},
         "throughput_mode_fp16": None if head["ms_fp16"] is None else {
             "value": pages / (head["ms_fp16"] / 1e3), "unit": "pages/s", "ms_per_step": head["ms_fp16"] / steps,
             "note": "precision='fp16' (one fp16 product per MMA): max rel. error of the logits vs the live-reference "

@@ -37,6 +37,21 @@ __device__ __forceinline__ void split4(const float4 v, __nv_bfloat16* hi, __nv_b
   *reinterpret_cast<uint2*>(lo + idx) = make_uint2(l01, l23);
 }
 
+// Storage-type accessors: the training maps are fp32 (fp32-parity mode) or bf16 (the bf16 training mode, BASELINE config 3:
+// half the bytes of every pass); 4 consecutive channels per access, arithmetic always in fp32.
+template <typename T> __device__ __forceinline__ float4 ld4(const T* p, int64_t e);
+template <> __device__ __forceinline__ float4 ld4<float>(const float* p, int64_t e) {
+  return __ldg(reinterpret_cast<const float4*>(p + e));
+}
+template <> __device__ __forceinline__ float4 ld4<__nv_bfloat16>(const __nv_bfloat16* p, int64_t e) {
+  const uint2 u = __ldg(reinterpret_cast<const uint2*>(p + e));
+  return make_float4(bf16lo_to_f32(u.x), bf16hi_to_f32(u.x), bf16lo_to_f32(u.y), bf16hi_to_f32(u.y));
+}
+__device__ __forceinline__ void st4(float* p, int64_t e, const float4 v) { *reinterpret_cast<float4*>(p + e) = v; }
+__device__ __forceinline__ void st4(__nv_bfloat16* p, int64_t e, const float4 v) {
+  *reinterpret_cast<uint2*>(p + e) = make_uint2(pack2_bf16(v.x, v.y), pack2_bf16(v.z, v.w));
+}
+
 // power-of-two scale that brings max|x| into [2^target, 2^(target+1)); 1 for a zero / non-finite maximum
 __device__ __forceinline__ float pow2_scale(unsigned int amax_bits, int target_log2) {
   const int e = (int)(amax_bits >> 23) & 0xff;
@@ -49,9 +64,9 @@ __device__ __forceinline__ float pow2_scale(unsigned int amax_bits, int target_l
 // MODE 0: a = sum x, b = sum x^2.   MODE 1: a = sum g, b = sum g * xhat with g = dy * [y > 0] (y recomputed).
 // MODE 2: MODE 1 + wmax[c] = max |x - mean| per channel and wmax[C] = max |g| (bit patterns of non-negative floats): what
 // bounds |dx| before dx exists, so that the apply pass can emit SCALED split-fp16 planes directly (bn_act_bwd_kernel<true>).
-template <int MODE>
+template <int MODE, typename TS = float, typename TG = float>
 __global__ void __launch_bounds__(BN_THREADS)
-bn_reduce_kernel(const float* __restrict__ x, const float* __restrict__ dy, const float* __restrict__ res, int64_t M,
+bn_reduce_kernel(const TS* __restrict__ x, const TG* __restrict__ dy, const TS* __restrict__ res, int64_t M,
                  int C, const float* __restrict__ mean, const float* __restrict__ invstd,
                  const float* __restrict__ gamma, const float* __restrict__ beta, int relu, double* __restrict__ ws,
                  unsigned int* __restrict__ wmax = nullptr) {
@@ -75,7 +90,7 @@ bn_reduce_kernel(const float* __restrict__ x, const float* __restrict__ dy, cons
     for (; p + 3 * stride < M; p += 4 * stride) {
       float4 v[4];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) v[u] = __ldg(reinterpret_cast<const float4*>(x + (p + u * stride) * C + c0));
+      for (int u = 0; u < 4; ++u) v[u] = ld4<TS>(x, (p + u * stride) * C + c0);
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         a.x += v[u].x; a.y += v[u].y; a.z += v[u].z; a.w += v[u].w;
@@ -85,18 +100,18 @@ bn_reduce_kernel(const float* __restrict__ x, const float* __restrict__ dy, cons
     }
   }
   for (; p < M; p += stride) {
-    const float4 xv = __ldg(reinterpret_cast<const float4*>(x + p * C + c0));
+    const float4 xv = ld4<TS>(x, p * C + c0);
     if (MODE == 0) {
       a.x += xv.x; a.y += xv.y; a.z += xv.z; a.w += xv.w;
       b.x = fmaf(xv.x, xv.x, b.x); b.y = fmaf(xv.y, xv.y, b.y); b.z = fmaf(xv.z, xv.z, b.z); b.w = fmaf(xv.w, xv.w, b.w);
     } else {
-      float4 g = __ldg(reinterpret_cast<const float4*>(dy + p * C + c0));
+      float4 g = ld4<TG>(dy, p * C + c0);
       const float4 xh = make_float4((xv.x - mu.x) * iv.x, (xv.y - mu.y) * iv.y, (xv.z - mu.z) * iv.z, (xv.w - mu.w) * iv.w);
       if (relu) {
         float4 y = make_float4(bn_val(xv.x, mu.x, iv.x, ga.x, be.x), bn_val(xv.y, mu.y, iv.y, ga.y, be.y),
                                bn_val(xv.z, mu.z, iv.z, ga.z, be.z), bn_val(xv.w, mu.w, iv.w, ga.w, be.w));
         if (res != nullptr) {
-          const float4 r = __ldg(reinterpret_cast<const float4*>(res + p * C + c0));
+          const float4 r = ld4<TS>(res, p * C + c0);
           y.x += r.x; y.y += r.y; y.z += r.z; y.w += r.w;
         }
         g.x = y.x > 0.f ? g.x : 0.f; g.y = y.y > 0.f ? g.y : 0.f;
@@ -154,25 +169,28 @@ __global__ void bn_finalize_kernel(const double* __restrict__ ws, int64_t M, int
   }
 }
 
+// TS = storage type of x / res, TY = type of y.  In the bf16 training mode the rounded y is compared against 0 by the
+// backward exactly as it is here: bn_val in fp32, + res, ReLU, then the store rounds (a positive value never rounds to <= 0).
+template <typename TS, typename TY>
 __global__ void __launch_bounds__(BN_THREADS)
-bn_act_fwd_kernel(const float* __restrict__ x, int64_t n4, int C, const float* __restrict__ mean,
+bn_act_fwd_kernel(const TS* __restrict__ x, int64_t n4, int C, const float* __restrict__ mean,
                   const float* __restrict__ invstd, const float* __restrict__ gamma, const float* __restrict__ beta,
-                  const float* __restrict__ res, int relu, float* __restrict__ y, __nv_bfloat16* __restrict__ y_hi,
+                  const TS* __restrict__ res, int relu, TY* __restrict__ y, __nv_bfloat16* __restrict__ y_hi,
                   __nv_bfloat16* __restrict__ y_lo, int f16) {
   const int c4n = C >> 2;
   for (int64_t i = (int64_t)blockIdx.x * BN_THREADS + threadIdx.x; i < n4; i += (int64_t)gridDim.x * BN_THREADS) {
     const int c0 = 4 * (int)(i % c4n);
-    const float4 xv = __ldg(reinterpret_cast<const float4*>(x) + i);
+    const float4 xv = ld4<TS>(x, i * 4);
     const float4 mu = *reinterpret_cast<const float4*>(mean + c0), iv = *reinterpret_cast<const float4*>(invstd + c0);
     const float4 ga = *reinterpret_cast<const float4*>(gamma + c0), be = *reinterpret_cast<const float4*>(beta + c0);
     float4 o = make_float4(bn_val(xv.x, mu.x, iv.x, ga.x, be.x), bn_val(xv.y, mu.y, iv.y, ga.y, be.y),
                            bn_val(xv.z, mu.z, iv.z, ga.z, be.z), bn_val(xv.w, mu.w, iv.w, ga.w, be.w));
     if (res != nullptr) {
-      const float4 r = __ldg(reinterpret_cast<const float4*>(res) + i);
+      const float4 r = ld4<TS>(res, i * 4);
       o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
     }
     if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-    if (y != nullptr) reinterpret_cast<float4*>(y)[i] = o;
+    if (y != nullptr) st4(y, i * 4, o);
     if (y_hi != nullptr) split4(o, y_hi, y_lo, (size_t)i * 4, f16);
   }
 }
@@ -181,12 +199,12 @@ bn_act_fwd_kernel(const float* __restrict__ x, int64_t n4, int C, const float* _
 // an upper bound of max|dx| - computed here from the reduce pass's maxima: |dx| <= |gamma inv| (max|g| + |S1/M| +
 // max|xhat| |S2/M|) - into [2^target, 2^(target+1)); block 0 publishes 256 copies of 1/s for the consuming convolution
 // kernels (dgrad epilogue scale / wgrad finalize).  The fp32 gradient map is never written nor re-read for the split.
-template <bool PLANES>
+template <bool PLANES, typename TS = float, typename TG = float>
 __global__ void __launch_bounds__(BN_THREADS)
-bn_act_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ res, int64_t n4,
+bn_act_bwd_kernel(const TG* __restrict__ dy, const TS* __restrict__ x, const TS* __restrict__ res, int64_t n4,
                   int64_t M, int C, const float* __restrict__ mean, const float* __restrict__ invstd,
                   const float* __restrict__ gamma, const float* __restrict__ beta, int relu,
-                  const double* __restrict__ ws, float* __restrict__ dx, float* __restrict__ dres,
+                  const double* __restrict__ ws, TS* __restrict__ dx, TS* __restrict__ dres,
                   float* __restrict__ dgamma, float* __restrict__ dbeta, const unsigned int* __restrict__ wmax,
                   __nv_bfloat16* __restrict__ dx_hi, __nv_bfloat16* __restrict__ dx_lo, int f16, int target_log2,
                   float* __restrict__ inv_vec) {
@@ -224,8 +242,8 @@ bn_act_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, con
   }
   for (int64_t i = (int64_t)blockIdx.x * BN_THREADS + threadIdx.x; i < n4; i += (int64_t)gridDim.x * BN_THREADS) {
     const int c0 = 4 * (int)(i % c4n);
-    const float4 xv = __ldg(reinterpret_cast<const float4*>(x) + i);
-    float4 g = __ldg(reinterpret_cast<const float4*>(dy) + i);
+    const float4 xv = ld4<TS>(x, i * 4);
+    float4 g = ld4<TG>(dy, i * 4);
     const float4 mu = *reinterpret_cast<const float4*>(mean + c0), iv = *reinterpret_cast<const float4*>(invstd + c0);
     const float4 ga = *reinterpret_cast<const float4*>(gamma + c0), be = *reinterpret_cast<const float4*>(beta + c0);
     const float4 xh = make_float4((xv.x - mu.x) * iv.x, (xv.y - mu.y) * iv.y, (xv.z - mu.z) * iv.z, (xv.w - mu.w) * iv.w);
@@ -233,13 +251,13 @@ bn_act_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, con
       float4 y = make_float4(bn_val(xv.x, mu.x, iv.x, ga.x, be.x), bn_val(xv.y, mu.y, iv.y, ga.y, be.y),
                              bn_val(xv.z, mu.z, iv.z, ga.z, be.z), bn_val(xv.w, mu.w, iv.w, ga.w, be.w));
       if (res != nullptr) {
-        const float4 r = __ldg(reinterpret_cast<const float4*>(res) + i);
+        const float4 r = ld4<TS>(res, i * 4);
         y.x += r.x; y.y += r.y; y.z += r.z; y.w += r.w;
       }
       g.x = y.x > 0.f ? g.x : 0.f; g.y = y.y > 0.f ? g.y : 0.f;
       g.z = y.z > 0.f ? g.z : 0.f; g.w = y.w > 0.f ? g.w : 0.f;
     }
-    if (dres != nullptr) reinterpret_cast<float4*>(dres)[i] = g;
+    if (dres != nullptr) st4(dres, i * 4, g);
     const float4 s1 = *reinterpret_cast<const float4*>(sums + c0), s2 = *reinterpret_cast<const float4*>(sums + C + c0);
     float4 o;
     o.x = ga.x * iv.x * (g.x - s1.x - xh.x * s2.x);
@@ -250,7 +268,7 @@ bn_act_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, con
       o.x *= scale; o.y *= scale; o.z *= scale; o.w *= scale;
       split4(o, dx_hi, dx_lo, (size_t)i * 4, f16);
     } else {
-      reinterpret_cast<float4*>(dx)[i] = o;
+      st4(dx, i * 4, o);
     }
   }
 }
@@ -263,9 +281,9 @@ bn_act_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, con
 // no rescans, no atomics.
 // IdxT = uint32_t whenever the element count fits (64-bit div / mod per element made these kernels index-math bound:
 // the backward ran at 1.7 TB/s)
-template <typename IdxT>
+template <typename IdxT, typename TS = float>
 __global__ void __launch_bounds__(256)
-maxpool_fwd_kernel(const float* __restrict__ x, int B, int H, int W, int C, int Ho, int Wo, float* __restrict__ y,
+maxpool_fwd_kernel(const TS* __restrict__ x, int B, int H, int W, int C, int Ho, int Wo, TS* __restrict__ y,
                    unsigned char* __restrict__ code, __nv_bfloat16* __restrict__ y_hi, __nv_bfloat16* __restrict__ y_lo,
                    int f16) {
   const IdxT c4n = (IdxT)(C >> 2);
@@ -282,7 +300,7 @@ maxpool_fwd_kernel(const float* __restrict__ x, int B, int H, int W, int C, int 
       for (int s2 = 0; s2 < 3; ++s2) {
         const int w = 2 * ow - 1 + s2;
         if (w < 0 || w >= W) continue;
-        const float4 v = __ldg(reinterpret_cast<const float4*>(x + (((size_t)b * H + h) * W + w) * C) + cg);
+        const float4 v = ld4<TS>(x, (int64_t)((((size_t)b * H + h) * W + w) * C) + 4 * cg);
         const int k = r * 3 + s2;
         if (v.x > m.x || mi.x < 0) { m.x = v.x; mi.x = k; }
         if (v.y > m.y || mi.y < 0) { m.y = v.y; mi.y = k; }
@@ -290,16 +308,16 @@ maxpool_fwd_kernel(const float* __restrict__ x, int B, int H, int W, int C, int 
         if (v.w > m.w || mi.w < 0) { m.w = v.w; mi.w = k; }
       }
     }
-    reinterpret_cast<float4*>(y)[i] = m;
+    st4(y, (int64_t)i * 4, m);
     if (code != nullptr) reinterpret_cast<uchar4*>(code)[i] = make_uchar4(mi.x, mi.y, mi.z, mi.w);
     if (y_hi != nullptr) split4(m, y_hi, y_lo, (size_t)i * 4, f16);
   }
 }
 
-template <typename IdxT>
+template <typename IdxT, typename TS = float>
 __global__ void __launch_bounds__(256)
-maxpool_bwd_kernel(const unsigned char* __restrict__ code, const float* __restrict__ dy, int B, int H, int W, int C, int Ho,
-                   int Wo, float* __restrict__ dx) {
+maxpool_bwd_kernel(const unsigned char* __restrict__ code, const TS* __restrict__ dy, int B, int H, int W, int C, int Ho,
+                   int Wo, TS* __restrict__ dx) {
   const IdxT c4n = (IdxT)(C >> 2);
   const IdxT n = (IdxT)B * H * W * c4n;
   for (IdxT i = (IdxT)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (IdxT)gridDim.x * blockDim.x) {
@@ -315,14 +333,14 @@ maxpool_bwd_kernel(const unsigned char* __restrict__ code, const float* __restri
         const int me = (h0 - (2 * oh - 1)) * 3 + (w0 - (2 * ow - 1));
         const size_t o = (((size_t)b * Ho + oh) * Wo + ow) * (size_t)c4n + cg;
         const uchar4 k = __ldg(reinterpret_cast<const uchar4*>(code) + o);
-        const float4 g = __ldg(reinterpret_cast<const float4*>(dy) + o);
+        const float4 g = ld4<TS>(dy, (int64_t)o * 4);
         if (k.x == me) acc.x += g.x;
         if (k.y == me) acc.y += g.y;
         if (k.z == me) acc.z += g.z;
         if (k.w == me) acc.w += g.w;
       }
     }
-    reinterpret_cast<float4*>(dx)[i] = acc;
+    st4(dx, (int64_t)i * 4, acc);
   }
 }
 
@@ -508,7 +526,7 @@ extern "C" int cova_bn_train_stats(const float* x, int64_t M, int C, double* ws,
   const size_t smem = (size_t)2 * rows * C * sizeof(float);
   int64_t grid = (M + rows - 1) / rows;
   if (grid > (int64_t)sm_count() * 8) grid = (int64_t)sm_count() * 8;
-  bn_reduce_kernel<0><<<(int)grid, BN_THREADS, smem, st>>>(x, nullptr, nullptr, M, C, nullptr, nullptr, nullptr, nullptr, 0,
+  bn_reduce_kernel<0, float, float><<<(int)grid, BN_THREADS, smem, st>>>(x, nullptr, nullptr, M, C, nullptr, nullptr, nullptr, nullptr, 0,
                                                            ws);
   COVA_LAUNCH_OK();
   return COVA_OK;
@@ -534,7 +552,7 @@ extern "C" int cova_bn_act_fwd(const float* x, int64_t M, int C, const float* me
                "cova_bn_act_fwd: 16-byte alignment");
   COVA_REQUIRE((y_hi == nullptr) == (y_lo == nullptr), "cova_bn_act_fwd: the split planes come together");
   const int64_t n4 = M * (C / 4);
-  bn_act_fwd_kernel<<<ew_grid(n4, BN_THREADS), BN_THREADS, 0, (cudaStream_t)stream>>>(x, n4, C, mean, invstd, gamma, beta,
+  bn_act_fwd_kernel<float, float><<<ew_grid(n4, BN_THREADS), BN_THREADS, 0, (cudaStream_t)stream>>>(x, n4, C, mean, invstd, gamma, beta,
                                                                                      res, relu, y, (__nv_bfloat16*)y_hi,
                                                                                      (__nv_bfloat16*)y_lo,
                                                                                      planes_dtype == COVA_F16X2);
@@ -555,10 +573,10 @@ extern "C" int cova_bn_act_bwd(const float* dy, const float* x, const float* res
   const size_t smem = (size_t)2 * rows * C * sizeof(float);
   int64_t grid = (M + rows - 1) / rows;
   if (grid > (int64_t)sm_count() * 8) grid = (int64_t)sm_count() * 8;
-  bn_reduce_kernel<1><<<(int)grid, BN_THREADS, smem, st>>>(x, dy, res, M, C, mean, invstd, gamma, beta, relu, ws);
+  bn_reduce_kernel<1, float, float><<<(int)grid, BN_THREADS, smem, st>>>(x, dy, res, M, C, mean, invstd, gamma, beta, relu, ws);
   COVA_LAUNCH_OK();
   const int64_t n4 = M * (C / 4);
-  bn_act_bwd_kernel<false><<<ew_grid(n4, BN_THREADS), BN_THREADS, 2 * C * sizeof(float), st>>>(
+  bn_act_bwd_kernel<false, float, float><<<ew_grid(n4, BN_THREADS), BN_THREADS, 2 * C * sizeof(float), st>>>(
       dy, x, res, n4, M, C, mean, invstd, gamma, beta, relu, ws, dx, dres, dgamma, dbeta, nullptr, nullptr, nullptr, 0, 0, nullptr);
   COVA_LAUNCH_OK();
   return COVA_OK;
@@ -582,10 +600,10 @@ extern "C" int cova_bn_act_bwd_planes(const float* dy, const float* x, const flo
   const size_t smem = (size_t)2 * rows * C * sizeof(float);
   int64_t grid = (M + rows - 1) / rows;
   if (grid > (int64_t)sm_count() * 8) grid = (int64_t)sm_count() * 8;
-  bn_reduce_kernel<2><<<(int)grid, BN_THREADS, smem, st>>>(x, dy, res, M, C, mean, invstd, gamma, beta, relu, ws, ws_max);
+  bn_reduce_kernel<2, float, float><<<(int)grid, BN_THREADS, smem, st>>>(x, dy, res, M, C, mean, invstd, gamma, beta, relu, ws, ws_max);
   COVA_LAUNCH_OK();
   const int64_t n4 = M * (C / 4);
-  bn_act_bwd_kernel<true><<<ew_grid(n4, BN_THREADS), BN_THREADS, 2 * C * sizeof(float), st>>>(
+  bn_act_bwd_kernel<true, float, float><<<ew_grid(n4, BN_THREADS), BN_THREADS, 2 * C * sizeof(float), st>>>(
       dy, x, res, n4, M, C, mean, invstd, gamma, beta, relu, ws, nullptr, dres, dgamma, dbeta, ws_max, (__nv_bfloat16*)dx_hi,
       (__nv_bfloat16*)dx_lo, planes_dtype == COVA_F16X2, target_log2, inv_scale_vec);
   COVA_LAUNCH_OK();
@@ -689,6 +707,120 @@ extern "C" int cova_bn_relu_pool_bwd(const float* x, const unsigned char* code, 
   COVA_LAUNCH_OK();
   bn_relu_pool_bwd_kernel<1><<<(int)grid, BN_THREADS, (size_t)2 * C * sizeof(float), st>>>(
       x, code, dy_pooled, B, H, W, C, Ho, Wo, mean, invstd, gamma, beta, ws, dx, dgamma, dbeta);
+  COVA_LAUNCH_OK();
+  return COVA_OK;
+}
+
+// ---------------------------------------------------------------- typed entry points (bf16 training mode)
+static bool dt_ok(int d) { return d == COVA_F32 || d == COVA_BF16; }
+typedef __nv_bfloat16 bf16_t;
+
+extern "C" int cova_bn_train_stats_t(const void* x, int x_dtype, int64_t M, int C, double* ws, void* stream) {
+  if (x_dtype == COVA_F32) return cova_bn_train_stats((const float*)x, M, C, ws, stream);
+  COVA_REQUIRE(x_dtype == COVA_BF16, "cova_bn_train_stats_t: x is fp32 or bf16");
+  COVA_REQUIRE(x && ws && M > 0, "cova_bn_train_stats_t: bad arguments");
+  COVA_REQUIRE(bn_c_ok(C), "cova_bn_train_stats_t: C=%d must be a power of two in [4, 1024]", C);
+  COVA_REQUIRE(((uintptr_t)x & 7) == 0, "cova_bn_train_stats_t: x must be 8-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  COVA_CUDA_OK(cudaMemsetAsync(ws, 0, 2 * C * sizeof(double), st));
+  const int rows = BN_THREADS / (C / 4);
+  const size_t smem = (size_t)2 * rows * C * sizeof(float);
+  int64_t grid = (M + rows - 1) / rows;
+  if (grid > (int64_t)sm_count() * 8) grid = (int64_t)sm_count() * 8;
+  bn_reduce_kernel<0, bf16_t, bf16_t><<<(int)grid, BN_THREADS, smem, st>>>((const bf16_t*)x, nullptr, nullptr, M, C, nullptr, nullptr,
+                                                                         nullptr, nullptr, 0, ws);
+  COVA_LAUNCH_OK();
+  return COVA_OK;
+}
+
+extern "C" int cova_bn_act_fwd_t(const void* x, int s_dtype, int64_t M, int C, const float* mean, const float* invstd,
+                                 const float* gamma, const float* beta, const void* res, int relu, void* y, int y_dtype,
+                                 void* stream) {
+  COVA_REQUIRE(dt_ok(s_dtype) && dt_ok(y_dtype), "cova_bn_act_fwd_t: dtypes are fp32 or bf16");
+  COVA_REQUIRE(x && y && mean && invstd && gamma && beta && M > 0, "cova_bn_act_fwd_t: bad arguments");
+  COVA_REQUIRE(bn_c_ok(C), "cova_bn_act_fwd_t: C=%d must be a power of two in [4, 1024]", C);
+  COVA_REQUIRE((((uintptr_t)x | (uintptr_t)y | (uintptr_t)res) & (s_dtype == COVA_F32 ? 15 : 7)) == 0, "cova_bn_act_fwd_t: alignment");
+  const int64_t n4 = M * (C / 4);
+  const int grid = ew_grid(n4, BN_THREADS);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (s_dtype == COVA_F32 && y_dtype == COVA_F32)
+    bn_act_fwd_kernel<float, float><<<grid, BN_THREADS, 0, st>>>((const float*)x, n4, C, mean, invstd, gamma, beta, (const float*)res, relu, (float*)y, nullptr, nullptr, 0);
+  else if (s_dtype == COVA_BF16 && y_dtype == COVA_BF16)
+    bn_act_fwd_kernel<bf16_t, bf16_t><<<grid, BN_THREADS, 0, st>>>((const bf16_t*)x, n4, C, mean, invstd, gamma, beta, (const bf16_t*)res, relu, (bf16_t*)y, nullptr, nullptr, 0);
+  else if (s_dtype == COVA_BF16)
+    bn_act_fwd_kernel<bf16_t, float><<<grid, BN_THREADS, 0, st>>>((const bf16_t*)x, n4, C, mean, invstd, gamma, beta, (const bf16_t*)res, relu, (float*)y, nullptr, nullptr, 0);
+  else
+    COVA_REQUIRE(false, "cova_bn_act_fwd_t: fp32 storage with a bf16 output is not built");
+  COVA_LAUNCH_OK();
+  return COVA_OK;
+}
+
+extern "C" int cova_bn_act_bwd_t(const void* dy, int dy_dtype, const void* x, const void* res, int s_dtype, int64_t M, int C,
+                                 const float* mean, const float* invstd, const float* gamma, const float* beta, int relu,
+                                 double* ws, void* dx, void* dres, float* dgamma, float* dbeta, void* stream) {
+  COVA_REQUIRE(dt_ok(s_dtype) && dt_ok(dy_dtype), "cova_bn_act_bwd_t: dtypes are fp32 or bf16");
+  if (s_dtype == COVA_F32 && dy_dtype == COVA_F32)
+    return cova_bn_act_bwd((const float*)dy, (const float*)x, (const float*)res, M, C, mean, invstd, gamma, beta, relu, ws,
+                           (float*)dx, (float*)dres, dgamma, dbeta, stream);
+  COVA_REQUIRE(s_dtype == COVA_BF16, "cova_bn_act_bwd_t: fp32 storage with a bf16 gradient is not built");
+  COVA_REQUIRE(dy && x && dx && ws && mean && invstd && gamma && beta && M > 0, "cova_bn_act_bwd_t: bad arguments");
+  COVA_REQUIRE(bn_c_ok(C), "cova_bn_act_bwd_t: C=%d must be a power of two in [4, 1024]", C);
+  COVA_REQUIRE((((uintptr_t)x | (uintptr_t)res | (uintptr_t)dx | (uintptr_t)dres) & 7) == 0 &&
+                   ((uintptr_t)dy & (dy_dtype == COVA_F32 ? 15 : 7)) == 0, "cova_bn_act_bwd_t: alignment");
+  cudaStream_t st = (cudaStream_t)stream;
+  COVA_CUDA_OK(cudaMemsetAsync(ws, 0, 2 * C * sizeof(double), st));
+  const int rows = BN_THREADS / (C / 4);
+  const size_t smem = (size_t)2 * rows * C * sizeof(float);
+  int64_t grid = (M + rows - 1) / rows;
+  if (grid > (int64_t)sm_count() * 8) grid = (int64_t)sm_count() * 8;
+  const int64_t n4 = M * (C / 4);
+  const int g2 = ew_grid(n4, BN_THREADS);
+  const bf16_t *xb = (const bf16_t*)x, *rb = (const bf16_t*)res;
+  if (dy_dtype == COVA_BF16) {
+    bn_reduce_kernel<1, bf16_t, bf16_t><<<(int)grid, BN_THREADS, smem, st>>>(xb, (const bf16_t*)dy, rb, M, C, mean, invstd, gamma, beta, relu, ws);
+    COVA_LAUNCH_OK();
+    bn_act_bwd_kernel<false, bf16_t, bf16_t><<<g2, BN_THREADS, 2 * C * sizeof(float), st>>>(
+        (const bf16_t*)dy, xb, rb, n4, M, C, mean, invstd, gamma, beta, relu, ws, (bf16_t*)dx, (bf16_t*)dres, dgamma, dbeta, nullptr,
+        nullptr, nullptr, 0, 0, nullptr);
+  } else {
+    bn_reduce_kernel<1, bf16_t, float><<<(int)grid, BN_THREADS, smem, st>>>(xb, (const float*)dy, rb, M, C, mean, invstd, gamma, beta, relu, ws);
+    COVA_LAUNCH_OK();
+    bn_act_bwd_kernel<false, bf16_t, float><<<g2, BN_THREADS, 2 * C * sizeof(float), st>>>(
+        (const float*)dy, xb, rb, n4, M, C, mean, invstd, gamma, beta, relu, ws, (bf16_t*)dx, (bf16_t*)dres, dgamma, dbeta, nullptr,
+        nullptr, nullptr, 0, 0, nullptr);
+  }
+  COVA_LAUNCH_OK();
+  return COVA_OK;
+}
+
+extern "C" int cova_maxpool3x3s2_fwd_t(const void* x, int dtype, int B, int H, int W, int C, void* y, unsigned char* code,
+                                       void* stream) {
+  if (dtype == COVA_F32) return cova_maxpool3x3s2_fwd((const float*)x, B, H, W, C, (float*)y, code, nullptr, nullptr, COVA_BF16X2, stream);
+  COVA_REQUIRE(dtype == COVA_BF16, "cova_maxpool3x3s2_fwd_t: dtype is fp32 or bf16");
+  COVA_REQUIRE(x && y && B > 0 && H > 0 && W > 0 && C > 0 && C % 4 == 0, "cova_maxpool3x3s2_fwd_t: bad arguments");
+  COVA_REQUIRE((((uintptr_t)x | (uintptr_t)y) & 7) == 0 && ((uintptr_t)code & 3) == 0, "cova_maxpool3x3s2_fwd_t: alignment");
+  const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
+  const int64_t n = (int64_t)B * Ho * Wo * (C / 4);
+  if (n < (1LL << 31))
+    maxpool_fwd_kernel<uint32_t, bf16_t><<<ew_grid(n, 256), 256, 0, (cudaStream_t)stream>>>((const bf16_t*)x, B, H, W, C, Ho, Wo, (bf16_t*)y, code, nullptr, nullptr, 0);
+  else
+    maxpool_fwd_kernel<int64_t, bf16_t><<<ew_grid(n, 256), 256, 0, (cudaStream_t)stream>>>((const bf16_t*)x, B, H, W, C, Ho, Wo, (bf16_t*)y, code, nullptr, nullptr, 0);
+  COVA_LAUNCH_OK();
+  return COVA_OK;
+}
+
+extern "C" int cova_maxpool3x3s2_bwd_t(const unsigned char* code, const void* dy, int dtype, int B, int H, int W, int C, void* dx,
+                                       void* stream) {
+  if (dtype == COVA_F32) return cova_maxpool3x3s2_bwd(code, (const float*)dy, B, H, W, C, (float*)dx, stream);
+  COVA_REQUIRE(dtype == COVA_BF16, "cova_maxpool3x3s2_bwd_t: dtype is fp32 or bf16");
+  COVA_REQUIRE(code && dy && dx && B > 0 && H > 0 && W > 0 && C > 0 && C % 4 == 0, "cova_maxpool3x3s2_bwd_t: bad arguments");
+  COVA_REQUIRE((((uintptr_t)dy | (uintptr_t)dx) & 7) == 0 && ((uintptr_t)code & 3) == 0, "cova_maxpool3x3s2_bwd_t: alignment");
+  const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
+  const int64_t n = (int64_t)B * H * W * (C / 4);
+  if (n < (1LL << 31))
+    maxpool_bwd_kernel<uint32_t, bf16_t><<<ew_grid(n, 256), 256, 0, (cudaStream_t)stream>>>(code, (const bf16_t*)dy, B, H, W, C, Ho, Wo, (bf16_t*)dx);
+  else
+    maxpool_bwd_kernel<int64_t, bf16_t><<<ew_grid(n, 256), 256, 0, (cudaStream_t)stream>>>(code, (const bf16_t*)dy, B, H, W, C, Ho, Wo, (bf16_t*)dx);
   COVA_LAUNCH_OK();
   return COVA_OK;
 }

@@ -39,22 +39,24 @@ struct PwParams {
   void* y1;
 };
 
-template <int KB, int COUT>
+template <int KB, int COUT, bool SINGLE = false>
 struct PwCfg {
-  static constexpr int W_KB_BYTES = 2 * COUT * 128;              // one k-block of the filter: hi rows then lo rows
+  static constexpr int W_KB_BYTES = (SINGLE ? 1 : 2) * COUT * 128;   // one k-block of the filter: hi rows then lo rows
   static constexpr int W_BYTES = KB * W_KB_BYTES;
-  static constexpr int ACC_COLS = COUT == 64 ? 128 : 256;
+  static constexpr int ACC_COLS = COUT == 64 ? (SINGLE ? 64 : 128) : 256;
   static constexpr int TMEM_COLS = 2 * ACC_COLS;
   static constexpr int SMEM = W_BYTES + PW_NSTAGE * PW_STAGE + 2 * COUT * 4 + 1024 + 1024;
 };
 
 // HALF: split-fp16 planes and filter (training path: forward and dgrad in the three-product fp16 mode; the filter comes
 // scaled by SPLIT_F16_WSCALE, which the caller folds into bn_scale); fp32 output, no residual.
-template <int KB, int COUT, int OUT_DTYPE, bool HALF = false>
+// SINGLE (bf16 training mode): one bf16 plane in, one bf16 product, one bf16 plane out (OUT_DTYPE = COVA_BF16): half the
+// bytes of this HBM-bound kernel; the lo maps are not touched.
+template <int KB, int COUT, int OUT_DTYPE, bool HALF = false, bool SINGLE = false>
 __global__ void __launch_bounds__(PW_THREADS, 1)
 pw_tc_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ CUtensorMap tm_x_lo,
              const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo, const PwParams p) {
-  using Cfg = PwCfg<KB, COUT>;
+  using Cfg = PwCfg<KB, COUT, SINGLE>;
   extern __shared__ unsigned char smem_raw[];
   const uint32_t raw_addr = ptx::smem_u32(smem_raw);
   unsigned char* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
@@ -96,7 +98,7 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant_
       ptx::mbar_arrive_expect_tx(&tail.wbar, Cfg::W_BYTES);
       for (int kb = 0; kb < KB; ++kb) {
         ptx::tma_load_2d(sm_w + kb * Cfg::W_KB_BYTES, &tm_w_hi, &tail.wbar, kb * 64, 0);
-        ptx::tma_load_2d(sm_w + kb * Cfg::W_KB_BYTES + COUT * 128, &tm_w_lo, &tail.wbar, kb * 64, 0);
+        if (!SINGLE) ptx::tma_load_2d(sm_w + kb * Cfg::W_KB_BYTES + COUT * 128, &tm_w_lo, &tail.wbar, kb * 64, 0);
       }
     }
     __syncwarp();
@@ -106,9 +108,9 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant_
         ptx::mbar_wait(&tail.empty[stage], phase ^ 1);
         if (ptx::elect_one()) {
           unsigned char* dst = sm_a + stage * PW_STAGE;
-          ptx::mbar_arrive_expect_tx(&tail.full[stage], PW_STAGE);
+          ptx::mbar_arrive_expect_tx(&tail.full[stage], SINGLE ? PW_A_PLANE : PW_STAGE);
           ptx::tma_load_2d(dst, &tm_x_hi, &tail.full[stage], kb * 64, tile * PW_BM);
-          ptx::tma_load_2d(dst + PW_A_PLANE, &tm_x_lo, &tail.full[stage], kb * 64, tile * PW_BM);
+          if (!SINGLE) ptx::tma_load_2d(dst + PW_A_PLANE, &tm_x_lo, &tail.full[stage], kb * 64, tile * PW_BM);
         }
         __syncwarp();
         if (++stage == PW_NSTAGE) { stage = 0; phase ^= 1; }
@@ -138,7 +140,9 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant_
           for (int kk = 0; kk < 4; ++kk) {
             const uint64_t a_hi = da_s + ((kk * 32) >> 4), a_lo = a_hi + (PW_A_PLANE >> 4);
             const uint64_t b_hi = db0 + ((kb * Cfg::W_KB_BYTES + kk * 32) >> 4), b_lo = b_hi + ((COUT * 128) >> 4);
-            if (COUT == 64) {
+            if (SINGLE) {
+              ptx::umma_bf16(d_tmem, a_hi, b_hi, idesc_n, (kb | kk) != 0);
+            } else if (COUT == 64) {
               ptx::umma_bf16(d_tmem, a_hi, b_hi, idesc_2n, (kb | kk) != 0);    // Ahi x [Whi; Wlo] -> 128 columns
               ptx::umma_bf16(d_tmem, a_lo, b_hi, idesc_n, 1);                  // Alo x Whi -> first 64 columns
             } else {
@@ -189,7 +193,7 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant_
         for (int q = 0; q < 2; ++q)
 #pragma unroll
           for (int j = 0; j < 16; ++j) o[q * 16 + j] = __uint_as_float(v[q][j]);
-        if (COUT == 64) {   // columns 64..127 hold Ahi*Wlo
+        if (COUT == 64 && !SINGLE) {   // columns 64..127 hold Ahi*Wlo
 #pragma unroll
           for (int q = 0; q < 2; ++q) ptx::tmem_ld16(taddr + 64 + c0 + q * 16, v[q]);
           ptx::tmem_ld_wait();
@@ -227,6 +231,14 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant_
             for (int e = 0; e < 8; ++e) w8[e] = __float_as_uint(o[j * 8 + e]);
             st_global_v8(dst + j * 8, w8);
           }
+        } else if (OUT_DTYPE == COVA_BF16) {
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            uint32_t hw[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) hw[e] = pack2_bf16(o[j * 16 + 2 * e], o[j * 16 + 2 * e + 1]);
+            st_global_v8(reinterpret_cast<__nv_bfloat16*>(p.y0) + row + c0 + j * 16, hw);
+          }
         } else {
 #pragma unroll
           for (int j = 0; j < 2; ++j) {
@@ -248,11 +260,11 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant_
   }
 }
 
-template <int KB, int COUT, int OUT_DTYPE, bool HALF = false>
+template <int KB, int COUT, int OUT_DTYPE, bool HALF = false, bool SINGLE = false>
 static int launch_pw(const CUtensorMap& xh, const CUtensorMap& xl, const CUtensorMap& wh, const CUtensorMap& wl,
                      const PwParams& p, cudaStream_t st) {
-  using Cfg = PwCfg<KB, COUT>;
-  auto kern = pw_tc_kernel<KB, COUT, OUT_DTYPE, HALF>;
+  using Cfg = PwCfg<KB, COUT, SINGLE>;
+  auto kern = pw_tc_kernel<KB, COUT, OUT_DTYPE, HALF, SINGLE>;
   COVA_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
   const int grid = p.n_tiles < sm_count() ? p.n_tiles : sm_count();
   kern<<<grid, PW_THREADS, Cfg::SMEM, st>>>(xh, xl, wh, wl, p);
@@ -274,8 +286,11 @@ extern "C" int cova_conv1x1_bn_act_fwd(const void* x_hi, const void* x_lo, int64
 }
 
 extern "C" int cova_conv1x1_raw_fwd(const void* x_hi, const void* x_lo, int planes_dtype, int64_t M, int Cin, int Cout,
-                                    const void* w_packed, const float* scale, const float* zero_shift, float* y, void* stream) {
-  COVA_REQUIRE(planes_dtype == COVA_F16X2 || planes_dtype == COVA_BF16X2, "cova_conv1x1_raw_fwd: planes are split-fp16 or split-bf16");
+                                    const void* w_packed, const float* scale, const float* zero_shift, void* y, void* stream) {
+  COVA_REQUIRE(planes_dtype == COVA_F16X2 || planes_dtype == COVA_BF16X2 || planes_dtype == COVA_BF16,
+               "cova_conv1x1_raw_fwd: planes are split-fp16, split-bf16 or one bf16 plane");
+  if (planes_dtype == COVA_BF16)   // bf16 training mode: x_lo unused, w_packed = bf16 [Cout][Cin], y = bf16 rows
+    return pw_run(x_hi, x_hi, M, Cin, Cout, w_packed, scale, zero_shift, nullptr, nullptr, 0, COVA_BF16, y, nullptr, false, stream);
   return pw_run(x_hi, x_lo, M, Cin, Cout, w_packed, scale, zero_shift, nullptr, nullptr, 0, COVA_F32, y, nullptr,
                 planes_dtype == COVA_F16X2, stream);
 }
@@ -287,7 +302,7 @@ static int pw_run(const void* x_hi, const void* x_lo, int64_t M, int Cin, int Co
   COVA_REQUIRE(x_hi && x_lo && w_packed && bn_scale && bn_shift && y0, "cova_conv1x1_bn_act_fwd: null pointer");
   COVA_REQUIRE((Cin == 64 && (Cout == 64 || Cout == 256)) || (Cin == 256 && Cout == 64),
                "cova_conv1x1_bn_act_fwd: built for 64->64, 64->256 and 256->64 (got %d->%d)", Cin, Cout);
-  COVA_REQUIRE(out_dtype == COVA_F32 || (out_dtype == COVA_BF16X2 && y1), "cova_conv1x1_bn_act_fwd: bad output dtype");
+  COVA_REQUIRE(out_dtype == COVA_F32 || out_dtype == COVA_BF16 || (out_dtype == COVA_BF16X2 && y1), "cova_conv1x1_bn_act_fwd: bad output dtype");
   COVA_REQUIRE((res_hi == nullptr) == (res_lo == nullptr), "cova_conv1x1_bn_act_fwd: residual needs both planes");
   COVA_REQUIRE(M >= 0 && M < (int64_t)1 << 31, "cova_conv1x1_bn_act_fwd: M out of range");
   if (M == 0) return COVA_OK;
@@ -301,7 +316,7 @@ static int pw_run(const void* x_hi, const void* x_lo, int64_t M, int Cin, int Co
   if ((rc = make_tmap_bf16(&tx_hi, x_hi, 2, xd, xs, xb))) return rc;
   if ((rc = make_tmap_bf16(&tx_lo, x_lo, 2, xd, xs, xb))) return rc;
   if ((rc = make_tmap_bf16(&tw_hi, wp, 2, wd, ws, wb))) return rc;
-  if ((rc = make_tmap_bf16(&tw_lo, wp + (size_t)Cout * Cin, 2, wd, ws, wb))) return rc;
+  if ((rc = make_tmap_bf16(&tw_lo, out_dtype == COVA_BF16 ? wp : wp + (size_t)Cout * Cin, 2, wd, ws, wb))) return rc;
   PwParams p;
   p.M = (int)M;
   p.n_tiles = ceil_div((int)M, PW_BM);
@@ -310,7 +325,8 @@ static int pw_run(const void* x_hi, const void* x_lo, int64_t M, int Cin, int Co
   p.res_hi = (const __nv_bfloat16*)res_hi; p.res_lo = (const __nv_bfloat16*)res_lo;
   p.y0 = y0; p.y1 = y1;
   cudaStream_t st = (cudaStream_t)stream;
-#define GO(KB, CO) (half ? launch_pw<KB, CO, COVA_F32, true>(tx_hi, tx_lo, tw_hi, tw_lo, p, st)          \
+#define GO(KB, CO) (out_dtype == COVA_BF16 ? launch_pw<KB, CO, COVA_BF16, false, true>(tx_hi, tx_lo, tw_hi, tw_lo, p, st) \
+                    : half ? launch_pw<KB, CO, COVA_F32, true>(tx_hi, tx_lo, tw_hi, tw_lo, p, st)          \
                     : out_dtype == COVA_F32 ? launch_pw<KB, CO, COVA_F32>(tx_hi, tx_lo, tw_hi, tw_lo, p, st) \
                                             : launch_pw<KB, CO, COVA_BF16X2>(tx_hi, tx_lo, tw_hi, tw_lo, p, st))
   if (Cin == 64 && Cout == 64) return GO(1, 64);

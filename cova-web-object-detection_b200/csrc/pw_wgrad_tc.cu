@@ -28,6 +28,7 @@ struct PwgTail {
 
 struct PwgParams {
   int M, n_tiles, drain_every;
+  int single;                                       // bf16 training mode: one plane per operand - lo atoms zero-filled once, never loaded
   float* ws;                                        // [Cin][Cout] fp32, zeroed
 };
 
@@ -84,6 +85,14 @@ pw_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_con
     ptx::tmem_alloc(&tail.tmem_base, Cfg::TMEM_COLS);
     ptx::tmem_relinquish();
   }
+  if (p.single) {
+    for (int st = 0; st < Cfg::NSTAGE; ++st)
+      for (int a = 0; a < CIB + COB; ++a) {
+        uint4* lo = reinterpret_cast<uint4*>(smem + st * Cfg::STAGE_BYTES + (a * 2 + 1) * PWG_ATOM);
+        for (int i = threadIdx.x; i < PWG_ATOM / 16; i += PWG_THREADS) lo[i] = make_uint4(0u, 0u, 0u, 0u);
+      }
+    ptx::fence_proxy_async();
+  }
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
@@ -96,16 +105,16 @@ pw_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_con
       ptx::mbar_wait(&tail.empty[stage], phase ^ 1);
       if (ptx::elect_one()) {
         unsigned char* s = smem + stage * Cfg::STAGE_BYTES;
-        ptx::mbar_arrive_expect_tx(&tail.full[stage], Cfg::STAGE_BYTES);
+        ptx::mbar_arrive_expect_tx(&tail.full[stage], p.single ? Cfg::STAGE_BYTES / 2 : Cfg::STAGE_BYTES);
 #pragma unroll
         for (int cb = 0; cb < CIB; ++cb) {
           ptx::tma_load_2d(s + (cb * 2) * PWG_ATOM, &tm_x_hi, &tail.full[stage], cb * 64, tile * PWG_BM);
-          ptx::tma_load_2d(s + (cb * 2 + 1) * PWG_ATOM, &tm_x_lo, &tail.full[stage], cb * 64, tile * PWG_BM);
+          if (!p.single) ptx::tma_load_2d(s + (cb * 2 + 1) * PWG_ATOM, &tm_x_lo, &tail.full[stage], cb * 64, tile * PWG_BM);
         }
 #pragma unroll
         for (int nb = 0; nb < COB; ++nb) {
           ptx::tma_load_2d(s + Cfg::X_BYTES + (nb * 2) * PWG_ATOM, &tm_dy_hi, &tail.full[stage], nb * 64, tile * PWG_BM);
-          ptx::tma_load_2d(s + Cfg::X_BYTES + (nb * 2 + 1) * PWG_ATOM, &tm_dy_lo, &tail.full[stage], nb * 64, tile * PWG_BM);
+          if (!p.single) ptx::tma_load_2d(s + Cfg::X_BYTES + (nb * 2 + 1) * PWG_ATOM, &tm_dy_lo, &tail.full[stage], nb * 64, tile * PWG_BM);
         }
       }
       __syncwarp();
@@ -216,10 +225,12 @@ static int launch_pwg(const CUtensorMap& xh, const CUtensorMap& xl, const CUtens
 extern "C" int cova_conv1x1_wgrad(const void* x_hi, const void* x_lo, const void* dy_hi, const void* dy_lo, int64_t M, int Cin,
                                   int Cout, int planes_dtype, const float* inv_scale, float* ws, float* dw, void* stream) {
   using namespace cova;
-  COVA_REQUIRE(x_hi && x_lo && dy_hi && dy_lo && ws && dw, "cova_conv1x1_wgrad: null pointer");
+  COVA_REQUIRE(x_hi && dy_hi && ws && dw, "cova_conv1x1_wgrad: null pointer");
+  COVA_REQUIRE(planes_dtype == COVA_BF16 || (x_lo && dy_lo), "cova_conv1x1_wgrad: split planes need their lo plane");
   COVA_REQUIRE((Cin == 64 && (Cout == 64 || Cout == 256)) || (Cin == 256 && Cout == 64),
                "cova_conv1x1_wgrad: built for 64->64, 64->256 and 256->64 (got %d->%d)", Cin, Cout);
-  COVA_REQUIRE(planes_dtype == COVA_F16X2 || planes_dtype == COVA_BF16X2, "cova_conv1x1_wgrad: planes are split-fp16 or split-bf16");
+  COVA_REQUIRE(planes_dtype == COVA_F16X2 || planes_dtype == COVA_BF16X2 || planes_dtype == COVA_BF16,
+               "cova_conv1x1_wgrad: planes are split-fp16, split-bf16 or single bf16 planes (x_lo = dy_lo = NULL)");
   COVA_REQUIRE(M > 0 && M < (int64_t)1 << 31, "cova_conv1x1_wgrad: M out of range");
   cudaStream_t st = (cudaStream_t)stream;
   CUtensorMap tx_hi, tx_lo, td_hi, td_lo;
@@ -228,15 +239,16 @@ extern "C" int cova_conv1x1_wgrad(const void* x_hi, const void* x_lo, const void
   const uint32_t bx[2] = {64, PWG_BM};
   int rc;
   if ((rc = make_tmap_bf16(&tx_hi, x_hi, 2, xd, xs, bx))) return rc;
-  if ((rc = make_tmap_bf16(&tx_lo, x_lo, 2, xd, xs, bx))) return rc;
+  if ((rc = make_tmap_bf16(&tx_lo, x_lo ? x_lo : x_hi, 2, xd, xs, bx))) return rc;
   if ((rc = make_tmap_bf16(&td_hi, dy_hi, 2, dd, ds, bx))) return rc;
-  if ((rc = make_tmap_bf16(&td_lo, dy_lo, 2, dd, ds, bx))) return rc;
+  if ((rc = make_tmap_bf16(&td_lo, dy_lo ? dy_lo : dy_hi, 2, dd, ds, bx))) return rc;
   PwgParams p;
   p.M = (int)M;
   p.n_tiles = ceil_div((int)M, PWG_BM);
   p.drain_every = 2 * knob(COVA_KNOB_WGRAD_DRAIN, 16);
   if (p.drain_every < 1) p.drain_every = 1;
   p.ws = ws;
+  p.single = planes_dtype == COVA_BF16;
   COVA_CUDA_OK(cudaMemsetAsync(ws, 0, (size_t)Cin * Cout * sizeof(float), st));
   const bool half = planes_dtype == COVA_F16X2;
   if (Cin == 64 && Cout == 64) rc = launch_pwg<1, 1>(tx_hi, tx_lo, td_hi, td_lo, p, half, st);

@@ -66,6 +66,7 @@ struct StemTcParams {
   void* out0;
   void* out1;
   float* raw_out;                          // training mode: un-normalised, un-pooled conv output [B,Hc,Wc,64] fp32 (or NULL)
+  int raw_bf16;                            // ... stored as bf16 instead (the bf16 training mode)
   unsigned long long* dbg;                 // optional wait-cycle counters (cova_debug_buffer), 8 words per CTA
   int pf_rows;                             // converter warps L2-prefetch the image row they will load this many turns ahead
 };
@@ -239,7 +240,13 @@ stem_tc_kernel(const StemTcParams p) {
         if (p.raw_out != nullptr) {
           // training mode (BatchNorm needs batch statistics of THIS tensor): write the raw conv row and skip the
           // pooling.  A band recomputes the conv row above it as pooling halo; only the owner band writes a row.
-          if (oy >= 2 * py0 && ox < p.Wc) {
+          if (oy >= 2 * py0 && ox < p.Wc && p.raw_bf16) {
+            __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.raw_out) + (((size_t)b * p.Hc + oy) * p.Wc + ox) * 64 + ch0;
+#pragma unroll
+            for (int hlf = 0; hlf < SX_CH / 8; ++hlf)
+              *reinterpret_cast<uint4*>(dst + hlf * 8) = make_uint4(pack2_bf16(v[hlf * 8], v[hlf * 8 + 1]), pack2_bf16(v[hlf * 8 + 2], v[hlf * 8 + 3]),
+                                                                    pack2_bf16(v[hlf * 8 + 4], v[hlf * 8 + 5]), pack2_bf16(v[hlf * 8 + 6], v[hlf * 8 + 7]));
+          } else if (oy >= 2 * py0 && ox < p.Wc) {
             float* dst = p.raw_out + (((size_t)b * p.Hc + oy) * p.Wc + ox) * 64 + ch0;
 #pragma unroll
             for (int hlf = 0; hlf < SX_CH / 8; ++hlf) {
@@ -535,9 +542,10 @@ static int launch_stem_tc(const StemTcParams& p, int grid, cudaStream_t st) {
 
 static int stem_tc_impl(const void* images, int img_u8, int B, int H, int W, const void* w_packed, const float* bn_scale,
                         const float* bn_shift, int out_dtype, void* out0, void* out1, cudaStream_t st, float* raw_out,
-                        bool split_f16 = false) {
+                        bool split_f16 = false, bool raw_bf16 = false) {
   StemTcParams p;
   p.raw_out = raw_out;
+  p.raw_bf16 = raw_bf16 ? 1 : 0;
   p.img = images; p.B = B; p.H = H; p.W = W;
   p.Hc = (H + 6 - 7) / 2 + 1; p.Wc = (W + 6 - 7) / 2 + 1;
   p.Hp = (p.Hc + 2 - 3) / 2 + 1; p.Wp = (p.Wc + 2 - 3) / 2 + 1;
@@ -607,6 +615,16 @@ extern "C" int cova_stem_conv_raw_fwd(const void* images, int img_dtype, int B, 
   COVA_REQUIRE(((uintptr_t)out & 31) == 0, "cova_stem_conv_raw_fwd: out must be 32-byte aligned");
   return cova::stem_tc_impl(images, img_dtype == COVA_U8, B, H, W, w_packed, nullptr, nullptr, COVA_F32, out, nullptr,
                             (cudaStream_t)stream, out, w_dtype == COVA_F16X2);
+}
+
+// bf16 training mode: conv1 in one bf16 product (filter from cova_pack_stem_weight: its hi plane), raw output stored as bf16
+extern "C" int cova_stem_conv_raw_fwd_bf16(const void* images, int img_dtype, int B, int H, int W, const void* w_packed,
+                                           void* out_bf16, void* stream) {
+  COVA_REQUIRE(images && w_packed && out_bf16 && B > 0 && H >= 7 && W >= 7, "cova_stem_conv_raw_fwd_bf16: bad arguments");
+  COVA_REQUIRE(img_dtype == COVA_F32 || img_dtype == COVA_U8, "cova_stem_conv_raw_fwd_bf16: images must be fp32 or uint8");
+  COVA_REQUIRE(((uintptr_t)out_bf16 & 15) == 0, "cova_stem_conv_raw_fwd_bf16: out must be 16-byte aligned");
+  return cova::stem_tc_impl(images, img_dtype == COVA_U8, B, H, W, w_packed, nullptr, nullptr, COVA_BF16, out_bf16, nullptr,
+                            (cudaStream_t)stream, reinterpret_cast<float*>(out_bf16), false, true);
 }
 
 extern "C" int cova_pack_stem_weight_f16x2(const float* w_oihw, void* packed, void* stream) {

@@ -56,6 +56,7 @@ struct StemWgradParams {
   const void* img;
   int B, H, W, Hc, Wc;
   int bands_per_page, rows_per_band, drain_every;
+  int dy_single;                           // bf16 training mode: dY is one bf16 plane - the lo slots are zero-filled once
   float* ws;                               // [64 co][224 = r*32 + s*4 + c] fp32, zeroed
 };
 
@@ -123,6 +124,13 @@ stem_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_dy_hi, const __grid_
     ptx::tmem_alloc(&sm.tmem_base, SW_TMEM_COLS);
     ptx::tmem_relinquish();
   }
+  if (p.dy_single) {
+    for (int st = 0; st < SW_NS; ++st) {
+      uint4* lo = reinterpret_cast<uint4*>(sm.dy[st] + SW_DY_PLANE);
+      for (int i = threadIdx.x; i < SW_DY_PLANE / 16; i += SW_THREADS) lo[i] = make_uint4(0u, 0u, 0u, 0u);
+    }
+    ptx::fence_proxy_async();
+  }
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
@@ -184,9 +192,9 @@ stem_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_dy_hi, const __grid_
         const uint32_t stage = t % SW_NS;
         ptx::mbar_wait(&sm.dy_empty[stage], ((t / SW_NS) & 1) ^ 1);
         if (ptx::elect_one()) {
-          ptx::mbar_arrive_expect_tx(&sm.dy_full[stage], SW_DY_STAGE);
+          ptx::mbar_arrive_expect_tx(&sm.dy_full[stage], p.dy_single ? SW_DY_PLANE : SW_DY_STAGE);
           ptx::tma_load_4d(sm.dy[stage], &tm_dy_hi, &sm.dy_full[stage], 0, strip * SW_TM, oy_begin + i, b);
-          ptx::tma_load_4d(sm.dy[stage] + SW_DY_PLANE, &tm_dy_lo, &sm.dy_full[stage], 0, strip * SW_TM, oy_begin + i, b);
+          if (!p.dy_single) ptx::tma_load_4d(sm.dy[stage] + SW_DY_PLANE, &tm_dy_lo, &sm.dy_full[stage], 0, strip * SW_TM, oy_begin + i, b);
         }
         __syncwarp();
       }
@@ -336,10 +344,12 @@ __global__ void stem_wgrad_finalize_kernel(const float* __restrict__ ws, const f
 extern "C" int cova_stem_wgrad(const void* images, int img_dtype, int B, int H, int W, const void* dy_hi, const void* dy_lo,
                                int planes_dtype, const float* inv_scale, float* ws, float* dw_oihw, void* stream) {
   using namespace cova;
-  COVA_REQUIRE(images && dy_hi && dy_lo && ws && dw_oihw, "cova_stem_wgrad: null pointer");
+  COVA_REQUIRE(images && dy_hi && ws && dw_oihw, "cova_stem_wgrad: null pointer");
+  COVA_REQUIRE(planes_dtype == COVA_BF16 || dy_lo, "cova_stem_wgrad: split planes need their lo plane");
   COVA_REQUIRE(B > 0 && H >= 7 && W >= 7, "cova_stem_wgrad: bad dims");
   COVA_REQUIRE(img_dtype == COVA_F32 || img_dtype == COVA_U8, "cova_stem_wgrad: images must be fp32 or uint8");
-  COVA_REQUIRE(planes_dtype == COVA_F16X2 || planes_dtype == COVA_BF16X2, "cova_stem_wgrad: planes are split-fp16 or split-bf16");
+  COVA_REQUIRE(planes_dtype == COVA_F16X2 || planes_dtype == COVA_BF16X2 || planes_dtype == COVA_BF16,
+               "cova_stem_wgrad: planes are split-fp16, split-bf16 or one bf16 plane (dy_lo NULL)");
   COVA_REQUIRE((((uintptr_t)dy_hi | (uintptr_t)dy_lo | (uintptr_t)ws) & 15) == 0, "cova_stem_wgrad: 16-byte alignment");
   cudaStream_t st = (cudaStream_t)stream;
   StemWgradParams p;
@@ -360,13 +370,14 @@ extern "C" int cova_stem_wgrad(const void* images, int img_dtype, int B, int H, 
   p.drain_every = knob(COVA_KNOB_WGRAD_DRAIN, 16);
   if (p.drain_every < 1) p.drain_every = 1;
   p.ws = ws;
+  p.dy_single = dy_lo == nullptr;
   CUtensorMap td_hi, td_lo;
   const uint64_t xd[4] = {64, (uint64_t)p.Wc, (uint64_t)p.Hc, (uint64_t)B};
   const uint64_t xs[3] = {128, (uint64_t)p.Wc * 128, (uint64_t)p.Hc * p.Wc * 128};
   const uint32_t db[4] = {64, SW_TM, 1, 1};
   int rc;
   if ((rc = make_tmap_bf16(&td_hi, dy_hi, 4, xd, xs, db))) return rc;
-  if ((rc = make_tmap_bf16(&td_lo, dy_lo, 4, xd, xs, db))) return rc;
+  if ((rc = make_tmap_bf16(&td_lo, dy_lo ? dy_lo : dy_hi, 4, xd, xs, db))) return rc;
   COVA_CUDA_OK(cudaMemsetAsync(ws, 0, (size_t)SW_WS * sizeof(float), st));
   const int smem = (int)sizeof(StemWgradSmem) + 1024;
   const int grid = B * p.bands_per_page;

@@ -54,6 +54,7 @@ struct WgradTail {
 
 struct WgradParams {
   int B, H, W, tiles_w, tiles_h, n_tiles, drain_every;
+  int x_single, dy_single;   // bf16 training mode: an operand is ONE plane - its lo slots are zero-filled once and never loaded
   float* ws;   // [9][64 ci][64 co] fp32, zeroed
 };
 
@@ -107,6 +108,15 @@ conv3x3_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __gri
     ptx::tmem_alloc(&tail.tmem_base, WG_TMEM_COLS);
     ptx::tmem_relinquish();
   }
+  if (p.x_single || p.dy_single) {
+    for (int st = 0; st < WG_NSTAGE; ++st) {
+      uint4* xl = reinterpret_cast<uint4*>(smem + st * WG_STAGE_BYTES + WG_PATCH_SLOT);
+      uint4* dl = reinterpret_cast<uint4*>(smem + st * WG_STAGE_BYTES + 2 * WG_PATCH_SLOT + WG_DY_BYTES);
+      if (p.x_single) for (int i = threadIdx.x; i < WG_PATCH_SLOT / 16; i += WG_THREADS) xl[i] = make_uint4(0u, 0u, 0u, 0u);
+      if (p.dy_single) for (int i = threadIdx.x; i < WG_DY_BYTES / 16; i += WG_THREADS) dl[i] = make_uint4(0u, 0u, 0u, 0u);
+    }
+    ptx::fence_proxy_async();
+  }
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
@@ -122,11 +132,11 @@ conv3x3_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __gri
       ptx::mbar_wait(&tail.empty[stage], phase ^ 1);
       if (ptx::elect_one()) {
         unsigned char* s = smem + stage * WG_STAGE_BYTES;
-        ptx::mbar_arrive_expect_tx(&tail.full[stage], WG_STAGE_TX);
+        ptx::mbar_arrive_expect_tx(&tail.full[stage], (p.x_single ? 1 : 2) * WG_PATCH_BYTES + (p.dy_single ? 1 : 2) * WG_DY_BYTES);
         ptx::tma_load_4d(s, &tm_x_hi, &tail.full[stage], 0, w0 - 1, h0 - 1, b);
-        ptx::tma_load_4d(s + WG_PATCH_SLOT, &tm_x_lo, &tail.full[stage], 0, w0 - 1, h0 - 1, b);
+        if (!p.x_single) ptx::tma_load_4d(s + WG_PATCH_SLOT, &tm_x_lo, &tail.full[stage], 0, w0 - 1, h0 - 1, b);
         ptx::tma_load_4d(s + 2 * WG_PATCH_SLOT, &tm_dy_hi, &tail.full[stage], 0, w0, h0, b);
-        ptx::tma_load_4d(s + 2 * WG_PATCH_SLOT + WG_DY_BYTES, &tm_dy_lo, &tail.full[stage], 0, w0, h0, b);
+        if (!p.dy_single) ptx::tma_load_4d(s + 2 * WG_PATCH_SLOT + WG_DY_BYTES, &tm_dy_lo, &tail.full[stage], 0, w0, h0, b);
       }
       __syncwarp();
       if (++stage == WG_NSTAGE) { stage = 0; phase ^= 1; }
@@ -246,9 +256,11 @@ int launch_wgrad_finalize(const float* ws, const float* inv_scale, float mult, i
 extern "C" int cova_conv3x3_wgrad(const void* x_hi, const void* x_lo, const void* dy_hi, const void* dy_lo, int B, int H, int W,
                                   int planes_dtype, const float* inv_scale, float* ws, float* dw_oihw, void* stream) {
   using namespace cova;
-  COVA_REQUIRE(x_hi && x_lo && dy_hi && dy_lo && ws && dw_oihw, "cova_conv3x3_wgrad: null pointer");
+  COVA_REQUIRE(x_hi && dy_hi && ws && dw_oihw, "cova_conv3x3_wgrad: null pointer");
   COVA_REQUIRE(B > 0 && H > 0 && W > 0, "cova_conv3x3_wgrad: bad dims");
-  COVA_REQUIRE(planes_dtype == COVA_F16X2 || planes_dtype == COVA_BF16X2, "cova_conv3x3_wgrad: planes are split-fp16 or split-bf16");
+  COVA_REQUIRE(planes_dtype == COVA_F16X2 || planes_dtype == COVA_BF16X2 || planes_dtype == COVA_BF16,
+               "cova_conv3x3_wgrad: planes are split-fp16, split-bf16 or single bf16 planes (x_lo / dy_lo NULL)");
+  COVA_REQUIRE(planes_dtype == COVA_BF16 || (x_lo && dy_lo), "cova_conv3x3_wgrad: split planes need their lo plane");
   COVA_REQUIRE((((uintptr_t)x_hi | (uintptr_t)x_lo | (uintptr_t)dy_hi | (uintptr_t)dy_lo | (uintptr_t)ws) & 15) == 0,
                "cova_conv3x3_wgrad: 16-byte alignment");
   cudaStream_t st = (cudaStream_t)stream;
@@ -259,9 +271,9 @@ extern "C" int cova_conv3x3_wgrad(const void* x_hi, const void* x_lo, const void
   const uint32_t db[4] = {WG_C, WG_TW, WG_TH, 1};
   int rc;
   if ((rc = make_tmap_bf16(&tx_hi, x_hi, 4, xd, xs, xb))) return rc;
-  if ((rc = make_tmap_bf16(&tx_lo, x_lo, 4, xd, xs, xb))) return rc;
+  if ((rc = make_tmap_bf16(&tx_lo, x_lo ? x_lo : x_hi, 4, xd, xs, xb))) return rc;
   if ((rc = make_tmap_bf16(&td_hi, dy_hi, 4, xd, xs, db))) return rc;
-  if ((rc = make_tmap_bf16(&td_lo, dy_lo, 4, xd, xs, db))) return rc;
+  if ((rc = make_tmap_bf16(&td_lo, dy_lo ? dy_lo : dy_hi, 4, xd, xs, db))) return rc;
   WgradParams p;
   p.B = B; p.H = H; p.W = W;
   p.tiles_w = ceil_div(W, WG_TW);
@@ -270,6 +282,7 @@ extern "C" int cova_conv3x3_wgrad(const void* x_hi, const void* x_lo, const void
   p.drain_every = knob(COVA_KNOB_WGRAD_DRAIN, 16);
   if (p.drain_every < 1) p.drain_every = 1;
   p.ws = ws;
+  p.x_single = x_lo == nullptr; p.dy_single = dy_lo == nullptr;
   COVA_CUDA_OK(cudaMemsetAsync(ws, 0, (size_t)9 * WG_C * WG_C * sizeof(float), st));
   static_assert(sizeof(WgradTail) <= 1024, "tail too large");
   const int grid = p.n_tiles < sm_count() ? p.n_tiles : sm_count();

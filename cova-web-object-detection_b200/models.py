@@ -443,7 +443,7 @@ class CoVA(nn.Module):
             images = images.float().div(255)
         if self.training and os.environ.get("COVA_B200_TRAIN_BACKBONE", "native") != "torch":
             from .train_backbone import feature_map_train          # NHWC end to end, native BatchNorm / maxpool
-            fm = feature_map_train(self.convnet, images)
+            fm = feature_map_train(self.convnet, images, self.precision)
         else:
             fm = self.convnet(images).permute(0, 2, 3, 1)            # NCHW -> NHWC view for the native RoI kernel
         if self.roi_mode == "pool":

@@ -422,7 +422,7 @@ def conv3x3_wgrad(x_planes, dy_planes, inv_scale=None):
     dev = x_planes.p0.device
     ws = torch.empty(9 * 64 * 64, dtype=torch.float32, device=dev)
     dw = torch.empty((64, 64, 3, 3), dtype=torch.float32, device=dev)
-    _call("cova_conv3x3_wgrad", x_planes.p0.data_ptr(), x_planes.p1.data_ptr(), dy_planes.p0.data_ptr(), dy_planes.p1.data_ptr(),
+    _call("cova_conv3x3_wgrad", x_planes.p0.data_ptr(), _ptr(x_planes.p1), dy_planes.p0.data_ptr(), _ptr(dy_planes.p1),
           B, H, W, x_planes.dtype, _ptr(inv_scale), ws.data_ptr(), dw.data_ptr(), _stream())
     return dw
 
@@ -447,16 +447,32 @@ def _inv256(device):
     return _W256[k]
 
 
+_ONES256 = {}
+
+
+def _ones256(device):
+    k = str(device)
+    if k not in _ONES256:
+        _ONES256[k] = (torch.ones(256, device=device), torch.zeros(256, device=device))
+    return _ONES256[k]
+
+
 def conv1x1_raw_fwd(x_planes, w_packed, scale=None):
     """1x1 convolution of split-fp16 NHWC planes [..., Cin] with `pack_linear_weight_f16x2(w [Cout,Cin])` -> raw fp32
     [..., Cout].  `scale` ([>= Cout] device floats, e.g. the 1/s of scaled gradient planes) multiplies the result."""
     Cin = x_planes.shape[-1]
-    Cout = w_packed.shape[1]
+    Cout = w_packed.shape[-2]
     M = 1
     for d in x_planes.shape[:-1]:
         M *= d
     dev = x_planes.p0.device
     inv, zero = _inv256(dev)
+    if x_planes.dtype == BF16:           # bf16 training mode: w_packed = bf16 [Cout, Cin] (unscaled), bf16 rows out
+        one, _ = _ones256(dev)
+        y = torch.empty(tuple(x_planes.shape[:-1]) + (Cout,), dtype=torch.bfloat16, device=dev)
+        _call("cova_conv1x1_raw_fwd", x_planes.p0.data_ptr(), 0, BF16, M, Cin, Cout, w_packed.data_ptr(), one.data_ptr(),
+              zero.data_ptr(), y.data_ptr(), _stream())
+        return y
     sc = inv if scale is None else scale[:256] * (1.0 / 256.0)
     y = torch.empty(tuple(x_planes.shape[:-1]) + (Cout,), dtype=torch.float32, device=dev)
     _call("cova_conv1x1_raw_fwd", x_planes.p0.data_ptr(), x_planes.p1.data_ptr(), x_planes.dtype, M, Cin, Cout,
@@ -473,7 +489,7 @@ def conv1x1_wgrad(x_planes, dy_planes, inv_scale=None):
     dev = x_planes.p0.device
     ws = torch.empty(Cin * Cout, dtype=torch.float32, device=dev)
     dw = torch.empty((Cout, Cin, 1, 1), dtype=torch.float32, device=dev)
-    _call("cova_conv1x1_wgrad", x_planes.p0.data_ptr(), x_planes.p1.data_ptr(), dy_planes.p0.data_ptr(), dy_planes.p1.data_ptr(),
+    _call("cova_conv1x1_wgrad", x_planes.p0.data_ptr(), _ptr(x_planes.p1), dy_planes.p0.data_ptr(), _ptr(dy_planes.p1),
           M, Cin, Cout, x_planes.dtype, _ptr(inv_scale), ws.data_ptr(), dw.data_ptr(), _stream())
     return dw
 
@@ -497,13 +513,13 @@ def stem_wgrad(images, dy_planes, inv_scale=None):
     images = images.contiguous()
     B, C, H, W = images.shape
     Hc, Wc = (H - 1) // 2 + 1, (W - 1) // 2 + 1
-    if C != 3 or tuple(dy_planes.shape) != (B, Hc, Wc, 64) or dy_planes.dtype not in (F16X2, BF16X2):
+    if C != 3 or tuple(dy_planes.shape) != (B, Hc, Wc, 64) or dy_planes.dtype not in (F16X2, BF16X2, BF16):
         raise RuntimeError("cova_b200: stem_wgrad needs [B,3,H,W] images and [B,H/2,W/2,64] split planes of dy")
     dev = images.device
     ws = torch.empty(64 * 224, dtype=torch.float32, device=dev)
     dw = torch.empty((64, 3, 7, 7), dtype=torch.float32, device=dev)
     _call("cova_stem_wgrad", images.data_ptr(), U8 if images.dtype == torch.uint8 else F32, B, H, W, dy_planes.p0.data_ptr(),
-          dy_planes.p1.data_ptr(), dy_planes.dtype, _ptr(inv_scale), ws.data_ptr(), dw.data_ptr(), _stream())
+          _ptr(dy_planes.p1), dy_planes.dtype, _ptr(inv_scale), ws.data_ptr(), dw.data_ptr(), _stream())
     return dw
 
 
@@ -620,3 +636,91 @@ def bn_relu_pool_bwd(x, code, dy_pooled, mean, invstd, gamma, beta):
           invstd.data_ptr(), gamma.data_ptr(), beta.data_ptr(), ws.data_ptr(), dx.data_ptr(), dg.data_ptr(), db.data_ptr(),
           _stream())
     return dx, dg, db
+
+
+# ----------------------------------------------------------------------------- bf16 training mode (typed entry points)
+def _dt(t):
+    if t.dtype == torch.float32:
+        return F32
+    if t.dtype == torch.bfloat16:
+        return BF16
+    raise RuntimeError("cova_b200: maps of the training path are fp32 or bf16")
+
+
+def _map(t, name):
+    if not t.is_cuda or not t.is_contiguous():
+        raise RuntimeError(f"cova_b200: `{name}` must be a contiguous CUDA NHWC tensor")
+    return t
+
+
+def stem_conv_raw_fwd_bf16(images, w_packed):
+    """conv1 in one bf16 product: images [B,3,H,W] fp32 / uint8 -> raw conv output [B,H/2,W/2,64] bf16 NHWC."""
+    _cuda(images, None, "images")
+    images = images.contiguous()
+    B, C, H, W = images.shape
+    out = torch.empty((B, (H - 1) // 2 + 1, (W - 1) // 2 + 1, 64), dtype=torch.bfloat16, device=images.device)
+    _call("cova_stem_conv_raw_fwd_bf16", images.data_ptr(), U8 if images.dtype == torch.uint8 else F32, B, H, W,
+          w_packed.data_ptr(), out.data_ptr(), _stream())
+    return out
+
+
+def bn_train_fwd_t(x, gamma, beta, running_mean, running_var, momentum, eps, res=None, relu=True, out_dtype=None):
+    """`bn_train_fwd` on a map of either storage type (fp32 / bf16); y in `out_dtype` (default: x's).  Returns (y, mean, invstd)."""
+    _map(x, "x")
+    C = x.shape[-1]
+    M = x.numel() // C
+    dev = x.device
+    ws = torch.empty(2 * C, dtype=torch.float64, device=dev)
+    mean, inv = torch.empty(C, dtype=torch.float32, device=dev), torch.empty(C, dtype=torch.float32, device=dev)
+    y = torch.empty(x.shape, dtype=out_dtype or x.dtype, device=dev)
+    if res is not None and _map(res, "res").dtype != x.dtype:
+        raise RuntimeError("cova_b200: the residual has the storage type of x")
+    _call("cova_bn_train_stats_t", x.data_ptr(), _dt(x), M, C, ws.data_ptr(), _stream())
+    _call("cova_bn_train_finalize", ws.data_ptr(), M, C, float(eps), float(momentum), mean.data_ptr(), inv.data_ptr(),
+          _ptr(running_mean), _ptr(running_var), _stream())
+    if running_mean is not None:
+        global param_generation
+        param_generation += 1
+    _call("cova_bn_act_fwd_t", x.data_ptr(), _dt(x), M, C, mean.data_ptr(), inv.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
+          _ptr(res), int(relu), y.data_ptr(), _dt(y), _stream())
+    return y, mean, inv
+
+
+def bn_train_bwd_t(dy, x, mean, invstd, gamma, beta, res=None, relu=True, want_dres=False):
+    """Backward of `bn_train_fwd_t`: dx / dres in x's storage type; dy fp32 or bf16.  Returns (dx, dres | None, dgamma, dbeta)."""
+    _map(dy, "dy"); _map(x, "x")
+    C = x.shape[-1]
+    M = x.numel() // C
+    dev = x.device
+    ws = torch.empty(2 * C, dtype=torch.float64, device=dev)
+    dx = torch.empty_like(x)
+    dres = torch.empty_like(x) if want_dres else None
+    dg, db = torch.empty(C, dtype=torch.float32, device=dev), torch.empty(C, dtype=torch.float32, device=dev)
+    _call("cova_bn_act_bwd_t", dy.data_ptr(), _dt(dy), x.data_ptr(), _ptr(res), _dt(x), M, C, mean.data_ptr(), invstd.data_ptr(),
+          gamma.data_ptr(), beta.data_ptr(), int(relu), ws.data_ptr(), dx.data_ptr(), _ptr(dres), dg.data_ptr(), db.data_ptr(),
+          _stream())
+    return dx, dres, dg, db
+
+
+def maxpool3x3s2_fwd_t(x):
+    _map(x, "x")
+    B, H, W, C = x.shape
+    y = torch.empty((B, (H - 1) // 2 + 1, (W - 1) // 2 + 1, C), dtype=x.dtype, device=x.device)
+    code = torch.empty(y.shape, dtype=torch.uint8, device=x.device)
+    _call("cova_maxpool3x3s2_fwd_t", x.data_ptr(), _dt(x), B, H, W, C, y.data_ptr(), code.data_ptr(), _stream())
+    return y, code
+
+
+def maxpool3x3s2_bwd_t(code, dy, in_shape):
+    _map(dy, "dy")
+    B, H, W, C = in_shape
+    dx = torch.empty(in_shape, dtype=dy.dtype, device=dy.device)
+    _call("cova_maxpool3x3s2_bwd_t", code.data_ptr(), dy.data_ptr(), _dt(dy), B, H, W, C, dx.data_ptr(), _stream())
+    return dx
+
+
+def bf16_plane(t):
+    """A contiguous bf16 NHWC tensor as single-plane `Planes` (the operand format of the bf16 training mode)."""
+    pl = Planes.__new__(Planes)
+    pl.dtype, pl.shape, pl.p0, pl.p1 = BF16, tuple(t.shape), t, None
+    return pl

@@ -407,6 +407,59 @@ def _unit_bwd(u, dy, need_dx=True):
     return dx, dw, dg, db, dres
 
 
+def _unit_fwd16(kind, xin, conv, bn, res=None, relu=True, out_fp32=False):
+    """bf16 training mode (BASELINE config 3): the unit with every map stored as bf16 - raw convolution output, y (one bf16
+    plane = the operand of the next convolution, one product per MMA) - statistics / parameters fp32.  xin = images (stem)
+    or the bf16 NHWC input map.  out_fp32: y as fp32 (the final feature map, read by RoIPool)."""
+    u = _Unit()
+    u.kind, u.xin, u.weight, u.bn, u.relu, u.has_res = kind, xin, conv.weight, bn, relu, res is not None
+    w = conv.weight.detach().float()
+    if kind == "stem":
+        u.raw = ops.stem_conv_raw_fwd_bf16(xin, ops.pack_stem_weight(w.contiguous()))
+    elif kind == 3:
+        _, w_hi, _ = ops.pack_conv_weight(w, simt=False, tc=True, split=False)
+        one, zero = _ones_zeros(w.device)
+        u.raw = ops.conv3x3_bn_act_fwd(ops.bf16_plane(xin), w_hi, None, one, zero, res=None, relu=False, out_dtype=ops.BF16,
+                                       engine=ENGINE_TCGEN05).p0
+    else:
+        u.raw = ops.conv1x1_raw_fwd(ops.bf16_plane(xin), w.flatten(1).to(torch.bfloat16).contiguous())
+    track = bn.track_running_stats and bn.running_mean is not None
+    mom = _momentum(bn, track)
+    u.res = res if (relu and res is not None) else None
+    u.y, u.mean, u.inv = ops.bn_train_fwd_t(u.raw, bn.weight.detach(), bn.bias.detach(), bn.running_mean if track else None,
+                                            bn.running_var if track else None, mom, bn.eps, res=res, relu=relu,
+                                            out_dtype=torch.float32 if out_fp32 else torch.bfloat16)
+    u.planes = None
+    if track and bn.num_batches_tracked is not None:
+        bn.num_batches_tracked += 1
+    return u
+
+
+def _unit_bwd16(u, dy, need_dx=True):
+    """Backward of `_unit_fwd16`: dy fp32 (the feature-map gradient) or bf16; bf16 gradient maps throughout (bf16 has fp32's
+    exponent range: no scaling), fp32 weight gradients from the single-plane tensor-core wgrad kernels."""
+    bn = u.bn
+    dxr, dres, dg, db = ops.bn_train_bwd_t(dy, u.raw, u.mean, u.inv, bn.weight.detach(), bn.bias.detach(), res=u.res, relu=u.relu,
+                                           want_dres=u.has_res)
+    dyp = ops.bf16_plane(dxr)
+    w = u.weight.detach().float()
+    dx = None
+    if u.kind == "stem":
+        dw = ops.stem_wgrad(u.xin, dyp, None)
+    elif u.kind == 3:
+        if need_dx:
+            _, w_hi, _ = ops.pack_conv_weight(w.flip(2, 3).transpose(0, 1).contiguous(), simt=False, tc=True, split=False)
+            one, zero = _ones_zeros(dxr.device)
+            dx = ops.conv3x3_bn_act_fwd(dyp, w_hi, None, one, zero, res=None, relu=False, out_dtype=ops.BF16, engine=ENGINE_TCGEN05).p0
+        dw = ops.conv3x3_wgrad(ops.bf16_plane(u.xin), dyp, None)
+    else:
+        if need_dx:
+            dx = ops.conv1x1_raw_fwd(dyp, w.flatten(1).t().to(torch.bfloat16).contiguous())
+        dw = ops.conv1x1_wgrad(ops.bf16_plane(u.xin), dyp, None)
+    u.raw = u.res = u.xin = u.mean = u.inv = None
+    return dx, dw, dg, db, dres
+
+
 class _BackboneFn(torch.autograd.Function):
     """`convnet(images)` in training mode as ONE autograd node: every convolution (forward, dgrad, wgrad) on the tensor
     cores in the split-fp16 three-product mode, BatchNorm(batch statistics) + residual + ReLU and the maxpool as the native
@@ -414,34 +467,48 @@ class _BackboneFn(torch.autograd.Function):
     for a residual / the pooled map / RoIPool).  Parameters arrive as (conv.weight, bn.weight, bn.bias) per unit, in unit order."""
 
     @staticmethod
-    def forward(ctx, images, convnet, *params):
+    def forward(ctx, images, convnet, bf16, *params):
         blocks = list(convnet[4])
         units = []
-        stem = _unit_fwd("stem", images, convnet[0], convnet[1], relu=True, want_y=True)
+        ctx.bf16 = bf16
+        if bf16:
+            def unit(kind, src, conv, bn, res=None, relu=True, want_y=True, want_planes=False, last=False):
+                return _unit_fwd16(kind, src, conv, bn, res=res, relu=relu, out_fp32=last)
+            operand = lambda u: u.y
+        else:
+            def unit(kind, src, conv, bn, res=None, relu=True, want_y=True, want_planes=False, last=False):
+                return _unit_fwd(kind, src, conv, bn, res=res, relu=relu, want_y=want_y, want_planes=want_planes)
+            operand = lambda u: u.planes
+        stem = unit("stem", images, convnet[0], convnet[1], relu=True, want_y=True)
         units.append(stem)
-        x, code, xp = ops.maxpool3x3s2_fwd(stem.y, want_planes=True, planes_dtype=F16X2)
+        if bf16:
+            x, code = ops.maxpool3x3s2_fwd_t(stem.y)
+            xp = x
+        else:
+            x, code, xp = ops.maxpool3x3s2_fwd(stem.y, want_planes=True, planes_dtype=F16X2)
         ctx.pool = (code, tuple(stem.y.shape))
-        stem.y = None                                            # the 640^2 map is not needed again (ReLU mask comes from raw)
+        stem.y = None                                            # the 640^2 map is not needed again (the ReLU mask comes from raw)
         plan = []
         for bi, blk in enumerate(blocks):
             last = bi + 1 == len(blocks)
             if hasattr(blk, "conv3"):                            # Bottleneck (torchvision resnet.py:143-163)
-                u1 = _unit_fwd(1, xp, blk.conv1, blk.bn1, want_y=False, want_planes=True)
-                u2 = _unit_fwd(3, u1.planes, blk.conv2, blk.bn2, want_y=False, want_planes=True)
+                u1 = unit(1, xp, blk.conv1, blk.bn1, want_y=False, want_planes=True)
+                u2 = unit(3, operand(u1), blk.conv2, blk.bn2, want_y=False, want_planes=True)
                 ud = None
                 if blk.downsample is not None:
-                    ud = _unit_fwd(1, xp, blk.downsample[0], blk.downsample[1], relu=False, want_y=True)
-                u3 = _unit_fwd(1, u2.planes, blk.conv3, blk.bn3, res=(x if ud is None else ud.y), want_y=True, want_planes=not last)
+                    ud = unit(1, xp, blk.downsample[0], blk.downsample[1], relu=False, want_y=True)
+                u3 = unit(1, operand(u2), blk.conv3, blk.bn3, res=(x if ud is None else ud.y), want_y=True, want_planes=not last,
+                          last=last)
                 group = [u1, u2, u3] + ([ud] if ud is not None else [])
-                x, xp = u3.y, u3.planes
+                x, xp = u3.y, operand(u3)
             else:                                                # BasicBlock (resnet.py:89-105)
-                u1 = _unit_fwd(3, xp, blk.conv1, blk.bn1, want_y=False, want_planes=True)
-                u2 = _unit_fwd(3, u1.planes, blk.conv2, blk.bn2, res=x, want_y=True, want_planes=not last)
+                u1 = unit(3, xp, blk.conv1, blk.bn1, want_y=False, want_planes=True)
+                u2 = unit(3, operand(u1), blk.conv2, blk.bn2, res=x, want_y=True, want_planes=not last, last=last)
                 group = [u1, u2]
-                x, xp = u2.y, u2.planes
+                x, xp = u2.y, operand(u2)
             plan.append((len(units), len(group), hasattr(blk, "conv3"), blk.downsample is not None))
             units.extend(group)
-        for u in units:            # outputs live on only where a consumer holds them: `xin` (planes), `res` (fp32 residual), the caller (x)
+        for u in units:            # outputs live on only where a consumer holds them: `xin` (operand), `res` (residual), the caller (x)
             u.y = u.planes = None
         ctx.units, ctx.plan = units, plan
         return x
@@ -449,35 +516,36 @@ class _BackboneFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g):
         units, plan = ctx.units, ctx.plan
+        ubwd = _unit_bwd16 if ctx.bf16 else _unit_bwd
         grads = [None] * len(units)
         g = g.contiguous()
         for start, n, bottleneck, has_ds in reversed(plan):
             us = units[start:start + n]
             if bottleneck:
-                d3, *p3, dres = _unit_bwd(us[2], g)
-                d2, *p2, _ = _unit_bwd(us[1], d3)
-                d1, *p1, _ = _unit_bwd(us[0], d2)
+                d3, *p3, dres = ubwd(us[2], g)
+                d2, *p2, _ = ubwd(us[1], d3)
+                d1, *p1, _ = ubwd(us[0], d2)
                 grads[start + 2], grads[start + 1], grads[start] = p3, p2, p1
                 if has_ds:
-                    dd, *pd, _ = _unit_bwd(us[3], dres)
+                    dd, *pd, _ = ubwd(us[3], dres)
                     grads[start + 3] = pd
                     g = d1.add_(dd)
                 else:
                     g = d1.add_(dres)
             else:
-                d2, *p2, dres = _unit_bwd(us[1], g)
-                d1, *p1, _ = _unit_bwd(us[0], d2)
+                d2, *p2, dres = ubwd(us[1], g)
+                d1, *p1, _ = ubwd(us[0], d2)
                 grads[start + 1], grads[start] = p2, p1
                 g = d1.add_(dres)
         code, shape = ctx.pool
-        g = ops.maxpool3x3s2_bwd(code, g, shape)
-        _, *p0, _ = _unit_bwd(units[0], g, need_dx=False)
+        g = ops.maxpool3x3s2_bwd_t(code, g, shape) if ctx.bf16 else ops.maxpool3x3s2_bwd(code, g, shape)
+        _, *p0, _ = ubwd(units[0], g, need_dx=False)
         grads[0] = p0
         flat = []
         for dw, dg, db in grads:
             flat += [dw, dg, db]
         ctx.units = ctx.plan = ctx.pool = None
-        return (None, None) + tuple(gr if need else None for gr, need in zip(flat, ctx.needs_input_grad[2:]))
+        return (None, None, None) + tuple(gr if need else None for gr, need in zip(flat, ctx.needs_input_grad[3:]))
 
 
 def _fused_ok(convnet):
@@ -514,11 +582,15 @@ def _unit_params(convnet):
     return out
 
 
-def feature_map_train(convnet, images):
+def feature_map_train(convnet, images, precision="fp32"):
     """`convnet(images)` (`models.py:125`) in training mode -> NHWC fp32 feature map [B, H/4, W/4, C].  Default: the
-    whole-backbone autograd node (`_BackboneFn`); COVA_B200_TRAIN_BACKBONE=modular (or any library-convolution switch)
-    selects the per-operator autograd functions above."""
+    whole-backbone autograd node (`_BackboneFn`) in the fp32-parity mode (split-fp16 three-product convolutions, fp32 maps);
+    precision="bf16" = the bf16 training mode (bf16 maps and gradient maps, one bf16 product per MMA; fp32 statistics,
+    parameters and weight gradients).  COVA_B200_TRAIN_BACKBONE=modular (or any library-convolution switch) selects the
+    per-operator autograd functions above."""
     if _fused_ok(convnet) and all(p is not None for p in _unit_params(convnet)):
         img = images if images.dtype == torch.uint8 else images.float()
-        return _BackboneFn.apply(img, convnet, *_unit_params(convnet))
+        return _BackboneFn.apply(img, convnet, precision == "bf16", *_unit_params(convnet))
+    if precision == "bf16":
+        raise RuntimeError("cova_b200: the bf16 training mode needs the tensor-core backbone (a ResNet-18 / ResNet-50 layer1 stack)")
     return feature_map_train_modular(convnet, images)

@@ -314,7 +314,7 @@ int cova_conv3x3_wgrad(const void* x_hi, const void* x_lo, const void* dy_hi, co
  * cova_conv1x1_wgrad: dw[co][ci] = inv_scale * sum_m dy[m][co] * x[m][ci] from the split planes of x and dy
  *   (ws: Cin*Cout floats of device scratch, zeroed here).  Both built for 64->64, 64->256, 256->64.                   */
 int cova_conv1x1_raw_fwd(const void* x_hi, const void* x_lo, int planes_dtype, int64_t M, int Cin, int Cout,
-                         const void* w_packed, const float* scale, const float* zero_shift, float* y, void* stream);
+                         const void* w_packed, const float* scale, const float* zero_shift, void* y, void* stream);
 int cova_conv1x1_wgrad(const void* x_hi, const void* x_lo, const void* dy_hi, const void* dy_lo, int64_t M, int Cin,
                        int Cout, int planes_dtype, const float* inv_scale, float* ws, float* dw, void* stream);
 
@@ -326,6 +326,30 @@ int cova_conv1x1_wgrad(const void* x_hi, const void* x_lo, const void* dy_hi, co
  * scratch (zeroed here); dw_oihw: [64,3,7,7] fp32, overwritten.                                                       */
 int cova_stem_wgrad(const void* images, int img_dtype, int B, int H, int W, const void* dy_hi, const void* dy_lo,
                     int planes_dtype, const float* inv_scale, float* ws, float* dw_oihw, void* stream);
+
+/* ---- bf16 training mode (BASELINE config 3: "ResNet-50 backbone bf16 ... train step"): the same passes with the maps
+ * stored as bf16 (COVA_BF16) instead of fp32 - raw convolution outputs, activations (one bf16 plane, which is also the
+ * operand of the next tensor-core convolution: one product per MMA), gradient maps; statistics, parameters and weight
+ * gradients stay fp32, arithmetic inside every kernel is fp32.  dtype arguments are COVA_F32 or COVA_BF16.
+ *   cova_bn_train_stats_t : ws = [sum x | sum x^2] of x [M, C] (x_dtype)
+ *   cova_bn_act_fwd_t     : y (y_dtype) = [relu](BN(x) [+ res]); x and res are s_dtype
+ *   cova_bn_act_bwd_t     : dx, dres (s_dtype) from dy (dy_dtype), x / res (s_dtype); dgamma / dbeta fp32
+ *   cova_maxpool3x3s2_*_t : nn.MaxPool2d(3,2,1) forward (+ winner codes) / backward on maps of `dtype`
+ *   cova_stem_conv_raw_fwd_bf16 : conv1 (7x7 s2) in one bf16 product (w = cova_pack_stem_weight), raw output as bf16
+ * The convolutions' bf16 entry points are the existing ones: cova_conv3x3_bn_act_fwd (COVA_BF16 in / out, identity
+ * scale / shift), cova_conv1x1_raw_fwd (planes_dtype COVA_BF16: x_lo unused, w = bf16 [Cout][Cin], y = bf16 rows) and
+ * the three wgrad calls with planes_dtype COVA_BF16 and NULL lo planes.                                               */
+int cova_bn_train_stats_t(const void* x, int x_dtype, int64_t M, int C, double* ws, void* stream);
+int cova_bn_act_fwd_t(const void* x, int s_dtype, int64_t M, int C, const float* mean, const float* invstd,
+                      const float* gamma, const float* beta, const void* res, int relu, void* y, int y_dtype, void* stream);
+int cova_bn_act_bwd_t(const void* dy, int dy_dtype, const void* x, const void* res, int s_dtype, int64_t M, int C,
+                      const float* mean, const float* invstd, const float* gamma, const float* beta, int relu, double* ws,
+                      void* dx, void* dres, float* dgamma, float* dbeta, void* stream);
+int cova_maxpool3x3s2_fwd_t(const void* x, int dtype, int B, int H, int W, int C, void* y, unsigned char* code, void* stream);
+int cova_maxpool3x3s2_bwd_t(const unsigned char* code, const void* dy, int dtype, int B, int H, int W, int C, void* dx,
+                            void* stream);
+int cova_stem_conv_raw_fwd_bf16(const void* images, int img_dtype, int B, int H, int W, const void* w_packed,
+                                void* out_bf16, void* stream);
 
 #ifdef __cplusplus
 }
