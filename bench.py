@@ -539,7 +539,9 @@ def measure(cfg, dev, rank, world, dist, args, sample_clocks, full):
         del m16
     if rank == 0:
         roi_b = roi_bytes(r.inp[1])
-        out["stages"] = time_stages(r.step_resident, max(2, min(steps, 10 if not r.train else 3)), roi_b)
+        # rank 0 alone times the stages: a train step must not issue its all-reduce here (the other ranks have moved on)
+        stage_step = r.local_step_no_collective if (r.train and world > 1) else r.step_resident
+        out["stages"] = time_stages(stage_step, max(2, min(steps, 10 if not r.train else 3)), roi_b)
         out["exec_factor"] = r.exec_factors()
     out["precision"] = r.model.precision
     out["engine"] = r.model.engine
@@ -603,7 +605,8 @@ def main():
     numa_cores = bind_to_gpu_numa(local) if world > 1 else None     # pinned buffers on the GPU's own NUMA node
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))   # a wedged collective fails fast
 
     head = measure(cfg, dev, rank, world, dist, args, sample_clocks=True, full=True)
     if "skipped" in head:
