@@ -61,75 +61,153 @@ __device__ __forceinline__ float pow2_scale(unsigned int amax_bits, int target_l
   return __uint_as_float((unsigned int)se << 23);
 }
 
+// Vector accessors: V channels per thread = one 16-byte access (4 fp32 / 8 bf16); a map with C % V != 0 falls back to the
+// host-side check.  Arithmetic on float[V].
+template <typename T> struct Vec { static constexpr int V = 16 / sizeof(T); };
+template <typename T> __device__ __forceinline__ void ldv(const T* p, int64_t e, float (&v)[Vec<T>::V]);
+template <> __device__ __forceinline__ void ldv<float>(const float* p, int64_t e, float (&v)[4]) {
+  const float4 t = __ldg(reinterpret_cast<const float4*>(p + e));
+  v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+}
+template <> __device__ __forceinline__ void ldv<__nv_bfloat16>(const __nv_bfloat16* p, int64_t e, float (&v)[8]) {
+  const uint4 u = __ldg(reinterpret_cast<const uint4*>(p + e));
+  v[0] = bf16lo_to_f32(u.x); v[1] = bf16hi_to_f32(u.x); v[2] = bf16lo_to_f32(u.y); v[3] = bf16hi_to_f32(u.y);
+  v[4] = bf16lo_to_f32(u.z); v[5] = bf16hi_to_f32(u.z); v[6] = bf16lo_to_f32(u.w); v[7] = bf16hi_to_f32(u.w);
+}
+__device__ __forceinline__ void stv(float* p, int64_t e, const float (&v)[4]) {
+  *reinterpret_cast<float4*>(p + e) = make_float4(v[0], v[1], v[2], v[3]);
+}
+__device__ __forceinline__ void stv(__nv_bfloat16* p, int64_t e, const float (&v)[8]) {
+  *reinterpret_cast<uint4*>(p + e) = make_uint4(pack2_bf16(v[0], v[1]), pack2_bf16(v[2], v[3]), pack2_bf16(v[4], v[5]), pack2_bf16(v[6], v[7]));
+}
+// V fp32 values -> the storage type TO (V may be 4 or 8: a bf16-storage kernel writing an fp32 map, or the reverse)
+template <int V> __device__ __forceinline__ void stv_any(float* p, int64_t e, const float (&v)[V]) {
+#pragma unroll
+  for (int k = 0; k < V; k += 4) *reinterpret_cast<float4*>(p + e + k) = make_float4(v[k], v[k + 1], v[k + 2], v[k + 3]);
+}
+template <int V> __device__ __forceinline__ void stv_any(__nv_bfloat16* p, int64_t e, const float (&v)[V]) {
+#pragma unroll
+  for (int k = 0; k < V; k += 4) *reinterpret_cast<uint2*>(p + e + k) = make_uint2(pack2_bf16(v[k], v[k + 1]), pack2_bf16(v[k + 2], v[k + 3]));
+}
+// V values of a map of type TI starting at element e, whatever V is (TI fp32 with V = 8: two 16-byte loads)
+template <int V> __device__ __forceinline__ void ldv_any(const float* p, int64_t e, float (&v)[V]) {
+#pragma unroll
+  for (int k = 0; k < V; k += 4) {
+    const float4 t = __ldg(reinterpret_cast<const float4*>(p + e + k));
+    v[k] = t.x; v[k + 1] = t.y; v[k + 2] = t.z; v[k + 3] = t.w;
+  }
+}
+template <int V> __device__ __forceinline__ void ldv_any(const __nv_bfloat16* p, int64_t e, float (&v)[V]) {
+#pragma unroll
+  for (int k = 0; k < V; k += 4) {
+    const uint2 u = __ldg(reinterpret_cast<const uint2*>(p + e + k));
+    v[k] = bf16lo_to_f32(u.x); v[k + 1] = bf16hi_to_f32(u.x); v[k + 2] = bf16lo_to_f32(u.y); v[k + 3] = bf16hi_to_f32(u.y);
+  }
+}
+
+// BatchNorm as ONE fma per element: y = x * A + B with A = invstd * gamma, B = beta - mean * A.  Forward, the backward's mask
+// recomputation and its reduction all use THIS expression (so the ReLU mask of the backward is bit-identical to the forward's);
+// these passes sit at the SM's issue limit, not only at the HBM limit (~30 lane-instructions per element against 128 per
+// clock and SM: 3e12 bf16 elements/s at 6 TB/s would need 2.5x the issue rate), so instructions per element are what counts.
+__device__ __forceinline__ void bn_affine(float mean, float inv, float g, float b, float& A, float& B) {
+  A = inv * g;
+  B = fmaf(-mean, A, b);
+}
+
+// V per-channel parameters (global or shared memory, 16-byte aligned at c0) with 128-bit loads
+template <int V> __device__ __forceinline__ void ldp(const float* p, int c0, float (&v)[V]) {
+#pragma unroll
+  for (int k = 0; k < V; k += 4) {
+    const float4 t = *reinterpret_cast<const float4*>(p + c0 + k);
+    v[k] = t.x; v[k + 1] = t.y; v[k + 2] = t.z; v[k + 3] = t.w;
+  }
+}
+
 // MODE 0: a = sum x, b = sum x^2.   MODE 1: a = sum g, b = sum g * xhat with g = dy * [y > 0] (y recomputed).
 // MODE 2: MODE 1 + wmax[c] = max |x - mean| per channel and wmax[C] = max |g| (bit patterns of non-negative floats): what
 // bounds |dx| before dx exists, so that the apply pass can emit SCALED split-fp16 planes directly (bn_act_bwd_kernel<true>).
+// TS = storage type of x / res, TG = type of dy; a thread owns V = 16 B / sizeof(TS) channels and strides over pixels.
 template <int MODE, typename TS = float, typename TG = float>
-__global__ void __launch_bounds__(BN_THREADS)
+__global__ void __launch_bounds__(BN_THREADS, 4)
 bn_reduce_kernel(const TS* __restrict__ x, const TG* __restrict__ dy, const TS* __restrict__ res, int64_t M,
                  int C, const float* __restrict__ mean, const float* __restrict__ invstd,
                  const float* __restrict__ gamma, const float* __restrict__ beta, int relu, double* __restrict__ ws,
                  unsigned int* __restrict__ wmax = nullptr) {
+  constexpr int V = Vec<TS>::V;
   extern __shared__ __align__(16) float red[];                       // [2][rows][C]
-  const int c4n = C >> 2, rows = BN_THREADS / c4n;
-  const int cg = threadIdx.x % c4n, prow = threadIdx.x / c4n;
-  const int c0 = 4 * cg;
-  float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
-  float4 mu = a, iv = a, ga = a, be = a;
-  float4 mx = a;
+  const int cvn = C / V, rows = BN_THREADS / cvn;
+  const int cg = threadIdx.x % cvn, prow = threadIdx.x / cvn;
+  const int c0 = V * cg;
+  float a[V], b[V], mu[V], iv[V], ga[V], be[V], mx[V];
   float gm = 0.f;
+#pragma unroll
+  for (int k = 0; k < V; ++k) {
+    a[k] = b[k] = mx[k] = 0.f;
+    mu[k] = iv[k] = ga[k] = be[k] = 0.f;
+  }
   if (MODE >= 1) {
-    mu = *reinterpret_cast<const float4*>(mean + c0);
-    iv = *reinterpret_cast<const float4*>(invstd + c0);
-    ga = *reinterpret_cast<const float4*>(gamma + c0);
-    be = *reinterpret_cast<const float4*>(beta + c0);
+    ldp<V>(mean, c0, mu); ldp<V>(invstd, c0, iv); ldp<V>(gamma, c0, ga); ldp<V>(beta, c0, be);
+#pragma unroll
+    for (int k = 0; k < V; ++k) {        // ga <- A, be <- B
+      float A, B;
+      bn_affine(mu[k], iv[k], ga[k], be[k], A, B);
+      ga[k] = A; be[k] = B;
+    }
   }
   const int64_t stride = (int64_t)gridDim.x * rows;
   int64_t p = (int64_t)blockIdx.x * rows + prow;
-  if (MODE == 0) {   // statistics pass: four independent loads in flight per thread (a plain loop ran at 4 TB/s)
-    for (; p + 3 * stride < M; p += 4 * stride) {
-      float4 v[4];
+  if (prow < rows) {
+    if (MODE == 0) {   // statistics pass: four independent loads in flight per thread (a plain loop ran at 4 TB/s)
+      for (; p + 3 * stride < M; p += 4 * stride) {
+        float v[4][V];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) v[u] = ld4<TS>(x, (p + u * stride) * C + c0);
+        for (int u = 0; u < 4; ++u) ldv<TS>(x, (p + u * stride) * C + c0, v[u]);
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        a.x += v[u].x; a.y += v[u].y; a.z += v[u].z; a.w += v[u].w;
-        b.x = fmaf(v[u].x, v[u].x, b.x); b.y = fmaf(v[u].y, v[u].y, b.y);
-        b.z = fmaf(v[u].z, v[u].z, b.z); b.w = fmaf(v[u].w, v[u].w, b.w);
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+          for (int k = 0; k < V; ++k) { a[k] += v[u][k]; b[k] = fmaf(v[u][k], v[u][k], b[k]); }
       }
-    }
-  }
-  for (; p < M; p += stride) {
-    const float4 xv = ld4<TS>(x, p * C + c0);
-    if (MODE == 0) {
-      a.x += xv.x; a.y += xv.y; a.z += xv.z; a.w += xv.w;
-      b.x = fmaf(xv.x, xv.x, b.x); b.y = fmaf(xv.y, xv.y, b.y); b.z = fmaf(xv.z, xv.z, b.z); b.w = fmaf(xv.w, xv.w, b.w);
+      for (; p < M; p += stride) {
+        float v[V];
+        ldv<TS>(x, p * C + c0, v);
+#pragma unroll
+        for (int k = 0; k < V; ++k) { a[k] += v[k]; b[k] = fmaf(v[k], v[k], b[k]); }
+      }
     } else {
-      float4 g = ld4<TG>(dy, p * C + c0);
-      const float4 xh = make_float4((xv.x - mu.x) * iv.x, (xv.y - mu.y) * iv.y, (xv.z - mu.z) * iv.z, (xv.w - mu.w) * iv.w);
-      if (relu) {
-        float4 y = make_float4(bn_val(xv.x, mu.x, iv.x, ga.x, be.x), bn_val(xv.y, mu.y, iv.y, ga.y, be.y),
-                               bn_val(xv.z, mu.z, iv.z, ga.z, be.z), bn_val(xv.w, mu.w, iv.w, ga.w, be.w));
-        if (res != nullptr) {
-          const float4 r = ld4<TS>(res, p * C + c0);
-          y.x += r.x; y.y += r.y; y.z += r.z; y.w += r.w;
+      for (; p < M; p += stride) {
+        float xv[V], g[V], r[V];
+        ldv<TS>(x, p * C + c0, xv);
+        ldv_any<V>(dy, p * C + c0, g);
+        if (relu && res != nullptr) ldv<TS>(res, p * C + c0, r);
+#pragma unroll
+        for (int k = 0; k < V; ++k) {
+          // bf16 storage: accumulate sum g*x and form sum g*xhat = inv (sum g*x - mean sum g) once per thread below (two
+          // instructions and 16 registers less per element; the cancellation costs |mean|/std ulps of fp32, irrelevant next to
+          // the bf16 maps).  fp32 storage keeps the centred product.
+          const float xh = sizeof(TS) == 2 ? xv[k] : (xv[k] - mu[k]) * iv[k];
+          if (relu) {
+            float y = fmaf(xv[k], ga[k], be[k]);
+            if (res != nullptr) y += r[k];
+            g[k] = y > 0.f ? g[k] : 0.f;
+          }
+          a[k] += g[k];
+          b[k] = fmaf(g[k], xh, b[k]);
+          if (MODE == 2) {
+            mx[k] = fmaxf(mx[k], fabsf(xv[k] - mu[k]));
+            gm = fmaxf(gm, fabsf(g[k]));
+          }
         }
-        g.x = y.x > 0.f ? g.x : 0.f; g.y = y.y > 0.f ? g.y : 0.f;
-        g.z = y.z > 0.f ? g.z : 0.f; g.w = y.w > 0.f ? g.w : 0.f;
-      }
-      a.x += g.x; a.y += g.y; a.z += g.z; a.w += g.w;
-      b.x = fmaf(g.x, xh.x, b.x); b.y = fmaf(g.y, xh.y, b.y); b.z = fmaf(g.z, xh.z, b.z); b.w = fmaf(g.w, xh.w, b.w);
-      if (MODE == 2) {
-        mx.x = fmaxf(mx.x, fabsf(xv.x - mu.x)); mx.y = fmaxf(mx.y, fabsf(xv.y - mu.y));
-        mx.z = fmaxf(mx.z, fabsf(xv.z - mu.z)); mx.w = fmaxf(mx.w, fabsf(xv.w - mu.w));
-        gm = fmaxf(gm, fmaxf(fmaxf(fabsf(g.x), fabsf(g.y)), fmaxf(fabsf(g.z), fabsf(g.w))));
       }
     }
   }
   float* ra = red + (size_t)prow * C + c0;
   float* rb = red + (size_t)(rows + prow) * C + c0;
-  *reinterpret_cast<float4*>(ra) = a;
-  *reinterpret_cast<float4*>(rb) = b;
+  if (MODE >= 1 && sizeof(TS) == 2) {
+#pragma unroll
+    for (int k = 0; k < V; ++k) b[k] = invstd[c0 + k] * fmaf(-mean[c0 + k], a[k], b[k]);
+  }
+#pragma unroll
+  for (int k = 0; k < V; ++k) { ra[k] = a[k]; rb[k] = b[k]; }
   __syncthreads();
   for (int c = threadIdx.x; c < 2 * C; c += BN_THREADS) {
     const int which = c / C, ch = c % C;
@@ -139,7 +217,8 @@ bn_reduce_kernel(const TS* __restrict__ x, const TG* __restrict__ dy, const TS* 
   }
   if (MODE == 2) {
     __syncthreads();
-    *reinterpret_cast<float4*>(ra) = mx;
+#pragma unroll
+    for (int k = 0; k < V; ++k) ra[k] = mx[k];
     __syncthreads();
     for (int c = threadIdx.x; c < C; c += BN_THREADS) {
       float m = 0.f;
@@ -169,49 +248,59 @@ __global__ void bn_finalize_kernel(const double* __restrict__ ws, int64_t M, int
   }
 }
 
-// TS = storage type of x / res, TY = type of y.  In the bf16 training mode the rounded y is compared against 0 by the
-// backward exactly as it is here: bn_val in fp32, + res, ReLU, then the store rounds (a positive value never rounds to <= 0).
+// TS = storage type of x / res, TY = type of y; V = 16 B / sizeof(TS) channels per thread.  In the bf16 training mode the
+// backward recomputes the ReLU mask exactly as it is computed here: bn_val in fp32, + res, compare with 0, THEN the store rounds
+// (a positive value never rounds to <= 0).
 template <typename TS, typename TY>
 __global__ void __launch_bounds__(BN_THREADS)
-bn_act_fwd_kernel(const TS* __restrict__ x, int64_t n4, int C, const float* __restrict__ mean,
+bn_act_fwd_kernel(const TS* __restrict__ x, int64_t nv, int C, const float* __restrict__ mean,
                   const float* __restrict__ invstd, const float* __restrict__ gamma, const float* __restrict__ beta,
                   const TS* __restrict__ res, int relu, TY* __restrict__ y, __nv_bfloat16* __restrict__ y_hi,
                   __nv_bfloat16* __restrict__ y_lo, int f16) {
-  const int c4n = C >> 2;
-  for (int64_t i = (int64_t)blockIdx.x * BN_THREADS + threadIdx.x; i < n4; i += (int64_t)gridDim.x * BN_THREADS) {
-    const int c0 = 4 * (int)(i % c4n);
-    const float4 xv = ld4<TS>(x, i * 4);
-    const float4 mu = *reinterpret_cast<const float4*>(mean + c0), iv = *reinterpret_cast<const float4*>(invstd + c0);
-    const float4 ga = *reinterpret_cast<const float4*>(gamma + c0), be = *reinterpret_cast<const float4*>(beta + c0);
-    float4 o = make_float4(bn_val(xv.x, mu.x, iv.x, ga.x, be.x), bn_val(xv.y, mu.y, iv.y, ga.y, be.y),
-                           bn_val(xv.z, mu.z, iv.z, ga.z, be.z), bn_val(xv.w, mu.w, iv.w, ga.w, be.w));
-    if (res != nullptr) {
-      const float4 r = ld4<TS>(res, i * 4);
-      o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+  constexpr int V = Vec<TS>::V;
+  extern __shared__ __align__(16) float tab[];                       // [2][C]: A, B
+  const int cvn = C / V;
+  for (int c = threadIdx.x; c < C; c += BN_THREADS) bn_affine(mean[c], invstd[c], gamma[c], beta[c], tab[c], tab[C + c]);
+  __syncthreads();
+  for (int64_t i = (int64_t)blockIdx.x * BN_THREADS + threadIdx.x; i < nv; i += (int64_t)gridDim.x * BN_THREADS) {
+    const int c0 = V * (int)(i % cvn);
+    float xv[V], r[V], o[V], A[V], B[V];
+    ldv<TS>(x, i * V, xv);
+    if (res != nullptr) ldv<TS>(res, i * V, r);
+    ldp<V>(tab, c0, A); ldp<V>(tab + C, c0, B);
+#pragma unroll
+    for (int k = 0; k < V; ++k) {
+      o[k] = fmaf(xv[k], A[k], B[k]);
+      if (res != nullptr) o[k] += r[k];
+      if (relu) o[k] = fmaxf(o[k], 0.f);
     }
-    if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-    if (y != nullptr) st4(y, i * 4, o);
-    if (y_hi != nullptr) split4(o, y_hi, y_lo, (size_t)i * 4, f16);
+    if (y != nullptr) stv_any<V>(y, i * V, o);
+    if (y_hi != nullptr) {
+#pragma unroll
+      for (int k = 0; k < V; k += 4) split4(make_float4(o[k], o[k + 1], o[k + 2], o[k + 3]), y_hi, y_lo, (size_t)i * V + k, f16);
+    }
   }
 }
 
-// PLANES = false: dx as fp32.  PLANES = true: dx as SCALED split planes (hi, lo) of dx * s, s = the power of two that brings
-// an upper bound of max|dx| - computed here from the reduce pass's maxima: |dx| <= |gamma inv| (max|g| + |S1/M| +
+// PLANES = false: dx in the storage type.  PLANES = true: dx as SCALED split planes (hi, lo) of dx * s, s = the power of two that
+// brings an upper bound of max|dx| - computed here from the reduce pass's maxima: |dx| <= |gamma inv| (max|g| + |S1/M| +
 // max|xhat| |S2/M|) - into [2^target, 2^(target+1)); block 0 publishes 256 copies of 1/s for the consuming convolution
 // kernels (dgrad epilogue scale / wgrad finalize).  The fp32 gradient map is never written nor re-read for the split.
 template <bool PLANES, typename TS = float, typename TG = float>
 __global__ void __launch_bounds__(BN_THREADS)
-bn_act_bwd_kernel(const TG* __restrict__ dy, const TS* __restrict__ x, const TS* __restrict__ res, int64_t n4,
+bn_act_bwd_kernel(const TG* __restrict__ dy, const TS* __restrict__ x, const TS* __restrict__ res, int64_t nv,
                   int64_t M, int C, const float* __restrict__ mean, const float* __restrict__ invstd,
                   const float* __restrict__ gamma, const float* __restrict__ beta, int relu,
                   const double* __restrict__ ws, TS* __restrict__ dx, TS* __restrict__ dres,
                   float* __restrict__ dgamma, float* __restrict__ dbeta, const unsigned int* __restrict__ wmax,
                   __nv_bfloat16* __restrict__ dx_hi, __nv_bfloat16* __restrict__ dx_lo, int f16, int target_log2,
                   float* __restrict__ inv_vec) {
-  extern __shared__ __align__(16) float sums[];                      // [2][C]: S1/M, S2/M
+  constexpr int V = Vec<TS>::V;
+  extern __shared__ __align__(16) float sums[];                      // [2][C]: S1/M, S2/M, then [4][C]: A, B, c1, c2
+  float* tab = sums + 2 * C;
   __shared__ float s_red[BN_THREADS / 32];
   __shared__ float s_scale;
-  const int c4n = C >> 2;
+  const int cvn = C / V;
   if (blockIdx.x == 0) {                               // parameter gradients: dbeta = S1, dgamma = S2
     for (int c = threadIdx.x; c < C; c += BN_THREADS) {
       if (dbeta != nullptr) dbeta[c] = (float)ws[c];
@@ -219,6 +308,14 @@ bn_act_bwd_kernel(const TG* __restrict__ dy, const TS* __restrict__ x, const TS*
     }
   }
   for (int c = threadIdx.x; c < 2 * C; c += BN_THREADS) sums[c] = (float)(ws[c] / (double)M);
+  __syncthreads();
+  // dx = A (g - s1 - xhat s2) = A g + c2 x + c1 with c2 = -A inv s2, c1 = -A s1 - c2 mean: two fma per element
+  for (int c = threadIdx.x; c < C; c += BN_THREADS) {
+    float A, B;
+    bn_affine(mean[c], invstd[c], gamma[c], beta[c], A, B);
+    const float c2 = -A * invstd[c] * sums[C + c];
+    tab[c] = A; tab[C + c] = B; tab[2 * C + c] = fmaf(-c2, mean[c], -A * sums[c]); tab[3 * C + c] = c2;
+  }
   __syncthreads();
   float scale = 1.f;
   if (PLANES) {
@@ -240,35 +337,30 @@ bn_act_bwd_kernel(const TG* __restrict__ dy, const TS* __restrict__ x, const TS*
     scale = s_scale;
     if (blockIdx.x == 0) inv_vec[threadIdx.x] = 1.f / scale;
   }
-  for (int64_t i = (int64_t)blockIdx.x * BN_THREADS + threadIdx.x; i < n4; i += (int64_t)gridDim.x * BN_THREADS) {
-    const int c0 = 4 * (int)(i % c4n);
-    const float4 xv = ld4<TS>(x, i * 4);
-    float4 g = ld4<TG>(dy, i * 4);
-    const float4 mu = *reinterpret_cast<const float4*>(mean + c0), iv = *reinterpret_cast<const float4*>(invstd + c0);
-    const float4 ga = *reinterpret_cast<const float4*>(gamma + c0), be = *reinterpret_cast<const float4*>(beta + c0);
-    const float4 xh = make_float4((xv.x - mu.x) * iv.x, (xv.y - mu.y) * iv.y, (xv.z - mu.z) * iv.z, (xv.w - mu.w) * iv.w);
-    if (relu) {
-      float4 y = make_float4(bn_val(xv.x, mu.x, iv.x, ga.x, be.x), bn_val(xv.y, mu.y, iv.y, ga.y, be.y),
-                             bn_val(xv.z, mu.z, iv.z, ga.z, be.z), bn_val(xv.w, mu.w, iv.w, ga.w, be.w));
-      if (res != nullptr) {
-        const float4 r = ld4<TS>(res, i * 4);
-        y.x += r.x; y.y += r.y; y.z += r.z; y.w += r.w;
+  for (int64_t i = (int64_t)blockIdx.x * BN_THREADS + threadIdx.x; i < nv; i += (int64_t)gridDim.x * BN_THREADS) {
+    const int c0 = V * (int)(i % cvn);
+    float xv[V], g[V], r[V], o[V], A[V], B[V], c1[V], c2[V];
+    ldv<TS>(x, i * V, xv);
+    ldv_any<V>(dy, i * V, g);
+    if (relu && res != nullptr) ldv<TS>(res, i * V, r);
+    ldp<V>(tab, c0, A); ldp<V>(tab + 2 * C, c0, c1); ldp<V>(tab + 3 * C, c0, c2);
+    if (relu) ldp<V>(tab + C, c0, B);
+#pragma unroll
+    for (int k = 0; k < V; ++k) {
+      if (relu) {
+        float y = fmaf(xv[k], A[k], B[k]);
+        if (res != nullptr) y += r[k];
+        g[k] = y > 0.f ? g[k] : 0.f;
       }
-      g.x = y.x > 0.f ? g.x : 0.f; g.y = y.y > 0.f ? g.y : 0.f;
-      g.z = y.z > 0.f ? g.z : 0.f; g.w = y.w > 0.f ? g.w : 0.f;
+      o[k] = fmaf(A[k], g[k], fmaf(c2[k], xv[k], c1[k]));
+      if (PLANES) o[k] *= scale;
     }
-    if (dres != nullptr) st4(dres, i * 4, g);
-    const float4 s1 = *reinterpret_cast<const float4*>(sums + c0), s2 = *reinterpret_cast<const float4*>(sums + C + c0);
-    float4 o;
-    o.x = ga.x * iv.x * (g.x - s1.x - xh.x * s2.x);
-    o.y = ga.y * iv.y * (g.y - s1.y - xh.y * s2.y);
-    o.z = ga.z * iv.z * (g.z - s1.z - xh.z * s2.z);
-    o.w = ga.w * iv.w * (g.w - s1.w - xh.w * s2.w);
+    if (dres != nullptr) stv(dres, i * V, g);
     if (PLANES) {
-      o.x *= scale; o.y *= scale; o.z *= scale; o.w *= scale;
-      split4(o, dx_hi, dx_lo, (size_t)i * 4, f16);
+#pragma unroll
+      for (int k = 0; k < V; k += 4) split4(make_float4(o[k], o[k + 1], o[k + 2], o[k + 3]), dx_hi, dx_lo, (size_t)i * V + k, f16);
     } else {
-      st4(dx, i * 4, o);
+      stv(dx, i * V, o);
     }
   }
 }
@@ -281,67 +373,77 @@ bn_act_bwd_kernel(const TG* __restrict__ dy, const TS* __restrict__ x, const TS*
 // no rescans, no atomics.
 // IdxT = uint32_t whenever the element count fits (64-bit div / mod per element made these kernels index-math bound:
 // the backward ran at 1.7 TB/s)
-template <typename IdxT, typename TS = float>
+// One thread = 8 channels of one pixel; blockIdx.y / z = image row / page, so no per-element division (the first version
+// did 64-bit div / mod per float4 and ran the backward at 1.1-1.7 TB/s); cvn = C / 8 is a power of two (shift / mask).
+template <typename TS>
 __global__ void __launch_bounds__(256)
-maxpool_fwd_kernel(const TS* __restrict__ x, int B, int H, int W, int C, int Ho, int Wo, TS* __restrict__ y,
+maxpool_fwd_kernel(const TS* __restrict__ x, int H, int W, int C, int Ho, int Wo, int cshift, TS* __restrict__ y,
                    unsigned char* __restrict__ code, __nv_bfloat16* __restrict__ y_hi, __nv_bfloat16* __restrict__ y_lo,
                    int f16) {
-  const IdxT c4n = (IdxT)(C >> 2);
-  const IdxT n = (IdxT)B * Ho * Wo * c4n;
-  for (IdxT i = (IdxT)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (IdxT)gridDim.x * blockDim.x) {
-    const int cg = (int)(i % c4n);
-    const IdxT pix = i / c4n;
-    const int ow = (int)(pix % (IdxT)Wo), oh = (int)((pix / (IdxT)Wo) % (IdxT)Ho), b = (int)(pix / ((IdxT)Wo * Ho));
-    float4 m = make_float4(-FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX);
-    int4 mi = make_int4(-1, -1, -1, -1);
-    for (int r = 0; r < 3; ++r) {
-      const int h = 2 * oh - 1 + r;
-      if (h < 0 || h >= H) continue;
-      for (int s2 = 0; s2 < 3; ++s2) {
-        const int w = 2 * ow - 1 + s2;
-        if (w < 0 || w >= W) continue;
-        const float4 v = ld4<TS>(x, (int64_t)((((size_t)b * H + h) * W + w) * C) + 4 * cg);
-        const int k = r * 3 + s2;
-        if (v.x > m.x || mi.x < 0) { m.x = v.x; mi.x = k; }
-        if (v.y > m.y || mi.y < 0) { m.y = v.y; mi.y = k; }
-        if (v.z > m.z || mi.z < 0) { m.z = v.z; mi.z = k; }
-        if (v.w > m.w || mi.w < 0) { m.w = v.w; mi.w = k; }
-      }
+  const int t = blockIdx.x * 256 + threadIdx.x;
+  const int cvn = 1 << cshift;
+  if (t >= Wo * cvn) return;
+  const int cg = t & (cvn - 1), ow = t >> cshift, oh = blockIdx.y, b = blockIdx.z;
+  float m[8];
+  int mi[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { m[k] = -FLT_MAX; mi[k] = -1; }
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    const int h = 2 * oh - 1 + r;
+    if (h < 0 || h >= H) continue;
+#pragma unroll
+    for (int s2 = 0; s2 < 3; ++s2) {
+      const int w = 2 * ow - 1 + s2;
+      if (w < 0 || w >= W) continue;
+      float v[8];
+      ldv_any<8>(x, (int64_t)((((size_t)b * H + h) * W + w) * C) + 8 * cg, v);
+      const int kk = r * 3 + s2;
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        if (v[k] > m[k] || mi[k] < 0) { m[k] = v[k]; mi[k] = kk; }
     }
-    st4(y, (int64_t)i * 4, m);
-    if (code != nullptr) reinterpret_cast<uchar4*>(code)[i] = make_uchar4(mi.x, mi.y, mi.z, mi.w);
-    if (y_hi != nullptr) split4(m, y_hi, y_lo, (size_t)i * 4, f16);
+  }
+  const size_t o = ((((size_t)b * Ho + oh) * Wo + ow) * C) + 8 * cg;
+  stv_any<8>(y, (int64_t)o, m);
+  if (code != nullptr)
+    *reinterpret_cast<uint2*>(code + o) = make_uint2((uint32_t)mi[0] | ((uint32_t)mi[1] << 8) | ((uint32_t)mi[2] << 16) | ((uint32_t)mi[3] << 24),
+                                                    (uint32_t)mi[4] | ((uint32_t)mi[5] << 8) | ((uint32_t)mi[6] << 16) | ((uint32_t)mi[7] << 24));
+  if (y_hi != nullptr) {
+    split4(make_float4(m[0], m[1], m[2], m[3]), y_hi, y_lo, o, f16);
+    split4(make_float4(m[4], m[5], m[6], m[7]), y_hi, y_lo, o + 4, f16);
   }
 }
 
-template <typename IdxT, typename TS = float>
+template <typename TS>
 __global__ void __launch_bounds__(256)
-maxpool_bwd_kernel(const unsigned char* __restrict__ code, const TS* __restrict__ dy, int B, int H, int W, int C, int Ho,
-                   int Wo, TS* __restrict__ dx) {
-  const IdxT c4n = (IdxT)(C >> 2);
-  const IdxT n = (IdxT)B * H * W * c4n;
-  for (IdxT i = (IdxT)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (IdxT)gridDim.x * blockDim.x) {
-    const int cg = (int)(i % c4n);
-    const IdxT pix = i / c4n;
-    const int w0 = (int)(pix % (IdxT)W), h0 = (int)((pix / (IdxT)W) % (IdxT)H), b = (int)(pix / ((IdxT)W * H));
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    const int oh_hi = (h0 + 1) >> 1, ow_hi = (w0 + 1) >> 1;     // == h0 >> 1 for even h0: one window per axis
-    for (int oh = h0 >> 1; oh <= oh_hi; ++oh) {
-      if (oh >= Ho) continue;
-      for (int ow = w0 >> 1; ow <= ow_hi; ++ow) {
-        if (ow >= Wo) continue;
-        const int me = (h0 - (2 * oh - 1)) * 3 + (w0 - (2 * ow - 1));
-        const size_t o = (((size_t)b * Ho + oh) * Wo + ow) * (size_t)c4n + cg;
-        const uchar4 k = __ldg(reinterpret_cast<const uchar4*>(code) + o);
-        const float4 g = ld4<TS>(dy, (int64_t)o * 4);
-        if (k.x == me) acc.x += g.x;
-        if (k.y == me) acc.y += g.y;
-        if (k.z == me) acc.z += g.z;
-        if (k.w == me) acc.w += g.w;
+maxpool_bwd_kernel(const unsigned char* __restrict__ code, const TS* __restrict__ dy, int H, int W, int C, int Ho, int Wo,
+                   int cshift, TS* __restrict__ dx) {
+  const int t = blockIdx.x * 256 + threadIdx.x;
+  const int cvn = 1 << cshift;
+  if (t >= W * cvn) return;
+  const int cg = t & (cvn - 1), w0 = t >> cshift, h0 = blockIdx.y, b = blockIdx.z;
+  float acc[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+  const int oh_hi = (h0 + 1) >> 1, ow_hi = (w0 + 1) >> 1;     // == h0 >> 1 for even h0: one window per axis
+  for (int oh = h0 >> 1; oh <= oh_hi; ++oh) {
+    if (oh >= Ho) continue;
+    for (int ow = w0 >> 1; ow <= ow_hi; ++ow) {
+      if (ow >= Wo) continue;
+      const uint32_t me = (uint32_t)((h0 - (2 * oh - 1)) * 3 + (w0 - (2 * ow - 1)));
+      const size_t o = ((((size_t)b * Ho + oh) * Wo + ow) * C) + 8 * cg;
+      const uint2 kc = __ldg(reinterpret_cast<const uint2*>(code + o));
+      float g[8];
+      ldv_any<8>(dy, (int64_t)o, g);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (((kc.x >> (8 * k)) & 255u) == me) acc[k] += g[k];
+        if (((kc.y >> (8 * k)) & 255u) == me) acc[4 + k] += g[4 + k];
       }
     }
-    st4(dx, (int64_t)i * 4, acc);
   }
+  stv_any<8>(dx, (int64_t)(((((size_t)b * H + h0) * W + w0) * C) + 8 * cg), acc);
 }
 
 // fp32 -> split-bf16 planes (hi = bf16(x), lo = bf16(x - hi)): the operand format of the tensor-core convolutions
@@ -506,6 +608,8 @@ bn_relu_pool_bwd_kernel(const float* __restrict__ x, const unsigned char* __rest
 }
 
 static bool bn_c_ok(int C) { return C >= 4 && C <= 1024 && (C & (C - 1)) == 0; }
+static bool pool_c_ok(int C) { return C >= 8 && (C & (C - 1)) == 0; }
+static int ilog2(int v) { int l = 0; while ((1 << l) < v) ++l; return l; }
 static int ew_grid(int64_t n, int threads) {
   int64_t b = (n + threads - 1) / threads;
   const int64_t cap = (int64_t)sm_count() * 16;
@@ -552,7 +656,7 @@ extern "C" int cova_bn_act_fwd(const float* x, int64_t M, int C, const float* me
                "cova_bn_act_fwd: 16-byte alignment");
   COVA_REQUIRE((y_hi == nullptr) == (y_lo == nullptr), "cova_bn_act_fwd: the split planes come together");
   const int64_t n4 = M * (C / 4);
-  bn_act_fwd_kernel<float, float><<<ew_grid(n4, BN_THREADS), BN_THREADS, 0, (cudaStream_t)stream>>>(x, n4, C, mean, invstd, gamma, beta,
+  bn_act_fwd_kernel<float, float><<<ew_grid(n4, BN_THREADS), BN_THREADS, 2 * C * sizeof(float), (cudaStream_t)stream>>>(x, n4, C, mean, invstd, gamma, beta,
                                                                                      res, relu, y, (__nv_bfloat16*)y_hi,
                                                                                      (__nv_bfloat16*)y_lo,
                                                                                      planes_dtype == COVA_F16X2);
@@ -576,7 +680,7 @@ extern "C" int cova_bn_act_bwd(const float* dy, const float* x, const float* res
   bn_reduce_kernel<1, float, float><<<(int)grid, BN_THREADS, smem, st>>>(x, dy, res, M, C, mean, invstd, gamma, beta, relu, ws);
   COVA_LAUNCH_OK();
   const int64_t n4 = M * (C / 4);
-  bn_act_bwd_kernel<false, float, float><<<ew_grid(n4, BN_THREADS), BN_THREADS, 2 * C * sizeof(float), st>>>(
+  bn_act_bwd_kernel<false, float, float><<<ew_grid(n4, BN_THREADS), BN_THREADS, 6 * C * sizeof(float), st>>>(
       dy, x, res, n4, M, C, mean, invstd, gamma, beta, relu, ws, dx, dres, dgamma, dbeta, nullptr, nullptr, nullptr, 0, 0, nullptr);
   COVA_LAUNCH_OK();
   return COVA_OK;
@@ -603,7 +707,7 @@ extern "C" int cova_bn_act_bwd_planes(const float* dy, const float* x, const flo
   bn_reduce_kernel<2, float, float><<<(int)grid, BN_THREADS, smem, st>>>(x, dy, res, M, C, mean, invstd, gamma, beta, relu, ws, ws_max);
   COVA_LAUNCH_OK();
   const int64_t n4 = M * (C / 4);
-  bn_act_bwd_kernel<true, float, float><<<ew_grid(n4, BN_THREADS), BN_THREADS, 2 * C * sizeof(float), st>>>(
+  bn_act_bwd_kernel<true, float, float><<<ew_grid(n4, BN_THREADS), BN_THREADS, 6 * C * sizeof(float), st>>>(
       dy, x, res, n4, M, C, mean, invstd, gamma, beta, relu, ws, nullptr, dres, dgamma, dbeta, ws_max, (__nv_bfloat16*)dx_hi,
       (__nv_bfloat16*)dx_lo, planes_dtype == COVA_F16X2, target_log2, inv_scale_vec);
   COVA_LAUNCH_OK();
@@ -614,17 +718,14 @@ extern "C" int cova_maxpool3x3s2_fwd(const float* x, int B, int H, int W, int C,
                                      void* y_lo, int planes_dtype, void* stream) {
   COVA_REQUIRE(planes_dtype == COVA_BF16X2 || planes_dtype == COVA_F16X2, "cova_maxpool3x3s2_fwd: planes are split-bf16 or split-fp16");
   COVA_REQUIRE(x && y && B > 0 && H > 0 && W > 0 && C > 0 && C % 4 == 0, "cova_maxpool3x3s2_fwd: bad arguments");
-  COVA_REQUIRE((((uintptr_t)x | (uintptr_t)y | (uintptr_t)y_hi | (uintptr_t)y_lo) & 15) == 0 && ((uintptr_t)code & 3) == 0,
+  COVA_REQUIRE((((uintptr_t)x | (uintptr_t)y | (uintptr_t)y_hi | (uintptr_t)y_lo) & 15) == 0 && ((uintptr_t)code & 7) == 0,
                "cova_maxpool3x3s2_fwd: alignment");
   COVA_REQUIRE((y_hi == nullptr) == (y_lo == nullptr), "cova_maxpool3x3s2_fwd: the split planes come together");
   const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
-  const int64_t n = (int64_t)B * Ho * Wo * (C / 4);
-  if (n < (1LL << 31))
-    maxpool_fwd_kernel<uint32_t><<<ew_grid(n, 256), 256, 0, (cudaStream_t)stream>>>(
-        x, B, H, W, C, Ho, Wo, y, code, (__nv_bfloat16*)y_hi, (__nv_bfloat16*)y_lo, planes_dtype == COVA_F16X2);
-  else
-    maxpool_fwd_kernel<int64_t><<<ew_grid(n, 256), 256, 0, (cudaStream_t)stream>>>(
-        x, B, H, W, C, Ho, Wo, y, code, (__nv_bfloat16*)y_hi, (__nv_bfloat16*)y_lo, planes_dtype == COVA_F16X2);
+  COVA_REQUIRE(pool_c_ok(C) && Ho <= 65535 && B <= 65535, "cova_maxpool3x3s2_fwd: C / 8 must be a power of two, H/2 and B <= 65535");
+  const dim3 grid(ceil_div(Wo * (C / 8), 256), Ho, B);
+  maxpool_fwd_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(x, H, W, C, Ho, Wo, ilog2(C / 8), y, code, (__nv_bfloat16*)y_hi,
+                                                                   (__nv_bfloat16*)y_lo, planes_dtype == COVA_F16X2);
   COVA_LAUNCH_OK();
   return COVA_OK;
 }
@@ -632,13 +733,11 @@ extern "C" int cova_maxpool3x3s2_fwd(const float* x, int B, int H, int W, int C,
 extern "C" int cova_maxpool3x3s2_bwd(const unsigned char* code, const float* dy, int B, int H, int W, int C, float* dx,
                                      void* stream) {
   COVA_REQUIRE(code && dy && dx && B > 0 && H > 0 && W > 0 && C > 0 && C % 4 == 0, "cova_maxpool3x3s2_bwd: bad arguments");
-  COVA_REQUIRE((((uintptr_t)dy | (uintptr_t)dx) & 15) == 0 && ((uintptr_t)code & 3) == 0, "cova_maxpool3x3s2_bwd: alignment");
+  COVA_REQUIRE((((uintptr_t)dy | (uintptr_t)dx) & 15) == 0 && ((uintptr_t)code & 7) == 0, "cova_maxpool3x3s2_bwd: alignment");
   const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
-  const int64_t n = (int64_t)B * H * W * (C / 4);
-  if (n < (1LL << 31))
-    maxpool_bwd_kernel<uint32_t><<<ew_grid(n, 256), 256, 0, (cudaStream_t)stream>>>(code, dy, B, H, W, C, Ho, Wo, dx);
-  else
-    maxpool_bwd_kernel<int64_t><<<ew_grid(n, 256), 256, 0, (cudaStream_t)stream>>>(code, dy, B, H, W, C, Ho, Wo, dx);
+  COVA_REQUIRE(pool_c_ok(C) && H <= 65535 && B <= 65535, "cova_maxpool3x3s2_bwd: C / 8 must be a power of two, H and B <= 65535");
+  const dim3 grid(ceil_div(W * (C / 8), 256), H, B);
+  maxpool_bwd_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(code, dy, H, W, C, Ho, Wo, ilog2(C / 8), dx);
   COVA_LAUNCH_OK();
   return COVA_OK;
 }
@@ -676,7 +775,7 @@ extern "C" int cova_bn_relu_pool_fwd(const float* x, int B, int H, int W, int C,
   COVA_REQUIRE(bn_c_ok(C), "cova_bn_relu_pool_fwd: C=%d must be a power of two in [4, 1024]", C);
   COVA_REQUIRE((y_hi == nullptr) == (y_lo == nullptr), "cova_bn_relu_pool_fwd: the split planes come together");
   COVA_REQUIRE(planes_dtype == COVA_BF16X2 || planes_dtype == COVA_F16X2, "cova_bn_relu_pool_fwd: planes are split-bf16 or split-fp16");
-  COVA_REQUIRE((((uintptr_t)x | (uintptr_t)y | (uintptr_t)y_hi | (uintptr_t)y_lo) & 15) == 0 && ((uintptr_t)code & 3) == 0,
+  COVA_REQUIRE((((uintptr_t)x | (uintptr_t)y | (uintptr_t)y_hi | (uintptr_t)y_lo) & 15) == 0 && ((uintptr_t)code & 7) == 0,
                "cova_bn_relu_pool_fwd: alignment");
   const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
   const int64_t n = (int64_t)B * Ho * Wo * (C / 4);
@@ -693,7 +792,7 @@ extern "C" int cova_bn_relu_pool_bwd(const float* x, const unsigned char* code, 
   COVA_REQUIRE(x && code && dy_pooled && ws && dx && dgamma && dbeta && mean && invstd && gamma && beta && B > 0 && H > 0 && W > 0,
                "cova_bn_relu_pool_bwd: bad arguments");
   COVA_REQUIRE(bn_c_ok(C), "cova_bn_relu_pool_bwd: C=%d must be a power of two in [4, 1024]", C);
-  COVA_REQUIRE((((uintptr_t)x | (uintptr_t)dy_pooled | (uintptr_t)dx) & 15) == 0 && ((uintptr_t)code & 3) == 0,
+  COVA_REQUIRE((((uintptr_t)x | (uintptr_t)dy_pooled | (uintptr_t)dx) & 15) == 0 && ((uintptr_t)code & 7) == 0,
                "cova_bn_relu_pool_bwd: alignment");
   cudaStream_t st = (cudaStream_t)stream;
   const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
@@ -705,7 +804,7 @@ extern "C" int cova_bn_relu_pool_bwd(const float* x, const unsigned char* code, 
   bn_relu_pool_bwd_kernel<0><<<(int)grid, BN_THREADS, (size_t)2 * rows * C * sizeof(float), st>>>(
       x, code, dy_pooled, B, H, W, C, Ho, Wo, mean, invstd, gamma, beta, ws, nullptr, nullptr, nullptr);
   COVA_LAUNCH_OK();
-  bn_relu_pool_bwd_kernel<1><<<(int)grid, BN_THREADS, (size_t)2 * C * sizeof(float), st>>>(
+  bn_relu_pool_bwd_kernel<1><<<(int)grid, BN_THREADS, (size_t)6 * C * sizeof(float), st>>>(
       x, code, dy_pooled, B, H, W, C, Ho, Wo, mean, invstd, gamma, beta, ws, dx, dgamma, dbeta);
   COVA_LAUNCH_OK();
   return COVA_OK;
@@ -719,11 +818,11 @@ extern "C" int cova_bn_train_stats_t(const void* x, int x_dtype, int64_t M, int 
   if (x_dtype == COVA_F32) return cova_bn_train_stats((const float*)x, M, C, ws, stream);
   COVA_REQUIRE(x_dtype == COVA_BF16, "cova_bn_train_stats_t: x is fp32 or bf16");
   COVA_REQUIRE(x && ws && M > 0, "cova_bn_train_stats_t: bad arguments");
-  COVA_REQUIRE(bn_c_ok(C), "cova_bn_train_stats_t: C=%d must be a power of two in [4, 1024]", C);
-  COVA_REQUIRE(((uintptr_t)x & 7) == 0, "cova_bn_train_stats_t: x must be 8-byte aligned");
+  COVA_REQUIRE(bn_c_ok(C) && C >= 8, "cova_bn_train_stats_t: C=%d must be a power of two in [8, 1024]", C);
+  COVA_REQUIRE(((uintptr_t)x & 15) == 0, "cova_bn_train_stats_t: x must be 16-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
   COVA_CUDA_OK(cudaMemsetAsync(ws, 0, 2 * C * sizeof(double), st));
-  const int rows = BN_THREADS / (C / 4);
+  const int rows = BN_THREADS / (C / 8);
   const size_t smem = (size_t)2 * rows * C * sizeof(float);
   int64_t grid = (M + rows - 1) / rows;
   if (grid > (int64_t)sm_count() * 8) grid = (int64_t)sm_count() * 8;
@@ -738,17 +837,18 @@ extern "C" int cova_bn_act_fwd_t(const void* x, int s_dtype, int64_t M, int C, c
                                  void* stream) {
   COVA_REQUIRE(dt_ok(s_dtype) && dt_ok(y_dtype), "cova_bn_act_fwd_t: dtypes are fp32 or bf16");
   COVA_REQUIRE(x && y && mean && invstd && gamma && beta && M > 0, "cova_bn_act_fwd_t: bad arguments");
-  COVA_REQUIRE(bn_c_ok(C), "cova_bn_act_fwd_t: C=%d must be a power of two in [4, 1024]", C);
-  COVA_REQUIRE((((uintptr_t)x | (uintptr_t)y | (uintptr_t)res) & (s_dtype == COVA_F32 ? 15 : 7)) == 0, "cova_bn_act_fwd_t: alignment");
-  const int64_t n4 = M * (C / 4);
-  const int grid = ew_grid(n4, BN_THREADS);
+  COVA_REQUIRE(bn_c_ok(C) && (s_dtype == COVA_F32 || C >= 8), "cova_bn_act_fwd_t: C=%d must be a power of two in [4 (fp32) / 8 (bf16), 1024]", C);
+  COVA_REQUIRE((((uintptr_t)x | (uintptr_t)y | (uintptr_t)res) & 15) == 0, "cova_bn_act_fwd_t: 16-byte alignment");
+  const int V = s_dtype == COVA_F32 ? 4 : 8;
+  const int64_t nv = M * (C / V);
+  const int grid = ew_grid(nv, BN_THREADS);
   cudaStream_t st = (cudaStream_t)stream;
   if (s_dtype == COVA_F32 && y_dtype == COVA_F32)
-    bn_act_fwd_kernel<float, float><<<grid, BN_THREADS, 0, st>>>((const float*)x, n4, C, mean, invstd, gamma, beta, (const float*)res, relu, (float*)y, nullptr, nullptr, 0);
+    bn_act_fwd_kernel<float, float><<<grid, BN_THREADS, 2 * C * sizeof(float), st>>>((const float*)x, nv, C, mean, invstd, gamma, beta, (const float*)res, relu, (float*)y, nullptr, nullptr, 0);
   else if (s_dtype == COVA_BF16 && y_dtype == COVA_BF16)
-    bn_act_fwd_kernel<bf16_t, bf16_t><<<grid, BN_THREADS, 0, st>>>((const bf16_t*)x, n4, C, mean, invstd, gamma, beta, (const bf16_t*)res, relu, (bf16_t*)y, nullptr, nullptr, 0);
+    bn_act_fwd_kernel<bf16_t, bf16_t><<<grid, BN_THREADS, 2 * C * sizeof(float), st>>>((const bf16_t*)x, nv, C, mean, invstd, gamma, beta, (const bf16_t*)res, relu, (bf16_t*)y, nullptr, nullptr, 0);
   else if (s_dtype == COVA_BF16)
-    bn_act_fwd_kernel<bf16_t, float><<<grid, BN_THREADS, 0, st>>>((const bf16_t*)x, n4, C, mean, invstd, gamma, beta, (const bf16_t*)res, relu, (float*)y, nullptr, nullptr, 0);
+    bn_act_fwd_kernel<bf16_t, float><<<grid, BN_THREADS, 2 * C * sizeof(float), st>>>((const bf16_t*)x, nv, C, mean, invstd, gamma, beta, (const bf16_t*)res, relu, (float*)y, nullptr, nullptr, 0);
   else
     COVA_REQUIRE(false, "cova_bn_act_fwd_t: fp32 storage with a bf16 output is not built");
   COVA_LAUNCH_OK();
@@ -764,29 +864,29 @@ extern "C" int cova_bn_act_bwd_t(const void* dy, int dy_dtype, const void* x, co
                            (float*)dx, (float*)dres, dgamma, dbeta, stream);
   COVA_REQUIRE(s_dtype == COVA_BF16, "cova_bn_act_bwd_t: fp32 storage with a bf16 gradient is not built");
   COVA_REQUIRE(dy && x && dx && ws && mean && invstd && gamma && beta && M > 0, "cova_bn_act_bwd_t: bad arguments");
-  COVA_REQUIRE(bn_c_ok(C), "cova_bn_act_bwd_t: C=%d must be a power of two in [4, 1024]", C);
-  COVA_REQUIRE((((uintptr_t)x | (uintptr_t)res | (uintptr_t)dx | (uintptr_t)dres) & 7) == 0 &&
-                   ((uintptr_t)dy & (dy_dtype == COVA_F32 ? 15 : 7)) == 0, "cova_bn_act_bwd_t: alignment");
+  COVA_REQUIRE(bn_c_ok(C) && C >= 8, "cova_bn_act_bwd_t: C=%d must be a power of two in [8, 1024]", C);
+  COVA_REQUIRE((((uintptr_t)x | (uintptr_t)res | (uintptr_t)dx | (uintptr_t)dres | (uintptr_t)dy) & 15) == 0,
+               "cova_bn_act_bwd_t: 16-byte alignment");
   cudaStream_t st = (cudaStream_t)stream;
   COVA_CUDA_OK(cudaMemsetAsync(ws, 0, 2 * C * sizeof(double), st));
-  const int rows = BN_THREADS / (C / 4);
+  const int rows = BN_THREADS / (C / 8);
   const size_t smem = (size_t)2 * rows * C * sizeof(float);
   int64_t grid = (M + rows - 1) / rows;
   if (grid > (int64_t)sm_count() * 8) grid = (int64_t)sm_count() * 8;
-  const int64_t n4 = M * (C / 4);
-  const int g2 = ew_grid(n4, BN_THREADS);
+  const int64_t nv = M * (C / 8);
+  const int g2 = ew_grid(nv, BN_THREADS);
   const bf16_t *xb = (const bf16_t*)x, *rb = (const bf16_t*)res;
   if (dy_dtype == COVA_BF16) {
     bn_reduce_kernel<1, bf16_t, bf16_t><<<(int)grid, BN_THREADS, smem, st>>>(xb, (const bf16_t*)dy, rb, M, C, mean, invstd, gamma, beta, relu, ws);
     COVA_LAUNCH_OK();
-    bn_act_bwd_kernel<false, bf16_t, bf16_t><<<g2, BN_THREADS, 2 * C * sizeof(float), st>>>(
-        (const bf16_t*)dy, xb, rb, n4, M, C, mean, invstd, gamma, beta, relu, ws, (bf16_t*)dx, (bf16_t*)dres, dgamma, dbeta, nullptr,
+    bn_act_bwd_kernel<false, bf16_t, bf16_t><<<g2, BN_THREADS, 6 * C * sizeof(float), st>>>(
+        (const bf16_t*)dy, xb, rb, nv, M, C, mean, invstd, gamma, beta, relu, ws, (bf16_t*)dx, (bf16_t*)dres, dgamma, dbeta, nullptr,
         nullptr, nullptr, 0, 0, nullptr);
   } else {
     bn_reduce_kernel<1, bf16_t, float><<<(int)grid, BN_THREADS, smem, st>>>(xb, (const float*)dy, rb, M, C, mean, invstd, gamma, beta, relu, ws);
     COVA_LAUNCH_OK();
-    bn_act_bwd_kernel<false, bf16_t, float><<<g2, BN_THREADS, 2 * C * sizeof(float), st>>>(
-        (const float*)dy, xb, rb, n4, M, C, mean, invstd, gamma, beta, relu, ws, (bf16_t*)dx, (bf16_t*)dres, dgamma, dbeta, nullptr,
+    bn_act_bwd_kernel<false, bf16_t, float><<<g2, BN_THREADS, 6 * C * sizeof(float), st>>>(
+        (const float*)dy, xb, rb, nv, M, C, mean, invstd, gamma, beta, relu, ws, (bf16_t*)dx, (bf16_t*)dres, dgamma, dbeta, nullptr,
         nullptr, nullptr, 0, 0, nullptr);
   }
   COVA_LAUNCH_OK();
@@ -798,13 +898,12 @@ extern "C" int cova_maxpool3x3s2_fwd_t(const void* x, int dtype, int B, int H, i
   if (dtype == COVA_F32) return cova_maxpool3x3s2_fwd((const float*)x, B, H, W, C, (float*)y, code, nullptr, nullptr, COVA_BF16X2, stream);
   COVA_REQUIRE(dtype == COVA_BF16, "cova_maxpool3x3s2_fwd_t: dtype is fp32 or bf16");
   COVA_REQUIRE(x && y && B > 0 && H > 0 && W > 0 && C > 0 && C % 4 == 0, "cova_maxpool3x3s2_fwd_t: bad arguments");
-  COVA_REQUIRE((((uintptr_t)x | (uintptr_t)y) & 7) == 0 && ((uintptr_t)code & 3) == 0, "cova_maxpool3x3s2_fwd_t: alignment");
+  COVA_REQUIRE((((uintptr_t)x | (uintptr_t)y) & 7) == 0 && ((uintptr_t)code & 7) == 0, "cova_maxpool3x3s2_fwd_t: alignment");
   const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
-  const int64_t n = (int64_t)B * Ho * Wo * (C / 4);
-  if (n < (1LL << 31))
-    maxpool_fwd_kernel<uint32_t, bf16_t><<<ew_grid(n, 256), 256, 0, (cudaStream_t)stream>>>((const bf16_t*)x, B, H, W, C, Ho, Wo, (bf16_t*)y, code, nullptr, nullptr, 0);
-  else
-    maxpool_fwd_kernel<int64_t, bf16_t><<<ew_grid(n, 256), 256, 0, (cudaStream_t)stream>>>((const bf16_t*)x, B, H, W, C, Ho, Wo, (bf16_t*)y, code, nullptr, nullptr, 0);
+  COVA_REQUIRE(pool_c_ok(C) && Ho <= 65535 && B <= 65535, "cova_maxpool3x3s2_fwd_t: C / 8 must be a power of two, H/2 and B <= 65535");
+  const dim3 grid(ceil_div(Wo * (C / 8), 256), Ho, B);
+  maxpool_fwd_kernel<bf16_t><<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16_t*)x, H, W, C, Ho, Wo, ilog2(C / 8), (bf16_t*)y, code,
+                                                                    nullptr, nullptr, 0);
   COVA_LAUNCH_OK();
   return COVA_OK;
 }
@@ -814,13 +913,11 @@ extern "C" int cova_maxpool3x3s2_bwd_t(const unsigned char* code, const void* dy
   if (dtype == COVA_F32) return cova_maxpool3x3s2_bwd(code, (const float*)dy, B, H, W, C, (float*)dx, stream);
   COVA_REQUIRE(dtype == COVA_BF16, "cova_maxpool3x3s2_bwd_t: dtype is fp32 or bf16");
   COVA_REQUIRE(code && dy && dx && B > 0 && H > 0 && W > 0 && C > 0 && C % 4 == 0, "cova_maxpool3x3s2_bwd_t: bad arguments");
-  COVA_REQUIRE((((uintptr_t)dy | (uintptr_t)dx) & 7) == 0 && ((uintptr_t)code & 3) == 0, "cova_maxpool3x3s2_bwd_t: alignment");
+  COVA_REQUIRE((((uintptr_t)dy | (uintptr_t)dx) & 7) == 0 && ((uintptr_t)code & 7) == 0, "cova_maxpool3x3s2_bwd_t: alignment");
   const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
-  const int64_t n = (int64_t)B * H * W * (C / 4);
-  if (n < (1LL << 31))
-    maxpool_bwd_kernel<uint32_t, bf16_t><<<ew_grid(n, 256), 256, 0, (cudaStream_t)stream>>>(code, (const bf16_t*)dy, B, H, W, C, Ho, Wo, (bf16_t*)dx);
-  else
-    maxpool_bwd_kernel<int64_t, bf16_t><<<ew_grid(n, 256), 256, 0, (cudaStream_t)stream>>>(code, (const bf16_t*)dy, B, H, W, C, Ho, Wo, (bf16_t*)dx);
+  COVA_REQUIRE(pool_c_ok(C) && H <= 65535 && B <= 65535, "cova_maxpool3x3s2_bwd_t: C / 8 must be a power of two, H and B <= 65535");
+  const dim3 grid(ceil_div(W * (C / 8), 256), H, B);
+  maxpool_bwd_kernel<bf16_t><<<grid, 256, 0, (cudaStream_t)stream>>>(code, (const bf16_t*)dy, H, W, C, Ho, Wo, ilog2(C / 8), (bf16_t*)dx);
   COVA_LAUNCH_OK();
   return COVA_OK;
 }
