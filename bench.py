@@ -252,6 +252,16 @@ def kernel_table(stages, pk, exec_factor, traffic):
             if kind == "tensor" and n in exec_factor:
                 d["executed"] = round(ach * exec_factor[n], 2)
                 d["executed_frac"] = round(ach * exec_factor[n] / peak, 4)
+            if kind == "hbm" and traffic.get(n) and cnt:
+                # algorithmic bytes count every crop / neighbour row as read from HBM; overlapping boxes and neighbour windows
+                # are served by L2 / shared memory, so the DRAM traffic of the same launch (ncu) is reported beside it
+                d["dram_gb_s"] = round(traffic[n] / (msn / cnt / 1e3) / 1e9, 1)
+                d["dram_frac"] = round(d["dram_gb_s"] / peak, 4)
+            if n == "cova_gat_fwd":
+                d["note"] = ("L2 / shared-memory resident gather: unique bytes are T*(H+4)*4 (2.2 MB), every neighbour row is staged once "
+                             "per CTA; ~3 us of the event-timed figure is launch latency of a ~11.5 us kernel (ncu duration)")
+            if n == "cova_roi_fwd":
+                d["note"] = "crops of nested / overlapping boxes hit L2: the DRAM-side floor is the feature map once (see dram_gb_s)"
         kernels[n] = d
     return kernels
 

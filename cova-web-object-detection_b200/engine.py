@@ -219,8 +219,12 @@ class NativeForward:
         return out
 
     def forward(self, images, bboxes, additional_feats, context_indices, return_intermediates=False):
+        return self.forward_from_fm(self.feature_map(images), bboxes, additional_feats, context_indices, return_intermediates)
+
+    def forward_from_fm(self, fm, bboxes, additional_feats, context_indices, return_intermediates=False):
+        """A3-A8 on a given NHWC fp32 feature map (RoI pooling, positional encoder, GAT, decoder)."""
         m = self.m
-        fm = self.feature_map(images)
+        self.prepare()
         T = bboxes.shape[0]
         comb = torch.empty((T, m.n_total_feat), dtype=torch.float32, device=fm.device)
         self.own_into(fm, bboxes, additional_feats, comb)

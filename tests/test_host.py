@@ -194,3 +194,19 @@ def test_page_offsets_and_numa_binding_host_logic():
     assert page_offsets_of(torch.zeros(0, 5)).tolist() == [0]
     cores = bind_to_gpu_numa(0)
     assert cores is None or (isinstance(cores, list) and len(cores) > 0)
+
+
+def test_bench_alg_table_matches_abi_signatures():
+    """bench.py derives the algorithmic work of a launch from the ABI call's own arguments by POSITION: every entry must
+    name a declared symbol and index inside its argument list (a signature change must not silently zero a roofline)."""
+    import bench
+    from cova_b200 import _lib
+    table = bench._alg_table(1.0e6)
+    for name, fn in table.items():
+        assert name in _lib.SIGNATURES, name
+        nargs = len(_lib.SIGNATURES[name][1])
+        kind, work = fn([8] * nargs)
+        assert kind in ("tensor", "hbm") and work > 0, name
+    for cid, cfg in bench.CONFIGS.items():
+        assert cfg["mode"] in ("infer", "train") and cfg["backbone"] in ("resnet18", "resnet50")
+    assert bench.get_config(3)["precision"] == "bf16" and bench.get_config(2).get("precision", "fp32") == "fp32"
