@@ -10,7 +10,7 @@ int conv3x3_simt(const float* x, int B, int H, int W, const float* w, const floa
                  const float* res, int relu, float* y, cudaStream_t st);
 int conv3x3_tc(const void* x_hi, const void* x_lo, int split, int half, int B, int H, int W, const void* w_hi, const void* w_lo,
                const float* bn_scale, const float* bn_shift, const void* res_hi, const void* res_lo, int relu,
-               int out_dtype, void* y0, void* y1, cudaStream_t st);
+               int out_dtype, void* y0, void* y1, cudaStream_t st, double* stats = nullptr);
 int linear_simt(const float* x, int64_t ld_x, int M, int K, const float* w, int N, const float* bias,
                 const float* scale, const float* shift, const float* res, int64_t ld_res, int relu, float* y,
                 int64_t ld_y, cudaStream_t st);
@@ -43,10 +43,25 @@ extern "C" int cova_stem_fwd(const void* images, int img_dtype, int B, int H, in
                    (cudaStream_t)stream);
 }
 
+extern "C" int cova_conv3x3_bn_act_stats_fwd(const void* x0, const void* x1, int dtype, int B, int H, int W, int Cin, int Cout,
+                                             const void* w_a, const void* w_b, const float* bn_scale, const float* bn_shift,
+                                             const void* res0, const void* res1, int relu, int out_dtype, void* y0, void* y1,
+                                             int engine, double* stats_ws, void* stream);
+
 extern "C" int cova_conv3x3_bn_act_fwd(const void* x0, const void* x1, int dtype, int B, int H, int W, int Cin, int Cout,
                                        const void* w_a, const void* w_b, const float* bn_scale, const float* bn_shift,
                                        const void* res0, const void* res1, int relu, int out_dtype, void* y0, void* y1,
                                        int engine, void* stream) {
+  return cova_conv3x3_bn_act_stats_fwd(x0, x1, dtype, B, H, W, Cin, Cout, w_a, w_b, bn_scale, bn_shift, res0, res1, relu, out_dtype,
+                                       y0, y1, engine, nullptr, stream);
+}
+
+extern "C" int cova_conv3x3_bn_act_stats_fwd(const void* x0, const void* x1, int dtype, int B, int H, int W, int Cin, int Cout,
+                                             const void* w_a, const void* w_b, const float* bn_scale, const float* bn_shift,
+                                             const void* res0, const void* res1, int relu, int out_dtype, void* y0, void* y1,
+                                             int engine, double* stats_ws, void* stream) {
+  COVA_REQUIRE(!stats_ws || (engine == COVA_ENGINE_TCGEN05 && !res0 && !relu),
+               "cova_conv3x3_bn_act_stats_fwd: output statistics come with the tensor-core engine, no residual, no ReLU");
   COVA_REQUIRE(x0 && w_a && bn_scale && bn_shift && y0, "cova_conv3x3_bn_act_fwd: null pointer");
   COVA_REQUIRE(B > 0 && H > 0 && W > 0, "cova_conv3x3_bn_act_fwd: bad dims");
   COVA_REQUIRE(Cin == 64 && Cout == 64, "cova_conv3x3_bn_act_fwd: only Cin=Cout=64 is built (got %d->%d)", Cin, Cout);
@@ -66,7 +81,7 @@ extern "C" int cova_conv3x3_bn_act_fwd(const void* x0, const void* x1, int dtype
   COVA_REQUIRE(!split || (x1 && w_b), "cova_conv3x3_bn_act_fwd: BF16X2 needs lo planes for x and w");
   COVA_REQUIRE(!split || !res0 || res1, "cova_conv3x3_bn_act_fwd: BF16X2 residual needs its lo plane");
   COVA_REQUIRE((out_dtype != COVA_BF16X2 && out_dtype != COVA_F16X2) || y1, "cova_conv3x3_bn_act_fwd: split output needs the lo plane");
-  return conv3x3_tc(x0, x1, split, half, B, H, W, w_a, w_b, bn_scale, bn_shift, res0, res1, relu, out_dtype, y0, y1, st);
+  return conv3x3_tc(x0, x1, split, half, B, H, W, w_a, w_b, bn_scale, bn_shift, res0, res1, relu, out_dtype, y0, y1, st, stats_ws);
 }
 
 extern "C" int cova_linear_fwd(const float* x, int64_t ld_x, int M, int K, const void* w, int N, const float* bias,

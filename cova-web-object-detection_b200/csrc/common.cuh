@@ -130,4 +130,40 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
+// Column sums of a [32 lanes][32 values] register tile: lane l returns the sum over the warp's lanes of v[l] (v is clobbered).
+// 31 shuffles (16 + 8 + 4 + 2 + 1: every step halves the values a lane is responsible for) instead of 32 x 5.  Used by the
+// convolution epilogues (lane = pixel, value = output channel) to accumulate the BatchNorm batch statistics of the tile they
+// are writing, so that no separate pass has to re-read the raw convolution output.
+__device__ __forceinline__ float warp_transpose_sum32(float (&v)[32], int lane) {
+#pragma unroll
+  for (int step = 16; step >= 1; step >>= 1) {
+    const bool up = (lane & step) != 0;
+#pragma unroll
+    for (int i = 0; i < step; ++i) {
+      const float send = up ? v[i] : v[i + step];
+      const float keep = up ? v[i + step] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, step);
+    }
+  }
+  return v[0];
+}
+// The same for 16 values per lane: lanes l and l ^ 16 are added first, then the 16 x 16 transpose-reduce; lane l (and l + 16)
+// returns the total of v[l & 15].
+__device__ __forceinline__ float warp_transpose_sum16(float (&v)[16], int lane) {
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] += __shfl_xor_sync(0xffffffffu, v[i], 16);
+#pragma unroll
+  for (int step = 8; step >= 1; step >>= 1) {
+    const bool up = (lane & step) != 0;
+#pragma unroll
+    for (int i = 0; i < step; ++i) {
+      const float send = up ? v[i] : v[i + step];
+      const float keep = up ? v[i + step] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, step);
+    }
+  }
+  return v[0];
+}
+__device__ __forceinline__ float round_bf16(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
+
 }  // namespace cova

@@ -84,6 +84,7 @@ struct ConvTcParams {
                       // one-sector-per-line access pattern thrashes L1 line allocation; measured -13 % cycles)
   int res_pf_tiles;   // epilogue: L2-prefetch the residual rows this many iterations ahead (0 = off; 1 is the register prefetch)
   unsigned long long* dbg;   // optional per-CTA wait-cycle counters (cova_debug_buffer)
+  double* stats;             // optional [2][64]: sum y, sum y^2 over all pixels (raw mode: BatchNorm batch statistics), += here
 };
 
 // mbarrier wait that adds the cycles spent to `acc` when instrumentation is on
@@ -286,6 +287,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_cons
     };
     load_res(blockIdx.x);
     const bool res_pf = has_res && p.res_pf_tiles > 1;
+    double st_s = 0.0, st_q = 0.0;                  // running statistics of channel ch0 + lane
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
       const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
@@ -322,6 +324,18 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_cons
       ptx::tc_fence_before();
       ptx::mbar_arrive(&tail.tmem_empty[acc]);     // accumulator buffer is free for tile it+2
 
+      if (p.stats != nullptr) {   // raw mode (no residual / ReLU): statistics of the values as they are STORED (warp-collective)
+        float z[32], z2[32];
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {
+          float t = fmaf(o[c], tail.scale[ch0 + c], tail.shift[ch0 + c]);
+          if (OUT_DTYPE == COVA_BF16 && !HALF) t = round_bf16(t);
+          z[c] = inb ? t : 0.f;
+          z2[c] = z[c] * z[c];
+        }
+        st_s += (double)warp_transpose_sum32(z, lane);
+        st_q += (double)warp_transpose_sum32(z2, lane);
+      }
       if (!inb) continue;
 #pragma unroll
       for (int c = 0; c < 32; ++c) o[c] = fmaf(o[c], tail.scale[ch0 + c], tail.shift[ch0 + c]);
@@ -380,6 +394,10 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_cons
         }
       }
     }
+    if (p.stats != nullptr) {
+      atomicAdd(p.stats + ch0 + lane, st_s);
+      atomicAdd(p.stats + CT_C + ch0 + lane, st_q);
+    }
   }
 
   if (timed && warp == 2 && lane == 0) atomicAdd(p.dbg + blockIdx.x * 8 + 3, wc0);
@@ -407,7 +425,7 @@ static int launch_conv_tc(const CUtensorMap& xh, const CUtensorMap& xl, const CU
 
 int conv3x3_tc(const void* x_hi, const void* x_lo, int split, int half, int B, int H, int W, const void* w_hi, const void* w_lo,
                const float* bn_scale, const float* bn_shift, const void* res_hi, const void* res_lo, int relu,
-               int out_dtype, void* y0, void* y1, cudaStream_t st) {
+               int out_dtype, void* y0, void* y1, cudaStream_t st, double* stats) {
   CUtensorMap tx_hi, tx_lo, tw_hi, tw_lo;
   const uint64_t xd[4] = {(uint64_t)CT_C, (uint64_t)W, (uint64_t)H, (uint64_t)B};
   const uint64_t xs[3] = {(uint64_t)CT_C * 2, (uint64_t)W * CT_C * 2, (uint64_t)H * W * CT_C * 2};
@@ -438,6 +456,8 @@ int conv3x3_tc(const void* x_hi, const void* x_lo, int split, int half, int B, i
   p.res_pf_tiles = knob(COVA_KNOB_CONV_RES_PREFETCH, 1);
   p.res_load = knob(COVA_KNOB_CONV_RES_LOAD, 2);
   p.dbg = debug_words(8LL * sm_count());
+  p.stats = stats;
+  if (stats) COVA_CUDA_OK(cudaMemsetAsync(stats, 0, 2 * CT_C * sizeof(double), st));
 #define DISPATCH(SP)                                                                               \
   switch (out_dtype) {                                                                             \
     case COVA_F32: return launch_conv_tc<SP, COVA_F32>(tx_hi, tx_lo, tw_hi, tw_lo, p, st);         \

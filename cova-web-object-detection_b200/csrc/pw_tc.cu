@@ -37,6 +37,7 @@ struct PwParams {
   const __nv_bfloat16* res_lo;
   void* y0;
   void* y1;
+  double* stats;     // optional [2][COUT]: sum y, sum y^2 over all pixel rows (BatchNorm batch statistics of the output), += here
 };
 
 template <int KB, int COUT, bool SINGLE = false>
@@ -164,6 +165,9 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant_
     const int cbase = ((warp - 2) >> 2) * (COUT / 2);
     constexpr int NCHUNK = COUT / 64;              // 32-channel passes per warp
     const bool has_res = p.res_hi != nullptr;
+    double st_s[NCHUNK], st_q[NCHUNK];             // running statistics of this lane's channel (cbase + ch * 32 + lane)
+#pragma unroll
+    for (int ch = 0; ch < NCHUNK; ++ch) st_s[ch] = st_q[ch] = 0.0;
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
       const uint32_t acc = it & 1;
@@ -205,6 +209,18 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant_
         if (ch == NCHUNK - 1) {
           ptx::tc_fence_before();
           ptx::mbar_arrive(&tail.tmem_empty[acc]);
+        }
+        if (p.stats != nullptr) {   // raw mode (no residual / ReLU): statistics of the values as they are STORED (warp-collective)
+          float z[32], z2[32];
+#pragma unroll
+          for (int c = 0; c < 32; ++c) {
+            float t = fmaf(o[c], sm_scale[c0 + c], sm_shift[c0 + c]);
+            if (OUT_DTYPE == COVA_BF16) t = round_bf16(t);
+            z[c] = inb ? t : 0.f;
+            z2[c] = z[c] * z[c];
+          }
+          st_s[ch] += (double)warp_transpose_sum32(z, lane);
+          st_q[ch] += (double)warp_transpose_sum32(z2, lane);
         }
         if (!inb) continue;
 #pragma unroll
@@ -251,6 +267,13 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant_
         }
       }
     }
+    if (p.stats != nullptr) {
+#pragma unroll
+      for (int ch = 0; ch < NCHUNK; ++ch) {
+        atomicAdd(p.stats + cbase + ch * 32 + lane, st_s[ch]);
+        atomicAdd(p.stats + COUT + cbase + ch * 32 + lane, st_q[ch]);
+      }
+    }
   }
   ptx::tc_fence_before();
   __syncthreads();
@@ -276,7 +299,7 @@ static int launch_pw(const CUtensorMap& xh, const CUtensorMap& xl, const CUtenso
 
 static int pw_run(const void* x_hi, const void* x_lo, int64_t M, int Cin, int Cout, const void* w_packed, const float* bn_scale,
                   const float* bn_shift, const void* res_hi, const void* res_lo, int relu, int out_dtype, void* y0, void* y1,
-                  bool half, void* stream);
+                  bool half, void* stream, double* stats = nullptr);
 
 extern "C" int cova_conv1x1_bn_act_fwd(const void* x_hi, const void* x_lo, int64_t M, int Cin, int Cout,
                                        const void* w_packed, const float* bn_scale, const float* bn_shift,
@@ -285,19 +308,30 @@ extern "C" int cova_conv1x1_bn_act_fwd(const void* x_hi, const void* x_lo, int64
   return pw_run(x_hi, x_lo, M, Cin, Cout, w_packed, bn_scale, bn_shift, res_hi, res_lo, relu, out_dtype, y0, y1, false, stream);
 }
 
+extern "C" int cova_conv1x1_raw_stats_fwd(const void* x_hi, const void* x_lo, int planes_dtype, int64_t M, int Cin, int Cout,
+                                          const void* w_packed, const float* scale, const float* zero_shift, void* y,
+                                          double* stats_ws, void* stream);
+
 extern "C" int cova_conv1x1_raw_fwd(const void* x_hi, const void* x_lo, int planes_dtype, int64_t M, int Cin, int Cout,
                                     const void* w_packed, const float* scale, const float* zero_shift, void* y, void* stream) {
+  return cova_conv1x1_raw_stats_fwd(x_hi, x_lo, planes_dtype, M, Cin, Cout, w_packed, scale, zero_shift, y, nullptr, stream);
+}
+
+extern "C" int cova_conv1x1_raw_stats_fwd(const void* x_hi, const void* x_lo, int planes_dtype, int64_t M, int Cin, int Cout,
+                                          const void* w_packed, const float* scale, const float* zero_shift, void* y,
+                                          double* stats_ws, void* stream) {
   COVA_REQUIRE(planes_dtype == COVA_F16X2 || planes_dtype == COVA_BF16X2 || planes_dtype == COVA_BF16,
                "cova_conv1x1_raw_fwd: planes are split-fp16, split-bf16 or one bf16 plane");
   if (planes_dtype == COVA_BF16)   // bf16 training mode: x_lo unused, w_packed = bf16 [Cout][Cin], y = bf16 rows
-    return pw_run(x_hi, x_hi, M, Cin, Cout, w_packed, scale, zero_shift, nullptr, nullptr, 0, COVA_BF16, y, nullptr, false, stream);
+    return pw_run(x_hi, x_hi, M, Cin, Cout, w_packed, scale, zero_shift, nullptr, nullptr, 0, COVA_BF16, y, nullptr, false, stream,
+                  stats_ws);
   return pw_run(x_hi, x_lo, M, Cin, Cout, w_packed, scale, zero_shift, nullptr, nullptr, 0, COVA_F32, y, nullptr,
-                planes_dtype == COVA_F16X2, stream);
+                planes_dtype == COVA_F16X2, stream, stats_ws);
 }
 
 static int pw_run(const void* x_hi, const void* x_lo, int64_t M, int Cin, int Cout, const void* w_packed, const float* bn_scale,
                   const float* bn_shift, const void* res_hi, const void* res_lo, int relu, int out_dtype, void* y0, void* y1,
-                  bool half, void* stream) {
+                  bool half, void* stream, double* stats) {
   using namespace cova;
   COVA_REQUIRE(x_hi && x_lo && w_packed && bn_scale && bn_shift && y0, "cova_conv1x1_bn_act_fwd: null pointer");
   COVA_REQUIRE((Cin == 64 && (Cout == 64 || Cout == 256)) || (Cin == 256 && Cout == 64),
@@ -324,7 +358,9 @@ static int pw_run(const void* x_hi, const void* x_lo, int64_t M, int Cin, int Co
   p.bn_scale = bn_scale; p.bn_shift = bn_shift;
   p.res_hi = (const __nv_bfloat16*)res_hi; p.res_lo = (const __nv_bfloat16*)res_lo;
   p.y0 = y0; p.y1 = y1;
+  p.stats = stats;
   cudaStream_t st = (cudaStream_t)stream;
+  if (stats) COVA_CUDA_OK(cudaMemsetAsync(stats, 0, 2 * Cout * sizeof(double), st));
 #define GO(KB, CO) (out_dtype == COVA_BF16 ? launch_pw<KB, CO, COVA_BF16, false, true>(tx_hi, tx_lo, tw_hi, tw_lo, p, st) \
                     : half ? launch_pw<KB, CO, COVA_F32, true>(tx_hi, tx_lo, tw_hi, tw_lo, p, st)          \
                     : out_dtype == COVA_F32 ? launch_pw<KB, CO, COVA_F32>(tx_hi, tx_lo, tw_hi, tw_lo, p, st) \

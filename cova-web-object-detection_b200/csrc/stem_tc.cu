@@ -67,6 +67,7 @@ struct StemTcParams {
   void* out1;
   float* raw_out;                          // training mode: un-normalised, un-pooled conv output [B,Hc,Wc,64] fp32 (or NULL)
   int raw_bf16;                            // ... stored as bf16 instead (the bf16 training mode)
+  double* stats;                           // raw mode, optional [2][64]: sum y, sum y^2 over all conv pixels (BatchNorm statistics)
   unsigned long long* dbg;                 // optional wait-cycle counters (cova_debug_buffer), 8 words per CTA
   int pf_rows;                             // converter warps L2-prefetch the image row they will load this many turns ahead
 };
@@ -209,6 +210,7 @@ stem_tc_kernel(const StemTcParams p) {
     const int ch0 = ((warp - 1) >> 2) * SX_CH;     // this warp's output channels (SX_EPI_WARPS/4 warps per lane group)
     const int m = lg * 32 + lane;                  // conv column within the strip
     float acc_v[SX_CH];                            // running vertical max of the current pooling window
+    double st_s = 0.0, st_q = 0.0;                 // raw mode: running statistics of channel ch0 + (lane & 15)
     uint32_t t = 0;
     for (int strip = 0; strip < n_strips; ++strip) {
       const int ox = strip * SX_TM + m;
@@ -240,6 +242,22 @@ stem_tc_kernel(const StemTcParams p) {
         if (p.raw_out != nullptr) {
           // training mode (BatchNorm needs batch statistics of THIS tensor): write the raw conv row and skip the
           // pooling.  A band recomputes the conv row above it as pooling halo; only the owner band writes a row.
+          if (OUT_DTYPE != COVA_BF16X2 && p.stats != nullptr) {   // (raw outputs are fp32 or one bf16 plane: the split-plane
+            // inference instantiation carries none of this)  statistics of the values as they are STORED; every conv pixel
+            // is counted by its owner band
+            static_assert(SX_CH == 16, "warp_transpose_sum16");
+            const bool valid = oy >= 2 * py0 && ox < p.Wc;
+            float z[16], z2[16];
+#pragma unroll
+            for (int c = 0; c < 16; ++c) {
+              float tv = (SPLIT && HALF) ? v[c] * (1.f / SPLIT_F16_WSCALE) : v[c];
+              if (p.raw_bf16) tv = round_bf16(tv);
+              z[c] = valid ? tv : 0.f;
+              z2[c] = z[c] * z[c];
+            }
+            st_s += (double)warp_transpose_sum16(z, lane);
+            st_q += (double)warp_transpose_sum16(z2, lane);
+          }
           if (oy >= 2 * py0 && ox < p.Wc && p.raw_bf16) {
             __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.raw_out) + (((size_t)b * p.Hc + oy) * p.Wc + ox) * 64 + ch0;
 #pragma unroll
@@ -332,6 +350,10 @@ stem_tc_kernel(const StemTcParams p) {
           }
         }
       }
+    }
+    if (OUT_DTYPE != COVA_BF16X2 && p.raw_out != nullptr && p.stats != nullptr && lane < 16) {
+      atomicAdd(p.stats + ch0 + lane, st_s);
+      atomicAdd(p.stats + 64 + ch0 + lane, st_q);
     }
   } else {
     // ======================= converters: NCHW fp32 rows -> ring of 4-channel bf16 pixels =======================
@@ -542,10 +564,12 @@ static int launch_stem_tc(const StemTcParams& p, int grid, cudaStream_t st) {
 
 static int stem_tc_impl(const void* images, int img_u8, int B, int H, int W, const void* w_packed, const float* bn_scale,
                         const float* bn_shift, int out_dtype, void* out0, void* out1, cudaStream_t st, float* raw_out,
-                        bool split_f16 = false, bool raw_bf16 = false) {
+                        bool split_f16 = false, bool raw_bf16 = false, double* stats = nullptr) {
   StemTcParams p;
   p.raw_out = raw_out;
   p.raw_bf16 = raw_bf16 ? 1 : 0;
+  p.stats = raw_out ? stats : nullptr;
+  if (p.stats) COVA_CUDA_OK(cudaMemsetAsync(p.stats, 0, 2 * 64 * sizeof(double), st));
   p.img = images; p.B = B; p.H = H; p.W = W;
   p.Hc = (H + 6 - 7) / 2 + 1; p.Wc = (W + 6 - 7) / 2 + 1;
   p.Hp = (p.Hc + 2 - 3) / 2 + 1; p.Wp = (p.Wc + 2 - 3) / 2 + 1;
@@ -615,6 +639,22 @@ extern "C" int cova_stem_conv_raw_fwd(const void* images, int img_dtype, int B, 
   COVA_REQUIRE(((uintptr_t)out & 31) == 0, "cova_stem_conv_raw_fwd: out must be 32-byte aligned");
   return cova::stem_tc_impl(images, img_dtype == COVA_U8, B, H, W, w_packed, nullptr, nullptr, COVA_F32, out, nullptr,
                             (cudaStream_t)stream, out, w_dtype == COVA_F16X2);
+}
+
+// The raw conv1 entry points with the BatchNorm batch statistics of the output accumulated by the epilogue
+// (stats_ws: [2][64] doubles = sum y, sum y^2, zeroed here; feeds cova_bn_train_finalize directly - no separate statistics pass)
+extern "C" int cova_stem_conv_raw_stats_fwd(const void* images, int img_dtype, int B, int H, int W, const void* w_packed,
+                                            int w_dtype, void* out, double* stats_ws, void* stream) {
+  COVA_REQUIRE(w_dtype == COVA_BF16X2 || w_dtype == COVA_F16X2 || w_dtype == COVA_BF16,
+               "cova_stem_conv_raw_stats_fwd: w_dtype is the packed filter's format (COVA_BF16 = one bf16 product, bf16 output)");
+  COVA_REQUIRE(images && w_packed && out && B > 0 && H >= 7 && W >= 7, "cova_stem_conv_raw_stats_fwd: bad arguments");
+  COVA_REQUIRE(img_dtype == COVA_F32 || img_dtype == COVA_U8, "cova_stem_conv_raw_stats_fwd: images must be fp32 or uint8");
+  COVA_REQUIRE(((uintptr_t)out & 31) == 0, "cova_stem_conv_raw_stats_fwd: out must be 32-byte aligned");
+  if (w_dtype == COVA_BF16)
+    return cova::stem_tc_impl(images, img_dtype == COVA_U8, B, H, W, w_packed, nullptr, nullptr, COVA_BF16, out, nullptr,
+                              (cudaStream_t)stream, reinterpret_cast<float*>(out), false, true, stats_ws);
+  return cova::stem_tc_impl(images, img_dtype == COVA_U8, B, H, W, w_packed, nullptr, nullptr, COVA_F32, out, nullptr,
+                            (cudaStream_t)stream, reinterpret_cast<float*>(out), w_dtype == COVA_F16X2, false, stats_ws);
 }
 
 // bf16 training mode: conv1 in one bf16 product (filter from cova_pack_stem_weight: its hi plane), raw output stored as bf16

@@ -146,13 +146,24 @@ def pack_conv_weight(w_oihw, simt=True, tc=True, split=True):
     return s, hi, lo
 
 
-def conv3x3_bn_act_fwd(x, w_a, w_b, bn_scale, bn_shift, res=None, relu=True, out_dtype=None, engine=ENGINE_SIMT):
-    """3x3 s1 p1 conv (64->64) + folded BN (+ residual) (+ ReLU) on NHWC Planes."""
+def new_stats_ws(C, device):
+    """[2][C] doubles a raw-output convolution fills with sum y / sum y^2 of its output (-> bn_train_fwd(stats_ws=...))."""
+    return torch.empty(2 * C, dtype=torch.float64, device=device)
+
+
+def conv3x3_bn_act_fwd(x, w_a, w_b, bn_scale, bn_shift, res=None, relu=True, out_dtype=None, engine=ENGINE_SIMT, stats_ws=None):
+    """3x3 s1 p1 conv (64->64) + folded BN (+ residual) (+ ReLU) on NHWC Planes.  stats_ws (tensor-core engine, no residual /
+    ReLU): the epilogue also accumulates the BatchNorm batch statistics of the output into it."""
     B, H, W, C = x.shape
     out_dtype = x.dtype if out_dtype is None else out_dtype
     y = Planes(out_dtype, (B, H, W, C), x.p0.device)
     if res is not None and res.dtype != x.dtype:
         raise RuntimeError("cova_b200: residual must have the input's dtype")
+    if stats_ws is not None:
+        _call("cova_conv3x3_bn_act_stats_fwd", x.p0.data_ptr(), _ptr(x.p1), x.dtype, B, H, W, C, C, w_a.data_ptr(), _ptr(w_b),
+              bn_scale.data_ptr(), bn_shift.data_ptr(), 0, 0, int(relu), out_dtype, y.p0.data_ptr(), _ptr(y.p1), engine,
+              stats_ws.data_ptr(), _stream())
+        return y
     _call("cova_conv3x3_bn_act_fwd", x.p0.data_ptr(), _ptr(x.p1), x.dtype, B, H, W, C, C, w_a.data_ptr(), _ptr(w_b),
           bn_scale.data_ptr(), bn_shift.data_ptr(), _ptr(res.p0) if res is not None else 0,
           _ptr(res.p1) if res is not None else 0, int(relu), out_dtype, y.p0.data_ptr(), _ptr(y.p1), engine, _stream())
@@ -457,7 +468,7 @@ def _ones256(device):
     return _ONES256[k]
 
 
-def conv1x1_raw_fwd(x_planes, w_packed, scale=None):
+def conv1x1_raw_fwd(x_planes, w_packed, scale=None, stats_ws=None):
     """1x1 convolution of split-fp16 NHWC planes [..., Cin] with `pack_linear_weight_f16x2(w [Cout,Cin])` -> raw fp32
     [..., Cout].  `scale` ([>= Cout] device floats, e.g. the 1/s of scaled gradient planes) multiplies the result."""
     Cin = x_planes.shape[-1]
@@ -470,13 +481,13 @@ def conv1x1_raw_fwd(x_planes, w_packed, scale=None):
     if x_planes.dtype == BF16:           # bf16 training mode: w_packed = bf16 [Cout, Cin] (unscaled), bf16 rows out
         one, _ = _ones256(dev)
         y = torch.empty(tuple(x_planes.shape[:-1]) + (Cout,), dtype=torch.bfloat16, device=dev)
-        _call("cova_conv1x1_raw_fwd", x_planes.p0.data_ptr(), 0, BF16, M, Cin, Cout, w_packed.data_ptr(), one.data_ptr(),
-              zero.data_ptr(), y.data_ptr(), _stream())
+        _call("cova_conv1x1_raw_stats_fwd", x_planes.p0.data_ptr(), 0, BF16, M, Cin, Cout, w_packed.data_ptr(), one.data_ptr(),
+              zero.data_ptr(), y.data_ptr(), _ptr(stats_ws), _stream())
         return y
     sc = inv if scale is None else scale[:256] * (1.0 / 256.0)
     y = torch.empty(tuple(x_planes.shape[:-1]) + (Cout,), dtype=torch.float32, device=dev)
-    _call("cova_conv1x1_raw_fwd", x_planes.p0.data_ptr(), x_planes.p1.data_ptr(), x_planes.dtype, M, Cin, Cout,
-          w_packed.data_ptr(), sc.data_ptr(), zero.data_ptr(), y.data_ptr(), _stream())
+    _call("cova_conv1x1_raw_stats_fwd", x_planes.p0.data_ptr(), x_planes.p1.data_ptr(), x_planes.dtype, M, Cin, Cout,
+          w_packed.data_ptr(), sc.data_ptr(), zero.data_ptr(), y.data_ptr(), _ptr(stats_ws), _stream())
     return y
 
 
@@ -494,15 +505,15 @@ def conv1x1_wgrad(x_planes, dy_planes, inv_scale=None):
     return dw
 
 
-def stem_conv_raw_fwd(images, w_packed):
+def stem_conv_raw_fwd(images, w_packed, stats_ws=None):
     """conv1 alone (training mode): images [B,3,H,W] fp32 / uint8 NCHW -> raw conv output [B,H/2,W/2,64] fp32 NHWC.
     w_packed from pack_stem_weight (bf16: split-bf16 products) or pack_stem_weight_f16x2 (fp16: split-fp16)."""
     _cuda(images, None, "images")
     images = images.contiguous()
     B, C, H, W = images.shape
     out = torch.empty((B, (H - 1) // 2 + 1, (W - 1) // 2 + 1, 64), dtype=torch.float32, device=images.device)
-    _call("cova_stem_conv_raw_fwd", images.data_ptr(), U8 if images.dtype == torch.uint8 else F32, B, H, W,
-          w_packed.data_ptr(), F16X2 if w_packed.dtype == torch.float16 else BF16X2, out.data_ptr(), _stream())
+    _call("cova_stem_conv_raw_stats_fwd", images.data_ptr(), U8 if images.dtype == torch.uint8 else F32, B, H, W,
+          w_packed.data_ptr(), F16X2 if w_packed.dtype == torch.float16 else BF16X2, out.data_ptr(), _ptr(stats_ws), _stream())
     return out
 
 
@@ -524,18 +535,19 @@ def stem_wgrad(images, dy_planes, inv_scale=None):
 
 
 def bn_train_fwd(x, gamma, beta, running_mean, running_var, momentum, eps, res=None, relu=True, want_planes=False,
-                 planes_dtype=BF16X2, want_y=True):
+                 planes_dtype=BF16X2, want_y=True, stats_ws=None):
     """BatchNorm2d with batch statistics (+ residual) (+ ReLU) on an NHWC fp32 map x [..., C]; updates the running
     statistics in place (pass None to skip).  Returns (y, mean [C], invstd [C], split-bf16 Planes of y or None)."""
     _nhwc(x, "x")
     C = x.shape[-1]
     M = x.numel() // C
     dev = x.device
-    ws = torch.empty(2 * C, dtype=torch.float64, device=dev)
+    ws = stats_ws if stats_ws is not None else torch.empty(2 * C, dtype=torch.float64, device=dev)
     mean, inv = torch.empty(C, dtype=torch.float32, device=dev), torch.empty(C, dtype=torch.float32, device=dev)
     y = torch.empty_like(x) if (want_y or not want_planes) else None
     pl = _planes_like(x, planes_dtype) if want_planes else None
-    _call("cova_bn_train_stats", x.data_ptr(), M, C, ws.data_ptr(), _stream())
+    if stats_ws is None:                 # (else: the producing convolution's epilogue already accumulated them)
+        _call("cova_bn_train_stats", x.data_ptr(), M, C, ws.data_ptr(), _stream())
     _call("cova_bn_train_finalize", ws.data_ptr(), M, C, float(eps), float(momentum), mean.data_ptr(), inv.data_ptr(),
           _ptr(running_mean), _ptr(running_var), _stream())
     if running_mean is not None:          # raw-pointer buffer update: tell the derived-weight caches
@@ -653,29 +665,30 @@ def _map(t, name):
     return t
 
 
-def stem_conv_raw_fwd_bf16(images, w_packed):
+def stem_conv_raw_fwd_bf16(images, w_packed, stats_ws=None):
     """conv1 in one bf16 product: images [B,3,H,W] fp32 / uint8 -> raw conv output [B,H/2,W/2,64] bf16 NHWC."""
     _cuda(images, None, "images")
     images = images.contiguous()
     B, C, H, W = images.shape
     out = torch.empty((B, (H - 1) // 2 + 1, (W - 1) // 2 + 1, 64), dtype=torch.bfloat16, device=images.device)
-    _call("cova_stem_conv_raw_fwd_bf16", images.data_ptr(), U8 if images.dtype == torch.uint8 else F32, B, H, W,
-          w_packed.data_ptr(), out.data_ptr(), _stream())
+    _call("cova_stem_conv_raw_stats_fwd", images.data_ptr(), U8 if images.dtype == torch.uint8 else F32, B, H, W,
+          w_packed.data_ptr(), BF16, out.data_ptr(), _ptr(stats_ws), _stream())
     return out
 
 
-def bn_train_fwd_t(x, gamma, beta, running_mean, running_var, momentum, eps, res=None, relu=True, out_dtype=None):
+def bn_train_fwd_t(x, gamma, beta, running_mean, running_var, momentum, eps, res=None, relu=True, out_dtype=None, stats_ws=None):
     """`bn_train_fwd` on a map of either storage type (fp32 / bf16); y in `out_dtype` (default: x's).  Returns (y, mean, invstd)."""
     _map(x, "x")
     C = x.shape[-1]
     M = x.numel() // C
     dev = x.device
-    ws = torch.empty(2 * C, dtype=torch.float64, device=dev)
+    ws = stats_ws if stats_ws is not None else torch.empty(2 * C, dtype=torch.float64, device=dev)
     mean, inv = torch.empty(C, dtype=torch.float32, device=dev), torch.empty(C, dtype=torch.float32, device=dev)
     y = torch.empty(x.shape, dtype=out_dtype or x.dtype, device=dev)
     if res is not None and _map(res, "res").dtype != x.dtype:
         raise RuntimeError("cova_b200: the residual has the storage type of x")
-    _call("cova_bn_train_stats_t", x.data_ptr(), _dt(x), M, C, ws.data_ptr(), _stream())
+    if stats_ws is None:
+        _call("cova_bn_train_stats_t", x.data_ptr(), _dt(x), M, C, ws.data_ptr(), _stream())
     _call("cova_bn_train_finalize", ws.data_ptr(), M, C, float(eps), float(momentum), mean.data_ptr(), inv.data_ptr(),
           _ptr(running_mean), _ptr(running_var), _stream())
     if running_mean is not None:

@@ -362,23 +362,34 @@ def _unit_fwd(kind, xin, conv, bn, res=None, relu=True, want_y=True, want_planes
     u = _Unit()
     u.kind, u.xin, u.weight, u.bn, u.relu, u.has_res = kind, xin, conv.weight, bn, relu, res is not None
     w = conv.weight.detach().float()
+    # the convolution's epilogue accumulates the BatchNorm batch statistics of its output (COVA_B200_TRAIN_EPI_STATS=0: separate pass)
+    sw = ops.new_stats_ws(conv.out_channels, w.device) if _epi_stats(kind) else None
     if kind == "stem":
-        u.raw = ops.stem_conv_raw_fwd(xin, ops.pack_stem_weight_f16x2(w.contiguous()))
+        u.raw = ops.stem_conv_raw_fwd(xin, ops.pack_stem_weight_f16x2(w.contiguous()), stats_ws=sw)
     elif kind == 3:
         w_hi, w_lo = ops.pack_conv_weight_f16x2(w)
         one, zero = _ones_zeros(w.device)
-        u.raw = ops.conv3x3_bn_act_fwd(xin, w_hi, w_lo, one, zero, res=None, relu=False, out_dtype=F32, engine=ENGINE_TCGEN05).p0
+        u.raw = ops.conv3x3_bn_act_fwd(xin, w_hi, w_lo, one, zero, res=None, relu=False, out_dtype=F32, engine=ENGINE_TCGEN05,
+                                       stats_ws=sw).p0
     else:
-        u.raw = ops.conv1x1_raw_fwd(xin, ops.pack_linear_weight_f16x2(w.flatten(1)))
+        u.raw = ops.conv1x1_raw_fwd(xin, ops.pack_linear_weight_f16x2(w.flatten(1)), stats_ws=sw)
     track = bn.track_running_stats and bn.running_mean is not None
     mom = _momentum(bn, track)
     u.res = res if (relu and res is not None) else None
     u.y, u.mean, u.inv, u.planes = ops.bn_train_fwd(u.raw, bn.weight.detach(), bn.bias.detach(), bn.running_mean if track else None,
                                                     bn.running_var if track else None, mom, bn.eps, res=res, relu=relu,
-                                                    want_planes=want_planes, planes_dtype=F16X2, want_y=want_y)
+                                                    want_planes=want_planes, planes_dtype=F16X2, want_y=want_y, stats_ws=sw)
     if track and bn.num_batches_tracked is not None:
         bn.num_batches_tracked += 1
     return u
+
+
+def _epi_stats(kind=3):
+    """Which convolutions accumulate their output's BatchNorm statistics in the epilogue: COVA_B200_TRAIN_EPI_STATS = "3" (the
+    tensor-bound 3x3 convolutions, default), "all" (also the HBM-bound 1x1 / conv1 kernels, whose epilogues have no issue slots
+    to spare: measured slower than the separate pass) or "0" (none)."""
+    v = os.environ.get("COVA_B200_TRAIN_EPI_STATS", "3")
+    return v == "all" or (v == "3" and kind == 3)
 
 
 def _unit_bwd(u, dy, need_dx=True):
@@ -414,21 +425,22 @@ def _unit_fwd16(kind, xin, conv, bn, res=None, relu=True, out_fp32=False):
     u = _Unit()
     u.kind, u.xin, u.weight, u.bn, u.relu, u.has_res = kind, xin, conv.weight, bn, relu, res is not None
     w = conv.weight.detach().float()
+    sw = ops.new_stats_ws(conv.out_channels, w.device) if _epi_stats(kind) else None
     if kind == "stem":
-        u.raw = ops.stem_conv_raw_fwd_bf16(xin, ops.pack_stem_weight(w.contiguous()))
+        u.raw = ops.stem_conv_raw_fwd_bf16(xin, ops.pack_stem_weight(w.contiguous()), stats_ws=sw)
     elif kind == 3:
         _, w_hi, _ = ops.pack_conv_weight(w, simt=False, tc=True, split=False)
         one, zero = _ones_zeros(w.device)
         u.raw = ops.conv3x3_bn_act_fwd(ops.bf16_plane(xin), w_hi, None, one, zero, res=None, relu=False, out_dtype=ops.BF16,
-                                       engine=ENGINE_TCGEN05).p0
+                                       engine=ENGINE_TCGEN05, stats_ws=sw).p0
     else:
-        u.raw = ops.conv1x1_raw_fwd(ops.bf16_plane(xin), w.flatten(1).to(torch.bfloat16).contiguous())
+        u.raw = ops.conv1x1_raw_fwd(ops.bf16_plane(xin), w.flatten(1).to(torch.bfloat16).contiguous(), stats_ws=sw)
     track = bn.track_running_stats and bn.running_mean is not None
     mom = _momentum(bn, track)
     u.res = res if (relu and res is not None) else None
     u.y, u.mean, u.inv = ops.bn_train_fwd_t(u.raw, bn.weight.detach(), bn.bias.detach(), bn.running_mean if track else None,
                                             bn.running_var if track else None, mom, bn.eps, res=res, relu=relu,
-                                            out_dtype=torch.float32 if out_fp32 else torch.bfloat16)
+                                            out_dtype=torch.float32 if out_fp32 else torch.bfloat16, stats_ws=sw)
     u.planes = None
     if track and bn.num_batches_tracked is not None:
         bn.num_batches_tracked += 1

@@ -351,6 +351,21 @@ int cova_maxpool3x3s2_bwd_t(const unsigned char* code, const void* dy, int dtype
 int cova_stem_conv_raw_fwd_bf16(const void* images, int img_dtype, int B, int H, int W, const void* w_packed,
                                 void* out_bf16, void* stream);
 
+/* ---- BatchNorm batch statistics accumulated by the producing convolution's epilogue (A9): the raw-output convolutions of the
+ * train path with one more argument, stats_ws = [2][Cout] doubles (sum y, sum y^2 over all output pixels of the values as they
+ * are stored; zeroed by the call), which feeds cova_bn_train_finalize directly - the separate cova_bn_train_stats pass over the
+ * raw map is not needed.  cova_conv3x3_bn_act_stats_fwd needs the tensor-core engine, no residual, no ReLU;
+ * cova_stem_conv_raw_stats_fwd: w_dtype COVA_BF16X2 / COVA_F16X2 (fp32 output) or COVA_BF16 (one bf16 product, bf16 output). */
+int cova_conv3x3_bn_act_stats_fwd(const void* x0, const void* x1, int dtype, int B, int H, int W, int Cin, int Cout,
+                                  const void* w_a, const void* w_b, const float* bn_scale, const float* bn_shift,
+                                  const void* res0, const void* res1, int relu, int out_dtype, void* y0, void* y1,
+                                  int engine, double* stats_ws, void* stream);
+int cova_conv1x1_raw_stats_fwd(const void* x_hi, const void* x_lo, int planes_dtype, int64_t M, int Cin, int Cout,
+                               const void* w_packed, const float* scale, const float* zero_shift, void* y, double* stats_ws,
+                               void* stream);
+int cova_stem_conv_raw_stats_fwd(const void* images, int img_dtype, int B, int H, int W, const void* w_packed, int w_dtype,
+                                 void* out, double* stats_ws, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -563,3 +563,57 @@ def test_bf16_train_mode_close_to_fp32_parity_mode(backbone):
     for k in b32:
         if "running" in k:
             assert rel_err(n(b16[k]), n(b32[k])) < 2e-2, k
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+@pytest.mark.parametrize("shape", [(2, 37, 45), (1, 8, 16), (3, 64, 96)])
+def test_conv_epilogue_batch_statistics(mode, shape):
+    """BatchNorm batch statistics accumulated by the convolution epilogues (conv1, 3x3, the three 1x1 shapes; fp32-parity and
+    bf16 modes) against the separate statistics pass over the map the convolution wrote: ragged sizes (partial pixel tiles,
+    bands and strips must contribute nothing for the pixels they do not own), sum and sum of squares to 1e-5 (fp32 partial sums
+    in a different order; a sum near zero is measured against 1e-3 of the largest channel)."""
+    from cova_b200 import ops
+    B, H, W = shape
+    g = torch.Generator().manual_seed(B * 100 + H + W)
+
+    def stats_of(y):
+        C = y.shape[-1]
+        ws = torch.empty(2 * C, dtype=torch.float64, device=DEV)
+        ops._call("cova_bn_train_stats_t", y.data_ptr(), ops._dt(y), y.numel() // C, C, ws.data_ptr(), ops._stream())
+        return ws
+
+    def check(y, sw, what):
+        want = stats_of(y.contiguous())
+        err = float(((sw - want).abs() / (want.abs() + 1e-3 * want.abs().max())).max())
+        assert err < 1e-5, (what, err)
+
+    one, zero = torch.ones(64, device=DEV), torch.zeros(64, device=DEV)
+    img = torch.rand(B, 3, 2 * H, 2 * W, generator=g).to(DEV)
+    w7 = (torch.randn(64, 3, 7, 7, generator=g) * 0.05).to(DEV)
+    x64 = torch.randn(B, H, W, 64, generator=g).to(DEV)
+    w3 = (torch.randn(64, 64, 3, 3, generator=g) * 0.05).to(DEV)
+    if mode == "fp32":
+        sw = ops.new_stats_ws(64, DEV)
+        check(ops.stem_conv_raw_fwd(img, ops.pack_stem_weight_f16x2(w7), stats_ws=sw), sw, "stem")
+        sw = ops.new_stats_ws(64, DEV)
+        w_hi, w_lo = ops.pack_conv_weight_f16x2(w3)
+        y = ops.conv3x3_bn_act_fwd(ops.split_planes(x64, ops.F16X2), w_hi, w_lo, one, zero, relu=False, out_dtype=ops.F32,
+                                   engine=ops.ENGINE_TCGEN05, stats_ws=sw).p0
+        check(y, sw, "3x3")
+    else:
+        sw = ops.new_stats_ws(64, DEV)
+        check(ops.stem_conv_raw_fwd_bf16(img, ops.pack_stem_weight(w7), stats_ws=sw), sw, "stem")
+        sw = ops.new_stats_ws(64, DEV)
+        _, w_hi, _ = ops.pack_conv_weight(w3, simt=False, tc=True, split=False)
+        y = ops.conv3x3_bn_act_fwd(ops.bf16_plane(_bf(x64).contiguous()), w_hi, None, one, zero, relu=False, out_dtype=ops.BF16,
+                                   engine=ops.ENGINE_TCGEN05, stats_ws=sw).p0
+        check(y, sw, "3x3")
+    for cin, cout in ((64, 64), (64, 256), (256, 64)):
+        x = torch.randn(B, H, W, cin, generator=g).to(DEV)
+        w = (torch.randn(cout, cin, generator=g) * 0.1).to(DEV)
+        sw = ops.new_stats_ws(cout, DEV)
+        if mode == "fp32":
+            y = ops.conv1x1_raw_fwd(ops.split_planes(x, ops.F16X2), ops.pack_linear_weight_f16x2(w), stats_ws=sw)
+        else:
+            y = ops.conv1x1_raw_fwd(ops.bf16_plane(_bf(x).contiguous()), _bf(w).contiguous(), stats_ws=sw)
+        check(y, sw, "1x1 %d->%d" % (cin, cout))
