@@ -489,120 +489,199 @@ split_planes_scaled_kernel(const float* __restrict__ x, int64_t n4, __nv_bfloat1
 // ---------------------------------------------------------------- stem: BatchNorm(batch stats) + ReLU + maxpool, fused
 // The normalised [B,H,W,C] map between bn1 and the maxpool (1.7 GB at B=16) is never written: the forward pools
 // relu(bn(x)) on the fly from the raw conv1 output, the backward re-derives each input pixel's gradient from the
-// pooled gradient and the winner codes inside the BatchNorm reduction / apply passes.
+// pooled gradient and the winner codes inside the BatchNorm reduction / apply passes (and emits dx in the format its
+// consumer - conv1's wgrad - reads).  One thread = 8 channels; rows / pages come from the grid (forward) or from a
+// per-CTA row loop (backward): no per-element division (the first version of these kernels was index-math bound).
+template <typename TS, typename TY>
 __global__ void __launch_bounds__(256)
-bn_relu_pool_fwd_kernel(const float* __restrict__ x, int B, int H, int W, int C, int Ho, int Wo,
+bn_relu_pool_fwd_kernel(const TS* __restrict__ x, int H, int W, int C, int Ho, int Wo, int cshift,
                         const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ gamma,
-                        const float* __restrict__ beta, float* __restrict__ y, unsigned char* __restrict__ code,
+                        const float* __restrict__ beta, TY* __restrict__ y, unsigned char* __restrict__ code,
                         __nv_bfloat16* __restrict__ y_hi, __nv_bfloat16* __restrict__ y_lo, int f16) {
-  const int c4n = C >> 2;
-  const int64_t n = (int64_t)B * Ho * Wo * c4n;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    const int cg = (int)(i % c4n), c0 = 4 * cg;
-    const int64_t pix = i / c4n;
-    const int ow = (int)(pix % Wo), oh = (int)((pix / Wo) % Ho), b = (int)(pix / ((int64_t)Wo * Ho));
-    const float4 mu = *reinterpret_cast<const float4*>(mean + c0), iv = *reinterpret_cast<const float4*>(invstd + c0);
-    const float4 ga = *reinterpret_cast<const float4*>(gamma + c0), be = *reinterpret_cast<const float4*>(beta + c0);
-    float4 m = make_float4(-FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX);
-    int4 mi = make_int4(-1, -1, -1, -1);
-    for (int r = 0; r < 3; ++r) {
-      const int h = 2 * oh - 1 + r;
-      if (h < 0 || h >= H) continue;
-      for (int s2 = 0; s2 < 3; ++s2) {
-        const int w = 2 * ow - 1 + s2;
-        if (w < 0 || w >= W) continue;
-        const float4 xv = __ldg(reinterpret_cast<const float4*>(x + (((size_t)b * H + h) * W + w) * C) + cg);
-        const float4 v = make_float4(fmaxf(bn_val(xv.x, mu.x, iv.x, ga.x, be.x), 0.f), fmaxf(bn_val(xv.y, mu.y, iv.y, ga.y, be.y), 0.f),
-                                     fmaxf(bn_val(xv.z, mu.z, iv.z, ga.z, be.z), 0.f), fmaxf(bn_val(xv.w, mu.w, iv.w, ga.w, be.w), 0.f));
-        const int k = r * 3 + s2;
-        if (v.x > m.x || mi.x < 0) { m.x = v.x; mi.x = k; }
-        if (v.y > m.y || mi.y < 0) { m.y = v.y; mi.y = k; }
-        if (v.z > m.z || mi.z < 0) { m.z = v.z; mi.z = k; }
-        if (v.w > m.w || mi.w < 0) { m.w = v.w; mi.w = k; }
+  extern __shared__ __align__(16) float tab[];                       // [2][C]: A, B
+  for (int c = threadIdx.x; c < C; c += 256) bn_affine(mean[c], invstd[c], gamma[c], beta[c], tab[c], tab[C + c]);
+  __syncthreads();
+  const int t = blockIdx.x * 256 + threadIdx.x;
+  const int cvn = 1 << cshift;
+  if (t >= Wo * cvn) return;
+  const int cg = t & (cvn - 1), ow = t >> cshift, oh = blockIdx.y, b = blockIdx.z;
+  float A[8], Bc[8], m[8];
+  int mi[8];
+  ldp<8>(tab, 8 * cg, A);
+  ldp<8>(tab + C, 8 * cg, Bc);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { m[k] = -FLT_MAX; mi[k] = -1; }
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    const int h = 2 * oh - 1 + r;
+    if (h < 0 || h >= H) continue;
+#pragma unroll
+    for (int s2 = 0; s2 < 3; ++s2) {
+      const int w = 2 * ow - 1 + s2;
+      if (w < 0 || w >= W) continue;
+      float v[8];
+      ldv_any<8>(x, (int64_t)((((size_t)b * H + h) * W + w) * C) + 8 * cg, v);
+      const int kk = r * 3 + s2;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float yv = fmaxf(fmaf(v[k], A[k], Bc[k]), 0.f);
+        if (yv > m[k] || mi[k] < 0) { m[k] = yv; mi[k] = kk; }
       }
     }
-    reinterpret_cast<float4*>(y)[i] = m;
-    reinterpret_cast<uchar4*>(code)[i] = make_uchar4(mi.x, mi.y, mi.z, mi.w);
-    if (y_hi != nullptr) split4(m, y_hi, y_lo, (size_t)i * 4, f16);
+  }
+  const size_t o = ((((size_t)b * Ho + oh) * Wo + ow) * C) + 8 * cg;
+  if (y != nullptr) stv_any<8>(y, (int64_t)o, m);
+  *reinterpret_cast<uint2*>(code + o) = make_uint2((uint32_t)mi[0] | ((uint32_t)mi[1] << 8) | ((uint32_t)mi[2] << 16) | ((uint32_t)mi[3] << 24),
+                                                  (uint32_t)mi[4] | ((uint32_t)mi[5] << 8) | ((uint32_t)mi[6] << 16) | ((uint32_t)mi[7] << 24));
+  if (y_hi != nullptr) {
+    split4(make_float4(m[0], m[1], m[2], m[3]), y_hi, y_lo, o, f16);
+    split4(make_float4(m[4], m[5], m[6], m[7]), y_hi, y_lo, o + 4, f16);
   }
 }
 
-// gradient that reaches input pixel (b, h0, w0) of the pooled map through the <= 2 x 2 windows it won
-__device__ __forceinline__ float4 pool_gather(const unsigned char* __restrict__ code, const float* __restrict__ dyp, int b,
-                                              int h0, int w0, int cg, int c4n, int Ho, int Wo) {
-  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+// gradient that reaches 8 channels of input pixel (b, h0, w0) of the pooled map through the <= 2 x 2 windows it won
+template <typename TG>
+__device__ __forceinline__ void pool_gather8(const unsigned char* __restrict__ code, const TG* __restrict__ dyp, int b, int h0, int w0,
+                                             int cg, int C, int Ho, int Wo, float (&acc)[8]) {
+#pragma unroll
+  for (int k = 0; k < 8; ++k) acc[k] = 0.f;
   const int oh_hi = (h0 + 1) >> 1, ow_hi = (w0 + 1) >> 1;
   for (int oh = h0 >> 1; oh <= oh_hi; ++oh) {
     if (oh >= Ho) continue;
     for (int ow = w0 >> 1; ow <= ow_hi; ++ow) {
       if (ow >= Wo) continue;
-      const int me = (h0 - (2 * oh - 1)) * 3 + (w0 - (2 * ow - 1));
-      const size_t o = (((size_t)b * Ho + oh) * Wo + ow) * c4n + cg;
-      const uchar4 k = __ldg(reinterpret_cast<const uchar4*>(code) + o);
-      const float4 g = __ldg(reinterpret_cast<const float4*>(dyp) + o);
-      if (k.x == me) acc.x += g.x;
-      if (k.y == me) acc.y += g.y;
-      if (k.z == me) acc.z += g.z;
-      if (k.w == me) acc.w += g.w;
+      const uint32_t me = (uint32_t)((h0 - (2 * oh - 1)) * 3 + (w0 - (2 * ow - 1)));
+      const size_t o = ((((size_t)b * Ho + oh) * Wo + ow) * C) + 8 * cg;
+      const uint2 kc = __ldg(reinterpret_cast<const uint2*>(code + o));
+      float g[8];
+      ldv_any<8>(dyp, (int64_t)o, g);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (((kc.x >> (8 * k)) & 255u) == me) acc[k] += g[k];
+        if (((kc.y >> (8 * k)) & 255u) == me) acc[4 + k] += g[4 + k];
+      }
     }
   }
-  return acc;
 }
 
-// PASS 0: ws = [sum g | sum g*xhat];  PASS 1: dx = gamma*inv*(g - S1/M - xhat*S2/M), dgamma / dbeta from ws
-template <int PASS>
-__global__ void __launch_bounds__(BN_THREADS)
-bn_relu_pool_bwd_kernel(const float* __restrict__ x, const unsigned char* __restrict__ code, const float* __restrict__ dyp,
-                        int B, int H, int W, int C, int Ho, int Wo, const float* __restrict__ mean,
-                        const float* __restrict__ invstd, const float* __restrict__ gamma, const float* __restrict__ beta,
-                        double* __restrict__ ws, float* __restrict__ dx, float* __restrict__ dgamma,
-                        float* __restrict__ dbeta) {
-  extern __shared__ __align__(16) float sm[];           // PASS 0: [2][rows][C] partial sums; PASS 1: [2][C] S1/M, S2/M
-  const int c4n = C >> 2, rows = BN_THREADS / c4n;
-  const int cg = threadIdx.x % c4n, prow = threadIdx.x / c4n, c0 = 4 * cg;
+// PASS 0: ws = [sum g | sum g*xhat] (+ wmax: per-channel max|x - mean|, max|g|, for the PLANES scale bound)
+// PASS 1: dx = A g + c2 x + c1 (bn_act_bwd_kernel's form), stored in the map's type or as scaled split planes; dgamma / dbeta
+// CTA = a strided set of image rows (b, h); thread = 8 channels (fixed) of every (256 / cvn)-th pixel of the row.
+template <int PASS, bool PLANES, typename TS, typename TG>
+__global__ void __launch_bounds__(256)
+bn_relu_pool_bwd_kernel(const TS* __restrict__ x, const unsigned char* __restrict__ code, const TG* __restrict__ dyp, int B, int H,
+                        int W, int C, int Ho, int Wo, int cshift, const float* __restrict__ mean, const float* __restrict__ invstd,
+                        const float* __restrict__ gamma, const float* __restrict__ beta, double* __restrict__ ws,
+                        unsigned int* __restrict__ wmax, TS* __restrict__ dx, __nv_bfloat16* __restrict__ dx_hi,
+                        __nv_bfloat16* __restrict__ dx_lo, int f16, int target_log2, float* __restrict__ inv_vec,
+                        float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  extern __shared__ __align__(16) float sm[];           // PASS 0: [2][ppi][C] partial sums; PASS 1: [2][C] S1/M, S2/M
+  __shared__ float s_red[8];
+  __shared__ float s_scale;
+  const int cvn = 1 << cshift, ppi = 256 >> cshift;     // channel groups, pixels per iteration
+  const int cg = threadIdx.x & (cvn - 1), wl = threadIdx.x >> cshift, c0 = 8 * cg;
   const int64_t M = (int64_t)B * H * W;
-  const float4 mu = *reinterpret_cast<const float4*>(mean + c0), iv = *reinterpret_cast<const float4*>(invstd + c0);
-  const float4 ga = *reinterpret_cast<const float4*>(gamma + c0), be = *reinterpret_cast<const float4*>(beta + c0);
+  float A[8], Bc[8], p2[8], p3[8];                      // PASS 0: p2 = mean, p3 = invstd;  PASS 1: p2 = c1, p3 = c2
+  {
+    float mu[8], iv[8], ga[8], be[8];
+    ldp<8>(mean, c0, mu); ldp<8>(invstd, c0, iv); ldp<8>(gamma, c0, ga); ldp<8>(beta, c0, be);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      bn_affine(mu[k], iv[k], ga[k], be[k], A[k], Bc[k]);
+      p2[k] = mu[k]; p3[k] = iv[k];
+    }
+  }
+  float scale = 1.f;
   if (PASS == 1) {
     if (blockIdx.x == 0)
-      for (int c = threadIdx.x; c < C; c += BN_THREADS) { dbeta[c] = (float)ws[c]; dgamma[c] = (float)ws[C + c]; }
-    for (int c = threadIdx.x; c < 2 * C; c += BN_THREADS) sm[c] = (float)(ws[c] / (double)M);
+      for (int c = threadIdx.x; c < C; c += 256) { dbeta[c] = (float)ws[c]; dgamma[c] = (float)ws[C + c]; }
+    for (int c = threadIdx.x; c < 2 * C; c += 256) sm[c] = (float)(ws[c] / (double)M);
     __syncthreads();
+    if (PLANES) {
+      const float gmax = __uint_as_float(wmax[C]);
+      float bound = 0.f;
+      for (int c = threadIdx.x; c < C; c += 256) {
+        const float iv = invstd[c];
+        bound = fmaxf(bound, fabsf(gamma[c] * iv) * (gmax + fabsf(sm[c]) + __uint_as_float(wmax[c]) * iv * fabsf(sm[C + c])));
+      }
+      bound = warp_max(bound);
+      if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = bound;
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        float m = 0.f;
+        for (int w = 0; w < 8; ++w) m = fmaxf(m, s_red[w]);
+        s_scale = pow2_scale(__float_as_uint(m), target_log2);
+      }
+      __syncthreads();
+      scale = s_scale;
+      if (blockIdx.x == 0) inv_vec[threadIdx.x] = 1.f / scale;
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float mu = p2[k], iv = p3[k];
+      const float c2 = -A[k] * iv * sm[C + c0 + k];
+      p2[k] = fmaf(-c2, mu, -A[k] * sm[c0 + k]);        // c1
+      p3[k] = c2;
+    }
   }
-  float4 a = make_float4(0.f, 0.f, 0.f, 0.f), bsum = a;
-  const int64_t stride = (int64_t)gridDim.x * rows;
-  for (int64_t p = (int64_t)blockIdx.x * rows + prow; p < M; p += stride) {
-    const int w0 = (int)(p % W), h0 = (int)((p / W) % H), b = (int)(p / ((int64_t)W * H));
-    const float4 xv = __ldg(reinterpret_cast<const float4*>(x + p * C + c0));
-    float4 g = pool_gather(code, dyp, b, h0, w0, cg, c4n, Ho, Wo);
-    const float4 xh = make_float4((xv.x - mu.x) * iv.x, (xv.y - mu.y) * iv.y, (xv.z - mu.z) * iv.z, (xv.w - mu.w) * iv.w);
-    g.x = bn_val(xv.x, mu.x, iv.x, ga.x, be.x) > 0.f ? g.x : 0.f;
-    g.y = bn_val(xv.y, mu.y, iv.y, ga.y, be.y) > 0.f ? g.y : 0.f;
-    g.z = bn_val(xv.z, mu.z, iv.z, ga.z, be.z) > 0.f ? g.z : 0.f;
-    g.w = bn_val(xv.w, mu.w, iv.w, ga.w, be.w) > 0.f ? g.w : 0.f;
-    if (PASS == 0) {
-      a.x += g.x; a.y += g.y; a.z += g.z; a.w += g.w;
-      bsum.x = fmaf(g.x, xh.x, bsum.x); bsum.y = fmaf(g.y, xh.y, bsum.y);
-      bsum.z = fmaf(g.z, xh.z, bsum.z); bsum.w = fmaf(g.w, xh.w, bsum.w);
-    } else {
-      const float4 s1 = *reinterpret_cast<const float4*>(sm + c0), s2 = *reinterpret_cast<const float4*>(sm + C + c0);
-      float4 o;
-      o.x = ga.x * iv.x * (g.x - s1.x - xh.x * s2.x);
-      o.y = ga.y * iv.y * (g.y - s1.y - xh.y * s2.y);
-      o.z = ga.z * iv.z * (g.z - s1.z - xh.z * s2.z);
-      o.w = ga.w * iv.w * (g.w - s1.w - xh.w * s2.w);
-      *reinterpret_cast<float4*>(dx + p * C + c0) = o;
+  float a[8], bs[8], mx[8];
+  float gm = 0.f;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) a[k] = bs[k] = mx[k] = 0.f;
+  for (int row = blockIdx.x; row < B * H; row += gridDim.x) {
+    const int b = row / H, h0 = row - b * H;
+    for (int w0 = wl; w0 < W; w0 += ppi) {
+      const size_t e = (((size_t)row * W + w0) * C) + c0;
+      float xv[8], g[8];
+      ldv_any<8>(x, (int64_t)e, xv);
+      pool_gather8<TG>(code, dyp, b, h0, w0, cg, C, Ho, Wo, g);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        g[k] = fmaf(xv[k], A[k], Bc[k]) > 0.f ? g[k] : 0.f;
+        if (PASS == 0) {
+          const float xc = xv[k] - p2[k];
+          a[k] += g[k];
+          bs[k] = fmaf(g[k], xc * p3[k], bs[k]);
+          if (PLANES) { mx[k] = fmaxf(mx[k], fabsf(xc)); gm = fmaxf(gm, fabsf(g[k])); }
+        } else {
+          g[k] = fmaf(A[k], g[k], fmaf(p3[k], xv[k], p2[k]));
+          if (PLANES) g[k] *= scale;
+        }
+      }
+      if (PASS == 1) {
+        if (PLANES) {
+          split4(make_float4(g[0], g[1], g[2], g[3]), dx_hi, dx_lo, e, f16);
+          split4(make_float4(g[4], g[5], g[6], g[7]), dx_hi, dx_lo, e + 4, f16);
+        } else {
+          stv_any<8>(dx, (int64_t)e, g);
+        }
+      }
     }
   }
   if (PASS == 0) {
-    *reinterpret_cast<float4*>(sm + (size_t)prow * C + c0) = a;
-    *reinterpret_cast<float4*>(sm + (size_t)(rows + prow) * C + c0) = bsum;
+    float* ra = sm + (size_t)wl * C + c0;
+    float* rb = sm + (size_t)(ppi + wl) * C + c0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { ra[k] = a[k]; rb[k] = bs[k]; }
     __syncthreads();
-    for (int c = threadIdx.x; c < 2 * C; c += BN_THREADS) {
+    for (int c = threadIdx.x; c < 2 * C; c += 256) {
       const int which = c / C, ch = c % C;
       double t = 0.0;
-      for (int r = 0; r < rows; ++r) t += (double)sm[(size_t)(which * rows + r) * C + ch];
+      for (int r = 0; r < ppi; ++r) t += (double)sm[(size_t)(which * ppi + r) * C + ch];
       atomicAdd(ws + c, t);
+    }
+    if (PLANES) {
+      __syncthreads();
+#pragma unroll
+      for (int k = 0; k < 8; ++k) ra[k] = mx[k];
+      __syncthreads();
+      for (int c = threadIdx.x; c < C; c += 256) {
+        float m = 0.f;
+        for (int r = 0; r < ppi; ++r) m = fmaxf(m, sm[(size_t)r * C + c]);
+        atomicMax(wmax + c, __float_as_uint(m));
+      }
+      gm = warp_max(gm);
+      if ((threadIdx.x & 31) == 0) atomicMax(wmax + C, __float_as_uint(gm));
     }
   }
 }
@@ -768,51 +847,89 @@ extern "C" int cova_split_planes_scaled(const float* x, int64_t n, void* hi, voi
   return COVA_OK;
 }
 
+typedef __nv_bfloat16 bf16_t;
+static bool dt_ok(int d) { return d == COVA_F32 || d == COVA_BF16; }
+
+extern "C" int cova_bn_relu_pool_fwd_t(const void* x, int s_dtype, int B, int H, int W, int C, const float* mean, const float* invstd,
+                                       const float* gamma, const float* beta, void* y, int y_dtype, unsigned char* code,
+                                       void* y_hi, void* y_lo, int planes_dtype, void* stream) {
+  COVA_REQUIRE(x && code && (y || y_hi) && mean && invstd && gamma && beta && B > 0 && H > 0 && W > 0, "cova_bn_relu_pool_fwd_t: bad arguments");
+  COVA_REQUIRE(dt_ok(s_dtype) && dt_ok(y_dtype) && s_dtype == y_dtype, "cova_bn_relu_pool_fwd_t: x and y are both fp32 or both bf16");
+  COVA_REQUIRE(bn_c_ok(C) && C >= 8, "cova_bn_relu_pool_fwd_t: C=%d must be a power of two in [8, 1024]", C);
+  COVA_REQUIRE((y_hi == nullptr) == (y_lo == nullptr), "cova_bn_relu_pool_fwd_t: the split planes come together");
+  COVA_REQUIRE(planes_dtype == COVA_BF16X2 || planes_dtype == COVA_F16X2, "cova_bn_relu_pool_fwd_t: planes are split-bf16 or split-fp16");
+  COVA_REQUIRE((((uintptr_t)x | (uintptr_t)y | (uintptr_t)y_hi | (uintptr_t)y_lo) & 15) == 0 && ((uintptr_t)code & 7) == 0,
+               "cova_bn_relu_pool_fwd_t: alignment");
+  const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
+  COVA_REQUIRE(Ho <= 65535 && B <= 65535, "cova_bn_relu_pool_fwd_t: H/2 and B <= 65535");
+  const dim3 grid(ceil_div(Wo * (C / 8), 256), Ho, B);
+  const size_t smem = (size_t)2 * C * sizeof(float);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (s_dtype == COVA_F32)
+    bn_relu_pool_fwd_kernel<float, float><<<grid, 256, smem, st>>>((const float*)x, H, W, C, Ho, Wo, ilog2(C / 8), mean, invstd, gamma, beta,
+                                                                  (float*)y, code, (__nv_bfloat16*)y_hi, (__nv_bfloat16*)y_lo,
+                                                                  planes_dtype == COVA_F16X2);
+  else
+    bn_relu_pool_fwd_kernel<bf16_t, bf16_t><<<grid, 256, smem, st>>>((const bf16_t*)x, H, W, C, Ho, Wo, ilog2(C / 8), mean, invstd, gamma,
+                                                                    beta, (bf16_t*)y, code, (__nv_bfloat16*)y_hi, (__nv_bfloat16*)y_lo,
+                                                                    planes_dtype == COVA_F16X2);
+  COVA_LAUNCH_OK();
+  return COVA_OK;
+}
+
+extern "C" int cova_bn_relu_pool_bwd_t(const void* x, int s_dtype, const unsigned char* code, const void* dy_pooled, int dy_dtype,
+                                       int B, int H, int W, int C, const float* mean, const float* invstd, const float* gamma,
+                                       const float* beta, double* ws, unsigned int* ws_max, void* dx, void* dx_hi, void* dx_lo,
+                                       int planes_dtype, int target_log2, float* inv_scale_vec, float* dgamma, float* dbeta,
+                                       void* stream) {
+  const bool planes = dx_hi != nullptr;
+  COVA_REQUIRE(x && code && dy_pooled && ws && (dx || planes) && dgamma && dbeta && mean && invstd && gamma && beta && B > 0 && H > 0 && W > 0,
+               "cova_bn_relu_pool_bwd_t: bad arguments");
+  COVA_REQUIRE(dt_ok(s_dtype) && dt_ok(dy_dtype) && s_dtype == dy_dtype, "cova_bn_relu_pool_bwd_t: x and dy are both fp32 or both bf16");
+  COVA_REQUIRE(!planes || (s_dtype == COVA_F32 && dx_lo && ws_max && inv_scale_vec), "cova_bn_relu_pool_bwd_t: plane output goes with fp32 maps");
+  COVA_REQUIRE(bn_c_ok(C) && C >= 8, "cova_bn_relu_pool_bwd_t: C=%d must be a power of two in [8, 1024]", C);
+  COVA_REQUIRE(planes_dtype == COVA_BF16X2 || planes_dtype == COVA_F16X2, "cova_bn_relu_pool_bwd_t: planes are split-bf16 or split-fp16");
+  COVA_REQUIRE((((uintptr_t)x | (uintptr_t)dy_pooled | (uintptr_t)dx) & 15) == 0 && ((uintptr_t)code & 7) == 0 &&
+                   (((uintptr_t)dx_hi | (uintptr_t)dx_lo) & 7) == 0, "cova_bn_relu_pool_bwd_t: alignment");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
+  COVA_CUDA_OK(cudaMemsetAsync(ws, 0, 2 * C * sizeof(double), st));
+  if (planes) COVA_CUDA_OK(cudaMemsetAsync(ws_max, 0, (C + 1) * sizeof(unsigned int), st));
+  const int cs = ilog2(C / 8), ppi = 256 >> cs;
+  int grid = B * H < sm_count() * 8 ? B * H : sm_count() * 8;
+  const size_t sm0 = (size_t)2 * ppi * C * sizeof(float), sm1 = (size_t)2 * C * sizeof(float);
+  const int f16 = planes_dtype == COVA_F16X2;
+#define COVA_POOL_BWD(PL, TS, TG)                                                                                              \
+  do {                                                                                                                         \
+    bn_relu_pool_bwd_kernel<0, PL, TS, TG><<<grid, 256, sm0, st>>>((const TS*)x, code, (const TG*)dy_pooled, B, H, W, C, Ho, Wo, cs, mean, \
+        invstd, gamma, beta, ws, ws_max, nullptr, nullptr, nullptr, f16, target_log2, nullptr, nullptr, nullptr);              \
+    COVA_LAUNCH_OK();                                                                                                          \
+    bn_relu_pool_bwd_kernel<1, PL, TS, TG><<<grid, 256, sm1, st>>>((const TS*)x, code, (const TG*)dy_pooled, B, H, W, C, Ho, Wo, cs, mean, \
+        invstd, gamma, beta, ws, ws_max, (TS*)dx, (__nv_bfloat16*)dx_hi, (__nv_bfloat16*)dx_lo, f16, target_log2, inv_scale_vec,   \
+        dgamma, dbeta);                                                                                                        \
+  } while (0)
+  if (s_dtype == COVA_BF16) COVA_POOL_BWD(false, bf16_t, bf16_t);
+  else if (planes) COVA_POOL_BWD(true, float, float);
+  else COVA_POOL_BWD(false, float, float);
+#undef COVA_POOL_BWD
+  COVA_LAUNCH_OK();
+  return COVA_OK;
+}
+
 extern "C" int cova_bn_relu_pool_fwd(const float* x, int B, int H, int W, int C, const float* mean, const float* invstd,
                                      const float* gamma, const float* beta, float* y, unsigned char* code, void* y_hi,
                                      void* y_lo, int planes_dtype, void* stream) {
-  COVA_REQUIRE(x && y && code && mean && invstd && gamma && beta && B > 0 && H > 0 && W > 0, "cova_bn_relu_pool_fwd: bad arguments");
-  COVA_REQUIRE(bn_c_ok(C), "cova_bn_relu_pool_fwd: C=%d must be a power of two in [4, 1024]", C);
-  COVA_REQUIRE((y_hi == nullptr) == (y_lo == nullptr), "cova_bn_relu_pool_fwd: the split planes come together");
-  COVA_REQUIRE(planes_dtype == COVA_BF16X2 || planes_dtype == COVA_F16X2, "cova_bn_relu_pool_fwd: planes are split-bf16 or split-fp16");
-  COVA_REQUIRE((((uintptr_t)x | (uintptr_t)y | (uintptr_t)y_hi | (uintptr_t)y_lo) & 15) == 0 && ((uintptr_t)code & 7) == 0,
-               "cova_bn_relu_pool_fwd: alignment");
-  const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
-  const int64_t n = (int64_t)B * Ho * Wo * (C / 4);
-  bn_relu_pool_fwd_kernel<<<ew_grid(n, 256), 256, 0, (cudaStream_t)stream>>>(
-      x, B, H, W, C, Ho, Wo, mean, invstd, gamma, beta, y, code, (__nv_bfloat16*)y_hi, (__nv_bfloat16*)y_lo,
-      planes_dtype == COVA_F16X2);
-  COVA_LAUNCH_OK();
-  return COVA_OK;
+  return cova_bn_relu_pool_fwd_t(x, COVA_F32, B, H, W, C, mean, invstd, gamma, beta, y, COVA_F32, code, y_hi, y_lo, planes_dtype, stream);
 }
 
 extern "C" int cova_bn_relu_pool_bwd(const float* x, const unsigned char* code, const float* dy_pooled, int B, int H, int W,
                                      int C, const float* mean, const float* invstd, const float* gamma, const float* beta,
                                      double* ws, float* dx, float* dgamma, float* dbeta, void* stream) {
-  COVA_REQUIRE(x && code && dy_pooled && ws && dx && dgamma && dbeta && mean && invstd && gamma && beta && B > 0 && H > 0 && W > 0,
-               "cova_bn_relu_pool_bwd: bad arguments");
-  COVA_REQUIRE(bn_c_ok(C), "cova_bn_relu_pool_bwd: C=%d must be a power of two in [4, 1024]", C);
-  COVA_REQUIRE((((uintptr_t)x | (uintptr_t)dy_pooled | (uintptr_t)dx) & 15) == 0 && ((uintptr_t)code & 7) == 0,
-               "cova_bn_relu_pool_bwd: alignment");
-  cudaStream_t st = (cudaStream_t)stream;
-  const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
-  COVA_CUDA_OK(cudaMemsetAsync(ws, 0, 2 * C * sizeof(double), st));
-  const int rows = BN_THREADS / (C / 4);
-  const int64_t M = (int64_t)B * H * W;
-  int64_t grid = (M + rows - 1) / rows;
-  if (grid > (int64_t)sm_count() * 8) grid = (int64_t)sm_count() * 8;
-  bn_relu_pool_bwd_kernel<0><<<(int)grid, BN_THREADS, (size_t)2 * rows * C * sizeof(float), st>>>(
-      x, code, dy_pooled, B, H, W, C, Ho, Wo, mean, invstd, gamma, beta, ws, nullptr, nullptr, nullptr);
-  COVA_LAUNCH_OK();
-  bn_relu_pool_bwd_kernel<1><<<(int)grid, BN_THREADS, (size_t)6 * C * sizeof(float), st>>>(
-      x, code, dy_pooled, B, H, W, C, Ho, Wo, mean, invstd, gamma, beta, ws, dx, dgamma, dbeta);
-  COVA_LAUNCH_OK();
-  return COVA_OK;
+  return cova_bn_relu_pool_bwd_t(x, COVA_F32, code, dy_pooled, COVA_F32, B, H, W, C, mean, invstd, gamma, beta, ws, nullptr, dx, nullptr,
+                                 nullptr, COVA_F16X2, 10, nullptr, dgamma, dbeta, stream);
 }
 
 // ---------------------------------------------------------------- typed entry points (bf16 training mode)
-static bool dt_ok(int d) { return d == COVA_F32 || d == COVA_BF16; }
-typedef __nv_bfloat16 bf16_t;
 
 extern "C" int cova_bn_train_stats_t(const void* x, int x_dtype, int64_t M, int C, double* ws, void* stream) {
   if (x_dtype == COVA_F32) return cova_bn_train_stats((const float*)x, M, C, ws, stream);

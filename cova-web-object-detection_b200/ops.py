@@ -737,3 +737,51 @@ def bf16_plane(t):
     pl = Planes.__new__(Planes)
     pl.dtype, pl.shape, pl.p0, pl.p1 = BF16, tuple(t.shape), t, None
     return pl
+
+
+def bn_relu_pool_fwd_t(x, gamma, beta, running_mean, running_var, momentum, eps, want_planes=False, planes_dtype=F16X2, stats_ws=None):
+    """The stem's tail fused on an fp32 or bf16 map: BatchNorm2d(batch statistics) + ReLU + MaxPool2d(3,2,1) of the raw conv1
+    output x [B,H,W,C] without the normalised map.  Returns (y pooled in x's type, codes uint8, mean, invstd, Planes of y | None)."""
+    _map(x, "x")
+    B, H, W, C = x.shape
+    M = B * H * W
+    dev = x.device
+    ws = stats_ws if stats_ws is not None else torch.empty(2 * C, dtype=torch.float64, device=dev)
+    mean, inv = torch.empty(C, dtype=torch.float32, device=dev), torch.empty(C, dtype=torch.float32, device=dev)
+    if stats_ws is None:
+        _call("cova_bn_train_stats_t", x.data_ptr(), _dt(x), M, C, ws.data_ptr(), _stream())
+    _call("cova_bn_train_finalize", ws.data_ptr(), M, C, float(eps), float(momentum), mean.data_ptr(), inv.data_ptr(),
+          _ptr(running_mean), _ptr(running_var), _stream())
+    if running_mean is not None:
+        global param_generation
+        param_generation += 1
+    y = torch.empty((B, (H - 1) // 2 + 1, (W - 1) // 2 + 1, C), dtype=x.dtype, device=dev)
+    code = torch.empty(y.shape, dtype=torch.uint8, device=dev)
+    pl = _planes_like(y, planes_dtype) if want_planes else None
+    _call("cova_bn_relu_pool_fwd_t", x.data_ptr(), _dt(x), B, H, W, C, mean.data_ptr(), inv.data_ptr(), gamma.data_ptr(),
+          beta.data_ptr(), y.data_ptr(), _dt(y), code.data_ptr(), pl.p0.data_ptr() if pl else 0, pl.p1.data_ptr() if pl else 0,
+          planes_dtype, _stream())
+    return y, code, mean, inv, pl
+
+
+def bn_relu_pool_bwd_t(x, code, dy_pooled, mean, invstd, gamma, beta, planes=False, planes_dtype=F16X2, target_log2=10):
+    """Backward of `bn_relu_pool_fwd_t`.  planes=False: (dx in x's type, None, dgamma, dbeta); planes=True (fp32 maps): (scaled
+    split Planes of dx, inv_scale_vec, dgamma, dbeta) - the operand of conv1's tensor-core wgrad."""
+    _map(x, "x"); _map(dy_pooled, "dy")
+    B, H, W, C = x.shape
+    dev = x.device
+    ws = torch.empty(2 * C, dtype=torch.float64, device=dev)
+    dg, db = torch.empty(C, dtype=torch.float32, device=dev), torch.empty(C, dtype=torch.float32, device=dev)
+    if planes:
+        wmax = torch.empty(C + 1, dtype=torch.int32, device=dev)
+        pl = _planes_like(x, planes_dtype)
+        inv = torch.empty(256, dtype=torch.float32, device=dev)
+        _call("cova_bn_relu_pool_bwd_t", x.data_ptr(), _dt(x), code.data_ptr(), dy_pooled.data_ptr(), _dt(dy_pooled), B, H, W, C,
+              mean.data_ptr(), invstd.data_ptr(), gamma.data_ptr(), beta.data_ptr(), ws.data_ptr(), wmax.data_ptr(), 0,
+              pl.p0.data_ptr(), pl.p1.data_ptr(), planes_dtype, int(target_log2), inv.data_ptr(), dg.data_ptr(), db.data_ptr(), _stream())
+        return pl, inv, dg, db
+    dx = torch.empty_like(x)
+    _call("cova_bn_relu_pool_bwd_t", x.data_ptr(), _dt(x), code.data_ptr(), dy_pooled.data_ptr(), _dt(dy_pooled), B, H, W, C,
+          mean.data_ptr(), invstd.data_ptr(), gamma.data_ptr(), beta.data_ptr(), ws.data_ptr(), 0, dx.data_ptr(), 0, 0, planes_dtype,
+          int(target_log2), 0, dg.data_ptr(), db.data_ptr(), _stream())
+    return dx, None, dg, db

@@ -491,15 +491,35 @@ class _BackboneFn(torch.autograd.Function):
             def unit(kind, src, conv, bn, res=None, relu=True, want_y=True, want_planes=False, last=False):
                 return _unit_fwd(kind, src, conv, bn, res=res, relu=relu, want_y=want_y, want_planes=want_planes)
             operand = lambda u: u.planes
-        stem = unit("stem", images, convnet[0], convnet[1], relu=True, want_y=True)
-        units.append(stem)
-        if bf16:
-            x, code = ops.maxpool3x3s2_fwd_t(stem.y)
-            xp = x
+        ctx.fused_stem = os.environ.get("COVA_B200_TRAIN_STEM_FUSED", "1") == "1"
+        if ctx.fused_stem:
+            # conv1 -> [bn1 + ReLU + maxpool fused: the normalised 640^2 map is never written, forward or backward]
+            stem = _Unit()
+            bn, w = convnet[1], convnet[0].weight.detach().float().contiguous()
+            stem.kind, stem.xin, stem.weight, stem.bn = "stem", images, convnet[0].weight, bn
+            sw = ops.new_stats_ws(64, w.device) if _epi_stats("stem") else None
+            stem.raw = (ops.stem_conv_raw_fwd_bf16(images, ops.pack_stem_weight(w), stats_ws=sw) if bf16
+                        else ops.stem_conv_raw_fwd(images, ops.pack_stem_weight_f16x2(w), stats_ws=sw))
+            track = bn.track_running_stats and bn.running_mean is not None
+            x, code, stem.mean, stem.inv, pl = ops.bn_relu_pool_fwd_t(
+                stem.raw, bn.weight.detach(), bn.bias.detach(), bn.running_mean if track else None,
+                bn.running_var if track else None, _momentum(bn, track), bn.eps, want_planes=not bf16, planes_dtype=F16X2, stats_ws=sw)
+            if track and bn.num_batches_tracked is not None:
+                bn.num_batches_tracked += 1
+            stem.y = stem.planes = stem.res = None
+            xp = x if bf16 else pl
+            units.append(stem)
+            ctx.pool = (code, None)
         else:
-            x, code, xp = ops.maxpool3x3s2_fwd(stem.y, want_planes=True, planes_dtype=F16X2)
-        ctx.pool = (code, tuple(stem.y.shape))
-        stem.y = None                                            # the 640^2 map is not needed again (the ReLU mask comes from raw)
+            stem = unit("stem", images, convnet[0], convnet[1], relu=True, want_y=True)
+            units.append(stem)
+            if bf16:
+                x, code = ops.maxpool3x3s2_fwd_t(stem.y)
+                xp = x
+            else:
+                x, code, xp = ops.maxpool3x3s2_fwd(stem.y, want_planes=True, planes_dtype=F16X2)
+            ctx.pool = (code, tuple(stem.y.shape))
+            stem.y = None                                            # the 640^2 map is not needed again (the ReLU mask comes from raw)
         plan = []
         for bi, blk in enumerate(blocks):
             last = bi + 1 == len(blocks)
@@ -550,9 +570,33 @@ class _BackboneFn(torch.autograd.Function):
                 grads[start + 1], grads[start] = p2, p1
                 g = d1.add_(dres)
         code, shape = ctx.pool
-        g = ops.maxpool3x3s2_bwd_t(code, g, shape) if ctx.bf16 else ops.maxpool3x3s2_bwd(code, g, shape)
-        _, *p0, _ = ubwd(units[0], g, need_dx=False)
-        grads[0] = p0
+        if ctx.fused_stem:
+            u = units[0]
+            bn = u.bn
+            gam, bet = bn.weight.detach(), bn.bias.detach()
+            in_shape = tuple(u.raw.shape)
+            if os.environ.get("COVA_B200_TRAIN_STEM_FUSED_BWD", "0") == "1":
+                # gather-in-the-passes backward (no dense pooled-gradient map at all): fewer bytes, but ~25 instructions per
+                # element against an issue budget of ~20 - measured slower (2.6 vs 1.9 ms at B=16), kept as a memory option
+                if ctx.bf16:
+                    dxr, _, dg0, db0 = ops.bn_relu_pool_bwd_t(u.raw, code, g, u.mean, u.inv, gam, bet)
+                    dyp, inv = ops.bf16_plane(dxr), None
+                else:
+                    dyp, inv, dg0, db0 = ops.bn_relu_pool_bwd_t(u.raw, code, g, u.mean, u.inv, gam, bet, planes=True, planes_dtype=F16X2)
+            elif ctx.bf16:
+                gd = ops.maxpool3x3s2_bwd_t(code, g, in_shape)
+                dxr, _, dg0, db0 = ops.bn_train_bwd_t(gd, u.raw, u.mean, u.inv, gam, bet, res=None, relu=True)
+                dyp, inv = ops.bf16_plane(dxr), None
+            else:
+                gd = ops.maxpool3x3s2_bwd(code, g, in_shape)
+                dyp, inv, _, dg0, db0 = ops.bn_train_bwd_planes(gd, u.raw, u.mean, u.inv, gam, bet, res=None, relu=True, planes_dtype=F16X2)
+            dw0 = ops.stem_wgrad(u.xin, dyp, inv)
+            u.raw = u.xin = None
+            grads[0] = [dw0, dg0, db0]
+        else:
+            g = ops.maxpool3x3s2_bwd_t(code, g, shape) if ctx.bf16 else ops.maxpool3x3s2_bwd(code, g, shape)
+            _, *p0, _ = ubwd(units[0], g, need_dx=False)
+            grads[0] = p0
         flat = []
         for dw, dg, db in grads:
             flat += [dw, dg, db]

@@ -366,6 +366,19 @@ int cova_conv1x1_raw_stats_fwd(const void* x_hi, const void* x_lo, int planes_dt
 int cova_stem_conv_raw_stats_fwd(const void* images, int img_dtype, int B, int H, int W, const void* w_packed, int w_dtype,
                                  void* out, double* stats_ws, void* stream);
 
+/* ---- The stem's tail fused, typed (default of the training path): BatchNorm(batch statistics) + ReLU + MaxPool2d(3,2,1) of the
+ * raw conv1 output without the normalised 640^2 map, forward and backward, on fp32 or bf16 maps (x / y / dy share the type).
+ *   fwd: y (pooled, may be NULL when the planes are wanted alone), winner codes, optional split planes of y (fp32 maps).
+ *   bwd: from the pooled gradient and the codes, dx of the raw map either in the map's type (dx) or - fp32 maps - as scaled
+ *        split planes for conv1's wgrad (dx_hi / dx_lo, ws_max = C+1 words, inv_scale_vec = 256 x 1/s); dgamma / dbeta.  */
+int cova_bn_relu_pool_fwd_t(const void* x, int s_dtype, int B, int H, int W, int C, const float* mean, const float* invstd,
+                            const float* gamma, const float* beta, void* y, int y_dtype, unsigned char* code, void* y_hi,
+                            void* y_lo, int planes_dtype, void* stream);
+int cova_bn_relu_pool_bwd_t(const void* x, int s_dtype, const unsigned char* code, const void* dy_pooled, int dy_dtype, int B,
+                            int H, int W, int C, const float* mean, const float* invstd, const float* gamma, const float* beta,
+                            double* ws, unsigned int* ws_max, void* dx, void* dx_hi, void* dx_lo, int planes_dtype,
+                            int target_log2, float* inv_scale_vec, float* dgamma, float* dbeta, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
