@@ -51,4 +51,24 @@ inline int make_tmap_bf16(CUtensorMap* map, const void* base, int rank, const ui
   return COVA_OK;
 }
 
+// fp32 matrix [rows][cols] (row pitch in bytes, a multiple of 16), box {box_cols, box_rows}, NO swizzle, zero fill outside:
+// the raw activation tiles of linear_tc.cu (converted to split planes on the way from shared memory to shared memory).
+inline int make_tmap_f32_2d(CUtensorMap* map, const void* base, uint64_t cols, uint64_t rows, uint64_t pitch_bytes,
+                            uint32_t box_cols, uint32_t box_rows) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (!fn) {
+    set_error("cuTensorMapEncodeTiled is not available from the driver");
+    return COVA_ERR_CUDA;
+  }
+  cuuint64_t gd[2] = {cols, rows}, gs[1] = {pitch_bytes};
+  cuuint32_t bx[2] = {box_cols, box_rows}, es[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(fp32) failed with CUresult %d", (int)r);
+    return COVA_ERR_CUDA;
+  }
+  return COVA_OK;
+}
+
 }  // namespace cova
