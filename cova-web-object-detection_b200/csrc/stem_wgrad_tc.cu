@@ -169,7 +169,9 @@ stem_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_dy_hi, const __grid_
             for (int r = 0; r < 7; ++r) {
               const uint32_t row = ring0 + ((g0 + r) % SW_R) * SW_ROW_BYTES + kk * 256;        // 16 pixels x 16 B
               ptx::umma_bf16(d_tmem + r * 32, da, sw_desc_noswz(row, 128, 16), idesc, first);
-              ptx::umma_bf16(d_tmem + r * 32, da, sw_desc_noswz(row + SW_R * SW_ROW_BYTES, 128, 16), idesc, 1u);
+              // bf16 training mode (one dY plane): the forward convolved bf16(image), so the gradient of what was computed
+              // takes the hi plane of the image alone - half the MMAs
+              if (!p.dy_single) ptx::umma_bf16(d_tmem + r * 32, da, sw_desc_noswz(row + SW_R * SW_ROW_BYTES, 128, 16), idesc, 1u);
             }
           }
           ptx::umma_commit(&sm.mma_done[t % SW_ND]);
