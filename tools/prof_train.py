@@ -9,7 +9,7 @@ from torch.profiler import profile, ProfilerActivity
 dev = torch.device("cuda", 0)
 bk = os.environ.get("BACKBONE", "resnet18")
 B = int(os.environ.get("B", "16"))
-m = CoVA((3, 3), 1280, 4, True, 384, 32, 0, 0.2, None, pretrained=False, backbone=bk)
+m = CoVA((3, 3), 1280, 4, True, 384, 32, 0, 0.2, None, pretrained=False, backbone=bk, precision=os.environ.get("PRECISION", "fp32"))
 m.load_state_dict(synth.make_state_dict(123, backbone=bk), strict=True)
 m = m.to(dev).train()
 opt = FlatAdam(m.parameters(), lr=5e-4, weight_decay=1e-3)
