@@ -185,7 +185,7 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant_
 #pragma unroll
           for (int j = 0; j < 2; ++j) {
             ld_global_nc_v8(p.res_hi + row + c0 + j * 16, rh[j]);
-            ld_global_nc_v8(p.res_lo + row + c0 + j * 16, rl[j]);
+            if (!SINGLE) ld_global_nc_v8(p.res_lo + row + c0 + j * 16, rl[j]);
           }
         }
         uint32_t v[2][16];
@@ -230,8 +230,13 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant_
           for (int j = 0; j < 2; ++j)
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
-              o[j * 16 + 2 * e] += bf16lo_to_f32(rh[j][e]) + bf16lo_to_f32(rl[j][e]);
-              o[j * 16 + 2 * e + 1] += bf16hi_to_f32(rh[j][e]) + bf16hi_to_f32(rl[j][e]);
+              if (SINGLE) {     // bf16 training mode: the residual (e.g. the skip branch's gradient) is one bf16 plane
+                o[j * 16 + 2 * e] += bf16lo_to_f32(rh[j][e]);
+                o[j * 16 + 2 * e + 1] += bf16hi_to_f32(rh[j][e]);
+              } else {
+                o[j * 16 + 2 * e] += bf16lo_to_f32(rh[j][e]) + bf16lo_to_f32(rl[j][e]);
+                o[j * 16 + 2 * e + 1] += bf16hi_to_f32(rh[j][e]) + bf16hi_to_f32(rl[j][e]);
+              }
             }
         }
         if (p.relu) {
@@ -311,6 +316,8 @@ extern "C" int cova_conv1x1_bn_act_fwd(const void* x_hi, const void* x_lo, int64
 extern "C" int cova_conv1x1_raw_stats_fwd(const void* x_hi, const void* x_lo, int planes_dtype, int64_t M, int Cin, int Cout,
                                           const void* w_packed, const float* scale, const float* zero_shift, void* y,
                                           double* stats_ws, void* stream);
+extern "C" int cova_conv1x1_raw_res_fwd(const void* x, int64_t M, int Cin, int Cout, const void* w_bf16, const float* scale,
+                                        const float* zero_shift, const void* res_bf16, void* y_bf16, void* stream);
 
 extern "C" int cova_conv1x1_raw_fwd(const void* x_hi, const void* x_lo, int planes_dtype, int64_t M, int Cin, int Cout,
                                     const void* w_packed, const float* scale, const float* zero_shift, void* y, void* stream) {
@@ -327,6 +334,14 @@ extern "C" int cova_conv1x1_raw_stats_fwd(const void* x_hi, const void* x_lo, in
                   stats_ws);
   return pw_run(x_hi, x_lo, M, Cin, Cout, w_packed, scale, zero_shift, nullptr, nullptr, 0, COVA_F32, y, nullptr,
                 planes_dtype == COVA_F16X2, stream, stats_ws);
+}
+
+// bf16 training mode: y = x W^T + res on single bf16 planes (a dgrad with the skip branch's gradient added in the epilogue: no
+// separate elementwise add pass over the 256-channel map)
+extern "C" int cova_conv1x1_raw_res_fwd(const void* x, int64_t M, int Cin, int Cout, const void* w_bf16, const float* scale,
+                                        const float* zero_shift, const void* res_bf16, void* y_bf16, void* stream) {
+  COVA_REQUIRE(x && w_bf16 && scale && zero_shift && res_bf16 && y_bf16, "cova_conv1x1_raw_res_fwd: null pointer");
+  return pw_run(x, x, M, Cin, Cout, w_bf16, scale, zero_shift, res_bf16, res_bf16, 0, COVA_BF16, y_bf16, nullptr, false, stream, nullptr);
 }
 
 static int pw_run(const void* x_hi, const void* x_lo, int64_t M, int Cin, int Cout, const void* w_packed, const float* bn_scale,

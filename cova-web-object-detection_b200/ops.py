@@ -468,6 +468,17 @@ def _ones256(device):
     return _ONES256[k]
 
 
+def conv1x1_raw_res_fwd_bf16(x, w_bf16, res):
+    """bf16 training mode: x [.., Cin] bf16 @ w_bf16 [Cout, Cin]^T + res [.., Cout] bf16 -> bf16 (dgrad + skip-branch gradient)."""
+    Cin, Cout = x.shape[-1], w_bf16.shape[0]
+    M = x.numel() // Cin
+    one, zero = _ones256(x.device)
+    y = torch.empty(tuple(x.shape[:-1]) + (Cout,), dtype=torch.bfloat16, device=x.device)
+    _call("cova_conv1x1_raw_res_fwd", x.data_ptr(), M, Cin, Cout, w_bf16.data_ptr(), one.data_ptr(), zero.data_ptr(),
+          _map(res, "res").data_ptr(), y.data_ptr(), _stream())
+    return y
+
+
 def conv1x1_raw_fwd(x_planes, w_packed, scale=None, stats_ws=None):
     """1x1 convolution of split-fp16 NHWC planes [..., Cin] with `pack_linear_weight_f16x2(w [Cout,Cin])` -> raw fp32
     [..., Cout].  `scale` ([>= Cout] device floats, e.g. the 1/s of scaled gradient planes) multiplies the result."""

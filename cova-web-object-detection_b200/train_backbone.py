@@ -447,7 +447,7 @@ def _unit_fwd16(kind, xin, conv, bn, res=None, relu=True, out_fp32=False):
     return u
 
 
-def _unit_bwd16(u, dy, need_dx=True):
+def _unit_bwd16(u, dy, need_dx=True, add=None):
     """Backward of `_unit_fwd16`: dy fp32 (the feature-map gradient) or bf16; bf16 gradient maps throughout (bf16 has fp32's
     exponent range: no scaling), fp32 weight gradients from the single-plane tensor-core wgrad kernels."""
     bn = u.bn
@@ -459,14 +459,16 @@ def _unit_bwd16(u, dy, need_dx=True):
     if u.kind == "stem":
         dw = ops.stem_wgrad(u.xin, dyp, None)
     elif u.kind == 3:
-        if need_dx:
+        if need_dx:        # `add` (the skip branch's gradient) rides in the dgrad convolution's residual epilogue: no add pass
             _, w_hi, _ = ops.pack_conv_weight(w.flip(2, 3).transpose(0, 1).contiguous(), simt=False, tc=True, split=False)
             one, zero = _ones_zeros(dxr.device)
-            dx = ops.conv3x3_bn_act_fwd(dyp, w_hi, None, one, zero, res=None, relu=False, out_dtype=ops.BF16, engine=ENGINE_TCGEN05).p0
+            dx = ops.conv3x3_bn_act_fwd(dyp, w_hi, None, one, zero, res=None if add is None else ops.bf16_plane(add), relu=False,
+                                        out_dtype=ops.BF16, engine=ENGINE_TCGEN05).p0
         dw = ops.conv3x3_wgrad(ops.bf16_plane(u.xin), dyp, None)
     else:
         if need_dx:
-            dx = ops.conv1x1_raw_fwd(dyp, w.flatten(1).t().to(torch.bfloat16).contiguous())
+            wt = w.flatten(1).t().to(torch.bfloat16).contiguous()
+            dx = ops.conv1x1_raw_fwd(dyp, wt) if add is None else ops.conv1x1_raw_res_fwd_bf16(dxr, wt, add)
         dw = ops.conv1x1_wgrad(ops.bf16_plane(u.xin), dyp, None)
     u.raw = u.res = u.xin = u.mean = u.inv = None
     return dx, dw, dg, db, dres
@@ -556,19 +558,24 @@ class _BackboneFn(torch.autograd.Function):
             if bottleneck:
                 d3, *p3, dres = ubwd(us[2], g)
                 d2, *p2, _ = ubwd(us[1], d3)
-                d1, *p1, _ = ubwd(us[0], d2)
-                grads[start + 2], grads[start + 1], grads[start] = p3, p2, p1
                 if has_ds:
                     dd, *pd, _ = ubwd(us[3], dres)
                     grads[start + 3] = pd
-                    g = d1.add_(dd)
+                    dres = dd
+                if ctx.bf16:           # the skip gradient is added by conv1's dgrad epilogue
+                    g, *p1, _ = ubwd(us[0], d2, add=dres)
                 else:
+                    d1, *p1, _ = ubwd(us[0], d2)
                     g = d1.add_(dres)
+                grads[start + 2], grads[start + 1], grads[start] = p3, p2, p1
             else:
                 d2, *p2, dres = ubwd(us[1], g)
-                d1, *p1, _ = ubwd(us[0], d2)
+                if ctx.bf16:
+                    g, *p1, _ = ubwd(us[0], d2, add=dres)
+                else:
+                    d1, *p1, _ = ubwd(us[0], d2)
+                    g = d1.add_(dres)
                 grads[start + 1], grads[start] = p2, p1
-                g = d1.add_(dres)
         code, shape = ctx.pool
         if ctx.fused_stem:
             u = units[0]

@@ -379,6 +379,11 @@ int cova_bn_relu_pool_bwd_t(const void* x, int s_dtype, const unsigned char* cod
                             double* ws, unsigned int* ws_max, void* dx, void* dx_hi, void* dx_lo, int planes_dtype,
                             int target_log2, float* inv_scale_vec, float* dgamma, float* dbeta, void* stream);
 
+/* bf16 training mode: y = scale * (x W^T) + zero_shift + res on single bf16 planes [M, C] - the dgrad of a 1x1 convolution with the
+ * skip branch's gradient added in the epilogue (no separate elementwise add pass over the 256-channel map).              */
+int cova_conv1x1_raw_res_fwd(const void* x, int64_t M, int Cin, int Cout, const void* w_bf16, const float* scale,
+                             const float* zero_shift, const void* res_bf16, void* y_bf16, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -501,6 +501,11 @@ def test_bf16_unit_fwd_bwd_vs_emulation(kind, cin, cout, with_res, relu):
         assert rms(dres.float().permute(0, 3, 1, 2), re.grad) < 1e-3
     assert rms(dw, conv.weight.grad) < 2e-3
     assert rms(dg, bn.weight.grad) < 2e-3 and rms(db, bn.bias.grad) < 2e-3
+    if kind != "stem":   # the skip branch's gradient added by the dgrad epilogue (one rounding) vs the rounded dx + add (two)
+        bn.running_mean.zero_(); bn.running_var.fill_(1.0)
+        add = _bf(torch.randn(xin.shape, generator=g)).to(DEV).contiguous()
+        dx2 = _unit_bwd16(_unit_fwd16(kind, xin, conv, bn, res=res, relu=relu), dy, add=add)[0]
+        assert rms(dx2.float(), dx.float() + add.float()) < 4e-3
 
 
 @pytest.mark.parametrize("backbone,img", [("resnet18", 96), ("resnet50", 160)])
