@@ -127,6 +127,8 @@ SIGNATURES = {
     "cova_bn_relu_pool_fwd_t": (_I, [_P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _I, _P, _P, _P, _I, _P]),
     "cova_bn_relu_pool_bwd_t": (_I, [_P, _I, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P, _P, _P, _P]),
     "cova_conv1x1_raw_res_fwd": (_I, [_P, _L, _I, _I, _P, _P, _P, _P, _P, _P]),
+    "cova_conv3x3_scale_res_f32_fwd": (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P]),
+    "cova_conv1x1_raw_res_f32_fwd": (_I, [_P, _P, _I, _L, _I, _I, _P, _P, _P, _P, _P, _P]),
     "cova_maxpool3x3s2_fwd": (_I, [_P, _I, _I, _I, _I, _P, _P, _P, _P, _I, _P]),
     "cova_maxpool3x3s2_bwd": (_I, [_P, _P, _I, _I, _I, _I, _P, _P]),
     "cova_bn_relu_pool_fwd": (_I, [_P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _I, _P]),

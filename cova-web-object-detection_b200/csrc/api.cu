@@ -10,7 +10,7 @@ int conv3x3_simt(const float* x, int B, int H, int W, const float* w, const floa
                  const float* res, int relu, float* y, cudaStream_t st);
 int conv3x3_tc(const void* x_hi, const void* x_lo, int split, int half, int B, int H, int W, const void* w_hi, const void* w_lo,
                const float* bn_scale, const float* bn_shift, const void* res_hi, const void* res_lo, int relu,
-               int out_dtype, void* y0, void* y1, cudaStream_t st, double* stats = nullptr);
+               int out_dtype, void* y0, void* y1, cudaStream_t st, double* stats = nullptr, const float* res_f32 = nullptr);
 int linear_simt(const float* x, int64_t ld_x, int M, int K, const float* w, int N, const float* bias,
                 const float* scale, const float* shift, const float* res, int64_t ld_res, int relu, float* y,
                 int64_t ld_y, cudaStream_t st);
@@ -47,6 +47,17 @@ extern "C" int cova_conv3x3_bn_act_stats_fwd(const void* x0, const void* x1, int
                                              const void* w_a, const void* w_b, const float* bn_scale, const float* bn_shift,
                                              const void* res0, const void* res1, int relu, int out_dtype, void* y0, void* y1,
                                              int engine, double* stats_ws, void* stream);
+
+// fp32 output + fp32 NHWC residual (training dgrad on split planes with the skip branch's fp32 gradient added in the epilogue)
+extern "C" int cova_conv3x3_scale_res_f32_fwd(const void* x0, const void* x1, int dtype, int B, int H, int W, const void* w_a,
+                                              const void* w_b, const float* scale, const float* shift, const float* res_f32,
+                                              float* y, void* stream) {
+  COVA_REQUIRE(x0 && x1 && w_a && w_b && scale && shift && res_f32 && y && B > 0 && H > 0 && W > 0, "cova_conv3x3_scale_res_f32_fwd: bad arguments");
+  COVA_REQUIRE(dtype == COVA_BF16X2 || dtype == COVA_F16X2, "cova_conv3x3_scale_res_f32_fwd: split planes in");
+  COVA_REQUIRE((((uintptr_t)res_f32 | (uintptr_t)y) & 31) == 0, "cova_conv3x3_scale_res_f32_fwd: 32-byte alignment");
+  return conv3x3_tc(x0, x1, 1, dtype == COVA_F16X2, B, H, W, w_a, w_b, scale, shift, nullptr, nullptr, 0, COVA_F32, y, nullptr,
+                    (cudaStream_t)stream, nullptr, res_f32);
+}
 
 extern "C" int cova_conv3x3_bn_act_fwd(const void* x0, const void* x1, int dtype, int B, int H, int W, int Cin, int Cout,
                                        const void* w_a, const void* w_b, const float* bn_scale, const float* bn_shift,

@@ -85,6 +85,7 @@ struct ConvTcParams {
   int res_pf_tiles;   // epilogue: L2-prefetch the residual rows this many iterations ahead (0 = off; 1 is the register prefetch)
   unsigned long long* dbg;   // optional per-CTA wait-cycle counters (cova_debug_buffer)
   double* stats;             // optional [2][64]: sum y, sum y^2 over all pixels (raw mode: BatchNorm batch statistics), += here
+  const float* res_f32;      // optional fp32 NHWC residual added to an fp32 output (training dgrad + the skip branch's gradient)
 };
 
 // mbarrier wait that adds the cycles spent to `acc` when instrumentation is on
@@ -102,7 +103,7 @@ __device__ __forceinline__ void mbar_wait_t(uint64_t* bar, uint32_t parity, bool
 // ~8x tighter than bf16 - measured ~5e-4 on the logits, inside BASELINE.json's 1e-3 bar).  SPLIT: COVA_F16X2, the same
 // three products on split-fp16 planes (22 significand bits: an fp32 convolution to ~1e-6); the filter comes scaled by
 // SPLIT_F16_WSCALE, undone in the epilogue's scale.
-template <bool SPLIT, int OUT_DTYPE, bool HALF>
+template <bool SPLIT, int OUT_DTYPE, bool HALF, bool RES32 = false>
 __global__ void __launch_bounds__(CT_THREADS, 1)
 conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ CUtensorMap tm_x_lo,
                   const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo,
@@ -363,6 +364,15 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_cons
             }
           }
       }
+      if (RES32) {   // fp32 residual row segment, 8 channels at a time (32 more live registers spilled; the 8 epilogue warps hide the loads)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          uint32_t rf[8];
+          ld_global_na_v8(p.res_f32 + pix + j * 8, rf);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) o[j * 8 + e] += __uint_as_float(rf[e]);
+        }
+      }
       if (p.relu) {
 #pragma unroll
         for (int c = 0; c < 32; ++c) o[c] = fmaxf(o[c], 0.f);
@@ -410,12 +420,12 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_cons
   }
 }
 
-template <bool SPLIT, int OUT_DTYPE, bool HALF = false>
+template <bool SPLIT, int OUT_DTYPE, bool HALF = false, bool RES32 = false>
 static int launch_conv_tc(const CUtensorMap& xh, const CUtensorMap& xl, const CUtensorMap& wh, const CUtensorMap& wl,
                           const ConvTcParams& p, cudaStream_t st) {
   using Cfg = ConvTcCfg<SPLIT>;
   static_assert(sizeof(ConvTcTail) <= 1024, "tail too large");
-  auto kern = conv3x3_tc_kernel<SPLIT, OUT_DTYPE, HALF>;
+  auto kern = conv3x3_tc_kernel<SPLIT, OUT_DTYPE, HALF, RES32>;
   COVA_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
   const int grid = p.n_tiles < sm_count() ? p.n_tiles : sm_count();
   kern<<<grid, CT_THREADS, Cfg::SMEM_BYTES, st>>>(xh, xl, wh, wl, p);
@@ -425,7 +435,7 @@ static int launch_conv_tc(const CUtensorMap& xh, const CUtensorMap& xl, const CU
 
 int conv3x3_tc(const void* x_hi, const void* x_lo, int split, int half, int B, int H, int W, const void* w_hi, const void* w_lo,
                const float* bn_scale, const float* bn_shift, const void* res_hi, const void* res_lo, int relu,
-               int out_dtype, void* y0, void* y1, cudaStream_t st, double* stats) {
+               int out_dtype, void* y0, void* y1, cudaStream_t st, double* stats, const float* res_f32) {
   CUtensorMap tx_hi, tx_lo, tw_hi, tw_lo;
   const uint64_t xd[4] = {(uint64_t)CT_C, (uint64_t)W, (uint64_t)H, (uint64_t)B};
   const uint64_t xs[3] = {(uint64_t)CT_C * 2, (uint64_t)W * CT_C * 2, (uint64_t)H * W * CT_C * 2};
@@ -457,12 +467,19 @@ int conv3x3_tc(const void* x_hi, const void* x_lo, int split, int half, int B, i
   p.res_load = knob(COVA_KNOB_CONV_RES_LOAD, 2);
   p.dbg = debug_words(8LL * sm_count());
   p.stats = stats;
+  p.res_f32 = res_f32;
   if (stats) COVA_CUDA_OK(cudaMemsetAsync(stats, 0, 2 * CT_C * sizeof(double), st));
 #define DISPATCH(SP)                                                                               \
   switch (out_dtype) {                                                                             \
     case COVA_F32: return launch_conv_tc<SP, COVA_F32>(tx_hi, tx_lo, tw_hi, tw_lo, p, st);         \
     case COVA_BF16: return launch_conv_tc<SP, COVA_BF16>(tx_hi, tx_lo, tw_hi, tw_lo, p, st);       \
     default: return launch_conv_tc<SP, COVA_BF16X2>(tx_hi, tx_lo, tw_hi, tw_lo, p, st);            \
+  }
+  if (res_f32 != nullptr) {   // training dgrad: split planes in, fp32 out + fp32 residual (its own instantiation: the 32
+    // residual registers must not burden the inference kernels)
+    if (!(split && out_dtype == COVA_F32)) { set_error("conv3x3_tc: an fp32 residual goes with split planes in and fp32 out"); return COVA_ERR_ARG; }
+    return half ? launch_conv_tc<true, COVA_F32, true, true>(tx_hi, tx_lo, tw_hi, tw_lo, p, st)
+                : launch_conv_tc<true, COVA_F32, false, true>(tx_hi, tx_lo, tw_hi, tw_lo, p, st);
   }
   if (half && split) {   // split-fp16 planes in; split-fp16 planes or fp32 out (stored through the COVA_BF16X2 code path)
     if (out_dtype == COVA_F32) return launch_conv_tc<true, COVA_F32, true>(tx_hi, tx_lo, tw_hi, tw_lo, p, st);

@@ -38,6 +38,7 @@ struct PwParams {
   void* y0;
   void* y1;
   double* stats;     // optional [2][COUT]: sum y, sum y^2 over all pixel rows (BatchNorm batch statistics of the output), += here
+  const float* res_f32;   // optional fp32 residual rows [M, COUT] added to an fp32 output (training dgrad + skip gradient)
 };
 
 template <int KB, int COUT, bool SINGLE = false>
@@ -53,7 +54,7 @@ struct PwCfg {
 // scaled by SPLIT_F16_WSCALE, which the caller folds into bn_scale); fp32 output, no residual.
 // SINGLE (bf16 training mode): one bf16 plane in, one bf16 product, one bf16 plane out (OUT_DTYPE = COVA_BF16): half the
 // bytes of this HBM-bound kernel; the lo maps are not touched.
-template <int KB, int COUT, int OUT_DTYPE, bool HALF = false, bool SINGLE = false>
+template <int KB, int COUT, int OUT_DTYPE, bool HALF = false, bool SINGLE = false, bool RES32 = false>
 __global__ void __launch_bounds__(PW_THREADS, 1)
 pw_tc_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ CUtensorMap tm_x_lo,
              const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo, const PwParams p) {
@@ -239,6 +240,15 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant_
               }
             }
         }
+        if (RES32) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint32_t rf[8];
+            ld_global_na_v8(p.res_f32 + row + c0 + j * 8, rf);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) o[j * 8 + e] += __uint_as_float(rf[e]);
+          }
+        }
         if (p.relu) {
 #pragma unroll
           for (int c = 0; c < 32; ++c) o[c] = fmaxf(o[c], 0.f);
@@ -288,11 +298,11 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant_
   }
 }
 
-template <int KB, int COUT, int OUT_DTYPE, bool HALF = false, bool SINGLE = false>
+template <int KB, int COUT, int OUT_DTYPE, bool HALF = false, bool SINGLE = false, bool RES32 = false>
 static int launch_pw(const CUtensorMap& xh, const CUtensorMap& xl, const CUtensorMap& wh, const CUtensorMap& wl,
                      const PwParams& p, cudaStream_t st) {
   using Cfg = PwCfg<KB, COUT, SINGLE>;
-  auto kern = pw_tc_kernel<KB, COUT, OUT_DTYPE, HALF, SINGLE>;
+  auto kern = pw_tc_kernel<KB, COUT, OUT_DTYPE, HALF, SINGLE, RES32>;
   COVA_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
   const int grid = p.n_tiles < sm_count() ? p.n_tiles : sm_count();
   kern<<<grid, PW_THREADS, Cfg::SMEM, st>>>(xh, xl, wh, wl, p);
@@ -304,7 +314,7 @@ static int launch_pw(const CUtensorMap& xh, const CUtensorMap& xl, const CUtenso
 
 static int pw_run(const void* x_hi, const void* x_lo, int64_t M, int Cin, int Cout, const void* w_packed, const float* bn_scale,
                   const float* bn_shift, const void* res_hi, const void* res_lo, int relu, int out_dtype, void* y0, void* y1,
-                  bool half, void* stream, double* stats = nullptr);
+                  bool half, void* stream, double* stats = nullptr, const float* res_f32 = nullptr);
 
 extern "C" int cova_conv1x1_bn_act_fwd(const void* x_hi, const void* x_lo, int64_t M, int Cin, int Cout,
                                        const void* w_packed, const float* bn_scale, const float* bn_shift,
@@ -336,6 +346,17 @@ extern "C" int cova_conv1x1_raw_stats_fwd(const void* x_hi, const void* x_lo, in
                 planes_dtype == COVA_F16X2, stream, stats_ws);
 }
 
+// fp32-parity training mode: y = scale * (x W^T) + zero_shift + res_f32, split planes in, fp32 rows out (dgrad + skip gradient)
+extern "C" int cova_conv1x1_raw_res_f32_fwd(const void* x_hi, const void* x_lo, int planes_dtype, int64_t M, int Cin, int Cout,
+                                            const void* w_packed, const float* scale, const float* zero_shift, const float* res_f32,
+                                            float* y, void* stream) {
+  COVA_REQUIRE(planes_dtype == COVA_F16X2 || planes_dtype == COVA_BF16X2, "cova_conv1x1_raw_res_f32_fwd: planes are split-fp16 or split-bf16");
+  COVA_REQUIRE(x_hi && x_lo && w_packed && scale && zero_shift && res_f32 && y, "cova_conv1x1_raw_res_f32_fwd: null pointer");
+  COVA_REQUIRE((((uintptr_t)res_f32 | (uintptr_t)y) & 31) == 0, "cova_conv1x1_raw_res_f32_fwd: 32-byte alignment");
+  return pw_run(x_hi, x_lo, M, Cin, Cout, w_packed, scale, zero_shift, nullptr, nullptr, 0, COVA_F32, y, nullptr,
+                planes_dtype == COVA_F16X2, stream, nullptr, res_f32);
+}
+
 // bf16 training mode: y = x W^T + res on single bf16 planes (a dgrad with the skip branch's gradient added in the epilogue: no
 // separate elementwise add pass over the 256-channel map)
 extern "C" int cova_conv1x1_raw_res_fwd(const void* x, int64_t M, int Cin, int Cout, const void* w_bf16, const float* scale,
@@ -346,7 +367,7 @@ extern "C" int cova_conv1x1_raw_res_fwd(const void* x, int64_t M, int Cin, int C
 
 static int pw_run(const void* x_hi, const void* x_lo, int64_t M, int Cin, int Cout, const void* w_packed, const float* bn_scale,
                   const float* bn_shift, const void* res_hi, const void* res_lo, int relu, int out_dtype, void* y0, void* y1,
-                  bool half, void* stream, double* stats) {
+                  bool half, void* stream, double* stats, const float* res_f32) {
   using namespace cova;
   COVA_REQUIRE(x_hi && x_lo && w_packed && bn_scale && bn_shift && y0, "cova_conv1x1_bn_act_fwd: null pointer");
   COVA_REQUIRE((Cin == 64 && (Cout == 64 || Cout == 256)) || (Cin == 256 && Cout == 64),
@@ -374,9 +395,12 @@ static int pw_run(const void* x_hi, const void* x_lo, int64_t M, int Cin, int Co
   p.res_hi = (const __nv_bfloat16*)res_hi; p.res_lo = (const __nv_bfloat16*)res_lo;
   p.y0 = y0; p.y1 = y1;
   p.stats = stats;
+  p.res_f32 = res_f32;
   cudaStream_t st = (cudaStream_t)stream;
   if (stats) COVA_CUDA_OK(cudaMemsetAsync(stats, 0, 2 * Cout * sizeof(double), st));
-#define GO(KB, CO) (out_dtype == COVA_BF16 ? launch_pw<KB, CO, COVA_BF16, false, true>(tx_hi, tx_lo, tw_hi, tw_lo, p, st) \
+#define GO(KB, CO) (res_f32 != nullptr ? (half ? launch_pw<KB, CO, COVA_F32, true, false, true>(tx_hi, tx_lo, tw_hi, tw_lo, p, st)     \
+                                              : launch_pw<KB, CO, COVA_F32, false, false, true>(tx_hi, tx_lo, tw_hi, tw_lo, p, st))   \
+                    : out_dtype == COVA_BF16 ? launch_pw<KB, CO, COVA_BF16, false, true>(tx_hi, tx_lo, tw_hi, tw_lo, p, st) \
                     : half ? launch_pw<KB, CO, COVA_F32, true>(tx_hi, tx_lo, tw_hi, tw_lo, p, st)          \
                     : out_dtype == COVA_F32 ? launch_pw<KB, CO, COVA_F32>(tx_hi, tx_lo, tw_hi, tw_lo, p, st) \
                                             : launch_pw<KB, CO, COVA_BF16X2>(tx_hi, tx_lo, tw_hi, tw_lo, p, st))

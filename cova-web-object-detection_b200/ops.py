@@ -468,6 +468,30 @@ def _ones256(device):
     return _ONES256[k]
 
 
+def conv3x3_scale_res_f32_fwd(x_planes, w_hi, w_lo, scale, shift, res_f32):
+    """fp32-parity training dgrad: split planes in -> fp32 [B,H,W,64] = scale * conv3x3(x) + shift + res_f32."""
+    B, H, W, C = x_planes.shape
+    y = torch.empty((B, H, W, C), dtype=torch.float32, device=x_planes.p0.device)
+    _call("cova_conv3x3_scale_res_f32_fwd", x_planes.p0.data_ptr(), x_planes.p1.data_ptr(), x_planes.dtype, B, H, W, w_hi.data_ptr(),
+          w_lo.data_ptr(), scale.data_ptr(), shift.data_ptr(), _nhwc(res_f32, "res").data_ptr(), y.data_ptr(), _stream())
+    return y
+
+
+def conv1x1_raw_res_f32_fwd(x_planes, w_packed, scale, res_f32):
+    """fp32-parity training dgrad of a 1x1 convolution: fp32 rows = (scale / 256) * (x W^T) + res_f32."""
+    Cin, Cout = x_planes.shape[-1], w_packed.shape[-2]
+    M = 1
+    for d in x_planes.shape[:-1]:
+        M *= d
+    dev = x_planes.p0.device
+    inv, zero = _inv256(dev)
+    sc = inv if scale is None else scale[:256] * (1.0 / 256.0)
+    y = torch.empty(tuple(x_planes.shape[:-1]) + (Cout,), dtype=torch.float32, device=dev)
+    _call("cova_conv1x1_raw_res_f32_fwd", x_planes.p0.data_ptr(), x_planes.p1.data_ptr(), x_planes.dtype, M, Cin, Cout,
+          w_packed.data_ptr(), sc.data_ptr(), zero.data_ptr(), _nhwc(res_f32, "res").data_ptr(), y.data_ptr(), _stream())
+    return y
+
+
 def conv1x1_raw_res_fwd_bf16(x, w_bf16, res):
     """bf16 training mode: x [.., Cin] bf16 @ w_bf16 [Cout, Cin]^T + res [.., Cout] bf16 -> bf16 (dgrad + skip-branch gradient)."""
     Cin, Cout = x.shape[-1], w_bf16.shape[0]

@@ -392,7 +392,7 @@ def _epi_stats(kind=3):
     return v == "all" or (v == "3" and kind == 3)
 
 
-def _unit_bwd(u, dy, need_dx=True):
+def _unit_bwd(u, dy, need_dx=True, add=None):
     """dy = gradient of the unit's output (fp32 NHWC).  BatchNorm backward emits the gradient of the raw convolution output
     directly as scaled split-fp16 planes (no fp32 map, no max / split passes); dgrad and wgrad consume them on the tensor
     cores.  Returns (dx fp32 or None, dw, dgamma, dbeta, dres or None)."""
@@ -404,15 +404,19 @@ def _unit_bwd(u, dy, need_dx=True):
     if u.kind == "stem":
         dw = ops.stem_wgrad(u.xin, dyp, inv)
     elif u.kind == 3:
-        if need_dx:
+        if need_dx:        # `add` (the skip branch's fp32 gradient) rides in the dgrad convolution's epilogue: no add pass
             w_hi, w_lo = ops.pack_conv_weight_f16x2(w.flip(2, 3).transpose(0, 1).contiguous())
             _, zero = _ones_zeros(dy.device)
-            dx = ops.conv3x3_bn_act_fwd(dyp, w_hi, w_lo, inv[:64], zero, res=None, relu=False, out_dtype=F32,
-                                        engine=ENGINE_TCGEN05).p0
+            if add is None:
+                dx = ops.conv3x3_bn_act_fwd(dyp, w_hi, w_lo, inv[:64], zero, res=None, relu=False, out_dtype=F32,
+                                            engine=ENGINE_TCGEN05).p0
+            else:
+                dx = ops.conv3x3_scale_res_f32_fwd(dyp, w_hi, w_lo, inv[:64], zero, add)
         dw = ops.conv3x3_wgrad(u.xin, dyp, inv)
     else:
         if need_dx:
-            dx = ops.conv1x1_raw_fwd(dyp, ops.pack_linear_weight_f16x2(w.flatten(1).t().contiguous()), scale=inv)
+            wt = ops.pack_linear_weight_f16x2(w.flatten(1).t().contiguous())
+            dx = ops.conv1x1_raw_fwd(dyp, wt, scale=inv) if add is None else ops.conv1x1_raw_res_f32_fwd(dyp, wt, inv, add)
         dw = ops.conv1x1_wgrad(u.xin, dyp, inv)
     u.raw = u.res = u.xin = u.mean = u.inv = None        # release the unit's saved maps as the backward walks up the network
     return dx, dw, dg, db, dres
@@ -562,19 +566,11 @@ class _BackboneFn(torch.autograd.Function):
                     dd, *pd, _ = ubwd(us[3], dres)
                     grads[start + 3] = pd
                     dres = dd
-                if ctx.bf16:           # the skip gradient is added by conv1's dgrad epilogue
-                    g, *p1, _ = ubwd(us[0], d2, add=dres)
-                else:
-                    d1, *p1, _ = ubwd(us[0], d2)
-                    g = d1.add_(dres)
+                g, *p1, _ = ubwd(us[0], d2, add=dres)          # the skip gradient is added by conv1's dgrad epilogue
                 grads[start + 2], grads[start + 1], grads[start] = p3, p2, p1
             else:
                 d2, *p2, dres = ubwd(us[1], g)
-                if ctx.bf16:
-                    g, *p1, _ = ubwd(us[0], d2, add=dres)
-                else:
-                    d1, *p1, _ = ubwd(us[0], d2)
-                    g = d1.add_(dres)
+                g, *p1, _ = ubwd(us[0], d2, add=dres)
                 grads[start + 1], grads[start] = p2, p1
         code, shape = ctx.pool
         if ctx.fused_stem:

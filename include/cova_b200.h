@@ -384,6 +384,15 @@ int cova_bn_relu_pool_bwd_t(const void* x, int s_dtype, const unsigned char* cod
 int cova_conv1x1_raw_res_fwd(const void* x, int64_t M, int Cin, int Cout, const void* w_bf16, const float* scale,
                              const float* zero_shift, const void* res_bf16, void* y_bf16, void* stream);
 
+/* fp32-parity training mode, the same idea on split planes: fp32 output = scale * conv(x) + shift + res_f32 (fp32 NHWC / rows),
+ * i.e. a dgrad with the skip branch's fp32 gradient added by the epilogue.                                                */
+int cova_conv3x3_scale_res_f32_fwd(const void* x0, const void* x1, int dtype, int B, int H, int W, const void* w_a,
+                                   const void* w_b, const float* scale, const float* shift, const float* res_f32, float* y,
+                                   void* stream);
+int cova_conv1x1_raw_res_f32_fwd(const void* x_hi, const void* x_lo, int planes_dtype, int64_t M, int Cin, int Cout,
+                                 const void* w_packed, const float* scale, const float* zero_shift, const float* res_f32,
+                                 float* y, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
