@@ -82,7 +82,9 @@ __device__ __forceinline__ uint64_t desc_noswz(uint32_t addr, uint32_t lbo, uint
 }
 
 // HALF (single-plane mode only): ring pixels, filter and output plane are fp16 instead of bf16 (COVA_F16).
-template <bool SPLIT, int OUT_DTYPE, bool U8, int NCV, bool HALF>
+// RAW: training mode (raw conv output + optional batch statistics instead of BN + ReLU + pool) - its own instantiations, so the
+// inference kernels carry none of that code.
+template <bool SPLIT, int OUT_DTYPE, bool U8, int NCV, bool HALF, bool RAW = false>
 __global__ void __launch_bounds__(sx_threads(NCV), 1)
 stem_tc_kernel(const StemTcParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -102,8 +104,8 @@ stem_tc_kernel(const StemTcParams p) {
   const int n_strips = (p.Wc + SX_TM - 1) / SX_TM;
 
   if (threadIdx.x < 64) {
-    sm.scale[threadIdx.x] = (p.raw_out ? 1.f : p.bn_scale[threadIdx.x]) * ((SPLIT && HALF) ? 1.f / SPLIT_F16_WSCALE : 1.f);
-    sm.shift[threadIdx.x] = p.raw_out ? 0.f : p.bn_shift[threadIdx.x];
+    sm.scale[threadIdx.x] = (RAW ? 1.f : p.bn_scale[threadIdx.x]) * ((SPLIT && HALF) ? 1.f / SPLIT_F16_WSCALE : 1.f);
+    sm.shift[threadIdx.x] = RAW ? 0.f : p.bn_shift[threadIdx.x];
   }
   if (U8 && threadIdx.x < 256) {   // v/255 with IEEE division == torchvision ToTensor; split once per pixel value
     const float pv = __fdiv_rn((float)threadIdx.x, 255.f);
@@ -239,12 +241,10 @@ stem_tc_kernel(const StemTcParams p) {
         ptx::tc_fence_before();
         ptx::mbar_arrive(&sm.tmem_empty[acc]);
 
-        if (p.raw_out != nullptr) {
+        if (RAW) {
           // training mode (BatchNorm needs batch statistics of THIS tensor): write the raw conv row and skip the
           // pooling.  A band recomputes the conv row above it as pooling halo; only the owner band writes a row.
-          if (OUT_DTYPE != COVA_BF16X2 && p.stats != nullptr) {   // (raw outputs are fp32 or one bf16 plane: the split-plane
-            // inference instantiation carries none of this)  statistics of the values as they are STORED; every conv pixel
-            // is counted by its owner band
+          if (p.stats != nullptr) {   // statistics of the values as they are STORED; every conv pixel is counted by its owner band
             static_assert(SX_CH == 16, "warp_transpose_sum16");
             const bool valid = oy >= 2 * py0 && ox < p.Wc;
             float z[16], z2[16];
@@ -351,7 +351,7 @@ stem_tc_kernel(const StemTcParams p) {
         }
       }
     }
-    if (OUT_DTYPE != COVA_BF16X2 && p.raw_out != nullptr && p.stats != nullptr && lane < 16) {
+    if (RAW && p.stats != nullptr && lane < 16) {
       atomicAdd(p.stats + ch0 + lane, st_s);
       atomicAdd(p.stats + 64 + ch0 + lane, st_q);
     }
@@ -547,9 +547,9 @@ __global__ void pack_stem_weight_f16x2_kernel(const float* __restrict__ w, __hal
   out[((chunk * 2 + 1) * 64 + co) * 8 + e] = __float2half_rn(v - __half2float(h));
 }
 
-template <bool SPLIT, int OUT_DTYPE, bool U8, int NCV, bool HALF>
+template <bool SPLIT, int OUT_DTYPE, bool U8, int NCV, bool HALF, bool RAW = false>
 static int launch_stem_tc_n(const StemTcParams& p, int grid, cudaStream_t st) {
-  auto kern = stem_tc_kernel<SPLIT, OUT_DTYPE, U8, NCV, HALF>;
+  auto kern = stem_tc_kernel<SPLIT, OUT_DTYPE, U8, NCV, HALF, RAW>;
   const int smem = (int)sizeof(StemTcSmem<SPLIT>) + 128;
   COVA_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   kern<<<grid, sx_threads(NCV), smem, st>>>(p);
@@ -558,6 +558,12 @@ static int launch_stem_tc_n(const StemTcParams& p, int grid, cudaStream_t st) {
 }
 template <bool SPLIT, int OUT_DTYPE, bool U8, bool HALF = false>
 static int launch_stem_tc(const StemTcParams& p, int grid, cudaStream_t st) {
+  if (p.raw_out != nullptr) {
+    if constexpr (OUT_DTYPE == COVA_F32 || (OUT_DTYPE == COVA_BF16 && !HALF))
+      return launch_stem_tc_n<SPLIT, OUT_DTYPE, U8, 8, HALF, true>(p, grid, st);
+    set_error("stem_tc: raw (training) output is fp32 or one bf16 plane");
+    return COVA_ERR_ARG;
+  }
   if (knob(COVA_KNOB_STEM_CONVERTERS, 8) >= 8) return launch_stem_tc_n<SPLIT, OUT_DTYPE, U8, 8, HALF>(p, grid, st);
   return launch_stem_tc_n<SPLIT, OUT_DTYPE, U8, 4, HALF>(p, grid, st);
 }
