@@ -696,7 +696,7 @@ def main():
                              "reps_ms_per_step": [round(x / steps, 4) for x in head["reps_u8"]],
                              "aggregate_h2d_gb_s": agg_h2d(head["ms_e2e_u8"], head["h2d_u8"]),
                              "note": "optional input format (SURVEY 8(f) N1; the PNGs of datasets.py:96-97 are uint8): raw "
-                                     "pixels, v/255 in the stem kernel, bit-identical logits"},
+                                     "pixels as integers in the stem kernel, 1/255 in its epilogue scale (two products): within one ulp of the split-bf16 stem output of the ToTensor path (tests/test_gpu_parity.py::test_uint8_images_equal_totensor_path); knob stem_u8_exact=1 gives the bit-identical v/255 path"},
         "fp32_parity_mode": None if not head.get("ms_train_fp32") else {
             "value": cfg["B"] * world / (head["ms_train_fp32"] / 1e3), "unit": "pages/s", "ms_per_step": head["ms_train_fp32"],
             "note": "same train step with fp32 maps and split-fp16 three-product convolutions; side measurement, 3 steps"},

@@ -26,7 +26,7 @@ int sm_count() {
 }
 
 // Tuning knobs (include/cova_b200.h COVA_KNOB_*): plain ints read at launch time; -1 = kernel default.
-static int g_knob[COVA_KNOB_COUNT] = {-1, -1, -1, -1, -1, -1, -1, -1, -1};
+static int g_knob[COVA_KNOB_COUNT] = {-1, -1, -1, -1, -1, -1, -1, -1, -1, -1};
 int knob(int id, int dflt) { return (id >= 0 && id < COVA_KNOB_COUNT && g_knob[id] >= 0) ? g_knob[id] : dflt; }
 static unsigned long long* g_dbg = nullptr;
 static long long g_dbg_words = 0;

@@ -408,8 +408,9 @@ class CoVA(nn.Module):
 
     @staticmethod
     def _img(images):
-        """fp32 in [0,1] (the reference contract) or raw uint8 pixels: the native stem converts v/255 itself
-        (bit-identical to `ToTensor`, a quarter of the host->device bytes - SURVEY.md 8(f) N1)."""
+        """fp32 in [0,1] (the reference contract) or raw uint8 pixels: the native stem applies the 1/255 itself
+        (a quarter of the host->device bytes - SURVEY.md 8(f) N1; `ops.set_knob("stem_u8_exact", 1)` = the per-pixel
+        v/255 path that is bit-identical to `ToTensor`)."""
         return images if images.dtype == torch.uint8 else images.float()
 
     def _forward_composite(self, images, bboxes, additional_feats, context_indices):

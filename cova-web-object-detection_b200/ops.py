@@ -58,7 +58,7 @@ def device_info():
     return sm.value, smem.value
 
 
-KNOBS = {"wgrad_drain": 8, "conv_l2_prefetch": 0, "conv_res_prefetch": 1, "stem_l2_prefetch": 2, "stem_converters": 5, "conv_res_load": 6, "roi_rowsplit": 7}
+KNOBS = {"wgrad_drain": 8, "conv_l2_prefetch": 0, "conv_res_prefetch": 1, "stem_l2_prefetch": 2, "stem_converters": 5, "conv_res_load": 6, "roi_rowsplit": 7, "stem_u8_exact": 9}
 
 
 def set_knob(name, value):

@@ -58,12 +58,15 @@ int cova_device_info(int* sm_count, int* max_smem_optin);
  *   COVA_KNOB_CONV_RES_LOAD      3x3 conv residual loads: 0 = ld.global.nc, 1 = ld.global, 2 = L1::no_allocate
  *   COVA_KNOB_ROI_ROWSPLIT       RoIPool: 1 = one CTA per (box, row bin) (default), 0 = one CTA per box
  *   COVA_KNOB_WGRAD_DRAIN        wgrad kernels: pixel tiles accumulated in TMEM between two drains to the global fp32 sum
+ *   COVA_KNOB_STEM_U8_EXACT      stem, uint8 images: 1 = v/255 split through the look-up table (bit-identical to ToTensor, three
+ *                                products); 0 (default) = integer pixels, exact in one 16-bit plane, 1/255 folded into the
+ *                                epilogue scale: TWO products (stem output within one ulp of its split-bf16 format, 3e-5 absolute, of the ToTensor path)
  * cova_debug_buffer: a caller-owned device array of uint64 words; kernels that support it (the 3x3 tensor-core conv:
  *   8 words per CTA = cycles the MMA issuer waited for operands / for a free accumulator, the TMA producer for a free
  *   ring slot, epilogue warp 2 for a finished accumulator, CTA total, tiles) add their counters.  NULL disables. */
 enum { COVA_KNOB_CONV_L2_PREFETCH = 0, COVA_KNOB_CONV_RES_PREFETCH = 1, COVA_KNOB_STEM_L2_PREFETCH = 2,
        COVA_KNOB_STEM_CONVERTERS = 5, COVA_KNOB_CONV_RES_LOAD = 6, COVA_KNOB_ROI_ROWSPLIT = 7, COVA_KNOB_WGRAD_DRAIN = 8,
-       COVA_KNOB_COUNT = 9 };
+       COVA_KNOB_STEM_U8_EXACT = 9, COVA_KNOB_COUNT = 10 };
 int cova_set_knob(int id, int value);
 int cova_debug_buffer(void* dev_words, int64_t n_words);
 
@@ -71,9 +74,10 @@ int cova_debug_buffer(void* dev_words, int64_t n_words);
  * maxpool 3x3 s2 p1 (`models.py:49-51`, applied `models.py:125`).  ONE fused kernel: the
  * [B,64,H/2,W/2] conv output never reaches HBM.
  *   images  [B,3,H,W] NCHW; img_dtype COVA_F32 = fp32 in [0,1] (the reference's input contract, `models.py:96`)
- *           or COVA_U8 = raw 8-bit pixels, converted as v/255 (IEEE division) on the way into shared memory -
- *           bit-identical to `torchvision.transforms.ToTensor` (`datasets.py:41-45`) at a quarter of the
- *           host->device bytes
+ *           or COVA_U8 = raw 8-bit pixels at a quarter of the host->device bytes.  SIMT engine and
+ *           COVA_KNOB_STEM_U8_EXACT = 1: converted as v/255 (IEEE division) on the way into shared memory, bit-identical
+ *           to `torchvision.transforms.ToTensor` (`datasets.py:41-45`); TCGEN05 default: integer pixels, 1/255 in the
+ *           epilogue scale (two tensor products instead of three; within one output ulp of the ToTensor path)
  *   w       engine SIMT   : [64,3,7,7] fp32 OIHW (`convnet.0.weight`)
  *           engine TCGEN05: the split-bf16 K-chunked filter written by cova_pack_stem_weight
  *   bn_scale/bn_shift [64] folded `convnet.1`
