@@ -120,6 +120,30 @@ def test_stem_tcgen05_uint8_images(W):
     assert rel_err(t2n(out.p0), ref) < 3e-5
 
 
+@pytest.mark.parametrize("u8", [False, True])
+@pytest.mark.parametrize("B,H,W", [(1, 8, 1600), (1, 18, 1028), (2, 10, 772), (1, 1280, 36), (5, 38, 516), (1, 14, 2052)])
+def test_stem_tcgen05_band_and_strip_geometries(B, H, W, u8):
+    """Rectangular pages against the exact-fp32 CUDA-core stem: one or two emitted pooled rows per band with up to 9 strips
+    (the strip-edge ring and the exchange buffers are reused with almost no barrier in between), an odd number of conv
+    rows (H = 10, 14, 18, 38: the last conv row is an even one that still completes a pooled row), a 36-pixel-wide page
+    with 148 one-row bands, and consecutive tiles whose two MMA issuers start on either accumulator."""
+    o = ops()
+    g = torch.Generator().manual_seed(B * 1000 + H + W)
+    if u8:
+        img = torch.randint(0, 256, (B, 3, H, W), dtype=torch.uint8, generator=g).to(DEV)
+    else:
+        img = torch.rand(B, 3, H, W, generator=g).to(DEV)
+    w = (torch.randn(64, 3, 7, 7, generator=g) * 0.1).to(DEV)
+    scale, shift = (0.5 + torch.rand(64, generator=g)).to(DEV), (0.1 * torch.randn(64, generator=g)).to(DEV)
+    a = o.stem_fwd(img, w, scale, shift, out_dtype=o.F32, engine=o.ENGINE_SIMT)
+    wp = o.pack_stem_weight(w)
+    for _ in range(3):      # a race would not show on every launch
+        b = o.stem_fwd(img, wp, scale, shift, out_dtype=o.F32, engine=o.ENGINE_TCGEN05)
+        torch.cuda.synchronize()
+        assert b.p0.shape == a.p0.shape
+        assert rel_err(t2n(b.p0), t2n(a.p0)) < 3e-5
+
+
 def test_stem_tcgen05_full_size_vs_simt():
     """1280x1280 (5 strips x 9 bands per page): the tensor-core stem against the exact-fp32 CUDA-core stem."""
     o = ops()

@@ -19,6 +19,13 @@ def step():
     opt.zero_grad(); loss = crit(m(*inp[:4]), inp[4]); loss.backward(); opt.step()
 for _ in range(2): step()
 torch.cuda.synchronize()
+if os.environ.get("TIME") == "1":         # CUDA-event time of 10 steps (no profiler)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(10): step()
+    e1.record(); torch.cuda.synchronize()
+    print(f"{bk} B={B} precision={os.environ.get('PRECISION', 'fp32')}: {e0.elapsed_time(e1) / 10:.3f} ms per train step (fwd + CE + bwd + Adam)")
+    sys.exit(0)
 if os.environ.get("NCU") == "1":          # ncu --profile-from-start off: one step between cudaProfilerStart / Stop
     torch.cuda.cudart().cudaProfilerStart(); step(); torch.cuda.synchronize(); torch.cuda.cudart().cudaProfilerStop()
     sys.exit(0)
