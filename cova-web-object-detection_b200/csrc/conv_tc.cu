@@ -51,7 +51,8 @@ constexpr int CT_PATCH_BYTES = CT_HW * CT_HH * 128;        // 23,040 bytes lande
 constexpr int CT_SLOT_BYTES = 23 * 1024;                   // ring slot (1024-B aligned for the swizzle atoms)
 constexpr int CT_GROUP_STRIDE = CT_HW * 128;               // 8-row-group stride of a tap view: one patch row
 constexpr int CT_W_TAP_BYTES = CT_C * 128;                 // 8,192: one tap of one plane (64 cout rows x 128 B)
-constexpr int CT_THREADS = 320;                 // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue (2 per TMEM lane group)
+constexpr int CT_THREADS = 352;                 // warp 0 TMA, warps 1 and 10 MMA issuers (even / odd tiles), warps 2-9 epilogue
+constexpr int CT_ISSUER_B = 10;                 // (2 per TMEM lane group)
 constexpr int CT_EPI_THREADS = 256;
 
 template <bool SPLIT>
@@ -189,8 +190,12 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_cons
       }
     }
     if (timed && lane == 0) atomicAdd(p.dbg + blockIdx.x * 8 + 2, wc0);
-  } else if (warp == 1) {
-    // ======================= MMA issuer (warp converged; one elected lane issues) =======================
+  } else if (warp == 1 || warp == CT_ISSUER_B) {
+    // ======================= MMA issuers (warp converged; one elected lane issues) =======================
+    // Two of them, one per accumulator buffer: the barrier checks, commits and loop overhead between two planes / tiles are
+    // serial latency in the issuing thread during which the tensor pipe drains its queue (stem_tc.cu, round-2 probes); the
+    // other issuer's MMAs fill it.  A tile's MMAs all come from one thread, so every tcgen05.commit covers what it must.
+    const uint32_t ipar = warp == 1 ? 0u : 1u;
     // Descriptors differ only in their 14-bit start-address field, so each MMA costs two 32-bit adds on
     // warp-uniform values (the elect.sync guard lets the compiler keep them in uniform registers; an
     // `if (lane == 0)` region would wrap every UTCHMMA in a per-lane serialisation loop).
@@ -201,6 +206,11 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_cons
     ptx::mbar_wait(&tail.wbar, 0);
     uint32_t stage = 0, phase = 0, it = 0;
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
+      if ((it & 1u) != ipar) {   // the other issuer's tile: step over its ring slots
+        for (int pl = 0; pl < Cfg::NPLANE; ++pl)
+          if (++stage == Cfg::NSTAGE) { stage = 0; phase ^= 1; }
+        continue;
+      }
       const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
       mbar_wait_t(&tail.tmem_empty[acc], acc_phase ^ 1, timed, wc1);
       ptx::tc_fence_after();
@@ -228,7 +238,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_cons
         if (++stage == Cfg::NSTAGE) { stage = 0; phase ^= 1; }
       }
     }
-    if (timed && lane == 0) {
+    if (timed && lane == 0 && warp == 1) {
       atomicAdd(p.dbg + blockIdx.x * 8 + 0, wc0);
       atomicAdd(p.dbg + blockIdx.x * 8 + 1, wc1);
       atomicAdd(p.dbg + blockIdx.x * 8 + 5, (unsigned long long)it);
