@@ -650,7 +650,7 @@ def main():
     pages = cfg["B"] * world * steps
     value, e2e = pages / (head["ms"] / 1e3), pages / (head["ms_e2e"] / 1e3)
     traffic = {}
-    tp = os.path.join(ROOT, "profiles", "traffic_r02.json")    # dram__bytes per launch from the committed ncu capture
+    tp = os.path.join(ROOT, "profiles", "traffic_r02e.json")    # dram__bytes per launch from the committed ncu capture
     if not os.path.exists(tp):
         tp = os.path.join(ROOT, "profiles", "traffic_r01.json")
     if os.path.exists(tp) and args.config == 2 and model.precision in ("fp32", "fp32x") and model.engine == "tcgen05" and not cfg["overridden"]:
