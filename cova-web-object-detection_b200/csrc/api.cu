@@ -15,6 +15,10 @@ int linear_simt(const float* x, int64_t ld_x, int M, int K, const float* w, int 
                 const float* scale, const float* shift, const float* res, int64_t ld_res, int relu, float* y,
                 int64_t ld_y, cudaStream_t st);
 bool linear_tc_supported(const float* x, int64_t ld_x, int K);
+bool linear_skinny_supported(const float* x, int64_t ld_x, int K, int N, const void* w);
+int linear_skinny(const float* x, int64_t ld_x, int M, int K, const void* w, bool packed, int N, const float* bias,
+                  const float* scale, const float* shift, const float* res, int64_t ld_res, int relu, float* y,
+                  int64_t ld_y, cudaStream_t st);
 int linear_tc(const float* x, int64_t ld_x, int M, int K, const void* w_packed, int N, const float* bias,
               const float* scale, const float* shift, const float* res, int64_t ld_res, int relu, int out_dtype,
               void* y0, void* y1, int64_t ld_y, cudaStream_t st, bool half);
@@ -107,6 +111,11 @@ extern "C" int cova_linear_fwd(const float* x, int64_t ld_x, int M, int K, const
   COVA_REQUIRE(!res || ld_res >= N, "cova_linear_fwd: ld_res too small");
   COVA_REQUIRE(out_dtype == COVA_F32 || (out_dtype == COVA_BF16X2 && y1 && engine == COVA_ENGINE_TCGEN05),
                "cova_linear_fwd: output is fp32, or split-bf16 planes (y0 = hi, y1 = lo) on the tcgen05 engine");
+  // skinny outputs (decoder.5: N = 4): exact-fp32 warp-per-row kernel on either engine (the split-fp16 training engine keeps its path)
+  if (engine != COVA_ENGINE_TCGEN05_F16X2 && out_dtype == COVA_F32 && linear_skinny_supported(x, ld_x, K, N, w) &&
+      (engine == COVA_ENGINE_SIMT || K % 8 == 0))
+    return linear_skinny(x, ld_x, M, K, w, engine == COVA_ENGINE_TCGEN05, N, bias, scale, shift, res, ld_res, relu, (float*)y0, ld_y,
+                         (cudaStream_t)stream);
   if (engine != COVA_ENGINE_SIMT) {
     COVA_REQUIRE(linear_tc_supported(x, ld_x, K),
                  "cova_linear_fwd: the tcgen05 engine needs K %% 8 == 0, ld_x %% 4 == 0 and a 16-byte aligned x "
