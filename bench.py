@@ -190,8 +190,8 @@ def _alg_table(roi_b):
         "cova_maxpool3x3s2_bwd": lambda a: ("hbm", 4.0 * i(a[2]) * i(a[3]) * i(a[4]) * i(a[5]) * (1 + 0.25 * 1.25)),
         # typed (bf16 training mode) passes: element sizes from the dtype codes (0 = fp32, 1 = bf16)
         "cova_bn_train_stats_t": lambda a: ("hbm", float(es(a[1])) * i(a[2]) * i(a[3])),
-        "cova_bn_act_fwd_t": lambda a: ("hbm", float(i(a[2])) * i(a[3]) * (es(a[1]) * (1 + (1 if a[8] else 0)) + es(a[11]))),
-        "cova_bn_act_bwd_t": lambda a: ("hbm", float(i(a[5])) * i(a[6]) * (2 * (es(a[1]) + es(a[4]) * (1 + (1 if a[3] else 0)))
+        "cova_bn_act_fwd_t": lambda a: ("hbm", float(i(a[2])) * i(a[3]) * (es(a[1]) * (1 + (1 if a[8] else 0)) + es(a[11]) + (0.125 if a[12] else 0))),
+        "cova_bn_act_bwd_t": lambda a: ("hbm", float(i(a[5])) * i(a[6]) * (2 * (es(a[1]) + es(a[4]) + (0.125 if a[17] else (es(a[4]) if a[3] else 0)))
                                                                          + es(a[4]) * (1 + (1 if a[14] else 0)))),
         "cova_maxpool3x3s2_fwd_t": lambda a: ("hbm", float(es(a[1])) * i(a[2]) * i(a[3]) * i(a[4]) * i(a[5]) * 1.25 + 0.25 * i(a[2]) * i(a[3]) * i(a[4]) * i(a[5])),
         "cova_maxpool3x3s2_bwd_t": lambda a: ("hbm", float(es(a[2])) * i(a[3]) * i(a[4]) * i(a[5]) * i(a[6]) * 1.25 + 0.25 * i(a[3]) * i(a[4]) * i(a[5]) * i(a[6])),

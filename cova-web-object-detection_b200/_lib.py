@@ -116,8 +116,8 @@ SIGNATURES = {
     "cova_bn_act_bwd": (_I, [_P, _P, _P, _L, _I, _P, _P, _P, _P, _I, _P, _P, _P, _P, _P, _P]),
     "cova_bn_act_bwd_planes": (_I, [_P, _P, _P, _L, _I, _P, _P, _P, _P, _I, _P, _P, _P, _P, _I, _I, _P, _P, _P, _P, _P]),
     "cova_bn_train_stats_t": (_I, [_P, _I, _L, _I, _P, _P]),
-    "cova_bn_act_fwd_t": (_I, [_P, _I, _L, _I, _P, _P, _P, _P, _P, _I, _P, _I, _P]),
-    "cova_bn_act_bwd_t": (_I, [_P, _I, _P, _P, _I, _L, _I, _P, _P, _P, _P, _I, _P, _P, _P, _P, _P, _P]),
+    "cova_bn_act_fwd_t": (_I, [_P, _I, _L, _I, _P, _P, _P, _P, _P, _I, _P, _I, _P, _P]),
+    "cova_bn_act_bwd_t": (_I, [_P, _I, _P, _P, _I, _L, _I, _P, _P, _P, _P, _I, _P, _P, _P, _P, _P, _P, _P]),
     "cova_maxpool3x3s2_fwd_t": (_I, [_P, _I, _I, _I, _I, _I, _P, _P, _P]),
     "cova_maxpool3x3s2_bwd_t": (_I, [_P, _P, _I, _I, _I, _I, _I, _P, _P]),
     "cova_stem_conv_raw_fwd_bf16": (_I, [_P, _I, _I, _I, _I, _P, _P, _P]),

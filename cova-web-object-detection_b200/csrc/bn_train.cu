@@ -127,12 +127,12 @@ template <int V> __device__ __forceinline__ void ldp(const float* p, int c0, flo
 // MODE 2: MODE 1 + wmax[c] = max |x - mean| per channel and wmax[C] = max |g| (bit patterns of non-negative floats): what
 // bounds |dx| before dx exists, so that the apply pass can emit SCALED split-fp16 planes directly (bn_act_bwd_kernel<true>).
 // TS = storage type of x / res, TG = type of dy; a thread owns V = 16 B / sizeof(TS) channels and strides over pixels.
-template <int MODE, typename TS = float, typename TG = float>
+template <int MODE, typename TS = float, typename TG = float, bool MASK = false>
 __global__ void __launch_bounds__(BN_THREADS, 4)
 bn_reduce_kernel(const TS* __restrict__ x, const TG* __restrict__ dy, const TS* __restrict__ res, int64_t M,
                  int C, const float* __restrict__ mean, const float* __restrict__ invstd,
                  const float* __restrict__ gamma, const float* __restrict__ beta, int relu, double* __restrict__ ws,
-                 unsigned int* __restrict__ wmax = nullptr) {
+                 unsigned int* __restrict__ wmax = nullptr, const unsigned char* __restrict__ mask = nullptr) {
   constexpr int V = Vec<TS>::V;
   extern __shared__ __align__(16) float red[];                       // [2][rows][C]
   const int cvn = C / V, rows = BN_THREADS / cvn;
@@ -178,14 +178,19 @@ bn_reduce_kernel(const TS* __restrict__ x, const TG* __restrict__ dy, const TS* 
         float xv[V], g[V], r[V];
         ldv<TS>(x, p * C + c0, xv);
         ldv_any<V>(dy, p * C + c0, g);
-        if (relu && res != nullptr) ldv<TS>(res, p * C + c0, r);
+        // ReLU decision: the forward's bit mask (one byte per thread and pixel) when it was kept - the residual map is then
+        // not read at all - otherwise y is recomputed from x (and res)
+        const unsigned bits = (MASK && relu) ? (unsigned)__ldg(mask + p * cvn + cg) : 0u;
+        if (!MASK && relu && res != nullptr) ldv<TS>(res, p * C + c0, r);
 #pragma unroll
         for (int k = 0; k < V; ++k) {
           // bf16 storage: accumulate sum g*x and form sum g*xhat = inv (sum g*x - mean sum g) once per thread below (two
           // instructions and 16 registers less per element; the cancellation costs |mean|/std ulps of fp32, irrelevant next to
           // the bf16 maps).  fp32 storage keeps the centred product.
           const float xh = sizeof(TS) == 2 ? xv[k] : (xv[k] - mu[k]) * iv[k];
-          if (relu) {
+          if (MASK) {
+            if (relu) g[k] = ((bits >> k) & 1u) ? g[k] : 0.f;
+          } else if (relu) {
             float y = fmaf(xv[k], ga[k], be[k]);
             if (res != nullptr) y += r[k];
             g[k] = y > 0.f ? g[k] : 0.f;
@@ -256,7 +261,7 @@ __global__ void __launch_bounds__(BN_THREADS)
 bn_act_fwd_kernel(const TS* __restrict__ x, int64_t nv, int C, const float* __restrict__ mean,
                   const float* __restrict__ invstd, const float* __restrict__ gamma, const float* __restrict__ beta,
                   const TS* __restrict__ res, int relu, TY* __restrict__ y, __nv_bfloat16* __restrict__ y_hi,
-                  __nv_bfloat16* __restrict__ y_lo, int f16) {
+                  __nv_bfloat16* __restrict__ y_lo, int f16, unsigned char* __restrict__ mask = nullptr) {
   constexpr int V = Vec<TS>::V;
   extern __shared__ __align__(16) float tab[];                       // [2][C]: A, B
   const int cvn = C / V;
@@ -274,6 +279,12 @@ bn_act_fwd_kernel(const TS* __restrict__ x, int64_t nv, int C, const float* __re
       if (res != nullptr) o[k] += r[k];
       if (relu) o[k] = fmaxf(o[k], 0.f);
     }
+    if (mask != nullptr) {   // bit k = [y_k > 0]: what the backward passes need of the residual map (1 bit instead of 16 / 32)
+      unsigned bits = 0u;
+#pragma unroll
+      for (int k = 0; k < V; ++k) bits |= (o[k] > 0.f ? 1u : 0u) << k;
+      mask[i] = (unsigned char)bits;
+    }
     if (y != nullptr) stv_any<V>(y, i * V, o);
     if (y_hi != nullptr) {
 #pragma unroll
@@ -286,7 +297,7 @@ bn_act_fwd_kernel(const TS* __restrict__ x, int64_t nv, int C, const float* __re
 // brings an upper bound of max|dx| - computed here from the reduce pass's maxima: |dx| <= |gamma inv| (max|g| + |S1/M| +
 // max|xhat| |S2/M|) - into [2^target, 2^(target+1)); block 0 publishes 256 copies of 1/s for the consuming convolution
 // kernels (dgrad epilogue scale / wgrad finalize).  The fp32 gradient map is never written nor re-read for the split.
-template <bool PLANES, typename TS = float, typename TG = float>
+template <bool PLANES, typename TS = float, typename TG = float, bool MASK = false>
 __global__ void __launch_bounds__(BN_THREADS)
 bn_act_bwd_kernel(const TG* __restrict__ dy, const TS* __restrict__ x, const TS* __restrict__ res, int64_t nv,
                   int64_t M, int C, const float* __restrict__ mean, const float* __restrict__ invstd,
@@ -294,7 +305,7 @@ bn_act_bwd_kernel(const TG* __restrict__ dy, const TS* __restrict__ x, const TS*
                   const double* __restrict__ ws, TS* __restrict__ dx, TS* __restrict__ dres,
                   float* __restrict__ dgamma, float* __restrict__ dbeta, const unsigned int* __restrict__ wmax,
                   __nv_bfloat16* __restrict__ dx_hi, __nv_bfloat16* __restrict__ dx_lo, int f16, int target_log2,
-                  float* __restrict__ inv_vec) {
+                  float* __restrict__ inv_vec, const unsigned char* __restrict__ mask = nullptr) {
   constexpr int V = Vec<TS>::V;
   extern __shared__ __align__(16) float sums[];                      // [2][C]: S1/M, S2/M, then [4][C]: A, B, c1, c2
   float* tab = sums + 2 * C;
@@ -342,12 +353,15 @@ bn_act_bwd_kernel(const TG* __restrict__ dy, const TS* __restrict__ x, const TS*
     float xv[V], g[V], r[V], o[V], A[V], B[V], c1[V], c2[V];
     ldv<TS>(x, i * V, xv);
     ldv_any<V>(dy, i * V, g);
-    if (relu && res != nullptr) ldv<TS>(res, i * V, r);
+    const unsigned bits = (MASK && relu) ? (unsigned)__ldg(mask + i) : 0u;
+    if (!MASK && relu && res != nullptr) ldv<TS>(res, i * V, r);
     ldp<V>(tab, c0, A); ldp<V>(tab + 2 * C, c0, c1); ldp<V>(tab + 3 * C, c0, c2);
-    if (relu) ldp<V>(tab + C, c0, B);
+    if (!MASK && relu) ldp<V>(tab + C, c0, B);
 #pragma unroll
     for (int k = 0; k < V; ++k) {
-      if (relu) {
+      if (MASK) {
+        if (relu) g[k] = ((bits >> k) & 1u) ? g[k] : 0.f;
+      } else if (relu) {
         float y = fmaf(xv[k], A[k], B[k]);
         if (res != nullptr) y += r[k];
         g[k] = y > 0.f ? g[k] : 0.f;
@@ -951,8 +965,10 @@ extern "C" int cova_bn_train_stats_t(const void* x, int x_dtype, int64_t M, int 
 
 extern "C" int cova_bn_act_fwd_t(const void* x, int s_dtype, int64_t M, int C, const float* mean, const float* invstd,
                                  const float* gamma, const float* beta, const void* res, int relu, void* y, int y_dtype,
-                                 void* stream) {
+                                 unsigned char* relu_mask, void* stream) {
   COVA_REQUIRE(dt_ok(s_dtype) && dt_ok(y_dtype), "cova_bn_act_fwd_t: dtypes are fp32 or bf16");
+  COVA_REQUIRE(!relu_mask || (s_dtype == COVA_BF16 && relu), "cova_bn_act_fwd_t: the ReLU bit mask comes with bf16 storage and relu");
+  unsigned char* mk = relu_mask;
   COVA_REQUIRE(x && y && mean && invstd && gamma && beta && M > 0, "cova_bn_act_fwd_t: bad arguments");
   COVA_REQUIRE(bn_c_ok(C) && (s_dtype == COVA_F32 || C >= 8), "cova_bn_act_fwd_t: C=%d must be a power of two in [4 (fp32) / 8 (bf16), 1024]", C);
   COVA_REQUIRE((((uintptr_t)x | (uintptr_t)y | (uintptr_t)res) & 15) == 0, "cova_bn_act_fwd_t: 16-byte alignment");
@@ -963,9 +979,9 @@ extern "C" int cova_bn_act_fwd_t(const void* x, int s_dtype, int64_t M, int C, c
   if (s_dtype == COVA_F32 && y_dtype == COVA_F32)
     bn_act_fwd_kernel<float, float><<<grid, BN_THREADS, 2 * C * sizeof(float), st>>>((const float*)x, nv, C, mean, invstd, gamma, beta, (const float*)res, relu, (float*)y, nullptr, nullptr, 0);
   else if (s_dtype == COVA_BF16 && y_dtype == COVA_BF16)
-    bn_act_fwd_kernel<bf16_t, bf16_t><<<grid, BN_THREADS, 2 * C * sizeof(float), st>>>((const bf16_t*)x, nv, C, mean, invstd, gamma, beta, (const bf16_t*)res, relu, (bf16_t*)y, nullptr, nullptr, 0);
+    bn_act_fwd_kernel<bf16_t, bf16_t><<<grid, BN_THREADS, 2 * C * sizeof(float), st>>>((const bf16_t*)x, nv, C, mean, invstd, gamma, beta, (const bf16_t*)res, relu, (bf16_t*)y, nullptr, nullptr, 0, mk);
   else if (s_dtype == COVA_BF16)
-    bn_act_fwd_kernel<bf16_t, float><<<grid, BN_THREADS, 2 * C * sizeof(float), st>>>((const bf16_t*)x, nv, C, mean, invstd, gamma, beta, (const bf16_t*)res, relu, (float*)y, nullptr, nullptr, 0);
+    bn_act_fwd_kernel<bf16_t, float><<<grid, BN_THREADS, 2 * C * sizeof(float), st>>>((const bf16_t*)x, nv, C, mean, invstd, gamma, beta, (const bf16_t*)res, relu, (float*)y, nullptr, nullptr, 0, mk);
   else
     COVA_REQUIRE(false, "cova_bn_act_fwd_t: fp32 storage with a bf16 output is not built");
   COVA_LAUNCH_OK();
@@ -974,8 +990,11 @@ extern "C" int cova_bn_act_fwd_t(const void* x, int s_dtype, int64_t M, int C, c
 
 extern "C" int cova_bn_act_bwd_t(const void* dy, int dy_dtype, const void* x, const void* res, int s_dtype, int64_t M, int C,
                                  const float* mean, const float* invstd, const float* gamma, const float* beta, int relu,
-                                 double* ws, void* dx, void* dres, float* dgamma, float* dbeta, void* stream) {
+                                 double* ws, void* dx, void* dres, float* dgamma, float* dbeta, const unsigned char* relu_mask,
+                                 void* stream) {
   COVA_REQUIRE(dt_ok(s_dtype) && dt_ok(dy_dtype), "cova_bn_act_bwd_t: dtypes are fp32 or bf16");
+  COVA_REQUIRE(!relu_mask || (s_dtype == COVA_BF16 && relu), "cova_bn_act_bwd_t: the ReLU bit mask comes with bf16 storage and relu");
+  const unsigned char* mk = relu_mask;
   if (s_dtype == COVA_F32 && dy_dtype == COVA_F32)
     return cova_bn_act_bwd((const float*)dy, (const float*)x, (const float*)res, M, C, mean, invstd, gamma, beta, relu, ws,
                            (float*)dx, (float*)dres, dgamma, dbeta, stream);
@@ -993,19 +1012,21 @@ extern "C" int cova_bn_act_bwd_t(const void* dy, int dy_dtype, const void* x, co
   const int64_t nv = M * (C / 8);
   const int g2 = ew_grid(nv, BN_THREADS);
   const bf16_t *xb = (const bf16_t*)x, *rb = (const bf16_t*)res;
+#define COVA_BN_BWD_T(TGT, MK)                                                                                                  \
+  do {                                                                                                                         \
+    bn_reduce_kernel<1, bf16_t, TGT, MK><<<(int)grid, BN_THREADS, smem, st>>>(xb, (const TGT*)dy, rb, M, C, mean, invstd, gamma, \
+                                                                              beta, relu, ws, nullptr, mk);                     \
+    COVA_LAUNCH_OK();                                                                                                          \
+    bn_act_bwd_kernel<false, bf16_t, TGT, MK><<<g2, BN_THREADS, 6 * C * sizeof(float), st>>>(                                   \
+        (const TGT*)dy, xb, rb, nv, M, C, mean, invstd, gamma, beta, relu, ws, (bf16_t*)dx, (bf16_t*)dres, dgamma, dbeta,      \
+        nullptr, nullptr, nullptr, 0, 0, nullptr, mk);                                                                         \
+  } while (0)
   if (dy_dtype == COVA_BF16) {
-    bn_reduce_kernel<1, bf16_t, bf16_t><<<(int)grid, BN_THREADS, smem, st>>>(xb, (const bf16_t*)dy, rb, M, C, mean, invstd, gamma, beta, relu, ws);
-    COVA_LAUNCH_OK();
-    bn_act_bwd_kernel<false, bf16_t, bf16_t><<<g2, BN_THREADS, 6 * C * sizeof(float), st>>>(
-        (const bf16_t*)dy, xb, rb, nv, M, C, mean, invstd, gamma, beta, relu, ws, (bf16_t*)dx, (bf16_t*)dres, dgamma, dbeta, nullptr,
-        nullptr, nullptr, 0, 0, nullptr);
+    if (mk) COVA_BN_BWD_T(bf16_t, true); else COVA_BN_BWD_T(bf16_t, false);
   } else {
-    bn_reduce_kernel<1, bf16_t, float><<<(int)grid, BN_THREADS, smem, st>>>(xb, (const float*)dy, rb, M, C, mean, invstd, gamma, beta, relu, ws);
-    COVA_LAUNCH_OK();
-    bn_act_bwd_kernel<false, bf16_t, float><<<g2, BN_THREADS, 6 * C * sizeof(float), st>>>(
-        (const float*)dy, xb, rb, nv, M, C, mean, invstd, gamma, beta, relu, ws, (bf16_t*)dx, (bf16_t*)dres, dgamma, dbeta, nullptr,
-        nullptr, nullptr, 0, 0, nullptr);
+    if (mk) COVA_BN_BWD_T(float, true); else COVA_BN_BWD_T(float, false);
   }
+#undef COVA_BN_BWD_T
   COVA_LAUNCH_OK();
   return COVA_OK;
 }

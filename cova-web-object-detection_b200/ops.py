@@ -711,8 +711,10 @@ def stem_conv_raw_fwd_bf16(images, w_packed, stats_ws=None):
     return out
 
 
-def bn_train_fwd_t(x, gamma, beta, running_mean, running_var, momentum, eps, res=None, relu=True, out_dtype=None, stats_ws=None):
-    """`bn_train_fwd` on a map of either storage type (fp32 / bf16); y in `out_dtype` (default: x's).  Returns (y, mean, invstd)."""
+def bn_train_fwd_t(x, gamma, beta, running_mean, running_var, momentum, eps, res=None, relu=True, out_dtype=None, stats_ws=None,
+                   relu_mask=None):
+    """`bn_train_fwd` on a map of either storage type (fp32 / bf16); y in `out_dtype` (default: x's).  Returns (y, mean, invstd).
+    relu_mask (bf16 storage, relu): uint8 [numel / 8], filled with the ReLU decisions for `bn_train_bwd_t`."""
     _map(x, "x")
     C = x.shape[-1]
     M = x.numel() // C
@@ -730,12 +732,13 @@ def bn_train_fwd_t(x, gamma, beta, running_mean, running_var, momentum, eps, res
         global param_generation
         param_generation += 1
     _call("cova_bn_act_fwd_t", x.data_ptr(), _dt(x), M, C, mean.data_ptr(), inv.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
-          _ptr(res), int(relu), y.data_ptr(), _dt(y), _stream())
+          _ptr(res), int(relu), y.data_ptr(), _dt(y), _ptr(relu_mask), _stream())
     return y, mean, inv
 
 
-def bn_train_bwd_t(dy, x, mean, invstd, gamma, beta, res=None, relu=True, want_dres=False):
-    """Backward of `bn_train_fwd_t`: dx / dres in x's storage type; dy fp32 or bf16.  Returns (dx, dres | None, dgamma, dbeta)."""
+def bn_train_bwd_t(dy, x, mean, invstd, gamma, beta, res=None, relu=True, want_dres=False, relu_mask=None):
+    """Backward of `bn_train_fwd_t`: dx / dres in x's storage type; dy fp32 or bf16.  Returns (dx, dres | None, dgamma, dbeta).
+    relu_mask = the forward's bit mask: the residual map is then not needed (nor read)."""
     _map(dy, "dy"); _map(x, "x")
     C = x.shape[-1]
     M = x.numel() // C
@@ -746,7 +749,7 @@ def bn_train_bwd_t(dy, x, mean, invstd, gamma, beta, res=None, relu=True, want_d
     dg, db = torch.empty(C, dtype=torch.float32, device=dev), torch.empty(C, dtype=torch.float32, device=dev)
     _call("cova_bn_act_bwd_t", dy.data_ptr(), _dt(dy), x.data_ptr(), _ptr(res), _dt(x), M, C, mean.data_ptr(), invstd.data_ptr(),
           gamma.data_ptr(), beta.data_ptr(), int(relu), ws.data_ptr(), dx.data_ptr(), _ptr(dres), dg.data_ptr(), db.data_ptr(),
-          _stream())
+          _ptr(relu_mask), _stream())
     return dx, dres, dg, db
 
 

@@ -353,7 +353,7 @@ def feature_map_train_modular(convnet, images):
 # ----------------------------------------------------------------------------- whole-backbone autograd function
 class _Unit:
     """Saved state of one conv -> BatchNorm(batch statistics) (+ residual) (+ ReLU) unit of the backbone."""
-    __slots__ = ("kind", "xin", "weight", "bn", "raw", "mean", "inv", "res", "relu", "has_res", "y", "planes", "x_shape")
+    __slots__ = ("kind", "xin", "weight", "bn", "raw", "mean", "inv", "res", "relu", "has_res", "y", "planes", "x_shape", "mask")
 
 
 def _unit_fwd(kind, xin, conv, bn, res=None, relu=True, want_y=True, want_planes=False):
@@ -422,6 +422,11 @@ def _unit_bwd(u, dy, need_dx=True, add=None):
     return dx, dw, dg, db, dres
 
 
+def _relu_mask():
+    """bf16 mode: residual units hand a ReLU bit mask to their backward (COVA_B200_TRAIN_RELU_MASK=0: re-read the residual)."""
+    return os.environ.get("COVA_B200_TRAIN_RELU_MASK", "1") != "0"
+
+
 def _unit_fwd16(kind, xin, conv, bn, res=None, relu=True, out_fp32=False):
     """bf16 training mode (BASELINE config 3): the unit with every map stored as bf16 - raw convolution output, y (one bf16
     plane = the operand of the next convolution, one product per MMA) - statistics / parameters fp32.  xin = images (stem)
@@ -441,10 +446,16 @@ def _unit_fwd16(kind, xin, conv, bn, res=None, relu=True, out_fp32=False):
         u.raw = ops.conv1x1_raw_fwd(ops.bf16_plane(xin), w.flatten(1).to(torch.bfloat16).contiguous(), stats_ws=sw)
     track = bn.track_running_stats and bn.running_mean is not None
     mom = _momentum(bn, track)
-    u.res = res if (relu and res is not None) else None
+    # residual units keep the forward's ReLU decisions as a bit mask (1/16 of the residual map's bytes): the two backward passes
+    # then do not read the residual at all
+    u.res = None
+    u.mask = (torch.empty(u.raw.numel() // 8, dtype=torch.uint8, device=u.raw.device)
+              if (relu and res is not None and _relu_mask()) else None)
+    if u.mask is None and relu and res is not None:
+        u.res = res
     u.y, u.mean, u.inv = ops.bn_train_fwd_t(u.raw, bn.weight.detach(), bn.bias.detach(), bn.running_mean if track else None,
                                             bn.running_var if track else None, mom, bn.eps, res=res, relu=relu,
-                                            out_dtype=torch.float32 if out_fp32 else torch.bfloat16, stats_ws=sw)
+                                            out_dtype=torch.float32 if out_fp32 else torch.bfloat16, stats_ws=sw, relu_mask=u.mask)
     u.planes = None
     if track and bn.num_batches_tracked is not None:
         bn.num_batches_tracked += 1
@@ -456,7 +467,8 @@ def _unit_bwd16(u, dy, need_dx=True, add=None):
     exponent range: no scaling), fp32 weight gradients from the single-plane tensor-core wgrad kernels."""
     bn = u.bn
     dxr, dres, dg, db = ops.bn_train_bwd_t(dy, u.raw, u.mean, u.inv, bn.weight.detach(), bn.bias.detach(), res=u.res, relu=u.relu,
-                                           want_dres=u.has_res)
+                                           want_dres=u.has_res, relu_mask=getattr(u, "mask", None))
+    u.mask = None
     dyp = ops.bf16_plane(dxr)
     w = u.weight.detach().float()
     dx = None

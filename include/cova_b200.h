@@ -336,8 +336,10 @@ int cova_stem_wgrad(const void* images, int img_dtype, int B, int H, int W, cons
  * operand of the next tensor-core convolution: one product per MMA), gradient maps; statistics, parameters and weight
  * gradients stay fp32, arithmetic inside every kernel is fp32.  dtype arguments are COVA_F32 or COVA_BF16.
  *   cova_bn_train_stats_t : ws = [sum x | sum x^2] of x [M, C] (x_dtype)
- *   cova_bn_act_fwd_t     : y (y_dtype) = [relu](BN(x) [+ res]); x and res are s_dtype
- *   cova_bn_act_bwd_t     : dx, dres (s_dtype) from dy (dy_dtype), x / res (s_dtype); dgamma / dbeta fp32
+ *   cova_bn_act_fwd_t     : y (y_dtype) = [relu](BN(x) [+ res]); x and res are s_dtype.  relu_mask (optional, bf16 storage with
+ *                           relu): [M * C / 8] bytes, bit k of byte i = [y > 0] of element 8 i + k - the forward's ReLU decisions
+ *   cova_bn_act_bwd_t     : dx, dres (s_dtype) from dy (dy_dtype), x / res (s_dtype); dgamma / dbeta fp32.  With relu_mask (the
+ *                           forward's) neither backward pass reads res: 1 bit instead of 16 per element and pass
  *   cova_maxpool3x3s2_*_t : nn.MaxPool2d(3,2,1) forward (+ winner codes) / backward on maps of `dtype`
  *   cova_stem_conv_raw_fwd_bf16 : conv1 (7x7 s2) in one bf16 product (w = cova_pack_stem_weight), raw output as bf16
  * The convolutions' bf16 entry points are the existing ones: cova_conv3x3_bn_act_fwd (COVA_BF16 in / out, identity
@@ -345,10 +347,11 @@ int cova_stem_wgrad(const void* images, int img_dtype, int B, int H, int W, cons
  * the three wgrad calls with planes_dtype COVA_BF16 and NULL lo planes.                                               */
 int cova_bn_train_stats_t(const void* x, int x_dtype, int64_t M, int C, double* ws, void* stream);
 int cova_bn_act_fwd_t(const void* x, int s_dtype, int64_t M, int C, const float* mean, const float* invstd,
-                      const float* gamma, const float* beta, const void* res, int relu, void* y, int y_dtype, void* stream);
+                      const float* gamma, const float* beta, const void* res, int relu, void* y, int y_dtype,
+                      unsigned char* relu_mask, void* stream);
 int cova_bn_act_bwd_t(const void* dy, int dy_dtype, const void* x, const void* res, int s_dtype, int64_t M, int C,
                       const float* mean, const float* invstd, const float* gamma, const float* beta, int relu, double* ws,
-                      void* dx, void* dres, float* dgamma, float* dbeta, void* stream);
+                      void* dx, void* dres, float* dgamma, float* dbeta, const unsigned char* relu_mask, void* stream);
 int cova_maxpool3x3s2_fwd_t(const void* x, int dtype, int B, int H, int W, int C, void* y, unsigned char* code, void* stream);
 int cova_maxpool3x3s2_bwd_t(const unsigned char* code, const void* dy, int dtype, int B, int H, int W, int C, void* dx,
                             void* stream);

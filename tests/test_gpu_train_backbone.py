@@ -339,6 +339,31 @@ def test_bn_train_bf16_storage_vs_torch(shape, relu, with_res, out32):
     assert rel_err(n(rm), n(rm2)) < 2e-5 and rel_err(n(rv), n(rv2)) < 2e-5
 
 
+@pytest.mark.parametrize("shape,out32", [((3, 16, 20, 64), False), ((2, 12, 12, 256), True), ((1, 7, 9, 8), False)])
+def test_bn_train_bf16_relu_mask_equals_residual_reread(shape, out32):
+    """The forward's ReLU bit mask (1 bit per element) drives the backward exactly as re-reading the residual map does:
+    dx, dres, dgamma, dbeta bit-identical; the mask itself equals [y > 0]."""
+    from cova_b200 import ops
+    g = torch.Generator().manual_seed(sum(shape) + 11)
+    C = shape[-1]
+    x = _bf(torch.randn(shape, generator=g) * 2 + 0.5).to(DEV)
+    res = _bf(torch.randn(shape, generator=g)).to(DEV)
+    gamma = (torch.rand(C, generator=g) + 0.5).to(DEV); beta = (torch.randn(C, generator=g) * 0.2).to(DEV)
+    dy = torch.randn(shape, generator=g)
+    dy = (dy if out32 else _bf(dy)).to(DEV)
+    mask = torch.zeros(x.numel() // 8, dtype=torch.uint8, device=DEV)
+    od = torch.float32 if out32 else torch.bfloat16
+    y, mean, inv = ops.bn_train_fwd_t(x, gamma, beta, None, None, 0.1, 1e-5, res=res, relu=True, out_dtype=od, relu_mask=mask)
+    y0, _, _ = ops.bn_train_fwd_t(x, gamma, beta, None, None, 0.1, 1e-5, res=res, relu=True, out_dtype=od)
+    assert torch.equal(y, y0)
+    bits = ((mask.view(-1, 1).int() >> torch.arange(8, device=DEV).view(1, 8)) & 1).bool().view(shape)
+    assert torch.equal(bits, y.float() > 0)
+    a = ops.bn_train_bwd_t(dy, x, mean, inv, gamma, beta, res=res, relu=True, want_dres=True)
+    b = ops.bn_train_bwd_t(dy, x, mean, inv, gamma, beta, res=None, relu=True, want_dres=True, relu_mask=mask)
+    for u, v in zip(a, b):
+        assert torch.equal(u, v)
+
+
 def test_maxpool_bf16_bit_exact():
     from cova_b200 import ops
     g = torch.Generator().manual_seed(5)
