@@ -267,7 +267,8 @@ bn_act_fwd_kernel(const TS* __restrict__ x, int64_t nv, int C, const float* __re
   const int cvn = C / V;
   for (int c = threadIdx.x; c < C; c += BN_THREADS) bn_affine(mean[c], invstd[c], gamma[c], beta[c], tab[c], tab[C + c]);
   __syncthreads();
-  for (int64_t i = (int64_t)blockIdx.x * BN_THREADS + threadIdx.x; i < nv; i += (int64_t)gridDim.x * BN_THREADS) {
+  // descending order: the statistics pass that ran just before this one read the map ascending, so its tail is what L2 still holds
+  for (int64_t i = nv - 1 - ((int64_t)blockIdx.x * BN_THREADS + threadIdx.x); i >= 0; i -= (int64_t)gridDim.x * BN_THREADS) {
     const int c0 = V * (int)(i % cvn);
     float xv[V], r[V], o[V], A[V], B[V];
     ldv<TS>(x, i * V, xv);
@@ -348,7 +349,8 @@ bn_act_bwd_kernel(const TG* __restrict__ dy, const TS* __restrict__ x, const TS*
     scale = s_scale;
     if (blockIdx.x == 0) inv_vec[threadIdx.x] = 1.f / scale;
   }
-  for (int64_t i = (int64_t)blockIdx.x * BN_THREADS + threadIdx.x; i < nv; i += (int64_t)gridDim.x * BN_THREADS) {
+  // descending order: the statistics pass that ran just before this one read the map ascending, so its tail is what L2 still holds
+  for (int64_t i = nv - 1 - ((int64_t)blockIdx.x * BN_THREADS + threadIdx.x); i >= 0; i -= (int64_t)gridDim.x * BN_THREADS) {
     const int c0 = V * (int)(i % cvn);
     float xv[V], g[V], r[V], o[V], A[V], B[V], c1[V], c2[V];
     ldv<TS>(x, i * V, xv);
