@@ -40,7 +40,8 @@ constexpr int SW_NS = 3;                   // dY stages
 constexpr int SW_DY_PLANE = SW_TM * 128;   // 16,384 B: one plane of a dY tile
 constexpr int SW_DY_STAGE = 2 * SW_DY_PLANE;
 constexpr int SW_NCV = 8;                  // converter warps
-constexpr int SW_THREADS = 32 * (2 + 4 + SW_NCV);
+constexpr int SW_THREADS = 32 * (3 + 4 + SW_NCV);   // + a second MMA issuer warp (the last one)
+constexpr int SW_ISSUER_B = 2 + 4 + SW_NCV;
 constexpr int SW_ACC_COLS = 256;           // 7 x 32 used
 constexpr int SW_TMEM_COLS = 512;
 constexpr int SW_WS = 64 * 224;            // floats of the global partial sum
@@ -84,6 +85,27 @@ __host__ __device__ constexpr uint32_t sw_idesc_mn(int M, int N, bool half) {
          ((uint32_t)(M >> 4) << 24);
 }
 
+// The MMAs of filter rows R0 .. R1-1 for one tile of 128 conv pixels (8 K-steps of 16 pixels).  `first0` = 0: the tile opens
+// its accumulator buffer (the first K-step overwrites).
+template <int R0, int R1, bool HALF>
+__device__ __forceinline__ void sw_issue_rows(uint32_t d_tmem, uint32_t dy_addr, uint32_t ring0, uint32_t g0, uint32_t first0,
+                                              bool dy_single) {
+  constexpr uint32_t idesc = sw_idesc_mn(128, 32, HALF);
+#pragma unroll 1
+  for (int kk = 0; kk < 8; ++kk) {                         // K = 16 conv pixels
+    const uint64_t da = sw_desc_mn_sw128(dy_addr + kk * 2048, SW_DY_PLANE, 1024);      // [dYhi ; dYlo]
+    const uint32_t first = (first0 == 0u && kk == 0) ? 0u : 1u;
+#pragma unroll
+    for (int r = R0; r < R1; ++r) {
+      const uint32_t row = ring0 + ((g0 + r) % SW_R) * SW_ROW_BYTES + kk * 256;        // 16 pixels x 16 B
+      ptx::umma_bf16(d_tmem + r * 32, da, sw_desc_noswz(row, 128, 16), idesc, first);
+      // bf16 training mode (one dY plane): the forward convolved bf16(image), so the gradient of what was computed
+      // takes the hi plane of the image alone - half the MMAs
+      if (!dy_single) ptx::umma_bf16(d_tmem + r * 32, da, sw_desc_noswz(row + SW_R * SW_ROW_BYTES, 128, 16), idesc, 1u);
+    }
+  }
+}
+
 template <bool U8, bool HALF>
 __global__ void __launch_bounds__(SW_THREADS, 1)
 stem_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_dy_hi, const __grid_constant__ CUtensorMap tm_dy_lo,
@@ -105,15 +127,15 @@ stem_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_dy_hi, const __grid_
   if (threadIdx.x == 0) {
     for (int i = 0; i < SW_R; ++i) ptx::mbar_init(&sm.in_full[i], 1);
     for (int i = 0; i < SW_ND; ++i) {
-      ptx::mbar_init(&sm.mma_done[i], 1);
+      ptx::mbar_init(&sm.mma_done[i], 2);          // one commit per issuer warp
       ptx::mbar_init(&sm.pair_full[i], 2);
     }
     for (int i = 0; i < SW_NS; ++i) {
       ptx::mbar_init(&sm.dy_full[i], 1);
-      ptx::mbar_init(&sm.dy_empty[i], 1);
+      ptx::mbar_init(&sm.dy_empty[i], 2);
     }
     for (int i = 0; i < 2; ++i) {
-      ptx::mbar_init(&sm.acc_full[i], 1);
+      ptx::mbar_init(&sm.acc_full[i], 2);
       ptx::mbar_init(&sm.acc_empty[i], 128);
     }
     ptx::fence_barrier_init();
@@ -137,9 +159,11 @@ stem_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_dy_hi, const __grid_
   const uint32_t tmem_base = sm.tmem_base;
   if (n_conv <= 0) goto teardown;
 
-  if (warp == 0) {
-    // ======================= MMA issuer =======================
-    constexpr uint32_t idesc = sw_idesc_mn(128, 32, HALF);
+  if (warp == 0 || warp == SW_ISSUER_B) {
+    // ======================= MMA issuers =======================
+    // Two warps share every tile: filter rows 0..3 / 4..6 accumulate in disjoint TMEM columns (r * 32), so the two issue streams
+    // never touch the same accumulator.  Fourteen N = 32 MMAs per 16 pixels from one thread ran at ~53 clk each against the
+    // pipe's ~40-clk floor for this shape (stem_tc.cu: the issuing thread's latency).
     const uint32_t ring0 = ptx::smem_u32(&sm.ring[0][0][0]);
     const uint32_t dy0 = ptx::smem_u32(&sm.dy[0][0]);
     uint32_t t = 0, buf = 0, n_in_buf = 0, uses[2] = {0u, 0u};
@@ -161,19 +185,9 @@ stem_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_dy_hi, const __grid_
         if (ptx::elect_one()) {
           const uint32_t d_tmem = tmem_base + buf * SW_ACC_COLS;
           const uint32_t dy_addr = dy0 + stage * SW_DY_STAGE;
-#pragma unroll 1
-          for (int kk = 0; kk < 8; ++kk) {                         // K = 16 conv pixels
-            const uint64_t da = sw_desc_mn_sw128(dy_addr + kk * 2048, SW_DY_PLANE, 1024);      // [dYhi ; dYlo]
-            const uint32_t first = (n_in_buf == 0 && kk == 0) ? 0u : 1u;
-#pragma unroll
-            for (int r = 0; r < 7; ++r) {
-              const uint32_t row = ring0 + ((g0 + r) % SW_R) * SW_ROW_BYTES + kk * 256;        // 16 pixels x 16 B
-              ptx::umma_bf16(d_tmem + r * 32, da, sw_desc_noswz(row, 128, 16), idesc, first);
-              // bf16 training mode (one dY plane): the forward convolved bf16(image), so the gradient of what was computed
-              // takes the hi plane of the image alone - half the MMAs
-              if (!p.dy_single) ptx::umma_bf16(d_tmem + r * 32, da, sw_desc_noswz(row + SW_R * SW_ROW_BYTES, 128, 16), idesc, 1u);
-            }
-          }
+          const uint32_t first0 = n_in_buf == 0 ? 0u : 1u;
+          if (warp == 0) sw_issue_rows<0, 4, HALF>(d_tmem, dy_addr, ring0, g0, first0, p.dy_single != 0);
+          else           sw_issue_rows<4, 7, HALF>(d_tmem, dy_addr, ring0, g0, first0, p.dy_single != 0);
           ptx::umma_commit(&sm.mma_done[t % SW_ND]);
           ptx::umma_commit(&sm.dy_empty[stage]);
           if (n_in_buf + 1 == (uint32_t)p.drain_every || last) ptx::umma_commit(&sm.acc_full[buf]);
@@ -201,7 +215,7 @@ stem_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_dy_hi, const __grid_
         __syncwarp();
       }
     }
-  } else if (warp < 6) {
+  } else if (warp >= 2 && warp < 6) {
     // ======================= drain: TMEM -> RED.ADD.F32x4 into ws[co][224] =======================
     const int lg = warp & 3;
     const int co = (lg * 32 + lane) & 63;          // lanes 0-63: dYhi rows, 64-127: dYlo rows of the same cout
@@ -228,7 +242,7 @@ stem_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_dy_hi, const __grid_
       ptx::tc_fence_before();
       ptx::mbar_arrive(&sm.acc_empty[bf]);
     }
-  } else {
+  } else if (warp < SW_ISSUER_B) {
     // ======================= converters: NCHW image rows -> ring of 4-channel 16-bit pixels (hi, lo) =======================
     const int cw = warp - 6;
     const size_t plane = (size_t)p.H * p.W;
