@@ -182,10 +182,10 @@ def _alg_table(roi_b):
         "cova_linear_fwd": lambda a: ("tensor", 2.0 * i(a[2]) * i(a[3]) * i(a[5])),
         "cova_bbox_enc_fwd": lambda a: ("hbm", float(i(a[1])) * (20 + 4 * i(a[6]))),
         "cova_bn_train_stats": lambda a: ("hbm", 4.0 * i(a[1]) * i(a[2])),
-        "cova_bn_act_fwd": lambda a: ("hbm", 4.0 * i(a[1]) * i(a[2]) * (2 + (1 if a[7] else 0) + (1 if a[10] else 0))),
+        "cova_bn_act_fwd": lambda a: ("hbm", 4.0 * i(a[1]) * i(a[2]) * (2 + (1 if a[7] else 0) + (1 if a[10] else 0) + (0.0625 if a[13] else 0))),
         "cova_bn_act_bwd": lambda a: ("hbm", 4.0 * i(a[3]) * i(a[4]) * (2 * (2 + (1 if a[2] else 0)) + 1 + (1 if a[12] else 0))),
         # two passes over (x, dy [, res]) + the scaled split planes of dx (4 B/elt) [+ dres]
-        "cova_bn_act_bwd_planes": lambda a: ("hbm", 4.0 * i(a[3]) * i(a[4]) * (2 * (2 + (1 if a[2] else 0)) + 1 + (1 if a[17] else 0))),
+        "cova_bn_act_bwd_planes": lambda a: ("hbm", 4.0 * i(a[3]) * i(a[4]) * (2 * (2 + (0.0625 if a[20] else (1 if a[2] else 0))) + 1 + (1 if a[17] else 0))),
         "cova_maxpool3x3s2_fwd": lambda a: ("hbm", 4.0 * i(a[1]) * i(a[2]) * i(a[3]) * i(a[4]) * (1 + 0.25 * (1.25 + (1 if a[7] else 0)))),
         "cova_maxpool3x3s2_bwd": lambda a: ("hbm", 4.0 * i(a[2]) * i(a[3]) * i(a[4]) * i(a[5]) * (1 + 0.25 * 1.25)),
         # typed (bf16 training mode) passes: element sizes from the dtype codes (0 = fp32, 1 = bf16)

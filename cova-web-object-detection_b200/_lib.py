@@ -106,7 +106,7 @@ SIGNATURES = {
     "cova_build_batch": (_I, [_P, _I, _I, _I, _P, _P, _P, _P]),
     "cova_bn_train_stats": (_I, [_P, _L, _I, _P, _P]),
     "cova_bn_train_finalize": (_I, [_P, _L, _I, _F, _F, _P, _P, _P, _P, _P]),
-    "cova_bn_act_fwd": (_I, [_P, _L, _I, _P, _P, _P, _P, _P, _I, _P, _P, _P, _I, _P]),
+    "cova_bn_act_fwd": (_I, [_P, _L, _I, _P, _P, _P, _P, _P, _I, _P, _P, _P, _I, _P, _P]),
     "cova_split_planes": (_I, [_P, _L, _P, _P, _I, _P]),
     "cova_split_planes_scaled": (_I, [_P, _L, _P, _P, _I, _I, _P, _P, _P]),
     "cova_conv3x3_wgrad": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P]),
@@ -114,7 +114,7 @@ SIGNATURES = {
     "cova_stem_wgrad": (_I, [_P, _I, _I, _I, _I, _P, _P, _I, _P, _P, _P, _P]),
     "cova_conv1x1_wgrad": (_I, [_P, _P, _P, _P, _L, _I, _I, _I, _P, _P, _P, _P]),
     "cova_bn_act_bwd": (_I, [_P, _P, _P, _L, _I, _P, _P, _P, _P, _I, _P, _P, _P, _P, _P, _P]),
-    "cova_bn_act_bwd_planes": (_I, [_P, _P, _P, _L, _I, _P, _P, _P, _P, _I, _P, _P, _P, _P, _I, _I, _P, _P, _P, _P, _P]),
+    "cova_bn_act_bwd_planes": (_I, [_P, _P, _P, _L, _I, _P, _P, _P, _P, _I, _P, _P, _P, _P, _I, _I, _P, _P, _P, _P, _P, _P]),
     "cova_bn_train_stats_t": (_I, [_P, _I, _L, _I, _P, _P]),
     "cova_bn_act_fwd_t": (_I, [_P, _I, _L, _I, _P, _P, _P, _P, _P, _I, _P, _I, _P, _P]),
     "cova_bn_act_bwd_t": (_I, [_P, _I, _P, _P, _I, _L, _I, _P, _P, _P, _P, _I, _P, _P, _P, _P, _P, _P, _P]),

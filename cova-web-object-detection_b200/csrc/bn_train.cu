@@ -743,8 +743,9 @@ extern "C" int cova_bn_train_finalize(const double* ws, int64_t M, int C, float 
 
 extern "C" int cova_bn_act_fwd(const float* x, int64_t M, int C, const float* mean, const float* invstd,
                                const float* gamma, const float* beta, const float* res, int relu, float* y,
-                               void* y_hi, void* y_lo, int planes_dtype, void* stream) {
+                               void* y_hi, void* y_lo, int planes_dtype, unsigned char* relu_mask, void* stream) {
   COVA_REQUIRE(planes_dtype == COVA_BF16X2 || planes_dtype == COVA_F16X2, "cova_bn_act_fwd: planes are split-bf16 or split-fp16");
+  COVA_REQUIRE(!relu_mask || relu, "cova_bn_act_fwd: the ReLU bit mask comes with relu");
   COVA_REQUIRE(x && (y || y_hi) && mean && invstd && gamma && beta && M > 0, "cova_bn_act_fwd: bad arguments");
   COVA_REQUIRE(bn_c_ok(C), "cova_bn_act_fwd: C=%d must be a power of two in [4, 1024]", C);
   COVA_REQUIRE((((uintptr_t)x | (uintptr_t)y | (uintptr_t)res | (uintptr_t)y_hi | (uintptr_t)y_lo) & 15) == 0,
@@ -754,7 +755,7 @@ extern "C" int cova_bn_act_fwd(const float* x, int64_t M, int C, const float* me
   bn_act_fwd_kernel<float, float><<<ew_grid(n4, BN_THREADS), BN_THREADS, 2 * C * sizeof(float), (cudaStream_t)stream>>>(x, n4, C, mean, invstd, gamma, beta,
                                                                                      res, relu, y, (__nv_bfloat16*)y_hi,
                                                                                      (__nv_bfloat16*)y_lo,
-                                                                                     planes_dtype == COVA_F16X2);
+                                                                                     planes_dtype == COVA_F16X2, relu_mask);
   COVA_LAUNCH_OK();
   return COVA_OK;
 }
@@ -784,7 +785,9 @@ extern "C" int cova_bn_act_bwd(const float* dy, const float* x, const float* res
 extern "C" int cova_bn_act_bwd_planes(const float* dy, const float* x, const float* res, int64_t M, int C, const float* mean,
                                       const float* invstd, const float* gamma, const float* beta, int relu, double* ws,
                                       unsigned int* ws_max, void* dx_hi, void* dx_lo, int planes_dtype, int target_log2,
-                                      float* inv_scale_vec, float* dres, float* dgamma, float* dbeta, void* stream) {
+                                      float* inv_scale_vec, float* dres, float* dgamma, float* dbeta, const unsigned char* relu_mask,
+                                      void* stream) {
+  COVA_REQUIRE(!relu_mask || relu, "cova_bn_act_bwd_planes: the ReLU bit mask comes with relu");
   COVA_REQUIRE(dy && x && dx_hi && dx_lo && ws && ws_max && inv_scale_vec && mean && invstd && gamma && beta && M > 0,
                "cova_bn_act_bwd_planes: bad arguments");
   COVA_REQUIRE(bn_c_ok(C), "cova_bn_act_bwd_planes: C=%d must be a power of two in [4, 1024]", C);
@@ -799,9 +802,19 @@ extern "C" int cova_bn_act_bwd_planes(const float* dy, const float* x, const flo
   const size_t smem = (size_t)2 * rows * C * sizeof(float);
   int64_t grid = (M + rows - 1) / rows;
   if (grid > (int64_t)sm_count() * 8) grid = (int64_t)sm_count() * 8;
+  const int64_t n4 = M * (C / 4);
+  if (relu_mask) {   // the forward's ReLU decisions (4 bits of a byte per 4 channels): the residual map is not read
+    bn_reduce_kernel<2, float, float, true><<<(int)grid, BN_THREADS, smem, st>>>(x, dy, res, M, C, mean, invstd, gamma, beta, relu, ws,
+                                                                               ws_max, relu_mask);
+    COVA_LAUNCH_OK();
+    bn_act_bwd_kernel<true, float, float, true><<<ew_grid(n4, BN_THREADS), BN_THREADS, 6 * C * sizeof(float), st>>>(
+        dy, x, res, n4, M, C, mean, invstd, gamma, beta, relu, ws, nullptr, dres, dgamma, dbeta, ws_max, (__nv_bfloat16*)dx_hi,
+        (__nv_bfloat16*)dx_lo, planes_dtype == COVA_F16X2, target_log2, inv_scale_vec, relu_mask);
+    COVA_LAUNCH_OK();
+    return COVA_OK;
+  }
   bn_reduce_kernel<2, float, float><<<(int)grid, BN_THREADS, smem, st>>>(x, dy, res, M, C, mean, invstd, gamma, beta, relu, ws, ws_max);
   COVA_LAUNCH_OK();
-  const int64_t n4 = M * (C / 4);
   bn_act_bwd_kernel<true, float, float><<<ew_grid(n4, BN_THREADS), BN_THREADS, 6 * C * sizeof(float), st>>>(
       dy, x, res, n4, M, C, mean, invstd, gamma, beta, relu, ws, nullptr, dres, dgamma, dbeta, ws_max, (__nv_bfloat16*)dx_hi,
       (__nv_bfloat16*)dx_lo, planes_dtype == COVA_F16X2, target_log2, inv_scale_vec);

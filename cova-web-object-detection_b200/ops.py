@@ -570,7 +570,7 @@ def stem_wgrad(images, dy_planes, inv_scale=None):
 
 
 def bn_train_fwd(x, gamma, beta, running_mean, running_var, momentum, eps, res=None, relu=True, want_planes=False,
-                 planes_dtype=BF16X2, want_y=True, stats_ws=None):
+                 planes_dtype=BF16X2, want_y=True, stats_ws=None, relu_mask=None):
     """BatchNorm2d with batch statistics (+ residual) (+ ReLU) on an NHWC fp32 map x [..., C]; updates the running
     statistics in place (pass None to skip).  Returns (y, mean [C], invstd [C], split-bf16 Planes of y or None)."""
     _nhwc(x, "x")
@@ -590,7 +590,7 @@ def bn_train_fwd(x, gamma, beta, running_mean, running_var, momentum, eps, res=N
         param_generation += 1
     _call("cova_bn_act_fwd", x.data_ptr(), M, C, mean.data_ptr(), inv.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
           _ptr(None if res is None else _nhwc(res, "res")), int(relu), _ptr(y),
-          pl.p0.data_ptr() if pl else 0, pl.p1.data_ptr() if pl else 0, planes_dtype, _stream())
+          pl.p0.data_ptr() if pl else 0, pl.p1.data_ptr() if pl else 0, planes_dtype, _ptr(relu_mask), _stream())
     return y, mean, inv, pl
 
 
@@ -611,7 +611,7 @@ def bn_train_bwd(dy, x, mean, invstd, gamma, beta, res=None, relu=True, want_dre
 
 
 def bn_train_bwd_planes(dy, x, mean, invstd, gamma, beta, res=None, relu=True, want_dres=False, planes_dtype=F16X2,
-                        target_log2=10):
+                        target_log2=10, relu_mask=None):
     """Backward of `bn_train_fwd` with dx emitted as scaled split planes for the tensor-core dgrad / wgrad kernels:
     returns (Planes of dx * s, inv_scale_vec [256] = 1/s, dres or None, dgamma [C], dbeta [C])."""
     _nhwc(dy, "dy"); _nhwc(x, "x")
@@ -626,7 +626,7 @@ def bn_train_bwd_planes(dy, x, mean, invstd, gamma, beta, res=None, relu=True, w
     dg, db = torch.empty(C, dtype=torch.float32, device=dev), torch.empty(C, dtype=torch.float32, device=dev)
     _call("cova_bn_act_bwd_planes", dy.data_ptr(), x.data_ptr(), _ptr(res), M, C, mean.data_ptr(), invstd.data_ptr(),
           gamma.data_ptr(), beta.data_ptr(), int(relu), ws.data_ptr(), wmax.data_ptr(), pl.p0.data_ptr(), pl.p1.data_ptr(),
-          planes_dtype, int(target_log2), inv.data_ptr(), _ptr(dres), dg.data_ptr(), db.data_ptr(), _stream())
+          planes_dtype, int(target_log2), inv.data_ptr(), _ptr(dres), dg.data_ptr(), db.data_ptr(), _ptr(relu_mask), _stream())
     return pl, inv, dres, dg, db
 
 

@@ -375,10 +375,15 @@ def _unit_fwd(kind, xin, conv, bn, res=None, relu=True, want_y=True, want_planes
         u.raw = ops.conv1x1_raw_fwd(xin, ops.pack_linear_weight_f16x2(w.flatten(1)), stats_ws=sw)
     track = bn.track_running_stats and bn.running_mean is not None
     mom = _momentum(bn, track)
-    u.res = res if (relu and res is not None) else None
+    u.res = None
+    u.mask = (torch.empty(u.raw.numel() // 4, dtype=torch.uint8, device=u.raw.device)
+              if (relu and res is not None and _relu_mask()) else None)    # 4 decisions per byte (one per thread of the passes)
+    if u.mask is None and relu and res is not None:
+        u.res = res
     u.y, u.mean, u.inv, u.planes = ops.bn_train_fwd(u.raw, bn.weight.detach(), bn.bias.detach(), bn.running_mean if track else None,
                                                     bn.running_var if track else None, mom, bn.eps, res=res, relu=relu,
-                                                    want_planes=want_planes, planes_dtype=F16X2, want_y=want_y, stats_ws=sw)
+                                                    want_planes=want_planes, planes_dtype=F16X2, want_y=want_y, stats_ws=sw,
+                                                    relu_mask=u.mask)
     if track and bn.num_batches_tracked is not None:
         bn.num_batches_tracked += 1
     return u
@@ -398,7 +403,9 @@ def _unit_bwd(u, dy, need_dx=True, add=None):
     cores.  Returns (dx fp32 or None, dw, dgamma, dbeta, dres or None)."""
     bn = u.bn
     dyp, inv, dres, dg, db = ops.bn_train_bwd_planes(dy, u.raw, u.mean, u.inv, bn.weight.detach(), bn.bias.detach(), res=u.res,
-                                                     relu=u.relu, want_dres=u.has_res, planes_dtype=F16X2)
+                                                     relu=u.relu, want_dres=u.has_res, planes_dtype=F16X2,
+                                                     relu_mask=getattr(u, "mask", None))
+    u.mask = None
     w = u.weight.detach().float()
     dx = None
     if u.kind == "stem":
@@ -423,7 +430,7 @@ def _unit_bwd(u, dy, need_dx=True, add=None):
 
 
 def _relu_mask():
-    """bf16 mode: residual units hand a ReLU bit mask to their backward (COVA_B200_TRAIN_RELU_MASK=0: re-read the residual)."""
+    """Residual units hand a ReLU bit mask to their backward (COVA_B200_TRAIN_RELU_MASK=0: re-read the residual)."""
     return os.environ.get("COVA_B200_TRAIN_RELU_MASK", "1") != "0"
 
 

@@ -246,7 +246,8 @@ int cova_build_batch(const int* page_offsets, int B, int T, int context_size, co
  * momentum on the unbiased variance.  ws: caller-owned scratch of 2*C doubles.
  *   cova_bn_train_stats    ws = [sum x | sum x^2]
  *   cova_bn_train_finalize mean, invstd = 1/sqrt(var+eps) (fp32 [C]); running_mean / running_var updated in place (or NULL)
- *   cova_bn_act_fwd        y = [relu]((x - mean) * invstd * gamma + beta [+ res])
+ *   cova_bn_act_fwd        y = [relu]((x - mean) * invstd * gamma + beta [+ res]); relu_mask (optional, with relu): [M * C / 4]
+ *                          bytes, bit k of byte i = [y > 0] of element 4 i + k, for cova_bn_act_bwd_planes (which then does not read res)
  *   cova_bn_act_bwd        g = dy * [y > 0] (y recomputed);  dx = gamma*invstd*(g - mean(g) - xhat*mean(g*xhat));
  *                          dres = g (optional);  dgamma = sum g*xhat;  dbeta = sum g                              */
 int cova_bn_train_stats(const float* x, int64_t M, int C, double* ws, void* stream);
@@ -254,7 +255,7 @@ int cova_bn_train_finalize(const double* ws, int64_t M, int C, float eps, float 
                            float* running_mean, float* running_var, void* stream);
 int cova_bn_act_fwd(const float* x, int64_t M, int C, const float* mean, const float* invstd, const float* gamma,
                     const float* beta, const float* res, int relu, float* y, void* y_hi, void* y_lo, int planes_dtype,
-                    void* stream);
+                    unsigned char* relu_mask, void* stream);
 /*   y_hi / y_lo (optional, both or neither): the same result as split planes in `planes_dtype` (COVA_BF16X2 or
  *   COVA_F16X2) - the operand format of the tensor-core convolution that consumes it; y may be NULL when only the
  *   planes are wanted (a map whose single consumer is a tensor-core convolution).                                   */
@@ -268,7 +269,7 @@ int cova_bn_act_bwd(const float* dy, const float* x, const float* res, int64_t M
 int cova_bn_act_bwd_planes(const float* dy, const float* x, const float* res, int64_t M, int C, const float* mean,
                            const float* invstd, const float* gamma, const float* beta, int relu, double* ws,
                            unsigned int* ws_max, void* dx_hi, void* dx_lo, int planes_dtype, int target_log2,
-                           float* inv_scale_vec, float* dres, float* dgamma, float* dbeta, void* stream);
+                           float* inv_scale_vec, float* dres, float* dgamma, float* dbeta, const unsigned char* relu_mask, void* stream);
 
 /* ---- A2 / A9: the stem's `nn.MaxPool2d(3, 2, 1)` on NHWC fp32 maps, forward and backward (the gradient of an output
  * goes to the FIRST maximum of its window in row-major scan order, as torch's max_pool2d_with_indices).

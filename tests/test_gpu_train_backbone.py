@@ -364,6 +364,28 @@ def test_bn_train_bf16_relu_mask_equals_residual_reread(shape, out32):
         assert torch.equal(u, v)
 
 
+@pytest.mark.parametrize("shape", [(3, 16, 20, 64), (1, 7, 9, 256), (2, 5, 3, 4)])
+def test_bn_train_fp32_relu_mask_equals_residual_reread(shape):
+    """fp32-parity mode: the forward's ReLU bit mask (4 decisions per byte) gives the backward with scaled split planes the
+    same dx planes, scale, dres, dgamma, dbeta as re-reading the fp32 residual - bit for bit."""
+    from cova_b200 import ops
+    g = torch.Generator().manual_seed(sum(shape) + 13)
+    C = shape[-1]
+    x = (torch.randn(shape, generator=g) * 2 + 0.5).to(DEV)
+    res = torch.randn(shape, generator=g).to(DEV)
+    gamma = (torch.rand(C, generator=g) + 0.5).to(DEV); beta = (torch.randn(C, generator=g) * 0.2).to(DEV)
+    dy = torch.randn(shape, generator=g).to(DEV)
+    mask = torch.zeros(x.numel() // 4, dtype=torch.uint8, device=DEV)
+    y, mean, inv, _ = ops.bn_train_fwd(x, gamma, beta, None, None, 0.1, 1e-5, res=res, relu=True, relu_mask=mask)
+    bits = ((mask.view(-1, 1).int() >> torch.arange(4, device=DEV).view(1, 4)) & 1).bool().view(shape)
+    assert torch.equal(bits, y > 0)
+    a = ops.bn_train_bwd_planes(dy, x, mean, inv, gamma, beta, res=res, relu=True, want_dres=True)
+    b = ops.bn_train_bwd_planes(dy, x, mean, inv, gamma, beta, res=None, relu=True, want_dres=True, relu_mask=mask)
+    assert torch.equal(a[0].p0, b[0].p0) and torch.equal(a[0].p1, b[0].p1)
+    for u, v in zip(a[1:], b[1:]):
+        assert torch.equal(u, v)
+
+
 def test_maxpool_bf16_bit_exact():
     from cova_b200 import ops
     g = torch.Generator().manual_seed(5)
